@@ -1,0 +1,565 @@
+/*
+ * oracle/bn254_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ * See bn254_oracle.h for scope, citations and the "parity unpinned" note.
+ * Build: make -C oracle   (gcc -O3 -march=x86-64-v3 -shared -fPIC -pthread)
+ */
+#include "bn254_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+typedef struct {
+    uint64_t m[4];   /* modulus                */
+    uint64_t r[4];   /* R   = 2^256 mod m      */
+    uint64_t r2[4];  /* R^2 mod m              */
+    uint64_t inv;    /* -m^-1 mod 2^64         */
+} field_params_t;
+
+/* BN254 base field Fq and scalar field Fr (recomputed in
+ * tests/test_oracle.py from p and r with Python integers). */
+static const field_params_t FIELDS[2] = {
+    { { 0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL },
+      { 0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL },
+      { 0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL },
+      0x87d20782e4866389ULL },
+    { { 0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL },
+      { 0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL },
+      { 0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL },
+      0xc2e1f593efffffffULL },
+};
+
+/* ------------------------------------------------------------------ fields */
+
+static inline int ge4(const uint64_t a[4], const uint64_t b[4]) {
+    for (int i = 3; i >= 0; --i) {
+        if (a[i] != b[i]) return a[i] > b[i];
+    }
+    return 1;
+}
+
+static inline uint64_t sub4(uint64_t out[4], const uint64_t a[4], const uint64_t b[4]) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        u128 t = (u128)a[i] - b[i] - borrow;
+        out[i] = (uint64_t)t;
+        borrow = (uint64_t)(t >> 64) & 1;
+    }
+    return borrow;
+}
+
+static inline uint64_t add4(uint64_t out[4], const uint64_t a[4], const uint64_t b[4]) {
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; ++i) {
+        u128 t = (u128)a[i] + b[i] + carry;
+        out[i] = (uint64_t)t;
+        carry = (uint64_t)(t >> 64);
+    }
+    return carry;
+}
+
+/* Montgomery product a*b*R^-1 mod m, coarsely-integrated operand scanning. */
+static inline __attribute__((always_inline)) void mont_mul(const field_params_t *f, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    uint64_t t[6] = { 0, 0, 0, 0, 0, 0 };
+#pragma GCC unroll 4
+    for (int i = 0; i < 4; ++i) {
+        uint64_t carry = 0;
+#pragma GCC unroll 4
+        for (int j = 0; j < 4; ++j) {
+            u128 cur = (u128)a[j] * b[i] + t[j] + carry;
+            t[j] = (uint64_t)cur;
+            carry = (uint64_t)(cur >> 64);
+        }
+        u128 cur = (u128)t[4] + carry;
+        t[4] = (uint64_t)cur;
+        t[5] = (uint64_t)(cur >> 64);
+
+        uint64_t q = t[0] * f->inv;
+        cur = (u128)q * f->m[0] + t[0];
+        carry = (uint64_t)(cur >> 64);
+#pragma GCC unroll 4
+        for (int j = 1; j < 4; ++j) {
+            cur = (u128)q * f->m[j] + t[j] + carry;
+            t[j - 1] = (uint64_t)cur;
+            carry = (uint64_t)(cur >> 64);
+        }
+        cur = (u128)t[4] + carry;
+        t[3] = (uint64_t)cur;
+        t[4] = t[5] + (uint64_t)(cur >> 64);
+    }
+    if (t[4] || ge4(t, f->m)) {
+        sub4(out, t, f->m);
+    } else {
+        memcpy(out, t, 32);
+    }
+}
+
+static void fe_add(const field_params_t *f, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    uint64_t t[4];
+    uint64_t carry = add4(t, a, b);
+    if (carry || ge4(t, f->m)) sub4(out, t, f->m); else memcpy(out, t, 32);
+}
+
+static void fe_sub(const field_params_t *f, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    uint64_t t[4];
+    if (sub4(t, a, b)) add4(out, t, f->m); else memcpy(out, t, 32);
+}
+
+static int fe_is_zero(const uint64_t a[4]) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
+
+/* a^(m-2) by square-and-multiply; 0 -> 0. */
+static void fe_inv(const field_params_t *f, const uint64_t a[4], uint64_t out[4]) {
+    uint64_t e[4], two[4] = { 2, 0, 0, 0 };
+    sub4(e, f->m, two);
+    uint64_t acc[4], base[4];
+    memcpy(acc, f->r, 32);
+    memcpy(base, a, 32);
+    for (int i = 0; i < 256; ++i) {
+        if ((e[i / 64] >> (i % 64)) & 1) mont_mul(f, acc, base, acc);
+        mont_mul(f, base, base, base);
+    }
+    memcpy(out, acc, 32);
+}
+
+void oracle_fe_mul(int w, const ofe_t *a, const ofe_t *b, ofe_t *o) { mont_mul(&FIELDS[w], a->l, b->l, o->l); }
+void oracle_fe_add(int w, const ofe_t *a, const ofe_t *b, ofe_t *o) { fe_add(&FIELDS[w], a->l, b->l, o->l); }
+void oracle_fe_sub(int w, const ofe_t *a, const ofe_t *b, ofe_t *o) { fe_sub(&FIELDS[w], a->l, b->l, o->l); }
+void oracle_fe_inv(int w, const ofe_t *a, ofe_t *o) { fe_inv(&FIELDS[w], a->l, o->l); }
+
+void oracle_fe_from_canonical(int w, const uint64_t c[4], ofe_t *out) {
+    mont_mul(&FIELDS[w], c, FIELDS[w].r2, out->l);
+}
+
+/* halo2_curves `to_repr` [ext]: one Montgomery reduction, little-endian bytes. */
+void oracle_fe_to_canonical(int w, const ofe_t *a, uint64_t c[4]) {
+    static const uint64_t one[4] = { 1, 0, 0, 0 };
+    mont_mul(&FIELDS[w], a->l, one, c);
+}
+
+/* ------------------------------------------------------------------- curve */
+
+#define FQ (&FIELDS[0])
+#define FR (&FIELDS[1])
+
+static void q_mul(const ofe_t *a, const ofe_t *b, ofe_t *o) { mont_mul(FQ, a->l, b->l, o->l); }
+static void q_sqr(const ofe_t *a, ofe_t *o) { mont_mul(FQ, a->l, a->l, o->l); }
+static void q_add(const ofe_t *a, const ofe_t *b, ofe_t *o) { fe_add(FQ, a->l, b->l, o->l); }
+static void q_sub(const ofe_t *a, const ofe_t *b, ofe_t *o) { fe_sub(FQ, a->l, b->l, o->l); }
+static void q_dbl(const ofe_t *a, ofe_t *o) { fe_add(FQ, a->l, a->l, o->l); }
+
+static int affine_is_identity(const og1_affine_t *p) { return fe_is_zero(p->x.l) && fe_is_zero(p->y.l); }
+static int jac_is_identity(const og1_jac_t *p) { return fe_is_zero(p->z.l); }
+
+static void jac_set_identity(og1_jac_t *p) {
+    memset(p, 0, sizeof(*p));
+    memcpy(p->y.l, FQ->r, 32); /* (0 : 1 : 0) */
+}
+
+void oracle_g1_generator(og1_affine_t *out) {
+    static const uint64_t one[4] = { 1, 0, 0, 0 }, two[4] = { 2, 0, 0, 0 };
+    oracle_fe_from_canonical(0, one, &out->x);
+    oracle_fe_from_canonical(0, two, &out->y);
+}
+
+int oracle_g1_is_on_curve(const og1_affine_t *p) {
+    if (affine_is_identity(p)) return 1;
+    static const uint64_t three[4] = { 3, 0, 0, 0 };
+    ofe_t b, y2, x3;
+    oracle_fe_from_canonical(0, three, &b);
+    q_sqr(&p->y, &y2);
+    q_sqr(&p->x, &x3);
+    q_mul(&x3, &p->x, &x3);
+    q_add(&x3, &b, &x3);
+    return memcmp(&y2, &x3, 32) == 0;
+}
+
+void oracle_g1_from_affine(const og1_affine_t *a, og1_jac_t *out) {
+    if (affine_is_identity(a)) { jac_set_identity(out); return; }
+    out->x = a->x;
+    out->y = a->y;
+    memcpy(out->z.l, FQ->r, 32);
+}
+
+/* dbl-2009-l (a = 0): 2M + 5S. */
+void oracle_g1_double(const og1_jac_t *p, og1_jac_t *out) {
+    if (jac_is_identity(p)) { jac_set_identity(out); return; }
+    ofe_t a, b, c, d, e, f, t, z3;
+    q_sqr(&p->x, &a);
+    q_sqr(&p->y, &b);
+    q_sqr(&b, &c);
+    q_add(&p->x, &b, &d);
+    q_sqr(&d, &d);
+    q_sub(&d, &a, &d);
+    q_sub(&d, &c, &d);
+    q_dbl(&d, &d);
+    q_dbl(&a, &e);
+    q_add(&e, &a, &e);
+    q_sqr(&e, &f);
+    q_mul(&p->y, &p->z, &z3);
+    q_dbl(&z3, &z3);
+    q_dbl(&d, &t);
+    q_sub(&f, &t, &out->x);
+    q_dbl(&c, &c); q_dbl(&c, &c); q_dbl(&c, &c);
+    q_sub(&d, &out->x, &t);
+    q_mul(&e, &t, &t);
+    q_sub(&t, &c, &out->y);
+    out->z = z3;
+}
+
+/* add-2007-bl with the exceptional cases (identity operands, P+P, P+(-P)). */
+void oracle_g1_add(const og1_jac_t *p, const og1_jac_t *q, og1_jac_t *out) {
+    if (jac_is_identity(p)) { *out = *q; return; }
+    if (jac_is_identity(q)) { *out = *p; return; }
+    ofe_t z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t;
+    q_sqr(&p->z, &z1z1);
+    q_sqr(&q->z, &z2z2);
+    q_mul(&p->x, &z2z2, &u1);
+    q_mul(&q->x, &z1z1, &u2);
+    q_mul(&p->y, &q->z, &s1); q_mul(&s1, &z2z2, &s1);
+    q_mul(&q->y, &p->z, &s2); q_mul(&s2, &z1z1, &s2);
+    if (memcmp(&u1, &u2, 32) == 0) {
+        if (memcmp(&s1, &s2, 32) == 0) { oracle_g1_double(p, out); } else { jac_set_identity(out); }
+        return;
+    }
+    q_sub(&u2, &u1, &h);
+    q_dbl(&h, &i); q_sqr(&i, &i);
+    q_mul(&h, &i, &j);
+    q_sub(&s2, &s1, &rr); q_dbl(&rr, &rr);
+    q_mul(&u1, &i, &v);
+    og1_jac_t o;
+    q_sqr(&rr, &o.x); q_sub(&o.x, &j, &o.x); q_dbl(&v, &t); q_sub(&o.x, &t, &o.x);
+    q_sub(&v, &o.x, &t); q_mul(&rr, &t, &t);
+    q_mul(&s1, &j, &s1); q_dbl(&s1, &s1);
+    q_sub(&t, &s1, &o.y);
+    q_add(&p->z, &q->z, &o.z); q_sqr(&o.z, &o.z); q_sub(&o.z, &z1z1, &o.z); q_sub(&o.z, &z2z2, &o.z);
+    q_mul(&o.z, &h, &o.z);
+    *out = o;
+}
+
+/* madd-2007-bl with the exceptional cases. */
+void oracle_g1_add_mixed(const og1_jac_t *p, const og1_affine_t *q, og1_jac_t *out) {
+    if (affine_is_identity(q)) { *out = *p; return; }
+    if (jac_is_identity(p)) { oracle_g1_from_affine(q, out); return; }
+    ofe_t z1z1, u2, s2, h, hh, i, j, rr, v, t;
+    q_sqr(&p->z, &z1z1);
+    q_mul(&q->x, &z1z1, &u2);
+    q_mul(&q->y, &p->z, &s2); q_mul(&s2, &z1z1, &s2);
+    if (memcmp(&p->x, &u2, 32) == 0) {
+        if (memcmp(&p->y, &s2, 32) == 0) { oracle_g1_double(p, out); } else { jac_set_identity(out); }
+        return;
+    }
+    q_sub(&u2, &p->x, &h);
+    q_sqr(&h, &hh);
+    q_dbl(&hh, &i); q_dbl(&i, &i);
+    q_mul(&h, &i, &j);
+    q_sub(&s2, &p->y, &rr); q_dbl(&rr, &rr);
+    q_mul(&p->x, &i, &v);
+    og1_jac_t o;
+    q_sqr(&rr, &o.x); q_sub(&o.x, &j, &o.x); q_dbl(&v, &t); q_sub(&o.x, &t, &o.x);
+    q_sub(&v, &o.x, &t); q_mul(&rr, &t, &t);
+    ofe_t yj; q_mul(&p->y, &j, &yj); q_dbl(&yj, &yj);
+    q_sub(&t, &yj, &o.y);
+    q_add(&p->z, &h, &o.z); q_sqr(&o.z, &o.z); q_sub(&o.z, &z1z1, &o.z); q_sub(&o.z, &hh, &o.z);
+    *out = o;
+}
+
+void oracle_g1_to_affine(const og1_jac_t *p, og1_affine_t *out) {
+    if (jac_is_identity(p)) { memset(out, 0, sizeof(*out)); return; }
+    ofe_t zi, zi2, zi3;
+    fe_inv(FQ, p->z.l, zi.l);
+    q_sqr(&zi, &zi2);
+    q_mul(&zi2, &zi, &zi3);
+    q_mul(&p->x, &zi2, &out->x);
+    q_mul(&p->y, &zi3, &out->y);
+}
+
+void oracle_g1_scalar_mul(const og1_affine_t *base, const uint64_t k[4], og1_jac_t *out) {
+    og1_jac_t acc;
+    jac_set_identity(&acc);
+    for (int i = 255; i >= 0; --i) {
+        oracle_g1_double(&acc, &acc);
+        if ((k[i / 64] >> (i % 64)) & 1) oracle_g1_add_mixed(&acc, base, &acc);
+    }
+    *out = acc;
+}
+
+int oracle_g1_transcript_bytes(const og1_affine_t *p, uint8_t out[64]) {
+    if (affine_is_identity(p)) return -1;
+    const ofe_t *coord[2] = { &p->x, &p->y };
+    for (int c = 0; c < 2; ++c) {
+        uint64_t canon[4];
+        oracle_fe_to_canonical(0, coord[c], canon);
+        for (int i = 0; i < 32; ++i) {
+            /* to_repr() is little-endian; the transcript reverses it (transcript.rs:221-222). */
+            out[32 * c + i] = (uint8_t)(canon[(31 - i) / 8] >> (8 * ((31 - i) % 8)));
+        }
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- hot path */
+
+/* msm.rs:8-14 */
+size_t oracle_window_size(size_t num_scalars) {
+    if (num_scalars < 32) return 3;
+    return (size_t)floor(log((double)num_scalars));
+}
+
+/* msm.rs:33-48 */
+size_t oracle_windowed_scalar(size_t window_size, size_t window_mask, size_t idx, const uint8_t repr[32]) {
+    size_t skip_bits = idx * window_size;
+    size_t skip_bytes = skip_bits / 8;
+    uint8_t value[8] = { 0 };
+    for (size_t k = 0; k < 8 && skip_bytes + k < 32; ++k) value[k] = repr[skip_bytes + k];
+    uint64_t v = 0;
+    for (int k = 7; k >= 0; --k) v = (v << 8) | value[k];
+    return (size_t)((v >> (skip_bits - skip_bytes * 8)) & window_mask);
+}
+
+/* msm.rs:122-151 — enum CurveAcc { Empty, Affine(C), Projective(C::Curve) } */
+typedef struct {
+    int tag; /* 0 Empty, 1 Affine, 2 Projective */
+    og1_affine_t affine;
+    og1_jac_t projective;
+} curve_acc_t;
+
+/* msm.rs:130-139 */
+static void curve_acc_add_assign(curve_acc_t *acc, const og1_affine_t *rhs) {
+    switch (acc->tag) {
+    case 0:
+        acc->tag = 1;
+        acc->affine = *rhs;
+        break;
+    case 1: {
+        og1_jac_t lhs;
+        oracle_g1_from_affine(&acc->affine, &lhs);       /* affine + affine -> projective */
+        oracle_g1_add_mixed(&lhs, rhs, &acc->projective);
+        acc->tag = 2;
+        break;
+    }
+    default:
+        oracle_g1_add_mixed(&acc->projective, rhs, &acc->projective);
+    }
+}
+
+/* msm.rs:141-150 */
+static void curve_acc_add(const curve_acc_t *acc, og1_jac_t *rhs) {
+    switch (acc->tag) {
+    case 0: break;
+    case 1: oracle_g1_add_mixed(rhs, &acc->affine, rhs); break;
+    default: oracle_g1_add(&acc->projective, rhs, rhs);
+    }
+}
+
+/* msm.rs:117-181 */
+void oracle_variable_base_msm_serial(const ofe_t *scalars, const og1_affine_t *bases, size_t n,
+                                     og1_jac_t *result) {
+    if (n == 0) return;
+    uint8_t *reprs = (uint8_t *)malloc(32 * n);                          /* :153 */
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t canon[4];
+        oracle_fe_to_canonical(1, &scalars[i], canon);
+        memcpy(reprs + 32 * i, canon, 32);                               /* x86: little-endian */
+    }
+    const size_t num_bits = 8 * 32;                                      /* :154-155 */
+    const size_t window_size = oracle_window_size(n);                    /* :157 */
+    const size_t num_buckets = ((size_t)1 << window_size) - 1;           /* :158 */
+    const size_t num_windows = (num_bits + window_size - 1) / window_size; /* :160 */
+    curve_acc_t *buckets = (curve_acc_t *)malloc(sizeof(curve_acc_t) * num_buckets);
+
+    for (size_t idx = num_windows; idx-- > 0;) {                         /* :161 */
+        for (size_t k = 0; k < window_size; ++k) oracle_g1_double(result, result); /* :162-164 */
+        for (size_t b = 0; b < num_buckets; ++b) buckets[b].tag = 0;     /* :166 */
+        for (size_t i = 0; i < n; ++i) {                                 /* :168-173 */
+            size_t s = oracle_windowed_scalar(window_size, num_buckets, idx, reprs + 32 * i);
+            if (s != 0) curve_acc_add_assign(&buckets[s - 1], &bases[i]);
+        }
+        og1_jac_t running_sum;                                           /* :175-179 */
+        jac_set_identity(&running_sum);
+        for (size_t b = num_buckets; b-- > 0;) {
+            curve_acc_add(&buckets[b], &running_sum);
+            oracle_g1_add(result, &running_sum, result);
+        }
+    }
+    free(buckets);
+    free(reprs);
+}
+
+typedef struct {
+    const ofe_t *scalars;
+    const og1_affine_t *bases;
+    size_t n;
+    og1_jac_t result;
+} msm_task_t;
+
+static void *msm_task_run(void *arg) {
+    msm_task_t *t = (msm_task_t *)arg;
+    oracle_variable_base_msm_serial(t->scalars, t->bases, t->n, &t->result);
+    return NULL;
+}
+
+/* msm.rs:84-115, with parallel.rs:9-25 restated as one pthread per chunk. */
+void oracle_variable_base_msm(const ofe_t *scalars, const og1_affine_t *bases, size_t n,
+                              int num_threads, og1_jac_t *out) {
+    jac_set_identity(out);
+    if (n == 0) return;
+    if (num_threads < 1) num_threads = 1;
+    if (n <= (size_t)num_threads) {                                      /* :95-99 */
+        oracle_variable_base_msm_serial(scalars, bases, n, out);
+        return;
+    }
+    size_t chunk_size = (n + num_threads - 1) / num_threads;             /* :101 */
+    size_t num_chunks = (n + chunk_size - 1) / chunk_size;
+    msm_task_t *tasks = (msm_task_t *)calloc(num_chunks, sizeof(msm_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_chunks, sizeof(pthread_t));
+    for (size_t c = 0; c < num_chunks; ++c) {                            /* :103-111 */
+        size_t start = c * chunk_size;
+        tasks[c].scalars = scalars + start;
+        tasks[c].bases = bases + start;
+        tasks[c].n = (start + chunk_size <= n) ? chunk_size : n - start;
+        jac_set_identity(&tasks[c].result);
+        pthread_create(&threads[c], NULL, msm_task_run, &tasks[c]);
+    }
+    for (size_t c = 0; c < num_chunks; ++c) {
+        pthread_join(threads[c], NULL);
+        oracle_g1_add(out, &tasks[c].result, out);                       /* :112-114 */
+    }
+    free(threads);
+    free(tasks);
+}
+
+void oracle_msm_naive(const ofe_t *scalars, const og1_affine_t *bases, size_t n, og1_jac_t *out) {
+    jac_set_identity(out);
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t k[4];
+        og1_jac_t t;
+        oracle_fe_to_canonical(1, &scalars[i], k);
+        oracle_g1_scalar_mul(&bases[i], k, &t);
+        oracle_g1_add(out, &t, out);
+    }
+}
+
+/* ------------------------------------------------- known-discrete-log inputs */
+
+/* Normalise jac[0..n) to affine with one inversion (Montgomery's trick). */
+static void batch_to_affine(const og1_jac_t *jac, size_t n, og1_affine_t *out) {
+    if (n == 0) return;
+    ofe_t *prefix = (ofe_t *)malloc(sizeof(ofe_t) * n);
+    ofe_t acc;
+    memcpy(acc.l, FQ->r, 32);
+    for (size_t i = 0; i < n; ++i) {
+        prefix[i] = acc;
+        if (!jac_is_identity(&jac[i])) q_mul(&acc, &jac[i].z, &acc);
+    }
+    ofe_t inv;
+    fe_inv(FQ, acc.l, inv.l);
+    for (size_t i = n; i-- > 0;) {
+        if (jac_is_identity(&jac[i])) { memset(&out[i], 0, sizeof(out[i])); continue; }
+        ofe_t zi, zi2, zi3;
+        q_mul(&inv, &prefix[i], &zi);
+        q_mul(&inv, &jac[i].z, &inv);
+        q_sqr(&zi, &zi2);
+        q_mul(&zi2, &zi, &zi3);
+        q_mul(&jac[i].x, &zi2, &out[i].x);
+        q_mul(&jac[i].y, &zi3, &out[i].y);
+    }
+    free(prefix);
+}
+
+typedef struct {
+    uint64_t a[4], d[4];
+    size_t start, count;
+    og1_affine_t step; /* d*G */
+    og1_affine_t *out;
+} dlog_task_t;
+
+static void *dlog_task_run(void *arg) {
+    dlog_task_t *t = (dlog_task_t *)arg;
+    if (t->count == 0) return NULL;
+    /* k0 = a + start*d (mod r) */
+    ofe_t fa, fd, fs, k0m;
+    uint64_t s[4] = { (uint64_t)t->start, 0, 0, 0 }, k0[4];
+    oracle_fe_from_canonical(1, t->a, &fa);
+    oracle_fe_from_canonical(1, t->d, &fd);
+    oracle_fe_from_canonical(1, s, &fs);
+    mont_mul(FR, fs.l, fd.l, k0m.l);
+    fe_add(FR, k0m.l, fa.l, k0m.l);
+    oracle_fe_to_canonical(1, &k0m, k0);
+    og1_affine_t g;
+    oracle_g1_generator(&g);
+    const size_t BATCH = 1024;
+    og1_jac_t *buf = (og1_jac_t *)malloc(sizeof(og1_jac_t) * BATCH);
+    og1_jac_t cur;
+    oracle_g1_scalar_mul(&g, k0, &cur);
+    size_t done = 0;
+    while (done < t->count) {
+        size_t m = t->count - done < BATCH ? t->count - done : BATCH;
+        for (size_t i = 0; i < m; ++i) {
+            buf[i] = cur;
+            oracle_g1_add_mixed(&cur, &t->step, &cur);
+        }
+        batch_to_affine(buf, m, t->out + done);
+        done += m;
+    }
+    free(buf);
+    return NULL;
+}
+
+void oracle_known_dlog_bases(const uint64_t a[4], const uint64_t d[4], size_t n, int num_threads,
+                             og1_affine_t *out) {
+    if (n == 0) return;
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > n) num_threads = (int)n;
+    og1_affine_t g, step;
+    og1_jac_t dj;
+    oracle_g1_generator(&g);
+    oracle_g1_scalar_mul(&g, d, &dj);
+    oracle_g1_to_affine(&dj, &step);
+    dlog_task_t *tasks = (dlog_task_t *)calloc(num_threads, sizeof(dlog_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+    size_t chunk = (n + num_threads - 1) / num_threads;
+    for (int t = 0; t < num_threads; ++t) {
+        size_t start = (size_t)t * chunk;
+        memcpy(tasks[t].a, a, 32);
+        memcpy(tasks[t].d, d, 32);
+        tasks[t].start = start;
+        tasks[t].count = start >= n ? 0 : (start + chunk <= n ? chunk : n - start);
+        tasks[t].step = step;
+        tasks[t].out = out + start;
+        pthread_create(&threads[t], NULL, dlog_task_run, &tasks[t]);
+    }
+    for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+    free(threads);
+    free(tasks);
+}
+
+void oracle_known_dlog_answer(const uint64_t a[4], const uint64_t d[4], const ofe_t *scalars, size_t n,
+                              og1_affine_t *out) {
+    ofe_t fa, fd, sum, wsum, idx, one, t;
+    static const uint64_t c1[4] = { 1, 0, 0, 0 };
+    oracle_fe_from_canonical(1, a, &fa);
+    oracle_fe_from_canonical(1, d, &fd);
+    oracle_fe_from_canonical(1, c1, &one);
+    memset(&sum, 0, sizeof(sum));
+    memset(&wsum, 0, sizeof(wsum));
+    memset(&idx, 0, sizeof(idx));
+    for (size_t i = 0; i < n; ++i) {
+        fe_add(FR, sum.l, scalars[i].l, sum.l);
+        mont_mul(FR, idx.l, scalars[i].l, t.l);
+        fe_add(FR, wsum.l, t.l, wsum.l);
+        fe_add(FR, idx.l, one.l, idx.l);
+    }
+    mont_mul(FR, fa.l, sum.l, sum.l);
+    mont_mul(FR, fd.l, wsum.l, wsum.l);
+    fe_add(FR, sum.l, wsum.l, sum.l);
+    uint64_t k[4];
+    oracle_fe_to_canonical(1, &sum, k);
+    og1_affine_t g;
+    og1_jac_t rj;
+    oracle_g1_generator(&g);
+    oracle_g1_scalar_mul(&g, k, &rj);
+    oracle_g1_to_affine(&rj, out);
+}

@@ -1,0 +1,93 @@
+/*
+ * oracle/bn254_oracle.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, gcc, no dependencies) of the reference's BN254 G1
+ * variable-base MSM path.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load this library; the
+ * product (plonkish_b200/, include/) never links, imports or calls it.
+ *
+ * Parity status: "parity unpinned" against reference *binaries* — the
+ * reference is Rust (no cargo/rustc here) and holds no golden vectors for
+ * msm.rs.  The oracle is pinned instead by (1) an independent
+ * Python big-int implementation (oracle/bigint_ref.py), (2) public BN254 /
+ * EIP-196 known answers, (3) known-discrete-log identities; see
+ * tests/test_oracle.py and tests/golden/.
+ *
+ * What is restated, with the reference lines it follows
+ * (paths relative to /root/reference/plonkish_backend/src):
+ *   util/arithmetic/msm.rs:8-14     window_size
+ *   util/arithmetic/msm.rs:33-48    windowed_scalar
+ *   util/arithmetic/msm.rs:84-115   variable_base_msm (T-way point chunking)
+ *   util/arithmetic/msm.rs:117-181  variable_base_msm_serial + CurveAcc
+ *   util/parallel.rs:9-25           parallelize_iter (one task per chunk)
+ *   util/transcript.rs:216-229      write_commitment byte encoding
+ * The field / curve arithmetic the reference gets from the un-vendored
+ * third-party crate halo2_curves 0.3.3 (plonkish_backend/Cargo.toml:7, patched
+ * at Cargo.toml:9-11, no lockfile) is restated from the published BN254
+ * (alt_bn128) definition: y^2 = x^3 + 3 over Fq, G = (1, 2), 4x64-bit
+ * little-endian Montgomery limbs with R = 2^256, affine identity = (0, 0),
+ * Jacobian identity z = 0.
+ */
+#ifndef PLONKISH_ORACLE_BN254_H
+#define PLONKISH_ORACLE_BN254_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } ofe_t;            /* Fq or Fr element, Montgomery form */
+typedef struct { ofe_t x, y; } og1_affine_t;        /* 64 B; (0,0) = identity            */
+typedef struct { ofe_t x, y, z; } og1_jac_t;        /* 96 B Jacobian; z = 0 = identity   */
+
+/* ---- field helpers (which = 0 -> Fq, 1 -> Fr) ---- */
+void oracle_fe_mul(int which, const ofe_t *a, const ofe_t *b, ofe_t *out);
+void oracle_fe_add(int which, const ofe_t *a, const ofe_t *b, ofe_t *out);
+void oracle_fe_sub(int which, const ofe_t *a, const ofe_t *b, ofe_t *out);
+void oracle_fe_inv(int which, const ofe_t *a, ofe_t *out);          /* 0 -> 0 */
+void oracle_fe_from_canonical(int which, const uint64_t c[4], ofe_t *out);
+void oracle_fe_to_canonical(int which, const ofe_t *a, uint64_t c[4]); /* == to_repr (LE limbs) */
+
+/* ---- curve helpers ---- */
+void oracle_g1_generator(og1_affine_t *out);
+int  oracle_g1_is_on_curve(const og1_affine_t *p);                 /* identity counts as on-curve */
+void oracle_g1_add(const og1_jac_t *a, const og1_jac_t *b, og1_jac_t *out);
+void oracle_g1_add_mixed(const og1_jac_t *a, const og1_affine_t *b, og1_jac_t *out);
+void oracle_g1_double(const og1_jac_t *a, og1_jac_t *out);
+void oracle_g1_to_affine(const og1_jac_t *a, og1_affine_t *out);
+void oracle_g1_from_affine(const og1_affine_t *a, og1_jac_t *out);
+/* k = canonical (non-Montgomery) 256-bit little-endian limbs */
+void oracle_g1_scalar_mul(const og1_affine_t *base, const uint64_t k[4], og1_jac_t *out);
+
+/* transcript.rs:216-229 — x||y, each 32-byte big-endian canonical. Returns 0 on
+ * success, -1 for the identity (the reference's coordinates().unwrap() panics). */
+int oracle_g1_transcript_bytes(const og1_affine_t *p, uint8_t out[64]);
+
+/* ---- the hot path ---- */
+size_t oracle_window_size(size_t num_scalars);                          /* msm.rs:8-14  */
+size_t oracle_windowed_scalar(size_t window_size, size_t window_mask,
+                              size_t idx, const uint8_t repr[32]);      /* msm.rs:33-48 */
+/* msm.rs:117-181; accumulates into *result exactly as the reference does. */
+void oracle_variable_base_msm_serial(const ofe_t *scalars, const og1_affine_t *bases,
+                                     size_t n, og1_jac_t *result);
+/* msm.rs:84-115 with num_threads() == T.  n == 0 returns the identity (the
+ * reference panics at msm.rs:154; documented deviation). */
+void oracle_variable_base_msm(const ofe_t *scalars, const og1_affine_t *bases, size_t n,
+                              int num_threads, og1_jac_t *out);
+/* Independent check: plain double-and-add per point, summed. Small n only. */
+void oracle_msm_naive(const ofe_t *scalars, const og1_affine_t *bases, size_t n, og1_jac_t *out);
+
+/* ---- synthetic inputs with a known answer ----
+ * bases[i] = (a + i*d) * G  (a, d canonical 256-bit LE limbs, small in practice),
+ * so sum_i s_i * bases[i] = ((a * sum s_i + d * sum i*s_i) mod r) * G.           */
+void oracle_known_dlog_bases(const uint64_t a[4], const uint64_t d[4], size_t n,
+                             int num_threads, og1_affine_t *out);
+void oracle_known_dlog_answer(const uint64_t a[4], const uint64_t d[4],
+                              const ofe_t *scalars, size_t n, og1_affine_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

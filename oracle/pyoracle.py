@@ -1,0 +1,195 @@
+"""oracle/pyoracle.py — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes loader for oracle/liboracle_bn254.so (the C restatement of
+/root/reference/plonkish_backend/src/util/arithmetic/msm.rs:84-181) with numpy
+array plumbing.  Import only from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.
+
+Array conventions (same bytes that cross the product's C ABI):
+  scalars : np.uint64 [n, 4]  — Fr, Montgomery form, little-endian limbs
+  bases   : np.uint64 [n, 8]  — G1Affine x||y, Montgomery Fq limbs, (0,0) = identity
+  point   : np.uint64 [8]     — affine result
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle_bn254.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "bn254_oracle.c")
+    hdr = os.path.join(_HERE, "bn254_oracle.h")
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in (src, hdr)
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        _lib.oracle_fe_mul.argtypes = [ci, vp, vp, vp]
+        _lib.oracle_fe_add.argtypes = [ci, vp, vp, vp]
+        _lib.oracle_fe_sub.argtypes = [ci, vp, vp, vp]
+        _lib.oracle_fe_inv.argtypes = [ci, vp, vp]
+        _lib.oracle_fe_from_canonical.argtypes = [ci, vp, vp]
+        _lib.oracle_fe_to_canonical.argtypes = [ci, vp, vp]
+        _lib.oracle_g1_generator.argtypes = [vp]
+        _lib.oracle_g1_is_on_curve.argtypes = [vp]
+        _lib.oracle_g1_is_on_curve.restype = ci
+        _lib.oracle_g1_to_affine.argtypes = [vp, vp]
+        _lib.oracle_g1_scalar_mul.argtypes = [vp, vp, vp]
+        _lib.oracle_g1_transcript_bytes.argtypes = [vp, vp]
+        _lib.oracle_g1_transcript_bytes.restype = ci
+        _lib.oracle_window_size.argtypes = [sz]
+        _lib.oracle_window_size.restype = sz
+        _lib.oracle_windowed_scalar.argtypes = [sz, sz, sz, vp]
+        _lib.oracle_windowed_scalar.restype = sz
+        _lib.oracle_variable_base_msm.argtypes = [vp, vp, sz, ci, vp]
+        _lib.oracle_msm_naive.argtypes = [vp, vp, sz, vp]
+        _lib.oracle_known_dlog_bases.argtypes = [vp, vp, sz, ci, vp]
+        _lib.oracle_known_dlog_answer.argtypes = [vp, vp, vp, sz, vp]
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def int_to_limbs(v: int) -> np.ndarray:
+    return np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint64).copy()
+
+
+def limbs_to_int(a) -> int:
+    return int.from_bytes(_u64(a).tobytes(), "little")
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def fe_op(op: str, which: int, a, b=None) -> np.ndarray:
+    a = _u64(a)
+    out = np.zeros(4, dtype=np.uint64)
+    fn = getattr(lib(), f"oracle_fe_{op}")
+    if b is None:
+        fn(which, _ptr(a), _ptr(out))
+    else:
+        b = _u64(b)
+        fn(which, _ptr(a), _ptr(b), _ptr(out))
+    return out
+
+
+def to_canonical(which: int, a) -> np.ndarray:
+    a = _u64(a).reshape(-1, 4)
+    out = np.zeros_like(a)
+    for i in range(a.shape[0]):
+        lib().oracle_fe_to_canonical(which, _ptr(a[i]), _ptr(out[i]))
+    return out
+
+
+def from_canonical(which: int, c) -> np.ndarray:
+    c = _u64(c).reshape(-1, 4)
+    out = np.zeros_like(c)
+    for i in range(c.shape[0]):
+        lib().oracle_fe_from_canonical(which, _ptr(c[i]), _ptr(out[i]))
+    return out
+
+
+def generator() -> np.ndarray:
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_g1_generator(_ptr(out))
+    return out
+
+
+def is_on_curve(pt) -> bool:
+    pt = _u64(pt)
+    return bool(lib().oracle_g1_is_on_curve(_ptr(pt)))
+
+
+def scalar_mul(base, k_canonical: int) -> np.ndarray:
+    base = _u64(base)
+    k = int_to_limbs(k_canonical)
+    jac = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_g1_scalar_mul(_ptr(base), _ptr(k), _ptr(jac))
+    lib().oracle_g1_to_affine(_ptr(jac), _ptr(out))
+    return out
+
+
+def transcript_bytes(pt) -> bytes:
+    pt = _u64(pt)
+    out = np.zeros(64, dtype=np.uint8)
+    if lib().oracle_g1_transcript_bytes(_ptr(pt), _ptr(out)) != 0:
+        raise ValueError("identity has no coordinates")
+    return out.tobytes()
+
+
+def variable_base_msm(scalars, bases, num_threads: int | None = None) -> np.ndarray:
+    """msm.rs:84-115 followed by the callers' to_affine(); returns np.uint64[8]."""
+    scalars = _u64(scalars).reshape(-1, 4)
+    bases = _u64(bases).reshape(-1, 8)
+    assert scalars.shape[0] == bases.shape[0]  # msm.rs:90
+    if num_threads is None:
+        num_threads = host_threads()
+    jac = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_variable_base_msm(_ptr(scalars), _ptr(bases), scalars.shape[0], int(num_threads), _ptr(jac))
+    lib().oracle_g1_to_affine(_ptr(jac), _ptr(out))
+    return out
+
+
+def msm_naive(scalars, bases) -> np.ndarray:
+    scalars = _u64(scalars).reshape(-1, 4)
+    bases = _u64(bases).reshape(-1, 8)
+    jac = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().oracle_msm_naive(_ptr(scalars), _ptr(bases), scalars.shape[0], _ptr(jac))
+    lib().oracle_g1_to_affine(_ptr(jac), _ptr(out))
+    return out
+
+
+def known_dlog_bases(a: int, d: int, n: int, num_threads: int | None = None) -> np.ndarray:
+    if num_threads is None:
+        num_threads = host_threads()
+    out = np.zeros((n, 8), dtype=np.uint64)
+    la, ld = int_to_limbs(a), int_to_limbs(d)
+    lib().oracle_known_dlog_bases(_ptr(la), _ptr(ld), n, int(num_threads), _ptr(out))
+    return out
+
+
+def known_dlog_answer(a: int, d: int, scalars) -> np.ndarray:
+    scalars = _u64(scalars).reshape(-1, 4)
+    out = np.zeros(8, dtype=np.uint64)
+    la, ld = int_to_limbs(a), int_to_limbs(d)
+    lib().oracle_known_dlog_answer(_ptr(la), _ptr(ld), _ptr(scalars), scalars.shape[0], _ptr(out))
+    return out
+
+
+def random_scalars(n: int, seed: int) -> np.ndarray:
+    """Uniform-digit Fr elements in Montgomery form: three uniform u64 limbs and a
+    top limb below r's top limb, so every value is a valid representation < r."""
+    rng = np.random.default_rng(seed)
+    out = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] = rng.integers(0, 0x30644E72E131A029, size=n, dtype=np.uint64)
+    return out

@@ -1,0 +1,336 @@
+// BN254 field arithmetic for sm_100a: 254-bit Montgomery values on 8 x 32-bit
+// limbs, products built from mad.lo.cc / madc.hi.cc carry chains (ptxas fuses each
+// lo/hi pair into one IMAD.WIDE.U32 with carry-in/out), even/odd column
+// accumulators so no carry ever ripples between the two halves of a product.
+//
+// Replaces, on the device, the halo2_curves 0.3.3 [ext] Fq/Fr arithmetic that
+// /root/reference/plonkish_backend/src/util/arithmetic/msm.rs:133-148,153,163
+// calls into (64-bit-limb mac/adc on the CPU).
+//
+// The same file compiles under g++ with tests/emul/cuda_emul.h, where every
+// carry-chain block below has a portable restatement; that is test plumbing —
+// the product only ever runs the PTX.
+#pragma once
+#include <stdint.h>
+
+#ifndef PLONKISH_EMUL
+#define PK_HD __device__ __forceinline__
+#else
+#define PK_HD inline
+#endif
+
+namespace pk {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct fe {  // one field element, little-endian 32-bit limbs, Montgomery form (R = 2^256)
+    u32 l[8];
+};
+
+// ---------------------------------------------------------------- constants
+// Fq modulus p, -p^-1 mod 2^32, R mod p (the Montgomery "one").
+#define PK_P0 0xd87cfd47u
+#define PK_P1 0x3c208c16u
+#define PK_P2 0x6871ca8du
+#define PK_P3 0x97816a91u
+#define PK_P4 0x8181585du
+#define PK_P5 0xb85045b6u
+#define PK_P6 0xe131a029u
+#define PK_P7 0x30644e72u
+#define PK_PINV 0xe4866389u
+// Fr modulus r and -r^-1 mod 2^32.
+#define PK_R0 0xf0000001u
+#define PK_R1 0x43e1f593u
+#define PK_R2 0x79b97091u
+#define PK_R3 0x2833e848u
+#define PK_R4 0x8181585du
+#define PK_R5 0xb85045b6u
+#define PK_R6 0xe131a029u
+#define PK_R7 0x30644e72u
+#define PK_RINV 0xefffffffu
+
+PK_HD fe fq_one() {
+    fe r = {{0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}};
+    return r;
+}
+PK_HD fe fe_zero() {
+    fe r = {{0, 0, 0, 0, 0, 0, 0, 0}};
+    return r;
+}
+PK_HD bool fe_is_zero(const fe &a) {
+    return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0;
+}
+PK_HD bool fe_eq(const fe &a, const fe &b) {
+    u32 d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d |= a.l[i] ^ b.l[i];
+    return d == 0;
+}
+
+// ------------------------------------------------------- carry-chain blocks
+// Each block is ONE asm statement, so the condition-code register never has to
+// survive between statements.  MOD selects the modulus for the immediate forms.
+
+#ifndef PLONKISH_EMUL
+
+// acc[0..7] += {x0,x2,x4,x6} * y laid out as 4 (lo,hi) pairs; returns carry-out.
+PK_HD u32 cmad8(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    u32 c;
+    asm("mad.lo.cc.u32  %0, %9,  %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9,  %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32       %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "=r"(c)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    return c;
+}
+
+// e0 += carry_word; then o[k] = o[k+2] + {x1,x3,x5,x7} * y pairs (o[8] = o[9] = 0), the
+// carry of the first add entering the chain.  The top pair cannot overflow because
+// x7 < 2^31 (operands < 2p < 2^255).
+PK_HD void shift_mad8(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
+    asm("add.cc.u32     %0, %0, %9;\n\t"
+        "madc.lo.cc.u32 %1, %10, %14, %3;\n\t"
+        "madc.hi.cc.u32 %2, %10, %14, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %14, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %14, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %14, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %14, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %14, 0;\n\t"
+        "madc.hi.u32    %8, %13, %14, 0;"
+        : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+        : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+}
+
+// out = a + b (8 limbs), returns carry-out.
+PK_HD u32 add8(u32 *out, const u32 *a, const u32 *b) {
+    u32 c;
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;"
+        : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]), "=r"(out[4]), "=r"(out[5]), "=r"(out[6]),
+          "=r"(out[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+}
+
+// out = a - b (8 limbs), returns borrow (0 or 1).
+PK_HD u32 sub8(u32 *out, const u32 *a, const u32 *b) {
+    u32 c;
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]), "=r"(out[4]), "=r"(out[5]), "=r"(out[6]),
+          "=r"(out[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c & 1u;
+}
+
+#else  // PLONKISH_EMUL: portable restatements of the blocks above (tests only)
+
+inline u32 cmad8(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    const u32 x[4] = {x0, x2, x4, x6};
+    u64 carry = 0;
+    for (int k = 0; k < 4; ++k) {
+        u64 prod = (u64)x[k] * y;
+        u64 lo = (u64)acc[2 * k] + (u32)prod + carry;
+        acc[2 * k] = (u32)lo;
+        u64 hi = (u64)acc[2 * k + 1] + (u32)(prod >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (u32)hi;
+        carry = hi >> 32;
+    }
+    return (u32)carry;
+}
+inline void shift_mad8(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
+    const u32 x[4] = {x1, x3, x5, x7};
+    u64 t = (u64)e0 + carry_word;
+    e0 = (u32)t;
+    u64 carry = t >> 32;
+    for (int k = 0; k < 4; ++k) {
+        u64 prod = (u64)x[k] * y;
+        u32 src_lo = (2 * k + 2 < 8) ? o[2 * k + 2] : 0, src_hi = (2 * k + 3 < 8) ? o[2 * k + 3] : 0;
+        u64 lo = (u64)src_lo + (u32)prod + carry;
+        o[2 * k] = (u32)lo;
+        u64 hi = (u64)src_hi + (u32)(prod >> 32) + (lo >> 32);
+        o[2 * k + 1] = (u32)hi;
+        carry = hi >> 32;
+    }
+}
+inline u32 add8(u32 *out, const u32 *a, const u32 *b) {
+    u64 carry = 0;
+    for (int i = 0; i < 8; ++i) {
+        u64 t = (u64)a[i] + b[i] + carry;
+        out[i] = (u32)t;
+        carry = t >> 32;
+    }
+    return (u32)carry;
+}
+inline u32 sub8(u32 *out, const u32 *a, const u32 *b) {
+    u64 borrow = 0;
+    for (int i = 0; i < 8; ++i) {
+        u64 t = (u64)a[i] - b[i] - borrow;
+        out[i] = (u32)t;
+        borrow = (t >> 32) & 1;
+    }
+    return (u32)borrow;
+}
+#endif
+
+// ------------------------------------------------------------ modulus tables
+struct FqMod {
+    static PK_HD u32 inv() { return PK_PINV; }
+    static PK_HD void limbs(u32 *m) {
+        m[0] = PK_P0; m[1] = PK_P1; m[2] = PK_P2; m[3] = PK_P3;
+        m[4] = PK_P4; m[5] = PK_P5; m[6] = PK_P6; m[7] = PK_P7;
+    }
+};
+struct FrMod {
+    static PK_HD u32 inv() { return PK_RINV; }
+    static PK_HD void limbs(u32 *m) {
+        m[0] = PK_R0; m[1] = PK_R1; m[2] = PK_R2; m[3] = PK_R3;
+        m[4] = PK_R4; m[5] = PK_R5; m[6] = PK_R6; m[7] = PK_R7;
+    }
+};
+
+// r = (r >= m) ? r - m : r, for r < 2m.
+template <class MOD>
+PK_HD void final_sub(u32 *r) {
+    u32 m[8], t[8];
+    MOD::limbs(m);
+    u32 borrow = sub8(t, r, m);
+    if (!borrow) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = t[i];
+    }
+}
+
+// Montgomery product a*b/2^256 mod m, a,b < m, result < m.
+//
+// Word-serial reduction, one row per limb of b.  The running value T is kept
+// as two accumulators: `ev` holds the 64-bit partial products that start at even
+// word positions, `od` those that start at odd positions (its word k sits at
+// true word k+1).  A row adds a*b_i, then m*q with q = T[0]*(-m^-1), which clears
+// T[0]; dividing by 2^32 turns the odd accumulator into the even one as is, and
+// the old even one (minus its dead word 0) into the odd one — the single
+// left-over word ev[1] is folded in by shift_mad8's first add.  136 multiply
+// instructions per product: 64 (a*b) + 64 (m*q) + 8 (q).
+template <class MOD>
+PK_HD fe mont_mul(const fe &a, const fe &b) {
+    u32 m[8];
+    MOD::limbs(m);
+    u32 ev[8], od[8];
+
+    // row 0
+    {
+        const u32 y = b.l[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u64 pe = (u64)a.l[2 * k] * y, po = (u64)a.l[2 * k + 1] * y;
+            ev[2 * k] = (u32)pe; ev[2 * k + 1] = (u32)(pe >> 32);
+            od[2 * k] = (u32)po; od[2 * k + 1] = (u32)(po >> 32);
+        }
+        const u32 q = ev[0] * MOD::inv();
+        cmad8(od, m[1], m[3], m[5], m[7], q);               // top pair has headroom: no carry-out
+        od[7] += cmad8(ev, m[0], m[2], m[4], m[6], q);      // carry sits at true word 8 = od word 7
+    }
+    // rows 1..7, roles of ev/od alternate
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        u32 *E = (i & 1) ? od : ev;   // aligned at even positions after the shift
+        u32 *O = (i & 1) ? ev : od;   // old even accumulator: word 0 is dead, word 1 folds into E[0]
+        const u32 y = b.l[i];
+        shift_mad8(E[0], O[1], O, a.l[1], a.l[3], a.l[5], a.l[7], y);
+        O[7] += cmad8(E, a.l[0], a.l[2], a.l[4], a.l[6], y);
+        const u32 q = E[0] * MOD::inv();
+        cmad8(O, m[1], m[3], m[5], m[7], q);
+        O[7] += cmad8(E, m[0], m[2], m[4], m[6], q);
+    }
+    // Row 7 ran with E = od, O = ev and left od[0] == 0; the last shift gives
+    // T/2^256 = ev + (od >> 32).
+    fe r;
+    {
+        u32 sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sh[k] = od[k + 1];
+        sh[7] = 0;
+        add8(r.l, ev, sh);
+    }
+    final_sub<MOD>(r.l);
+    return r;
+}
+
+PK_HD fe fq_mul(const fe &a, const fe &b) { return mont_mul<FqMod>(a, b); }
+PK_HD fe fq_sqr(const fe &a) { return mont_mul<FqMod>(a, a); }
+
+template <class MOD>
+PK_HD fe mod_add(const fe &a, const fe &b) {
+    fe r;
+    add8(r.l, a.l, b.l);  // a + b < 2^255: no carry-out
+    final_sub<MOD>(r.l);
+    return r;
+}
+template <class MOD>
+PK_HD fe mod_sub(const fe &a, const fe &b) {
+    fe r;
+    u32 borrow = sub8(r.l, a.l, b.l);
+    if (borrow) {
+        u32 m[8];
+        MOD::limbs(m);
+        add8(r.l, r.l, m);
+    }
+    return r;
+}
+PK_HD fe fq_add(const fe &a, const fe &b) { return mod_add<FqMod>(a, b); }
+PK_HD fe fq_sub(const fe &a, const fe &b) { return mod_sub<FqMod>(a, b); }
+PK_HD fe fq_dbl(const fe &a) { return mod_add<FqMod>(a, a); }
+PK_HD fe fq_neg(const fe &a) {
+    if (fe_is_zero(a)) return a;
+    fe r;
+    u32 m[8];
+    FqMod::limbs(m);
+    sub8(r.l, m, a.l);
+    return r;
+}
+
+// a^(p-2): 0 -> 0.  Only used once per MSM (projective -> affine).
+PK_HD fe fq_inv(const fe &a) {
+    u32 e[8];
+    FqMod::limbs(e);
+    e[0] -= 2;  // p ends in ...47, no borrow
+    fe acc = fq_one(), base = a;
+    for (int i = 0; i < 254; ++i) {
+        if ((e[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, base);
+        base = fq_sqr(base);
+    }
+    return acc;
+}
+
+// Fr Montgomery form -> canonical integer (halo2_curves `to_repr`, called at
+// msm.rs:153): one Montgomery reduction, i.e. a product with the plain integer 1.
+PK_HD fe fr_to_canonical(const fe &a) {
+    fe one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+    return mont_mul<FrMod>(a, one);
+}
+
+}  // namespace pk

@@ -1,0 +1,675 @@
+// BN254 G1 variable-base MSM on one B200: the kernels and the launch sequence.
+//
+// Replaces /root/reference/plonkish_backend/src/util/arithmetic/msm.rs:84-181
+// (variable_base_msm + variable_base_msm_serial).  The reference walks unsigned
+// c-bit windows high->low per CPU thread and does a random read-modify-write on
+// a bucket array per (point, window) (msm.rs:168-173).  Here the same sum is
+// reorganised for HBM and the integer pipe:
+//
+//   K1 decompose   Fr Montgomery -> canonical (to_repr, msm.rs:153), negate if
+//                  > (r-1)/2, signed base-2^c digits; per-tile histogram of the
+//                  high bucket bits in shared memory.            [HBM bound]
+//   K2 scan/scatter/sort  counting sort of (bucket, point) pairs: tile offsets ->
+//                  scatter into (window, high-bits) bins -> per-bin sort on the low
+//                  bits; output is one dense array ordered by (window, bucket) and
+//                  bucket_start[].                               [HBM bound]
+//   K3 accumulate  every thread owns a fixed-length run of the sorted array (skew
+//                  proof), sums its points with XYZZ mixed additions, stores the
+//                  buckets that lie wholly inside the run and hands the two partial
+//                  ends to a warp-level segmented reduction by shuffles; warps emit
+//                  two items each to the next level.             [IMAD bound]
+//   K4 bucket reduce   sum_k k*B_k per window by chunked running sums.
+//   K5 window combine  2^(c*w) weights, final sum, XYZZ -> affine.
+//
+// This header is also compiled by g++ against tests/emul/cuda_emul.h so the
+// kernels' logic runs in the CPU test suite; the product only runs the nvcc build.
+#pragma once
+#include "g1.cuh"
+
+#ifndef PLONKISH_EMUL
+#include <cuda_runtime.h>
+#define PK_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define PK_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type *name = reinterpret_cast<type *>(name##_raw)
+typedef cudaStream_t pk_stream_t;
+#else
+#define PK_LAUNCH(kern, grid, block, smem, stream, ...) emul::launch(grid, block, smem, [&] { kern(__VA_ARGS__); })
+#define PK_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emul::g_dyn_smem)
+typedef int pk_stream_t;
+#endif
+
+namespace pk {
+
+typedef uint16_t u16;
+
+static const u32 PK_INVALID_KEY = 0xffffffffu;
+static const u32 PK_ZERO_DIGIT = 0xffffu;
+
+// ------------------------------------------------------------------ the plan
+struct MsmPlan {
+    u32 n;          // points in this launch sequence (<= 2^26)
+    u32 n_pad;      // n rounded up to 8 (digit rows are read as uint4)
+    u32 c;          // window bits, 8..16
+    u32 W;          // windows = ceil(254 / c) (scalars are folded to <= (r-1)/2 first)
+    u32 B;          // buckets per window = 2^(c-1)
+    u32 hi_bits, lo_bits, idx_bits;
+    u32 HI;         // 2^hi_bits bins per window
+    u32 nbins;      // W * HI
+    u32 nbuckets;   // W * B
+    u32 tile;       // points per K1 block
+    u32 ntiles;
+    u32 L;          // run length per K3 thread
+    u32 nthreads1;  // K3 threads (multiple of 32)
+    u32 rb;         // buckets per K4 thread
+    u32 red_threads;  // K4 threads per window
+    u32 red_blocks;   // K4 blocks per window
+    u32 blk;          // threads per block of the streaming kernels (256; tests shrink it)
+    u32 serial_items; // item levels above this many items let every lane fold 8 items serially first
+};
+
+inline u32 pk_ceil_log2(u32 v) {
+    u32 b = 0;
+    while ((1ull << b) < v) ++b;
+    return b;
+}
+
+inline u32 pk_default_window_bits(u32 n) {
+    u32 lg = pk_ceil_log2(n < 2 ? 2 : n);
+    if (lg >= 22) return 16;
+    if (lg >= 20) return 15;
+    if (lg >= 18) return 14;
+    if (lg >= 16) return 13;
+    if (lg >= 14) return 12;
+    if (lg >= 12) return 10;
+    return 8;
+}
+
+inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
+    MsmPlan p;
+    p.n = n;
+    p.n_pad = (n + 7u) & ~7u;
+    p.c = c_override ? c_override : pk_default_window_bits(n);
+    if (p.c < 8) p.c = 8;
+    if (p.c > 16) p.c = 16;
+    p.W = (254 + p.c - 1) / p.c;
+    if (p.c * p.W < 255) p.W += 1;  // keep one spare bit so the top digit never carries out
+    p.B = 1u << (p.c - 1);
+    p.idx_bits = pk_ceil_log2(n < 2 ? 2 : n);
+    u32 hi = (p.c - 1 < 8) ? p.c - 1 : 8;
+    u32 room = 31 - p.idx_bits;  // bits left for the low bucket bits in a scatter entry
+    if (p.c - 1 > hi + room) hi = p.c - 1 - room;
+    p.hi_bits = hi;
+    p.lo_bits = p.c - 1 - hi;
+    p.HI = 1u << hi;
+    p.nbins = p.W * p.HI;
+    p.nbuckets = p.W * p.B;
+    u32 tile = 1024;
+    while (tile < 65536 && (n + tile - 1) / tile > 1024) tile <<= 1;
+    p.tile = tile;
+    p.ntiles = (n + tile - 1) / tile;
+    unsigned long long emax = (unsigned long long)n * p.W;
+    unsigned long long resident = (unsigned long long)sm_count * 512ull;
+    unsigned long long L = emax / (resident * 3ull);
+    if (L < 16) L = 16;
+    if (L > 256) L = 256;
+    p.L = (u32)L;
+    unsigned long long t1 = (emax + L - 1) / L;
+    // one warp -> a 32-thread terminal launch; otherwise whole 128-thread blocks
+    p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
+    p.rb = p.B < 8 ? p.B : 8;
+    p.red_threads = p.B / p.rb;
+    p.red_blocks = (p.red_threads + 255) / 256;
+    p.blk = 256;
+    p.serial_items = 8192;
+    return p;
+}
+
+// Workspace layout (one arena, 256-byte aligned pieces).
+struct MsmWorkspace {
+    u16 *digits;        // [W][n_pad]
+    u32 *tile_hist;     // [ntiles][nbins]
+    u32 *bin_total;     // [nbins]
+    u32 *bin_start;     // [nbins + 1]
+    u32 *l1;            // [n * W] entries after the bin scatter
+    u32 *sorted;        // [n * W] (sign << 31 | point index), ordered by (window, bucket)
+    u32 *bucket_start;  // [nbuckets + 1]
+    xyzz *bucket_sum;   // [nbuckets]
+    u32 *item_keys[2];  // ping-pong item lists for the segmented reduction levels
+    xyzz *item_pts[2];
+    xyzz *block_out;    // [W][red_blocks]
+    xyzz *result;       // [1] projective result of this launch sequence
+};
+
+inline size_t pk_align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+inline size_t pk_workspace_bytes(const MsmPlan &p) {
+    size_t e = (size_t)p.n * p.W;
+    size_t items = (size_t)(p.nthreads1 / 32) * 2;
+    size_t s = 0;
+    s += pk_align256(sizeof(u16) * (size_t)p.W * p.n_pad);
+    s += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
+    s += pk_align256(sizeof(u32) * p.nbins);
+    s += pk_align256(sizeof(u32) * (p.nbins + 1));
+    s += pk_align256(sizeof(u32) * e);
+    s += pk_align256(sizeof(u32) * e);
+    s += pk_align256(sizeof(u32) * (p.nbuckets + 1));
+    s += pk_align256(sizeof(xyzz) * p.nbuckets);
+    s += 2 * pk_align256(sizeof(u32) * items);
+    s += 2 * pk_align256(sizeof(xyzz) * items);
+    s += pk_align256(sizeof(xyzz) * (size_t)p.W * p.red_blocks);
+    s += pk_align256(sizeof(xyzz));
+    return s;
+}
+
+inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
+    MsmWorkspace w;
+    unsigned char *q = (unsigned char *)arena;
+    size_t e = (size_t)p.n * p.W;
+    size_t items = (size_t)(p.nthreads1 / 32) * 2;
+    w.digits = (u16 *)q; q += pk_align256(sizeof(u16) * (size_t)p.W * p.n_pad);
+    w.tile_hist = (u32 *)q; q += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
+    w.bin_total = (u32 *)q; q += pk_align256(sizeof(u32) * p.nbins);
+    w.bin_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbins + 1));
+    w.l1 = (u32 *)q; q += pk_align256(sizeof(u32) * e);
+    w.sorted = (u32 *)q; q += pk_align256(sizeof(u32) * e);
+    w.bucket_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
+    w.bucket_sum = (xyzz *)q; q += pk_align256(sizeof(xyzz) * p.nbuckets);
+    for (int k = 0; k < 2; ++k) { w.item_keys[k] = (u32 *)q; q += pk_align256(sizeof(u32) * items); }
+    for (int k = 0; k < 2; ++k) { w.item_pts[k] = (xyzz *)q; q += pk_align256(sizeof(xyzz) * items); }
+    w.block_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.W * p.red_blocks);
+    w.result = (xyzz *)q;
+    return w;
+}
+
+// ------------------------------------------------------- 128-bit load/store
+PK_HD fe load_fe(const uint4 *p) {
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    fe r = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+    return r;
+}
+PK_HD void store_fe(uint4 *p, const fe &v) {
+    p[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    p[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+PK_HD xyzz load_xyzz(const xyzz *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    xyzz r;
+    r.x = load_fe(q); r.y = load_fe(q + 2); r.zz = load_fe(q + 4); r.zzz = load_fe(q + 6);
+    return r;
+}
+PK_HD void store_xyzz(xyzz *p, const xyzz &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    store_fe(q, v.x); store_fe(q + 2, v.y); store_fe(q + 4, v.zz); store_fe(q + 6, v.zzz);
+}
+
+// ================================================================= K1 decompose
+// (r - 1) / 2, little-endian 32-bit limbs.
+PK_HD bool fr_above_half(const fe &v) {
+    const u32 h[8] = {0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (v.l[i] != h[i]) return v.l[i] > h[i];
+    }
+    return false;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_decompose(const uint4 *__restrict__ scalars, MsmPlan p, u16 *__restrict__ digits,
+                                                   u32 *__restrict__ tile_hist) {
+    constexpr int W = (254 + C - 1) / C + ((C * ((254 + C - 1) / C) < 255) ? 1 : 0);
+    constexpr u32 B = 1u << (C - 1);
+    PK_DYN_SMEM(u32, hist);  // [W][HI]
+    const u32 tile = blockIdx.x;
+    for (u32 k = threadIdx.x; k < p.nbins; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const u32 beg = tile * p.tile;
+    const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
+    for (u32 i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        fe v = fr_to_canonical(load_fe(scalars + 2 * (size_t)i));
+        const bool neg = fr_above_half(v);
+        if (neg) {
+            u32 m[8];
+            FrMod::limbs(m);
+            fe t;
+            sub8(t.l, m, v.l);
+            v = t;
+        }
+        u32 carry = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int off = w * C;
+            const int word = off >> 5, sh = off & 31;
+            u32 raw = 0;
+            if (word < 8) {
+                raw = v.l[word] >> sh;
+                if (sh + C > 32 && word + 1 < 8) raw |= v.l[word + 1] << (32 - sh);
+            }
+            raw = (raw & ((1u << C) - 1u)) + carry;
+            // Non-negated scalars borrow when raw > B, negated ones when raw >= B, so
+            // the encoded (sign, |d| - 1) pair never collides with PK_ZERO_DIGIT.
+            const bool borrow = neg ? (raw >= B) : (raw > B);
+            const u32 mag = borrow ? (1u << C) - raw : raw;
+            carry = borrow ? 1u : 0u;
+            const u32 sign = (borrow ? 1u : 0u) ^ (neg ? 1u : 0u);
+            u32 enc = PK_ZERO_DIGIT;
+            if (mag != 0) {
+                enc = (sign << 15) | (mag - 1u);
+                atomicAdd(&hist[w * p.HI + ((mag - 1u) >> p.lo_bits)], 1u);
+            }
+            digits[(size_t)w * p.n_pad + i] = (u16)enc;
+        }
+    }
+    __syncthreads();
+    u32 *out = tile_hist + (size_t)tile * p.nbins;
+    for (u32 k = threadIdx.x; k < p.nbins; k += blockDim.x) out[k] = hist[k];
+}
+
+// ===================================================================== K2 scans
+// Column scan: for each bin, exclusive prefix over tiles (in place) and the total.
+__global__ void __launch_bounds__(256) k_scan_tiles(u32 *__restrict__ tile_hist, u32 ntiles, u32 nbins, u32 *__restrict__ bin_total) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    u32 run = 0;
+    for (u32 t = 0; t < ntiles; ++t) {
+        const u32 v = tile_hist[(size_t)t * nbins + b];
+        tile_hist[(size_t)t * nbins + b] = run;
+        run += v;
+    }
+    bin_total[b] = run;
+}
+
+// Exclusive scan of bin_total[nbins] into bin_start[nbins + 1]; one block of 1024.
+__global__ void __launch_bounds__(1024) k_scan_bins(const u32 *__restrict__ bin_total, u32 nbins, u32 *__restrict__ bin_start) {
+    __shared__ u32 part[1024];
+    const u32 per = (nbins + blockDim.x - 1) / blockDim.x;
+    const u32 beg = threadIdx.x * per;
+    u32 sum = 0;
+    for (u32 k = 0; k < per; ++k) {
+        if (beg + k < nbins) sum += bin_total[beg + k];
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums.
+    for (u32 d = 1; d < blockDim.x; d <<= 1) {
+        u32 v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = part[threadIdx.x] - sum;
+    for (u32 k = 0; k < per; ++k) {
+        if (beg + k < nbins) {
+            bin_start[beg + k] = run;
+            run += bin_total[beg + k];
+        }
+    }
+    if (threadIdx.x == blockDim.x - 1) bin_start[nbins] = part[threadIdx.x];
+}
+
+// =========================================================== K2 bin scatter (L1)
+// grid (ntiles, W).  Entry layout: lo_bits | sign | point index (idx_bits).
+__global__ void __launch_bounds__(256) k_scatter_bins(const u16 *__restrict__ digits, MsmPlan p, const u32 *__restrict__ tile_hist,
+                                                      const u32 *__restrict__ bin_start, u32 *__restrict__ l1) {
+    __shared__ u32 cursor[1024];
+    const u32 tile = blockIdx.x, w = blockIdx.y;
+    for (u32 h = threadIdx.x; h < p.HI; h += blockDim.x)
+        cursor[h] = bin_start[w * p.HI + h] + tile_hist[(size_t)tile * p.nbins + w * p.HI + h];
+    __syncthreads();
+    const u32 beg = tile * p.tile;
+    const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
+    const u16 *row = digits + (size_t)w * p.n_pad;
+    const u32 lo_mask = (1u << p.lo_bits) - 1u;
+    // tile is a multiple of 8 and rows are padded to 8: 128-bit loads of 8 digits.
+    for (u32 i = beg + 8 * threadIdx.x; i < end; i += 8 * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + i));
+        const u32 words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const u32 d = (words[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            if (i + k < end && d != PK_ZERO_DIGIT) {
+                const u32 b = d & 0x7fffu;
+                const u32 pos = atomicAdd(&cursor[b >> p.lo_bits], 1u);
+                l1[pos] = ((b & lo_mask) << (p.idx_bits + 1)) | ((d >> 15) << p.idx_bits) | (i + k);
+            }
+        }
+    }
+}
+
+// ============================================================= K2 bin sort (L2)
+// One block per (window, high-bits) bin: counting sort on the low bucket bits.
+// Writes bucket_start[] for the bin's buckets and the final (sign | index) entries.
+__global__ void __launch_bounds__(256) k_sort_bins(const u32 *__restrict__ l1, MsmPlan p, const u32 *__restrict__ bin_start,
+                                                   u32 *__restrict__ sorted, u32 *__restrict__ bucket_start) {
+    __shared__ u32 cnt[128];
+    const u32 bin = blockIdx.x;
+    const u32 beg = bin_start[bin], end = bin_start[bin + 1];
+    const u32 nlo = 1u << p.lo_bits;
+    for (u32 k = threadIdx.x; k < nlo; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    const u32 sh = p.idx_bits + 1;
+    for (u32 q = beg + threadIdx.x; q < end; q += blockDim.x) atomicAdd(&cnt[l1[q] >> sh], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 run = beg;
+        for (u32 k = 0; k < nlo; ++k) {
+            const u32 v = cnt[k];
+            cnt[k] = run;
+            bucket_start[(size_t)bin * nlo + k] = run;
+            run += v;
+        }
+        if (bin == p.nbins - 1) bucket_start[p.nbuckets] = run;
+    }
+    __syncthreads();
+    const u32 idx_mask = (1u << p.idx_bits) - 1u;
+    for (u32 q = beg + threadIdx.x; q < end; q += blockDim.x) {
+        const u32 e = l1[q];
+        const u32 pos = atomicAdd(&cnt[e >> sh], 1u);
+        sorted[pos] = (((e >> p.idx_bits) & 1u) << 31) | (e & idx_mask);
+    }
+}
+
+// ==================================================== warp segmented reduction
+PK_HD u32 shfl_u32(u32 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+#ifndef PLONKISH_EMUL
+PK_HD xyzz shfl_down_xyzz(const xyzz &v, u32 d) {
+    xyzz r;
+    const u32 *src = reinterpret_cast<const u32 *>(&v);
+    u32 *dst = reinterpret_cast<u32 *>(&r);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d);
+    return r;
+}
+PK_HD xyzz shfl_up_xyzz(const xyzz &v, u32 d) {
+    xyzz r;
+    const u32 *src = reinterpret_cast<const u32 *>(&v);
+    u32 *dst = reinterpret_cast<u32 *>(&r);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dst[i] = __shfl_up_sync(0xffffffffu, src[i], d);
+    return r;
+}
+#else  // emulation moves the whole point in one exchange (32x fewer barriers)
+inline xyzz shfl_down_xyzz(const xyzz &v, u32 d) { return emul::warp_exchange_blob(v, (int)d); }
+inline xyzz shfl_up_xyzz(const xyzz &v, u32 d) { return emul::warp_exchange_blob(v, -(int)d); }
+#endif
+
+// Every lane brings the two open ends of its run: head (hk, hp) = the sum for the
+// first key it saw, tail (tk, tp) = the sum for the last key if different (else
+// tk == hk and tp = identity).  Keys are non-decreasing across lanes and within a
+// lane.  Sums that are provably complete inside this warp are stored to
+// bucket_sum[key]; the warp's first and last open sums go to the next level as
+// items 2*warp and 2*warp+1 (terminal: everything is stored).
+PK_HD void warp_merge(u32 hk, xyzz hp, u32 tk, const xyzz &tp, xyzz *bucket_sum, u32 *out_keys, xyzz *out_pts,
+                      u32 warp_global, bool terminal) {
+    const u32 lane = threadIdx.x & 31u;
+    const bool real_tail = (tk != hk);
+    // A: a lane's tail continues in the next lane's head.
+    const u32 prev_tk = __shfl_up_sync(0xffffffffu, tk, 1);
+    const xyzz prev_tp = shfl_up_xyzz(tp, 1);
+    const u32 next_hk = __shfl_down_sync(0xffffffffu, hk, 1);
+    if (lane > 0 && prev_tk == hk) hp = xyzz_add(hp, prev_tp);
+    const bool tail_consumed = (lane < 31) && (next_hk == tk);
+    if (real_tail && lane < 31 && !tail_consumed && tk != PK_INVALID_KEY) store_xyzz(bucket_sum + tk, tp);
+    // B: segmented reduction of the heads.
+#pragma unroll 1
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 okey = __shfl_down_sync(0xffffffffu, hk, d);
+        const xyzz other = shfl_down_xyzz(hp, d);
+        if (lane + d < 32 && okey == hk) hp = xyzz_add(hp, other);
+    }
+    const u32 prev_hk = __shfl_up_sync(0xffffffffu, hk, 1);
+    const bool leader = (lane == 0) || (prev_hk != hk);
+    const u32 hk31 = shfl_u32(hk, 31), tk31 = shfl_u32(tk, 31), hk0 = shfl_u32(hk, 0);
+    const bool rt31 = (tk31 != hk31);
+    if (terminal) {
+        if (leader && hk != PK_INVALID_KEY) store_xyzz(bucket_sum + hk, hp);
+        if (lane == 31 && real_tail && tk != PK_INVALID_KEY) store_xyzz(bucket_sum + tk, tp);
+        return;
+    }
+    if (leader) {
+        if (lane == 0) {
+            out_keys[2 * warp_global] = hk;
+            store_xyzz(out_pts + 2 * warp_global, hp);
+        } else if (!rt31 && hk == hk31) {
+            out_keys[2 * warp_global + 1] = hk;
+            store_xyzz(out_pts + 2 * warp_global + 1, hp);
+        } else if (hk != PK_INVALID_KEY) {
+            store_xyzz(bucket_sum + hk, hp);
+        }
+    }
+    if (rt31) {
+        if (lane == 31) {
+            out_keys[2 * warp_global + 1] = tk;
+            store_xyzz(out_pts + 2 * warp_global + 1, tp);
+        }
+    } else if (hk0 == hk31) {
+        if (lane == 0) {
+            out_keys[2 * warp_global + 1] = hk31;
+            store_xyzz(out_pts + 2 * warp_global + 1, xyzz_identity());
+        }
+    }
+}
+
+// ================================================================ K3 accumulate
+// Thread t sums sorted[t*L, (t+1)*L).  bucket_start[nbuckets] is the entry count.
+__global__ void __launch_bounds__(128) k_accumulate(const u32 *__restrict__ sorted, const u32 *__restrict__ bucket_start,
+                                                    const affine *__restrict__ bases, MsmPlan p, xyzz *__restrict__ bucket_sum,
+                                                    u32 *__restrict__ out_keys, xyzz *__restrict__ out_pts, int terminal) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 total = bucket_start[p.nbuckets];
+    const unsigned long long s64 = (unsigned long long)t * p.L;
+    u32 hk = PK_INVALID_KEY, tk = PK_INVALID_KEY;
+    xyzz hp = xyzz_identity(), acc = xyzz_identity();
+    if (s64 < total) {
+        const u32 s = (u32)s64;
+        const u32 e = (s + p.L < total) ? s + p.L : total;
+        // largest g with bucket_start[g] <= s
+        u32 lo = 0, hi = p.nbuckets;
+        while (hi - lo > 1) {
+            const u32 mid = (lo + hi) >> 1;
+            if (bucket_start[mid] <= s) lo = mid; else hi = mid;
+        }
+        u32 g = lo;
+        u32 next = bucket_start[g + 1];
+        u32 nflushed = 0;
+        for (u32 pos = s; pos < e; ++pos) {
+            if (pos == next) {
+                if (nflushed == 0) { hk = g; hp = acc; } else { store_xyzz(bucket_sum + g, acc); }
+                ++nflushed;
+                acc = xyzz_identity();
+                do { ++g; next = bucket_start[g + 1]; } while (next <= pos);
+            }
+            const u32 entry = sorted[pos];
+            const uint4 *bp = reinterpret_cast<const uint4 *>(bases + (entry & 0x7fffffffu));
+            const fe x = load_fe(bp);
+            fe y = load_fe(bp + 2);
+            if (entry >> 31) y = fq_neg(y);
+            xyzz_madd(acc, x, y);
+        }
+        if (nflushed == 0) { hk = g; hp = acc; tk = g; acc = xyzz_identity(); } else { tk = g; }
+    }
+    warp_merge(hk, hp, tk, acc, bucket_sum, out_keys, out_pts, t >> 5, terminal != 0);
+}
+
+// ======================================================= K3b item reduce levels
+// Lane handles K consecutive (key, point) items of the previous level.
+__global__ void __launch_bounds__(128) k_reduce_items(const u32 *__restrict__ in_keys, const xyzz *__restrict__ in_pts, u32 count,
+                                                      u32 K, xyzz *__restrict__ bucket_sum, u32 *__restrict__ out_keys,
+                                                      xyzz *__restrict__ out_pts, int terminal) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long s64 = (unsigned long long)t * K;
+    u32 hk = PK_INVALID_KEY, tk = PK_INVALID_KEY;
+    xyzz hp = xyzz_identity(), acc = xyzz_identity();
+    if (s64 < count) {
+        const u32 s = (u32)s64;
+        const u32 e = (s + K < count) ? s + K : count;
+        u32 g = in_keys[s];
+        acc = load_xyzz(in_pts + s);
+        u32 nflushed = 0;
+        for (u32 pos = s + 1; pos < e; ++pos) {
+            const u32 k = in_keys[pos];
+            const xyzz v = load_xyzz(in_pts + pos);
+            if (k != g) {
+                if (nflushed == 0) { hk = g; hp = acc; } else if (g != PK_INVALID_KEY) { store_xyzz(bucket_sum + g, acc); }
+                ++nflushed;
+                g = k;
+                acc = v;
+            } else {
+                acc = xyzz_add(acc, v);
+            }
+        }
+        if (nflushed == 0) { hk = g; hp = acc; tk = g; acc = xyzz_identity(); } else { tk = g; }
+    }
+    warp_merge(hk, hp, tk, acc, bucket_sum, out_keys, out_pts, t >> 5, terminal != 0);
+}
+
+// ============================================================== K4 bucket reduce
+PK_HD xyzz warp_sum_xyzz(xyzz v) {
+#pragma unroll 1
+    for (u32 d = 16; d >= 1; d >>= 1) {
+        const xyzz o = shfl_down_xyzz(v, d);
+        v = xyzz_add(v, o);
+    }
+    return v;  // lane 0 holds the sum
+}
+
+// k * P by double-and-add, k < 2^16.
+PK_HD xyzz xyzz_mul_small(const xyzz &pnt, u32 k) {
+    xyzz r = xyzz_identity();
+    for (int b = 15; b >= 0; --b) {
+        r = xyzz_double(r);
+        if ((k >> b) & 1u) r = xyzz_add(r, pnt);
+    }
+    return r;
+}
+
+// grid (red_blocks, W), block 256.  Thread j of window w owns buckets
+// [j*rb, (j+1)*rb): sum_i (j*rb + i + 1) * B_i = acc + (j*rb) * run, where run is
+// the plain sum and acc the running-sum total (msm.rs:175-179 restated per chunk).
+__global__ void __launch_bounds__(256) k_bucket_reduce(const xyzz *__restrict__ bucket_sum, const u32 *__restrict__ bucket_start,
+                                                       MsmPlan p, xyzz *__restrict__ block_out) {
+    __shared__ xyzz warp_part[8];
+    const u32 w = blockIdx.y;
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    xyzz contrib = xyzz_identity();
+    if (j < p.red_threads) {
+        xyzz run = xyzz_identity(), acc = xyzz_identity();
+        for (int i = (int)p.rb - 1; i >= 0; --i) {
+            const u32 g = w * p.B + j * p.rb + (u32)i;
+            if (bucket_start[g + 1] > bucket_start[g]) run = xyzz_add(run, load_xyzz(bucket_sum + g));
+            acc = xyzz_add(acc, run);
+        }
+        contrib = xyzz_add(acc, xyzz_mul_small(run, j * p.rb));
+    }
+    contrib = warp_sum_xyzz(contrib);
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_part[wid] = contrib;
+    __syncthreads();
+    if (wid == 0) {
+        xyzz v = (lane < (blockDim.x >> 5)) ? warp_part[lane] : xyzz_identity();
+        v = warp_sum_xyzz(v);
+        if (lane == 0) store_xyzz(block_out + (size_t)w * p.red_blocks + blockIdx.x, v);
+    }
+}
+
+// ============================================================ K5 window combine
+// One block, one warp per window: S_w = sum of the window's block partials,
+// T_w = 2^(c*w) * S_w, result = sum_w T_w.  Optionally adds `prev` (the running
+// total of earlier chunks of the same MSM) before the result is stored.
+__global__ void __launch_bounds__(1024) k_window_combine(const xyzz *__restrict__ block_out, MsmPlan p, const xyzz *prev,
+                                                         xyzz *__restrict__ result) {
+    __shared__ xyzz win[32];
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    xyzz v = xyzz_identity();
+    if (w < p.W) {
+        for (u32 k = lane; k < p.red_blocks; k += 32) v = xyzz_add(v, load_xyzz(block_out + (size_t)w * p.red_blocks + k));
+    }
+    v = warp_sum_xyzz(v);
+    if (lane == 0) {
+        if (w < p.W) {
+            for (u32 k = 0; k < p.c * w; ++k) v = xyzz_double(v);
+        }
+        win[w] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+        xyzz t = (lane < p.W) ? win[lane] : xyzz_identity();
+        t = warp_sum_xyzz(t);
+        if (lane == 0) {
+            if (prev) t = xyzz_add(t, load_xyzz(prev));
+            store_xyzz(result, t);
+        }
+    }
+}
+
+// Sum `count` projective partials (one per chunk or per GPU) and normalise:
+// the `.to_affine()` every reference caller applies (e.g. kzg.rs:255, pcs.rs:175).
+__global__ void k_finalize(const xyzz *__restrict__ partials, u32 count, affine *__restrict__ out_affine, xyzz *__restrict__ out_xyzz) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    xyzz t = xyzz_identity();
+    for (u32 k = 0; k < count; ++k) t = xyzz_add(t, load_xyzz(partials + k));
+    if (out_xyzz) store_xyzz(out_xyzz, t);
+    if (out_affine) {
+        const affine a = xyzz_to_affine(t);
+        uint4 *q = reinterpret_cast<uint4 *>(out_affine);
+        store_fe(q, a.x);
+        store_fe(q + 2, a.y);
+    }
+}
+
+// ================================================================ launch sequence
+template <int C>
+inline void pk_launch_decompose(const MsmPlan &p, const void *scalars, const MsmWorkspace &ws, pk_stream_t stream) {
+    const size_t smem = sizeof(u32) * p.nbins;
+#ifndef PLONKISH_EMUL
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_decompose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+#endif
+    PK_LAUNCH(k_decompose<C>, dim3(p.ntiles), dim3(p.blk), smem, stream, (const uint4 *)scalars, p, ws.digits, ws.tile_hist);
+}
+
+// Enqueues one MSM over p.n points; the projective result lands in ws.result
+// (plus *prev if given).  No host synchronisation.
+inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *bases, const MsmWorkspace &ws, const xyzz *prev,
+                           pk_stream_t stream) {
+    switch (p.c) {
+        case 8: pk_launch_decompose<8>(p, scalars, ws, stream); break;
+        case 9: pk_launch_decompose<9>(p, scalars, ws, stream); break;
+        case 10: pk_launch_decompose<10>(p, scalars, ws, stream); break;
+        case 11: pk_launch_decompose<11>(p, scalars, ws, stream); break;
+        case 12: pk_launch_decompose<12>(p, scalars, ws, stream); break;
+        case 13: pk_launch_decompose<13>(p, scalars, ws, stream); break;
+        case 14: pk_launch_decompose<14>(p, scalars, ws, stream); break;
+        case 15: pk_launch_decompose<15>(p, scalars, ws, stream); break;
+        default: pk_launch_decompose<16>(p, scalars, ws, stream); break;
+    }
+    PK_LAUNCH(k_scan_tiles, dim3((p.nbins + p.blk - 1) / p.blk), dim3(p.blk), 0, stream, ws.tile_hist, p.ntiles, p.nbins, ws.bin_total);
+    PK_LAUNCH(k_scan_bins, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.nbins, ws.bin_start);
+    PK_LAUNCH(k_scatter_bins, dim3(p.ntiles, p.W), dim3(p.blk), 0, stream, ws.digits, p, ws.tile_hist, ws.bin_start, ws.l1);
+    PK_LAUNCH(k_sort_bins, dim3(p.nbins), dim3(p.blk), 0, stream, ws.l1, p, ws.bin_start, ws.sorted, ws.bucket_start);
+
+    // K3 + the item levels.
+    u32 warps = p.nthreads1 / 32;
+    int terminal = (warps == 1) ? 1 : 0;
+    PK_LAUNCH(k_accumulate, dim3(terminal ? 1 : p.nthreads1 / 128), dim3(terminal ? 32 : 128), 0, stream, ws.sorted,
+              ws.bucket_start, (const affine *)bases, p, ws.bucket_sum, ws.item_keys[0], ws.item_pts[0], terminal);
+    u32 count = 2 * warps;
+    int src = 0;
+    while (!terminal) {
+        const u32 K = (count > p.serial_items) ? 8 : 1;
+        const u32 lanes = (count + K - 1) / K;
+        const u32 nthreads = (lanes <= 32) ? 32u : ((lanes + 127u) & ~127u);
+        warps = nthreads / 32;
+        terminal = (warps == 1) ? 1 : 0;
+        PK_LAUNCH(k_reduce_items, dim3(terminal ? 1 : nthreads / 128), dim3(terminal ? 32 : 128), 0, stream, ws.item_keys[src], ws.item_pts[src], count, K,
+                  ws.bucket_sum, ws.item_keys[src ^ 1], ws.item_pts[src ^ 1], terminal);
+        count = 2 * warps;
+        src ^= 1;
+    }
+    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.W), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
+    PK_LAUNCH(k_window_combine, dim3(1), dim3(1024), 0, stream, ws.block_out, p, prev, ws.result);
+}
+
+}  // namespace pk

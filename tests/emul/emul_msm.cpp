@@ -1,0 +1,77 @@
+// tests/emul/emul_msm.cpp — TEST INFRASTRUCTURE ONLY.
+// Builds the product's kernel sources for the CPU through cuda_emul.h and exposes
+// the launch sequence plus a few stage probes to pytest (tests/test_emulated_kernels.py).
+#define PLONKISH_EMUL 1
+#include "cuda_emul.h"
+
+#include "../../plonkish_b200/csrc/msm_kernels.cuh"
+
+#include <stdlib.h>
+
+#include <vector>
+
+using namespace pk;
+
+extern "C" {
+
+// Field / point probes (the portable restatements of the carry-chain blocks).
+void emul_fq_mul(const u32 *a, const u32 *b, u32 *o) {
+    fe x, y;
+    memcpy(&x, a, 32); memcpy(&y, b, 32);
+    fe r = fq_mul(x, y);
+    memcpy(o, &r, 32);
+}
+void emul_fr_to_canonical(const u32 *a, u32 *o) {
+    fe x;
+    memcpy(&x, a, 32);
+    fe r = fr_to_canonical(x);
+    memcpy(o, &r, 32);
+}
+void emul_xyzz_madd(u32 *acc128, const u32 *pt64) {
+    xyzz a; affine p;
+    memcpy(&a, acc128, 128); memcpy(&p, pt64, 64);
+    xyzz_madd(a, p.x, p.y);
+    memcpy(acc128, &a, 128);
+}
+void emul_xyzz_add(const u32 *a128, const u32 *b128, u32 *o128) {
+    xyzz a, b;
+    memcpy(&a, a128, 128); memcpy(&b, b128, 128);
+    xyzz r = xyzz_add(a, b);
+    memcpy(o128, &r, 128);
+}
+void emul_xyzz_to_affine(const u32 *a128, u32 *o64) {
+    xyzz a;
+    memcpy(&a, a128, 128);
+    affine r = xyzz_to_affine(a);
+    memcpy(o64, &r, 64);
+}
+
+void emul_plan(u32 n, u32 c, u32 sms, u32 *out /*[8]*/) {
+    MsmPlan p = pk_make_plan(n, c, sms);
+    out[0] = p.c; out[1] = p.W; out[2] = p.hi_bits; out[3] = p.lo_bits; out[4] = p.idx_bits;
+    out[5] = p.tile; out[6] = p.L; out[7] = p.nthreads1;
+}
+
+// Full launch sequence on host memory.  digits_out (optional): [W][n_pad] u16;
+// sorted_out / bucket_start_out (optional) sized n*W and nbuckets+1.
+int emul_msm(const void *scalars, const void *bases, u32 n, u32 c_override, u32 sm_count, u32 serial_items, void *out_affine64,
+             u16 *digits_out, u32 *sorted_out, u32 *bucket_start_out) {
+    if (n == 0) { memset(out_affine64, 0, 64); return 0; }
+    MsmPlan p = pk_make_plan(n, c_override, sm_count);
+    if (serial_items) p.serial_items = serial_items;
+    p.blk = 32;  // fewer OS threads per emulated block; the kernels index by blockDim.x
+    size_t bytes = pk_workspace_bytes(p);
+    void *arena = aligned_alloc(256, bytes);
+    memset(arena, 0xA5, bytes);  // poison: nothing may rely on zeroed scratch
+    MsmWorkspace ws = pk_carve_workspace(p, arena);
+    pk_enqueue_msm(p, scalars, bases, ws, nullptr, 0);
+    affine out;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, 0, ws.result, 1u, &out, (xyzz *)nullptr);
+    memcpy(out_affine64, &out, 64);
+    if (digits_out) memcpy(digits_out, ws.digits, sizeof(u16) * (size_t)p.W * p.n_pad);
+    if (sorted_out) memcpy(sorted_out, ws.sorted, sizeof(u32) * (size_t)p.n * p.W);
+    if (bucket_start_out) memcpy(bucket_start_out, ws.bucket_start, sizeof(u32) * (p.nbuckets + 1));
+    free(arena);
+    return 0;
+}
+}
