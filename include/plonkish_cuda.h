@@ -1,0 +1,144 @@
+/*
+ * plonkish_cuda.h — C ABI of libplonkish_cuda.so: BN254 G1 variable-base MSM on
+ * NVIDIA B200 (sm_100a).  This is the drop-in boundary for
+ *
+ *     plonkish_backend::util::arithmetic::variable_base_msm(scalars, bases)
+ *     /root/reference/plonkish_backend/src/util/arithmetic/msm.rs:84-115
+ *
+ * The reference has no FFI of its own (100 % Rust); these are the
+ * entry points the `plonkish_cuda` Rust crate binds (bindings/plonkish_cuda/src/lib.rs,
+ * INTEGRATION.md) from inside that function when C == bn256::G1Affine.
+ *
+ * Data crossing the boundary (all little-endian, exactly the in-memory layout
+ * of halo2_curves 0.3.3 [ext] types, plonkish_backend/Cargo.toml:7):
+ *   scalar  32 B  bn256::Fr       4 x u64 limbs, Montgomery form (a * 2^256 mod r)
+ *   base    64 B  bn256::G1Affine x || y, each a Montgomery Fq; (0, 0) = identity
+ *   result  64 B  bn256::G1Affine same encoding; the identity comes back as (0, 0)
+ * The reference returns a projective `C::Curve` that every hot-path caller
+ * normalises at once (`.into()` at pcs/multilinear/kzg.rs:255,271,292 and
+ * pcs/univariate/kzg.rs:28; `.to_affine()` at pcs.rs:175); the library returns
+ * that affine value, bit-exact.
+ *
+ * Conventions: every function returns 0 on success or a negative PLONKISH_CUDA_E_*
+ * code; plonkish_cuda_last_error() gives the message for the calling thread.
+ * There is no CPU fallback: without a usable CUDA device every compute call fails.
+ * Calls are blocking unless they take a stream, and thread-safe (the reference
+ * calls variable_base_msm from rayon workers, pcs/multilinear/hyrax.rs:176-180).
+ * n == 0 returns the identity (the reference panics at msm.rs:154; documented
+ * deviation).  Mismatched lengths cannot be expressed: one `n` covers both arrays
+ * (the reference asserts equality at msm.rs:90).
+ */
+#ifndef PLONKISH_CUDA_H
+#define PLONKISH_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLONKISH_CUDA_OK 0
+#define PLONKISH_CUDA_E_INVALID (-1)   /* bad argument (null pointer, unknown handle, device out of range) */
+#define PLONKISH_CUDA_E_CUDA (-2)      /* a CUDA runtime call failed; see last_error */
+#define PLONKISH_CUDA_E_NO_DEVICE (-3) /* no CUDA device / library not initialised */
+#define PLONKISH_CUDA_E_COMM (-4)      /* multi-GPU exchange failed */
+
+#define PLONKISH_CUDA_SCALAR_BYTES 32
+#define PLONKISH_CUDA_AFFINE_BYTES 64
+#define PLONKISH_CUDA_XYZZ_BYTES 128 /* projective partial: X, Y, ZZ, ZZZ (x = X/ZZ, y = Y/ZZZ); ZZ = 0 is the identity */
+
+/* ---- lifetime ------------------------------------------------------------------
+ * Creates one context (stream, scratch arena, base cache) per device for the first
+ * n_devices CUDA devices; n_devices <= 0 means all visible devices.  Idempotent.
+ * Replaces nothing in the reference (rayon's pool is implicit, util/parallel.rs:1-7). */
+int plonkish_cuda_init(int n_devices);
+int plonkish_cuda_device_count(void); /* contexts created by init, or a negative error */
+void plonkish_cuda_shutdown(void);
+const char *plonkish_cuda_last_error(void);
+
+/* ---- resident bases --------------------------------------------------------------
+ * Uploads n affine bases to `device` and returns a handle.  The reference re-reads
+ * its SRS from host memory on every call (ProverParam.eqs, pcs/multilinear/kzg.rs:55-77;
+ * powers_of_s_g1, pcs/univariate/kzg.rs:24-30); the SRS is static per ProverParam, so
+ * the shim registers each slice once, keyed by (pointer, length), and passes the
+ * handle afterwards.  A later MSM may use any prefix n' <= n of a registered slice. */
+int plonkish_cuda_bases_register(int device, const void *bases_affine64, size_t n, uint64_t *handle);
+int plonkish_cuda_bases_release(uint64_t handle);
+
+/* ---- the hot path, host buffers in, host result out -----------------------------------
+ * out = sum_i scalars[i] * bases[i].  Exactly one of (bases_affine64, bases_handle != 0)
+ * selects the bases; with a handle the bases are not copied again.  Runs on the
+ * handle's device, or device 0.  Replaces msm.rs:84-115 for C = bn256::G1Affine;
+ * when PLONKISH_CUDA_TIMER=1 it prints the reference's timer label
+ * "variable_base_msm-{n}" (msm.rs:92) with the elapsed time to stderr. */
+int plonkish_cuda_msm_bn254_g1(const void *scalars_mont32, const void *bases_affine64, uint64_t bases_handle, size_t n,
+                               void *out_affine64);
+
+/* Same for the reference's non-contiguous callers, which pass iterators of
+ * references (chain![..] at pcs/univariate/kzg.rs:346,408; .map(|c| &c.0) at
+ * pcs/multilinear/kzg.rs:145): gathers the n scalars and n bases into staging first. */
+int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs, const void *const *base_ptrs, size_t n,
+                                      void *out_affine64);
+
+/* Point-sharded over the first n_gpus devices: GPU g runs the whole
+ * pipeline on points [g*ceil(n/G), (g+1)*ceil(n/G)), the G projective partials are
+ * gathered on device 0 and added there.  This is msm.rs:101-114 (chunk per thread,
+ * fold the partials) lifted from threads to GPUs.  bases_affine64 is uploaded per
+ * call unless bases_handle names a slice registered with .._register_sharded. */
+int plonkish_cuda_bases_register_sharded(int n_gpus, const void *bases_affine64, size_t n, uint64_t *handle);
+int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars_mont32, const void *bases_affine64,
+                                     uint64_t bases_handle, size_t n, void *out_affine64);
+
+/* ---- device-resident entry points (no host copies, stream-ordered) ---------------------
+ * d_scalars / d_bases are device pointers on `device`; the call only enqueues work on
+ * `cuda_stream` (a cudaStream_t; NULL = the context's own stream) and returns.
+ * window_bits = 0 picks the default for n, 8..16 forces it.  Either output may be NULL:
+ * d_out_affine64 receives the normalised point, d_out_xyzz128 the projective partial
+ * (what one rank contributes before the multi-GPU gather). */
+int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scalars, const void *d_bases, size_t n,
+                                      uint32_t window_bits, void *d_out_affine64, void *d_out_xyzz128, void *cuda_stream);
+
+/* Adds `count` projective partials (128 B each, e.g. one per rank after an NCCL
+ * all-gather) and normalises: msm.rs:112-114 followed by the caller's to_affine(). */
+int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials_xyzz128, size_t count, void *d_out_affine64,
+                                         void *cuda_stream);
+
+/* ---- introspection / measurement helpers ------------------------------------------------- */
+
+/* Fills out[0..8) with the plan the library would use for n points on `device`:
+ * window bits c, windows W, high/low bucket bits of the two sort levels, point
+ * index bits, points per decompose tile, run length per accumulate thread, and the
+ * number of accumulate threads. */
+int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint32_t out[8]);
+
+/* Kernels launched by the library in this process since init (for bench accounting). */
+uint64_t plonkish_cuda_launch_count(void);
+
+/* Integer-pipe microbenchmarks on `device` (CUDA-event timed):
+ *   out[0] = independent mad.wide.u32 (IMAD.WIDE.U32) per second, all SMs busy
+ *   out[1] = 254-bit Montgomery products per second from the library's own fq_mul
+ *   out[2] = the device's maximum SM clock in MHz, out[3] = SM count             */
+int plonkish_cuda_bench_integer_pipe(int device, double out[4]);
+
+/* Synthetic bases with a known discrete log: d_out[i] = (a + i*step) * G for
+ * i in [first, first + n), affine, written on the device.  Used by bench.py and the
+ * tests so that sum_i s_i*B_i can be checked against ((a*sum s_i + step*sum i*s_i) mod r)*G
+ * at any size.  The reference's SRS has the same shape
+ * (eq_j(s) * G, pcs/multilinear/kzg.rs:174-212). */
+int plonkish_cuda_synth_bases_device(int device, void *d_out_affine64, size_t first, size_t n, uint64_t a, uint64_t step,
+                                     void *cuda_stream);
+
+/* ---- test hooks ------------------------------------------------------------------------------
+ * Element-wise probes of the device arithmetic on host arrays, for the parity tests.
+ * field ops (32-byte elements): 0 Fq mul, 1 Fq add, 2 Fq sub, 3 Fr Montgomery->canonical
+ * (halo2_curves to_repr, msm.rs:153), 4 Fq inverse, 5 Fr mul, 6 Fq negate.
+ * point ops (128-byte X,Y,ZZ,ZZZ slots; b's first 64 bytes are an affine point for op 0):
+ * 0 mixed add, 1 full add, 2 double, 3 to_affine (result in the first 64 bytes). */
+int plonkish_cuda_debug_field_op(int device, int op, const void *a32, const void *b32, void *out32, size_t n);
+int plonkish_cuda_debug_point_op(int device, int op, const void *a128, const void *b128, void *out128, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONKISH_CUDA_H */

@@ -1,0 +1,20 @@
+"""plonkish_b200 — BN254 G1 variable-base MSM for amit0365/plonkish on NVIDIA B200.
+
+Only the hot path of SURVEY.md §8 lives here: hand-written sm_100a kernels and the
+C ABI (csrc/, include/plonkish_cuda.h) plus the host-side mirror of the reference
+interface (msm.py, kzg.py, distributed.py).
+"""
+from ._lib import PlonkishCudaError, LIB_PATH  # noqa: F401
+from .msm import (  # noqa: F401
+    G1Bases,
+    ShardedG1Bases,
+    variable_base_msm,
+    variable_base_msm_device,
+    sum_partials_device,
+    synth_bases_device,
+    msm_plan,
+    launch_count,
+    bench_integer_pipe,
+    random_scalars,
+)
+from .distributed import shard_bounds, variable_base_msm_sharded  # noqa: F401

@@ -1,0 +1,96 @@
+"""ctypes binding of libplonkish_cuda.so (include/plonkish_cuda.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``plonkish_b200.build.build_library()``.  There is no CPU fallback: if the shared
+object is missing, or no CUDA device is usable, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplonkish_cuda.so")
+
+# Every symbol include/plonkish_cuda.h declares (checked by tests/test_abi.py).
+EXPORTS = (
+    "plonkish_cuda_init",
+    "plonkish_cuda_device_count",
+    "plonkish_cuda_shutdown",
+    "plonkish_cuda_last_error",
+    "plonkish_cuda_bases_register",
+    "plonkish_cuda_bases_release",
+    "plonkish_cuda_msm_bn254_g1",
+    "plonkish_cuda_msm_bn254_g1_gather",
+    "plonkish_cuda_bases_register_sharded",
+    "plonkish_cuda_msm_bn254_g1_multi",
+    "plonkish_cuda_msm_bn254_g1_device",
+    "plonkish_cuda_g1_sum_partials_device",
+    "plonkish_cuda_msm_plan",
+    "plonkish_cuda_launch_count",
+    "plonkish_cuda_bench_integer_pipe",
+    "plonkish_cuda_synth_bases_device",
+    "plonkish_cuda_debug_field_op",
+    "plonkish_cuda_debug_point_op",
+)
+
+
+class PlonkishCudaError(RuntimeError):
+    """A non-zero return code from the C ABI (the Rust shim panics on these)."""
+
+
+_lib = None
+_initialised = False
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and declare the prototypes; does not touch the GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PlonkishCudaError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). plonkish_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, u64, u32, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+    lib.plonkish_cuda_init.argtypes = [ci]
+    lib.plonkish_cuda_device_count.argtypes = []
+    lib.plonkish_cuda_shutdown.argtypes = []
+    lib.plonkish_cuda_shutdown.restype = None
+    lib.plonkish_cuda_last_error.argtypes = []
+    lib.plonkish_cuda_last_error.restype = ctypes.c_char_p
+    lib.plonkish_cuda_bases_register.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_bases_release.argtypes = [u64]
+    lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
+    lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
+    lib.plonkish_cuda_bases_register_sharded.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_msm_bn254_g1_multi.argtypes = [ci, vp, vp, u64, sz, vp]
+    lib.plonkish_cuda_msm_bn254_g1_device.argtypes = [ci, vp, vp, sz, u32, vp, vp, vp]
+    lib.plonkish_cuda_g1_sum_partials_device.argtypes = [ci, vp, sz, vp, vp]
+    lib.plonkish_cuda_msm_plan.argtypes = [ci, sz, u32, ctypes.POINTER(u32)]
+    lib.plonkish_cuda_launch_count.argtypes = []
+    lib.plonkish_cuda_launch_count.restype = u64
+    lib.plonkish_cuda_bench_integer_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.plonkish_cuda_synth_bases_device.argtypes = [ci, vp, sz, sz, u64, u64, vp]
+    lib.plonkish_cuda_debug_field_op.argtypes = [ci, ci, vp, vp, vp, sz]
+    lib.plonkish_cuda_debug_point_op.argtypes = [ci, ci, vp, vp, vp, sz]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().plonkish_cuda_last_error().decode("utf-8", "replace")
+        raise PlonkishCudaError(f"{what} failed (code {rc}): {msg}")
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library with its device contexts created (plonkish_cuda_init)."""
+    global _initialised
+    l = load()
+    if not _initialised:
+        check(l.plonkish_cuda_init(0), "plonkish_cuda_init")
+        _initialised = True
+    return l

@@ -1,0 +1,682 @@
+// libplonkish_cuda.so — the C ABI declared in include/plonkish_cuda.h.
+//
+// Host side of the drop-in for variable_base_msm
+// (/root/reference/plonkish_backend/src/util/arithmetic/msm.rs:84-115): per-device
+// contexts (stream, scratch arena, resident bases), host<->device staging, point
+// chunking, the multi-GPU point sharding of msm.rs:101-114, and two measurement
+// helpers.  No CPU fallback anywhere: every compute entry point needs a CUDA device.
+#include "../../include/plonkish_cuda.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace pk {
+static std::atomic<unsigned long long> g_launches{0};
+}
+#define PK_COUNT_LAUNCH() (pk::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+#include "msm_kernels.cuh"
+
+using namespace pk;
+
+// ------------------------------------------------------------------ error state
+static thread_local std::string t_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t err__ = (expr);                                                                          \
+        if (err__ != cudaSuccess)                                                                            \
+            return fail(PLONKISH_CUDA_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+// -------------------------------------------------------------------- contexts
+static const size_t MAX_POINTS_PER_LAUNCH = (size_t)1 << 26;  // scatter entries keep 26 index bits
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct Ctx {
+    int dev = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t last_done = nullptr;  // end of the last enqueued MSM: orders arena reuse across streams
+    bool has_last = false;
+    DeviceBuffer arena, scalars, bases_tmp, partials;
+    void *d_out = nullptr;  // [0,64) affine out, [192,256) synth step point, [256,384) running projective sum
+    void *h_out = nullptr;  // pinned mirror of the affine result
+    std::mutex mu;
+};
+
+struct BasesEntry {
+    int n_shards = 1;                 // 1: whole slice on `dev`; G: shard g on device g
+    int dev = 0;
+    size_t n = 0;
+    std::vector<void *> d_ptr;        // per shard
+    std::vector<size_t> shard_n;
+};
+
+static std::mutex g_mu;
+static std::vector<Ctx *> g_ctx;
+static std::map<uint64_t, BasesEntry> g_bases;
+static uint64_t g_next_handle = 1;
+
+static int grow(DeviceBuffer &b, size_t bytes) {
+    if (bytes <= b.bytes) return 0;
+    if (b.ptr) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    CUDA_TRY(cudaMalloc(&b.ptr, bytes));
+    b.bytes = bytes;
+    return 0;
+}
+
+static Ctx *ctx_for(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (device < 0 || (size_t)device >= g_ctx.size()) return nullptr;
+    return g_ctx[device];
+}
+
+extern "C" int plonkish_cuda_init(int n_devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int visible = 0;
+    cudaError_t err = cudaGetDeviceCount(&visible);
+    if (err != cudaSuccess || visible == 0)
+        return fail(PLONKISH_CUDA_E_NO_DEVICE, "no CUDA device: %s", err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+    if (n_devices <= 0 || n_devices > visible) n_devices = visible;
+    while ((int)g_ctx.size() < n_devices) {
+        Ctx *c = new Ctx();
+        c->dev = (int)g_ctx.size();
+        CUDA_TRY(cudaSetDevice(c->dev));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, c->dev));
+        if (prop.major < 10)
+            return fail(PLONKISH_CUDA_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", c->dev, prop.major, prop.minor);
+        c->sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&c->d_out, 512));
+        CUDA_TRY(cudaMallocHost(&c->h_out, 256));
+        g_ctx.push_back(c);
+    }
+    // Direct NVLink peer copies for the multi-GPU partial gather (ignored where unsupported).
+    for (int a = 0; a < (int)g_ctx.size(); ++a) {
+        for (int b = 0; b < (int)g_ctx.size(); ++b) {
+            int can = 0;
+            if (a == b || cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) continue;
+            cudaSetDevice(a);
+            if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
+        }
+    }
+    cudaSetDevice(0);
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return (int)g_ctx.size();
+}
+
+extern "C" void plonkish_cuda_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &kv : g_bases) {
+        for (size_t s = 0; s < kv.second.d_ptr.size(); ++s) {
+            cudaSetDevice(kv.second.n_shards == 1 ? kv.second.dev : (int)s);
+            cudaFree(kv.second.d_ptr[s]);
+        }
+    }
+    g_bases.clear();
+    for (Ctx *c : g_ctx) {
+        cudaSetDevice(c->dev);
+        cudaDeviceSynchronize();
+        cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
+        cudaFree(c->d_out); cudaFreeHost(c->h_out);
+        cudaEventDestroy(c->last_done);
+        cudaStreamDestroy(c->stream);
+        delete c;
+    }
+    g_ctx.clear();
+}
+
+extern "C" const char *plonkish_cuda_last_error(void) { return t_last_error.c_str(); }
+extern "C" uint64_t plonkish_cuda_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------ base cache
+extern "C" int plonkish_cuda_bases_register(int device, const void *bases, size_t n, uint64_t *handle) {
+    if (!bases || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "bases_register: null argument or n == 0");
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_register: device %d not initialised (call plonkish_cuda_init)", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_AFFINE_BYTES));
+    CUDA_TRY(cudaMemcpy(d, bases, n * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice));
+    BasesEntry e;
+    e.n_shards = 1; e.dev = device; e.n = n;
+    e.d_ptr.push_back(d); e.shard_n.push_back(n);
+    std::lock_guard<std::mutex> lk2(g_mu);
+    *handle = g_next_handle++;
+    g_bases[*handle] = e;
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_bases_register_sharded(int n_gpus, const void *bases, size_t n, uint64_t *handle) {
+    if (!bases || !handle || n == 0 || n_gpus < 1) return fail(PLONKISH_CUDA_E_INVALID, "bases_register_sharded: bad argument");
+    if (n_gpus > plonkish_cuda_device_count()) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_register_sharded: %d GPUs requested, %d initialised", n_gpus, plonkish_cuda_device_count());
+    const size_t per = (n + n_gpus - 1) / n_gpus;  // msm.rs:101 chunk_size
+    BasesEntry e;
+    e.n_shards = n_gpus; e.dev = 0; e.n = n;
+    for (int g = 0; g < n_gpus; ++g) {
+        const size_t beg = (size_t)g * per;
+        const size_t cnt = beg >= n ? 0 : (beg + per <= n ? per : n - beg);
+        void *d = nullptr;
+        CUDA_TRY(cudaSetDevice(g));
+        if (cnt) {
+            CUDA_TRY(cudaMalloc(&d, cnt * PLONKISH_CUDA_AFFINE_BYTES));
+            CUDA_TRY(cudaMemcpy(d, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice));
+        }
+        e.d_ptr.push_back(d); e.shard_n.push_back(cnt);
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    *handle = g_next_handle++;
+    g_bases[*handle] = e;
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_bases_release(uint64_t handle) {
+    BasesEntry e;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_bases.find(handle);
+        if (it == g_bases.end()) return fail(PLONKISH_CUDA_E_INVALID, "bases_release: unknown handle %llu", (unsigned long long)handle);
+        e = it->second;
+        g_bases.erase(it);
+    }
+    for (size_t s = 0; s < e.d_ptr.size(); ++s) {
+        if (!e.d_ptr[s]) continue;
+        CUDA_TRY(cudaSetDevice(e.n_shards == 1 ? e.dev : (int)s));
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaFree(e.d_ptr[s]));
+    }
+    return PLONKISH_CUDA_OK;
+}
+
+static bool lookup_bases(uint64_t handle, BasesEntry &out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_bases.find(handle);
+    if (it == g_bases.end()) return false;
+    out = it->second;
+    return true;
+}
+
+// ------------------------------------------------------------- enqueue helpers
+// Caller holds c->mu and has made c->dev current.  Enqueues the MSM over n device-
+// resident points on `stream`; leaves the projective sum in *d_xyzz_out (device).
+static int enqueue_device_msm(Ctx *c, const void *d_scalars, const void *d_bases, size_t n, uint32_t window_bits,
+                              cudaStream_t stream, xyzz **d_result) {
+    const size_t first_chunk = n < MAX_POINTS_PER_LAUNCH ? n : MAX_POINTS_PER_LAUNCH;
+    const size_t tail_chunk = n % MAX_POINTS_PER_LAUNCH;
+    MsmPlan plan0 = pk_make_plan((u32)first_chunk, window_bits, (u32)c->sm_count);
+    size_t need = pk_workspace_bytes(plan0);
+    if (n > MAX_POINTS_PER_LAUNCH && tail_chunk) {
+        const size_t t = pk_workspace_bytes(pk_make_plan((u32)tail_chunk, window_bits, (u32)c->sm_count));
+        if (t > need) need = t;
+    }
+    int rc = grow(c->arena, need);
+    if (rc) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(stream, c->last_done, 0));
+    // Chunks of <= 2^26 points run back to back on the stream and chain their
+    // projective sums through one slot outside the arena (msm.rs:112-114).
+    xyzz *running = (xyzz *)((char *)c->d_out + 256);
+    xyzz *prev = nullptr;
+    for (size_t done = 0; done < n;) {
+        const size_t cnt = (n - done < MAX_POINTS_PER_LAUNCH) ? n - done : MAX_POINTS_PER_LAUNCH;
+        MsmPlan plan = (cnt == first_chunk) ? plan0 : pk_make_plan((u32)cnt, window_bits, (u32)c->sm_count);
+        MsmWorkspace w = pk_carve_workspace(plan, c->arena.ptr);
+        w.result = running;
+        pk_enqueue_msm(plan, (const char *)d_scalars + done * PLONKISH_CUDA_SCALAR_BYTES,
+                       (const char *)d_bases + done * PLONKISH_CUDA_AFFINE_BYTES, w, prev, stream);
+        prev = running;
+        done += cnt;
+    }
+    CUDA_TRY(cudaGetLastError());
+    *d_result = running;
+    return PLONKISH_CUDA_OK;
+}
+
+static int mark_done(Ctx *c, cudaStream_t stream) {
+    CUDA_TRY(cudaEventRecord(c->last_done, stream));
+    c->has_last = true;
+    return PLONKISH_CUDA_OK;
+}
+
+static void timer_report(size_t n, std::chrono::steady_clock::time_point t0) {
+    static const bool enabled = [] {
+        const char *e = getenv("PLONKISH_CUDA_TIMER");
+        return e && e[0] == '1';
+    }();
+    if (!enabled) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // Same label as start_timer(|| format!("variable_base_msm-{}", n)) at msm.rs:92.
+    fprintf(stderr, "variable_base_msm-%zu ....... %.3fms\n", n, ms);
+}
+
+// --------------------------------------------------------------- device entry
+extern "C" int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scalars, const void *d_bases, size_t n,
+                                                 uint32_t window_bits, void *d_out_affine64, void *d_out_xyzz128, void *cuda_stream) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_device: device %d not initialised (call plonkish_cuda_init)", device);
+    if (!d_out_affine64 && !d_out_xyzz128) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: no output pointer");
+    if (n && (!d_scalars || !d_bases)) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: null input");
+    if (window_bits && (window_bits < 8 || window_bits > 16)) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: window_bits must be 0 or 8..16");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    if (n == 0) {
+        if (d_out_affine64) CUDA_TRY(cudaMemsetAsync(d_out_affine64, 0, PLONKISH_CUDA_AFFINE_BYTES, stream));
+        if (d_out_xyzz128) CUDA_TRY(cudaMemsetAsync(d_out_xyzz128, 0, PLONKISH_CUDA_XYZZ_BYTES, stream));
+        return PLONKISH_CUDA_OK;
+    }
+    xyzz *res = nullptr;
+    int rc = enqueue_device_msm(c, d_scalars, d_bases, n, window_bits, stream, &res);
+    if (rc) return rc;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, stream, res, 1u, (affine *)d_out_affine64, (xyzz *)d_out_xyzz128);
+    CUDA_TRY(cudaGetLastError());
+    return mark_done(c, stream);
+}
+
+extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials, size_t count, void *d_out_affine64, void *cuda_stream) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sum_partials: device %d not initialised", device);
+    if (!d_partials || !d_out_affine64 || count == 0) return fail(PLONKISH_CUDA_E_INVALID, "sum_partials: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, stream, (const xyzz *)d_partials, (u32)count, (affine *)d_out_affine64, (xyzz *)nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return PLONKISH_CUDA_OK;
+}
+
+// ----------------------------------------------------------------- host entry
+extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases, uint64_t bases_handle, size_t n, void *out_affine64) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm: null output");
+    if (n && !scalars) return fail(PLONKISH_CUDA_E_INVALID, "msm: null scalars");
+    if (n && !bases && !bases_handle) return fail(PLONKISH_CUDA_E_INVALID, "msm: neither bases nor a handle given");
+    int device = 0;
+    BasesEntry entry;
+    if (bases_handle) {
+        if (!lookup_bases(bases_handle, entry)) return fail(PLONKISH_CUDA_E_INVALID, "msm: unknown bases handle %llu", (unsigned long long)bases_handle);
+        if (entry.n_shards != 1) return fail(PLONKISH_CUDA_E_INVALID, "msm: handle is sharded; use plonkish_cuda_msm_bn254_g1_multi");
+        if (n > entry.n) return fail(PLONKISH_CUDA_E_INVALID, "msm: n = %zu exceeds the %zu registered bases", n, entry.n);
+        device = entry.dev;
+    }
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm: device %d not initialised (call plonkish_cuda_init; there is no CPU fallback)", device);
+    if (n == 0) {
+        memset(out_affine64, 0, PLONKISH_CUDA_AFFINE_BYTES);
+        return PLONKISH_CUDA_OK;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc = grow(c->scalars, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->scalars.ptr, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    const void *d_bases = nullptr;
+    if (bases_handle) {
+        d_bases = entry.d_ptr[0];
+    } else {
+        rc = grow(c->bases_tmp, n * PLONKISH_CUDA_AFFINE_BYTES);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->bases_tmp.ptr, bases, n * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+        d_bases = c->bases_tmp.ptr;
+    }
+    xyzz *res = nullptr;
+    rc = enqueue_device_msm(c, c->scalars.ptr, d_bases, n, 0, c->stream, &res);
+    if (rc) return rc;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, (affine *)c->d_out, (xyzz *)nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    rc = mark_done(c, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_affine64, c->h_out, PLONKISH_CUDA_AFFINE_BYTES);
+    timer_report(n, t0);
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs, const void *const *base_ptrs, size_t n, void *out_affine64) {
+    if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null output");
+    if (n && (!scalar_ptrs || !base_ptrs)) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null pointer table");
+    std::vector<unsigned char> s(n * PLONKISH_CUDA_SCALAR_BYTES), b(n * PLONKISH_CUDA_AFFINE_BYTES);
+    for (size_t i = 0; i < n; ++i) {
+        if (!scalar_ptrs[i] || !base_ptrs[i]) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null element %zu", i);
+        memcpy(&s[i * PLONKISH_CUDA_SCALAR_BYTES], scalar_ptrs[i], PLONKISH_CUDA_SCALAR_BYTES);
+        memcpy(&b[i * PLONKISH_CUDA_AFFINE_BYTES], base_ptrs[i], PLONKISH_CUDA_AFFINE_BYTES);
+    }
+    return plonkish_cuda_msm_bn254_g1(s.data(), b.data(), 0, n, out_affine64);
+}
+
+// ------------------------------------------------------------ multi-GPU entry
+// One process, G devices: shard g runs on device g's stream; the G projective
+// partials are copied to device 0 over NVLink peer copies and added there.  (The
+// one-process-per-GPU deployment gathers the same 128-byte partials with NCCL —
+// plonkish_b200/distributed.py.)
+extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars, const void *bases, uint64_t bases_handle, size_t n, void *out_affine64) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm_multi: null output");
+    if (n_gpus < 1 || n_gpus > plonkish_cuda_device_count())
+        return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_multi: %d GPUs requested, %d initialised", n_gpus, plonkish_cuda_device_count());
+    if (n == 0) { memset(out_affine64, 0, PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
+    if (!scalars || (!bases && !bases_handle)) return fail(PLONKISH_CUDA_E_INVALID, "msm_multi: null input");
+    BasesEntry entry;
+    if (bases_handle) {
+        if (!lookup_bases(bases_handle, entry)) return fail(PLONKISH_CUDA_E_INVALID, "msm_multi: unknown bases handle");
+        if (entry.n_shards != n_gpus || entry.n != n) return fail(PLONKISH_CUDA_E_INVALID, "msm_multi: handle was sharded for %d GPUs / %zu points", entry.n_shards, entry.n);
+    }
+    const size_t per = (n + n_gpus - 1) / n_gpus;  // msm.rs:101
+    std::vector<Ctx *> cs(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) cs[g] = ctx_for(g);
+    for (int g = 0; g < n_gpus; ++g) cs[g]->mu.lock();
+    int rc = PLONKISH_CUDA_OK;
+    auto unlock_all = [&] { for (int g = n_gpus - 1; g >= 0; --g) cs[g]->mu.unlock(); };
+#define MULTI_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { unlock_all(); return fail(PLONKISH_CUDA_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+    rc = 0;
+    MULTI_TRY(cudaSetDevice(0));
+    if ((rc = grow(cs[0]->partials, (size_t)n_gpus * PLONKISH_CUDA_XYZZ_BYTES))) { unlock_all(); return rc; }
+    std::vector<cudaEvent_t> done(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g) {
+        Ctx *c = cs[g];
+        const size_t beg = (size_t)g * per;
+        const size_t cnt = beg >= n ? 0 : (beg + per <= n ? per : n - beg);
+        MULTI_TRY(cudaSetDevice(g));
+        char *slot = (char *)cs[0]->partials.ptr + (size_t)g * PLONKISH_CUDA_XYZZ_BYTES;
+        if (cnt == 0) {
+            MULTI_TRY(cudaSetDevice(0));
+            MULTI_TRY(cudaMemsetAsync(slot, 0, PLONKISH_CUDA_XYZZ_BYTES, cs[0]->stream));
+            continue;
+        }
+        if ((rc = grow(c->scalars, cnt * PLONKISH_CUDA_SCALAR_BYTES))) { unlock_all(); return rc; }
+        MULTI_TRY(cudaMemcpyAsync(c->scalars.ptr, (const char *)scalars + beg * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        const void *d_bases;
+        if (bases_handle) {
+            d_bases = entry.d_ptr[g];
+        } else {
+            if ((rc = grow(c->bases_tmp, cnt * PLONKISH_CUDA_AFFINE_BYTES))) { unlock_all(); return rc; }
+            MULTI_TRY(cudaMemcpyAsync(c->bases_tmp.ptr, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+            d_bases = c->bases_tmp.ptr;
+        }
+        xyzz *res = nullptr;
+        if ((rc = enqueue_device_msm(c, c->scalars.ptr, d_bases, cnt, 0, c->stream, &res))) { unlock_all(); return rc; }
+        MULTI_TRY(cudaMemcpyPeerAsync(slot, 0, res, g, PLONKISH_CUDA_XYZZ_BYTES, c->stream));
+        if ((rc = mark_done(c, c->stream))) { unlock_all(); return rc; }
+        MULTI_TRY(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
+        MULTI_TRY(cudaEventRecord(done[g], c->stream));
+    }
+    MULTI_TRY(cudaSetDevice(0));
+    for (int g = 0; g < n_gpus; ++g) {
+        if (done[g]) MULTI_TRY(cudaStreamWaitEvent(cs[0]->stream, done[g], 0));
+    }
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, cs[0]->stream, (const xyzz *)cs[0]->partials.ptr, (u32)n_gpus, (affine *)cs[0]->d_out, (xyzz *)nullptr);
+    MULTI_TRY(cudaGetLastError());
+    MULTI_TRY(cudaMemcpyAsync(cs[0]->h_out, cs[0]->d_out, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, cs[0]->stream));
+    MULTI_TRY(cudaStreamSynchronize(cs[0]->stream));
+    memcpy(out_affine64, cs[0]->h_out, PLONKISH_CUDA_AFFINE_BYTES);
+    for (int g = 0; g < n_gpus; ++g) {
+        if (done[g]) { cudaSetDevice(g); cudaEventDestroy(done[g]); }
+    }
+    unlock_all();
+#undef MULTI_TRY
+    timer_report(n, t0);
+    return PLONKISH_CUDA_OK;
+}
+
+// ------------------------------------------------------------------ plan probe
+extern "C" int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint32_t out[8]) {
+    if (!out || n == 0 || n > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm_plan: bad argument");
+    Ctx *c = ctx_for(device);
+    const u32 sms = c ? (u32)c->sm_count : 148u;
+    MsmPlan p = pk_make_plan((u32)n, window_bits, sms);
+    out[0] = p.c; out[1] = p.W; out[2] = p.hi_bits; out[3] = p.lo_bits; out[4] = p.idx_bits;
+    out[5] = p.tile; out[6] = p.L; out[7] = p.nthreads1;
+    return PLONKISH_CUDA_OK;
+}
+
+// ------------------------------------------------------- synthetic known-dlog bases
+static const int SYNTH_RUN = 16;
+
+// k * G by double-and-add, k a 64-bit integer.
+__device__ xyzz mul_generator_u64(unsigned long long k) {
+    affine g;
+    g.x = fq_one();
+    g.y = fq_dbl(fq_one());
+    xyzz r = xyzz_identity();
+    for (int b = 63; b >= 0; --b) {
+        r = xyzz_double(r);
+        if ((k >> b) & 1ull) xyzz_madd(r, g.x, g.y);
+    }
+    return r;
+}
+
+__global__ void k_synth_step(affine *d_step, unsigned long long step) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d_step = xyzz_to_affine(mul_generator_u64(step));
+}
+
+// Thread t writes out[t*16 .. t*16+16): walks P += step*G and normalises its 16
+// points with one shared inversion (Montgomery's trick).
+__global__ void __launch_bounds__(128) k_synth_bases(affine *__restrict__ out, unsigned long long first, unsigned long long n,
+                                                     unsigned long long a, unsigned long long step, const affine *__restrict__ d_step) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long i0 = t * SYNTH_RUN;
+    if (i0 >= n) return;
+    const int cnt = (n - i0 < (unsigned long long)SYNTH_RUN) ? (int)(n - i0) : SYNTH_RUN;
+    const affine d = *d_step;
+    xyzz p = mul_generator_u64(a + (first + i0) * step);
+    xyzz pts[SYNTH_RUN];
+    fe prefix[SYNTH_RUN];
+    fe acc = fq_one();
+    for (int j = 0; j < cnt; ++j) {
+        pts[j] = p;
+        prefix[j] = acc;
+        if (!xyzz_is_identity(p)) acc = fq_mul(acc, fq_mul(p.zz, p.zzz));
+        xyzz_madd(p, d.x, d.y);
+    }
+    fe inv = fq_inv(acc);
+    for (int j = cnt - 1; j >= 0; --j) {
+        affine r;
+        if (xyzz_is_identity(pts[j])) {
+            r.x = fe_zero(); r.y = fe_zero();
+        } else {
+            const fe i = fq_mul(inv, prefix[j]);  // 1 / (zz*zzz)
+            inv = fq_mul(inv, fq_mul(pts[j].zz, pts[j].zzz));
+            r.x = fq_mul(pts[j].x, fq_mul(i, pts[j].zzz));
+            r.y = fq_mul(pts[j].y, fq_mul(i, pts[j].zz));
+        }
+        uint4 *q = reinterpret_cast<uint4 *>(out + i0 + j);
+        store_fe(q, r.x);
+        store_fe(q + 2, r.y);
+    }
+}
+
+extern "C" int plonkish_cuda_synth_bases_device(int device, void *d_out, size_t first, size_t n, uint64_t a, uint64_t step, void *cuda_stream) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "synth_bases: device %d not initialised", device);
+    if (!d_out || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "synth_bases: bad argument");
+    if (a >> 31 || step >> 31 || (first + n) >> 32) return fail(PLONKISH_CUDA_E_INVALID, "synth_bases: a, step < 2^31 and first + n < 2^32 required");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    affine *d_step = (affine *)((char *)c->d_out + 192);
+    PK_LAUNCH(k_synth_step, dim3(1), dim3(32), 0, stream, d_step, (unsigned long long)step);
+    const unsigned long long threads = (n + SYNTH_RUN - 1) / SYNTH_RUN;
+    PK_LAUNCH(k_synth_bases, dim3((unsigned)((threads + 127) / 128)), dim3(128), 0, stream, (affine *)d_out,
+              (unsigned long long)first, (unsigned long long)n, (unsigned long long)a, (unsigned long long)step, d_step);
+    CUDA_TRY(cudaGetLastError());
+    return PLONKISH_CUDA_OK;
+}
+
+// ------------------------------------------------------ integer-pipe microbenchmarks
+// 16 independent 64-bit accumulators per thread, each fed by mad.wide.u32: no
+// dependent chain shorter than 16 instructions, so the multiplier pipe is the limit.
+__global__ void __launch_bounds__(256) k_bench_imad_wide(unsigned long long *out, u32 iters, u32 seed) {
+    unsigned long long acc[16];
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = (unsigned long long)(a + k) << 7;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + (u32)k), "r"(b));
+        b += 0x9e3779b9u;
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s ^= acc[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Two independent Montgomery products per thread per iteration (the K3 instruction mix).
+__global__ void __launch_bounds__(256) k_bench_fq_mul(uint4 *out, u32 iters, u32 seed) {
+    fe x = fq_one(), y = fq_one(), z = fq_one();
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x; z.l[2] ^= seed;
+    x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu; z.l[7] &= 0x0fffffffu;
+    for (u32 it = 0; it < iters; ++it) {
+        x = fq_mul(x, z);
+        y = fq_mul(y, z);
+    }
+    fe r = fq_add(x, y);
+    store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), r);
+}
+
+extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[4]) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bench_integer_pipe: device %d not initialised", device);
+    if (!out) return fail(PLONKISH_CUDA_E_INVALID, "bench_integer_pipe: null output");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * threads * 32));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float ms = 0;
+    const u32 it_wide = 4096, it_mul = 256;
+    for (int rep = 0; rep < 3; ++rep) {  // last repetition is the one reported
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_imad_wide, dim3(blocks), dim3(threads), 0, c->stream, (unsigned long long *)scratch, it_wide, 17u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    out[0] = (double)blocks * threads * 16.0 * it_wide / (ms * 1e-3);
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_fq_mul, dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, it_mul, 29u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    out[1] = (double)blocks * threads * 2.0 * it_mul / (ms * 1e-3);
+    int clock_khz = 0;
+    cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, c->dev);
+    out[2] = clock_khz / 1000.0;  // the device's maximum SM clock; bench.py samples the live one
+    out[3] = c->sm_count;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
+}
+
+// ------------------------------------------------------------------ test hooks
+// Element-wise probes of the device arithmetic, so the parity tests can pin the PTX
+// carry chains and the group law element by element without going through an MSM.
+__global__ void k_debug_field(int op, const fe *a, const fe *b, fe *out, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe r;
+    switch (op) {
+        case 0: r = fq_mul(a[i], b[i]); break;
+        case 1: r = fq_add(a[i], b[i]); break;
+        case 2: r = fq_sub(a[i], b[i]); break;
+        case 3: r = fr_to_canonical(a[i]); break;
+        case 4: r = fq_inv(a[i]); break;
+        case 5: r = mont_mul<FrMod>(a[i], b[i]); break;
+        default: r = fq_neg(a[i]); break;
+    }
+    out[i] = r;
+}
+// op 0: out = xyzz(a) + affine(b); 1: out = xyzz(a) + xyzz(b); 2: out = 2*xyzz(a);
+// op 3: out[0..64) = to_affine(xyzz(a)).  a, b, out are arrays of 128-byte slots.
+__global__ void k_debug_point(int op, const xyzz *a, const xyzz *b, xyzz *out, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz r = a[i];
+    switch (op) {
+        case 0: xyzz_madd(r, b[i].x, b[i].y); break;
+        case 1: r = xyzz_add(a[i], b[i]); break;
+        case 2: r = xyzz_double(a[i]); break;
+        default: {
+            const affine q = xyzz_to_affine(a[i]);
+            r.x = q.x; r.y = q.y; r.zz = fe_zero(); r.zzz = fe_zero();
+        }
+    }
+    out[i] = r;
+}
+
+static int debug_run(int device, int op, bool point, const void *a, const void *b, void *out, size_t n) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "debug: device %d not initialised", device);
+    if (!a || !out || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "debug: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t elem = point ? sizeof(xyzz) : sizeof(fe);
+    void *da = nullptr, *db = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc(&da, n * elem));
+    CUDA_TRY(cudaMalloc(&db, n * elem));
+    CUDA_TRY(cudaMalloc(&dout, n * elem));
+    CUDA_TRY(cudaMemcpy(da, a, n * elem, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db, b ? b : a, n * elem, cudaMemcpyHostToDevice));
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (point) {
+        PK_LAUNCH(k_debug_point, dim3(blocks), dim3(128), 0, c->stream, op, (const xyzz *)da, (const xyzz *)db, (xyzz *)dout, (u32)n);
+    } else {
+        PK_LAUNCH(k_debug_field, dim3(blocks), dim3(128), 0, c->stream, op, (const fe *)da, (const fe *)db, (fe *)dout, (u32)n);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(out, dout, n * elem, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_debug_field_op(int device, int op, const void *a32, const void *b32, void *out32, size_t n) {
+    return debug_run(device, op, false, a32, b32, out32, n);
+}
+extern "C" int plonkish_cuda_debug_point_op(int device, int op, const void *a128, const void *b128, void *out128, size_t n) {
+    return debug_run(device, op, true, a128, b128, out128, n);
+}

@@ -28,7 +28,11 @@
 
 #ifndef PLONKISH_EMUL
 #include <cuda_runtime.h>
-#define PK_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#ifndef PK_COUNT_LAUNCH
+#define PK_COUNT_LAUNCH() ((void)0)
+#endif
+#define PK_LAUNCH(kern, grid, block, smem, stream, ...) \
+    do { PK_COUNT_LAUNCH(); kern<<<grid, block, smem, stream>>>(__VA_ARGS__); } while (0)
 #define PK_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type *name = reinterpret_cast<type *>(name##_raw)
 typedef cudaStream_t pk_stream_t;
 #else
@@ -58,7 +62,8 @@ struct MsmPlan {
     u32 tile;       // points per K1 block
     u32 ntiles;
     u32 L;          // run length per K3 thread
-    u32 nthreads1;  // K3 threads (multiple of 32)
+    u32 nthreads1;  // K3 threads (multiple of blk_acc)
+    u32 blk_acc;    // K3 block size: 128, or 32 when one warp covers everything
     u32 rb;         // buckets per K4 thread
     u32 red_threads;  // K4 threads per window
     u32 red_blocks;   // K4 blocks per window
@@ -115,6 +120,7 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     unsigned long long t1 = (emax + L - 1) / L;
     // one warp -> a 32-thread terminal launch; otherwise whole 128-thread blocks
     p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
+    p.blk_acc = (t1 <= 32) ? 32u : 128u;
     p.rb = p.B < 8 ? p.B : 8;
     p.red_threads = p.B / p.rb;
     p.red_blocks = (p.red_threads + 255) / 256;
@@ -136,6 +142,7 @@ struct MsmWorkspace {
     u32 *item_keys[2];  // ping-pong item lists for the segmented reduction levels
     xyzz *item_pts[2];
     xyzz *block_out;    // [W][red_blocks]
+    xyzz *win_out;      // [W] weighted window sums
     xyzz *result;       // [1] projective result of this launch sequence
 };
 
@@ -143,7 +150,7 @@ inline size_t pk_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 inline size_t pk_workspace_bytes(const MsmPlan &p) {
     size_t e = (size_t)p.n * p.W;
-    size_t items = (size_t)(p.nthreads1 / 32) * 2;
+    size_t items = (size_t)p.nthreads1 * 2;
     size_t s = 0;
     s += pk_align256(sizeof(u16) * (size_t)p.W * p.n_pad);
     s += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
@@ -156,6 +163,7 @@ inline size_t pk_workspace_bytes(const MsmPlan &p) {
     s += 2 * pk_align256(sizeof(u32) * items);
     s += 2 * pk_align256(sizeof(xyzz) * items);
     s += pk_align256(sizeof(xyzz) * (size_t)p.W * p.red_blocks);
+    s += pk_align256(sizeof(xyzz) * 32);
     s += pk_align256(sizeof(xyzz));
     return s;
 }
@@ -164,7 +172,7 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     MsmWorkspace w;
     unsigned char *q = (unsigned char *)arena;
     size_t e = (size_t)p.n * p.W;
-    size_t items = (size_t)(p.nthreads1 / 32) * 2;
+    size_t items = (size_t)p.nthreads1 * 2;
     w.digits = (u16 *)q; q += pk_align256(sizeof(u16) * (size_t)p.W * p.n_pad);
     w.tile_hist = (u32 *)q; q += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
     w.bin_total = (u32 *)q; q += pk_align256(sizeof(u32) * p.nbins);
@@ -176,6 +184,7 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     for (int k = 0; k < 2; ++k) { w.item_keys[k] = (u32 *)q; q += pk_align256(sizeof(u32) * items); }
     for (int k = 0; k < 2; ++k) { w.item_pts[k] = (xyzz *)q; q += pk_align256(sizeof(xyzz) * items); }
     w.block_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.W * p.red_blocks);
+    w.win_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * 32);
     w.result = (xyzz *)q;
     return w;
 }
@@ -450,15 +459,21 @@ PK_HD void warp_merge(u32 hk, xyzz hp, u32 tk, const xyzz &tp, xyzz *bucket_sum,
 }
 
 // ================================================================ K3 accumulate
-// Thread t sums sorted[t*L, (t+1)*L).  bucket_start[nbuckets] is the entry count.
-__global__ void __launch_bounds__(128) k_accumulate(const u32 *__restrict__ sorted, const u32 *__restrict__ bucket_start,
-                                                    const affine *__restrict__ bases, MsmPlan p, xyzz *__restrict__ bucket_sum,
-                                                    u32 *__restrict__ out_keys, xyzz *__restrict__ out_pts, int terminal) {
+// Thread t sums sorted[t*L, (t+1)*L) and leaves two items for the segmented
+// reduction: item 2t = (first key of the run, its sum), item 2t+1 = (last key, its
+// sum), the second being (same key, identity) when the run stays inside one bucket.
+// Buckets that begin and end inside the run are complete and stored directly.
+// bucket_start[nbuckets] is the entry count.  The kernel keeps only the running
+// XYZZ sum and one affine point live so that four warps fit per SM sub-partition.
+__global__ void __launch_bounds__(128, 4) k_accumulate(const u32 *__restrict__ sorted, const u32 *__restrict__ bucket_start,
+                                                       const affine *__restrict__ bases, MsmPlan p, xyzz *__restrict__ bucket_sum,
+                                                       u32 *__restrict__ out_keys, xyzz *__restrict__ out_pts) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 total = bucket_start[p.nbuckets];
     const unsigned long long s64 = (unsigned long long)t * p.L;
     u32 hk = PK_INVALID_KEY, tk = PK_INVALID_KEY;
-    xyzz hp = xyzz_identity(), acc = xyzz_identity();
+    xyzz acc = xyzz_identity();
+    bool head_written = false;
     if (s64 < total) {
         const u32 s = (u32)s64;
         const u32 e = (s + p.L < total) ? s + p.L : total;
@@ -470,11 +485,10 @@ __global__ void __launch_bounds__(128) k_accumulate(const u32 *__restrict__ sort
         }
         u32 g = lo;
         u32 next = bucket_start[g + 1];
-        u32 nflushed = 0;
+        hk = g;
         for (u32 pos = s; pos < e; ++pos) {
             if (pos == next) {
-                if (nflushed == 0) { hk = g; hp = acc; } else { store_xyzz(bucket_sum + g, acc); }
-                ++nflushed;
+                if (!head_written) { store_xyzz(out_pts + 2 * (size_t)t, acc); head_written = true; } else { store_xyzz(bucket_sum + g, acc); }
                 acc = xyzz_identity();
                 do { ++g; next = bucket_start[g + 1]; } while (next <= pos);
             }
@@ -485,9 +499,15 @@ __global__ void __launch_bounds__(128) k_accumulate(const u32 *__restrict__ sort
             if (entry >> 31) y = fq_neg(y);
             xyzz_madd(acc, x, y);
         }
-        if (nflushed == 0) { hk = g; hp = acc; tk = g; acc = xyzz_identity(); } else { tk = g; }
+        tk = g;
     }
-    warp_merge(hk, hp, tk, acc, bucket_sum, out_keys, out_pts, t >> 5, terminal != 0);
+    out_keys[2 * (size_t)t] = hk;
+    out_keys[2 * (size_t)t + 1] = tk;
+    if (!head_written) {
+        store_xyzz(out_pts + 2 * (size_t)t, acc);
+        acc = xyzz_identity();
+    }
+    store_xyzz(out_pts + 2 * (size_t)t + 1, acc);
 }
 
 // ======================================================= K3b item reduce levels
@@ -572,32 +592,25 @@ __global__ void __launch_bounds__(256) k_bucket_reduce(const xyzz *__restrict__ 
 }
 
 // ============================================================ K5 window combine
-// One block, one warp per window: S_w = sum of the window's block partials,
-// T_w = 2^(c*w) * S_w, result = sum_w T_w.  Optionally adds `prev` (the running
-// total of earlier chunks of the same MSM) before the result is stored.
-__global__ void __launch_bounds__(1024) k_window_combine(const xyzz *__restrict__ block_out, MsmPlan p, const xyzz *prev,
-                                                         xyzz *__restrict__ result) {
-    __shared__ xyzz win[32];
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+// One warp per window: S_w = sum of the window's block partials, T_w = 2^(c*w) * S_w.
+__global__ void __launch_bounds__(32) k_window_weight(const xyzz *__restrict__ block_out, MsmPlan p, xyzz *__restrict__ win_out) {
+    const u32 lane = threadIdx.x & 31u, w = blockIdx.x;
     xyzz v = xyzz_identity();
-    if (w < p.W) {
-        for (u32 k = lane; k < p.red_blocks; k += 32) v = xyzz_add(v, load_xyzz(block_out + (size_t)w * p.red_blocks + k));
-    }
+    for (u32 k = lane; k < p.red_blocks; k += 32) v = xyzz_add(v, load_xyzz(block_out + (size_t)w * p.red_blocks + k));
     v = warp_sum_xyzz(v);
     if (lane == 0) {
-        if (w < p.W) {
-            for (u32 k = 0; k < p.c * w; ++k) v = xyzz_double(v);
-        }
-        win[w] = v;
+        for (u32 k = 0; k < p.c * w; ++k) v = xyzz_double(v);
+        store_xyzz(win_out + w, v);
     }
-    __syncthreads();
-    if (w == 0) {
-        xyzz t = (lane < p.W) ? win[lane] : xyzz_identity();
-        t = warp_sum_xyzz(t);
-        if (lane == 0) {
-            if (prev) t = xyzz_add(t, load_xyzz(prev));
-            store_xyzz(result, t);
-        }
+}
+// result = sum_w T_w (+ *prev: the running total of earlier chunks of the same MSM).
+__global__ void __launch_bounds__(32) k_window_sum(const xyzz *__restrict__ win_out, u32 W, const xyzz *prev, xyzz *__restrict__ result) {
+    const u32 lane = threadIdx.x & 31u;
+    xyzz t = (lane < W) ? load_xyzz(win_out + lane) : xyzz_identity();
+    t = warp_sum_xyzz(t);
+    if (lane == 0) {
+        if (prev) t = xyzz_add(t, load_xyzz(prev));
+        store_xyzz(result, t);
     }
 }
 
@@ -621,11 +634,7 @@ template <int C>
 inline void pk_launch_decompose(const MsmPlan &p, const void *scalars, const MsmWorkspace &ws, pk_stream_t stream) {
     const size_t smem = sizeof(u32) * p.nbins;
 #ifndef PLONKISH_EMUL
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_decompose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_decompose<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
     PK_LAUNCH(k_decompose<C>, dim3(p.ntiles), dim3(p.blk), smem, stream, (const uint4 *)scalars, p, ws.digits, ws.tile_hist);
 }
@@ -650,18 +659,16 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
     PK_LAUNCH(k_scatter_bins, dim3(p.ntiles, p.W), dim3(p.blk), 0, stream, ws.digits, p, ws.tile_hist, ws.bin_start, ws.l1);
     PK_LAUNCH(k_sort_bins, dim3(p.nbins), dim3(p.blk), 0, stream, ws.l1, p, ws.bin_start, ws.sorted, ws.bucket_start);
 
-    // K3 + the item levels.
-    u32 warps = p.nthreads1 / 32;
-    int terminal = (warps == 1) ? 1 : 0;
-    PK_LAUNCH(k_accumulate, dim3(terminal ? 1 : p.nthreads1 / 128), dim3(terminal ? 32 : 128), 0, stream, ws.sorted,
-              ws.bucket_start, (const affine *)bases, p, ws.bucket_sum, ws.item_keys[0], ws.item_pts[0], terminal);
-    u32 count = 2 * warps;
+    // K3, then the item levels until one warp stores everything that is left.
+    PK_LAUNCH(k_accumulate, dim3(p.nthreads1 / p.blk_acc), dim3(p.blk_acc), 0, stream, ws.sorted, ws.bucket_start,
+              (const affine *)bases, p, ws.bucket_sum, ws.item_keys[0], ws.item_pts[0]);
+    u32 count = 2 * p.nthreads1;
     int src = 0;
-    while (!terminal) {
+    for (int terminal = 0; !terminal;) {
         const u32 K = (count > p.serial_items) ? 8 : 1;
         const u32 lanes = (count + K - 1) / K;
         const u32 nthreads = (lanes <= 32) ? 32u : ((lanes + 127u) & ~127u);
-        warps = nthreads / 32;
+        const u32 warps = nthreads / 32;
         terminal = (warps == 1) ? 1 : 0;
         PK_LAUNCH(k_reduce_items, dim3(terminal ? 1 : nthreads / 128), dim3(terminal ? 32 : 128), 0, stream, ws.item_keys[src], ws.item_pts[src], count, K,
                   ws.bucket_sum, ws.item_keys[src ^ 1], ws.item_pts[src ^ 1], terminal);
@@ -669,7 +676,8 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
         src ^= 1;
     }
     PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.W), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
-    PK_LAUNCH(k_window_combine, dim3(1), dim3(1024), 0, stream, ws.block_out, p, prev, ws.result);
+    PK_LAUNCH(k_window_weight, dim3(p.W), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
+    PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.W, prev, ws.result);
 }
 
 }  // namespace pk

@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's MSM interface, over the C ABI.
+
+Mirrors ``plonkish_backend::util::arithmetic::variable_base_msm``
+(/root/reference/plonkish_backend/src/util/arithmetic/msm.rs:84-115): same
+argument meaning (scalars, bases of equal length), same error behaviour for a
+length mismatch (the reference's ``assert_eq!`` at msm.rs:90 -> AssertionError),
+and the affine value the reference's callers take with ``.into()`` /
+``.to_affine()`` (pcs/multilinear/kzg.rs:255).
+
+Array conventions (the bytes that cross the ABI, see include/plonkish_cuda.h):
+  scalars  uint64 [n, 4]  bn256::Fr, Montgomery form, little-endian limbs
+  bases    uint64 [n, 8]  bn256::G1Affine x||y (Montgomery Fq), (0,0) = identity
+  result   uint64 [8]     G1Affine
+Everything is computed on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+SCALAR_BYTES = 32
+AFFINE_BYTES = 64
+XYZZ_BYTES = 128
+
+
+def _as_u64(a, width: int, what: str) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.uint64)
+    if arr.ndim == 1 and arr.size % width == 0:
+        arr = arr.reshape(-1, width)
+    if arr.ndim != 2 or arr.shape[1] != width:
+        raise ValueError(f"{what} must have shape [n, {width}] of uint64 limbs, got {arr.shape}")
+    return arr
+
+
+class G1Bases:
+    """Bases resident on one GPU (the SRS slice a ProverParam holds:
+    MultilinearKzgProverParam.eqs[k], pcs/multilinear/kzg.rs:55-77;
+    UnivariateKzgProverParam.powers_of_s_g1, pcs/univariate/kzg.rs:24-30)."""
+
+    def __init__(self, bases, device: int = 0):
+        arr = _as_u64(bases, 8, "bases")
+        self.n = arr.shape[0]
+        self.device = device
+        handle = ctypes.c_uint64(0)
+        _lib.check(
+            _lib.lib().plonkish_cuda_bases_register(device, arr.ctypes.data, self.n, ctypes.byref(handle)),
+            "plonkish_cuda_bases_register",
+        )
+        self.handle = handle.value
+
+    def __len__(self) -> int:
+        return self.n
+
+    def release(self) -> None:
+        if self.handle:
+            _lib.check(_lib.lib().plonkish_cuda_bases_release(self.handle), "plonkish_cuda_bases_release")
+            self.handle = 0
+
+
+class ShardedG1Bases:
+    """Bases split across n_gpus devices the way msm.rs:101-107 chunks them."""
+
+    def __init__(self, bases, n_gpus: int):
+        arr = _as_u64(bases, 8, "bases")
+        self.n = arr.shape[0]
+        self.n_gpus = n_gpus
+        handle = ctypes.c_uint64(0)
+        _lib.check(
+            _lib.lib().plonkish_cuda_bases_register_sharded(n_gpus, arr.ctypes.data, self.n, ctypes.byref(handle)),
+            "plonkish_cuda_bases_register_sharded",
+        )
+        self.handle = handle.value
+
+    def release(self) -> None:
+        if self.handle:
+            _lib.check(_lib.lib().plonkish_cuda_bases_release(self.handle), "plonkish_cuda_bases_release")
+            self.handle = 0
+
+
+def variable_base_msm(scalars, bases, n_gpus: int = 1) -> np.ndarray:
+    """sum_i scalars[i] * bases[i] on the GPU; returns the affine point, uint64[8].
+
+    `bases` is an [n, 8] array, a G1Bases / ShardedG1Bases, or — like the
+    reference's iterator-of-references callers (pcs/univariate/kzg.rs:346) — a
+    sequence of separate 8-limb arrays, in which case `scalars` must be a sequence
+    of 4-limb arrays too and the gather entry point is used.
+    """
+    lib = _lib.lib()
+    out = np.zeros(8, dtype=np.uint64)
+    if isinstance(bases, (G1Bases, ShardedG1Bases)):
+        sc = _as_u64(scalars, 4, "scalars")
+        assert sc.shape[0] <= bases.n, "more scalars than registered bases"  # msm.rs:90
+        if isinstance(bases, ShardedG1Bases):
+            assert sc.shape[0] == bases.n, "scalars and sharded bases differ in length"  # msm.rs:90
+            rc = lib.plonkish_cuda_msm_bn254_g1_multi(bases.n_gpus, sc.ctypes.data, None, bases.handle, sc.shape[0], out.ctypes.data)
+            _lib.check(rc, "plonkish_cuda_msm_bn254_g1_multi")
+        else:
+            rc = lib.plonkish_cuda_msm_bn254_g1(sc.ctypes.data, None, bases.handle, sc.shape[0], out.ctypes.data)
+            _lib.check(rc, "plonkish_cuda_msm_bn254_g1")
+        return out
+    if isinstance(bases, (list, tuple)) and not isinstance(scalars, np.ndarray):
+        return _variable_base_msm_gather(scalars, bases)
+    sc = _as_u64(scalars, 4, "scalars")
+    bs = _as_u64(bases, 8, "bases")
+    assert sc.shape[0] == bs.shape[0], "scalars and bases differ in length"  # msm.rs:90
+    if n_gpus > 1:
+        rc = lib.plonkish_cuda_msm_bn254_g1_multi(n_gpus, sc.ctypes.data, bs.ctypes.data, 0, sc.shape[0], out.ctypes.data)
+        _lib.check(rc, "plonkish_cuda_msm_bn254_g1_multi")
+    else:
+        rc = lib.plonkish_cuda_msm_bn254_g1(sc.ctypes.data, bs.ctypes.data, 0, sc.shape[0], out.ctypes.data)
+        _lib.check(rc, "plonkish_cuda_msm_bn254_g1")
+    return out
+
+
+def _variable_base_msm_gather(scalars: Sequence, bases: Sequence) -> np.ndarray:
+    assert len(scalars) == len(bases), "scalars and bases differ in length"  # msm.rs:90
+    n = len(scalars)
+    keep_s = [np.ascontiguousarray(s, dtype=np.uint64).reshape(4) for s in scalars]
+    keep_b = [np.ascontiguousarray(b, dtype=np.uint64).reshape(8) for b in bases]
+    sp = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in keep_s])
+    bp = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data for a in keep_b])
+    out = np.zeros(8, dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_gather(sp, bp, n, out.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_gather")
+    return out
+
+
+# ------------------------------------------------------------ device-resident API
+def _torch():
+    import torch
+
+    return torch
+
+
+def variable_base_msm_device(scalars, bases, out=None, *, window_bits: int = 0, partial: bool = False):
+    """Device-resident MSM on torch CUDA tensors, enqueued on the current stream.
+
+    scalars: [n, 4] int64/uint64 CUDA tensor (raw limbs), bases: [n, 8].  Returns a
+    CUDA tensor holding the affine point ([8] limbs), or with partial=True the
+    projective XYZZ partial ([16] limbs) a rank contributes before the gather.
+    """
+    torch = _torch()
+    assert scalars.is_cuda and bases.is_cuda and scalars.is_contiguous() and bases.is_contiguous()
+    n = scalars.numel() * scalars.element_size() // SCALAR_BYTES
+    assert bases.numel() * bases.element_size() // AFFINE_BYTES >= n, "fewer bases than scalars"  # msm.rs:90
+    dev = scalars.device.index if scalars.device.index is not None else torch.cuda.current_device()
+    words = 16 if partial else 8
+    if out is None:
+        out = torch.empty(words, dtype=torch.int64, device=scalars.device)
+    stream = torch.cuda.current_stream(scalars.device).cuda_stream
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_device(
+        dev, scalars.data_ptr(), bases.data_ptr(), n, window_bits,
+        None if partial else out.data_ptr(), out.data_ptr() if partial else None, stream,
+    )
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_device")
+    return out
+
+
+def sum_partials_device(partials, out=None):
+    """Adds [k, 16]-limb projective partials and normalises to an affine [8] tensor."""
+    torch = _torch()
+    assert partials.is_cuda and partials.is_contiguous()
+    count = partials.numel() * partials.element_size() // XYZZ_BYTES
+    dev = partials.device.index if partials.device.index is not None else torch.cuda.current_device()
+    if out is None:
+        out = torch.empty(8, dtype=torch.int64, device=partials.device)
+    stream = torch.cuda.current_stream(partials.device).cuda_stream
+    rc = _lib.lib().plonkish_cuda_g1_sum_partials_device(dev, partials.data_ptr(), count, out.data_ptr(), stream)
+    _lib.check(rc, "plonkish_cuda_g1_sum_partials_device")
+    return out
+
+
+def synth_bases_device(n: int, a: int, step: int, device=None, first: int = 0):
+    """bases[i] = (a + (first + i)*step) * G on the GPU -> [n, 8] int64 CUDA tensor."""
+    torch = _torch()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((n, 8), dtype=torch.int64, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    rc = _lib.lib().plonkish_cuda_synth_bases_device(device.index or 0, out.data_ptr(), first, n, a, step, stream)
+    _lib.check(rc, "plonkish_cuda_synth_bases_device")
+    return out
+
+
+def msm_plan(n: int, window_bits: int = 0, device: int = 0) -> dict:
+    out = (ctypes.c_uint32 * 8)()
+    _lib.check(_lib.lib().plonkish_cuda_msm_plan(device, n, window_bits, out), "plonkish_cuda_msm_plan")
+    keys = ("window_bits", "windows", "hi_bits", "lo_bits", "idx_bits", "tile", "run_length", "accumulate_threads")
+    return dict(zip(keys, [int(v) for v in out]))
+
+
+def launch_count() -> int:
+    return int(_lib.load().plonkish_cuda_launch_count())
+
+
+def bench_integer_pipe(device: int = 0) -> dict:
+    out = (ctypes.c_double * 4)()
+    _lib.check(_lib.lib().plonkish_cuda_bench_integer_pipe(device, out), "plonkish_cuda_bench_integer_pipe")
+    return {"imad_wide_per_s": out[0], "fq_mul_per_s": out[1], "sm_max_mhz": out[2], "sm_count": int(out[3])}
+
+
+def random_scalars(n: int, seed: int) -> np.ndarray:
+    """Synthetic Fr elements (Montgomery limbs): three uniform u64 limbs and a top
+    limb drawn below r's top limb, so every value is a valid representation < r."""
+    rng = np.random.default_rng(seed)
+    out = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] = rng.integers(0, 0x30644E72E131A029, size=n, dtype=np.uint64)
+    return out

@@ -1,0 +1,106 @@
+"""CPU suite: the product's kernel sources (plonkish_b200/csrc/*.cuh) compiled by
+g++ against tests/emul/cuda_emul.h and run thread-for-thread on the CPU, compared
+with the oracle.  This checks the kernels' logic (signed-digit recoding, the two
+counting-sort levels, run partitioning, warp segmented reduction, bucket reduce)
+without a GPU; the PTX carry chains themselves are pinned by the -m gpu tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, case_arrays
+from oracle import bigint_ref as br
+
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-C", EMUL_DIR], check=True, capture_output=True)
+    lib = ctypes.CDLL(os.path.join(EMUL_DIR, "libemul_msm.so"))
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    lib.emul_msm.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp, vp]
+    lib.emul_fq_mul.argtypes = [vp, vp, vp]
+    lib.emul_fr_to_canonical.argtypes = [vp, vp]
+    lib.emul_plan.argtypes = [u32, u32, u32, vp]
+
+    def msm(sc, bs, c=0, sms=148, serial_items=0):
+        sc = np.ascontiguousarray(sc, dtype=np.uint64)
+        bs = np.ascontiguousarray(bs, dtype=np.uint64)
+        out = np.zeros(8, dtype=np.uint64)
+        lib.emul_msm(sc.ctypes.data, bs.ctypes.data, sc.shape[0], c, sms, serial_items, out.ctypes.data, None, None, None)
+        return out
+
+    lib.msm = msm
+    return lib
+
+
+def _mont(vals):
+    return np.array([np.frombuffer(br.scalar_to_bytes(v), dtype=np.uint64) for v in vals])
+
+
+def test_field_restatement(emul):
+    rng = np.random.default_rng(5)
+    rinv = pow(br.MONT, -1, br.P)
+    vals = [0, 1, br.P - 1, br.P - 2] + [int.from_bytes(rng.bytes(32), "little") % br.P for _ in range(40)]
+    for a in vals:
+        for b in vals[:10]:
+            la = np.frombuffer(a.to_bytes(32, "little"), dtype=np.uint32).copy()
+            lb = np.frombuffer(b.to_bytes(32, "little"), dtype=np.uint32).copy()
+            out = np.zeros(8, dtype=np.uint32)
+            emul.emul_fq_mul(la.ctypes.data, lb.ctypes.data, out.ctypes.data)
+            assert int.from_bytes(out.tobytes(), "little") == a * b * rinv % br.P
+    for v in [0, 1, br.R - 1] + [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(20)]:
+        la = np.frombuffer(br.scalar_to_bytes(v), dtype=np.uint32).copy()
+        out = np.zeros(8, dtype=np.uint32)
+        emul.emul_fr_to_canonical(la.ctypes.data, out.ctypes.data)
+        assert int.from_bytes(out.tobytes(), "little") == v
+
+
+def test_plan_invariants(emul):
+    out = np.zeros(8, dtype=np.uint32)
+    for n in (1, 2, 100, 1 << 10, 1 << 16, 1 << 20, 1 << 24, 1 << 26):
+        for c in (0, 8, 11, 16):
+            emul.emul_plan(n, c, 148, out.ctypes.data)
+            cc, w, hi, lo, idx, tile, run, threads = [int(v) for v in out]
+            assert 8 <= cc <= 16 and cc * w >= 255 and hi + lo == cc - 1
+            assert lo + 1 + idx <= 32 and lo <= 7 and hi <= 10 and (1 << idx) >= n
+            assert tile % 8 == 0 and -(-n // tile) <= 1024
+            assert threads * run >= n * w and threads % 32 == 0
+
+
+def test_golden_vectors(emul, golden):
+    for case in golden["cases"]:
+        sc, bs, want = case_arrays(case)
+        assert emul.msm(sc, bs, 8).tobytes() == want.tobytes(), case["name"]
+    sc, bs, want = case_arrays(golden["cases"][5])
+    assert emul.msm(sc, bs, 16, 1).tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("n,c,sms,serial", [(1, 8, 148, 0), (257, 10, 148, 0), (3000, 12, 2, 0), (2000, 16, 1, 0), (5000, 13, 1, 16)])
+def test_uniform_scalars(emul, oracle, n, c, sms, serial):
+    sc = oracle.random_scalars(n, n)
+    bs = oracle.known_dlog_bases(3, 5, n)
+    assert (emul.msm(sc, bs, c, sms, serial) == oracle.known_dlog_answer(3, 5, sc)).all()
+
+
+def test_skewed_and_degenerate_inputs(emul, oracle):
+    n = 600
+    rng = np.random.default_rng(0)
+    bs = oracle.known_dlog_bases(9, 2, n)
+    for name, vals, c, sms in [
+        ("all-zero", [0] * n, 8, 148),
+        ("all-minus-one", [br.R - 1] * n, 9, 1),
+        ("selector", [[0, 1, br.R - 1][int(x)] for x in rng.integers(0, 3, n)], 10, 2),
+        ("same-wide-value", [0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF123456789 % br.R] * n, 12, 1),
+    ]:
+        sc = _mont(vals)
+        assert (emul.msm(sc, bs, c, sms) == oracle.variable_base_msm(sc, bs, 2)).all(), name
+    dup = np.repeat(bs[:1], 300, axis=0)
+    sc = oracle.random_scalars(300, 3)
+    assert (emul.msm(sc, dup, 9, 1) == oracle.variable_base_msm(sc, dup, 2)).all()
+    idb = bs[:300].copy()
+    idb[::3] = 0
+    assert (emul.msm(sc, idb, 10, 1) == oracle.variable_base_msm(sc, idb, 2)).all()
