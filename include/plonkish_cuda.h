@@ -53,7 +53,7 @@ extern "C" {
  * n_devices CUDA devices; n_devices <= 0 means all visible devices.  Idempotent.
  * Replaces nothing in the reference (rayon's pool is implicit, util/parallel.rs:1-7). */
 int plonkish_cuda_init(int n_devices);
-int plonkish_cuda_device_count(void); /* contexts created by init, or a negative error */
+int plonkish_cuda_device_count(void); /* devices made available by init (contexts are created on first use) */
 void plonkish_cuda_shutdown(void);
 const char *plonkish_cuda_last_error(void);
 
@@ -92,7 +92,8 @@ int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars_mont32, con
 
 /* ---- device-resident entry points (no host copies, stream-ordered) ---------------------
  * d_scalars / d_bases are device pointers on `device`; the call only enqueues work on
- * `cuda_stream` (a cudaStream_t; NULL = the context's own stream) and returns.
+ * `cuda_stream` (a cudaStream_t; NULL = the legacy default stream, as everywhere in the
+ * CUDA runtime) and returns.
  * window_bits = 0 picks the default for n, 8..16 forces it.  Either output may be NULL:
  * d_out_affine64 receives the normalised point, d_out_xyzz128 the projective partial
  * (what one rank contributes before the multi-GPU gather). */
@@ -112,14 +113,23 @@ int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials_xyzz
  * number of accumulate threads. */
 int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint32_t out[8]);
 
+/* One synchronous MSM on the context stream with CUDA events between the stages;
+ * stage_ms[0..9) = decompose, scans, bin scatter, bin sort, accumulate, item levels,
+ * bucket reduce, window combine, finalize (to_affine).  d_out_affine64 may be NULL. */
+int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const void *d_bases, size_t n, uint32_t window_bits,
+                                     void *d_out_affine64, double stage_ms[9]);
+
 /* Kernels launched by the library in this process since init (for bench accounting). */
 uint64_t plonkish_cuda_launch_count(void);
 
 /* Integer-pipe microbenchmarks on `device` (CUDA-event timed):
  *   out[0] = independent mad.wide.u32 (IMAD.WIDE.U32) per second, all SMs busy
  *   out[1] = 254-bit Montgomery products per second from the library's own fq_mul
- *   out[2] = the device's maximum SM clock in MHz, out[3] = SM count             */
-int plonkish_cuda_bench_integer_pipe(int device, double out[4]);
+ *   out[2] = the device's maximum SM clock in MHz, out[3] = SM count
+ *   out[4] = independent 32-bit mad.lo.u32 (IMAD) per second
+ *   out[5] = wide multiply-adds per second inside mad.lo.cc/madc.hi.cc carry chains
+ *            (IMAD.WIDE.U32.X, the instruction the Montgomery products are built from) */
+int plonkish_cuda_bench_integer_pipe(int device, double out[6]);
 
 /* Synthetic bases with a known discrete log: d_out[i] = (a + i*step) * G for
  * i in [first, first + n), affine, written on the device.  Used by bench.py and the

@@ -13,6 +13,7 @@ from .msm import (  # noqa: F401
     sum_partials_device,
     synth_bases_device,
     msm_plan,
+    profile_stages_device,
     launch_count,
     bench_integer_pipe,
     random_scalars,

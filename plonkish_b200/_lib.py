@@ -27,6 +27,7 @@ EXPORTS = (
     "plonkish_cuda_msm_bn254_g1_device",
     "plonkish_cuda_g1_sum_partials_device",
     "plonkish_cuda_msm_plan",
+    "plonkish_cuda_msm_profile_device",
     "plonkish_cuda_launch_count",
     "plonkish_cuda_bench_integer_pipe",
     "plonkish_cuda_synth_bases_device",
@@ -70,6 +71,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_device.argtypes = [ci, vp, vp, sz, u32, vp, vp, vp]
     lib.plonkish_cuda_g1_sum_partials_device.argtypes = [ci, vp, sz, vp, vp]
     lib.plonkish_cuda_msm_plan.argtypes = [ci, sz, u32, ctypes.POINTER(u32)]
+    lib.plonkish_cuda_msm_profile_device.argtypes = [ci, vp, vp, sz, u32, vp, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_launch_count.argtypes = []
     lib.plonkish_cuda_launch_count.restype = u64
     lib.plonkish_cuda_bench_integer_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]

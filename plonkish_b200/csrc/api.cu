@@ -95,9 +95,29 @@ static int grow(DeviceBuffer &b, size_t bytes) {
     return 0;
 }
 
+// Contexts are created on first use of a device, so a one-process-per-GPU rank only
+// ever touches its own GPU.  Caller must not hold g_mu.
+static int create_ctx_locked(int device) {
+    Ctx *c = new Ctx();
+    c->dev = device;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(PLONKISH_CUDA_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&c->d_out, 512));
+    CUDA_TRY(cudaMallocHost(&c->h_out, 256));
+    g_ctx[device] = c;
+    return PLONKISH_CUDA_OK;
+}
+
 static Ctx *ctx_for(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (device < 0 || (size_t)device >= g_ctx.size()) return nullptr;
+    if (!g_ctx[device] && create_ctx_locked(device) != PLONKISH_CUDA_OK) return nullptr;
     return g_ctx[device];
 }
 
@@ -108,32 +128,22 @@ extern "C" int plonkish_cuda_init(int n_devices) {
     if (err != cudaSuccess || visible == 0)
         return fail(PLONKISH_CUDA_E_NO_DEVICE, "no CUDA device: %s", err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
     if (n_devices <= 0 || n_devices > visible) n_devices = visible;
-    while ((int)g_ctx.size() < n_devices) {
-        Ctx *c = new Ctx();
-        c->dev = (int)g_ctx.size();
-        CUDA_TRY(cudaSetDevice(c->dev));
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, c->dev));
-        if (prop.major < 10)
-            return fail(PLONKISH_CUDA_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", c->dev, prop.major, prop.minor);
-        c->sm_count = prop.multiProcessorCount;
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
-        CUDA_TRY(cudaMalloc(&c->d_out, 512));
-        CUDA_TRY(cudaMallocHost(&c->h_out, 256));
-        g_ctx.push_back(c);
-    }
-    // Direct NVLink peer copies for the multi-GPU partial gather (ignored where unsupported).
-    for (int a = 0; a < (int)g_ctx.size(); ++a) {
-        for (int b = 0; b < (int)g_ctx.size(); ++b) {
+    if ((int)g_ctx.size() < n_devices) g_ctx.resize(n_devices, nullptr);
+    return PLONKISH_CUDA_OK;
+}
+
+static std::atomic<bool> g_peers_enabled{false};
+// Direct NVLink peer copies for the single-process multi-GPU gather (ignored where unsupported).
+static void enable_peer_access(int n_gpus) {
+    if (g_peers_enabled.exchange(true)) return;
+    for (int a = 0; a < n_gpus; ++a) {
+        for (int b = 0; b < n_gpus; ++b) {
             int can = 0;
             if (a == b || cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) continue;
             cudaSetDevice(a);
             if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
         }
     }
-    cudaSetDevice(0);
-    return PLONKISH_CUDA_OK;
 }
 
 extern "C" int plonkish_cuda_device_count(void) {
@@ -151,6 +161,7 @@ extern "C" void plonkish_cuda_shutdown(void) {
     }
     g_bases.clear();
     for (Ctx *c : g_ctx) {
+        if (!c) continue;
         cudaSetDevice(c->dev);
         cudaDeviceSynchronize();
         cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
@@ -295,7 +306,7 @@ extern "C" int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scala
     if (window_bits && (window_bits < 8 || window_bits > 16)) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: window_bits must be 0 or 8..16");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
-    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream, as in the CUDA runtime
     if (n == 0) {
         if (d_out_affine64) CUDA_TRY(cudaMemsetAsync(d_out_affine64, 0, PLONKISH_CUDA_AFFINE_BYTES, stream));
         if (d_out_xyzz128) CUDA_TRY(cudaMemsetAsync(d_out_xyzz128, 0, PLONKISH_CUDA_XYZZ_BYTES, stream));
@@ -315,7 +326,7 @@ extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_pa
     if (!d_partials || !d_out_affine64 || count == 0) return fail(PLONKISH_CUDA_E_INVALID, "sum_partials: bad argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
-    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream, as in the CUDA runtime
     PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, stream, (const xyzz *)d_partials, (u32)count, (affine *)d_out_affine64, (xyzz *)nullptr);
     CUDA_TRY(cudaGetLastError());
     return PLONKISH_CUDA_OK;
@@ -400,7 +411,11 @@ extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars,
     }
     const size_t per = (n + n_gpus - 1) / n_gpus;  // msm.rs:101
     std::vector<Ctx *> cs(n_gpus);
-    for (int g = 0; g < n_gpus; ++g) cs[g] = ctx_for(g);
+    for (int g = 0; g < n_gpus; ++g) {
+        cs[g] = ctx_for(g);
+        if (!cs[g]) return PLONKISH_CUDA_E_NO_DEVICE;
+    }
+    enable_peer_access(n_gpus);
     for (int g = 0; g < n_gpus; ++g) cs[g]->mu.lock();
     int rc = PLONKISH_CUDA_OK;
     auto unlock_all = [&] { for (int g = n_gpus - 1; g >= 0; --g) cs[g]->mu.unlock(); };
@@ -452,6 +467,41 @@ extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars,
     unlock_all();
 #undef MULTI_TRY
     timer_report(n, t0);
+    return PLONKISH_CUDA_OK;
+}
+
+// ------------------------------------------------------------ per-stage timing
+extern "C" int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const void *d_bases, size_t n, uint32_t window_bits,
+                                                void *d_out_affine64, double stage_ms[9]) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_profile: device %d not initialised", device);
+    if (!d_scalars || !d_bases || !stage_ms || n == 0 || n > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm_profile: bad argument");
+    if (window_bits && (window_bits < 8 || window_bits > 16)) return fail(PLONKISH_CUDA_E_INVALID, "msm_profile: window_bits must be 0 or 8..16");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    MsmPlan plan = pk_make_plan((u32)n, window_bits, (u32)c->sm_count);
+    int rc = grow(c->arena, pk_workspace_bytes(plan));
+    if (rc) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
+    ws.result = (xyzz *)((char *)c->d_out + 256);
+    StageMarks marks;
+    cudaEvent_t ev[10];
+    for (int i = 0; i < 10; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < 9; ++i) marks.ev[i] = ev[i];
+    pk_enqueue_msm(plan, d_scalars, d_bases, ws, nullptr, c->stream, &marks);
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, ws.result, 1u, (affine *)(d_out_affine64 ? d_out_affine64 : c->d_out), (xyzz *)nullptr);
+    CUDA_TRY(cudaEventRecord(ev[9], c->stream));
+    CUDA_TRY(cudaGetLastError());
+    rc = mark_done(c, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 9; ++i) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        stage_ms[i] = ms;
+    }
+    for (int i = 0; i < 10; ++i) cudaEventDestroy(ev[i]);
     return PLONKISH_CUDA_OK;
 }
 
@@ -529,7 +579,7 @@ extern "C" int plonkish_cuda_synth_bases_device(int device, void *d_out, size_t 
     if (a >> 31 || step >> 31 || (first + n) >> 32) return fail(PLONKISH_CUDA_E_INVALID, "synth_bases: a, step < 2^31 and first + n < 2^32 required");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
-    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream, as in the CUDA runtime
     affine *d_step = (affine *)((char *)c->d_out + 192);
     PK_LAUNCH(k_synth_step, dim3(1), dim3(32), 0, stream, d_step, (unsigned long long)step);
     const unsigned long long threads = (n + SYNTH_RUN - 1) / SYNTH_RUN;
@@ -559,6 +609,46 @@ __global__ void __launch_bounds__(256) k_bench_imad_wide(unsigned long long *out
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// 16 independent 32-bit accumulators fed by mad.lo.u32 (plain IMAD).
+__global__ void __launch_bounds__(256) k_bench_imad32(u32 *out, u32 iters, u32 seed) {
+    u32 acc[16];
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = a + k;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(a));
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s ^= acc[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Four independent 8-word accumulators fed by the library's own carry-chain block
+// (cmad8: mad.lo.cc / madc.hi.cc pairs -> IMAD.WIDE.U32.X), the exact instruction
+// K3's Montgomery products are made of.  4 wide multiply-adds per cmad8.
+__global__ void __launch_bounds__(256) k_bench_chain(u32 *out, u32 iters, u32 seed) {
+    u32 acc[4][8];
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j][k] = a + 8 * j + k;
+    u32 carries = 0;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) carries += cmad8(acc[j], a + j, a ^ 0x55u, b + j, b ^ 0xaau, b);
+        b += 0x9e3779b9u;
+    }
+    u32 s = carries;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s ^= acc[j][k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // Two independent Montgomery products per thread per iteration (the K3 instruction mix).
 __global__ void __launch_bounds__(256) k_bench_fq_mul(uint4 *out, u32 iters, u32 seed) {
     fe x = fq_one(), y = fq_one(), z = fq_one();
@@ -572,7 +662,7 @@ __global__ void __launch_bounds__(256) k_bench_fq_mul(uint4 *out, u32 iters, u32
     store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), r);
 }
 
-extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[4]) {
+extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[6]) {
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bench_integer_pipe: device %d not initialised", device);
     if (!out) return fail(PLONKISH_CUDA_E_INVALID, "bench_integer_pipe: null output");
@@ -602,6 +692,22 @@ extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[4]) {
         CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     }
     out[1] = (double)blocks * threads * 2.0 * it_mul / (ms * 1e-3);
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_imad32, dim3(blocks), dim3(threads), 0, c->stream, (u32 *)scratch, it_wide, 31u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    out[4] = (double)blocks * threads * 16.0 * it_wide / (ms * 1e-3);
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_chain, dim3(blocks), dim3(threads), 0, c->stream, (u32 *)scratch, it_wide, 37u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    out[5] = (double)blocks * threads * 16.0 * it_wide / (ms * 1e-3);
     int clock_khz = 0;
     cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, c->dev);
     out[2] = clock_khz / 1000.0;  // the device's maximum SM clock; bench.py samples the live one

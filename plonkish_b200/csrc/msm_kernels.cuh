@@ -35,7 +35,9 @@
     do { PK_COUNT_LAUNCH(); kern<<<grid, block, smem, stream>>>(__VA_ARGS__); } while (0)
 #define PK_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type *name = reinterpret_cast<type *>(name##_raw)
 typedef cudaStream_t pk_stream_t;
+#define PK_MARK(marks, i, stream) do { if (marks) cudaEventRecord((cudaEvent_t)(marks)->ev[i], stream); } while (0)
 #else
+#define PK_MARK(marks, i, stream) ((void)0)
 #define PK_LAUNCH(kern, grid, block, smem, stream, ...) emul::launch(grid, block, smem, [&] { kern(__VA_ARGS__); })
 #define PK_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emul::g_dyn_smem)
 typedef int pk_stream_t;
@@ -639,10 +641,18 @@ inline void pk_launch_decompose(const MsmPlan &p, const void *scalars, const Msm
     PK_LAUNCH(k_decompose<C>, dim3(p.ntiles), dim3(p.blk), smem, stream, (const uint4 *)scalars, p, ws.digits, ws.tile_hist);
 }
 
+// Optional stage boundaries for the profiling entry point: ev[0] before K1, then one
+// event after decompose, scans, scatter, sort, accumulate, item levels, bucket
+// reduce, window combine (9 events).
+struct StageMarks {
+    void *ev[9];
+};
+
 // Enqueues one MSM over p.n points; the projective result lands in ws.result
 // (plus *prev if given).  No host synchronisation.
 inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *bases, const MsmWorkspace &ws, const xyzz *prev,
-                           pk_stream_t stream) {
+                           pk_stream_t stream, const StageMarks *marks = nullptr) {
+    PK_MARK(marks, 0, stream);
     switch (p.c) {
         case 8: pk_launch_decompose<8>(p, scalars, ws, stream); break;
         case 9: pk_launch_decompose<9>(p, scalars, ws, stream); break;
@@ -654,14 +664,19 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
         case 15: pk_launch_decompose<15>(p, scalars, ws, stream); break;
         default: pk_launch_decompose<16>(p, scalars, ws, stream); break;
     }
+    PK_MARK(marks, 1, stream);
     PK_LAUNCH(k_scan_tiles, dim3((p.nbins + p.blk - 1) / p.blk), dim3(p.blk), 0, stream, ws.tile_hist, p.ntiles, p.nbins, ws.bin_total);
     PK_LAUNCH(k_scan_bins, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.nbins, ws.bin_start);
+    PK_MARK(marks, 2, stream);
     PK_LAUNCH(k_scatter_bins, dim3(p.ntiles, p.W), dim3(p.blk), 0, stream, ws.digits, p, ws.tile_hist, ws.bin_start, ws.l1);
+    PK_MARK(marks, 3, stream);
     PK_LAUNCH(k_sort_bins, dim3(p.nbins), dim3(p.blk), 0, stream, ws.l1, p, ws.bin_start, ws.sorted, ws.bucket_start);
+    PK_MARK(marks, 4, stream);
 
     // K3, then the item levels until one warp stores everything that is left.
     PK_LAUNCH(k_accumulate, dim3(p.nthreads1 / p.blk_acc), dim3(p.blk_acc), 0, stream, ws.sorted, ws.bucket_start,
               (const affine *)bases, p, ws.bucket_sum, ws.item_keys[0], ws.item_pts[0]);
+    PK_MARK(marks, 5, stream);
     u32 count = 2 * p.nthreads1;
     int src = 0;
     for (int terminal = 0; !terminal;) {
@@ -675,9 +690,12 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
         count = 2 * warps;
         src ^= 1;
     }
+    PK_MARK(marks, 6, stream);
     PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.W), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
+    PK_MARK(marks, 7, stream);
     PK_LAUNCH(k_window_weight, dim3(p.W), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
     PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.W, prev, ws.result);
+    PK_MARK(marks, 8, stream);
 }
 
 }  // namespace pk

@@ -192,14 +192,30 @@ def msm_plan(n: int, window_bits: int = 0, device: int = 0) -> dict:
     return dict(zip(keys, [int(v) for v in out]))
 
 
+STAGES = ("decompose", "scans", "bin_scatter", "bin_sort", "accumulate", "item_levels", "bucket_reduce", "window_combine", "finalize")
+
+
+def profile_stages_device(scalars, bases, *, window_bits: int = 0) -> dict:
+    """One synchronous MSM with CUDA events between the stages -> {stage: ms}."""
+    torch = _torch()
+    n = scalars.numel() * scalars.element_size() // SCALAR_BYTES
+    dev = scalars.device.index if scalars.device.index is not None else torch.cuda.current_device()
+    torch.cuda.synchronize(scalars.device)
+    out = (ctypes.c_double * 9)()
+    rc = _lib.lib().plonkish_cuda_msm_profile_device(dev, scalars.data_ptr(), bases.data_ptr(), n, window_bits, None, out)
+    _lib.check(rc, "plonkish_cuda_msm_profile_device")
+    return dict(zip(STAGES, [float(v) for v in out]))
+
+
 def launch_count() -> int:
     return int(_lib.load().plonkish_cuda_launch_count())
 
 
 def bench_integer_pipe(device: int = 0) -> dict:
-    out = (ctypes.c_double * 4)()
+    out = (ctypes.c_double * 6)()
     _lib.check(_lib.lib().plonkish_cuda_bench_integer_pipe(device, out), "plonkish_cuda_bench_integer_pipe")
-    return {"imad_wide_per_s": out[0], "fq_mul_per_s": out[1], "sm_max_mhz": out[2], "sm_count": int(out[3])}
+    return {"imad_wide_per_s": out[0], "fq_mul_per_s": out[1], "sm_max_mhz": out[2], "sm_count": int(out[3]),
+            "imad32_per_s": out[4], "imad_wide_chain_per_s": out[5]}
 
 
 def random_scalars(n: int, seed: int) -> np.ndarray:
