@@ -1,0 +1,101 @@
+//! Rust side of the drop-in: `variable_base_msm` for `bn256::G1Affine` on a B200.
+//!
+//! Binds include/plonkish_cuda.h.  `plonkish_backend::util::arithmetic::msm::variable_base_msm`
+//! (util/arithmetic/msm.rs:84-115) keeps its signature and routes here when
+//! `C == bn256::G1Affine` (see INTEGRATION.md for the three-line patch).  There is no CPU
+//! fallback: a non-zero return code panics, as the reference panics on its own errors
+//! (msm.rs:90, :154).
+use halo2_curves::bn256::{Fr, G1Affine, G1};
+use halo2_curves::CurveAffine;
+use std::{collections::HashMap, ffi::CStr, mem::size_of, os::raw::{c_char, c_int, c_void}, sync::{Mutex, Once}};
+
+extern "C" {
+    fn plonkish_cuda_init(n_devices: c_int) -> c_int;
+    fn plonkish_cuda_last_error() -> *const c_char;
+    fn plonkish_cuda_bases_register(device: c_int, bases: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1(scalars: *const c_void, bases: *const c_void, handle: u64, n: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1_gather(scalars: *const *const c_void, bases: *const *const c_void, n: usize, out: *mut c_void) -> c_int;
+}
+
+static INIT: Once = Once::new();
+/// (pointer, length) of a base slice -> device handle.  ProverParam slices
+/// (`eqs[k]`, pcs/multilinear/kzg.rs:74-76; `powers_of_s_g1`, pcs/univariate/kzg.rs:24-30)
+/// live as long as the ProverParam, so the address is a stable key.
+static BASES: Mutex<Option<HashMap<(usize, usize), u64>>> = Mutex::new(None);
+/// Slices shorter than this are not worth a resident copy (sum_with_scalar folds, pcs.rs:175).
+const REGISTER_MIN: usize = 1 << 12;
+
+fn check(rc: c_int, what: &str) {
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(plonkish_cuda_last_error()) }.to_string_lossy().into_owned();
+        panic!("{what} failed ({rc}): {msg}");
+    }
+}
+
+fn init() {
+    INIT.call_once(|| {
+        // halo2_curves types are not repr(C)-guaranteed: probe the layout once.
+        assert_eq!(size_of::<Fr>(), 32);
+        assert_eq!(size_of::<G1Affine>(), 64);
+        let g = G1Affine::generator();
+        let bytes: [u8; 64] = unsafe { std::mem::transmute(g) };
+        // x = 1 and y = 2 in Montgomery form: R mod p and 2R mod p, little-endian limbs.
+        assert_eq!(&bytes[..8], &0xd35d438dc58f0d9du64.to_le_bytes());
+        assert_eq!(&bytes[32..40], &0xa6ba871b8b1e1b3au64.to_le_bytes());
+        check(unsafe { plonkish_cuda_init(0) }, "plonkish_cuda_init");
+    });
+}
+
+/// `variable_base_msm` for BN254 G1 (msm.rs:84-115).  Accepts the same iterators of
+/// references; contiguous inputs (the commit paths, pcs/multilinear/kzg.rs:255,271,292;
+/// pcs/univariate/kzg.rs:28) go down as two slices, anything else is gathered.
+pub fn variable_base_msm_bn254<'a, 'b>(
+    scalars: impl IntoIterator<Item = &'a Fr>,
+    bases: impl IntoIterator<Item = &'b G1Affine>,
+) -> G1 {
+    init();
+    let scalars: Vec<&Fr> = scalars.into_iter().collect();
+    let bases: Vec<&G1Affine> = bases.into_iter().collect();
+    assert_eq!(scalars.len(), bases.len()); // msm.rs:90
+    let n = scalars.len();
+    let mut out = [0u8; 64];
+    if n == 0 {
+        return G1::default(); // documented deviation: the reference panics at msm.rs:154
+    }
+    let contiguous = |first: usize, last: usize, stride: usize| last == first + (n - 1) * stride;
+    let s0 = scalars[0] as *const Fr as usize;
+    let b0 = bases[0] as *const G1Affine as usize;
+    let s_contig = contiguous(s0, scalars[n - 1] as *const Fr as usize, 32)
+        && scalars.windows(2).all(|w| (w[1] as *const Fr as usize) == (w[0] as *const Fr as usize) + 32);
+    let b_contig = contiguous(b0, bases[n - 1] as *const G1Affine as usize, 64)
+        && bases.windows(2).all(|w| (w[1] as *const G1Affine as usize) == (w[0] as *const G1Affine as usize) + 64);
+    if s_contig && b_contig {
+        let handle = if n >= REGISTER_MIN {
+            let mut guard = BASES.lock().unwrap();
+            let map = guard.get_or_insert_with(HashMap::new);
+            *map.entry((b0, n)).or_insert_with(|| {
+                let mut h = 0u64;
+                check(unsafe { plonkish_cuda_bases_register(0, b0 as *const c_void, n, &mut h) }, "plonkish_cuda_bases_register");
+                h
+            })
+        } else {
+            0
+        };
+        let bases_ptr = if handle == 0 { b0 as *const c_void } else { std::ptr::null() };
+        check(
+            unsafe { plonkish_cuda_msm_bn254_g1(s0 as *const c_void, bases_ptr, handle, n, out.as_mut_ptr() as *mut c_void) },
+            "plonkish_cuda_msm_bn254_g1",
+        );
+    } else {
+        let sp: Vec<*const c_void> = scalars.iter().map(|s| *s as *const Fr as *const c_void).collect();
+        let bp: Vec<*const c_void> = bases.iter().map(|b| *b as *const G1Affine as *const c_void).collect();
+        check(
+            unsafe { plonkish_cuda_msm_bn254_g1_gather(sp.as_ptr(), bp.as_ptr(), n, out.as_mut_ptr() as *mut c_void) },
+            "plonkish_cuda_msm_bn254_g1_gather",
+        );
+    }
+    // The library returns the normalised point; every hot-path caller normalises anyway
+    // (`.into()` kzg.rs:255,271,292; `.to_affine()` pcs.rs:175), so G1 is rebuilt from it.
+    let affine: G1Affine = unsafe { std::mem::transmute(out) };
+    affine.to_curve()
+}
