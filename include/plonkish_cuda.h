@@ -66,6 +66,15 @@ const char *plonkish_cuda_last_error(void);
 int plonkish_cuda_bases_register(int device, const void *bases_affine64, size_t n, uint64_t *handle);
 int plonkish_cuda_bases_release(uint64_t handle);
 
+/* Same, from a device pointer on `device` (no host copy).  Registration expands the slice
+ * into a table of window multiples T[w][i] = 2^(c*w) * P_i (W = ceil(254/c) rows, c chosen
+ * from n; 12-32x the memory of the bases) so that every window shares one bucket set: no
+ * per-window reduction, no 2^(c*w) doubling chain (msm.rs:162-164), and wider windows.
+ * mode: 0 = policy (table when it fits in free HBM, unless PLONKISH_CUDA_PRECOMPUTE=0),
+ * 1 = plain bases only (borrows d_bases, which must stay alive), 2 = table or fail.
+ * plonkish_cuda_bases_register follows mode 0. */
+int plonkish_cuda_bases_register_device(int device, const void *d_bases_affine64, size_t n, int mode, uint64_t *handle);
+
 /* ---- the hot path, host buffers in, host result out -----------------------------------
  * out = sum_i scalars[i] * bases[i].  Exactly one of (bases_affine64, bases_handle != 0)
  * selects the bases; with a handle the bases are not copied again.  Runs on the
@@ -100,6 +109,11 @@ int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars_mont32, con
 int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scalars, const void *d_bases, size_t n,
                                       uint32_t window_bits, void *d_out_affine64, void *d_out_xyzz128, void *cuda_stream);
 
+/* Device-resident scalars against a registered (single-device) base slice; runs on the
+ * handle's device with the table of window multiples when the handle has one. */
+int plonkish_cuda_msm_bn254_g1_device_resident(const void *d_scalars, uint64_t bases_handle, size_t n, void *d_out_affine64,
+                                               void *d_out_xyzz128, void *cuda_stream);
+
 /* Adds `count` projective partials (128 B each, e.g. one per rank after an NCCL
  * all-gather) and normalises: msm.rs:112-114 followed by the caller's to_affine(). */
 int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials_xyzz128, size_t count, void *d_out_affine64,
@@ -110,14 +124,15 @@ int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials_xyzz
 /* Fills out[0..8) with the plan the library would use for n points on `device`:
  * window bits c, windows W, high/low bucket bits of the two sort levels, point
  * index bits, points per decompose tile, run length per accumulate thread, and the
- * number of accumulate threads. */
-int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint32_t out[8]);
+ * number of accumulate threads.  With a bases_handle the plan is the handle's (table) plan. */
+int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint64_t bases_handle, uint32_t out[8]);
 
 /* One synchronous MSM on the context stream with CUDA events between the stages;
  * stage_ms[0..9) = decompose, scans, bin scatter, bin sort, accumulate, item levels,
- * bucket reduce, window combine, finalize (to_affine).  d_out_affine64 may be NULL. */
-int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const void *d_bases, size_t n, uint32_t window_bits,
-                                     void *d_out_affine64, double stage_ms[9]);
+ * bucket reduce, window combine, finalize (to_affine).  d_out_affine64 may be NULL; bases come
+ * from d_bases or, when bases_handle != 0, from the registered slice. */
+int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const void *d_bases, uint64_t bases_handle, size_t n,
+                                     uint32_t window_bits, void *d_out_affine64, double stage_ms[9]);
 
 /* Kernels launched by the library in this process since init (for bench accounting). */
 uint64_t plonkish_cuda_launch_count(void);

@@ -20,11 +20,13 @@ EXPORTS = (
     "plonkish_cuda_last_error",
     "plonkish_cuda_bases_register",
     "plonkish_cuda_bases_release",
+    "plonkish_cuda_bases_register_device",
     "plonkish_cuda_msm_bn254_g1",
     "plonkish_cuda_msm_bn254_g1_gather",
     "plonkish_cuda_bases_register_sharded",
     "plonkish_cuda_msm_bn254_g1_multi",
     "plonkish_cuda_msm_bn254_g1_device",
+    "plonkish_cuda_msm_bn254_g1_device_resident",
     "plonkish_cuda_g1_sum_partials_device",
     "plonkish_cuda_msm_plan",
     "plonkish_cuda_msm_profile_device",
@@ -64,14 +66,16 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_last_error.restype = ctypes.c_char_p
     lib.plonkish_cuda_bases_register.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_bases_release.argtypes = [u64]
+    lib.plonkish_cuda_bases_register_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
     lib.plonkish_cuda_bases_register_sharded.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1_multi.argtypes = [ci, vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_device.argtypes = [ci, vp, vp, sz, u32, vp, vp, vp]
+    lib.plonkish_cuda_msm_bn254_g1_device_resident.argtypes = [vp, u64, sz, vp, vp, vp]
     lib.plonkish_cuda_g1_sum_partials_device.argtypes = [ci, vp, sz, vp, vp]
-    lib.plonkish_cuda_msm_plan.argtypes = [ci, sz, u32, ctypes.POINTER(u32)]
-    lib.plonkish_cuda_msm_profile_device.argtypes = [ci, vp, vp, sz, u32, vp, ctypes.POINTER(ctypes.c_double)]
+    lib.plonkish_cuda_msm_plan.argtypes = [ci, sz, u32, u64, ctypes.POINTER(u32)]
+    lib.plonkish_cuda_msm_profile_device.argtypes = [ci, vp, vp, u64, sz, u32, vp, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_launch_count.argtypes = []
     lib.plonkish_cuda_launch_count.restype = u64
     lib.plonkish_cuda_bench_integer_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]

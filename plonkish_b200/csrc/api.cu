@@ -73,8 +73,17 @@ struct BasesEntry {
     int n_shards = 1;                 // 1: whole slice on `dev`; G: shard g on device g
     int dev = 0;
     size_t n = 0;
-    std::vector<void *> d_ptr;        // per shard
+    std::vector<void *> d_ptr;        // per shard: plain bases, or the table of window multiples (row 0 = the bases)
     std::vector<size_t> shard_n;
+    std::vector<uint32_t> table_c;    // per shard: window bits of the table, 0 = plain bases (no table)
+    bool owns = true;                 // false: d_ptr borrows the caller's device memory
+};
+
+// What an MSM launch sequence reads its bases from.
+struct BasesView {
+    const void *ptr = nullptr;
+    uint32_t table_c = 0;   // 0: plain affine array; else table T[w*stride + i]
+    size_t stride = 0;
 };
 
 static std::mutex g_mu;
@@ -155,6 +164,7 @@ extern "C" void plonkish_cuda_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &kv : g_bases) {
         for (size_t s = 0; s < kv.second.d_ptr.size(); ++s) {
+            if (!kv.second.owns) continue;
             cudaSetDevice(kv.second.n_shards == 1 ? kv.second.dev : (int)s);
             cudaFree(kv.second.d_ptr[s]);
         }
@@ -177,22 +187,91 @@ extern "C" const char *plonkish_cuda_last_error(void) { return t_last_error.c_st
 extern "C" uint64_t plonkish_cuda_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------ base cache
-extern "C" int plonkish_cuda_bases_register(int device, const void *bases, size_t n, uint64_t *handle) {
-    if (!bases || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "bases_register: null argument or n == 0");
+static bool precompute_enabled() {
+    const char *e = getenv("PLONKISH_CUDA_PRECOMPUTE");
+    return !(e && e[0] == '0');
+}
+
+// Makes `n` bases resident on c's device.  src is a host pointer (src_is_device = false) or
+// a device pointer on the same device.  mode: 0 = policy (table of window multiples when it
+// fits in free memory), 1 = plain bases, 2 = table or fail.  Caller holds c->mu.
+static int make_resident(Ctx *c, const void *src, bool src_is_device, size_t n, int mode, void **out_ptr, uint32_t *out_c, bool *owns) {
+    CUDA_TRY(cudaSetDevice(c->dev));
+    // One-time, heavyweight: order after whatever stream produced a device-side source.
+    if (src_is_device) CUDA_TRY(cudaDeviceSynchronize());
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    bool want_table = (mode == 2) || (mode == 0 && precompute_enabled());
+    const uint32_t tc = pk_table_window_bits((u32)(n > 0xffffffffull ? 0xffffffffull : n));
+    const uint32_t tw = pk_windows_for(tc);
+    const size_t table_bytes = (size_t)tw * n * PLONKISH_CUDA_AFFINE_BYTES, cur_bytes = n * sizeof(xyzz);
+    if (want_table) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const bool fits = (n <= ((size_t)1 << 27)) && (table_bytes + cur_bytes + ((size_t)8 << 30) < free_b);
+        if (!fits) {
+            if (mode == 2) return fail(PLONKISH_CUDA_E_INVALID, "bases_register: a table of %u x %zu points does not fit in %zu free bytes", tw, n, free_b);
+            want_table = false;
+        }
+    }
+    if (!want_table) {
+        *out_c = 0;
+        if (src_is_device) { *out_ptr = const_cast<void *>(src); *owns = false; return PLONKISH_CUDA_OK; }
+        void *d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_AFFINE_BYTES));
+        CUDA_TRY(cudaMemcpy(d, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind));
+        *out_ptr = d; *owns = true;
+        return PLONKISH_CUDA_OK;
+    }
+    void *table = nullptr, *cur = nullptr, *staged = nullptr;
+    CUDA_TRY(cudaMalloc(&table, table_bytes));
+    CUDA_TRY(cudaMalloc(&cur, cur_bytes));
+    const void *d_src = src;
+    if (!src_is_device) {
+        CUDA_TRY(cudaMalloc(&staged, n * PLONKISH_CUDA_AFFINE_BYTES));
+        CUDA_TRY(cudaMemcpy(staged, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind));
+        d_src = staged;
+    }
+    pk_enqueue_table_build(d_src, (u32)n, tc, tw, (xyzz *)cur, (affine *)table, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaFree(cur));
+    if (staged) CUDA_TRY(cudaFree(staged));
+    *out_ptr = table; *out_c = tc; *owns = true;
+    return PLONKISH_CUDA_OK;
+}
+
+static uint64_t publish(const BasesEntry &e) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint64_t h = g_next_handle++;
+    g_bases[h] = e;
+    return h;
+}
+
+static int register_one(int device, const void *src, bool src_is_device, size_t n, int mode, uint64_t *handle) {
+    if (!src || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "bases_register: null argument or n == 0");
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_register: device %d not initialised (call plonkish_cuda_init)", device);
-    std::lock_guard<std::mutex> lk(c->mu);
-    CUDA_TRY(cudaSetDevice(c->dev));
-    void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_AFFINE_BYTES));
-    CUDA_TRY(cudaMemcpy(d, bases, n * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice));
     BasesEntry e;
-    e.n_shards = 1; e.dev = device; e.n = n;
-    e.d_ptr.push_back(d); e.shard_n.push_back(n);
-    std::lock_guard<std::mutex> lk2(g_mu);
-    *handle = g_next_handle++;
-    g_bases[*handle] = e;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        void *d = nullptr;
+        uint32_t tc = 0;
+        int rc = make_resident(c, src, src_is_device, n, mode, &d, &tc, &e.owns);
+        if (rc) return rc;
+        e.n_shards = 1; e.dev = device; e.n = n;
+        e.d_ptr.push_back(d); e.shard_n.push_back(n); e.table_c.push_back(tc);
+    }
+    *handle = publish(e);
     return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_bases_register(int device, const void *bases, size_t n, uint64_t *handle) {
+    return register_one(device, bases, false, n, 0, handle);
+}
+
+extern "C" int plonkish_cuda_bases_register_device(int device, const void *d_bases, size_t n, int mode, uint64_t *handle) {
+    if (mode < 0 || mode > 2) return fail(PLONKISH_CUDA_E_INVALID, "bases_register_device: mode must be 0, 1 or 2");
+    return register_one(device, d_bases, true, n, mode, handle);
 }
 
 extern "C" int plonkish_cuda_bases_register_sharded(int n_gpus, const void *bases, size_t n, uint64_t *handle) {
@@ -205,16 +284,18 @@ extern "C" int plonkish_cuda_bases_register_sharded(int n_gpus, const void *base
         const size_t beg = (size_t)g * per;
         const size_t cnt = beg >= n ? 0 : (beg + per <= n ? per : n - beg);
         void *d = nullptr;
-        CUDA_TRY(cudaSetDevice(g));
+        uint32_t tc = 0;
         if (cnt) {
-            CUDA_TRY(cudaMalloc(&d, cnt * PLONKISH_CUDA_AFFINE_BYTES));
-            CUDA_TRY(cudaMemcpy(d, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice));
+            Ctx *c = ctx_for(g);
+            if (!c) return PLONKISH_CUDA_E_NO_DEVICE;
+            std::lock_guard<std::mutex> lk(c->mu);
+            bool owns = true;
+            int rc = make_resident(c, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, false, cnt, 0, &d, &tc, &owns);
+            if (rc) return rc;
         }
-        e.d_ptr.push_back(d); e.shard_n.push_back(cnt);
+        e.d_ptr.push_back(d); e.shard_n.push_back(cnt); e.table_c.push_back(tc);
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    *handle = g_next_handle++;
-    g_bases[*handle] = e;
+    *handle = publish(e);
     return PLONKISH_CUDA_OK;
 }
 
@@ -228,7 +309,7 @@ extern "C" int plonkish_cuda_bases_release(uint64_t handle) {
         g_bases.erase(it);
     }
     for (size_t s = 0; s < e.d_ptr.size(); ++s) {
-        if (!e.d_ptr[s]) continue;
+        if (!e.d_ptr[s] || !e.owns) continue;
         CUDA_TRY(cudaSetDevice(e.n_shards == 1 ? e.dev : (int)s));
         CUDA_TRY(cudaDeviceSynchronize());
         CUDA_TRY(cudaFree(e.d_ptr[s]));
@@ -247,14 +328,19 @@ static bool lookup_bases(uint64_t handle, BasesEntry &out) {
 // ------------------------------------------------------------- enqueue helpers
 // Caller holds c->mu and has made c->dev current.  Enqueues the MSM over n device-
 // resident points on `stream`; leaves the projective sum in *d_xyzz_out (device).
-static int enqueue_device_msm(Ctx *c, const void *d_scalars, const void *d_bases, size_t n, uint32_t window_bits,
-                              cudaStream_t stream, xyzz **d_result) {
+static MsmPlan plan_for(const Ctx *c, const BasesView &b, size_t n, uint32_t window_bits) {
+    if (b.table_c) return pk_make_plan_b((u32)n, b.table_c, (u32)b.stride, (u32)c->sm_count);
+    return pk_make_plan((u32)n, window_bits, (u32)c->sm_count);
+}
+
+static int enqueue_device_msm(Ctx *c, const void *d_scalars, const BasesView &bases, size_t n, uint32_t window_bits,
+                              cudaStream_t stream, xyzz **d_result, const StageMarks *marks = nullptr) {
     const size_t first_chunk = n < MAX_POINTS_PER_LAUNCH ? n : MAX_POINTS_PER_LAUNCH;
     const size_t tail_chunk = n % MAX_POINTS_PER_LAUNCH;
-    MsmPlan plan0 = pk_make_plan((u32)first_chunk, window_bits, (u32)c->sm_count);
+    MsmPlan plan0 = plan_for(c, bases, first_chunk, window_bits);
     size_t need = pk_workspace_bytes(plan0);
     if (n > MAX_POINTS_PER_LAUNCH && tail_chunk) {
-        const size_t t = pk_workspace_bytes(pk_make_plan((u32)tail_chunk, window_bits, (u32)c->sm_count));
+        const size_t t = pk_workspace_bytes(plan_for(c, bases, tail_chunk, window_bits));
         if (t > need) need = t;
     }
     int rc = grow(c->arena, need);
@@ -266,11 +352,11 @@ static int enqueue_device_msm(Ctx *c, const void *d_scalars, const void *d_bases
     xyzz *prev = nullptr;
     for (size_t done = 0; done < n;) {
         const size_t cnt = (n - done < MAX_POINTS_PER_LAUNCH) ? n - done : MAX_POINTS_PER_LAUNCH;
-        MsmPlan plan = (cnt == first_chunk) ? plan0 : pk_make_plan((u32)cnt, window_bits, (u32)c->sm_count);
+        MsmPlan plan = (cnt == first_chunk) ? plan0 : plan_for(c, bases, cnt, window_bits);
         MsmWorkspace w = pk_carve_workspace(plan, c->arena.ptr);
         w.result = running;
         pk_enqueue_msm(plan, (const char *)d_scalars + done * PLONKISH_CUDA_SCALAR_BYTES,
-                       (const char *)d_bases + done * PLONKISH_CUDA_AFFINE_BYTES, w, prev, stream);
+                       (const char *)bases.ptr + done * PLONKISH_CUDA_AFFINE_BYTES, w, prev, stream, marks);
         prev = running;
         done += cnt;
     }
@@ -297,12 +383,12 @@ static void timer_report(size_t n, std::chrono::steady_clock::time_point t0) {
 }
 
 // --------------------------------------------------------------- device entry
-extern "C" int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scalars, const void *d_bases, size_t n,
-                                                 uint32_t window_bits, void *d_out_affine64, void *d_out_xyzz128, void *cuda_stream) {
+static int msm_device_common(int device, const void *d_scalars, const BasesView &bases, size_t n, uint32_t window_bits,
+                             void *d_out_affine64, void *d_out_xyzz128, void *cuda_stream) {
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_device: device %d not initialised (call plonkish_cuda_init)", device);
     if (!d_out_affine64 && !d_out_xyzz128) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: no output pointer");
-    if (n && (!d_scalars || !d_bases)) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: null input");
+    if (n && (!d_scalars || !bases.ptr)) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: null input");
     if (window_bits && (window_bits < 8 || window_bits > 16)) return fail(PLONKISH_CUDA_E_INVALID, "msm_device: window_bits must be 0 or 8..16");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
@@ -313,11 +399,42 @@ extern "C" int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scala
         return PLONKISH_CUDA_OK;
     }
     xyzz *res = nullptr;
-    int rc = enqueue_device_msm(c, d_scalars, d_bases, n, window_bits, stream, &res);
+    int rc = enqueue_device_msm(c, d_scalars, bases, n, window_bits, stream, &res);
     if (rc) return rc;
     PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, stream, res, 1u, (affine *)d_out_affine64, (xyzz *)d_out_xyzz128);
     CUDA_TRY(cudaGetLastError());
     return mark_done(c, stream);
+}
+
+extern "C" int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scalars, const void *d_bases, size_t n,
+                                                 uint32_t window_bits, void *d_out_affine64, void *d_out_xyzz128, void *cuda_stream) {
+    BasesView v;
+    v.ptr = d_bases;
+    return msm_device_common(device, d_scalars, v, n, window_bits, d_out_affine64, d_out_xyzz128, cuda_stream);
+}
+
+static int view_of(uint64_t handle, size_t n, int shard, BasesView &v, int *device, const char *who) {
+    BasesEntry e;
+    if (!lookup_bases(handle, e)) return fail(PLONKISH_CUDA_E_INVALID, "%s: unknown bases handle %llu", who, (unsigned long long)handle);
+    if (shard < 0) {
+        if (e.n_shards != 1) return fail(PLONKISH_CUDA_E_INVALID, "%s: handle is sharded; use plonkish_cuda_msm_bn254_g1_multi", who);
+        shard = 0;
+    }
+    if (n > e.shard_n[shard]) return fail(PLONKISH_CUDA_E_INVALID, "%s: n = %zu exceeds the %zu registered bases", who, n, e.shard_n[shard]);
+    v.ptr = e.d_ptr[shard];
+    v.table_c = e.table_c[shard];
+    v.stride = e.shard_n[shard];
+    if (device) *device = e.n_shards == 1 ? e.dev : shard;
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_msm_bn254_g1_device_resident(const void *d_scalars, uint64_t bases_handle, size_t n, void *d_out_affine64,
+                                                          void *d_out_xyzz128, void *cuda_stream) {
+    BasesView v;
+    int device = 0;
+    int rc = view_of(bases_handle, n, -1, v, &device, "msm_device_resident");
+    if (rc) return rc;
+    return msm_device_common(device, d_scalars, v, n, 0, d_out_affine64, d_out_xyzz128, cuda_stream);
 }
 
 extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials, size_t count, void *d_out_affine64, void *cuda_stream) {
@@ -339,12 +456,10 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
     if (n && !scalars) return fail(PLONKISH_CUDA_E_INVALID, "msm: null scalars");
     if (n && !bases && !bases_handle) return fail(PLONKISH_CUDA_E_INVALID, "msm: neither bases nor a handle given");
     int device = 0;
-    BasesEntry entry;
+    BasesView view;
     if (bases_handle) {
-        if (!lookup_bases(bases_handle, entry)) return fail(PLONKISH_CUDA_E_INVALID, "msm: unknown bases handle %llu", (unsigned long long)bases_handle);
-        if (entry.n_shards != 1) return fail(PLONKISH_CUDA_E_INVALID, "msm: handle is sharded; use plonkish_cuda_msm_bn254_g1_multi");
-        if (n > entry.n) return fail(PLONKISH_CUDA_E_INVALID, "msm: n = %zu exceeds the %zu registered bases", n, entry.n);
-        device = entry.dev;
+        int rc0 = view_of(bases_handle, n, -1, view, &device, "msm");
+        if (rc0) return rc0;
     }
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm: device %d not initialised (call plonkish_cuda_init; there is no CPU fallback)", device);
@@ -357,17 +472,14 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
     int rc = grow(c->scalars, n * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->scalars.ptr, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
-    const void *d_bases = nullptr;
-    if (bases_handle) {
-        d_bases = entry.d_ptr[0];
-    } else {
+    if (!bases_handle) {
         rc = grow(c->bases_tmp, n * PLONKISH_CUDA_AFFINE_BYTES);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->bases_tmp.ptr, bases, n * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
-        d_bases = c->bases_tmp.ptr;
+        view.ptr = c->bases_tmp.ptr;
     }
     xyzz *res = nullptr;
-    rc = enqueue_device_msm(c, c->scalars.ptr, d_bases, n, 0, c->stream, &res);
+    rc = enqueue_device_msm(c, c->scalars.ptr, view, n, 0, c->stream, &res);
     if (rc) return rc;
     PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, (affine *)c->d_out, (xyzz *)nullptr);
     CUDA_TRY(cudaGetLastError());
@@ -437,16 +549,18 @@ extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars,
         }
         if ((rc = grow(c->scalars, cnt * PLONKISH_CUDA_SCALAR_BYTES))) { unlock_all(); return rc; }
         MULTI_TRY(cudaMemcpyAsync(c->scalars.ptr, (const char *)scalars + beg * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
-        const void *d_bases;
+        BasesView view;
         if (bases_handle) {
-            d_bases = entry.d_ptr[g];
+            view.ptr = entry.d_ptr[g];
+            view.table_c = entry.table_c[g];
+            view.stride = entry.shard_n[g];
         } else {
             if ((rc = grow(c->bases_tmp, cnt * PLONKISH_CUDA_AFFINE_BYTES))) { unlock_all(); return rc; }
             MULTI_TRY(cudaMemcpyAsync(c->bases_tmp.ptr, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
-            d_bases = c->bases_tmp.ptr;
+            view.ptr = c->bases_tmp.ptr;
         }
         xyzz *res = nullptr;
-        if ((rc = enqueue_device_msm(c, c->scalars.ptr, d_bases, cnt, 0, c->stream, &res))) { unlock_all(); return rc; }
+        if ((rc = enqueue_device_msm(c, c->scalars.ptr, view, cnt, 0, c->stream, &res))) { unlock_all(); return rc; }
         MULTI_TRY(cudaMemcpyPeerAsync(slot, 0, res, g, PLONKISH_CUDA_XYZZ_BYTES, c->stream));
         if ((rc = mark_done(c, c->stream))) { unlock_all(); return rc; }
         MULTI_TRY(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
@@ -471,26 +585,29 @@ extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars,
 }
 
 // ------------------------------------------------------------ per-stage timing
-extern "C" int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const void *d_bases, size_t n, uint32_t window_bits,
-                                                void *d_out_affine64, double stage_ms[9]) {
+extern "C" int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const void *d_bases, uint64_t bases_handle, size_t n,
+                                                uint32_t window_bits, void *d_out_affine64, double stage_ms[9]) {
+    if (!d_scalars || (!d_bases && !bases_handle) || !stage_ms || n == 0 || n > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm_profile: bad argument");
+    if (window_bits && (window_bits < 8 || window_bits > 16)) return fail(PLONKISH_CUDA_E_INVALID, "msm_profile: window_bits must be 0 or 8..16");
+    BasesView view;
+    view.ptr = d_bases;
+    if (bases_handle) {
+        int rc0 = view_of(bases_handle, n, -1, view, &device, "msm_profile");
+        if (rc0) return rc0;
+    }
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_profile: device %d not initialised", device);
-    if (!d_scalars || !d_bases || !stage_ms || n == 0 || n > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm_profile: bad argument");
-    if (window_bits && (window_bits < 8 || window_bits > 16)) return fail(PLONKISH_CUDA_E_INVALID, "msm_profile: window_bits must be 0 or 8..16");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
-    MsmPlan plan = pk_make_plan((u32)n, window_bits, (u32)c->sm_count);
-    int rc = grow(c->arena, pk_workspace_bytes(plan));
-    if (rc) return rc;
-    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
-    MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
-    ws.result = (xyzz *)((char *)c->d_out + 256);
+    CUDA_TRY(cudaDeviceSynchronize());  // inputs may come from another stream; this call is synchronous anyway
     StageMarks marks;
     cudaEvent_t ev[10];
     for (int i = 0; i < 10; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
     for (int i = 0; i < 9; ++i) marks.ev[i] = ev[i];
-    pk_enqueue_msm(plan, d_scalars, d_bases, ws, nullptr, c->stream, &marks);
-    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, ws.result, 1u, (affine *)(d_out_affine64 ? d_out_affine64 : c->d_out), (xyzz *)nullptr);
+    xyzz *res = nullptr;
+    int rc = enqueue_device_msm(c, d_scalars, view, n, window_bits, c->stream, &res, &marks);
+    if (rc) return rc;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, (affine *)(d_out_affine64 ? d_out_affine64 : c->d_out), (xyzz *)nullptr);
     CUDA_TRY(cudaEventRecord(ev[9], c->stream));
     CUDA_TRY(cudaGetLastError());
     rc = mark_done(c, c->stream);
@@ -506,11 +623,16 @@ extern "C" int plonkish_cuda_msm_profile_device(int device, const void *d_scalar
 }
 
 // ------------------------------------------------------------------ plan probe
-extern "C" int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint32_t out[8]) {
+extern "C" int plonkish_cuda_msm_plan(int device, size_t n, uint32_t window_bits, uint64_t bases_handle, uint32_t out[8]) {
     if (!out || n == 0 || n > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm_plan: bad argument");
+    BasesView view;
+    if (bases_handle) {
+        int rc0 = view_of(bases_handle, n, -1, view, &device, "msm_plan");
+        if (rc0) return rc0;
+    }
     Ctx *c = ctx_for(device);
-    const u32 sms = c ? (u32)c->sm_count : 148u;
-    MsmPlan p = pk_make_plan((u32)n, window_bits, sms);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_plan: device %d not initialised", device);
+    MsmPlan p = plan_for(c, view, n, window_bits);
     out[0] = p.c; out[1] = p.W; out[2] = p.hi_bits; out[3] = p.lo_bits; out[4] = p.idx_bits;
     out[5] = p.tile; out[6] = p.L; out[7] = p.nthreads1;
     return PLONKISH_CUDA_OK;

@@ -71,6 +71,10 @@ struct MsmPlan {
     u32 red_blocks;   // K4 blocks per window
     u32 blk;          // threads per block of the streaming kernels (256; tests shrink it)
     u32 serial_items; // item levels above this many items let every lane fold 8 items serially first
+    u32 mode;         // 0: one bucket set per window (any bases); 1: one bucket set, bases are a table of
+                      //    precomputed window multiples T[w][i] = 2^(c*w) * P_i (resident bases only)
+    u32 ngroups;      // bucket sets: W in mode 0, 1 in mode 1
+    u32 stride;       // mode 1: points per table row
 };
 
 inline u32 pk_ceil_log2(u32 v) {
@@ -128,16 +132,65 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     p.red_blocks = (p.red_threads + 255) / 256;
     p.blk = 256;
     p.serial_items = 8192;
+    p.mode = 0;
+    p.ngroups = p.W;
+    p.stride = 0;
+    return p;
+}
+
+// Window width used when a resident base slice of n_registered points is expanded
+// into its table of window multiples: buckets (2^(c-1), one set) stay ~1/32 of the
+// adds (n * W).
+inline u32 pk_table_window_bits(u32 n_registered) {
+    int c = (int)pk_ceil_log2(n_registered < 2 ? 2 : n_registered) - 4;
+    if (c < 8) c = 8;
+    if (c > 22) c = 22;
+    return (u32)c;
+}
+
+inline u32 pk_windows_for(u32 c) {
+    u32 w = (254 + c - 1) / c;
+    if (c * w < 255) w += 1;
+    return w;
+}
+
+// Mode 1 plan: n points (a prefix of a table with `stride` points per row), c fixed by the table.
+inline MsmPlan pk_make_plan_b(u32 n, u32 c, u32 stride, u32 sm_count) {
+    MsmPlan p = pk_make_plan(n, 16, sm_count);
+    p.mode = 1;
+    p.c = c;
+    p.W = pk_windows_for(c);
+    p.B = 1u << (c - 1);
+    p.idx_bits = 0;
+    p.hi_bits = (c - 1 < 10) ? c - 1 : 10;
+    p.lo_bits = c - 1 - p.hi_bits;
+    p.HI = 1u << p.hi_bits;
+    p.nbins = p.HI;
+    p.nbuckets = p.B;
+    p.ngroups = 1;
+    p.stride = stride;
+    unsigned long long emax = (unsigned long long)n * p.W;
+    unsigned long long resident = (unsigned long long)sm_count * 512ull;
+    unsigned long long L = emax / (resident * 3ull);
+    if (L < 16) L = 16;
+    if (L > 256) L = 256;
+    p.L = (u32)L;
+    unsigned long long t1 = (emax + L - 1) / L;
+    p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
+    p.blk_acc = (t1 <= 32) ? 32u : 128u;
+    p.rb = p.B < 8 ? p.B : 8;
+    p.red_threads = p.B / p.rb;
+    p.red_blocks = (p.red_threads + 255) / 256;
     return p;
 }
 
 // Workspace layout (one arena, 256-byte aligned pieces).
 struct MsmWorkspace {
-    u16 *digits;        // [W][n_pad]
+    u16 *digits;        // [W][n_pad]           (mode 1: u32 digits in the same storage)
     u32 *tile_hist;     // [ntiles][nbins]
     u32 *bin_total;     // [nbins]
     u32 *bin_start;     // [nbins + 1]
-    u32 *l1;            // [n * W] entries after the bin scatter
+    u32 *l1;            // [n * W] entries after the bin scatter (mode 1: u64 entries)
     u32 *sorted;        // [n * W] (sign << 31 | point index), ordered by (window, bucket)
     u32 *bucket_start;  // [nbuckets + 1]
     xyzz *bucket_sum;   // [nbuckets]
@@ -154,17 +207,17 @@ inline size_t pk_workspace_bytes(const MsmPlan &p) {
     size_t e = (size_t)p.n * p.W;
     size_t items = (size_t)p.nthreads1 * 2;
     size_t s = 0;
-    s += pk_align256(sizeof(u16) * (size_t)p.W * p.n_pad);
+    s += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
     s += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
     s += pk_align256(sizeof(u32) * p.nbins);
     s += pk_align256(sizeof(u32) * (p.nbins + 1));
-    s += pk_align256(sizeof(u32) * e);
+    s += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
     s += pk_align256(sizeof(u32) * e);
     s += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     s += pk_align256(sizeof(xyzz) * p.nbuckets);
     s += 2 * pk_align256(sizeof(u32) * items);
     s += 2 * pk_align256(sizeof(xyzz) * items);
-    s += pk_align256(sizeof(xyzz) * (size_t)p.W * p.red_blocks);
+    s += pk_align256(sizeof(xyzz) * (size_t)p.ngroups * p.red_blocks);
     s += pk_align256(sizeof(xyzz) * 32);
     s += pk_align256(sizeof(xyzz));
     return s;
@@ -175,17 +228,17 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     unsigned char *q = (unsigned char *)arena;
     size_t e = (size_t)p.n * p.W;
     size_t items = (size_t)p.nthreads1 * 2;
-    w.digits = (u16 *)q; q += pk_align256(sizeof(u16) * (size_t)p.W * p.n_pad);
+    w.digits = (u16 *)q; q += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
     w.tile_hist = (u32 *)q; q += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
     w.bin_total = (u32 *)q; q += pk_align256(sizeof(u32) * p.nbins);
     w.bin_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbins + 1));
-    w.l1 = (u32 *)q; q += pk_align256(sizeof(u32) * e);
+    w.l1 = (u32 *)q; q += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
     w.sorted = (u32 *)q; q += pk_align256(sizeof(u32) * e);
     w.bucket_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     w.bucket_sum = (xyzz *)q; q += pk_align256(sizeof(xyzz) * p.nbuckets);
     for (int k = 0; k < 2; ++k) { w.item_keys[k] = (u32 *)q; q += pk_align256(sizeof(u32) * items); }
     for (int k = 0; k < 2; ++k) { w.item_pts[k] = (xyzz *)q; q += pk_align256(sizeof(xyzz) * items); }
-    w.block_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.W * p.red_blocks);
+    w.block_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.ngroups * p.red_blocks);
     w.win_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * 32);
     w.result = (xyzz *)q;
     return w;
@@ -329,18 +382,33 @@ __global__ void __launch_bounds__(256) k_scatter_bins(const u16 *__restrict__ di
     const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
     const u16 *row = digits + (size_t)w * p.n_pad;
     const u32 lo_mask = (1u << p.lo_bits) - 1u;
-    // tile is a multiple of 8 and rows are padded to 8: 128-bit loads of 8 digits.
-    for (u32 i = beg + 8 * threadIdx.x; i < end; i += 8 * blockDim.x) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + i));
-        const u32 words[4] = {v.x, v.y, v.z, v.w};
+    // tile is a multiple of 8 and rows are padded to 8: 128-bit loads of 8 digits, four
+    // loads in flight per thread, then all their shared-memory cursor updates, then the stores.
+    constexpr int U = 4;
+    for (u32 i0 = beg + 8 * threadIdx.x; i0 < end; i0 += 8 * blockDim.x * U) {
+        uint4 v[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const u32 d = (words[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-            if (i + k < end && d != PK_ZERO_DIGIT) {
+        for (int u = 0; u < U; ++u) {
+            const u32 i = i0 + (u32)u * 8 * blockDim.x;
+            v[u] = (i < end) ? __ldg(reinterpret_cast<const uint4 *>(row + i)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        }
+        u32 pos[U * 8], ent[U * 8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 i = i0 + (u32)u * 8 * blockDim.x;
+            const u32 words[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const u32 d = (words[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                const bool valid = (i + k < end) && d != PK_ZERO_DIGIT;
                 const u32 b = d & 0x7fffu;
-                const u32 pos = atomicAdd(&cursor[b >> p.lo_bits], 1u);
-                l1[pos] = ((b & lo_mask) << (p.idx_bits + 1)) | ((d >> 15) << p.idx_bits) | (i + k);
+                ent[u * 8 + k] = ((b & lo_mask) << (p.idx_bits + 1)) | ((d >> 15) << p.idx_bits) | (i + k);
+                pos[u * 8 + k] = valid ? atomicAdd(&cursor[b >> p.lo_bits], 1u) : 0xffffffffu;
             }
+        }
+#pragma unroll
+        for (int j = 0; j < U * 8; ++j) {
+            if (pos[j] != 0xffffffffu) l1[pos[j]] = ent[j];
         }
     }
 }
@@ -357,7 +425,19 @@ __global__ void __launch_bounds__(256) k_sort_bins(const u32 *__restrict__ l1, M
     for (u32 k = threadIdx.x; k < nlo; k += blockDim.x) cnt[k] = 0;
     __syncthreads();
     const u32 sh = p.idx_bits + 1;
-    for (u32 q = beg + threadIdx.x; q < end; q += blockDim.x) atomicAdd(&cnt[l1[q] >> sh], 1u);
+    constexpr int U = 8;  // independent loads in flight per thread
+    for (u32 q0 = beg + threadIdx.x; q0 < end; q0 += blockDim.x * U) {
+        u32 e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 q = q0 + (u32)u * blockDim.x;
+            e[u] = (q < end) ? l1[q] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (q0 + (u32)u * blockDim.x < end) atomicAdd(&cnt[e[u] >> sh], 1u);
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         u32 run = beg;
@@ -371,10 +451,239 @@ __global__ void __launch_bounds__(256) k_sort_bins(const u32 *__restrict__ l1, M
     }
     __syncthreads();
     const u32 idx_mask = (1u << p.idx_bits) - 1u;
-    for (u32 q = beg + threadIdx.x; q < end; q += blockDim.x) {
-        const u32 e = l1[q];
-        const u32 pos = atomicAdd(&cnt[e >> sh], 1u);
-        sorted[pos] = (((e >> p.idx_bits) & 1u) << 31) | (e & idx_mask);
+    for (u32 q0 = beg + threadIdx.x; q0 < end; q0 += blockDim.x * U) {
+        u32 e[U], pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 q = q0 + (u32)u * blockDim.x;
+            e[u] = (q < end) ? l1[q] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pos[u] = (q0 + (u32)u * blockDim.x < end) ? atomicAdd(&cnt[e[u] >> sh], 1u) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (pos[u] != 0xffffffffu) sorted[pos[u]] = (((e[u] >> p.idx_bits) & 1u) << 31) | (e[u] & idx_mask);
+        }
+    }
+}
+
+// ====================================================== mode 1: table of multiples
+// With resident bases the windows share ONE bucket set: digit d of window w selects
+// bucket |d| and the precomputed point T[w][i] = 2^(c*w) * P_i, so there is no
+// per-window reduction and no 2^(c*w) doubling chain at the end (msm.rs:162-164
+// disappears), and c can grow to 20-22 (fewer windows => fewer additions per point).
+template <int C>
+__global__ void __launch_bounds__(256) k_decompose_b(const uint4 *__restrict__ scalars, MsmPlan p, u32 *__restrict__ digits,
+                                                     u32 *__restrict__ tile_hist) {
+    constexpr int W = (254 + C - 1) / C + ((C * ((254 + C - 1) / C) < 255) ? 1 : 0);
+    constexpr u32 B = 1u << (C - 1);
+    __shared__ u32 hist[1024];
+    const u32 tile = blockIdx.x;
+    for (u32 k = threadIdx.x; k < p.HI; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const u32 beg = tile * p.tile;
+    const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
+    for (u32 i = beg + threadIdx.x; i < end; i += blockDim.x) {
+        fe v = fr_to_canonical(load_fe(scalars + 2 * (size_t)i));
+        const bool neg = fr_above_half(v);
+        if (neg) {
+            u32 m[8];
+            FrMod::limbs(m);
+            fe t;
+            sub8(t.l, m, v.l);
+            v = t;
+        }
+        u32 carry = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int off = w * C;
+            const int word = off >> 5, sh = off & 31;
+            u32 raw = 0;
+            if (word < 8) {
+                raw = v.l[word] >> sh;
+                if (sh + C > 32 && word + 1 < 8) raw |= v.l[word + 1] << (32 - sh);
+            }
+            raw = (raw & ((1u << C) - 1u)) + carry;
+            const bool borrow = neg ? (raw >= B) : (raw > B);  // see k_decompose
+            const u32 mag = borrow ? (1u << C) - raw : raw;
+            carry = borrow ? 1u : 0u;
+            const u32 sign = (borrow ? 1u : 0u) ^ (neg ? 1u : 0u);
+            u32 enc = 0xffffffffu;
+            if (mag != 0) {
+                enc = (sign << 31) | (mag - 1u);
+                atomicAdd(&hist[(mag - 1u) >> p.lo_bits], 1u);
+            }
+            digits[(size_t)w * p.n_pad + i] = enc;
+        }
+    }
+    __syncthreads();
+    u32 *out = tile_hist + (size_t)tile * p.HI;
+    for (u32 k = threadIdx.x; k < p.HI; k += blockDim.x) out[k] = hist[k];
+}
+
+// One block per tile, all windows.  Entry: low bucket bits << 32 | sign << 31 | table index.
+__global__ void __launch_bounds__(256) k_scatter_bins_b(const u32 *__restrict__ digits, MsmPlan p, const u32 *__restrict__ tile_hist,
+                                                        const u32 *__restrict__ bin_start, unsigned long long *__restrict__ l1) {
+    __shared__ u32 cursor[1024];
+    const u32 tile = blockIdx.x;
+    for (u32 h = threadIdx.x; h < p.HI; h += blockDim.x) cursor[h] = bin_start[h] + tile_hist[(size_t)tile * p.HI + h];
+    __syncthreads();
+    const u32 beg = tile * p.tile;
+    const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
+    const u32 lo_mask = (1u << p.lo_bits) - 1u;
+    for (u32 w = 0; w < p.W; ++w) {
+        const u32 *row = digits + (size_t)w * p.n_pad;
+        const u32 base_idx = w * p.stride;
+        constexpr int U = 4;  // independent 128-bit loads in flight per thread
+        for (u32 i0 = beg + 4 * threadIdx.x; i0 < end; i0 += 4 * blockDim.x * U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const u32 i = i0 + (u32)u * 4 * blockDim.x;
+                v[u] = (i < end) ? __ldg(reinterpret_cast<const uint4 *>(row + i)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            }
+            u32 pos[U * 4];
+            unsigned long long ent[U * 4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const u32 i = i0 + (u32)u * 4 * blockDim.x;
+                const u32 d4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const u32 d = d4[k];
+                    const bool valid = (i + k < end) && d != 0xffffffffu;
+                    const u32 b = d & 0x7fffffffu;
+                    ent[u * 4 + k] = ((unsigned long long)(b & lo_mask) << 32) | (d & 0x80000000u) | (base_idx + i + (u32)k);
+                    pos[u * 4 + k] = valid ? atomicAdd(&cursor[b >> p.lo_bits], 1u) : 0xffffffffu;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U * 4; ++j) {
+                if (pos[j] != 0xffffffffu) l1[pos[j]] = ent[j];
+            }
+        }
+    }
+}
+
+// One block per high-bits bin: counting sort on the low bucket bits (up to 2^12 of them).
+__global__ void __launch_bounds__(256) k_sort_bins_b(const unsigned long long *__restrict__ l1, MsmPlan p, const u32 *__restrict__ bin_start,
+                                                     u32 *__restrict__ sorted, u32 *__restrict__ bucket_start) {
+    __shared__ u32 cnt[4096];
+    __shared__ u32 part[256];
+    const u32 bin = blockIdx.x;
+    const u32 beg = bin_start[bin], end = bin_start[bin + 1];
+    const u32 nlo = 1u << p.lo_bits;
+    for (u32 k = threadIdx.x; k < nlo; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    constexpr int U = 8;  // independent loads in flight per thread
+    for (u32 q0 = beg + threadIdx.x; q0 < end; q0 += blockDim.x * U) {
+        unsigned long long e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 q = q0 + (u32)u * blockDim.x;
+            e[u] = (q < end) ? l1[q] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (q0 + (u32)u * blockDim.x < end) atomicAdd(&cnt[(u32)(e[u] >> 32)], 1u);
+        }
+    }
+    __syncthreads();
+    // block-wide exclusive scan of cnt[0..nlo), offset by beg
+    const u32 per = (nlo + blockDim.x - 1) / blockDim.x;
+    const u32 first = threadIdx.x * per;
+    u32 sum = 0;
+    for (u32 k = 0; k < per; ++k) {
+        if (first + k < nlo) sum += cnt[first + k];
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (u32 d = 1; d < blockDim.x; d <<= 1) {
+        const u32 v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = beg + part[threadIdx.x] - sum;
+    for (u32 k = 0; k < per; ++k) {
+        if (first + k < nlo) {
+            const u32 v = cnt[first + k];
+            cnt[first + k] = run;
+            bucket_start[(size_t)bin * nlo + first + k] = run;
+            run += v;
+        }
+    }
+    if (bin == p.nbins - 1 && threadIdx.x == 0) bucket_start[p.nbuckets] = end;
+    __syncthreads();
+    for (u32 q0 = beg + threadIdx.x; q0 < end; q0 += blockDim.x * U) {
+        unsigned long long e[U];
+        u32 pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 q = q0 + (u32)u * blockDim.x;
+            e[u] = (q < end) ? l1[q] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pos[u] = (q0 + (u32)u * blockDim.x < end) ? atomicAdd(&cnt[(u32)(e[u] >> 32)], 1u) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (pos[u] != 0xffffffffu) sorted[pos[u]] = (u32)e[u];
+        }
+    }
+}
+
+// ---- building the table (once per registered base slice)
+__global__ void __launch_bounds__(128) k_table_init(const affine *__restrict__ bases, u32 n, xyzz *__restrict__ cur, affine *__restrict__ row0) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *bp = reinterpret_cast<const uint4 *>(bases + i);
+    affine a;
+    a.x = load_fe(bp);
+    a.y = load_fe(bp + 2);
+    uint4 *q = reinterpret_cast<uint4 *>(row0 + i);
+    store_fe(q, a.x);
+    store_fe(q + 2, a.y);
+    store_xyzz(cur + i, xyzz_from_affine(a));
+}
+__global__ void __launch_bounds__(128) k_table_double(xyzz *__restrict__ cur, u32 n, u32 c) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xyzz v = load_xyzz(cur + i);
+    for (u32 k = 0; k < c; ++k) v = xyzz_double(v);
+    store_xyzz(cur + i, v);
+}
+// Thread normalises 8 consecutive points with one inversion (Montgomery's trick).
+__global__ void __launch_bounds__(128) k_table_normalize(const xyzz *__restrict__ cur, u32 n, affine *__restrict__ row) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 i0 = t * 8;
+    if (i0 >= n) return;
+    const u32 cnt = (n - i0 < 8) ? n - i0 : 8;
+    fe prefix[8];
+    fe acc = fq_one();
+    for (u32 j = 0; j < cnt; ++j) {
+        const xyzz v = load_xyzz(cur + i0 + j);
+        prefix[j] = acc;
+        if (!xyzz_is_identity(v)) acc = fq_mul(acc, fq_mul(v.zz, v.zzz));
+    }
+    fe inv = fq_inv(acc);
+    for (u32 jj = cnt; jj-- > 0;) {
+        const xyzz v = load_xyzz(cur + i0 + jj);
+        affine r;
+        if (xyzz_is_identity(v)) {
+            r.x = fe_zero(); r.y = fe_zero();
+        } else {
+            const fe i = fq_mul(inv, prefix[jj]);  // 1 / (zz * zzz)
+            inv = fq_mul(inv, fq_mul(v.zz, v.zzz));
+            r.x = fq_mul(v.x, fq_mul(i, v.zzz));
+            r.y = fq_mul(v.y, fq_mul(i, v.zz));
+        }
+        uint4 *q = reinterpret_cast<uint4 *>(row + i0 + jj);
+        store_fe(q, r.x);
+        store_fe(q + 2, r.y);
     }
 }
 
@@ -554,10 +863,10 @@ PK_HD xyzz warp_sum_xyzz(xyzz v) {
     return v;  // lane 0 holds the sum
 }
 
-// k * P by double-and-add, k < 2^16.
+// k * P by double-and-add over the bits of k.
 PK_HD xyzz xyzz_mul_small(const xyzz &pnt, u32 k) {
     xyzz r = xyzz_identity();
-    for (int b = 15; b >= 0; --b) {
+    for (int b = 31 - __clz(k | 1u); b >= 0; --b) {
         r = xyzz_double(r);
         if ((k >> b) & 1u) r = xyzz_add(r, pnt);
     }
@@ -653,25 +962,46 @@ struct StageMarks {
 inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *bases, const MsmWorkspace &ws, const xyzz *prev,
                            pk_stream_t stream, const StageMarks *marks = nullptr) {
     PK_MARK(marks, 0, stream);
-    switch (p.c) {
-        case 8: pk_launch_decompose<8>(p, scalars, ws, stream); break;
-        case 9: pk_launch_decompose<9>(p, scalars, ws, stream); break;
-        case 10: pk_launch_decompose<10>(p, scalars, ws, stream); break;
-        case 11: pk_launch_decompose<11>(p, scalars, ws, stream); break;
-        case 12: pk_launch_decompose<12>(p, scalars, ws, stream); break;
-        case 13: pk_launch_decompose<13>(p, scalars, ws, stream); break;
-        case 14: pk_launch_decompose<14>(p, scalars, ws, stream); break;
-        case 15: pk_launch_decompose<15>(p, scalars, ws, stream); break;
-        default: pk_launch_decompose<16>(p, scalars, ws, stream); break;
+    if (p.mode == 0) {
+        switch (p.c) {
+            case 8: pk_launch_decompose<8>(p, scalars, ws, stream); break;
+            case 9: pk_launch_decompose<9>(p, scalars, ws, stream); break;
+            case 10: pk_launch_decompose<10>(p, scalars, ws, stream); break;
+            case 11: pk_launch_decompose<11>(p, scalars, ws, stream); break;
+            case 12: pk_launch_decompose<12>(p, scalars, ws, stream); break;
+            case 13: pk_launch_decompose<13>(p, scalars, ws, stream); break;
+            case 14: pk_launch_decompose<14>(p, scalars, ws, stream); break;
+            case 15: pk_launch_decompose<15>(p, scalars, ws, stream); break;
+            default: pk_launch_decompose<16>(p, scalars, ws, stream); break;
+        }
+        PK_MARK(marks, 1, stream);
+        PK_LAUNCH(k_scan_tiles, dim3((p.nbins + p.blk - 1) / p.blk), dim3(p.blk), 0, stream, ws.tile_hist, p.ntiles, p.nbins, ws.bin_total);
+        PK_LAUNCH(k_scan_bins, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.nbins, ws.bin_start);
+        PK_MARK(marks, 2, stream);
+        PK_LAUNCH(k_scatter_bins, dim3(p.ntiles, p.W), dim3(p.blk), 0, stream, ws.digits, p, ws.tile_hist, ws.bin_start, ws.l1);
+        PK_MARK(marks, 3, stream);
+        PK_LAUNCH(k_sort_bins, dim3(p.nbins), dim3(p.blk), 0, stream, ws.l1, p, ws.bin_start, ws.sorted, ws.bucket_start);
+        PK_MARK(marks, 4, stream);
+    } else {
+        u32 *digits32 = reinterpret_cast<u32 *>(ws.digits);
+        unsigned long long *l1_64 = reinterpret_cast<unsigned long long *>(ws.l1);
+#define PK_DECOMPOSE_B(C) case C: PK_LAUNCH(k_decompose_b<C>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.tile_hist); break;
+        switch (p.c) {
+            PK_DECOMPOSE_B(8) PK_DECOMPOSE_B(9) PK_DECOMPOSE_B(10) PK_DECOMPOSE_B(11) PK_DECOMPOSE_B(12)
+            PK_DECOMPOSE_B(13) PK_DECOMPOSE_B(14) PK_DECOMPOSE_B(15) PK_DECOMPOSE_B(16) PK_DECOMPOSE_B(17)
+            PK_DECOMPOSE_B(18) PK_DECOMPOSE_B(19) PK_DECOMPOSE_B(20) PK_DECOMPOSE_B(21)
+            default: PK_LAUNCH(k_decompose_b<22>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.tile_hist); break;
+        }
+#undef PK_DECOMPOSE_B
+        PK_MARK(marks, 1, stream);
+        PK_LAUNCH(k_scan_tiles, dim3((p.nbins + p.blk - 1) / p.blk), dim3(p.blk), 0, stream, ws.tile_hist, p.ntiles, p.nbins, ws.bin_total);
+        PK_LAUNCH(k_scan_bins, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.nbins, ws.bin_start);
+        PK_MARK(marks, 2, stream);
+        PK_LAUNCH(k_scatter_bins_b, dim3(p.ntiles), dim3(p.blk), 0, stream, digits32, p, ws.tile_hist, ws.bin_start, l1_64);
+        PK_MARK(marks, 3, stream);
+        PK_LAUNCH(k_sort_bins_b, dim3(p.nbins), dim3(p.blk), 0, stream, l1_64, p, ws.bin_start, ws.sorted, ws.bucket_start);
+        PK_MARK(marks, 4, stream);
     }
-    PK_MARK(marks, 1, stream);
-    PK_LAUNCH(k_scan_tiles, dim3((p.nbins + p.blk - 1) / p.blk), dim3(p.blk), 0, stream, ws.tile_hist, p.ntiles, p.nbins, ws.bin_total);
-    PK_LAUNCH(k_scan_bins, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.nbins, ws.bin_start);
-    PK_MARK(marks, 2, stream);
-    PK_LAUNCH(k_scatter_bins, dim3(p.ntiles, p.W), dim3(p.blk), 0, stream, ws.digits, p, ws.tile_hist, ws.bin_start, ws.l1);
-    PK_MARK(marks, 3, stream);
-    PK_LAUNCH(k_sort_bins, dim3(p.nbins), dim3(p.blk), 0, stream, ws.l1, p, ws.bin_start, ws.sorted, ws.bucket_start);
-    PK_MARK(marks, 4, stream);
 
     // K3, then the item levels until one warp stores everything that is left.
     PK_LAUNCH(k_accumulate, dim3(p.nthreads1 / p.blk_acc), dim3(p.blk_acc), 0, stream, ws.sorted, ws.bucket_start,
@@ -691,11 +1021,22 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
         src ^= 1;
     }
     PK_MARK(marks, 6, stream);
-    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.W), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
+    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.ngroups), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
     PK_MARK(marks, 7, stream);
-    PK_LAUNCH(k_window_weight, dim3(p.W), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
-    PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.W, prev, ws.result);
+    PK_LAUNCH(k_window_weight, dim3(p.ngroups), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
+    PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.ngroups, prev, ws.result);
     PK_MARK(marks, 8, stream);
+}
+
+// Builds the table of window multiples for n bases: table[w*n + i] = 2^(c*w) * bases[i],
+// affine, W rows.  cur is n XYZZ points of scratch.
+inline void pk_enqueue_table_build(const void *bases, u32 n, u32 c, u32 W, xyzz *cur, affine *table, pk_stream_t stream) {
+    const u32 blocks = (n + 127) / 128;
+    PK_LAUNCH(k_table_init, dim3(blocks), dim3(128), 0, stream, (const affine *)bases, n, cur, table);
+    for (u32 w = 1; w < W; ++w) {
+        PK_LAUNCH(k_table_double, dim3(blocks), dim3(128), 0, stream, cur, n, c);
+        PK_LAUNCH(k_table_normalize, dim3(((n + 7) / 8 + 127) / 128), dim3(128), 0, stream, cur, n, table + (size_t)w * n);
+    }
 }
 
 }  // namespace pk

@@ -35,8 +35,9 @@ def gather_partials(partial, group=None):
 
 
 def variable_base_msm_sharded(local_scalars, local_bases, group=None, *, window_bits: int = 0):
-    """Each rank passes its own slice (CUDA tensors); returns the affine sum of all
-    ranks' slices as an [8]-limb CUDA tensor on every rank."""
+    """Each rank passes its own slice (CUDA scalars; bases as a CUDA tensor or a
+    G1Bases registered on this rank's GPU); returns the affine sum of all ranks'
+    slices as an [8]-limb CUDA tensor on every rank."""
     from . import msm
 
     partial = msm.variable_base_msm_device(local_scalars, local_bases, window_bits=window_bits, partial=True)

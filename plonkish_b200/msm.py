@@ -39,17 +39,37 @@ def _as_u64(a, width: int, what: str) -> np.ndarray:
 class G1Bases:
     """Bases resident on one GPU (the SRS slice a ProverParam holds:
     MultilinearKzgProverParam.eqs[k], pcs/multilinear/kzg.rs:55-77;
-    UnivariateKzgProverParam.powers_of_s_g1, pcs/univariate/kzg.rs:24-30)."""
+    UnivariateKzgProverParam.powers_of_s_g1, pcs/univariate/kzg.rs:24-30).
 
-    def __init__(self, bases, device: int = 0):
-        arr = _as_u64(bases, 8, "bases")
-        self.n = arr.shape[0]
-        self.device = device
+    `bases` is a host [n, 8] uint64 array or a torch CUDA tensor of the same shape.
+    Registration expands the slice into a table of window multiples when it fits in
+    free HBM (mode 0), keeps plain bases (mode 1) or insists on the table (mode 2)."""
+
+    PLAIN, TABLE = 1, 2
+
+    def __init__(self, bases, device: int = 0, mode: int = 0):
         handle = ctypes.c_uint64(0)
-        _lib.check(
-            _lib.lib().plonkish_cuda_bases_register(device, arr.ctypes.data, self.n, ctypes.byref(handle)),
-            "plonkish_cuda_bases_register",
-        )
+        if hasattr(bases, "is_cuda"):
+            assert bases.is_cuda and bases.is_contiguous()
+            self.n = bases.numel() * bases.element_size() // AFFINE_BYTES
+            self.device = bases.device.index or 0
+            self._keepalive = bases  # mode 1 borrows the tensor's memory
+            rc = _lib.lib().plonkish_cuda_bases_register_device(self.device, bases.data_ptr(), self.n, mode, ctypes.byref(handle))
+            _lib.check(rc, "plonkish_cuda_bases_register_device")
+        else:
+            arr = _as_u64(bases, 8, "bases")
+            self.n = arr.shape[0]
+            self.device = device
+            if mode == 0:
+                rc = _lib.lib().plonkish_cuda_bases_register(device, arr.ctypes.data, self.n, ctypes.byref(handle))
+                _lib.check(rc, "plonkish_cuda_bases_register")
+            else:
+                import torch
+
+                dev_t = torch.from_numpy(arr.view(np.int64)).to(torch.device("cuda", device))
+                self._keepalive = dev_t
+                rc = _lib.lib().plonkish_cuda_bases_register_device(device, dev_t.data_ptr(), self.n, mode, ctypes.byref(handle))
+                _lib.check(rc, "plonkish_cuda_bases_register_device")
         self.handle = handle.value
 
     def __len__(self) -> int:
@@ -139,23 +159,29 @@ def _torch():
 def variable_base_msm_device(scalars, bases, out=None, *, window_bits: int = 0, partial: bool = False):
     """Device-resident MSM on torch CUDA tensors, enqueued on the current stream.
 
-    scalars: [n, 4] int64/uint64 CUDA tensor (raw limbs), bases: [n, 8].  Returns a
-    CUDA tensor holding the affine point ([8] limbs), or with partial=True the
-    projective XYZZ partial ([16] limbs) a rank contributes before the gather.
+    scalars: [n, 4] int64/uint64 CUDA tensor (raw limbs); bases: an [n, 8] CUDA tensor
+    or a G1Bases registered on the same device.  Returns a CUDA tensor holding the
+    affine point ([8] limbs), or with partial=True the projective XYZZ partial
+    ([16] limbs) a rank contributes before the gather.
     """
     torch = _torch()
-    assert scalars.is_cuda and bases.is_cuda and scalars.is_contiguous() and bases.is_contiguous()
+    assert scalars.is_cuda and scalars.is_contiguous()
     n = scalars.numel() * scalars.element_size() // SCALAR_BYTES
-    assert bases.numel() * bases.element_size() // AFFINE_BYTES >= n, "fewer bases than scalars"  # msm.rs:90
     dev = scalars.device.index if scalars.device.index is not None else torch.cuda.current_device()
     words = 16 if partial else 8
     if out is None:
         out = torch.empty(words, dtype=torch.int64, device=scalars.device)
     stream = torch.cuda.current_stream(scalars.device).cuda_stream
-    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_device(
-        dev, scalars.data_ptr(), bases.data_ptr(), n, window_bits,
-        None if partial else out.data_ptr(), out.data_ptr() if partial else None, stream,
-    )
+    o_aff, o_xyzz = (None, out.data_ptr()) if partial else (out.data_ptr(), None)
+    if isinstance(bases, G1Bases):
+        assert n <= bases.n, "more scalars than registered bases"  # msm.rs:90
+        assert bases.device == dev, "bases are registered on another device"
+        rc = _lib.lib().plonkish_cuda_msm_bn254_g1_device_resident(scalars.data_ptr(), bases.handle, n, o_aff, o_xyzz, stream)
+        _lib.check(rc, "plonkish_cuda_msm_bn254_g1_device_resident")
+        return out
+    assert bases.is_cuda and bases.is_contiguous()
+    assert bases.numel() * bases.element_size() // AFFINE_BYTES >= n, "fewer bases than scalars"  # msm.rs:90
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_device(dev, scalars.data_ptr(), bases.data_ptr(), n, window_bits, o_aff, o_xyzz, stream)
     _lib.check(rc, "plonkish_cuda_msm_bn254_g1_device")
     return out
 
@@ -185,9 +211,10 @@ def synth_bases_device(n: int, a: int, step: int, device=None, first: int = 0):
     return out
 
 
-def msm_plan(n: int, window_bits: int = 0, device: int = 0) -> dict:
+def msm_plan(n: int, window_bits: int = 0, device: int = 0, bases: Optional["G1Bases"] = None) -> dict:
     out = (ctypes.c_uint32 * 8)()
-    _lib.check(_lib.lib().plonkish_cuda_msm_plan(device, n, window_bits, out), "plonkish_cuda_msm_plan")
+    handle = bases.handle if bases is not None else 0
+    _lib.check(_lib.lib().plonkish_cuda_msm_plan(device, n, window_bits, handle, out), "plonkish_cuda_msm_plan")
     keys = ("window_bits", "windows", "hi_bits", "lo_bits", "idx_bits", "tile", "run_length", "accumulate_threads")
     return dict(zip(keys, [int(v) for v in out]))
 
@@ -202,7 +229,10 @@ def profile_stages_device(scalars, bases, *, window_bits: int = 0) -> dict:
     dev = scalars.device.index if scalars.device.index is not None else torch.cuda.current_device()
     torch.cuda.synchronize(scalars.device)
     out = (ctypes.c_double * 9)()
-    rc = _lib.lib().plonkish_cuda_msm_profile_device(dev, scalars.data_ptr(), bases.data_ptr(), n, window_bits, None, out)
+    if isinstance(bases, G1Bases):
+        rc = _lib.lib().plonkish_cuda_msm_profile_device(dev, scalars.data_ptr(), None, bases.handle, n, 0, None, out)
+    else:
+        rc = _lib.lib().plonkish_cuda_msm_profile_device(dev, scalars.data_ptr(), bases.data_ptr(), 0, n, window_bits, None, out)
     _lib.check(rc, "plonkish_cuda_msm_profile_device")
     return dict(zip(STAGES, [float(v) for v in out]))
 

@@ -74,4 +74,27 @@ int emul_msm(const void *scalars, const void *bases, u32 n, u32 c_override, u32 
     free(arena);
     return 0;
 }
+
+// Mode 1: expand the first n_table bases into the table of window multiples with the
+// product's table kernels, then run an MSM over the first n_use points through it.
+int emul_msm_table(const void *scalars, const void *bases, u32 n_table, u32 n_use, u32 c, u32 sm_count, void *out_affine64) {
+    if (n_use == 0) { memset(out_affine64, 0, 64); return 0; }
+    if (!c) c = pk_table_window_bits(n_table);
+    const u32 W = pk_windows_for(c);
+    affine *table = (affine *)aligned_alloc(256, sizeof(affine) * (size_t)W * n_table);
+    xyzz *cur = (xyzz *)aligned_alloc(256, sizeof(xyzz) * (size_t)n_table);
+    pk_enqueue_table_build(bases, n_table, c, W, cur, table, 0);
+    MsmPlan p = pk_make_plan_b(n_use, c, n_table, sm_count);
+    p.blk = 32;
+    size_t bytes = pk_workspace_bytes(p);
+    void *arena = aligned_alloc(256, bytes);
+    memset(arena, 0xA5, bytes);
+    MsmWorkspace ws = pk_carve_workspace(p, arena);
+    pk_enqueue_msm(p, scalars, table, ws, nullptr, 0);
+    affine out;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, 0, ws.result, 1u, &out, (xyzz *)nullptr);
+    memcpy(out_affine64, &out, 64);
+    free(arena); free(cur); free(table);
+    return 0;
+}
 }

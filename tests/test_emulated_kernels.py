@@ -25,6 +25,16 @@ def emul():
     lib.emul_fq_mul.argtypes = [vp, vp, vp]
     lib.emul_fr_to_canonical.argtypes = [vp, vp]
     lib.emul_plan.argtypes = [u32, u32, u32, vp]
+    lib.emul_msm_table.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+
+    def msm_table(sc, bs, n_use, c=0, sms=148):
+        sc = np.ascontiguousarray(sc, dtype=np.uint64)
+        bs = np.ascontiguousarray(bs, dtype=np.uint64)
+        out = np.zeros(8, dtype=np.uint64)
+        lib.emul_msm_table(sc.ctypes.data, bs.ctypes.data, bs.shape[0], n_use, c, sms, out.ctypes.data)
+        return out
+
+    lib.msm_table = msm_table
 
     def msm(sc, bs, c=0, sms=148, serial_items=0):
         sc = np.ascontiguousarray(sc, dtype=np.uint64)
@@ -104,3 +114,23 @@ def test_skewed_and_degenerate_inputs(emul, oracle):
     idb = bs[:300].copy()
     idb[::3] = 0
     assert (emul.msm(sc, idb, 10, 1) == oracle.variable_base_msm(sc, idb, 2)).all()
+
+
+@pytest.mark.parametrize("n,use,c,sms", [(1, 1, 8, 148), (300, 77, 10, 2), (500, 500, 13, 1), (100, 100, 20, 1), (2000, 2000, 0, 1)])
+def test_table_of_window_multiples(emul, oracle, n, use, c, sms):
+    # mode 1: T[w][i] = 2^(c*w) * P_i built by the table kernels, one bucket set.
+    sc = oracle.random_scalars(use, n + use)
+    bs = oracle.known_dlog_bases(3, 5, n)
+    assert (emul.msm_table(sc, bs, use, c, sms) == oracle.known_dlog_answer(3, 5, sc)).all()
+
+
+def test_table_with_degenerate_inputs(emul, oracle):
+    n = 300
+    bs = oracle.known_dlog_bases(9, 2, n)
+    bs[::7] = 0
+    for vals, c in [([0] * n, 8), ([br.R - 1] * n, 9), ([0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF123456789 % br.R] * n, 12)]:
+        sc = _mont(vals)
+        assert (emul.msm_table(sc, bs, n, c, 1) == oracle.variable_base_msm(sc, bs, 2)).all()
+    dup = np.repeat(oracle.known_dlog_bases(9, 2, 1), 200, axis=0)
+    sc = oracle.random_scalars(200, 3)
+    assert (emul.msm_table(sc, dup, 200, 9, 1) == oracle.variable_base_msm(sc, dup, 2)).all()

@@ -204,6 +204,61 @@ def test_registered_bases_and_prefixes(pk, oracle):
     reg.release()
 
 
+@pytest.mark.parametrize("n", [1, 33, 1000, 1 << 13, (1 << 16) + 7])
+def test_table_of_window_multiples_matches_oracle(pk, oracle, n):
+    # Resident bases expanded into T[w][i] = 2^(c*w) * P_i: one bucket set, wider windows.
+    import torch
+
+    bs = oracle.known_dlog_bases(6, 7, n)
+    reg = pk.G1Bases(bs, mode=pk.G1Bases.TABLE)
+    plain = pk.G1Bases(bs, mode=pk.G1Bases.PLAIN)
+    for m in sorted({n, max(1, n // 2), max(1, n - 1), 1}):
+        sc = oracle.random_scalars(m, m + 13)
+        want = oracle.known_dlog_answer(6, 7, sc)
+        assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes(), m
+        assert pk.variable_base_msm(sc, plain).tobytes() == want.tobytes(), m
+        d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+        assert pk.variable_base_msm_device(d_sc, reg).cpu().numpy().view(np.uint64).tobytes() == want.tobytes(), m
+    reg.release()
+    plain.release()
+
+
+def test_table_with_skew_identity_and_duplicate_bases(pk, oracle):
+    n = 1 << 12
+    rng = np.random.default_rng(9)
+    bs = oracle.known_dlog_bases(2, 9, n)
+    bs[::9] = 0            # identity bases stay identity in every table row
+    bs[5::64] = bs[5]      # repeated bases force P + P inside buckets
+    reg = pk.G1Bases(bs, mode=pk.G1Bases.TABLE)
+
+    def mont(vals):
+        return np.frombuffer(b"".join(br.scalar_to_bytes(int(v)) for v in vals), dtype=np.uint64).reshape(-1, 4).copy()
+
+    for name, vals in {
+        "uniform": None,
+        "selector": [[0, 1, br.R - 1][int(x)] for x in rng.integers(0, 3, n)],
+        "all-minus-one": [br.R - 1] * n,
+        "all-zero": [0] * n,
+        "small": [int(x) for x in rng.integers(0, 3 * n, n)],
+    }.items():
+        sc = oracle.random_scalars(n, 4) if vals is None else mont(vals)
+        assert pk.variable_base_msm(sc, reg).tobytes() == oracle.variable_base_msm(sc, bs).tobytes(), name
+    reg.release()
+
+
+def test_table_at_2pow22_known_discrete_log(pk, oracle):
+    import torch
+
+    n = 1 << 22
+    sc = pk.random_scalars(n, seed=2222)
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    d_bs = pk.synth_bases_device(n, 3, 5)
+    reg = pk.G1Bases(d_bs, mode=pk.G1Bases.TABLE)
+    got = pk.variable_base_msm_device(d_sc, reg).cpu().numpy().view(np.uint64)
+    assert got.tobytes() == oracle.known_dlog_answer(3, 5, sc).tobytes()
+    reg.release()
+
+
 def test_linearity(pk, oracle):
     # MSM(s, B) + MSM(t, B) == MSM(s + t, B), checked through the oracle's field/curve ops.
     n = 5000

@@ -86,6 +86,28 @@ def timing(log_n, cs=(0,)):
             "parity": ok, "ms": round(min(times), 3), "mpts_per_s": round(n / min(times) / 1e3, 1),
             "stages_ms": {k: round(v, 3) for k, v in stages.items()}, "plan": plan,
         }
+    # resident bases with the table of window multiples
+    t0 = time.time()
+    reg = pk.G1Bases(d_bs)
+    torch.cuda.synchronize()
+    t_reg = time.time() - t0
+    got = pk.variable_base_msm_device(d_sc, reg).cpu().numpy().view(np.uint64)
+    ok = got.tobytes() == want.tobytes()
+    times = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        e0.record()
+        pk.variable_base_msm_device(d_sc, reg)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    stages = pk.profile_stages_device(d_sc, reg)
+    plan = pk.msm_plan(n, 0, 0, bases=reg)
+    out[f"table c={plan['window_bits']}"] = {
+        "parity": ok, "ms": round(min(times), 3), "mpts_per_s": round(n / min(times) / 1e3, 1), "register_s": round(t_reg, 3),
+        "stages_ms": {k: round(v, 3) for k, v in stages.items()}, "plan": plan,
+    }
+    reg.release()
     return out
 
 
