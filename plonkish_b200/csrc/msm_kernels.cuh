@@ -36,7 +36,11 @@
 #define PK_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; type *name = reinterpret_cast<type *>(name##_raw)
 typedef cudaStream_t pk_stream_t;
 #define PK_MARK(marks, i, stream) do { if (marks) cudaEventRecord((cudaEvent_t)(marks)->ev[i], stream); } while (0)
+#define PK_MEMSET0(ptr, bytes, stream) cudaMemsetAsync(ptr, 0, bytes, stream)
+#define PK_SET_SMEM(kern, bytes) do { if ((bytes) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); } while (0)
 #else
+#define PK_MEMSET0(ptr, bytes, stream) memset(ptr, 0, bytes)
+#define PK_SET_SMEM(kern, bytes) ((void)0)
 #define PK_MARK(marks, i, stream) ((void)0)
 #define PK_LAUNCH(kern, grid, block, smem, stream, ...) emul::launch(grid, block, smem, [&] { kern(__VA_ARGS__); })
 #define PK_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emul::g_dyn_smem)
@@ -71,6 +75,7 @@ struct MsmPlan {
     u32 red_blocks;   // K4 blocks per window
     u32 blk;          // threads per block of the streaming kernels (256; tests shrink it)
     u32 serial_items; // item levels above this many items let every lane fold 8 items serially first
+    u32 blk_stage;    // threads per block of the staged partition kernels (512; tests shrink it)
     u32 mode;         // 0: one bucket set per window (any bases); 1: one bucket set, bases are a table of
                       //    precomputed window multiples T[w][i] = 2^(c*w) * P_i (resident bases only)
     u32 ngroups;      // bucket sets: W in mode 0, 1 in mode 1
@@ -132,6 +137,7 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     p.red_blocks = (p.red_threads + 255) / 256;
     p.blk = 256;
     p.serial_items = 8192;
+    p.blk_stage = 512;
     p.mode = 0;
     p.ngroups = p.W;
     p.stride = 0;
@@ -193,6 +199,7 @@ struct MsmWorkspace {
     u32 *l1;            // [n * W] entries after the bin scatter (mode 1: u64 entries)
     u32 *sorted;        // [n * W] (sign << 31 | point index), ordered by (window, bucket)
     u32 *bucket_start;  // [nbuckets + 1]
+    u32 *bucket_cur;    // [nbuckets + 1] mode 1: per-bucket counts, then cursors
     xyzz *bucket_sum;   // [nbuckets]
     u32 *item_keys[2];  // ping-pong item lists for the segmented reduction levels
     xyzz *item_pts[2];
@@ -213,6 +220,7 @@ inline size_t pk_workspace_bytes(const MsmPlan &p) {
     s += pk_align256(sizeof(u32) * (p.nbins + 1));
     s += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
     s += pk_align256(sizeof(u32) * e);
+    s += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     s += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     s += pk_align256(sizeof(xyzz) * p.nbuckets);
     s += 2 * pk_align256(sizeof(u32) * items);
@@ -235,6 +243,7 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     w.l1 = (u32 *)q; q += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
     w.sorted = (u32 *)q; q += pk_align256(sizeof(u32) * e);
     w.bucket_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
+    w.bucket_cur = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     w.bucket_sum = (xyzz *)q; q += pk_align256(sizeof(xyzz) * p.nbuckets);
     for (int k = 0; k < 2; ++k) { w.item_keys[k] = (u32 *)q; q += pk_align256(sizeof(u32) * items); }
     for (int k = 0; k < 2; ++k) { w.item_pts[k] = (xyzz *)q; q += pk_align256(sizeof(xyzz) * items); }
@@ -519,119 +528,250 @@ __global__ void __launch_bounds__(256) k_decompose_b(const uint4 *__restrict__ s
         }
     }
     __syncthreads();
-    u32 *out = tile_hist + (size_t)tile * p.HI;
-    for (u32 k = threadIdx.x; k < p.HI; k += blockDim.x) out[k] = hist[k];
+    // tile_hist here is the global per-bin count (zeroed before the launch).
+    for (u32 k = threadIdx.x; k < p.HI; k += blockDim.x) {
+        if (hist[k]) atomicAdd(&tile_hist[k], hist[k]);
+    }
 }
 
-// One block per tile, all windows.  Entry: low bucket bits << 32 | sign << 31 | table index.
-__global__ void __launch_bounds__(256) k_scatter_bins_b(const u32 *__restrict__ digits, MsmPlan p, const u32 *__restrict__ tile_hist,
-                                                        const u32 *__restrict__ bin_start, unsigned long long *__restrict__ l1) {
-    __shared__ u32 cursor[1024];
-    const u32 tile = blockIdx.x;
-    for (u32 h = threadIdx.x; h < p.HI; h += blockDim.x) cursor[h] = bin_start[h] + tile_hist[(size_t)tile * p.HI + h];
+// ---------------------------------------------------------------- staged partition
+// Block-wide exclusive scan of cnt[0..R) into start[0..R); returns the total.  scratch: 33 words.
+PK_HD u32 block_exclusive_scan(const u32 *cnt, u32 *start, u32 R, u32 *scratch) {
+    const u32 per = (R + blockDim.x - 1) / blockDim.x;
+    const u32 first = threadIdx.x * per;
+    u32 sum = 0;
+    for (u32 k = 0; k < per; ++k) {
+        if (first + k < R) sum += cnt[first + k];
+    }
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    u32 incl = sum;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) scratch[wid] = incl;
     __syncthreads();
+    if (wid == 0) {
+        const u32 nw = (blockDim.x + 31) >> 5;
+        u32 w = (lane < nw) ? scratch[lane] : 0;
+        u32 wi = w;
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        scratch[lane] = wi - w;           // exclusive warp offsets
+        if (lane == 31) scratch[32] = wi; // grand total
+    }
+    __syncthreads();
+    u32 run = scratch[wid] + incl - sum;
+    for (u32 k = 0; k < per; ++k) {
+        if (first + k < R) {
+            start[first + k] = run;
+            run += cnt[first + k];
+        }
+    }
+    const u32 total = scratch[32];
+    __syncthreads();
+    return total;
+}
+
+// Shared-memory view used by the staged kernels (dynamic smem, all u32):
+//   lcnt[R] | lstart[R] | gbase[R] | scratch[64] | sval[S] | saux[S]
+struct StageSmem {
+    u32 *lcnt, *lstart, *gbase, *scratch, *sval, *saux;
+};
+PK_HD StageSmem stage_carve(u32 *base, u32 R, u32 S) {
+    StageSmem m;
+    m.lcnt = base; m.lstart = base + R; m.gbase = base + 2 * R; m.scratch = base + 3 * R;
+    m.sval = base + 3 * R + 64; m.saux = m.sval + S;
+    return m;
+}
+inline size_t stage_smem_bytes(u32 R, u32 S) { return sizeof(u32) * (3 * (size_t)R + 64 + 2 * (size_t)S); }
+
+// Partition the block's EPT*blockDim items by digit: rank in shared memory, stage the
+// items sorted by digit, claim one contiguous global range per (block, digit) run with a
+// single atomicAdd on gcursor[digit], then write the runs out with consecutive lanes on
+// consecutive addresses.  Needs lcnt zeroed on entry; leaves it zeroed.
+template <int EPT>
+PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val)[EPT], const u32 (&aux)[EPT], const bool (&ok)[EPT],
+                            const StageSmem &m, u32 *gcursor, u32 *out_val, u16 *out_aux) {
+    u32 rank[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) rank[e] = ok[e] ? atomicAdd(&m.lcnt[dig[e]], 1u) : 0u;
+    __syncthreads();
+    const u32 total = block_exclusive_scan(m.lcnt, m.lstart, R, m.scratch);
+    for (u32 d = threadIdx.x; d < R; d += blockDim.x) {
+        const u32 c = m.lcnt[d];
+        if (c) m.gbase[d] = atomicAdd(&gcursor[d], c);
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        if (ok[e]) {
+            const u32 pos = m.lstart[dig[e]] + rank[e];
+            m.sval[pos] = val[e];
+            m.saux[pos] = (dig[e] << 16) | aux[e];
+        }
+    }
+    __syncthreads();
+    for (u32 q = threadIdx.x; q < total; q += blockDim.x) {
+        const u32 kb = m.saux[q];
+        const u32 d = kb >> 16;
+        const u32 g = m.gbase[d] + (q - m.lstart[d]);
+        out_val[g] = m.sval[q];
+        if (out_aux) out_aux[g] = (u16)(kb & 0xffffu);
+    }
+    __syncthreads();
+    for (u32 d = threadIdx.x; d < R; d += blockDim.x) m.lcnt[d] = 0;
+    __syncthreads();
+}
+
+// Level 1: one block per tile of points, all windows.  Partitions (bucket, table index)
+// pairs by the high bucket bits into l1_val (sign << 31 | table index) and l1_key (low bits).
+#define PK_STAGE_EPT 16
+__global__ void __launch_bounds__(512) k_scatter_staged_b(const u32 *__restrict__ digits, MsmPlan p, u32 *__restrict__ gcursor,
+                                                          u32 *__restrict__ l1_val, u16 *__restrict__ l1_key) {
+    PK_DYN_SMEM(u32, smem);
+    const u32 S = blockDim.x * PK_STAGE_EPT;
+    const StageSmem m = stage_carve(smem, p.HI, S);
+    for (u32 d = threadIdx.x; d < p.HI; d += blockDim.x) m.lcnt[d] = 0;
+    __syncthreads();
+    const u32 tile = blockIdx.x;
     const u32 beg = tile * p.tile;
     const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
     const u32 lo_mask = (1u << p.lo_bits) - 1u;
     for (u32 w = 0; w < p.W; ++w) {
         const u32 *row = digits + (size_t)w * p.n_pad;
         const u32 base_idx = w * p.stride;
-        constexpr int U = 4;  // independent 128-bit loads in flight per thread
-        for (u32 i0 = beg + 4 * threadIdx.x; i0 < end; i0 += 4 * blockDim.x * U) {
-            uint4 v[U];
+        for (u32 s0 = beg; s0 < end; s0 += S) {
+            u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
+            bool ok[PK_STAGE_EPT];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const u32 i = i0 + (u32)u * 4 * blockDim.x;
-                v[u] = (i < end) ? __ldg(reinterpret_cast<const uint4 *>(row + i)) : make_uint4(~0u, ~0u, ~0u, ~0u);
-            }
-            u32 pos[U * 4];
-            unsigned long long ent[U * 4];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const u32 i = i0 + (u32)u * 4 * blockDim.x;
-                const u32 d4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            for (int u = 0; u < PK_STAGE_EPT / 4; ++u) {
+                const u32 i = s0 + 4 * (threadIdx.x + (u32)u * blockDim.x);
+                const uint4 v = (i < end) ? __ldg(reinterpret_cast<const uint4 *>(row + i)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+                const u32 d4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const u32 d = d4[k];
-                    const bool valid = (i + k < end) && d != 0xffffffffu;
                     const u32 b = d & 0x7fffffffu;
-                    ent[u * 4 + k] = ((unsigned long long)(b & lo_mask) << 32) | (d & 0x80000000u) | (base_idx + i + (u32)k);
-                    pos[u * 4 + k] = valid ? atomicAdd(&cursor[b >> p.lo_bits], 1u) : 0xffffffffu;
+                    ok[u * 4 + k] = (i + k < end) && d != 0xffffffffu;
+                    dig[u * 4 + k] = b >> p.lo_bits;
+                    aux[u * 4 + k] = b & lo_mask;
+                    val[u * 4 + k] = (d & 0x80000000u) | (base_idx + i + (u32)k);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < U * 4; ++j) {
-                if (pos[j] != 0xffffffffu) l1[pos[j]] = ent[j];
-            }
+            staged_partition<PK_STAGE_EPT>(p.HI, dig, val, aux, ok, m, gcursor, l1_val, l1_key);
         }
     }
 }
 
-// One block per high-bits bin: counting sort on the low bucket bits (up to 2^12 of them).
-__global__ void __launch_bounds__(256) k_sort_bins_b(const unsigned long long *__restrict__ l1, MsmPlan p, const u32 *__restrict__ bin_start,
-                                                     u32 *__restrict__ sorted, u32 *__restrict__ bucket_start) {
+// Level 2 histogram: grid (nbins, nslices).  Block (bin, s) counts the low bucket bits of
+// slices s, s + nslices, ... of its bin and adds them to the global per-bucket counts.
+__global__ void __launch_bounds__(256) k_bucket_hist_b(const u16 *__restrict__ l1_key, MsmPlan p, const u32 *__restrict__ bin_start,
+                                                       u32 slice, u32 *__restrict__ bucket_cnt) {
     __shared__ u32 cnt[4096];
-    __shared__ u32 part[256];
     const u32 bin = blockIdx.x;
     const u32 beg = bin_start[bin], end = bin_start[bin + 1];
+    if (beg + blockIdx.y * slice >= end) return;
     const u32 nlo = 1u << p.lo_bits;
     for (u32 k = threadIdx.x; k < nlo; k += blockDim.x) cnt[k] = 0;
     __syncthreads();
-    constexpr int U = 8;  // independent loads in flight per thread
-    for (u32 q0 = beg + threadIdx.x; q0 < end; q0 += blockDim.x * U) {
-        unsigned long long e[U];
+    constexpr int U = 8;
+    for (u32 sb = beg + blockIdx.y * slice; sb < end; sb += gridDim.y * slice) {
+        const u32 se = (sb + slice < end) ? sb + slice : end;
+        for (u32 q0 = sb + threadIdx.x; q0 < se; q0 += blockDim.x * U) {
+            u32 k[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const u32 q = q0 + (u32)u * blockDim.x;
-            e[u] = (q < end) ? l1[q] : 0ull;
-        }
+            for (int u = 0; u < U; ++u) {
+                const u32 q = q0 + (u32)u * blockDim.x;
+                k[u] = (q < se) ? (u32)l1_key[q] : 0xffffffffu;
+            }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (q0 + (u32)u * blockDim.x < end) atomicAdd(&cnt[(u32)(e[u] >> 32)], 1u);
+            for (int u = 0; u < U; ++u) {
+                if (k[u] != 0xffffffffu) atomicAdd(&cnt[k[u]], 1u);
+            }
         }
     }
     __syncthreads();
-    // block-wide exclusive scan of cnt[0..nlo), offset by beg
-    const u32 per = (nlo + blockDim.x - 1) / blockDim.x;
+    for (u32 k = threadIdx.x; k < nlo; k += blockDim.x) {
+        if (cnt[k]) atomicAdd(&bucket_cnt[(size_t)bin * nlo + k], cnt[k]);
+    }
+}
+
+// In-place exclusive scan of v[0..n) (one block of 1024); copy[0..n] receives the same
+// offsets plus the total at copy[n].  v then serves as the level's cursor array.
+__global__ void __launch_bounds__(1024) k_scan_inplace(u32 *__restrict__ v, u32 n, u32 *__restrict__ copy) {
+    __shared__ u32 scratch[64];
+    const u32 per = (n + blockDim.x - 1) / blockDim.x;
     const u32 first = threadIdx.x * per;
     u32 sum = 0;
     for (u32 k = 0; k < per; ++k) {
-        if (first + k < nlo) sum += cnt[first + k];
+        if (first + k < n) sum += v[first + k];
     }
-    part[threadIdx.x] = sum;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    u32 incl = sum;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) scratch[wid] = incl;
     __syncthreads();
-    for (u32 d = 1; d < blockDim.x; d <<= 1) {
-        const u32 v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (wid == 0) {
+        u32 w = scratch[lane];
+        u32 wi = w;
+#pragma unroll
+        for (u32 d = 1; d < 32; d <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        scratch[lane] = wi - w;
+        if (lane == 31) scratch[32] = wi;
     }
-    u32 run = beg + part[threadIdx.x] - sum;
+    __syncthreads();
+    u32 run = scratch[wid] + incl - sum;
     for (u32 k = 0; k < per; ++k) {
-        if (first + k < nlo) {
-            const u32 v = cnt[first + k];
-            cnt[first + k] = run;
-            bucket_start[(size_t)bin * nlo + first + k] = run;
-            run += v;
+        if (first + k < n) {
+            const u32 c = v[first + k];
+            v[first + k] = run;
+            copy[first + k] = run;
+            run += c;
         }
     }
-    if (bin == p.nbins - 1 && threadIdx.x == 0) bucket_start[p.nbuckets] = end;
+    if (threadIdx.x == 0) copy[n] = scratch[32];
+}
+
+// Level 2 scatter: same slicing as the histogram; partitions each slice by the low bucket
+// bits into the final (window-free) order.  gcursor = per-bucket cursors (bucket starts).
+__global__ void __launch_bounds__(512) k_bucket_scatter_staged_b(const u32 *__restrict__ l1_val, const u16 *__restrict__ l1_key, MsmPlan p,
+                                                                 const u32 *__restrict__ bin_start, u32 slice, u32 *__restrict__ gcursor,
+                                                                 u32 *__restrict__ sorted) {
+    PK_DYN_SMEM(u32, smem);
+    const u32 bin = blockIdx.x;
+    const u32 beg = bin_start[bin], end = bin_start[bin + 1];
+    if (beg + blockIdx.y * slice >= end) return;
+    const u32 nlo = 1u << p.lo_bits;
+    const u32 S = blockDim.x * PK_STAGE_EPT;
+    const StageSmem m = stage_carve(smem, nlo, S);
+    for (u32 d = threadIdx.x; d < nlo; d += blockDim.x) m.lcnt[d] = 0;
     __syncthreads();
-    for (u32 q0 = beg + threadIdx.x; q0 < end; q0 += blockDim.x * U) {
-        unsigned long long e[U];
-        u32 pos[U];
+    u32 *cur = gcursor + (size_t)bin * nlo;
+    for (u32 sb = beg + blockIdx.y * slice; sb < end; sb += gridDim.y * slice) {
+        const u32 se = (sb + slice < end) ? sb + slice : end;
+        for (u32 s0 = sb; s0 < se; s0 += S) {
+            u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
+            bool ok[PK_STAGE_EPT];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const u32 q = q0 + (u32)u * blockDim.x;
-            e[u] = (q < end) ? l1[q] : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            pos[u] = (q0 + (u32)u * blockDim.x < end) ? atomicAdd(&cnt[(u32)(e[u] >> 32)], 1u) : 0xffffffffu;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (pos[u] != 0xffffffffu) sorted[pos[u]] = (u32)e[u];
+            for (int e = 0; e < PK_STAGE_EPT; ++e) {
+                const u32 q = s0 + threadIdx.x + (u32)e * blockDim.x;
+                ok[e] = q < se;
+                dig[e] = ok[e] ? (u32)l1_key[q] : 0u;
+                val[e] = ok[e] ? l1_val[q] : 0u;
+                aux[e] = 0;
+            }
+            staged_partition<PK_STAGE_EPT>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr);
         }
     }
 }
@@ -984,22 +1124,35 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
         PK_MARK(marks, 4, stream);
     } else {
         u32 *digits32 = reinterpret_cast<u32 *>(ws.digits);
-        unsigned long long *l1_64 = reinterpret_cast<unsigned long long *>(ws.l1);
-#define PK_DECOMPOSE_B(C) case C: PK_LAUNCH(k_decompose_b<C>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.tile_hist); break;
+        const size_t emax = (size_t)p.n * p.W;
+        u32 *l1_val = ws.l1;
+        u16 *l1_key = reinterpret_cast<u16 *>(ws.l1 + emax);
+        PK_MEMSET0(ws.bin_total, sizeof(u32) * p.HI, stream);
+        PK_MEMSET0(ws.bucket_cur, sizeof(u32) * (p.nbuckets + 1), stream);
+#define PK_DECOMPOSE_B(C) case C: PK_LAUNCH(k_decompose_b<C>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
         switch (p.c) {
             PK_DECOMPOSE_B(8) PK_DECOMPOSE_B(9) PK_DECOMPOSE_B(10) PK_DECOMPOSE_B(11) PK_DECOMPOSE_B(12)
             PK_DECOMPOSE_B(13) PK_DECOMPOSE_B(14) PK_DECOMPOSE_B(15) PK_DECOMPOSE_B(16) PK_DECOMPOSE_B(17)
             PK_DECOMPOSE_B(18) PK_DECOMPOSE_B(19) PK_DECOMPOSE_B(20) PK_DECOMPOSE_B(21)
-            default: PK_LAUNCH(k_decompose_b<22>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.tile_hist); break;
+            default: PK_LAUNCH(k_decompose_b<22>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
         }
 #undef PK_DECOMPOSE_B
         PK_MARK(marks, 1, stream);
-        PK_LAUNCH(k_scan_tiles, dim3((p.nbins + p.blk - 1) / p.blk), dim3(p.blk), 0, stream, ws.tile_hist, p.ntiles, p.nbins, ws.bin_total);
-        PK_LAUNCH(k_scan_bins, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.nbins, ws.bin_start);
+        // bin_total becomes the level-1 cursor array, bin_start the bin offsets (+ total).
+        PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.HI, ws.bin_start);
         PK_MARK(marks, 2, stream);
-        PK_LAUNCH(k_scatter_bins_b, dim3(p.ntiles), dim3(p.blk), 0, stream, digits32, p, ws.tile_hist, ws.bin_start, l1_64);
+        const u32 S = p.blk_stage * PK_STAGE_EPT;
+        const size_t smem1 = stage_smem_bytes(p.HI, S);
+        PK_SET_SMEM(k_scatter_staged_b, smem1);
+        PK_LAUNCH(k_scatter_staged_b, dim3(p.ntiles), dim3(p.blk_stage), smem1, stream, digits32, p, ws.bin_total, l1_val, l1_key);
         PK_MARK(marks, 3, stream);
-        PK_LAUNCH(k_sort_bins_b, dim3(p.nbins), dim3(p.blk), 0, stream, l1_64, p, ws.bin_start, ws.sorted, ws.bucket_start);
+        const u32 slice = 4 * S, nslices = 8;
+        PK_LAUNCH(k_bucket_hist_b, dim3(p.nbins, nslices), dim3(p.blk), 0, stream, l1_key, p, ws.bin_start, slice, ws.bucket_cur);
+        PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.bucket_start);
+        const size_t smem2 = stage_smem_bytes(1u << p.lo_bits, S);
+        PK_SET_SMEM(k_bucket_scatter_staged_b, smem2);
+        PK_LAUNCH(k_bucket_scatter_staged_b, dim3(p.nbins, nslices), dim3(p.blk_stage), smem2, stream, l1_val, l1_key, p, ws.bin_start, slice,
+                  ws.bucket_cur, ws.sorted);
         PK_MARK(marks, 4, stream);
     }
 

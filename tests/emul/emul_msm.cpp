@@ -86,6 +86,7 @@ int emul_msm_table(const void *scalars, const void *bases, u32 n_table, u32 n_us
     pk_enqueue_table_build(bases, n_table, c, W, cur, table, 0);
     MsmPlan p = pk_make_plan_b(n_use, c, n_table, sm_count);
     p.blk = 32;
+    p.blk_stage = 32;
     size_t bytes = pk_workspace_bytes(p);
     void *arena = aligned_alloc(256, bytes);
     memset(arena, 0xA5, bytes);
