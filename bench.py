@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plain-bases", action="store_true", help="do not expand the resident bases into the table of window multiples")
+    ap.add_argument("--prove-k", type=int, default=24, help="k of the HyperPlonk prove MSM-sequence surrogate (0 = skip)")
     return ap.parse_args()
 
 
@@ -144,6 +145,49 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ------------------------------------------------- HyperPlonk::prove MSM-sequence surrogate
+def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
+    """The MSM calls HyperPlonk::prove makes for vanilla_plonk at 2^k rows (SURVEY.md §3.1):
+    4 commits of 2^k points (3 witness polys + 1 permutation z-poly, backend/hyperplonk.rs:201,
+    251-252) and the k quotient commitments of MultilinearKzg::open with 2^(k-1), ..., 2, 1 points
+    (kzg.rs:291-293), each a blocking host-scalar call against the resident eqs[i] slice."""
+    n = 1 << k
+    d_bases = pk.synth_bases_device(n, 7, 3, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    regs = [pk.G1Bases(d_bases[: 1 << i].contiguous()) for i in range(k + 1)]
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    host_t = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    host = host_t.numpy().view(np.uint64)
+    host[:] = pk.random_scalars(n, seed=4242)
+
+    def run():
+        outs = [pk.variable_base_msm(host, regs[k]) for _ in range(4)]
+        outs += [pk.variable_base_msm(host[: 1 << i], regs[i]) for i in reversed(range(k))]
+        return outs
+
+    run()
+    t0 = time.perf_counter()
+    outs = run()
+    gpu_ms = (time.perf_counter() - t0) * 1e3
+    res = {"k": k, "msm_calls": 4 + k, "points": 4 * n + n - 1, "gpu_ms": gpu_ms, "resident_srs_setup_s": setup_s}
+    if cpu:
+        from oracle import pyoracle as po
+
+        cores = po.host_threads()
+        bases_h = d_bases.cpu().numpy().view(np.uint64)
+        t0 = time.perf_counter()
+        ref = [po.variable_base_msm(host, bases_h, cores) for _ in range(4)]
+        ref += [po.variable_base_msm(host[: 1 << i], bases_h[: 1 << i], cores) for i in reversed(range(k))]
+        res["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+        res["cpu_cores"] = cores
+        res["bit_exact_vs_cpu"] = bool(all((a == b).all() for a, b in zip(outs, ref)))
+    for r in regs:
+        r.release()
+    return res
 
 
 # ------------------------------------------------------------------------- our arm
@@ -333,6 +377,16 @@ def run_ours(args) -> None:
             "sample": f"first 2^{log_c} points of the step's inputs, one pass, C port of msm.rs:84-181 with {cores} pthreads; "
                       "GPU result on the same sample checked bit-exact",
         }
+    if rank == 0 and not distributed and args.prove_k:
+        del d_scalars, d_bases
+        reg.release()
+        torch.cuda.empty_cache()
+        seq = {"what": "MSM calls of HyperPlonk::prove for vanilla_plonk (4 x 2^k + 2^(k-1) + ... + 1 points), host scalars, resident SRS; "
+                       "the field-only prover work between the calls stays in the Rust caller and is not included"}
+        seq["k%d" % args.prove_k] = prove_msm_sequence(pk, torch, np, args.prove_k, dev, cpu=False)
+        if not args.no_cpu_baseline:
+            seq["k20"] = prove_msm_sequence(pk, torch, np, min(20, args.prove_k), dev, cpu=True)
+        line["hyperplonk_prove_msm"] = seq
     if rank == 0:
         print(json.dumps(line))
     if distributed:

@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplonkish_cuda.so")
+# PLONKISH_CUDA_LIB overrides the path (A/B builds of the same ABI).
+LIB_PATH = os.environ.get("PLONKISH_CUDA_LIB") or os.path.join(_HERE, "libplonkish_cuda.so")
 
 # Every symbol include/plonkish_cuda.h declares (checked by tests/test_abi.py).
 EXPORTS = (

@@ -61,6 +61,8 @@ struct Ctx {
     int dev = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of scalar chunks, overlapped with the compute stream
+    cudaEvent_t chunk_ready[16] = {};
     cudaEvent_t last_done = nullptr;  // end of the last enqueued MSM: orders arena reuse across streams
     bool has_last = false;
     DeviceBuffer arena, scalars, bases_tmp, partials;
@@ -116,6 +118,8 @@ static int create_ctx_locked(int device) {
         return fail(PLONKISH_CUDA_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->chunk_ready[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->d_out, 512));
     CUDA_TRY(cudaMallocHost(&c->h_out, 256));
@@ -177,6 +181,8 @@ extern "C" void plonkish_cuda_shutdown(void) {
         cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
         cudaFree(c->d_out); cudaFreeHost(c->h_out);
         cudaEventDestroy(c->last_done);
+        for (int i = 0; i < 16; ++i) cudaEventDestroy(c->chunk_ready[i]);
+        cudaStreamDestroy(c->copy_stream);
         cudaStreamDestroy(c->stream);
         delete c;
     }
@@ -449,6 +455,56 @@ extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_pa
     return PLONKISH_CUDA_OK;
 }
 
+// ------------------------------------------------------- host scalars, pipelined
+// The step's scalars arrive from host memory (32 B per point, 512 MB at 2^24: ~10 ms of
+// PCIe).  The points are cut into chunks; chunk k+1 is copied on the copy stream while the
+// compute stream decomposes, sorts and accumulates chunk k into its own bucket array
+// (MsmPlan::chunk); one bucket reduce at the end adds the arrays.
+static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &bases, size_t n, xyzz **d_result) {
+    size_t nchunks = (n >= ((size_t)1 << 23)) ? 2 : 1;  // measured at 2^24: 53.6 / 51.6 / 54.1 ms for 1 / 2 / 4 chunks
+    if (const char *e = getenv("PLONKISH_CUDA_HOST_CHUNKS")) {  // tuning override
+        const long v = atol(e);
+        if (v >= 1 && v <= 16) nchunks = (size_t)v;
+    }
+    const size_t min_chunks = (n + MAX_POINTS_PER_LAUNCH - 1) / MAX_POINTS_PER_LAUNCH;
+    if (nchunks < min_chunks) nchunks = min_chunks;
+    if (nchunks > 16) return fail(PLONKISH_CUDA_E_INVALID, "msm: n = %zu is beyond 16 x 2^26 points", n);
+    const size_t per = (n + nchunks - 1) / nchunks;
+    // every chunk uses the window width the whole MSM would use, so the bucket layout is shared
+    const uint32_t c_all = bases.table_c ? 0 : plan_for(c, bases, n < MAX_POINTS_PER_LAUNCH ? n : MAX_POINTS_PER_LAUNCH, 0).c;
+    MsmPlan plan0 = plan_for(c, bases, per, c_all);
+    plan0.nchunks = (u32)nchunks;
+    int rc = grow(c->arena, pk_workspace_bytes(plan0));
+    if (rc) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    MsmWorkspace ws0 = pk_carve_workspace(plan0, c->arena.ptr);
+    MsmPlan last = plan0;
+    size_t k = 0;
+    for (size_t done = 0; done < n; done += per, ++k) {
+        const size_t cnt = (n - done < per) ? n - done : per;
+        char *d_chunk = (char *)c->scalars.ptr + done * PLONKISH_CUDA_SCALAR_BYTES;
+        cudaStream_t cs = (nchunks > 1) ? c->copy_stream : c->stream;
+        CUDA_TRY(cudaMemcpyAsync(d_chunk, (const char *)h_scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES,
+                                 cudaMemcpyHostToDevice, cs));
+        if (nchunks > 1) {
+            CUDA_TRY(cudaEventRecord(c->chunk_ready[k], cs));
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
+        }
+        MsmPlan plan = (cnt == per) ? plan0 : plan_for(c, bases, cnt, c_all);
+        plan.chunk = (u32)k;
+        plan.nchunks = (u32)nchunks;
+        MsmWorkspace w = pk_carve_workspace(plan, c->arena.ptr);
+        pk_enqueue_buckets(plan, d_chunk, (const char *)bases.ptr + done * PLONKISH_CUDA_AFFINE_BYTES, w, c->stream);
+        last = plan;
+    }
+    xyzz *running = (xyzz *)((char *)c->d_out + 256);
+    ws0.result = running;
+    pk_enqueue_reduce(last, ws0, nullptr, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    *d_result = running;
+    return PLONKISH_CUDA_OK;
+}
+
 // ----------------------------------------------------------------- host entry
 extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases, uint64_t bases_handle, size_t n, void *out_affine64) {
     const auto t0 = std::chrono::steady_clock::now();
@@ -471,7 +527,6 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
     CUDA_TRY(cudaSetDevice(c->dev));
     int rc = grow(c->scalars, n * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->scalars.ptr, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
     if (!bases_handle) {
         rc = grow(c->bases_tmp, n * PLONKISH_CUDA_AFFINE_BYTES);
         if (rc) return rc;
@@ -479,7 +534,7 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
         view.ptr = c->bases_tmp.ptr;
     }
     xyzz *res = nullptr;
-    rc = enqueue_device_msm(c, c->scalars.ptr, view, n, 0, c->stream, &res);
+    rc = enqueue_host_msm(c, scalars, view, n, &res);
     if (rc) return rc;
     PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, (affine *)c->d_out, (xyzz *)nullptr);
     CUDA_TRY(cudaGetLastError());

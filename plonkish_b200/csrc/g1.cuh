@@ -16,6 +16,26 @@
 
 namespace pk {
 
+// The point formulas are templated on how a field product is issued.  MulInline expands
+// the 270-instruction product in place: right for the accumulate loop, which is bound by
+// the integer pipe (measured: 37.6 ms inlined vs 39.8 ms with calls at 2^24).  MulCall
+// routes through one out-of-line copy: right for the latency-bound tail kernels (bucket
+// reduce 1.45 -> 1.04 ms, item levels 0.43 -> 0.35 ms) whose inlined bodies (up to 35 K
+// instructions) thrash the instruction cache.
+struct MulInline {
+    static PK_HD fe mul(const fe &a, const fe &b) { return fq_mul(a, b); }
+};
+#if !defined(PLONKISH_EMUL)
+__device__ __noinline__ fe fq_mul_call(fe a, fe b) { return mont_mul<FqMod>(a, b); }
+struct MulCall {
+    static PK_HD fe mul(const fe &a, const fe &b) { return fq_mul_call(a, b); }
+};
+#else
+typedef MulInline MulCall;
+#endif
+#define PK_MUL(a, b) M::mul(a, b)
+#define PK_SQR(a) M::mul(a, a)
+
 struct affine {  // 64 B, (0,0) = identity — the layout of halo2_curves G1Affine [ext]
     fe x, y;
 };
@@ -39,106 +59,114 @@ PK_HD xyzz xyzz_from_affine(const affine &p) {
 
 // 2 * (affine P), P != identity  (mdbl-2008-s-1 with a = 0): 3M + 2S... spelled out:
 // U = 2y, V = U^2, W = U*V, S = x*V, M = 3x^2, X3 = M^2 - 2S, Y3 = M(S - X3) - W*y.
+template <class M = MulCall>
 PK_HD xyzz xyzz_double_affine(const affine &p) {
     xyzz r;
     fe u = fq_dbl(p.y);
-    fe v = fq_sqr(u);
-    fe w = fq_mul(u, v);
-    fe s = fq_mul(p.x, v);
-    fe xx = fq_sqr(p.x);
+    fe v = PK_SQR(u);
+    fe w = PK_MUL(u, v);
+    fe s = PK_MUL(p.x, v);
+    fe xx = PK_SQR(p.x);
     fe m = fq_add(fq_dbl(xx), xx);
-    r.x = fq_sub(fq_sqr(m), fq_dbl(s));
-    r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, p.y));
+    r.x = fq_sub(PK_SQR(m), fq_dbl(s));
+    r.y = fq_sub(PK_MUL(m, fq_sub(s, r.x)), PK_MUL(w, p.y));
     r.zz = v;
     r.zzz = w;
     return r;
 }
 
 // 2 * P for an XYZZ point (dbl-2008-s-1, a = 0).
+template <class M = MulCall>
 PK_HD xyzz xyzz_double(const xyzz &p) {
     if (xyzz_is_identity(p)) return p;
     xyzz r;
     fe u = fq_dbl(p.y);
-    fe v = fq_sqr(u);
-    fe w = fq_mul(u, v);
-    fe s = fq_mul(p.x, v);
-    fe xx = fq_sqr(p.x);
+    fe v = PK_SQR(u);
+    fe w = PK_MUL(u, v);
+    fe s = PK_MUL(p.x, v);
+    fe xx = PK_SQR(p.x);
     fe m = fq_add(fq_dbl(xx), xx);
-    r.x = fq_sub(fq_sqr(m), fq_dbl(s));
-    r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, p.y));
-    r.zz = fq_mul(v, p.zz);
-    r.zzz = fq_mul(w, p.zzz);
+    r.x = fq_sub(PK_SQR(m), fq_dbl(s));
+    r.y = fq_sub(PK_MUL(m, fq_sub(s, r.x)), PK_MUL(w, p.y));
+    r.zz = PK_MUL(v, p.zz);
+    r.zzz = PK_MUL(w, p.zzz);
     return r;
 }
 
 // acc += (x2, y2) with the affine point given as two field elements (so a caller
 // can pass a negated y without building a struct).  madd-2008-s: 8M + 2S.
+template <class M = MulCall>
 PK_HD void xyzz_madd(xyzz &acc, const fe &x2, const fe &y2) {
     if (fe_is_zero(x2) && fe_is_zero(y2)) return;  // identity base
     if (xyzz_is_identity(acc)) {
         acc.x = x2; acc.y = y2; acc.zz = fq_one(); acc.zzz = fq_one();
         return;
     }
-    fe u2 = fq_mul(x2, acc.zz);
-    fe s2 = fq_mul(y2, acc.zzz);
+    fe u2 = PK_MUL(x2, acc.zz);
+    fe s2 = PK_MUL(y2, acc.zzz);
     fe p = fq_sub(u2, acc.x);
     fe r = fq_sub(s2, acc.y);
     if (fe_is_zero(p)) {
         if (fe_is_zero(r)) {
             affine q; q.x = x2; q.y = y2;
-            acc = xyzz_double_affine(q);
+            acc = xyzz_double_affine<M>(q);
         } else {
             acc = xyzz_identity();
         }
         return;
     }
-    fe pp = fq_sqr(p);
-    fe ppp = fq_mul(p, pp);
-    fe q = fq_mul(acc.x, pp);
-    fe x3 = fq_sub(fq_sub(fq_sqr(r), ppp), fq_dbl(q));
-    fe y3 = fq_sub(fq_mul(r, fq_sub(q, x3)), fq_mul(acc.y, ppp));
+    fe pp = PK_SQR(p);
+    fe ppp = PK_MUL(p, pp);
+    fe q = PK_MUL(acc.x, pp);
+    fe x3 = fq_sub(fq_sub(PK_SQR(r), ppp), fq_dbl(q));
+    fe y3 = fq_sub(PK_MUL(r, fq_sub(q, x3)), PK_MUL(acc.y, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = fq_mul(acc.zz, pp);
-    acc.zzz = fq_mul(acc.zzz, ppp);
+    acc.zz = PK_MUL(acc.zz, pp);
+    acc.zzz = PK_MUL(acc.zzz, ppp);
 }
 
 // a + b, both XYZZ (add-2008-s): 12M + 2S.
+template <class M = MulCall>
 PK_HD xyzz xyzz_add(const xyzz &a, const xyzz &b) {
     if (xyzz_is_identity(a)) return b;
     if (xyzz_is_identity(b)) return a;
-    fe u1 = fq_mul(a.x, b.zz);
-    fe u2 = fq_mul(b.x, a.zz);
-    fe s1 = fq_mul(a.y, b.zzz);
-    fe s2 = fq_mul(b.y, a.zzz);
+    fe u1 = PK_MUL(a.x, b.zz);
+    fe u2 = PK_MUL(b.x, a.zz);
+    fe s1 = PK_MUL(a.y, b.zzz);
+    fe s2 = PK_MUL(b.y, a.zzz);
     fe p = fq_sub(u2, u1);
     fe r = fq_sub(s2, s1);
     if (fe_is_zero(p)) {
-        if (fe_is_zero(r)) return xyzz_double(a);
+        if (fe_is_zero(r)) return xyzz_double<M>(a);
         return xyzz_identity();
     }
-    fe pp = fq_sqr(p);
-    fe ppp = fq_mul(p, pp);
-    fe q = fq_mul(u1, pp);
+    fe pp = PK_SQR(p);
+    fe ppp = PK_MUL(p, pp);
+    fe q = PK_MUL(u1, pp);
     xyzz o;
-    o.x = fq_sub(fq_sub(fq_sqr(r), ppp), fq_dbl(q));
-    o.y = fq_sub(fq_mul(r, fq_sub(q, o.x)), fq_mul(s1, ppp));
-    o.zz = fq_mul(fq_mul(a.zz, b.zz), pp);
-    o.zzz = fq_mul(fq_mul(a.zzz, b.zzz), ppp);
+    o.x = fq_sub(fq_sub(PK_SQR(r), ppp), fq_dbl(q));
+    o.y = fq_sub(PK_MUL(r, fq_sub(q, o.x)), PK_MUL(s1, ppp));
+    o.zz = PK_MUL(PK_MUL(a.zz, b.zz), pp);
+    o.zzz = PK_MUL(PK_MUL(a.zzz, b.zzz), ppp);
     return o;
 }
 
 // XYZZ -> affine with one inversion: I = (ZZ*ZZZ)^-1, 1/ZZ = I*ZZZ, 1/ZZZ = I*ZZ.
+template <class M = MulCall>
 PK_HD affine xyzz_to_affine(const xyzz &p) {
     affine r;
     if (xyzz_is_identity(p)) {
         r.x = fe_zero(); r.y = fe_zero();
         return r;
     }
-    fe i = fq_inv(fq_mul(p.zz, p.zzz));
-    r.x = fq_mul(p.x, fq_mul(i, p.zzz));
-    r.y = fq_mul(p.y, fq_mul(i, p.zz));
+    fe i = fq_inv(PK_MUL(p.zz, p.zzz));
+    r.x = PK_MUL(p.x, PK_MUL(i, p.zzz));
+    r.y = PK_MUL(p.y, PK_MUL(i, p.zz));
     return r;
 }
+
+#undef PK_MUL
+#undef PK_SQR
 
 }  // namespace pk

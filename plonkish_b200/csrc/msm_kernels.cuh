@@ -80,6 +80,8 @@ struct MsmPlan {
                       //    precomputed window multiples T[w][i] = 2^(c*w) * P_i (resident bases only)
     u32 ngroups;      // bucket sets: W in mode 0, 1 in mode 1
     u32 stride;       // mode 1: points per table row
+    u32 chunk;        // which of the MSM's bucket arrays this launch sequence fills (host path pipelining)
+    u32 nchunks;      // bucket arrays the reduce phase adds up (1 unless the host path cut the points into chunks)
 };
 
 inline u32 pk_ceil_log2(u32 v) {
@@ -141,6 +143,8 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     p.mode = 0;
     p.ngroups = p.W;
     p.stride = 0;
+    p.chunk = 0;
+    p.nchunks = 1;
     return p;
 }
 
@@ -210,24 +214,25 @@ struct MsmWorkspace {
 
 inline size_t pk_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Pieces whose size depends only on (mode, c) come first, so that every chunk of one MSM
+// (same table, different point counts) finds bucket_sum etc. at the same offsets.
 inline size_t pk_workspace_bytes(const MsmPlan &p) {
     size_t e = (size_t)p.n * p.W;
     size_t items = (size_t)p.nthreads1 * 2;
     size_t s = 0;
-    s += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
-    s += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
-    s += pk_align256(sizeof(u32) * p.nbins);
-    s += pk_align256(sizeof(u32) * (p.nbins + 1));
-    s += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
-    s += pk_align256(sizeof(u32) * e);
-    s += pk_align256(sizeof(u32) * (p.nbuckets + 1));
-    s += pk_align256(sizeof(u32) * (p.nbuckets + 1));
-    s += pk_align256(sizeof(xyzz) * p.nbuckets);
-    s += 2 * pk_align256(sizeof(u32) * items);
-    s += 2 * pk_align256(sizeof(xyzz) * items);
+    s += pk_align256(sizeof(xyzz) * (size_t)p.nbuckets * p.nchunks);
+    s += 2 * pk_align256(sizeof(u32) * (p.nbuckets + 1));
     s += pk_align256(sizeof(xyzz) * (size_t)p.ngroups * p.red_blocks);
     s += pk_align256(sizeof(xyzz) * 32);
     s += pk_align256(sizeof(xyzz));
+    s += pk_align256(sizeof(u32) * p.nbins);
+    s += pk_align256(sizeof(u32) * (p.nbins + 1));
+    s += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
+    s += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
+    s += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
+    s += pk_align256(sizeof(u32) * e);
+    s += 2 * pk_align256(sizeof(u32) * items);
+    s += 2 * pk_align256(sizeof(xyzz) * items);
     return s;
 }
 
@@ -236,20 +241,20 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     unsigned char *q = (unsigned char *)arena;
     size_t e = (size_t)p.n * p.W;
     size_t items = (size_t)p.nthreads1 * 2;
-    w.digits = (u16 *)q; q += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
-    w.tile_hist = (u32 *)q; q += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
-    w.bin_total = (u32 *)q; q += pk_align256(sizeof(u32) * p.nbins);
-    w.bin_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbins + 1));
-    w.l1 = (u32 *)q; q += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
-    w.sorted = (u32 *)q; q += pk_align256(sizeof(u32) * e);
+    w.bucket_sum = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.nbuckets * p.nchunks);
     w.bucket_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     w.bucket_cur = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
-    w.bucket_sum = (xyzz *)q; q += pk_align256(sizeof(xyzz) * p.nbuckets);
-    for (int k = 0; k < 2; ++k) { w.item_keys[k] = (u32 *)q; q += pk_align256(sizeof(u32) * items); }
-    for (int k = 0; k < 2; ++k) { w.item_pts[k] = (xyzz *)q; q += pk_align256(sizeof(xyzz) * items); }
     w.block_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.ngroups * p.red_blocks);
     w.win_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * 32);
-    w.result = (xyzz *)q;
+    w.result = (xyzz *)q; q += pk_align256(sizeof(xyzz));
+    w.bin_total = (u32 *)q; q += pk_align256(sizeof(u32) * p.nbins);
+    w.bin_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbins + 1));
+    w.digits = (u16 *)q; q += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
+    w.tile_hist = (u32 *)q; q += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
+    w.l1 = (u32 *)q; q += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
+    w.sorted = (u32 *)q; q += pk_align256(sizeof(u32) * e);
+    for (int k = 0; k < 2; ++k) { w.item_keys[k] = (u32 *)q; q += pk_align256(sizeof(u32) * items); }
+    for (int k = 0; k < 2; ++k) { w.item_pts[k] = (xyzz *)q; q += pk_align256(sizeof(xyzz) * items); }
     return w;
 }
 
@@ -948,7 +953,7 @@ __global__ void __launch_bounds__(128, 4) k_accumulate(const u32 *__restrict__ s
             const fe x = load_fe(bp);
             fe y = load_fe(bp + 2);
             if (entry >> 31) y = fq_neg(y);
-            xyzz_madd(acc, x, y);
+            xyzz_madd<MulInline>(acc, x, y);
         }
         tk = g;
     }
@@ -1026,7 +1031,8 @@ __global__ void __launch_bounds__(256) k_bucket_reduce(const xyzz *__restrict__ 
         xyzz run = xyzz_identity(), acc = xyzz_identity();
         for (int i = (int)p.rb - 1; i >= 0; --i) {
             const u32 g = w * p.B + j * p.rb + (u32)i;
-            if (bucket_start[g + 1] > bucket_start[g]) run = xyzz_add(run, load_xyzz(bucket_sum + g));
+            for (u32 k = 0; k < p.nchunks; ++k)  // untouched buckets are zeroed = identity
+                run = xyzz_add(run, load_xyzz(bucket_sum + (size_t)k * p.nbuckets + g));
             acc = xyzz_add(acc, run);
         }
         contrib = xyzz_add(acc, xyzz_mul_small(run, j * p.rb));
@@ -1097,11 +1103,14 @@ struct StageMarks {
     void *ev[9];
 };
 
-// Enqueues one MSM over p.n points; the projective result lands in ws.result
-// (plus *prev if given).  No host synchronisation.
-inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *bases, const MsmWorkspace &ws, const xyzz *prev,
-                           pk_stream_t stream, const StageMarks *marks = nullptr) {
+// Phase 1 of an MSM over p.n points: decompose, sort, accumulate into bucket array p.chunk of
+// ws.bucket_sum (zeroed first).  Chunks of one MSM share c and the bucket layout; the
+// reduce phase adds their arrays.
+inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void *bases, const MsmWorkspace &ws, pk_stream_t stream,
+                               const StageMarks *marks = nullptr) {
     PK_MARK(marks, 0, stream);
+    xyzz *bsum = ws.bucket_sum + (size_t)p.chunk * p.nbuckets;
+    PK_MEMSET0(bsum, sizeof(xyzz) * (size_t)p.nbuckets, stream);
     if (p.mode == 0) {
         switch (p.c) {
             case 8: pk_launch_decompose<8>(p, scalars, ws, stream); break;
@@ -1158,7 +1167,7 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
 
     // K3, then the item levels until one warp stores everything that is left.
     PK_LAUNCH(k_accumulate, dim3(p.nthreads1 / p.blk_acc), dim3(p.blk_acc), 0, stream, ws.sorted, ws.bucket_start,
-              (const affine *)bases, p, ws.bucket_sum, ws.item_keys[0], ws.item_pts[0]);
+              (const affine *)bases, p, bsum, ws.item_keys[0], ws.item_pts[0]);
     PK_MARK(marks, 5, stream);
     u32 count = 2 * p.nthreads1;
     int src = 0;
@@ -1169,16 +1178,29 @@ inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *ba
         const u32 warps = nthreads / 32;
         terminal = (warps == 1) ? 1 : 0;
         PK_LAUNCH(k_reduce_items, dim3(terminal ? 1 : nthreads / 128), dim3(terminal ? 32 : 128), 0, stream, ws.item_keys[src], ws.item_pts[src], count, K,
-                  ws.bucket_sum, ws.item_keys[src ^ 1], ws.item_pts[src ^ 1], terminal);
+                  bsum, ws.item_keys[src ^ 1], ws.item_pts[src ^ 1], terminal);
         count = 2 * warps;
         src ^= 1;
     }
     PK_MARK(marks, 6, stream);
+}
+
+// Phase 2: bucket reduce and window combine; the projective result lands in ws.result
+// (plus *prev if given).
+inline void pk_enqueue_reduce(const MsmPlan &p, const MsmWorkspace &ws, const xyzz *prev, pk_stream_t stream,
+                              const StageMarks *marks = nullptr) {
     PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.ngroups), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
     PK_MARK(marks, 7, stream);
     PK_LAUNCH(k_window_weight, dim3(p.ngroups), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
     PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.ngroups, prev, ws.result);
     PK_MARK(marks, 8, stream);
+}
+
+// One whole MSM.  No host synchronisation.
+inline void pk_enqueue_msm(const MsmPlan &p, const void *scalars, const void *bases, const MsmWorkspace &ws, const xyzz *prev,
+                           pk_stream_t stream, const StageMarks *marks = nullptr) {
+    pk_enqueue_buckets(p, scalars, bases, ws, stream, marks);
+    pk_enqueue_reduce(p, ws, prev, stream, marks);
 }
 
 // Builds the table of window multiples for n bases: table[w*n + i] = 2^(c*w) * bases[i],

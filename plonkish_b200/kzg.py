@@ -1,0 +1,107 @@
+"""Host-side mirror of the reference's MultilinearKzg commit paths over the GPU MSM.
+
+Mirrors, for BN254 (`M = Bn256`):
+  MultilinearKzg::commit        /root/reference/plonkish_backend/src/pcs/multilinear/kzg.rs:252-257
+  MultilinearKzg::batch_commit  kzg.rs:259-274
+  MultilinearKzg::open          kzg.rs:276-302  (quotient commitments written to the transcript)
+  quotients                     pcs/multilinear.rs:72-107
+  UnivariateKzg::commit_coeffs  pcs/univariate/kzg.rs:24-30
+Every one of them is `variable_base_msm(scalars, srs_slice)`; only the MSM runs on the
+GPU.  The scalar-field bookkeeping of `quotients` is done here with Python integers — it
+is the caller's CPU work in the reference too (field-only, out of scope per SURVEY.md §8)
+and is meant for the parity tests and small sizes, not for throughput.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from .msm import G1Bases, variable_base_msm
+
+FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+_MONT = 1 << 256
+
+
+def fr_to_montgomery(values: Sequence[int]) -> np.ndarray:
+    """Canonical integers -> [n, 4] uint64 Montgomery limbs (the bn256::Fr layout)."""
+    buf = b"".join((int(v) % FR_MODULUS * _MONT % FR_MODULUS).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 4).copy()
+
+
+def fr_from_montgomery(limbs: np.ndarray) -> List[int]:
+    rinv = pow(_MONT, -1, FR_MODULUS)
+    arr = np.ascontiguousarray(limbs, dtype=np.uint64).reshape(-1, 4)
+    return [int.from_bytes(row.tobytes(), "little") * rinv % FR_MODULUS for row in arr]
+
+
+class MultilinearKzgProverParam:
+    """`MultilinearKzgProverParams { g1, eqs }` (kzg.rs:55-77): eqs[k] holds the 2^k bases
+    eq_j(s_0..s_{k-1}) * G.  Each slice is made resident on the GPU once."""
+
+    def __init__(self, eqs: Sequence[np.ndarray], device: int = 0, mode: int = 0):
+        self.eqs = [G1Bases(e, device=device, mode=mode) for e in eqs]
+        for k, e in enumerate(self.eqs):
+            assert len(e) == 1 << k, f"eqs[{k}] must hold 2^{k} bases"
+
+    def num_vars(self) -> int:
+        return len(self.eqs) - 1  # kzg.rs:68-70
+
+    def eq(self, num_vars: int) -> G1Bases:
+        return self.eqs[num_vars]  # kzg.rs:74-76
+
+    def release(self) -> None:
+        for e in self.eqs:
+            e.release()
+
+
+def _num_vars_of(evals: np.ndarray) -> int:
+    n = np.asarray(evals).reshape(-1, 4).shape[0]
+    assert n and n & (n - 1) == 0, "a multilinear polynomial has 2^k evaluations"
+    return n.bit_length() - 1
+
+
+def commit(pp: MultilinearKzgProverParam, evals: np.ndarray) -> np.ndarray:
+    """kzg.rs:252-257: variable_base_msm(poly.evals(), pp.eq(poly.num_vars())).into()"""
+    k = _num_vars_of(evals)
+    if k > pp.num_vars():  # validate_input, pcs/multilinear.rs:26-58
+        raise ValueError(f"Too many variates of poly to commit (param supports variates up to {pp.num_vars()} but got {k})")
+    return variable_base_msm(evals, pp.eq(k))
+
+
+def batch_commit(pp: MultilinearKzgProverParam, polys: Sequence[np.ndarray]) -> List[np.ndarray]:
+    """kzg.rs:259-274: one MSM per polynomial, in order."""
+    return [commit(pp, p) for p in polys]
+
+
+def quotients(evals: Sequence[int], point: Sequence[int]) -> Tuple[List[List[int]], int]:
+    """pcs/multilinear.rs:72-107 on canonical integers: for i = k-1..0 the quotient
+    q_i = hi - lo (2^i values) and the remainder folds with x_i; returns ([q_0..q_{k-1}], f(x))."""
+    k = len(point)
+    assert len(evals) == 1 << k
+    r = FR_MODULUS
+    remainder = [int(v) % r for v in evals]
+    qs: List[List[int]] = []
+    for i in reversed(range(k)):
+        half = 1 << i
+        lo, hi = remainder[:half], remainder[half:2 * half]
+        qs.append([(h - l) % r for h, l in zip(hi, lo)])
+        remainder = [(l + (h - l) * point[i]) % r for h, l in zip(hi, lo)]
+    qs.reverse()
+    return qs, remainder[0]
+
+
+def open(pp: MultilinearKzgProverParam, evals: np.ndarray, point: Sequence[int]) -> Tuple[List[np.ndarray], int]:
+    """kzg.rs:276-302: the k quotient commitments (MSMs of 2^(k-1), ..., 2, 1 points against
+    eqs[k-1..0]) the reference writes to the transcript, and the evaluation f(point)."""
+    k = _num_vars_of(evals)
+    if k > pp.num_vars() or len(point) != k:
+        raise ValueError("Invalid point / polynomial size for open")
+    qs, value = quotients(fr_from_montgomery(evals), [int(x) for x in point])
+    comms = [variable_base_msm(fr_to_montgomery(q), pp.eq(i)) for i, q in enumerate(qs)]
+    return comms, value
+
+
+def commit_coeffs(powers_of_s_g1: G1Bases, coeffs: np.ndarray) -> np.ndarray:
+    """pcs/univariate/kzg.rs:24-30: variable_base_msm(coeffs, &powers_of_s_g1[..coeffs.len()])."""
+    return variable_base_msm(coeffs, powers_of_s_g1)

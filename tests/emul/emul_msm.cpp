@@ -77,21 +77,44 @@ int emul_msm(const void *scalars, const void *bases, u32 n, u32 c_override, u32 
 
 // Mode 1: expand the first n_table bases into the table of window multiples with the
 // product's table kernels, then run an MSM over the first n_use points through it.
+int emul_msm_table_chunked(const void *scalars, const void *bases, u32 n_table, u32 n_use, u32 c, u32 sm_count, u32 nchunks,
+                           void *out_affine64);
 int emul_msm_table(const void *scalars, const void *bases, u32 n_table, u32 n_use, u32 c, u32 sm_count, void *out_affine64) {
+    return emul_msm_table_chunked(scalars, bases, n_table, n_use, c, sm_count, 1, out_affine64);
+}
+
+// The host path's pipelining: the points are cut into nchunks consecutive chunks that all
+// add into one bucket array (p.accum), and one reduce phase follows.
+int emul_msm_table_chunked(const void *scalars, const void *bases, u32 n_table, u32 n_use, u32 c, u32 sm_count, u32 nchunks,
+                           void *out_affine64) {
     if (n_use == 0) { memset(out_affine64, 0, 64); return 0; }
     if (!c) c = pk_table_window_bits(n_table);
     const u32 W = pk_windows_for(c);
     affine *table = (affine *)aligned_alloc(256, sizeof(affine) * (size_t)W * n_table);
     xyzz *cur = (xyzz *)aligned_alloc(256, sizeof(xyzz) * (size_t)n_table);
     pk_enqueue_table_build(bases, n_table, c, W, cur, table, 0);
-    MsmPlan p = pk_make_plan_b(n_use, c, n_table, sm_count);
-    p.blk = 32;
-    p.blk_stage = 32;
-    size_t bytes = pk_workspace_bytes(p);
+    const u32 per = (n_use + nchunks - 1) / nchunks;
+    MsmPlan p0 = pk_make_plan_b(per, c, n_table, sm_count);
+    p0.blk = 32;
+    p0.blk_stage = 32;
+    p0.nchunks = nchunks;
+    size_t bytes = pk_workspace_bytes(p0);
     void *arena = aligned_alloc(256, bytes);
     memset(arena, 0xA5, bytes);
-    MsmWorkspace ws = pk_carve_workspace(p, arena);
-    pk_enqueue_msm(p, scalars, table, ws, nullptr, 0);
+    MsmWorkspace ws = pk_carve_workspace(p0, arena);
+    MsmPlan last = p0;
+    for (u32 done = 0, k = 0; done < n_use; done += per, ++k) {
+        const u32 cnt = (n_use - done < per) ? n_use - done : per;
+        MsmPlan p = pk_make_plan_b(cnt, c, n_table, sm_count);
+        p.blk = 32;
+        p.blk_stage = 32;
+        p.chunk = k;
+        p.nchunks = nchunks;
+        MsmWorkspace w = pk_carve_workspace(p, arena);
+        pk_enqueue_buckets(p, (const char *)scalars + (size_t)done * 32, (const char *)table + (size_t)done * 64, w, 0);
+        last = p;
+    }
+    pk_enqueue_reduce(last, ws, nullptr, 0);
     affine out;
     PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, 0, ws.result, 1u, &out, (xyzz *)nullptr);
     memcpy(out_affine64, &out, 64);

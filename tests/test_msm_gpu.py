@@ -259,6 +259,70 @@ def test_table_at_2pow22_known_discrete_log(pk, oracle):
     reg.release()
 
 
+@pytest.mark.parametrize("n", [(1 << 22) + 5, 1 << 23])
+def test_host_path_chunk_pipeline(pk, oracle, n):
+    # Host scalars at 2^23 and above are copied in chunks that overlap with compute; every
+    # chunk fills its own bucket array and one reduce adds them (api.cu enqueue_host_msm).
+    sc = pk.random_scalars(n, seed=n % 1000)
+    d_bs = pk.synth_bases_device(n, 3, 5)
+    want = oracle.known_dlog_answer(3, 5, sc)
+    import os
+
+    for mode in (pk.G1Bases.TABLE, pk.G1Bases.PLAIN):
+        reg = pk.G1Bases(d_bs, mode=mode)
+        for chunks in ("", "3"):
+            if chunks:
+                os.environ["PLONKISH_CUDA_HOST_CHUNKS"] = chunks
+            try:
+                assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes(), (mode, chunks)
+            finally:
+                os.environ.pop("PLONKISH_CUDA_HOST_CHUNKS", None)
+        reg.release()
+
+
+def test_multilinear_kzg_commit_open_round_trip(pk, oracle):
+    # The reference's PCS test is setup -> commit -> open -> verify (pcs/multilinear.rs:293-333)
+    # with the pairing check e(C - v*G, g2) = prod e(Q_i, [s_i - x_i]_2) (kzg.rs:330-361).
+    # With the trapdoor s known to the test the same identity is checked in G1:
+    #   sum_i (s_i - x_i) * Q_i == C - f(x) * G.
+    from plonkish_b200 import kzg
+
+    rng = np.random.default_rng(17)
+    k = 7
+    ss = [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(k)]
+    eq_scalars = [[1]]
+    for s_i in ss:  # kzg.rs:174-194
+        last = eq_scalars[-1]
+        hi = [s_i * e % br.R for e in last]
+        lo = [(e - h) % br.R for e, h in zip(last, hi)]
+        eq_scalars.append(lo + hi)
+    g = oracle.generator()
+    eqs = [np.array([oracle.scalar_mul(g, e) for e in row]) for row in eq_scalars]
+    for mode in (pk.G1Bases.PLAIN, pk.G1Bases.TABLE):
+        pp = kzg.MultilinearKzgProverParam(eqs, mode=mode)
+        evals_int = [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(1 << k)]
+        evals = kzg.fr_to_montgomery(evals_int)
+        comm = kzg.commit(pp, evals)
+        f_s = sum(e * q for e, q in zip(evals_int, eq_scalars[k])) % br.R
+        assert br.point_from_bytes(comm.tobytes()) == br.scalar_mul(f_s, br.G)  # commit(f) = f(s) * G
+        assert [c.tobytes() for c in kzg.batch_commit(pp, [evals, evals[: 1 << (k - 1)]])][0] == comm.tobytes()
+        x = [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(k)]
+        q_comms, value = kzg.open(pp, evals, x)
+        assert len(q_comms) == k
+        lhs = None
+        for s_i, x_i, q in zip(ss, x, q_comms):
+            lhs = br.add(lhs, br.scalar_mul((s_i - x_i) % br.R, br.point_from_bytes(q.tobytes())))
+        rhs = br.add(br.point_from_bytes(comm.tobytes()), br.neg(br.scalar_mul(value, br.G)))
+        assert lhs == rhs
+        # each quotient commitment equals the oracle's MSM of the same quotient
+        qs, _ = kzg.quotients(evals_int, x)
+        for i, (q, c) in enumerate(zip(qs, q_comms)):
+            assert oracle.variable_base_msm(kzg.fr_to_montgomery(q), eqs[i]).tobytes() == c.tobytes()
+        pp.release()
+    with pytest.raises(ValueError):
+        kzg.commit(kzg.MultilinearKzgProverParam(eqs[:3], mode=pk.G1Bases.PLAIN), evals)
+
+
 def test_linearity(pk, oracle):
     # MSM(s, B) + MSM(t, B) == MSM(s + t, B), checked through the oracle's field/curve ops.
     n = 5000
