@@ -165,7 +165,8 @@ def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
     host[:] = pk.random_scalars(n, seed=4242)
 
     def run():
-        outs = [pk.variable_base_msm(host, regs[k]) for _ in range(4)]
+        # batch_commit of the 3 witness polynomials (hyperplonk.rs:201), then the z-poly commit (:251)
+        outs = list(pk.variable_base_msm_batch([host, host, host], regs[k])) + [pk.variable_base_msm(host, regs[k])]
         outs += [pk.variable_base_msm(host[: 1 << i], regs[i]) for i in reversed(range(k))]
         return outs
 

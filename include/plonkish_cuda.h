@@ -84,6 +84,13 @@ int plonkish_cuda_bases_register_device(int device, const void *d_bases_affine64
 int plonkish_cuda_msm_bn254_g1(const void *scalars_mont32, const void *bases_affine64, uint64_t bases_handle, size_t n,
                                void *out_affine64);
 
+/* `count` MSMs of n points each against one registered base slice, results in
+ * out_affine64_list[j*64 ..].  Replaces the loop of MultilinearKzg::batch_commit
+ * (pcs/multilinear/kzg.rs:259-274) — same results in the same order; the upload of the
+ * next polynomial's scalars overlaps the current MSM and the host blocks once. */
+int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_mont32_list, size_t count, uint64_t bases_handle, size_t n,
+                                     void *out_affine64_list);
+
 /* Same for the reference's non-contiguous callers, which pass iterators of
  * references (chain![..] at pcs/univariate/kzg.rs:346,408; .map(|c| &c.0) at
  * pcs/multilinear/kzg.rs:145): gathers the n scalars and n bases into staging first. */
@@ -145,6 +152,8 @@ uint64_t plonkish_cuda_launch_count(void);
  *   out[5] = wide multiply-adds per second inside mad.lo.cc/madc.hi.cc carry chains
  *            (IMAD.WIDE.U32.X, the instruction the Montgomery products are built from) */
 int plonkish_cuda_bench_integer_pipe(int device, double out[6]);
+/* The library's fq_mul stream with warps_per_sm (multiple of 4, 4..64) resident warps per SM. */
+int plonkish_cuda_bench_fq_mul_occupancy(int device, int warps_per_sm, double *out_per_s);
 
 /* Synthetic bases with a known discrete log: d_out[i] = (a + i*step) * G for
  * i in [first, first + n), affine, written on the device.  Used by bench.py and the

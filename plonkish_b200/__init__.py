@@ -9,6 +9,7 @@ from .msm import (  # noqa: F401
     G1Bases,
     ShardedG1Bases,
     variable_base_msm,
+    variable_base_msm_batch,
     variable_base_msm_device,
     sum_partials_device,
     synth_bases_device,

@@ -23,6 +23,7 @@ EXPORTS = (
     "plonkish_cuda_bases_release",
     "plonkish_cuda_bases_register_device",
     "plonkish_cuda_msm_bn254_g1",
+    "plonkish_cuda_msm_bn254_g1_batch",
     "plonkish_cuda_msm_bn254_g1_gather",
     "plonkish_cuda_bases_register_sharded",
     "plonkish_cuda_msm_bn254_g1_multi",
@@ -33,6 +34,7 @@ EXPORTS = (
     "plonkish_cuda_msm_profile_device",
     "plonkish_cuda_launch_count",
     "plonkish_cuda_bench_integer_pipe",
+    "plonkish_cuda_bench_fq_mul_occupancy",
     "plonkish_cuda_synth_bases_device",
     "plonkish_cuda_debug_field_op",
     "plonkish_cuda_debug_point_op",
@@ -69,6 +71,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_bases_release.argtypes = [u64]
     lib.plonkish_cuda_bases_register_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
+    lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
     lib.plonkish_cuda_bases_register_sharded.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1_multi.argtypes = [ci, vp, vp, u64, sz, vp]
@@ -80,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_launch_count.argtypes = []
     lib.plonkish_cuda_launch_count.restype = u64
     lib.plonkish_cuda_bench_integer_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.plonkish_cuda_bench_fq_mul_occupancy.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_synth_bases_device.argtypes = [ci, vp, sz, sz, u64, u64, vp]
     lib.plonkish_cuda_debug_field_op.argtypes = [ci, ci, vp, vp, vp, sz]
     lib.plonkish_cuda_debug_point_op.argtypes = [ci, ci, vp, vp, vp, sz]

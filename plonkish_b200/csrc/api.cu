@@ -65,7 +65,8 @@ struct Ctx {
     cudaEvent_t chunk_ready[16] = {};
     cudaEvent_t last_done = nullptr;  // end of the last enqueued MSM: orders arena reuse across streams
     bool has_last = false;
-    DeviceBuffer arena, scalars, bases_tmp, partials;
+    DeviceBuffer arena, scalars, scalars2, bases_tmp, partials, batch_out;
+    cudaEvent_t buf_free[2] = {};         // batch path: scalar buffer b may be overwritten again
     void *d_out = nullptr;  // [0,64) affine out, [192,256) synth step point, [256,384) running projective sum
     void *h_out = nullptr;  // pinned mirror of the affine result
     std::mutex mu;
@@ -121,6 +122,7 @@ static int create_ctx_locked(int device) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->chunk_ready[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->buf_free[i], cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->d_out, 512));
     CUDA_TRY(cudaMallocHost(&c->h_out, 256));
     g_ctx[device] = c;
@@ -178,7 +180,9 @@ extern "C" void plonkish_cuda_shutdown(void) {
         if (!c) continue;
         cudaSetDevice(c->dev);
         cudaDeviceSynchronize();
-        cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
+        cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->scalars2.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
+        cudaFree(c->batch_out.ptr);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->buf_free[i]);
         cudaFree(c->d_out); cudaFreeHost(c->h_out);
         cudaEventDestroy(c->last_done);
         for (int i = 0; i < 16; ++i) cudaEventDestroy(c->chunk_ready[i]);
@@ -547,6 +551,58 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
     return PLONKISH_CUDA_OK;
 }
 
+// ---------------------------------------------------------------- batch entry
+// `count` MSMs of n points each against one resident base slice — the shape of
+// MultilinearKzg::batch_commit (pcs/multilinear/kzg.rs:259-274: one variable_base_msm per
+// polynomial, all against pp.eq(num_vars)).  The reference runs them one after another; here
+// the copy stream uploads the scalars of MSM j+1 (two device buffers) while the compute stream
+// works on MSM j, and the host waits once at the end.
+extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list, size_t count, uint64_t bases_handle, size_t n,
+                                                void *out_affine64_list) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!out_affine64_list || (count && !scalars_list)) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch: null argument");
+    if (!bases_handle) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch: a registered bases handle is required");
+    if (count == 0) return PLONKISH_CUDA_OK;
+    if (n == 0) { memset(out_affine64_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
+    if (n > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch: n = %zu exceeds 2^26 points per MSM", n);
+    BasesView view;
+    int device = 0;
+    int rc = view_of(bases_handle, n, -1, view, &device, "msm_batch");
+    if (rc) return rc;
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_batch: device %d not initialised", device);
+    for (size_t j = 0; j < count; ++j)
+        if (!scalars_list[j]) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch: null scalars for MSM %zu", j);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t bytes = n * PLONKISH_CUDA_SCALAR_BYTES;
+    if ((rc = grow(c->scalars, bytes)) || (rc = grow(c->scalars2, bytes))) return rc;
+    if ((rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES))) return rc;
+    MsmPlan plan = plan_for(c, view, n, 0);
+    if ((rc = grow(c->arena, pk_workspace_bytes(plan)))) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
+    ws.result = (xyzz *)((char *)c->d_out + 256);
+    void *bufs[2] = {c->scalars.ptr, c->scalars2.ptr};
+    for (size_t j = 0; j < count; ++j) {
+        const int b = (int)(j & 1);
+        if (j >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->buf_free[b], 0));  // MSM j-2 has consumed this buffer
+        CUDA_TRY(cudaMemcpyAsync(bufs[b], scalars_list[j], bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(cudaEventRecord(c->chunk_ready[b], c->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
+        pk_enqueue_msm(plan, bufs[b], view.ptr, ws, nullptr, c->stream);
+        CUDA_TRY(cudaEventRecord(c->buf_free[b], c->stream));  // scalars are dead after the decompose; recorded after the whole MSM for simplicity
+        PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, ws.result, 1u,
+                  (affine *)((char *)c->batch_out.ptr + j * PLONKISH_CUDA_AFFINE_BYTES), (xyzz *)nullptr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mark_done(c, c->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (size_t j = 0; j < count; ++j) timer_report(n, t0);
+    return PLONKISH_CUDA_OK;
+}
+
 extern "C" int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs, const void *const *base_ptrs, size_t n, void *out_affine64) {
     if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null output");
     if (n && (!scalar_ptrs || !base_ptrs)) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null pointer table");
@@ -837,6 +893,51 @@ __global__ void __launch_bounds__(256) k_bench_fq_mul(uint4 *out, u32 iters, u32
     }
     fe r = fq_add(x, y);
     store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), r);
+}
+
+// Occupancy experiment: the library's fq_mul stream with `warps_per_sm` resident warps
+// (128-thread blocks, dynamic shared memory as the limiter).  Returns products per second.
+__global__ void __launch_bounds__(128) k_bench_fq_mul_occ(uint4 *out, u32 iters, u32 seed) {
+    extern __shared__ unsigned char pad_smem[];
+    fe x = fq_one(), y = fq_one(), z = fq_one();
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x; z.l[2] ^= seed;
+    x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu; z.l[7] &= 0x0fffffffu;
+    if (seed == 0xffffffffu) pad_smem[threadIdx.x] = 1;  // keep the allocation alive
+    for (u32 it = 0; it < iters; ++it) {
+        x = fq_mul(x, z);
+        y = fq_mul(y, z);
+    }
+    fe r = fq_add(x, y);
+    store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), r);
+}
+extern "C" int plonkish_cuda_bench_fq_mul_occupancy(int device, int warps_per_sm, double *out_per_s) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out_per_s || warps_per_sm < 4 || warps_per_sm > 64 || warps_per_sm % 4) return fail(PLONKISH_CUDA_E_INVALID, "bench_fq_mul_occupancy: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const int blocks_per_sm = warps_per_sm / 4;
+    const size_t smem = blocks_per_sm >= 16 ? 0 : (size_t)(220 * 1024 / blocks_per_sm) - 2048;
+    CUDA_TRY(cudaFuncSetAttribute(k_bench_fq_mul_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
+    const unsigned blocks = (unsigned)c->sm_count * blocks_per_sm * 4;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * 128 * 32));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float ms = 0;
+    const u32 iters = 256;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_fq_mul_occ, dim3(blocks), dim3(128), smem, c->stream, (uint4 *)scratch, iters, 7u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    CUDA_TRY(cudaGetLastError());
+    *out_per_s = (double)blocks * 128 * 2.0 * iters / (ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
 }
 
 extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[6]) {

@@ -204,6 +204,7 @@ struct MsmWorkspace {
     u32 *sorted;        // [n * W] (sign << 31 | point index), ordered by (window, bucket)
     u32 *bucket_start;  // [nbuckets + 1]
     u32 *bucket_cur;    // [nbuckets + 1] mode 1: per-bucket counts, then cursors
+    u32 *scan_tmp;      // [2 * 2050] block totals / offsets of the multi-block scan
     xyzz *bucket_sum;   // [nbuckets]
     u32 *item_keys[2];  // ping-pong item lists for the segmented reduction levels
     xyzz *item_pts[2];
@@ -222,6 +223,7 @@ inline size_t pk_workspace_bytes(const MsmPlan &p) {
     size_t s = 0;
     s += pk_align256(sizeof(xyzz) * (size_t)p.nbuckets * p.nchunks);
     s += 2 * pk_align256(sizeof(u32) * (p.nbuckets + 1));
+    s += pk_align256(sizeof(u32) * 2 * 2050);
     s += pk_align256(sizeof(xyzz) * (size_t)p.ngroups * p.red_blocks);
     s += pk_align256(sizeof(xyzz) * 32);
     s += pk_align256(sizeof(xyzz));
@@ -244,6 +246,7 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     w.bucket_sum = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.nbuckets * p.nchunks);
     w.bucket_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
     w.bucket_cur = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbuckets + 1));
+    w.scan_tmp = (u32 *)q; q += pk_align256(sizeof(u32) * 2 * 2050);
     w.block_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * (size_t)p.ngroups * p.red_blocks);
     w.win_out = (xyzz *)q; q += pk_align256(sizeof(xyzz) * 32);
     w.result = (xyzz *)q; q += pk_align256(sizeof(xyzz));
@@ -748,6 +751,44 @@ __global__ void __launch_bounds__(1024) k_scan_inplace(u32 *__restrict__ v, u32 
     if (threadIdx.x == 0) copy[n] = scratch[32];
 }
 
+// Multi-block version for large arrays: per-block totals, a one-block scan of the totals,
+// then every block rescans its 2048 elements with its offset.
+#define PK_SCAN_CHUNK 2048
+__global__ void __launch_bounds__(1024) k_scan_partial(const u32 *__restrict__ v, u32 n, u32 *__restrict__ sums) {
+    __shared__ u32 scratch[64];
+    const u32 base = blockIdx.x * PK_SCAN_CHUNK;
+    const u32 i0 = base + threadIdx.x, i1 = i0 + 1024;
+    u32 sum = ((i0 < n) ? v[i0] : 0) + ((i1 < n) ? v[i1] : 0);
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (u32 d = 16; d >= 1; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if (lane == 0) scratch[wid] = sum;
+    __syncthreads();
+    if (wid == 0) {
+        u32 w = (lane < (blockDim.x >> 5)) ? scratch[lane] : 0;
+#pragma unroll
+        for (u32 d = 16; d >= 1; d >>= 1) w += __shfl_down_sync(0xffffffffu, w, d);
+        if (lane == 0) sums[blockIdx.x] = w;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(u32 *__restrict__ v, u32 n, const u32 *__restrict__ offsets, u32 *__restrict__ copy) {
+    __shared__ u32 cnt[PK_SCAN_CHUNK];
+    __shared__ u32 start[PK_SCAN_CHUNK];
+    __shared__ u32 scratch[64];
+    const u32 base = blockIdx.x * PK_SCAN_CHUNK;
+    for (u32 k = threadIdx.x; k < PK_SCAN_CHUNK; k += blockDim.x) cnt[k] = (base + k < n) ? v[base + k] : 0;
+    __syncthreads();
+    const u32 total = block_exclusive_scan(cnt, start, PK_SCAN_CHUNK, scratch);
+    const u32 off = offsets[blockIdx.x];
+    for (u32 k = threadIdx.x; k < PK_SCAN_CHUNK; k += blockDim.x) {
+        if (base + k < n) {
+            v[base + k] = off + start[k];
+            copy[base + k] = off + start[k];
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) copy[n] = off + total;
+}
+
 // Level 2 scatter: same slicing as the histogram; partitions each slice by the low bucket
 // bits into the final (window-free) order.  gcursor = per-bucket cursors (bucket starts).
 __global__ void __launch_bounds__(512) k_bucket_scatter_staged_b(const u32 *__restrict__ l1_val, const u16 *__restrict__ l1_key, MsmPlan p,
@@ -921,7 +962,10 @@ PK_HD void warp_merge(u32 hk, xyzz hp, u32 tk, const xyzz &tp, xyzz *bucket_sum,
 // Buckets that begin and end inside the run are complete and stored directly.
 // bucket_start[nbuckets] is the entry count.  The kernel keeps only the running
 // XYZZ sum and one affine point live so that four warps fit per SM sub-partition.
-__global__ void __launch_bounds__(128, 4) k_accumulate(const u32 *__restrict__ sorted, const u32 *__restrict__ bucket_start,
+#ifndef PK_ACC_MIN_BLOCKS
+#define PK_ACC_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, PK_ACC_MIN_BLOCKS) k_accumulate(const u32 *__restrict__ sorted, const u32 *__restrict__ bucket_start,
                                                        const affine *__restrict__ bases, MsmPlan p, xyzz *__restrict__ bucket_sum,
                                                        u32 *__restrict__ out_keys, xyzz *__restrict__ out_pts) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1157,7 +1201,14 @@ inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void
         PK_MARK(marks, 3, stream);
         const u32 slice = 4 * S, nslices = 8;
         PK_LAUNCH(k_bucket_hist_b, dim3(p.nbins, nslices), dim3(p.blk), 0, stream, l1_key, p, ws.bin_start, slice, ws.bucket_cur);
-        PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.bucket_start);
+        if (p.nbuckets <= 2 * PK_SCAN_CHUNK) {
+            PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.bucket_start);
+        } else {
+            const u32 nb = (p.nbuckets + PK_SCAN_CHUNK - 1) / PK_SCAN_CHUNK;  // <= 2048 for c <= 22
+            PK_LAUNCH(k_scan_partial, dim3(nb), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.scan_tmp);
+            PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.scan_tmp, nb, ws.scan_tmp + 2050);
+            PK_LAUNCH(k_scan_apply, dim3(nb), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.scan_tmp, ws.bucket_start);
+        }
         const size_t smem2 = stage_smem_bytes(1u << p.lo_bits, S);
         PK_SET_SMEM(k_bucket_scatter_staged_b, smem2);
         PK_LAUNCH(k_bucket_scatter_staged_b, dim3(p.nbins, nslices), dim3(p.blk_stage), smem2, stream, l1_val, l1_key, p, ws.bin_start, slice,

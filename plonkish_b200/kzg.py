@@ -17,7 +17,7 @@ from typing import List, Sequence, Tuple
 
 import numpy as np
 
-from .msm import G1Bases, variable_base_msm
+from .msm import G1Bases, variable_base_msm, variable_base_msm_batch
 
 FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 _MONT = 1 << 256
@@ -70,7 +70,17 @@ def commit(pp: MultilinearKzgProverParam, evals: np.ndarray) -> np.ndarray:
 
 
 def batch_commit(pp: MultilinearKzgProverParam, polys: Sequence[np.ndarray]) -> List[np.ndarray]:
-    """kzg.rs:259-274: one MSM per polynomial, in order."""
+    """kzg.rs:259-274: one MSM per polynomial, in order.  Polynomials of equal size go down
+    as one pipelined batch (upload of the next overlaps the current MSM)."""
+    polys = list(polys)
+    if not polys:
+        return []
+    sizes = {_num_vars_of(p) for p in polys}
+    if len(sizes) == 1 and len(polys) > 1:
+        k = sizes.pop()
+        if k > pp.num_vars():
+            raise ValueError(f"Too many variates of poly to batch commit (param supports variates up to {pp.num_vars()} but got {k})")
+        return list(variable_base_msm_batch(polys, pp.eq(k)))
     return [commit(pp, p) for p in polys]
 
 

@@ -136,6 +136,24 @@ def variable_base_msm(scalars, bases, n_gpus: int = 1) -> np.ndarray:
     return out
 
 
+def variable_base_msm_batch(scalars_list: Sequence, bases: "G1Bases") -> np.ndarray:
+    """One MSM per entry of scalars_list (equal lengths) against one resident base slice ->
+    [count, 8] affine points.  The batch_commit loop of pcs/multilinear/kzg.rs:259-274 with the
+    upload of polynomial j+1 overlapped with the MSM of polynomial j."""
+    arrs = [_as_u64(s, 4, "scalars") for s in scalars_list]
+    count = len(arrs)
+    out = np.zeros((count, 8), dtype=np.uint64)
+    if count == 0:
+        return out
+    n = arrs[0].shape[0]
+    assert all(a.shape[0] == n for a in arrs), "batched polynomials must have the same size"
+    assert n <= bases.n, "more scalars than registered bases"  # msm.rs:90
+    ptrs = (ctypes.c_void_p * count)(*[a.ctypes.data for a in arrs])
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_batch(ptrs, count, bases.handle, n, out.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_batch")
+    return out
+
+
 def _variable_base_msm_gather(scalars: Sequence, bases: Sequence) -> np.ndarray:
     assert len(scalars) == len(bases), "scalars and bases differ in length"  # msm.rs:90
     n = len(scalars)

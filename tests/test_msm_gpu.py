@@ -306,6 +306,7 @@ def test_multilinear_kzg_commit_open_round_trip(pk, oracle):
         f_s = sum(e * q for e, q in zip(evals_int, eq_scalars[k])) % br.R
         assert br.point_from_bytes(comm.tobytes()) == br.scalar_mul(f_s, br.G)  # commit(f) = f(s) * G
         assert [c.tobytes() for c in kzg.batch_commit(pp, [evals, evals[: 1 << (k - 1)]])][0] == comm.tobytes()
+        assert all(c.tobytes() == comm.tobytes() for c in kzg.batch_commit(pp, [evals, evals, evals]))
         x = [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(k)]
         q_comms, value = kzg.open(pp, evals, x)
         assert len(q_comms) == k
@@ -321,6 +322,24 @@ def test_multilinear_kzg_commit_open_round_trip(pk, oracle):
         pp.release()
     with pytest.raises(ValueError):
         kzg.commit(kzg.MultilinearKzgProverParam(eqs[:3], mode=pk.G1Bases.PLAIN), evals)
+
+
+def test_batch_entry_matches_single_calls(pk, oracle):
+    # batch_commit shape (kzg.rs:259-274): several polynomials against one SRS slice.
+    n = 1 << 14
+    bs = oracle.known_dlog_bases(5, 9, n)
+    for mode in (pk.G1Bases.TABLE, pk.G1Bases.PLAIN):
+        reg = pk.G1Bases(bs, mode=mode)
+        polys = [oracle.random_scalars(n, 300 + i) for i in range(5)]
+        got = pk.variable_base_msm_batch(polys, reg)
+        for g, p in zip(got, polys):
+            assert g.tobytes() == oracle.known_dlog_answer(5, 9, p).tobytes()
+        short = [p[:1000] for p in polys[:2]]
+        got = pk.variable_base_msm_batch(short, reg)
+        for g, p in zip(got, short):
+            assert g.tobytes() == oracle.known_dlog_answer(5, 9, p).tobytes()
+        assert pk.variable_base_msm_batch([], reg).shape == (0, 8)
+        reg.release()
 
 
 def test_linearity(pk, oracle):
