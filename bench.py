@@ -136,7 +136,7 @@ def run_reference(args) -> None:
     sec = sum(times) / len(times)
     value = n / sec / 1e6
     sample = f"2^{log_n} points per step (bounded sample of the 2^{args.log_n}-point workload), {cores} pthreads, C port of msm.rs:84-181"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
@@ -144,7 +144,7 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------- HyperPlonk::prove MSM-sequence surrogate
@@ -389,13 +389,32 @@ def run_ours(args) -> None:
             seq["k20"] = prove_msm_sequence(pk, torch, np, min(20, args.prove_k), dev, cpu=True)
         line["hyperplonk_prove_msm"] = seq
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if distributed:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) must not pollute the one-JSON-line contract:
+    everything written to fd 1 during the run goes to stderr; the result line goes to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
