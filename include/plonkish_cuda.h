@@ -152,6 +152,8 @@ uint64_t plonkish_cuda_launch_count(void);
  *   out[5] = wide multiply-adds per second inside mad.lo.cc/madc.hi.cc carry chains
  *            (IMAD.WIDE.U32.X, the instruction the Montgomery products are built from) */
 int plonkish_cuda_bench_integer_pipe(int device, double out[6]);
+/* Field inversions per second: out[0] safegcd division steps (used), out[1] Fermat ladder. */
+int plonkish_cuda_bench_inversion(int device, double out[2]);
 /* The library's fq_mul stream with warps_per_sm (multiple of 4, 4..64) resident warps per SM. */
 int plonkish_cuda_bench_fq_mul_occupancy(int device, int warps_per_sm, double *out_per_s);
 
@@ -166,7 +168,8 @@ int plonkish_cuda_synth_bases_device(int device, void *d_out_affine64, size_t fi
 /* ---- test hooks ------------------------------------------------------------------------------
  * Element-wise probes of the device arithmetic on host arrays, for the parity tests.
  * field ops (32-byte elements): 0 Fq mul, 1 Fq add, 2 Fq sub, 3 Fr Montgomery->canonical
- * (halo2_curves to_repr, msm.rs:153), 4 Fq inverse, 5 Fr mul, 6 Fq negate.
+ * (halo2_curves to_repr, msm.rs:153), 4 Fq inverse (Fermat ladder), 5 Fr mul, 6 Fq negate,
+ * 7 Fq inverse (safegcd, the one the library uses).
  * point ops (128-byte X,Y,ZZ,ZZZ slots; b's first 64 bytes are an affine point for op 0):
  * 0 mixed add, 1 full add, 2 double, 3 to_affine (result in the first 64 bytes). */
 int plonkish_cuda_debug_field_op(int device, int op, const void *a32, const void *b32, void *out32, size_t n);

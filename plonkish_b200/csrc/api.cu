@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(128) k_synth_bases(affine *__restrict__ out, u
         if (!xyzz_is_identity(p)) acc = fq_mul(acc, fq_mul(p.zz, p.zzz));
         xyzz_madd(p, d.x, d.y);
     }
-    fe inv = fq_inv(acc);
+    fe inv = fq_inv_fast(acc);
     for (int j = cnt - 1; j >= 0; --j) {
         affine r;
         if (xyzz_is_identity(pts[j])) {
@@ -940,6 +940,44 @@ extern "C" int plonkish_cuda_bench_fq_mul_occupancy(int device, int warps_per_sm
     return PLONKISH_CUDA_OK;
 }
 
+__global__ void __launch_bounds__(128) k_bench_inv(uint4 *out, u32 iters, u32 seed, int fast) {
+    fe x = fq_one();
+    x.l[0] ^= seed + threadIdx.x; x.l[1] ^= blockIdx.x; x.l[7] &= 0x0fffffffu;
+    for (u32 it = 0; it < iters; ++it) {
+        x = fast ? fq_inv_fast(x) : fq_inv(x);
+        x.l[0] ^= it;  x.l[7] &= 0x0fffffffu;
+    }
+    store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), x);
+}
+// Inversions per second: out[0] safegcd (fq_inv_fast), out[1] Fermat ladder (fq_inv).
+extern "C" int plonkish_cuda_bench_inversion(int device, double out[2]) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out) return fail(PLONKISH_CUDA_E_INVALID, "bench_inversion: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 8, threads = 128;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * threads * 32));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    for (int fast = 1; fast >= 0; --fast) {
+        float ms = 0;
+        const u32 iters = 8;
+        for (int rep = 0; rep < 2; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0, c->stream));
+            PK_LAUNCH(k_bench_inv, dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, iters, 5u + rep, fast);
+            CUDA_TRY(cudaEventRecord(e1, c->stream));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        out[fast ? 0 : 1] = (double)blocks * threads * iters / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
+}
+
 extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[6]) {
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bench_integer_pipe: device %d not initialised", device);
@@ -1010,6 +1048,7 @@ __global__ void k_debug_field(int op, const fe *a, const fe *b, fe *out, u32 n) 
         case 3: r = fr_to_canonical(a[i]); break;
         case 4: r = fq_inv(a[i]); break;
         case 5: r = mont_mul<FrMod>(a[i], b[i]); break;
+        case 7: r = fq_inv_fast(a[i]); break;
         default: r = fq_neg(a[i]); break;
     }
     out[i] = r;

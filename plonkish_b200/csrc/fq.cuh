@@ -326,6 +326,169 @@ PK_HD fe fq_inv(const fe &a) {
     return acc;
 }
 
+// ------------------------------------------------------------ fast inversion
+// Modular inverse by the Bernstein-Yang "safegcd" division steps, 30 steps per batch on
+// signed 30-bit limbs (the formulation popularised by libsecp256k1's modinv32): 20 batches
+// = 600 steps >= the 590 needed for a 256-bit modulus, constant time and branch-free, so
+// every lane of a warp inverts its own value in lock step.  About 15 K instructions against
+// 87 K for the Fermat ladder (380 products); used for the batched affine additions and the
+// final XYZZ -> affine.  Plain C integer arithmetic: the same code runs in the CPU tests.
+struct s30 {
+    int32_t v[9];  // value = sum v[i] * 2^(30 i)
+};
+struct trans30 {
+    int32_t u, v, q, r;
+};
+
+PK_HD s30 fq_modulus_s30() {
+    s30 m = {{0x187cfd47, 0x3082305b, 0x071ca8d3, 0x205aa45a, 0x01585d97, 0x0116da06, 0x1a029b85, 0x139cb84c, 0x3064}};
+    return m;
+}
+#define PK_P_INV30 0x1b799c77u  // p^-1 mod 2^30
+
+PK_HD s30 fe_to_s30(const fe &a) {
+    s30 r;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int bit = 30 * i, word = bit >> 5, sh = bit & 31;
+        u32 val = a.l[word] >> sh;
+        if (sh > 2 && word + 1 < 8) val |= a.l[word + 1] << (32 - sh);
+        r.v[i] = (int32_t)(val & 0x3fffffffu);
+    }
+    return r;
+}
+// r normalised: limbs in [0, 2^30), value < 2^256.
+PK_HD fe s30_to_fe(const s30 &r) {
+    fe o;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int bit = 32 * w, limb = bit / 30, sh = bit % 30;
+        u32 val = (u32)r.v[limb] >> sh;
+        if (limb + 1 < 9) val |= (u32)r.v[limb + 1] << (30 - sh);
+        if (sh > 28 && limb + 2 < 9) val |= (u32)r.v[limb + 2] << (60 - sh);
+        o.l[w] = val;
+    }
+    return o;
+}
+
+PK_HD int32_t divsteps_30(int32_t zeta, u32 f0, u32 g0, trans30 &t) {
+    u32 u = 1, v = 0, q = 0, r = 1;
+    u32 f = f0, g = g0;
+#pragma unroll 1
+    for (int i = 0; i < 30; ++i) {
+        u32 c1 = (u32)(zeta >> 31);
+        const u32 c2 = 0u - (g & 1u);
+        const u32 x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+        g += x & c2; q += y & c2; r += z & c2;
+        c1 &= c2;
+        zeta = (int32_t)(((u32)zeta ^ c1) - 1u);
+        f += g & c1; u += q & c1; v += r & c1;
+        g >>= 1; u <<= 1; v <<= 1;
+    }
+    t.u = (int32_t)u; t.v = (int32_t)v; t.q = (int32_t)q; t.r = (int32_t)r;
+    return zeta;
+}
+
+// [d, e] <- t / 2^30 * [d, e] mod p
+PK_HD void update_de_30(s30 &d, s30 &e, const trans30 &t) {
+    const int32_t M30 = 0x3fffffff;
+    const s30 m = fq_modulus_s30();
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    const int32_t sd = d.v[8] >> 31, se = e.v[8] >> 31;
+    int32_t md = (t.u & sd) + (t.v & se);
+    int32_t me = (t.q & sd) + (t.r & se);
+    int32_t di = d.v[0], ei = e.v[0];
+    int64_t cd = u * di + v * ei;
+    int64_t ce = q * di + r * ei;
+    md -= (int32_t)((PK_P_INV30 * (u32)cd + (u32)md) & (u32)M30);
+    me -= (int32_t)((PK_P_INV30 * (u32)ce + (u32)me) & (u32)M30);
+    cd += (int64_t)m.v[0] * md;
+    ce += (int64_t)m.v[0] * me;
+    cd >>= 30;
+    ce >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+        di = d.v[i]; ei = e.v[i];
+        cd += u * di + v * ei;
+        ce += q * di + r * ei;
+        cd += (int64_t)m.v[i] * md;
+        ce += (int64_t)m.v[i] * me;
+        d.v[i - 1] = (int32_t)cd & M30; cd >>= 30;
+        e.v[i - 1] = (int32_t)ce & M30; ce >>= 30;
+    }
+    d.v[8] = (int32_t)cd;
+    e.v[8] = (int32_t)ce;
+}
+
+// [f, g] <- t / 2^30 * [f, g]
+PK_HD void update_fg_30(s30 &f, s30 &g, const trans30 &t) {
+    const int32_t M30 = 0x3fffffff;
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    int32_t fi = f.v[0], gi = g.v[0];
+    int64_t cf = u * fi + v * gi;
+    int64_t cg = q * fi + r * gi;
+    cf >>= 30;
+    cg >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+        fi = f.v[i]; gi = g.v[i];
+        cf += u * fi + v * gi;
+        cg += q * fi + r * gi;
+        f.v[i - 1] = (int32_t)cf & M30; cf >>= 30;
+        g.v[i - 1] = (int32_t)cg & M30; cg >>= 30;
+    }
+    f.v[8] = (int32_t)cf;
+    g.v[8] = (int32_t)cg;
+}
+
+// r in (-2p, p) with limbs in (-2^30, 2^30) -> [0, p), negated first when sign < 0.
+PK_HD void normalize_30(s30 &r, int32_t sign) {
+    const int32_t M30 = 0x3fffffff;
+    const s30 m = fq_modulus_s30();
+    int32_t cond_add = r.v[8] >> 31;
+    const int32_t cond_negate = sign >> 31;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        r.v[i] += m.v[i] & cond_add;
+        r.v[i] = (r.v[i] ^ cond_negate) - cond_negate;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.v[i + 1] += r.v[i] >> 30;
+        r.v[i] &= M30;
+    }
+    cond_add = r.v[8] >> 31;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.v[i] += m.v[i] & cond_add;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r.v[i + 1] += r.v[i] >> 30;
+        r.v[i] &= M30;
+    }
+}
+
+// x^-1 mod p for a plain integer 0 <= x < p (0 -> 0).
+PK_HD fe fq_inv_plain(const fe &x) {
+    s30 d = {{0, 0, 0, 0, 0, 0, 0, 0, 0}}, e = {{1, 0, 0, 0, 0, 0, 0, 0, 0}};
+    s30 f = fq_modulus_s30(), g = fe_to_s30(x);
+    int32_t zeta = -1;
+#pragma unroll 1
+    for (int i = 0; i < 20; ++i) {
+        trans30 t;
+        zeta = divsteps_30(zeta, (u32)f.v[0], (u32)g.v[0], t);
+        update_de_30(d, e, t);
+        update_fg_30(f, g, t);
+    }
+    normalize_30(d, f.v[8]);
+    return s30_to_fe(d);
+}
+
+// Montgomery inverse: (aR)^-1 = a^-1 R^-1, times R^2 (one product with R^3) gives a^-1 R.
+PK_HD fe fq_inv_fast(const fe &a) {
+    const fe r3 = {{0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u}};
+    return fq_mul(fq_inv_plain(a), r3);
+}
+
 // Fr Montgomery form -> canonical integer (halo2_curves `to_repr`, called at
 // msm.rs:153): one Montgomery reduction, i.e. a product with the plain integer 1.
 PK_HD fe fr_to_canonical(const fe &a) {

@@ -160,7 +160,7 @@ PK_HD affine xyzz_to_affine(const xyzz &p) {
         r.x = fe_zero(); r.y = fe_zero();
         return r;
     }
-    fe i = fq_inv(PK_MUL(p.zz, p.zzz));
+    fe i = fq_inv_fast(PK_MUL(p.zz, p.zzz));
     r.x = PK_MUL(p.x, PK_MUL(i, p.zzz));
     r.y = PK_MUL(p.y, PK_MUL(i, p.zz));
     return r;

@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(128) k_table_normalize(const xyzz *__restrict_
         prefix[j] = acc;
         if (!xyzz_is_identity(v)) acc = fq_mul(acc, fq_mul(v.zz, v.zzz));
     }
-    fe inv = fq_inv(acc);
+    fe inv = fq_inv_fast(acc);
     for (u32 jj = cnt; jj-- > 0;) {
         const xyzz v = load_xyzz(cur + i0 + jj);
         affine r;
@@ -1147,6 +1147,18 @@ struct StageMarks {
     void *ev[9];
 };
 
+// In-place exclusive scan of v[0..n) with a copy (+ total at copy[n]); multi-block above 4096.
+inline void pk_enqueue_scan(u32 *v, u32 n, u32 *copy, u32 *scan_tmp, pk_stream_t stream) {
+    if (n <= 2 * PK_SCAN_CHUNK) {
+        PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, v, n, copy);
+    } else {
+        const u32 nb = (n + PK_SCAN_CHUNK - 1) / PK_SCAN_CHUNK;  // <= 2048 for c <= 22
+        PK_LAUNCH(k_scan_partial, dim3(nb), dim3(1024), 0, stream, v, n, scan_tmp);
+        PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, scan_tmp, nb, scan_tmp + 2050);
+        PK_LAUNCH(k_scan_apply, dim3(nb), dim3(1024), 0, stream, v, n, scan_tmp, copy);
+    }
+}
+
 // Phase 1 of an MSM over p.n points: decompose, sort, accumulate into bucket array p.chunk of
 // ws.bucket_sum (zeroed first).  Chunks of one MSM share c and the bucket layout; the
 // reduce phase adds their arrays.
@@ -1201,14 +1213,7 @@ inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void
         PK_MARK(marks, 3, stream);
         const u32 slice = 4 * S, nslices = 8;
         PK_LAUNCH(k_bucket_hist_b, dim3(p.nbins, nslices), dim3(p.blk), 0, stream, l1_key, p, ws.bin_start, slice, ws.bucket_cur);
-        if (p.nbuckets <= 2 * PK_SCAN_CHUNK) {
-            PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.bucket_start);
-        } else {
-            const u32 nb = (p.nbuckets + PK_SCAN_CHUNK - 1) / PK_SCAN_CHUNK;  // <= 2048 for c <= 22
-            PK_LAUNCH(k_scan_partial, dim3(nb), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.scan_tmp);
-            PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.scan_tmp, nb, ws.scan_tmp + 2050);
-            PK_LAUNCH(k_scan_apply, dim3(nb), dim3(1024), 0, stream, ws.bucket_cur, p.nbuckets, ws.scan_tmp, ws.bucket_start);
-        }
+        pk_enqueue_scan(ws.bucket_cur, p.nbuckets, ws.bucket_start, ws.scan_tmp, stream);
         const size_t smem2 = stage_smem_bytes(1u << p.lo_bits, S);
         PK_SET_SMEM(k_bucket_scatter_staged_b, smem2);
         PK_LAUNCH(k_bucket_scatter_staged_b, dim3(p.nbins, nslices), dim3(p.blk_stage), smem2, stream, l1_val, l1_key, p, ws.bin_start, slice,

@@ -79,6 +79,7 @@ int emul_msm(const void *scalars, const void *bases, u32 n, u32 c_override, u32 
 // product's table kernels, then run an MSM over the first n_use points through it.
 int emul_msm_table_chunked(const void *scalars, const void *bases, u32 n_table, u32 n_use, u32 c, u32 sm_count, u32 nchunks,
                            void *out_affine64);
+
 int emul_msm_table(const void *scalars, const void *bases, u32 n_table, u32 n_use, u32 c, u32 sm_count, void *out_affine64) {
     return emul_msm_table_chunked(scalars, bases, n_table, n_use, c, sm_count, 1, out_affine64);
 }

@@ -60,9 +60,11 @@ def test_ptx_field_arithmetic_matches_python_ints(pk):
     ks = [0, 1, br.R - 1, (br.R - 1) // 2] + [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(500)]
     mont = np.frombuffer(b"".join(br.scalar_to_bytes(k) for k in ks), dtype=np.uint64).reshape(-1, 4)
     assert _ints(_field_op(pk, 3, mont)) == ks
-    inv_in = a[:64]
-    got = _ints(_field_op(pk, 4, _limbs32(inv_in)))
-    assert got == [0 if x == 0 else pow(x, -1, br.P) * br.MONT * br.MONT % br.P for x in inv_in]
+    inv_in = a[:64] + [0, 1, br.P - 1, 2, (br.P - 1) // 2]
+    want_inv = [0 if x == 0 else pow(x, -1, br.P) * br.MONT * br.MONT % br.P for x in inv_in]
+    assert _ints(_field_op(pk, 4, _limbs32(inv_in))) == want_inv       # Fermat ladder
+    big = a + [0, 1, br.P - 1, 2, (br.P - 1) // 2]
+    assert _ints(_field_op(pk, 7, _limbs32(big))) == [0 if x == 0 else pow(x, -1, br.P) * br.MONT * br.MONT % br.P for x in big]  # safegcd
 
 
 def test_group_law_including_exceptional_cases(pk, oracle):
