@@ -465,27 +465,43 @@ extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_pa
 // compute stream decomposes, sorts and accumulates chunk k into its own bucket array
 // (MsmPlan::chunk); one bucket reduce at the end adds the arrays.
 static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &bases, size_t n, xyzz **d_result) {
-    size_t nchunks = (n >= ((size_t)1 << 23)) ? 2 : 1;  // measured at 2^24: 53.6 / 51.6 / 54.1 ms for 1 / 2 / 4 chunks
-    if (const char *e = getenv("PLONKISH_CUDA_HOST_CHUNKS")) {  // tuning override
-        const long v = atol(e);
-        if (v >= 1 && v <= 16) nchunks = (size_t)v;
+    // Chunk boundaries.  Only the first chunk's copy is exposed, so it is small; later chunks
+    // grow (1/8, 3/8, 1/2) and each copies while its predecessor computes.  Measured at 2^24:
+    // 53.6 ms unchunked, 51.6 ms for two halves (4- and 8-way equal splits lose to per-chunk costs).
+    std::vector<size_t> cuts;  // chunk end offsets
+    const char *env = getenv("PLONKISH_CUDA_HOST_CHUNKS");  // tuning override: N equal chunks
+    const long forced = env ? atol(env) : 0;
+    if (forced >= 1 && forced <= 16) {
+        for (long k = 1; k <= forced; ++k) cuts.push_back(n * (size_t)k / (size_t)forced);
+    } else if (n >= ((size_t)1 << 23) && n <= MAX_POINTS_PER_LAUNCH) {
+        cuts = {n / 8, n / 2, n};
+    } else {
+        const size_t pieces = (n + MAX_POINTS_PER_LAUNCH - 1) / MAX_POINTS_PER_LAUNCH;
+        for (size_t k = 1; k <= pieces; ++k) cuts.push_back(n * k / pieces);
     }
-    const size_t min_chunks = (n + MAX_POINTS_PER_LAUNCH - 1) / MAX_POINTS_PER_LAUNCH;
-    if (nchunks < min_chunks) nchunks = min_chunks;
+    {  // drop empty chunks (tiny n with a forced chunk count)
+        std::vector<size_t> kept;
+        for (size_t k = 0, prev = 0; k < cuts.size(); ++k) {
+            if (cuts[k] > prev) { kept.push_back(cuts[k]); prev = cuts[k]; }
+        }
+        cuts.swap(kept);
+    }
+    const size_t nchunks = cuts.size();
     if (nchunks > 16) return fail(PLONKISH_CUDA_E_INVALID, "msm: n = %zu is beyond 16 x 2^26 points", n);
-    const size_t per = (n + nchunks - 1) / nchunks;
+    size_t largest = 0;
+    for (size_t k = 0, prev = 0; k < nchunks; prev = cuts[k], ++k) largest = (cuts[k] - prev > largest) ? cuts[k] - prev : largest;
+    if (largest > MAX_POINTS_PER_LAUNCH) return fail(PLONKISH_CUDA_E_INVALID, "msm: chunk of %zu points exceeds 2^26", largest);
     // every chunk uses the window width the whole MSM would use, so the bucket layout is shared
     const uint32_t c_all = bases.table_c ? 0 : plan_for(c, bases, n < MAX_POINTS_PER_LAUNCH ? n : MAX_POINTS_PER_LAUNCH, 0).c;
-    MsmPlan plan0 = plan_for(c, bases, per, c_all);
+    MsmPlan plan0 = plan_for(c, bases, largest, c_all);
     plan0.nchunks = (u32)nchunks;
     int rc = grow(c->arena, pk_workspace_bytes(plan0));
     if (rc) return rc;
     if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
     MsmWorkspace ws0 = pk_carve_workspace(plan0, c->arena.ptr);
     MsmPlan last = plan0;
-    size_t k = 0;
-    for (size_t done = 0; done < n; done += per, ++k) {
-        const size_t cnt = (n - done < per) ? n - done : per;
+    for (size_t k = 0, done = 0; k < nchunks; done = cuts[k], ++k) {
+        const size_t cnt = cuts[k] - done;
         char *d_chunk = (char *)c->scalars.ptr + done * PLONKISH_CUDA_SCALAR_BYTES;
         cudaStream_t cs = (nchunks > 1) ? c->copy_stream : c->stream;
         CUDA_TRY(cudaMemcpyAsync(d_chunk, (const char *)h_scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES,
@@ -494,7 +510,7 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
             CUDA_TRY(cudaEventRecord(c->chunk_ready[k], cs));
             CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
         }
-        MsmPlan plan = (cnt == per) ? plan0 : plan_for(c, bases, cnt, c_all);
+        MsmPlan plan = plan_for(c, bases, cnt, c_all);
         plan.chunk = (u32)k;
         plan.nchunks = (u32)nchunks;
         MsmWorkspace w = pk_carve_workspace(plan, c->arena.ptr);
