@@ -314,8 +314,8 @@ def run_ours(args) -> None:
     entries = float(n) * plan["windows"]
     if plan["idx_bits"]:  # plain bases: u16 digit in, u32 entry out; then u32 in, u32 out
         sort_bytes = entries * (2 + 4) + entries * (4 + 4)
-    else:                 # table: u32 digit in, u64 entry out; then u64 in, u32 out
-        sort_bytes = entries * (4 + 8) + entries * (8 + 4)
+    else:                 # table layout: staged two-level partition
+        sort_bytes = entries * (4 + 6) + entries * (2 + 6 + 4)  # level 1: digit in, value + key out; level 2: key (hist), key + value in, entry out
     sort_ms = stages["bin_scatter"] + stages["bin_sort"]
     roofline = {
         "kernel": "k_accumulate (XYZZ mixed additions, 254-bit Montgomery, IMAD.WIDE carry chains)",
@@ -327,12 +327,19 @@ def run_ours(args) -> None:
         "executed_imad_per_launch": executed_imad,
         "executed_timad_per_s": executed_imad / (stages["accumulate"] * 1e-3) / 1e12,
         "kernel_ms": stages["accumulate"],
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one 2^24-point launch in the committed ncu --set full capture
+        # (profiles/r01_v3_kernels_ncu_raw.csv: 29.47 GB + 0.23 GB), scaled to this launch's entry count
+        "traffic": 29.70e9 * (float(n) * plan["windows"]) / (16777216.0 * 13),
+        "traffic_source": "ncu capture under profiles/ (not measured in this run); algorithmic gather = entries x 68 B",
+        "algorithmic_bytes": float(n) * plan["windows"] * 68,
     }
     roofline_sort = {
-        "kernel": "k_scatter_bins + k_sort_bins", "bound": "hbm", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9,
+        "kernel": "the two sort levels (k_scatter_staged_b, k_bucket_hist_b, k_bucket_scatter_staged_b; plain bases: k_scatter_bins, k_sort_bins)", "bound": "hbm", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9,
         "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
-        "frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": sort_ms, "traffic": None,
+        "frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": sort_ms,
+        # table layout, 2^24: k_scatter_staged_b 0.95 + 1.32 GB, k_bucket_hist_b 0.44 GB, k_bucket_scatter_staged_b 1.68 + 1.11 GB (same capture)
+        "traffic": (5.51e9 * entries / (16777216.0 * 13)) if not plan["idx_bits"] else None,
+        "algorithmic_bytes": sort_bytes,
     }
 
     line = {
