@@ -152,6 +152,13 @@ uint64_t plonkish_cuda_launch_count(void);
  *   out[5] = wide multiply-adds per second inside mad.lo.cc/madc.hi.cc carry chains
  *            (IMAD.WIDE.U32.X, the instruction the Montgomery products are built from) */
 int plonkish_cuda_bench_integer_pipe(int device, double out[6]);
+/* Field products per second inside register-resident mixed-addition streams shaped like
+ * k_accumulate (128-thread blocks, no memory traffic): out[0] one XYZZ accumulator per thread at
+ * 128 registers (4 blocks/SM), out[1] two accumulators per thread, out[2] one dependent fq_mul
+ * chain per thread, out[3] / out[4] = out[0] / out[1] with the register cap lifted (2 blocks/SM).
+ * k_accumulate's ceiling is out[0]; the fq_mul-stream peak of bench_integer_pipe is what two
+ * short independent chains per thread reach at 30 registers. */
+int plonkish_cuda_bench_madd(int device, double out[5]);
 /* Field inversions per second: out[0] safegcd division steps (used), out[1] Fermat ladder. */
 int plonkish_cuda_bench_inversion(int device, double out[2]);
 /* The library's fq_mul stream with warps_per_sm (multiple of 4, 4..64) resident warps per SM. */

@@ -17,6 +17,7 @@ from .msm import (  # noqa: F401
     profile_stages_device,
     launch_count,
     bench_integer_pipe,
+    bench_madd,
     random_scalars,
 )
 from .distributed import shard_bounds, variable_base_msm_sharded  # noqa: F401

@@ -965,6 +965,64 @@ __global__ void __launch_bounds__(128) k_bench_inv(uint4 *out, u32 iters, u32 se
     }
     store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), x);
 }
+// Register-resident mixed-addition streams (no memory traffic, no bucket logic), 128-thread
+// blocks like k_accumulate: variant 0 = one XYZZ accumulator per thread, 1 = two independent
+// accumulators per thread, 2 = one dependent fq_mul chain per thread; MINB = blocks per SM the
+// register allocation is capped for (4 -> 128 registers, 2 -> uncapped).
+template <int VARIANT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bench_madd(uint4 *out, u32 iters, u32 seed) {
+    fe x = fq_one(), y = fq_dbl(fq_one());
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x;
+    x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu;
+    xyzz a = xyzz_identity(), b = xyzz_identity();
+    if (VARIANT == 2) {
+        for (u32 it = 0; it < iters * 10; ++it) x = fq_mul(x, y);
+        store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), x);
+        return;
+    }
+    for (u32 it = 0; it < iters; ++it) {
+        xyzz_madd<MulInline>(a, x, y);
+        if (VARIANT == 1) xyzz_madd<MulInline>(b, y, x);
+        x.l[0] += 2; y.l[0] += 6;
+    }
+    fe r = fq_add(a.x, fq_add(a.zz, fq_add(b.y, b.zzz)));
+    store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), r);
+}
+// out[v] = field products per second inside the stream of variant v (10 per mixed addition).
+extern "C" int plonkish_cuda_bench_madd(int device, double out[5]) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out) return fail(PLONKISH_CUDA_E_INVALID, "bench_madd: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 4 * 4, threads = 128;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * threads * 32));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const u32 iters = 64;
+    for (int v = 0; v < 5; ++v) {
+        float ms = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0, c->stream));
+            if (v == 0) PK_LAUNCH((k_bench_madd<0, 4>), dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, iters, 3u + rep);
+            if (v == 1) PK_LAUNCH((k_bench_madd<1, 4>), dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, iters, 3u + rep);
+            if (v == 2) PK_LAUNCH((k_bench_madd<2, 4>), dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, iters, 3u + rep);
+            if (v == 3) PK_LAUNCH((k_bench_madd<0, 2>), dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, iters, 3u + rep);
+            if (v == 4) PK_LAUNCH((k_bench_madd<1, 2>), dim3(blocks), dim3(threads), 0, c->stream, (uint4 *)scratch, iters, 3u + rep);
+            CUDA_TRY(cudaEventRecord(e1, c->stream));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        const double madds = (double)blocks * threads * iters * ((v == 1 || v == 4) ? 2.0 : 1.0);
+        out[v] = madds * 10.0 / (ms * 1e-3);
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
+}
+
 // Inversions per second: out[0] safegcd (fq_inv_fast), out[1] Fermat ladder (fq_inv).
 extern "C" int plonkish_cuda_bench_inversion(int device, double out[2]) {
     Ctx *c = ctx_for(device);

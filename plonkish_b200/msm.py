@@ -266,6 +266,14 @@ def bench_integer_pipe(device: int = 0) -> dict:
             "imad32_per_s": out[4], "imad_wide_chain_per_s": out[5]}
 
 
+def bench_madd(device: int = 0) -> dict:
+    """Field products per second of register-resident mixed-addition streams (see the header)."""
+    out = (ctypes.c_double * 5)()
+    _lib.check(_lib.lib().plonkish_cuda_bench_madd(device, out), "plonkish_cuda_bench_madd")
+    keys = ("madd_1acc_128regs", "madd_2acc_128regs", "fq_mul_1chain", "madd_1acc_uncapped", "madd_2acc_uncapped")
+    return dict(zip(keys, [float(v) for v in out]))
+
+
 def random_scalars(n: int, seed: int) -> np.ndarray:
     """Synthetic Fr elements (Montgomery limbs): three uniform u64 limbs and a top
     limb drawn below r's top limb, so every value is a valid representation < r."""
