@@ -306,8 +306,7 @@ def run_ours(args) -> None:
             return pk.variable_base_msm(scalars_np, reg)
     else:
         def step_e2e():
-            sc = scalars_host_t.to(dev, non_blocking=True)
-            return pk.variable_base_msm_sharded(sc, step_bases, window_bits=args.window_bits).cpu().numpy().view(np.uint64)
+            return pk.variable_base_msm_sharded_host(scalars_np, reg).cpu().numpy().view(np.uint64)
 
     for _ in range(2):
         e2e_out = step_e2e()
@@ -394,7 +393,7 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 64 * world,
                 "path": "plonkish_cuda_msm_bn254_g1 (C ABI, pinned host scalars, registered bases)" if not distributed
-                        else "pinned host scalars -> H2D -> variable_base_msm_sharded -> host"},
+                        else "per rank: plonkish_cuda_msm_bn254_g1_host_partial (C ABI, pinned host scalars, registered bases) -> NCCL all_gather of partials -> fold -> host"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sort": roofline_sort,

@@ -121,6 +121,11 @@ int plonkish_cuda_msm_bn254_g1_device(int device, const void *d_scalars, const v
 int plonkish_cuda_msm_bn254_g1_device_resident(const void *d_scalars, uint64_t bases_handle, size_t n, void *d_out_affine64,
                                                void *d_out_xyzz128, void *cuda_stream);
 
+/* Host scalars against a registered slice, projective partial left in device memory
+ * (d_out_xyzz128): what one rank of the one-process-per-GPU deployment computes before the
+ * all-gather.  Blocking; the scalar upload is pipelined like plonkish_cuda_msm_bn254_g1. */
+int plonkish_cuda_msm_bn254_g1_host_partial(const void *scalars_mont32, uint64_t bases_handle, size_t n, void *d_out_xyzz128);
+
 /* Adds `count` projective partials (128 B each, e.g. one per rank after an NCCL
  * all-gather) and normalises: msm.rs:112-114 followed by the caller's to_affine(). */
 int plonkish_cuda_g1_sum_partials_device(int device, const void *d_partials_xyzz128, size_t count, void *d_out_affine64,

@@ -12,6 +12,7 @@ from .msm import (  # noqa: F401
     variable_base_msm_batch,
     variable_base_msm_device,
     sum_partials_device,
+    host_partial,
     synth_bases_device,
     msm_plan,
     profile_stages_device,
@@ -20,4 +21,4 @@ from .msm import (  # noqa: F401
     bench_madd,
     random_scalars,
 )
-from .distributed import shard_bounds, variable_base_msm_sharded  # noqa: F401
+from .distributed import shard_bounds, variable_base_msm_sharded, variable_base_msm_sharded_host  # noqa: F401

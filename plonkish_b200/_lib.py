@@ -29,6 +29,7 @@ EXPORTS = (
     "plonkish_cuda_msm_bn254_g1_multi",
     "plonkish_cuda_msm_bn254_g1_device",
     "plonkish_cuda_msm_bn254_g1_device_resident",
+    "plonkish_cuda_msm_bn254_g1_host_partial",
     "plonkish_cuda_g1_sum_partials_device",
     "plonkish_cuda_msm_plan",
     "plonkish_cuda_msm_profile_device",
@@ -79,6 +80,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_multi.argtypes = [ci, vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_device.argtypes = [ci, vp, vp, sz, u32, vp, vp, vp]
     lib.plonkish_cuda_msm_bn254_g1_device_resident.argtypes = [vp, u64, sz, vp, vp, vp]
+    lib.plonkish_cuda_msm_bn254_g1_host_partial.argtypes = [vp, u64, sz, vp]
     lib.plonkish_cuda_g1_sum_partials_device.argtypes = [ci, vp, sz, vp, vp]
     lib.plonkish_cuda_msm_plan.argtypes = [ci, sz, u32, u64, ctypes.POINTER(u32)]
     lib.plonkish_cuda_msm_profile_device.argtypes = [ci, vp, vp, u64, sz, u32, vp, ctypes.POINTER(ctypes.c_double)]

@@ -619,6 +619,35 @@ extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list,
     return PLONKISH_CUDA_OK;
 }
 
+// Host scalars in, this rank's projective partial out (device memory): the per-rank half of the
+// point-sharded MSM (msm.rs:101-111) for the one-process-per-GPU deployment; the ranks then
+// all-gather the 128-byte partials and fold them (plonkish_cuda_g1_sum_partials_device).
+extern "C" int plonkish_cuda_msm_bn254_g1_host_partial(const void *scalars, uint64_t bases_handle, size_t n, void *d_out_xyzz128) {
+    if (!d_out_xyzz128) return fail(PLONKISH_CUDA_E_INVALID, "msm_host_partial: null output");
+    if (!bases_handle) return fail(PLONKISH_CUDA_E_INVALID, "msm_host_partial: a registered bases handle is required");
+    if (n && !scalars) return fail(PLONKISH_CUDA_E_INVALID, "msm_host_partial: null scalars");
+    BasesView view;
+    int device = 0;
+    int rc = view_of(bases_handle, n, -1, view, &device, "msm_host_partial");
+    if (rc) return rc;
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_host_partial: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out_xyzz128, 0, PLONKISH_CUDA_XYZZ_BYTES, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return PLONKISH_CUDA_OK;
+    }
+    if ((rc = grow(c->scalars, n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    xyzz *res = nullptr;
+    if ((rc = enqueue_host_msm(c, scalars, view, n, &res))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_out_xyzz128, res, PLONKISH_CUDA_XYZZ_BYTES, cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = mark_done(c, c->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PLONKISH_CUDA_OK;
+}
+
 extern "C" int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs, const void *const *base_ptrs, size_t n, void *out_affine64) {
     if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null output");
     if (n && (!scalar_ptrs || !base_ptrs)) return fail(PLONKISH_CUDA_E_INVALID, "msm_gather: null pointer table");

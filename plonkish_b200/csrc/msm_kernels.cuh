@@ -1065,7 +1065,7 @@ PK_HD xyzz xyzz_mul_small(const xyzz &pnt, u32 k) {
 // grid (red_blocks, W), block 256.  Thread j of window w owns buckets
 // [j*rb, (j+1)*rb): sum_i (j*rb + i + 1) * B_i = acc + (j*rb) * run, where run is
 // the plain sum and acc the running-sum total (msm.rs:175-179 restated per chunk).
-__global__ void __launch_bounds__(256) k_bucket_reduce(const xyzz *__restrict__ bucket_sum, const u32 *__restrict__ bucket_start,
+__global__ void __launch_bounds__(256, 2) k_bucket_reduce(const xyzz *__restrict__ bucket_sum, const u32 *__restrict__ bucket_start,
                                                        MsmPlan p, xyzz *__restrict__ block_out) {
     __shared__ xyzz warp_part[8];
     const u32 w = blockIdx.y;

@@ -43,3 +43,14 @@ def variable_base_msm_sharded(local_scalars, local_bases, group=None, *, window_
     partial = msm.variable_base_msm_device(local_scalars, local_bases, window_bits=window_bits, partial=True)
     allp = gather_partials(partial, group)
     return msm.sum_partials_device(allp)
+
+
+def variable_base_msm_sharded_host(local_scalars, local_bases, group=None):
+    """Same with this rank's scalars in host memory (numpy [n, 4] uint64) and its bases resident
+    (G1Bases): the C-ABI host call uploads the scalars in chunks overlapped with the compute and
+    leaves the partial on the GPU; all_gather + fold follow.  Returns the affine sum ([8] CUDA tensor)."""
+    from . import msm
+
+    partial = msm.host_partial(local_scalars, local_bases)
+    allp = gather_partials(partial, group)
+    return msm.sum_partials_device(allp)

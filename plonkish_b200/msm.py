@@ -204,6 +204,18 @@ def variable_base_msm_device(scalars, bases, out=None, *, window_bits: int = 0, 
     return out
 
 
+def host_partial(scalars, bases: "G1Bases"):
+    """Host scalars against a resident slice -> this rank's projective partial, a [16]-limb int64
+    CUDA tensor on the slice's device (blocking; the upload is pipelined with the compute)."""
+    torch = _torch()
+    sc = _as_u64(scalars, 4, "scalars")
+    assert sc.shape[0] <= bases.n, "more scalars than registered bases"  # msm.rs:90
+    out = torch.empty(16, dtype=torch.int64, device=torch.device("cuda", bases.device))
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_host_partial(sc.ctypes.data, bases.handle, sc.shape[0], out.data_ptr())
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_host_partial")
+    return out
+
+
 def sum_partials_device(partials, out=None):
     """Adds [k, 16]-limb projective partials and normalises to an affine [8] tensor."""
     torch = _torch()

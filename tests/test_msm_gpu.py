@@ -403,6 +403,22 @@ def test_sharded_partials_sum_to_the_whole(pk, oracle):
         assert got.tobytes() == oracle.known_dlog_answer(9, 4, sc).tobytes()
 
 
+def test_host_partial_entry(pk, oracle):
+    import torch
+
+    n = 50000
+    sc = oracle.random_scalars(n, 31)
+    bs = oracle.known_dlog_bases(3, 5, n)
+    reg = pk.G1Bases(bs)
+    halves = [pk.host_partial(sc[: n // 2], reg)]
+    reg2 = pk.G1Bases(bs[n // 2:])
+    halves.append(pk.host_partial(sc[n // 2:], reg2))
+    got = pk.sum_partials_device(torch.stack(halves).contiguous()).cpu().numpy().view(np.uint64)
+    assert got.tobytes() == oracle.known_dlog_answer(3, 5, sc).tobytes()
+    reg.release()
+    reg2.release()
+
+
 def test_multi_gpu_single_process(pk, oracle):
     from plonkish_b200 import _lib
 
