@@ -352,6 +352,9 @@ def run_ours(args) -> None:
         "kernel": "k_accumulate (XYZZ mixed additions, 254-bit Montgomery, IMAD.WIDE carry chains)",
         "bound": "imad", "achieved": achieved, "peak": peak, "unit": "TIMAD/s (32x32->64 multiply-adds)",
         "frac": achieved / peak,
+        "frac_note": "above 1 is expected with the table layout: the algorithmic figure is fixed at 16 windows per point "
+                     "(SURVEY.md 8d) and the kernel executes plan['windows'] of them; executed_frac is the executed-work fraction",
+        "executed_frac": (executed_imad / (stages["accumulate"] * 1e-3) / 1e12) / peak,
         "peak_source": "measured in this run by plonkish_cuda_bench_integer_pipe: max(independent mad.wide.u32 stream, "
                        "IMAD.WIDE.U32.X carry-chain stream, library fq_mul stream x 136); MEASURED_PEAKS.json has no integer-pipe figure",
         "algorithmic_imad_per_launch": imad_per_launch,

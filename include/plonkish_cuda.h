@@ -164,6 +164,9 @@ int plonkish_cuda_bench_integer_pipe(int device, double out[6]);
  * k_accumulate's ceiling is out[0]; the fq_mul-stream peak of bench_integer_pipe is what two
  * short independent chains per thread reach at 30 registers. */
 int plonkish_cuda_bench_madd(int device, double out[5]);
+/* Rows of 8 partial products (8 limbs x 1 limb, accumulated) per second: out[0] spelled as 16
+ * 32-bit IMADs in two carry chains (lo then hi), out[1] as 8 fused IMAD.WIDE (the library's form). */
+int plonkish_cuda_bench_row_forms(int device, double out[2]);
 /* Field inversions per second: out[0] safegcd division steps (used), out[1] Fermat ladder. */
 int plonkish_cuda_bench_inversion(int device, double out[2]);
 /* The library's fq_mul stream with warps_per_sm (multiple of 4, 4..64) resident warps per SM. */

@@ -38,6 +38,7 @@ EXPORTS = (
     "plonkish_cuda_bench_fq_mul_occupancy",
     "plonkish_cuda_bench_inversion",
     "plonkish_cuda_bench_madd",
+    "plonkish_cuda_bench_row_forms",
     "plonkish_cuda_synth_bases_device",
     "plonkish_cuda_debug_field_op",
     "plonkish_cuda_debug_point_op",
@@ -90,6 +91,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_bench_fq_mul_occupancy.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_bench_inversion.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_bench_madd.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.plonkish_cuda_bench_row_forms.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_synth_bases_device.argtypes = [ci, vp, sz, sz, u64, u64, vp]
     lib.plonkish_cuda_debug_field_op.argtypes = [ci, ci, vp, vp, vp, sz]
     lib.plonkish_cuda_debug_point_op.argtypes = [ci, ci, vp, vp, vp, sz]

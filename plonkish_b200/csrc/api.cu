@@ -872,7 +872,7 @@ extern "C" int plonkish_cuda_synth_bases_device(int device, void *d_out, size_t 
 // dependent chain shorter than 16 instructions, so the multiplier pipe is the limit.
 __global__ void __launch_bounds__(256) k_bench_imad_wide(unsigned long long *out, u32 iters, u32 seed) {
     unsigned long long acc[16];
-    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u);
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = (unsigned long long)(a + k) << 7;
     for (u32 it = 0; it < iters; ++it) {
@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(256) k_bench_imad_wide(unsigned long long *out
 // 16 independent 32-bit accumulators fed by mad.lo.u32 (plain IMAD).
 __global__ void __launch_bounds__(256) k_bench_imad32(u32 *out, u32 iters, u32 seed) {
     u32 acc[16];
-    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u);
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = a + k;
     for (u32 it = 0; it < iters; ++it) {
@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(256) k_bench_imad32(u32 *out, u32 iters, u32 s
 // K3's Montgomery products are made of.  4 wide multiply-adds per cmad8.
 __global__ void __launch_bounds__(256) k_bench_chain(u32 *out, u32 iters, u32 seed) {
     u32 acc[4][8];
-    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u);
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -927,10 +927,117 @@ __global__ void __launch_bounds__(256) k_bench_chain(u32 *out, u32 iters, u32 se
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Narrow carry chains: 8 x mad.lo.cc then 8 x mad.hi.cc per accumulator row (the unfused form of
+// a row of partial products: 16 32-bit IMADs with carry instead of 8 IMAD.WIDE).
+__global__ void __launch_bounds__(256) k_bench_narrow_chain(u32 *out, u32 iters, u32 seed) {
+    u32 acc[2][10];
+    u32 a[8];
+    u32 b = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + threadIdx.x * 2654435761u + k * 97u;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) acc[j][k] = a[k & 7] + j;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            u32 *c = acc[j];
+            asm volatile("mad.lo.cc.u32  %0, %10, %18, %0;\n\t"
+                "madc.lo.cc.u32 %1, %11, %18, %1;\n\t"
+                "madc.lo.cc.u32 %2, %12, %18, %2;\n\t"
+                "madc.lo.cc.u32 %3, %13, %18, %3;\n\t"
+                "madc.lo.cc.u32 %4, %14, %18, %4;\n\t"
+                "madc.lo.cc.u32 %5, %15, %18, %5;\n\t"
+                "madc.lo.cc.u32 %6, %16, %18, %6;\n\t"
+                "madc.lo.cc.u32 %7, %17, %18, %7;\n\t"
+                "addc.u32       %8, %8, 0;\n\t"
+                "mad.hi.cc.u32  %1, %10, %18, %1;\n\t"
+                "madc.hi.cc.u32 %2, %11, %18, %2;\n\t"
+                "madc.hi.cc.u32 %3, %12, %18, %3;\n\t"
+                "madc.hi.cc.u32 %4, %13, %18, %4;\n\t"
+                "madc.hi.cc.u32 %5, %14, %18, %5;\n\t"
+                "madc.hi.cc.u32 %6, %15, %18, %6;\n\t"
+                "madc.hi.cc.u32 %7, %16, %18, %7;\n\t"
+                "madc.hi.cc.u32 %8, %17, %18, %8;\n\t"
+                "addc.u32       %9, %9, 0;"
+                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8]), "+r"(c[9])
+                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b + (u32)j));
+        }
+        b += 0x9e3779b9u;
+    }
+    u32 sres = 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 10; ++k) sres ^= acc[j][k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sres;
+}
+// Same row as 8 fused pairs (the even/odd form the library uses: two cmad8 per row).
+__global__ void __launch_bounds__(256) k_bench_wide_row(u32 *out, u32 iters, u32 seed) {
+    u32 ev[2][8], od[2][8];
+    u32 a[8];
+    u32 b = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + threadIdx.x * 2654435761u + k * 97u;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ev[j][k] = a[k] + j; od[j][k] = a[k] ^ j; }
+    u32 carries = 0;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            carries += cmad8(ev[j], a[0], a[2], a[4], a[6], b + (u32)j);
+            carries += cmad8(od[j], a[1], a[3], a[5], a[7], b + (u32)j);
+        }
+        b += 0x9e3779b9u;
+    }
+    u32 sres = carries;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sres ^= ev[j][k] ^ od[j][k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sres;
+}
+// out[0] rows per second in the narrow form (16 IMAD + 2 add per row), out[1] in the fused form
+// (8 IMAD.WIDE per row): which spelling of a row of partial products the multiplier pipe prefers.
+extern "C" int plonkish_cuda_bench_row_forms(int device, double out[2]) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out) return fail(PLONKISH_CUDA_E_INVALID, "bench_row_forms: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const u32 iters = 2048;
+    for (int v = 0; v < 2; ++v) {
+        float ms = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0, c->stream));
+            if (v == 0) PK_LAUNCH(k_bench_narrow_chain, dim3(blocks), dim3(threads), 0, c->stream, (u32 *)scratch, iters, 11u + rep);
+            if (v == 1) PK_LAUNCH(k_bench_wide_row, dim3(blocks), dim3(threads), 0, c->stream, (u32 *)scratch, iters, 11u + rep);
+            CUDA_TRY(cudaEventRecord(e1, c->stream));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        out[v] = (double)blocks * threads * 2.0 * iters / (ms * 1e-3);
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
+}
+
 // Two independent Montgomery products per thread per iteration (the K3 instruction mix).
 __global__ void __launch_bounds__(256) k_bench_fq_mul(uint4 *out, u32 iters, u32 seed) {
+    // every chain value depends on the thread index: a warp-uniform chain would be moved to the
+    // uniform datapath (UIMAD) by ptxas and would not load the vector multiplier pipe at all
     fe x = fq_one(), y = fq_one(), z = fq_one();
-    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x; z.l[2] ^= seed;
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x + 977u * threadIdx.x; z.l[2] ^= seed + 31u * threadIdx.x;
     x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu; z.l[7] &= 0x0fffffffu;
     for (u32 it = 0; it < iters; ++it) {
         x = fq_mul(x, z);
@@ -945,7 +1052,7 @@ __global__ void __launch_bounds__(256) k_bench_fq_mul(uint4 *out, u32 iters, u32
 __global__ void __launch_bounds__(128) k_bench_fq_mul_occ(uint4 *out, u32 iters, u32 seed) {
     extern __shared__ unsigned char pad_smem[];
     fe x = fq_one(), y = fq_one(), z = fq_one();
-    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x; z.l[2] ^= seed;
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x + 977u * threadIdx.x; z.l[2] ^= seed + 31u * threadIdx.x;
     x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu; z.l[7] &= 0x0fffffffu;
     if (seed == 0xffffffffu) pad_smem[threadIdx.x] = 1;  // keep the allocation alive
     for (u32 it = 0; it < iters; ++it) {
@@ -1001,7 +1108,7 @@ __global__ void __launch_bounds__(128) k_bench_inv(uint4 *out, u32 iters, u32 se
 template <int VARIANT, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_bench_madd(uint4 *out, u32 iters, u32 seed) {
     fe x = fq_one(), y = fq_dbl(fq_one());
-    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x;
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x + 977u * threadIdx.x;
     x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu;
     xyzz a = xyzz_identity(), b = xyzz_identity();
     if (VARIANT == 2) {
