@@ -167,7 +167,8 @@ def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
     def run():
         # batch_commit of the 3 witness polynomials (hyperplonk.rs:201), then the z-poly commit (:251)
         outs = list(pk.variable_base_msm_batch([host, host, host], regs[k])) + [pk.variable_base_msm(host, regs[k])]
-        outs += [pk.variable_base_msm(host[: 1 << i], regs[i]) for i in reversed(range(k))]
+        # open: the k quotient commitments in one call (kzg.rs:291-293), small ones concurrently
+        outs += list(pk.variable_base_msm_many([host[: 1 << i] for i in reversed(range(k))], [regs[i] for i in reversed(range(k))]))
         return outs
 
     run()

@@ -91,6 +91,14 @@ int plonkish_cuda_msm_bn254_g1(const void *scalars_mont32, const void *bases_aff
 int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_mont32_list, size_t count, uint64_t bases_handle, size_t n,
                                      void *out_affine64_list);
 
+/* `count` independent MSMs, MSM j with ns[j] host scalars against the registered slice
+ * bases_handles[j] (all on one device); results in out_affine64_list[j*64 ..].  The shape of
+ * MultilinearKzg::open (pcs/multilinear/kzg.rs:291-293): k quotient commitments of sizes
+ * 2^(k-1)..1 against eqs[k-1..0], which do not depend on one another.  Large MSMs run in turn
+ * with pipelined uploads, small ones concurrently on side streams; one host wait. */
+int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_mont32_list, const uint64_t *bases_handles, const size_t *ns,
+                                    size_t count, void *out_affine64_list);
+
 /* Same for the reference's non-contiguous callers, which pass iterators of
  * references (chain![..] at pcs/univariate/kzg.rs:346,408; .map(|c| &c.0) at
  * pcs/multilinear/kzg.rs:145): gathers the n scalars and n bases into staging first. */

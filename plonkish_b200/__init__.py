@@ -10,6 +10,7 @@ from .msm import (  # noqa: F401
     ShardedG1Bases,
     variable_base_msm,
     variable_base_msm_batch,
+    variable_base_msm_many,
     variable_base_msm_device,
     sum_partials_device,
     host_partial,

@@ -24,6 +24,7 @@ EXPORTS = (
     "plonkish_cuda_bases_register_device",
     "plonkish_cuda_msm_bn254_g1",
     "plonkish_cuda_msm_bn254_g1_batch",
+    "plonkish_cuda_msm_bn254_g1_many",
     "plonkish_cuda_msm_bn254_g1_gather",
     "plonkish_cuda_bases_register_sharded",
     "plonkish_cuda_msm_bn254_g1_multi",
@@ -76,6 +77,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_bases_register_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
+    lib.plonkish_cuda_msm_bn254_g1_many.argtypes = [vp, vp, vp, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
     lib.plonkish_cuda_bases_register_sharded.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1_multi.argtypes = [ci, vp, vp, u64, sz, vp]

@@ -67,6 +67,13 @@ struct Ctx {
     bool has_last = false;
     DeviceBuffer arena, scalars, scalars2, bases_tmp, partials, batch_out;
     cudaEvent_t buf_free[2] = {};         // batch path: scalar buffer b may be overwritten again
+    cudaEvent_t many_start = nullptr;     // many path: side lanes start after this point of the main stream
+    struct Lane {                         // extra streams with their own scratch: small independent MSMs run side by side
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DeviceBuffer arena, scalars;
+        void *d_res = nullptr;            // 128-byte projective result slot
+    } lanes[3];
     void *d_out = nullptr;  // [0,64) affine out, [192,256) synth step point, [256,384) running projective sum
     void *h_out = nullptr;  // pinned mirror of the affine result
     std::mutex mu;
@@ -123,6 +130,12 @@ static int create_ctx_locked(int device) {
     for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->chunk_ready[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->buf_free[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->many_start, cudaEventDisableTiming));
+    for (auto &ln : c->lanes) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&ln.d_res, 256));
+    }
     CUDA_TRY(cudaMalloc(&c->d_out, 512));
     CUDA_TRY(cudaMallocHost(&c->h_out, 256));
     g_ctx[device] = c;
@@ -183,6 +196,11 @@ extern "C" void plonkish_cuda_shutdown(void) {
         cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->scalars2.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
         cudaFree(c->batch_out.ptr);
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->buf_free[i]);
+        cudaEventDestroy(c->many_start);
+        for (auto &ln : c->lanes) {
+            cudaFree(ln.arena.ptr); cudaFree(ln.scalars.ptr); cudaFree(ln.d_res);
+            cudaEventDestroy(ln.done); cudaStreamDestroy(ln.stream);
+        }
         cudaFree(c->d_out); cudaFreeHost(c->h_out);
         cudaEventDestroy(c->last_done);
         for (int i = 0; i < 16; ++i) cudaEventDestroy(c->chunk_ready[i]);
@@ -228,7 +246,10 @@ static int make_resident(Ctx *c, const void *src, bool src_is_device, size_t n, 
         if (src_is_device) { *out_ptr = const_cast<void *>(src); *owns = false; return PLONKISH_CUDA_OK; }
         void *d = nullptr;
         CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_AFFINE_BYTES));
-        CUDA_TRY(cudaMemcpy(d, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind));
+        // stream-ordered with everything that will read it (a plain cudaMemcpy from pageable memory may
+        // return while the DMA is still in flight on the legacy stream, which c->stream does not wait for)
+        CUDA_TRY(cudaMemcpyAsync(d, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
         *out_ptr = d; *owns = true;
         return PLONKISH_CUDA_OK;
     }
@@ -238,7 +259,7 @@ static int make_resident(Ctx *c, const void *src, bool src_is_device, size_t n, 
     const void *d_src = src;
     if (!src_is_device) {
         CUDA_TRY(cudaMalloc(&staged, n * PLONKISH_CUDA_AFFINE_BYTES));
-        CUDA_TRY(cudaMemcpy(staged, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind));
+        CUDA_TRY(cudaMemcpyAsync(staged, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind, c->stream));  // ordered before the table kernels
         d_src = staged;
     }
     pk_enqueue_table_build(d_src, (u32)n, tc, tw, (xyzz *)cur, (affine *)table, c->stream);
@@ -497,7 +518,12 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
     plan0.nchunks = (u32)nchunks;
     int rc = grow(c->arena, pk_workspace_bytes(plan0));
     if (rc) return rc;
-    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    if (c->has_last) {
+        // the scalar buffer and the arena are free once the previous MSM is done; the uploads
+        // below run on the copy stream, so it waits as well
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->last_done, 0));
+    }
     MsmWorkspace ws0 = pk_carve_workspace(plan0, c->arena.ptr);
     MsmPlan last = plan0;
     for (size_t k = 0, done = 0; k < nchunks; done = cuts[k], ++k) {
@@ -616,6 +642,99 @@ extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list,
     if ((rc = mark_done(c, c->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (size_t j = 0; j < count; ++j) timer_report(n, t0);
+    return PLONKISH_CUDA_OK;
+}
+
+// ------------------------------------------------------------------ many entry
+// `count` independent MSMs, each with its own size and resident base slice — the k quotient
+// commitments of MultilinearKzg::open (pcs/multilinear/kzg.rs:291-293 through
+// pcs/multilinear.rs:72-107: sizes 2^(k-1), ..., 2, 1 against eqs[k-1..0]).  The quotients do not
+// depend on the commitments, so the caller computes them all and hands them over in one call:
+// large MSMs run one after another on the main stream (chunk-pipelined uploads), small ones are
+// spread over three more streams with their own scratch and overlap with everything else —
+// a small MSM is bound by the latency of its dozen short kernels, not by throughput.
+extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, const uint64_t *bases_handles, const size_t *ns,
+                                               size_t count, void *out_affine64_list) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (count == 0) return PLONKISH_CUDA_OK;
+    if (!scalars_list || !bases_handles || !ns || !out_affine64_list) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: null argument");
+    std::vector<BasesView> views(count);
+    int device = -1;
+    for (size_t j = 0; j < count; ++j) {
+        if (ns[j] == 0) continue;
+        if (!scalars_list[j] || !bases_handles[j]) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: MSM %zu lacks scalars or a bases handle", j);
+        int dev_j = 0;
+        int rc = view_of(bases_handles[j], ns[j], -1, views[j], &dev_j, "msm_many");
+        if (rc) return rc;
+        if (device < 0) device = dev_j;
+        if (dev_j != device) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: all base slices must live on one device");
+    }
+    if (device < 0) { memset(out_affine64_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_many: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->batch_out.ptr, 0, count * PLONKISH_CUDA_AFFINE_BYTES, c->stream));  // n == 0 entries
+    const size_t SMALL = (size_t)1 << 17;
+    const int NL = 3;
+    // size every lane's scratch once, before anything is enqueued (growing synchronises the device)
+    size_t lane_arena[NL] = {0, 0, 0}, lane_scalars[NL] = {0, 0, 0}, big_scalars = 0;
+    {
+        int next = 0;
+        for (size_t j = 0; j < count; ++j) {
+            if (ns[j] == 0) continue;
+            if (ns[j] <= SMALL) {
+                const size_t a = pk_workspace_bytes(plan_for(c, views[j], ns[j], 0));
+                lane_arena[next] = a > lane_arena[next] ? a : lane_arena[next];
+                lane_scalars[next] = ns[j] * PLONKISH_CUDA_SCALAR_BYTES > lane_scalars[next] ? ns[j] * PLONKISH_CUDA_SCALAR_BYTES : lane_scalars[next];
+                next = (next + 1) % NL;
+            } else {
+                big_scalars = ns[j] > big_scalars ? ns[j] : big_scalars;
+            }
+        }
+    }
+    for (int l = 0; l < NL; ++l) {
+        if ((rc = grow(c->lanes[l].arena, lane_arena[l])) || (rc = grow(c->lanes[l].scalars, lane_scalars[l]))) return rc;
+    }
+    if (big_scalars && (rc = grow(c->scalars, big_scalars * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    CUDA_TRY(cudaEventRecord(c->many_start, c->stream));  // lanes start after the memset / earlier work
+    bool lane_used[NL] = {false, false, false};
+    int next = 0;
+    for (size_t j = 0; j < count; ++j) {
+        if (ns[j] == 0) continue;
+        affine *d_out = (affine *)((char *)c->batch_out.ptr + j * PLONKISH_CUDA_AFFINE_BYTES);
+        if (ns[j] <= SMALL) {
+            Ctx::Lane &ln = c->lanes[next];
+            if (!lane_used[next]) CUDA_TRY(cudaStreamWaitEvent(ln.stream, c->many_start, 0));
+            lane_used[next] = true;
+            next = (next + 1) % NL;
+            CUDA_TRY(cudaMemcpyAsync(ln.scalars.ptr, scalars_list[j], ns[j] * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, ln.stream));
+            MsmPlan plan = plan_for(c, views[j], ns[j], 0);
+            MsmWorkspace w = pk_carve_workspace(plan, ln.arena.ptr);
+            w.result = (xyzz *)ln.d_res;
+            pk_enqueue_msm(plan, ln.scalars.ptr, views[j].ptr, w, nullptr, ln.stream);
+            PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, ln.stream, (const xyzz *)ln.d_res, 1u, d_out, (xyzz *)nullptr);
+        } else {
+            xyzz *res = nullptr;
+            if ((rc = enqueue_host_msm(c, scalars_list[j], views[j], ns[j], &res))) return rc;
+            PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, d_out, (xyzz *)nullptr);
+            CUDA_TRY(cudaEventRecord(c->last_done, c->stream));  // the next large MSM reuses the scalar buffer and the arena in stream order
+            c->has_last = true;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    for (int l = 0; l < NL; ++l) {
+        if (!lane_used[l]) continue;
+        CUDA_TRY(cudaEventRecord(c->lanes[l].done, c->lanes[l].stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mark_done(c, c->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (size_t j = 0; j < count; ++j) timer_report(ns[j], t0);
     return PLONKISH_CUDA_OK;
 }
 
@@ -1292,8 +1411,8 @@ static int debug_run(int device, int op, bool point, const void *a, const void *
     CUDA_TRY(cudaMalloc(&da, n * elem));
     CUDA_TRY(cudaMalloc(&db, n * elem));
     CUDA_TRY(cudaMalloc(&dout, n * elem));
-    CUDA_TRY(cudaMemcpy(da, a, n * elem, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(db, b ? b : a, n * elem, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(da, a, n * elem, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(db, b ? b : a, n * elem, cudaMemcpyHostToDevice, c->stream));
     const unsigned blocks = (unsigned)((n + 127) / 128);
     if (point) {
         PK_LAUNCH(k_debug_point, dim3(blocks), dim3(128), 0, c->stream, op, (const xyzz *)da, (const xyzz *)db, (xyzz *)dout, (u32)n);
@@ -1302,7 +1421,8 @@ static int debug_run(int device, int op, bool point, const void *a, const void *
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(out, dout, n * elem, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(out, dout, n * elem, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(da); cudaFree(db); cudaFree(dout);
     return PLONKISH_CUDA_OK;
 }

@@ -17,7 +17,7 @@ from typing import List, Sequence, Tuple
 
 import numpy as np
 
-from .msm import G1Bases, variable_base_msm, variable_base_msm_batch
+from .msm import G1Bases, variable_base_msm, variable_base_msm_batch, variable_base_msm_many
 
 FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 _MONT = 1 << 256
@@ -108,8 +108,9 @@ def open(pp: MultilinearKzgProverParam, evals: np.ndarray, point: Sequence[int])
     if k > pp.num_vars() or len(point) != k:
         raise ValueError("Invalid point / polynomial size for open")
     qs, value = quotients(fr_from_montgomery(evals), [int(x) for x in point])
-    comms = [variable_base_msm(fr_to_montgomery(q), pp.eq(i)) for i, q in enumerate(qs)]
-    return comms, value
+    # the quotients do not depend on their commitments: one call, small MSMs run concurrently
+    comms = variable_base_msm_many([fr_to_montgomery(q) for q in qs], [pp.eq(i) for i in range(k)])
+    return list(comms), value
 
 
 def commit_coeffs(powers_of_s_g1: G1Bases, coeffs: np.ndarray) -> np.ndarray:

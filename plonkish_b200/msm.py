@@ -154,6 +154,26 @@ def variable_base_msm_batch(scalars_list: Sequence, bases: "G1Bases") -> np.ndar
     return out
 
 
+def variable_base_msm_many(scalars_list: Sequence, bases_list: Sequence["G1Bases"]) -> np.ndarray:
+    """Independent MSMs of different sizes, MSM j against the resident slice bases_list[j] ->
+    [count, 8] affine points.  The quotient commitments of MultilinearKzg::open
+    (pcs/multilinear/kzg.rs:291-293) in one call: small MSMs run concurrently."""
+    arrs = [_as_u64(s, 4, "scalars") for s in scalars_list]
+    count = len(arrs)
+    assert count == len(bases_list), "scalars and bases lists differ in length"
+    out = np.zeros((count, 8), dtype=np.uint64)
+    if count == 0:
+        return out
+    for a, b in zip(arrs, bases_list):
+        assert a.shape[0] <= b.n, "more scalars than registered bases"  # msm.rs:90
+    ptrs = (ctypes.c_void_p * count)(*[a.ctypes.data if a.shape[0] else None for a in arrs])
+    handles = (ctypes.c_uint64 * count)(*[b.handle for b in bases_list])
+    ns = (ctypes.c_size_t * count)(*[a.shape[0] for a in arrs])
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_many(ptrs, handles, ns, count, out.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_many")
+    return out
+
+
 def _variable_base_msm_gather(scalars: Sequence, bases: Sequence) -> np.ndarray:
     assert len(scalars) == len(bases), "scalars and bases differ in length"  # msm.rs:90
     n = len(scalars)

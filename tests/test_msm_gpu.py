@@ -344,6 +344,23 @@ def test_batch_entry_matches_single_calls(pk, oracle):
         reg.release()
 
 
+def test_many_entry_matches_single_calls(pk, oracle):
+    # open() shape (kzg.rs:291-293): MSMs of sizes 2^(k-1)..1 against the slices eqs[k-1..0].
+    k = 19
+    full = oracle.known_dlog_bases(5, 9, 1 << (k - 1))
+    regs = [pk.G1Bases(full[: 1 << i]) for i in range(k)]
+    scal = [oracle.random_scalars(1 << i, 700 + i) for i in range(k)]
+    got = pk.variable_base_msm_many(scal, regs)
+    for i in range(k):
+        assert got[i].tobytes() == oracle.known_dlog_answer(5, 9, scal[i]).tobytes(), i
+    # order, empty entries and repeated slices
+    got = pk.variable_base_msm_many([scal[3], np.zeros((0, 4), np.uint64), scal[3], scal[10]], [regs[3], regs[0], regs[3], regs[10]])
+    assert got[0].tobytes() == got[2].tobytes() == oracle.known_dlog_answer(5, 9, scal[3]).tobytes()
+    assert not got[1].any() and got[3].tobytes() == oracle.known_dlog_answer(5, 9, scal[10]).tobytes()
+    for r in regs:
+        r.release()
+
+
 def test_linearity(pk, oracle):
     # MSM(s, B) + MSM(t, B) == MSM(s + t, B), checked through the oracle's field/curve ops.
     n = 5000
