@@ -16,6 +16,7 @@ extern "C" {
     fn plonkish_cuda_msm_bn254_g1(scalars: *const c_void, bases: *const c_void, handle: u64, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_gather(scalars: *const *const c_void, bases: *const *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_batch(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1_many(scalars_list: *const *const c_void, handles: *const u64, ns: *const usize, count: usize, out: *mut c_void) -> c_int;
 }
 
 static INIT: Once = Once::new();
@@ -127,6 +128,33 @@ pub fn batch_commit_bn254(polys: &[&[Fr]], bases: &[G1Affine]) -> Vec<G1Affine> 
     check(
         unsafe { plonkish_cuda_msm_bn254_g1_batch(ptrs.as_ptr(), polys.len(), handle, n, out.as_mut_ptr() as *mut c_void) },
         "plonkish_cuda_msm_bn254_g1_batch",
+    );
+    out.into_iter().map(|b| unsafe { std::mem::transmute::<[u8; 64], G1Affine>(b) }).collect()
+}
+
+/// The quotient commitments of `MultilinearKzg::open` (pcs/multilinear/kzg.rs:291-293) in one call:
+/// `quotients[i]` (2^i scalars) is committed against `eqs[i]`.  The quotients do not depend on the
+/// commitments, so `open` collects them first (pcs/multilinear.rs:72-107 with a collecting closure)
+/// and commits afterwards; small MSMs run concurrently on the GPU.
+pub fn commit_quotients_bn254(quotients: &[Vec<Fr>], eqs: &[Vec<G1Affine>]) -> Vec<G1Affine> {
+    init();
+    assert!(quotients.len() <= eqs.len());
+    let handles: Vec<u64> = quotients.iter().zip(eqs).map(|(q, e)| {
+        assert!(q.len() <= e.len());
+        let mut guard = BASES.lock().unwrap();
+        let map = guard.get_or_insert_with(HashMap::new);
+        *map.entry((e.as_ptr() as usize, e.len())).or_insert_with(|| {
+            let mut h = 0u64;
+            check(unsafe { plonkish_cuda_bases_register(0, e.as_ptr() as *const c_void, e.len(), &mut h) }, "plonkish_cuda_bases_register");
+            h
+        })
+    }).collect();
+    let ptrs: Vec<*const c_void> = quotients.iter().map(|q| q.as_ptr() as *const c_void).collect();
+    let ns: Vec<usize> = quotients.iter().map(|q| q.len()).collect();
+    let mut out = vec![[0u8; 64]; quotients.len()];
+    check(
+        unsafe { plonkish_cuda_msm_bn254_g1_many(ptrs.as_ptr(), handles.as_ptr(), ns.as_ptr(), quotients.len(), out.as_mut_ptr() as *mut c_void) },
+        "plonkish_cuda_msm_bn254_g1_many",
     );
     out.into_iter().map(|b| unsafe { std::mem::transmute::<[u8; 64], G1Affine>(b) }).collect()
 }

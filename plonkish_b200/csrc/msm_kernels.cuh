@@ -4,22 +4,28 @@
 // (variable_base_msm + variable_base_msm_serial).  The reference walks unsigned
 // c-bit windows high->low per CPU thread and does a random read-modify-write on
 // a bucket array per (point, window) (msm.rs:168-173).  Here the same sum is
-// reorganised for HBM and the integer pipe:
+// reorganised for HBM and the integer pipe, in two bucket layouts (MsmPlan::mode):
+//
+//   mode 0  plain bases: one bucket set per window (c <= 16), window weights 2^(c*w)
+//           applied at the end (the doubling chain of msm.rs:162-164).
+//   mode 1  resident bases expanded once into T[w][i] = 2^(c*w) * P_i: every window feeds
+//           ONE bucket set (c up to 22), no doubling chain, fewer windows per point.
 //
 //   K1 decompose   Fr Montgomery -> canonical (to_repr, msm.rs:153), negate if
-//                  > (r-1)/2, signed base-2^c digits; per-tile histogram of the
-//                  high bucket bits in shared memory.            [HBM bound]
-//   K2 scan/scatter/sort  counting sort of (bucket, point) pairs: tile offsets ->
-//                  scatter into (window, high-bits) bins -> per-bin sort on the low
-//                  bits; output is one dense array ordered by (window, bucket) and
-//                  bucket_start[].                               [HBM bound]
+//                  > (r-1)/2, signed base-2^c digits; histogram of the high bucket bits
+//                  in shared memory.                                  [HBM bound]
+//   K2 sort        two-level counting sort of (bucket, point) pairs on the high, then the
+//                  low bucket bits.  mode 1: ranks in shared memory, tiles staged sorted,
+//                  one global atomic per (block, digit) run, coalesced run writes, bins cut
+//                  into slices shared by several blocks.  Output: one dense array ordered by
+//                  bucket and bucket_start[].                          [HBM bound]
 //   K3 accumulate  every thread owns a fixed-length run of the sorted array (skew
 //                  proof), sums its points with XYZZ mixed additions, stores the
-//                  buckets that lie wholly inside the run and hands the two partial
-//                  ends to a warp-level segmented reduction by shuffles; warps emit
-//                  two items each to the next level.             [IMAD bound]
-//   K4 bucket reduce   sum_k k*B_k per window by chunked running sums.
-//   K5 window combine  2^(c*w) weights, final sum, XYZZ -> affine.
+//                  buckets that lie wholly inside the run and leaves its two open ends as
+//                  items; warp-level segmented reductions by shuffles fold the items,
+//                  16-128x fewer per level.                           [IMAD bound]
+//   K4 bucket reduce   sum_k k*B_k by chunked running sums (msm.rs:175-179 per chunk).
+//   K5 window combine  2^(c*w) weights (mode 0), final sum, XYZZ -> affine.
 //
 // This header is also compiled by g++ against tests/emul/cuda_emul.h so the
 // kernels' logic runs in the CPU test suite; the product only runs the nvcc build.
@@ -1065,7 +1071,7 @@ PK_HD xyzz xyzz_mul_small(const xyzz &pnt, u32 k) {
 // grid (red_blocks, W), block 256.  Thread j of window w owns buckets
 // [j*rb, (j+1)*rb): sum_i (j*rb + i + 1) * B_i = acc + (j*rb) * run, where run is
 // the plain sum and acc the running-sum total (msm.rs:175-179 restated per chunk).
-__global__ void __launch_bounds__(256, 2) k_bucket_reduce(const xyzz *__restrict__ bucket_sum, const u32 *__restrict__ bucket_start,
+__global__ void __launch_bounds__(256, 2) k_bucket_reduce(const xyzz *__restrict__ bucket_sum,
                                                        MsmPlan p, xyzz *__restrict__ block_out) {
     __shared__ xyzz warp_part[8];
     const u32 w = blockIdx.y;
@@ -1245,7 +1251,7 @@ inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void
 // (plus *prev if given).
 inline void pk_enqueue_reduce(const MsmPlan &p, const MsmWorkspace &ws, const xyzz *prev, pk_stream_t stream,
                               const StageMarks *marks = nullptr) {
-    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.ngroups), dim3(256), 0, stream, ws.bucket_sum, ws.bucket_start, p, ws.block_out);
+    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.ngroups), dim3(256), 0, stream, ws.bucket_sum, p, ws.block_out);
     PK_MARK(marks, 7, stream);
     PK_LAUNCH(k_window_weight, dim3(p.ngroups), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
     PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.ngroups, prev, ws.result);
