@@ -99,7 +99,55 @@ int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_mont32_list, siz
 int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_mont32_list, const uint64_t *bases_handles, const size_t *ns,
                                     size_t count, void *out_affine64_list);
 
-/* Same for the reference's non-contiguous callers, which pass iterators of
+/* ---- callers either side of the MSM ----------------------------
+ * Resident scalars: a polynomial's 2^k evaluations (n x 32 B Montgomery Fr) kept in HBM between
+ * its commit and its opening.  The reference re-reads poly.evals() from host memory in every
+ * caller (pcs/multilinear/kzg.rs:255, 291); here they cross PCIe once. */
+int plonkish_cuda_scalars_register(int device, const void *scalars_mont32, size_t n, uint64_t *handle);
+int plonkish_cuda_scalars_release(uint64_t handle);
+/* Copy scalars [offset, offset + n) of a resident polynomial back to the host. */
+int plonkish_cuda_scalars_read(uint64_t handle, size_t offset, size_t n, void *out_mont32);
+/* Copy bases [offset, offset + n) of a registered (unsharded) slice back to the host —
+ * how a device-built SRS (kzg_setup_eqs) is serialised (pcs/multilinear/kzg.rs:55-77). */
+int plonkish_cuda_bases_read(uint64_t handle, size_t offset, size_t n, void *out_affine64);
+
+/* MultilinearKzg::commit on a resident polynomial (pcs/multilinear/kzg.rs:252-257):
+ * variable_base_msm(first n resident scalars, first n bases of the slice) -> affine. */
+int plonkish_cuda_msm_bn254_g1_resident(uint64_t scalars_handle, uint64_t bases_handle, size_t n, void *out_affine64);
+/* plonkish_cuda_msm_bn254_g1_batch that also keeps every polynomial resident:
+ * scalars_handles_out[j] owns a device copy of scalars_mont32_list[j] (release with
+ * scalars_release).  For the witness / permutation polynomials HyperPlonk commits at
+ * backend/hyperplonk.rs:201,251 and opens at :287. */
+int plonkish_cuda_msm_bn254_g1_batch_keep(const void *const *scalars_mont32_list, size_t count, uint64_t bases_handle, size_t n,
+                                          void *out_affine64_list, uint64_t *scalars_handles_out);
+/* New resident polynomial sum_i coeffs[i] * poly_i over the first n evaluations of `count`
+ * resident polynomials: the g_prime merge of pcs/multilinear.rs:203-213. */
+int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const void *coeffs_mont32, size_t count, size_t n,
+                                        uint64_t *out_handle);
+/* MultilinearKzg::open on a resident polynomial of 2^num_vars evaluations
+ * (pcs/multilinear/kzg.rs:276-302): `quotients` (pcs/multilinear.rs:72-107) runs in HBM and
+ * the num_vars quotient MSMs (kzg.rs:291-293) read their scalars from there.  eq_handles[i] =
+ * the registered slice pp.eq(i) (2^i bases), i < num_vars.  out_comms_affine64 receives
+ * num_vars x 64 B in the order kzg.rs:299 writes them to the transcript; out_eval_mont32
+ * receives f(point), the `remainder` of kzg.rs:295. */
+int plonkish_cuda_kzg_open_bn254(uint64_t scalars_handle, const uint64_t *eq_handles, const void *point_mont32, size_t num_vars,
+                                 void *out_comms_affine64, void *out_eval_mont32);
+
+/* fixed_base_msm (util/arithmetic/msm.rs:67-81) over the window table of one base (msm.rs:16-31)
+ * followed by batch_normalize (pcs/multilinear/kzg.rs:204-207, pcs/univariate/kzg.rs:196-199):
+ * out_affine64_list[i] = scalars[i] * base.  Host in, host out; the table lives on the device
+ * for the duration of the call (signed 16-bit windows, 32 MiB). */
+int plonkish_cuda_fixed_base_msm_bn254_g1(int device, const void *base_affine64, const void *scalars_mont32, size_t n,
+                                          void *out_affine64_list);
+/* The prover half of MultilinearKzg::setup (pcs/multilinear/kzg.rs:167-212) on the device:
+ * eq tables from ss (num_vars Montgomery Fr, kzg.rs:174-193), times g1 by fixed-base MSM and
+ * normalised (:195-208), every slice eqs[k] (2^k bases, k = 0..num_vars) registered as resident
+ * bases.  handles_out receives num_vars + 1 handles (release each with bases_release; read
+ * back with bases_read).  The SRS never exists in host memory. */
+int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affine64, const void *ss_mont32, size_t num_vars,
+                                      uint64_t *handles_out);
+
+/* Same as plonkish_cuda_msm_bn254_g1 for the reference's non-contiguous callers, which pass iterators of
  * references (chain![..] at pcs/univariate/kzg.rs:346,408; .map(|c| &c.0) at
  * pcs/multilinear/kzg.rs:145): gathers the n scalars and n bases into staging first. */
 int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs, const void *const *base_ptrs, size_t n,

@@ -563,3 +563,133 @@ void oracle_known_dlog_answer(const uint64_t a[4], const uint64_t d[4], const of
     oracle_g1_scalar_mul(&g, k, &rj);
     oracle_g1_to_affine(&rj, out);
 }
+
+/* ------------------------------------------- callers either side of the MSM */
+
+/* pcs/multilinear.rs:72-107.  quotients[] holds 2^num_vars entries; q_i (2^i values,
+ * committed against eqs[i] at kzg.rs:291-293) sits at offset 2^i, entry 0 is unused. */
+void oracle_quotients(const ofe_t *evals, const ofe_t *point, size_t num_vars, ofe_t *quotients, ofe_t *eval_out) {
+    const size_t n = (size_t)1 << num_vars;
+    ofe_t *remainder = (ofe_t *)malloc(sizeof(ofe_t) * n);
+    memcpy(remainder, evals, sizeof(ofe_t) * n);
+    memset(&quotients[0], 0, sizeof(ofe_t));
+    for (size_t i = num_vars; i-- > 0;) {            /* .zip(0..num_vars).rev()           (:80-83) */
+        const size_t half = (size_t)1 << i;
+        ofe_t *q = quotients + half;
+        for (size_t j = 0; j < half; ++j) {
+            fe_sub(FR, remainder[half + j].l, remainder[j].l, q[j].l);      /* *q = *r_hi - r_lo   (:90-91) */
+            ofe_t t;
+            mont_mul(FR, q[j].l, point[i].l, t.l);                          /* (r_hi - r_lo) * x_i (:94-95) */
+            fe_add(FR, remainder[j].l, t.l, remainder[j].l);
+        }
+    }
+    *eval_out = remainder[0];
+    free(remainder);
+}
+
+/* pcs/multilinear.rs:203-213 ("g_prime"): sum_i coeffs[i] * polys[i], element-wise. */
+void oracle_fr_linear_combination(const ofe_t *const *polys, const ofe_t *coeffs, size_t count, size_t n, ofe_t *out) {
+    for (size_t j = 0; j < n; ++j) {
+        ofe_t acc, t;
+        memset(&acc, 0, sizeof(acc));
+        for (size_t i = 0; i < count; ++i) {
+            mont_mul(FR, coeffs[i].l, polys[i][j].l, t.l);
+            fe_add(FR, acc.l, t.l, acc.l);
+        }
+        out[j] = acc;
+    }
+}
+
+/* pcs/multilinear/kzg.rs:174-193: eqs[0] = [1]; eqs[k+1] = [e - s_k*e for e in eqs[k]] ++ [s_k*e ...].
+ * out holds 2^(num_vars+1) - 1 scalars, slice k at offset 2^k - 1 (the flat_map order of :199). */
+void oracle_kzg_eq_scalars(const ofe_t *ss, size_t num_vars, ofe_t *out) {
+    memcpy(out[0].l, FR->r, 32);
+    for (size_t k = 0; k < num_vars; ++k) {
+        const size_t len = (size_t)1 << k;
+        const ofe_t *last = out + (len - 1);
+        ofe_t *lo = out + (2 * len - 1), *hi = lo + len;
+        for (size_t j = 0; j < len; ++j) {
+            mont_mul(FR, ss[k].l, last[j].l, hi[j].l);        /* *eval_hi = *s_i * last_eval        (:186) */
+            fe_sub(FR, last[j].l, hi[j].l, lo[j].l);          /* *eval_lo = *last_eval - eval_hi    (:190) */
+        }
+    }
+}
+
+/* msm.rs:16-31 window_table + :50-81 fixed_base_msm, then batch_normalize (kzg.rs:204-207). */
+typedef struct {
+    size_t window_size, num_windows, start, count;
+    const og1_affine_t *table; /* num_windows rows of (2^window_size - 1) points */
+    const ofe_t *scalars;
+    og1_affine_t *out;
+} fixed_task_t;
+
+static void *fixed_task_run(void *arg) {
+    fixed_task_t *t = (fixed_task_t *)arg;
+    const size_t row = ((size_t)1 << t->window_size) - 1, mask = row;
+    const size_t BATCH = 1024;
+    og1_jac_t *buf = (og1_jac_t *)malloc(sizeof(og1_jac_t) * BATCH);
+    for (size_t done = 0; done < t->count;) {
+        const size_t m = t->count - done < BATCH ? t->count - done : BATCH;
+        for (size_t i = 0; i < m; ++i) {
+            uint64_t c[4];
+            uint8_t repr[32];
+            oracle_fe_to_canonical(1, &t->scalars[t->start + done + i], c);
+            memcpy(repr, c, 32);
+            og1_jac_t acc;
+            jac_set_identity(&acc);
+            for (size_t w = 0; w < t->num_windows; ++w) {                     /* windowed_scalar_mul (:50-65) */
+                const size_t d = oracle_windowed_scalar(t->window_size, mask, w, repr);
+                if (d > 0) oracle_g1_add_mixed(&acc, &t->table[w * row + d - 1], &acc);
+            }
+            buf[i] = acc;
+        }
+        batch_to_affine(buf, m, t->out + t->start + done);
+        done += m;
+    }
+    free(buf);
+    return NULL;
+}
+
+void oracle_fixed_base_msm(const og1_affine_t *base, size_t window_size, const ofe_t *scalars, size_t n, int num_threads,
+                           og1_affine_t *out) {
+    if (n == 0) return;
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > n) num_threads = (int)n;
+    const size_t scalar_size = 254;                                           /* field_size::<Fr>() (arithmetic.rs:202-205) */
+    const size_t num_windows = (scalar_size + window_size - 1) / window_size;
+    const size_t row = ((size_t)1 << window_size) - 1;
+    og1_affine_t *table = (og1_affine_t *)malloc(sizeof(og1_affine_t) * num_windows * row);
+    og1_jac_t *tmp = (og1_jac_t *)malloc(sizeof(og1_jac_t) * row);
+    og1_jac_t offset;
+    oracle_g1_from_affine(base, &offset);
+    for (size_t w = 0; w < num_windows; ++w) {                                /* window_table (:16-31) */
+        og1_affine_t off_aff;
+        oracle_g1_to_affine(&offset, &off_aff);
+        og1_jac_t acc = offset;
+        for (size_t v = 0; v < row; ++v) {
+            tmp[v] = acc;
+            oracle_g1_add_mixed(&acc, &off_aff, &acc);
+        }
+        batch_to_affine(tmp, row, table + w * row);
+        for (size_t b = 0; b < window_size; ++b) oracle_g1_double(&offset, &offset);
+    }
+    free(tmp);
+    fixed_task_t *tasks = (fixed_task_t *)calloc(num_threads, sizeof(fixed_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+    const size_t chunk = (n + num_threads - 1) / num_threads;
+    for (int t = 0; t < num_threads; ++t) {
+        const size_t start = (size_t)t * chunk;
+        tasks[t].window_size = window_size;
+        tasks[t].num_windows = num_windows;
+        tasks[t].start = start;
+        tasks[t].count = start >= n ? 0 : (start + chunk <= n ? chunk : n - start);
+        tasks[t].table = table;
+        tasks[t].scalars = scalars;
+        tasks[t].out = out;
+        pthread_create(&threads[t], NULL, fixed_task_run, &tasks[t]);
+    }
+    for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+    free(threads);
+    free(tasks);
+    free(table);
+}

@@ -21,6 +21,9 @@
  *   util/arithmetic/msm.rs:117-181  variable_base_msm_serial + CurveAcc
  *   util/parallel.rs:9-25           parallelize_iter (one task per chunk)
  *   util/transcript.rs:216-229      write_commitment byte encoding
+ *   util/arithmetic/msm.rs:16-31,50-81  window_table, fixed_base_msm
+ *   pcs/multilinear.rs:72-107, 203-213  quotients, g_prime merge
+ *   pcs/multilinear/kzg.rs:174-208      eq tables of the SRS
  * The field / curve arithmetic the reference gets from the un-vendored
  * third-party crate halo2_curves 0.3.3 (plonkish_backend/Cargo.toml:7, patched
  * at Cargo.toml:9-11, no lockfile) is restated from the published BN254
@@ -86,6 +89,18 @@ void oracle_known_dlog_bases(const uint64_t a[4], const uint64_t d[4], size_t n,
                              int num_threads, og1_affine_t *out);
 void oracle_known_dlog_answer(const uint64_t a[4], const uint64_t d[4],
                               const ofe_t *scalars, size_t n, og1_affine_t *out);
+
+/* ---- the callers either side of the MSM ---- */
+/* pcs/multilinear.rs:72-107: quotients[] has 2^num_vars entries, q_i (2^i values) at offset 2^i. */
+void oracle_quotients(const ofe_t *evals, const ofe_t *point, size_t num_vars, ofe_t *quotients, ofe_t *eval_out);
+/* pcs/multilinear.rs:203-213 (g_prime): out[j] = sum_i coeffs[i] * polys[i][j]. */
+void oracle_fr_linear_combination(const ofe_t *const *polys, const ofe_t *coeffs, size_t count, size_t n, ofe_t *out);
+/* pcs/multilinear/kzg.rs:174-193: the eq tables as scalars, slice k (2^k values) at offset 2^k - 1. */
+void oracle_kzg_eq_scalars(const ofe_t *ss, size_t num_vars, ofe_t *out);
+/* msm.rs:16-31 (window_table), :50-81 (fixed_base_msm) and batch_normalize (kzg.rs:204-207):
+ * out[i] = scalars[i] * base, affine. */
+void oracle_fixed_base_msm(const og1_affine_t *base, size_t window_size, const ofe_t *scalars, size_t n, int num_threads,
+                           og1_affine_t *out);
 
 #ifdef __cplusplus
 }

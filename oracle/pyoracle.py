@@ -62,6 +62,10 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_msm_naive.argtypes = [vp, vp, sz, vp]
         _lib.oracle_known_dlog_bases.argtypes = [vp, vp, sz, ci, vp]
         _lib.oracle_known_dlog_answer.argtypes = [vp, vp, vp, sz, vp]
+        _lib.oracle_quotients.argtypes = [vp, vp, sz, vp, vp]
+        _lib.oracle_fr_linear_combination.argtypes = [vp, vp, sz, sz, vp]
+        _lib.oracle_kzg_eq_scalars.argtypes = [vp, sz, vp]
+        _lib.oracle_fixed_base_msm.argtypes = [vp, sz, vp, sz, ci, vp]
     return _lib
 
 
@@ -192,4 +196,56 @@ def random_scalars(n: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     out = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
     out[:, 3] = rng.integers(0, 0x30644E72E131A029, size=n, dtype=np.uint64)
+    return out
+
+
+def window_size(num_scalars: int) -> int:
+    return int(lib().oracle_window_size(num_scalars))
+
+
+def quotients(evals, point):
+    """pcs/multilinear.rs:72-107: returns ([q_0, ..., q_{k-1}] with q_i of 2^i Montgomery
+    scalars, f(point) as Montgomery limbs)."""
+    evals = _u64(evals).reshape(-1, 4)
+    point = _u64(point).reshape(-1, 4)
+    k = point.shape[0]
+    assert evals.shape[0] == 1 << k
+    q = np.zeros((1 << k, 4), dtype=np.uint64)
+    value = np.zeros(4, dtype=np.uint64)
+    lib().oracle_quotients(_ptr(evals), _ptr(point), k, _ptr(q), _ptr(value))
+    return [q[1 << i: 2 << i].copy() for i in range(k)], value
+
+
+def fr_linear_combination(polys, coeffs) -> np.ndarray:
+    """pcs/multilinear.rs:203-213: sum_i coeffs[i] * polys[i]."""
+    polys = [_u64(p).reshape(-1, 4) for p in polys]
+    coeffs = _u64(coeffs).reshape(-1, 4)
+    n = polys[0].shape[0]
+    assert all(p.shape[0] == n for p in polys) and coeffs.shape[0] == len(polys)
+    ptrs = (ctypes.c_void_p * len(polys))(*[p.ctypes.data for p in polys])
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().oracle_fr_linear_combination(ctypes.cast(ptrs, ctypes.c_void_p), _ptr(coeffs), len(polys), n, _ptr(out))
+    return out
+
+
+def kzg_eq_scalars(ss):
+    """pcs/multilinear/kzg.rs:174-193: [eqs[0], ..., eqs[num_vars]] as Montgomery scalars."""
+    ss = _u64(ss).reshape(-1, 4)
+    k = ss.shape[0]
+    out = np.zeros(((2 << k) - 1, 4), dtype=np.uint64)
+    lib().oracle_kzg_eq_scalars(_ptr(ss), k, _ptr(out))
+    return [out[(1 << i) - 1: (2 << i) - 1].copy() for i in range(k + 1)]
+
+
+def fixed_base_msm(base, scalars, window: int | None = None, num_threads: int | None = None) -> np.ndarray:
+    """msm.rs:16-31, 50-81 + batch_normalize: out[i] = scalars[i] * base (affine, [n, 8])."""
+    base = _u64(base).reshape(8)
+    scalars = _u64(scalars).reshape(-1, 4)
+    n = scalars.shape[0]
+    if window is None:
+        window = window_size(n)
+    if num_threads is None:
+        num_threads = host_threads()
+    out = np.zeros((n, 8), dtype=np.uint64)
+    lib().oracle_fixed_base_msm(_ptr(base), int(window), _ptr(scalars), n, int(num_threads), _ptr(out))
     return out

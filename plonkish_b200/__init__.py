@@ -7,7 +7,13 @@ interface (msm.py, kzg.py, distributed.py).
 from ._lib import PlonkishCudaError, LIB_PATH  # noqa: F401
 from .msm import (  # noqa: F401
     G1Bases,
+    ResidentScalars,
     ShardedG1Bases,
+    variable_base_msm_batch_keep,
+    fr_linear_combination,
+    kzg_open_resident,
+    fixed_base_msm,
+    kzg_setup_eqs,
     variable_base_msm,
     variable_base_msm_batch,
     variable_base_msm_many,

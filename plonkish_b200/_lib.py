@@ -25,6 +25,16 @@ EXPORTS = (
     "plonkish_cuda_msm_bn254_g1",
     "plonkish_cuda_msm_bn254_g1_batch",
     "plonkish_cuda_msm_bn254_g1_many",
+    "plonkish_cuda_scalars_register",
+    "plonkish_cuda_scalars_release",
+    "plonkish_cuda_scalars_read",
+    "plonkish_cuda_bases_read",
+    "plonkish_cuda_msm_bn254_g1_resident",
+    "plonkish_cuda_msm_bn254_g1_batch_keep",
+    "plonkish_cuda_fr_linear_combination",
+    "plonkish_cuda_kzg_open_bn254",
+    "plonkish_cuda_fixed_base_msm_bn254_g1",
+    "plonkish_cuda_kzg_setup_eqs_bn254",
     "plonkish_cuda_msm_bn254_g1_gather",
     "plonkish_cuda_bases_register_sharded",
     "plonkish_cuda_msm_bn254_g1_multi",
@@ -79,6 +89,16 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_many.argtypes = [vp, vp, vp, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
+    lib.plonkish_cuda_scalars_register.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_scalars_release.argtypes = [u64]
+    lib.plonkish_cuda_scalars_read.argtypes = [u64, sz, sz, vp]
+    lib.plonkish_cuda_bases_read.argtypes = [u64, sz, sz, vp]
+    lib.plonkish_cuda_msm_bn254_g1_resident.argtypes = [u64, u64, sz, vp]
+    lib.plonkish_cuda_msm_bn254_g1_batch_keep.argtypes = [vp, sz, u64, sz, vp, vp]
+    lib.plonkish_cuda_fr_linear_combination.argtypes = [vp, vp, sz, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_kzg_open_bn254.argtypes = [u64, vp, vp, sz, vp, vp]
+    lib.plonkish_cuda_fixed_base_msm_bn254_g1.argtypes = [ci, vp, vp, sz, vp]
+    lib.plonkish_cuda_kzg_setup_eqs_bn254.argtypes = [ci, vp, vp, sz, vp]
     lib.plonkish_cuda_bases_register_sharded.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1_multi.argtypes = [ci, vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_device.argtypes = [ci, vp, vp, sz, u32, vp, vp, vp]

@@ -26,6 +26,7 @@ static std::atomic<unsigned long long> g_launches{0};
 #define PK_COUNT_LAUNCH() (pk::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 #include "msm_kernels.cuh"
+#include "poly_kernels.cuh"
 
 using namespace pk;
 
@@ -65,7 +66,7 @@ struct Ctx {
     cudaEvent_t chunk_ready[16] = {};
     cudaEvent_t last_done = nullptr;  // end of the last enqueued MSM: orders arena reuse across streams
     bool has_last = false;
-    DeviceBuffer arena, scalars, scalars2, bases_tmp, partials, batch_out;
+    DeviceBuffer arena, scalars, scalars2, bases_tmp, partials, batch_out, open_buf;
     cudaEvent_t buf_free[2] = {};         // batch path: scalar buffer b may be overwritten again
     cudaEvent_t many_start = nullptr;     // many path: side lanes start after this point of the main stream
     struct Lane {                         // extra streams with their own scratch: small independent MSMs run side by side
@@ -74,7 +75,7 @@ struct Ctx {
         DeviceBuffer arena, scalars;
         void *d_res = nullptr;            // 128-byte projective result slot
     } lanes[3];
-    void *d_out = nullptr;  // [0,64) affine out, [192,256) synth step point, [256,384) running projective sum
+    void *d_out = nullptr;  // [0,64) affine out, [192,256) synth step point, [256,384) running projective sum, [384,448) fixed base
     void *h_out = nullptr;  // pinned mirror of the affine result
     std::mutex mu;
 };
@@ -136,7 +137,7 @@ static int create_ctx_locked(int device) {
         CUDA_TRY(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&ln.d_res, 256));
     }
-    CUDA_TRY(cudaMalloc(&c->d_out, 512));
+    CUDA_TRY(cudaMalloc(&c->d_out, 512));  // see the slot map at Ctx::d_out
     CUDA_TRY(cudaMallocHost(&c->h_out, 256));
     g_ctx[device] = c;
     return PLONKISH_CUDA_OK;
@@ -179,6 +180,7 @@ extern "C" int plonkish_cuda_device_count(void) {
     return (int)g_ctx.size();
 }
 
+static void release_all_scalars();
 extern "C" void plonkish_cuda_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &kv : g_bases) {
@@ -189,12 +191,13 @@ extern "C" void plonkish_cuda_shutdown(void) {
         }
     }
     g_bases.clear();
+    release_all_scalars();
     for (Ctx *c : g_ctx) {
         if (!c) continue;
         cudaSetDevice(c->dev);
         cudaDeviceSynchronize();
         cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->scalars2.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
-        cudaFree(c->batch_out.ptr);
+        cudaFree(c->batch_out.ptr); cudaFree(c->open_buf.ptr);
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->buf_free[i]);
         cudaEventDestroy(c->many_start);
         for (auto &ln : c->lanes) {
@@ -599,8 +602,11 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
 // polynomial, all against pp.eq(num_vars)).  The reference runs them one after another; here
 // the copy stream uploads the scalars of MSM j+1 (two device buffers) while the compute stream
 // works on MSM j, and the host waits once at the end.
-extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list, size_t count, uint64_t bases_handle, size_t n,
-                                                void *out_affine64_list) {
+static uint64_t publish_scalars(int dev, void *d_ptr, size_t n);
+
+// keep != nullptr: every polynomial's scalars stay resident under keep[j] (its own allocation)
+// instead of passing through the two staging buffers.
+static int batch_impl(const void *const *scalars_list, size_t count, uint64_t bases_handle, size_t n, void *out_affine64_list, uint64_t *keep) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!out_affine64_list || (count && !scalars_list)) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch: null argument");
     if (!bases_handle) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch: a registered bases handle is required");
@@ -618,7 +624,17 @@ extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list,
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
     const size_t bytes = n * PLONKISH_CUDA_SCALAR_BYTES;
-    if ((rc = grow(c->scalars, bytes)) || (rc = grow(c->scalars2, bytes))) return rc;
+    std::vector<void *> kept(count, nullptr);
+    if (keep) {
+        for (size_t j = 0; j < count; ++j) {
+            if (cudaMalloc(&kept[j], bytes) != cudaSuccess) {
+                for (size_t i = 0; i < j; ++i) cudaFree(kept[i]);
+                return fail(PLONKISH_CUDA_E_CUDA, "msm_batch: cannot keep %zu x %zu bytes of scalars resident", count, bytes);
+            }
+        }
+    } else if ((rc = grow(c->scalars, bytes)) || (rc = grow(c->scalars2, bytes))) {
+        return rc;
+    }
     if ((rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES))) return rc;
     MsmPlan plan = plan_for(c, view, n, 0);
     if ((rc = grow(c->arena, pk_workspace_bytes(plan)))) return rc;
@@ -626,13 +642,15 @@ extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list,
     MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
     ws.result = (xyzz *)((char *)c->d_out + 256);
     void *bufs[2] = {c->scalars.ptr, c->scalars2.ptr};
+    if (c->has_last && !keep) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->last_done, 0));  // staging buffers may still be read
     for (size_t j = 0; j < count; ++j) {
         const int b = (int)(j & 1);
-        if (j >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->buf_free[b], 0));  // MSM j-2 has consumed this buffer
-        CUDA_TRY(cudaMemcpyAsync(bufs[b], scalars_list[j], bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        void *dst = keep ? kept[j] : bufs[b];
+        if (j >= 2 && !keep) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->buf_free[b], 0));  // MSM j-2 has consumed this buffer
+        CUDA_TRY(cudaMemcpyAsync(dst, scalars_list[j], bytes, cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->chunk_ready[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
-        pk_enqueue_msm(plan, bufs[b], view.ptr, ws, nullptr, c->stream);
+        pk_enqueue_msm(plan, dst, view.ptr, ws, nullptr, c->stream);
         CUDA_TRY(cudaEventRecord(c->buf_free[b], c->stream));  // scalars are dead after the decompose; recorded after the whole MSM for simplicity
         PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, ws.result, 1u,
                   (affine *)((char *)c->batch_out.ptr + j * PLONKISH_CUDA_AFFINE_BYTES), (xyzz *)nullptr);
@@ -641,8 +659,24 @@ extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list,
     CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
     if ((rc = mark_done(c, c->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (keep)
+        for (size_t j = 0; j < count; ++j) keep[j] = publish_scalars(c->dev, kept[j], n);
     for (size_t j = 0; j < count; ++j) timer_report(n, t0);
     return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list, size_t count, uint64_t bases_handle, size_t n,
+                                                void *out_affine64_list) {
+    return batch_impl(scalars_list, count, bases_handle, n, out_affine64_list, nullptr);
+}
+
+// batch_commit that leaves each polynomial's evaluations resident for the later open
+// (backend/hyperplonk.rs:201,251 commit the witness / permutation polynomials that :287 opens).
+extern "C" int plonkish_cuda_msm_bn254_g1_batch_keep(const void *const *scalars_list, size_t count, uint64_t bases_handle, size_t n,
+                                                     void *out_affine64_list, uint64_t *scalars_handles_out) {
+    if (!scalars_handles_out) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch_keep: null handle output");
+    if (n == 0) return fail(PLONKISH_CUDA_E_INVALID, "msm_batch_keep: n == 0");
+    return batch_impl(scalars_list, count, bases_handle, n, out_affine64_list, scalars_handles_out);
 }
 
 // ------------------------------------------------------------------ many entry
@@ -653,30 +687,18 @@ extern "C" int plonkish_cuda_msm_bn254_g1_batch(const void *const *scalars_list,
 // large MSMs run one after another on the main stream (chunk-pipelined uploads), small ones are
 // spread over three more streams with their own scratch and overlap with everything else —
 // a small MSM is bound by the latency of its dozen short kernels, not by throughput.
-extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, const uint64_t *bases_handles, const size_t *ns,
-                                               size_t count, void *out_affine64_list) {
-    const auto t0 = std::chrono::steady_clock::now();
-    if (count == 0) return PLONKISH_CUDA_OK;
-    if (!scalars_list || !bases_handles || !ns || !out_affine64_list) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: null argument");
-    std::vector<BasesView> views(count);
-    int device = -1;
-    for (size_t j = 0; j < count; ++j) {
-        if (ns[j] == 0) continue;
-        if (!scalars_list[j] || !bases_handles[j]) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: MSM %zu lacks scalars or a bases handle", j);
-        int dev_j = 0;
-        int rc = view_of(bases_handles[j], ns[j], -1, views[j], &dev_j, "msm_many");
-        if (rc) return rc;
-        if (device < 0) device = dev_j;
-        if (dev_j != device) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: all base slices must live on one device");
-    }
-    if (device < 0) { memset(out_affine64_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
-    Ctx *c = ctx_for(device);
-    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_many: device %d not initialised", device);
-    std::lock_guard<std::mutex> lk(c->mu);
-    CUDA_TRY(cudaSetDevice(c->dev));
-    int rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->batch_out.ptr, 0, count * PLONKISH_CUDA_AFFINE_BYTES, c->stream));  // n == 0 entries
+struct ManyJob {
+    const void *scalars = nullptr;  // host pointer, or device pointer when on_device
+    bool on_device = false;
+    BasesView view;
+    size_t n = 0;
+};
+
+// Enqueues every job (results to d_out_list[j], zero for n == 0) and joins the side lanes
+// back into c->stream.  Caller holds c->mu, has made c->dev current, and synchronises.
+static int enqueue_many(Ctx *c, const std::vector<ManyJob> &jobs, void *d_out_list) {
+    const size_t count = jobs.size();
+    int rc;
     const size_t SMALL = (size_t)1 << 17;
     const int NL = 3;
     // size every lane's scratch once, before anything is enqueued (growing synchronises the device)
@@ -684,14 +706,18 @@ extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, 
     {
         int next = 0;
         for (size_t j = 0; j < count; ++j) {
-            if (ns[j] == 0) continue;
-            if (ns[j] <= SMALL) {
-                const size_t a = pk_workspace_bytes(plan_for(c, views[j], ns[j], 0));
+            const ManyJob &jb = jobs[j];
+            if (jb.n == 0) continue;
+            if (jb.n <= SMALL) {
+                const size_t a = pk_workspace_bytes(plan_for(c, jb.view, jb.n, 0));
                 lane_arena[next] = a > lane_arena[next] ? a : lane_arena[next];
-                lane_scalars[next] = ns[j] * PLONKISH_CUDA_SCALAR_BYTES > lane_scalars[next] ? ns[j] * PLONKISH_CUDA_SCALAR_BYTES : lane_scalars[next];
+                const size_t sb = jb.on_device ? 0 : jb.n * PLONKISH_CUDA_SCALAR_BYTES;
+                lane_scalars[next] = sb > lane_scalars[next] ? sb : lane_scalars[next];
                 next = (next + 1) % NL;
+            } else if (jb.on_device) {
+                if (jb.n <= MAX_POINTS_PER_LAUNCH && (rc = grow(c->arena, pk_workspace_bytes(plan_for(c, jb.view, jb.n, 0))))) return rc;
             } else {
-                big_scalars = ns[j] > big_scalars ? ns[j] : big_scalars;
+                big_scalars = jb.n > big_scalars ? jb.n : big_scalars;
             }
         }
     }
@@ -699,27 +725,35 @@ extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, 
         if ((rc = grow(c->lanes[l].arena, lane_arena[l])) || (rc = grow(c->lanes[l].scalars, lane_scalars[l]))) return rc;
     }
     if (big_scalars && (rc = grow(c->scalars, big_scalars * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_out_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES, c->stream));  // n == 0 entries
     if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
-    CUDA_TRY(cudaEventRecord(c->many_start, c->stream));  // lanes start after the memset / earlier work
+    CUDA_TRY(cudaEventRecord(c->many_start, c->stream));  // lanes start after the memset / the producers of device scalars
     bool lane_used[NL] = {false, false, false};
     int next = 0;
     for (size_t j = 0; j < count; ++j) {
-        if (ns[j] == 0) continue;
-        affine *d_out = (affine *)((char *)c->batch_out.ptr + j * PLONKISH_CUDA_AFFINE_BYTES);
-        if (ns[j] <= SMALL) {
+        const ManyJob &jb = jobs[j];
+        if (jb.n == 0) continue;
+        affine *d_out = (affine *)((char *)d_out_list + j * PLONKISH_CUDA_AFFINE_BYTES);
+        if (jb.n <= SMALL) {
             Ctx::Lane &ln = c->lanes[next];
             if (!lane_used[next]) CUDA_TRY(cudaStreamWaitEvent(ln.stream, c->many_start, 0));
             lane_used[next] = true;
             next = (next + 1) % NL;
-            CUDA_TRY(cudaMemcpyAsync(ln.scalars.ptr, scalars_list[j], ns[j] * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, ln.stream));
-            MsmPlan plan = plan_for(c, views[j], ns[j], 0);
+            const void *d_sc = jb.scalars;
+            if (!jb.on_device) {
+                CUDA_TRY(cudaMemcpyAsync(ln.scalars.ptr, jb.scalars, jb.n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, ln.stream));
+                d_sc = ln.scalars.ptr;
+            }
+            MsmPlan plan = plan_for(c, jb.view, jb.n, 0);
             MsmWorkspace w = pk_carve_workspace(plan, ln.arena.ptr);
             w.result = (xyzz *)ln.d_res;
-            pk_enqueue_msm(plan, ln.scalars.ptr, views[j].ptr, w, nullptr, ln.stream);
+            pk_enqueue_msm(plan, d_sc, jb.view.ptr, w, nullptr, ln.stream);
             PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, ln.stream, (const xyzz *)ln.d_res, 1u, d_out, (xyzz *)nullptr);
         } else {
             xyzz *res = nullptr;
-            if ((rc = enqueue_host_msm(c, scalars_list[j], views[j], ns[j], &res))) return rc;
+            if (jb.on_device) rc = enqueue_device_msm(c, jb.scalars, jb.view, jb.n, 0, c->stream, &res);
+            else rc = enqueue_host_msm(c, jb.scalars, jb.view, jb.n, &res);
+            if (rc) return rc;
             PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, d_out, (xyzz *)nullptr);
             CUDA_TRY(cudaEventRecord(c->last_done, c->stream));  // the next large MSM reuses the scalar buffer and the arena in stream order
             c->has_last = true;
@@ -731,6 +765,35 @@ extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, 
         CUDA_TRY(cudaEventRecord(c->lanes[l].done, c->lanes[l].stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
     }
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, const uint64_t *bases_handles, const size_t *ns,
+                                               size_t count, void *out_affine64_list) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (count == 0) return PLONKISH_CUDA_OK;
+    if (!scalars_list || !bases_handles || !ns || !out_affine64_list) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: null argument");
+    std::vector<ManyJob> jobs(count);
+    int device = -1;
+    for (size_t j = 0; j < count; ++j) {
+        if (ns[j] == 0) continue;
+        if (!scalars_list[j] || !bases_handles[j]) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: MSM %zu lacks scalars or a bases handle", j);
+        int dev_j = 0;
+        int rc = view_of(bases_handles[j], ns[j], -1, jobs[j].view, &dev_j, "msm_many");
+        if (rc) return rc;
+        if (device < 0) device = dev_j;
+        if (dev_j != device) return fail(PLONKISH_CUDA_E_INVALID, "msm_many: all base slices must live on one device");
+        jobs[j].scalars = scalars_list[j];
+        jobs[j].n = ns[j];
+    }
+    if (device < 0) { memset(out_affine64_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_many: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES);
+    if (rc) return rc;
+    if ((rc = enqueue_many(c, jobs, c->batch_out.ptr))) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
     if ((rc = mark_done(c, c->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1432,4 +1495,326 @@ extern "C" int plonkish_cuda_debug_field_op(int device, int op, const void *a32,
 }
 extern "C" int plonkish_cuda_debug_point_op(int device, int op, const void *a128, const void *b128, void *out128, size_t n) {
     return debug_run(device, op, true, a128, b128, out128, n);
+}
+
+// ============================================================ resident scalars
+// Polynomial evaluations kept in HBM between commit and open: the
+// reference re-reads poly.evals() from host memory in every caller (kzg.rs:255, 291).
+struct ScalarsEntry {
+    int dev = 0;
+    size_t n = 0;
+    void *d_ptr = nullptr;
+};
+static std::map<uint64_t, ScalarsEntry> g_scalars;
+
+static void release_all_scalars() {  // caller holds g_mu
+    for (auto &kv : g_scalars) {
+        cudaSetDevice(kv.second.dev);
+        cudaFree(kv.second.d_ptr);
+    }
+    g_scalars.clear();
+}
+static uint64_t publish_scalars(int dev, void *d_ptr, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint64_t h = g_next_handle++;
+    ScalarsEntry e;
+    e.dev = dev; e.n = n; e.d_ptr = d_ptr;
+    g_scalars[h] = e;
+    return h;
+}
+static bool lookup_scalars(uint64_t handle, ScalarsEntry &out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_scalars.find(handle);
+    if (it == g_scalars.end()) return false;
+    out = it->second;
+    return true;
+}
+
+extern "C" int plonkish_cuda_scalars_register(int device, const void *scalars, size_t n, uint64_t *handle) {
+    if (!scalars || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "scalars_register: null argument or n == 0");
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "scalars_register: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_SCALAR_BYTES));
+    CUDA_TRY(cudaMemcpyAsync(d, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *handle = publish_scalars(device, d, n);
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_scalars_release(uint64_t handle) {
+    ScalarsEntry e;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_scalars.find(handle);
+        if (it == g_scalars.end()) return fail(PLONKISH_CUDA_E_INVALID, "scalars_release: unknown handle %llu", (unsigned long long)handle);
+        e = it->second;
+        g_scalars.erase(it);
+    }
+    CUDA_TRY(cudaSetDevice(e.dev));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaFree(e.d_ptr));
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_scalars_read(uint64_t handle, size_t offset, size_t n, void *out) {
+    ScalarsEntry e;
+    if (!lookup_scalars(handle, e)) return fail(PLONKISH_CUDA_E_INVALID, "scalars_read: unknown handle %llu", (unsigned long long)handle);
+    if (!out || offset > e.n || n > e.n - offset) return fail(PLONKISH_CUDA_E_INVALID, "scalars_read: range [%zu, +%zu) outside %zu scalars", offset, n, e.n);
+    Ctx *c = ctx_for(e.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "scalars_read: device %d not initialised", e.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    CUDA_TRY(cudaMemcpyAsync(out, (const char *)e.d_ptr + offset * PLONKISH_CUDA_SCALAR_BYTES, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_bases_read(uint64_t handle, size_t offset, size_t n, void *out) {
+    BasesEntry e;
+    if (!lookup_bases(handle, e)) return fail(PLONKISH_CUDA_E_INVALID, "bases_read: unknown handle %llu", (unsigned long long)handle);
+    if (e.n_shards != 1) return fail(PLONKISH_CUDA_E_INVALID, "bases_read: handle is sharded");
+    if (!out || offset > e.n || n > e.n - offset) return fail(PLONKISH_CUDA_E_INVALID, "bases_read: range [%zu, +%zu) outside %zu bases", offset, n, e.n);
+    Ctx *c = ctx_for(e.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_read: device %d not initialised", e.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    // row 0 of a table is the bases themselves
+    CUDA_TRY(cudaMemcpyAsync(out, (const char *)e.d_ptr[0] + offset * PLONKISH_CUDA_AFFINE_BYTES, n * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PLONKISH_CUDA_OK;
+}
+
+// commit from resident evaluations: variable_base_msm(poly.evals(), pp.eq(k)).into() (kzg.rs:255)
+extern "C" int plonkish_cuda_msm_bn254_g1_resident(uint64_t scalars_handle, uint64_t bases_handle, size_t n, void *out_affine64) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm_resident: null output");
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "msm_resident: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    if (n > se.n) return fail(PLONKISH_CUDA_E_INVALID, "msm_resident: n = %zu exceeds the %zu resident scalars", n, se.n);
+    if (n == 0) { memset(out_affine64, 0, PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
+    BasesView view;
+    int device = 0;
+    int rc = view_of(bases_handle, n, -1, view, &device, "msm_resident");
+    if (rc) return rc;
+    if (device != se.dev) return fail(PLONKISH_CUDA_E_INVALID, "msm_resident: scalars on device %d, bases on device %d", se.dev, device);
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_resident: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    xyzz *res = nullptr;
+    if ((rc = enqueue_device_msm(c, se.d_ptr, view, n, 0, c->stream, &res))) return rc;
+    PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res, 1u, (affine *)c->d_out, (xyzz *)nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mark_done(c, c->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_affine64, c->h_out, PLONKISH_CUDA_AFFINE_BYTES);
+    timer_report(n, t0);
+    return PLONKISH_CUDA_OK;
+}
+
+// g_prime = sum_i coeffs[i] * poly_i over resident polynomials (pcs/multilinear.rs:203-213).
+extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const void *coeffs, size_t count, size_t n, uint64_t *out_handle) {
+    if (!scalars_handles || !coeffs || !out_handle || count == 0 || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: bad argument");
+    std::vector<ScalarsEntry> es(count);
+    for (size_t i = 0; i < count; ++i) {
+        if (!lookup_scalars(scalars_handles[i], es[i])) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: unknown handle %llu", (unsigned long long)scalars_handles[i]);
+        if (es[i].n < n) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: polynomial %zu holds %zu < %zu scalars", i, es[i].n, n);
+        if (es[i].dev != es[0].dev) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: polynomials live on different devices");
+    }
+    Ctx *c = ctx_for(es[0].dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_linear_combination: device %d not initialised", es[0].dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_SCALAR_BYTES));
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)c->sm_count * 8) blocks = (size_t)c->sm_count * 8;
+    for (size_t done = 0; done < count; done += PK_LINCOMB_MAX) {
+        LincombArgs a;
+        a.count = (u32)(count - done < PK_LINCOMB_MAX ? count - done : PK_LINCOMB_MAX);
+        a.accumulate = done ? 1u : 0u;
+        for (u32 i = 0; i < a.count; ++i) {
+            a.poly[i] = (const uint4 *)es[done + i].d_ptr;
+            memcpy(a.coeff[i].l, (const char *)coeffs + (done + i) * PLONKISH_CUDA_SCALAR_BYTES, PLONKISH_CUDA_SCALAR_BYTES);
+        }
+        PK_LAUNCH(k_fr_lincomb, dim3((unsigned)blocks), dim3(256), 0, c->stream, a, n, (uint4 *)d);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d, n);
+    return PLONKISH_CUDA_OK;
+}
+
+// MultilinearKzg::open on a resident polynomial (kzg.rs:276-302): the quotients of
+// pcs/multilinear.rs:72-107 are produced in HBM and committed from there, so no scalar
+// crosses PCIe.  eq_handles[i] = pp.eq(i) for i < num_vars; point = num_vars Montgomery Fr;
+// out_comms = num_vars affine points (the order written to the transcript, kzg.rs:299),
+// out_eval = f(point) (the `remainder` of kzg.rs:295).
+extern "C" int plonkish_cuda_kzg_open_bn254(uint64_t scalars_handle, const uint64_t *eq_handles, const void *point, size_t num_vars,
+                                            void *out_comms_affine64, void *out_eval_mont32) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!out_eval_mont32 || (num_vars && (!eq_handles || !point || !out_comms_affine64))) return fail(PLONKISH_CUDA_E_INVALID, "kzg_open: null argument");
+    if (num_vars > 26) return fail(PLONKISH_CUDA_E_INVALID, "kzg_open: num_vars = %zu exceeds 26", num_vars);
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "kzg_open: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    const size_t n = (size_t)1 << num_vars;
+    if (se.n != n) return fail(PLONKISH_CUDA_E_INVALID, "kzg_open: polynomial holds %zu evaluations, point has %zu variables", se.n, num_vars);  // multilinear.rs:77
+    std::vector<ManyJob> jobs(num_vars);
+    for (size_t i = 0; i < num_vars; ++i) {
+        int dev_i = 0;
+        int rc = view_of(eq_handles[i], (size_t)1 << i, -1, jobs[i].view, &dev_i, "kzg_open");
+        if (rc) return rc;
+        if (dev_i != se.dev) return fail(PLONKISH_CUDA_E_INVALID, "kzg_open: eqs[%zu] lives on device %d, the polynomial on %d", i, dev_i, se.dev);
+    }
+    Ctx *c = ctx_for(se.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "kzg_open: device %d not initialised", se.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc;
+    // q buffer (2^k), two remainder buffers (2^(k-1), 2^(k-2)), point (k), eval (1)
+    const size_t q_elems = n, ra = n / 2 + 1, rb = n / 4 + 1;
+    const size_t total = (q_elems + ra + rb + num_vars + 2) * PLONKISH_CUDA_SCALAR_BYTES;
+    if ((rc = grow(c->open_buf, total))) return rc;
+    if ((rc = grow(c->batch_out, (num_vars + 1) * PLONKISH_CUDA_AFFINE_BYTES))) return rc;
+    char *base = (char *)c->open_buf.ptr;
+    void *q = base, *rem_a = base + q_elems * 32, *rem_b = base + (q_elems + ra) * 32;
+    void *d_point = base + (q_elems + ra + rb) * 32, *d_eval = base + (q_elems + ra + rb + num_vars + 1) * 32;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_point, point, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    pk_enqueue_quotients(se.d_ptr, (u32)num_vars, d_point, q, rem_a, rem_b, d_eval, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    // largest first on the main stream; the small ones overlap on the side lanes
+    for (size_t i = 0; i < num_vars; ++i) {
+        jobs[i].scalars = (const char *)q + ((size_t)1 << i) * PLONKISH_CUDA_SCALAR_BYTES;
+        jobs[i].on_device = true;
+        jobs[i].n = (size_t)1 << i;
+    }
+    if (num_vars && (rc = enqueue_many(c, jobs, c->batch_out.ptr))) return rc;
+    if (num_vars) CUDA_TRY(cudaMemcpyAsync(out_comms_affine64, c->batch_out.ptr, num_vars * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, d_eval, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mark_done(c, c->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_eval_mont32, c->h_out, PLONKISH_CUDA_SCALAR_BYTES);
+    for (size_t i = 0; i < num_vars; ++i) timer_report((size_t)1 << i, t0);
+    return PLONKISH_CUDA_OK;
+}
+
+// ============================================================== fixed-base MSM
+// fixed_base_msm (msm.rs:67-81) over a window table of one base (msm.rs:16-31) followed by
+// batch_normalize (kzg.rs:204-207, univariate/kzg.rs:196-199): out[i] = scalars[i] * base, affine.
+static const size_t FIXED_BATCH = (size_t)1 << 22;  // scalars per launch pair; bounds the projective scratch (512 MiB)
+
+struct FixedTable {
+    void *table = nullptr, *offsets = nullptr, *tmp = nullptr;  // tmp: max(table build, FIXED_BATCH) xyzz
+    void release() { cudaFree(table); cudaFree(offsets); cudaFree(tmp); table = offsets = tmp = nullptr; }
+};
+// Caller holds c->mu.  d_base: one affine point in device memory.
+static int fixed_table_build(Ctx *c, const void *d_base, size_t max_batch, FixedTable &ft) {
+    const size_t entries = (size_t)PK_FIXED_W * PK_FIXED_ROW;
+    const size_t tmp_pts = entries > max_batch ? entries : max_batch;
+    CUDA_TRY(cudaMalloc(&ft.table, entries * sizeof(affine)));
+    CUDA_TRY(cudaMalloc(&ft.offsets, PK_FIXED_W * sizeof(affine)));
+    CUDA_TRY(cudaMalloc(&ft.tmp, tmp_pts * sizeof(xyzz)));
+    pk_enqueue_fixed_table(d_base, (affine *)ft.offsets, (xyzz *)ft.tmp, (affine *)ft.table, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_fixed_base_msm_bn254_g1(int device, const void *base_affine64, const void *scalars, size_t n, void *out_affine64_list) {
+    if (!base_affine64 || (n && (!scalars || !out_affine64_list))) return fail(PLONKISH_CUDA_E_INVALID, "fixed_base_msm: null argument");
+    if (n == 0) return PLONKISH_CUDA_OK;
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fixed_base_msm: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t batch = n < FIXED_BATCH ? n : FIXED_BATCH;
+    int rc;
+    if ((rc = grow(c->scalars, batch * PLONKISH_CUDA_SCALAR_BYTES)) || (rc = grow(c->bases_tmp, batch * PLONKISH_CUDA_AFFINE_BYTES))) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    CUDA_TRY(cudaMemcpyAsync((char *)c->d_out + 384, base_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+    FixedTable ft;
+    if ((rc = fixed_table_build(c, (char *)c->d_out + 384, batch, ft))) { ft.release(); return rc; }
+    for (size_t done = 0; done < n; done += batch) {
+        const size_t cnt = n - done < batch ? n - done : batch;
+        CUDA_TRY(cudaMemcpyAsync(c->scalars.ptr, (const char *)scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        pk_enqueue_fixed_base(c->scalars.ptr, (u32)cnt, (const affine *)ft.table, (xyzz *)ft.tmp, (affine *)c->bases_tmp.ptr, c->stream);
+        CUDA_TRY(cudaMemcpyAsync((char *)out_affine64_list + done * PLONKISH_CUDA_AFFINE_BYTES, c->bases_tmp.ptr, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    rc = mark_done(c, c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    ft.release();
+    return rc;
+}
+
+// MultilinearKzg::setup's prover half (kzg.rs:167-212) on the device: eq tables from
+// ss (num_vars Montgomery Fr), times g1 by fixed-base MSM, normalised, and every slice
+// eqs[k] (2^k bases, k = 0..num_vars) registered as resident bases — the SRS never exists
+// in host memory.  handles_out receives num_vars + 1 handles.
+extern "C" int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affine64, const void *ss, size_t num_vars, uint64_t *handles_out) {
+    if (!g1_affine64 || !handles_out || (num_vars && !ss)) return fail(PLONKISH_CUDA_E_INVALID, "kzg_setup_eqs: null argument");
+    if (num_vars > 26) return fail(PLONKISH_CUDA_E_INVALID, "kzg_setup_eqs: num_vars = %zu exceeds 26", num_vars);
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "kzg_setup_eqs: device %d not initialised", device);
+    std::vector<BasesEntry> entries(num_vars + 1);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CUDA_TRY(cudaSetDevice(c->dev));
+        const size_t total = ((size_t)2 << num_vars) - 1;
+        const size_t batch = total < FIXED_BATCH ? total : FIXED_BATCH;
+        void *d_eq = nullptr, *d_pts = nullptr, *d_ss = nullptr;
+        FixedTable ft;
+        auto cleanup = [&] { cudaFree(d_eq); cudaFree(d_pts); cudaFree(d_ss); ft.release(); };
+        if (cudaMalloc(&d_eq, total * PLONKISH_CUDA_SCALAR_BYTES) != cudaSuccess || cudaMalloc(&d_pts, total * PLONKISH_CUDA_AFFINE_BYTES) != cudaSuccess ||
+            cudaMalloc(&d_ss, (num_vars + 1) * PLONKISH_CUDA_SCALAR_BYTES) != cudaSuccess) {
+            cleanup();
+            return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: out of device memory for %zu points", total);
+        }
+        if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+        if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_ss, ss, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync((char *)c->d_out + 384, g1_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+        pk_enqueue_eq_scalars(d_ss, (u32)num_vars, d_eq, (u32)c->sm_count, c->stream);
+        int rc = fixed_table_build(c, (char *)c->d_out + 384, batch, ft);
+        if (rc) { cleanup(); return rc; }
+        for (size_t done = 0; done < total; done += batch) {
+            const size_t cnt = total - done < batch ? total - done : batch;
+            pk_enqueue_fixed_base((const char *)d_eq + done * PLONKISH_CUDA_SCALAR_BYTES, (u32)cnt, (const affine *)ft.table, (xyzz *)ft.tmp,
+                                  (affine *)((char *)d_pts + done * PLONKISH_CUDA_AFFINE_BYTES), c->stream);
+        }
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            cleanup();
+            return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: kernel sequence failed");
+        }
+        cudaFree(d_eq); d_eq = nullptr;
+        ft.release();
+        for (size_t k = 0; k <= num_vars; ++k) {
+            const size_t nk = (size_t)1 << k;
+            const void *src = (const char *)d_pts + (nk - 1) * PLONKISH_CUDA_AFFINE_BYTES;
+            void *d = nullptr;
+            uint32_t tc = 0;
+            bool owns = true;
+            rc = make_resident(c, src, true, nk, 0, &d, &tc, &owns);
+            if (!rc && !owns) {  // plain slice: give it its own storage, d_pts goes away
+                if (cudaMalloc(&d, nk * PLONKISH_CUDA_AFFINE_BYTES) != cudaSuccess) rc = fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: out of device memory");
+                else if (cudaMemcpyAsync(d, src, nk * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) rc = fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: copy failed");
+                owns = true;
+            }
+            if (rc) {
+                for (size_t j = 0; j < k; ++j) cudaFree(entries[j].d_ptr[0]);
+                cleanup();
+                return rc;
+            }
+            BasesEntry &e = entries[k];
+            e.n_shards = 1; e.dev = device; e.n = nk; e.owns = true;
+            e.d_ptr.push_back(d); e.shard_n.push_back(nk); e.table_c.push_back(tc);
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cleanup();
+    }
+    for (size_t k = 0; k <= num_vars; ++k) handles_out[k] = publish(entries[k]);
+    return PLONKISH_CUDA_OK;
 }

@@ -1,0 +1,213 @@
+// Kernels for the callers either side of the MSM: the scalar
+// producers of MultilinearKzg::open and the SRS construction of MultilinearKzg::setup.
+//
+//   quotients        /root/reference/plonkish_backend/src/pcs/multilinear.rs:72-107
+//   g_prime merge    pcs/multilinear.rs:203-213
+//   eq tables        pcs/multilinear/kzg.rs:174-193
+//   window_table     util/arithmetic/msm.rs:16-31
+//   fixed_base_msm   util/arithmetic/msm.rs:50-81, then batch_normalize (kzg.rs:204-207)
+//
+// The Fr kernels are one multiplication per 64-96 bytes moved: HBM bound, 32-byte elements
+// moved as two 16-byte words.  The fixed-base kernel is the accumulate loop's mixed addition
+// against a small table that stays in L2: IMAD bound like k_accumulate.
+//
+// Also compiled by g++ against tests/emul/cuda_emul.h (PLONKISH_EMUL) for the CPU suite.
+#pragma once
+#include "msm_kernels.cuh"
+
+namespace pk {
+
+PK_HD fe fr_mul(const fe &a, const fe &b) { return mont_mul<FrMod>(a, b); }
+PK_HD fe fr_add(const fe &a, const fe &b) { return mod_add<FrMod>(a, b); }
+PK_HD fe fr_sub(const fe &a, const fe &b) { return mod_sub<FrMod>(a, b); }
+
+// plain (coherent) 32-byte load: for buffers another launch of the same stream wrote
+PK_HD fe load_fe_plain(const uint4 *p) {
+    const uint4 a = p[0], b = p[1];
+    fe r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// ------------------------------------------------------------------ quotients
+// One level of `quotients` (multilinear.rs:85-97): q[j] = hi[j] - lo[j],
+// rem_out[j] = lo[j] + q[j] * x with lo = rem_in[0..half), hi = rem_in[half..2*half).
+__global__ void __launch_bounds__(256) k_quotient_fold(const uint4 *__restrict__ rem_in, uint4 *__restrict__ rem_out, uint4 *__restrict__ q,
+                                                       const uint4 *__restrict__ x_ptr, u32 half) {
+    const fe x = load_fe_plain(x_ptr);
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < half; j += gridDim.x * blockDim.x) {
+        const fe lo = load_fe_plain(rem_in + 2 * (size_t)j);
+        const fe hi = load_fe_plain(rem_in + 2 * ((size_t)half + j));
+        const fe d = fr_sub(hi, lo);
+        store_fe(q + 2 * (size_t)j, d);
+        store_fe(rem_out + 2 * (size_t)j, fr_add(lo, fr_mul(d, x)));
+    }
+}
+
+// The last `levels` (<= 10) levels in one block: the remainder lives in shared memory.
+// q_base is the quotient buffer (q_i at element offset 2^i); point[i] = x_i.
+#define PK_QTAIL_MAX_LEVELS 10
+__global__ void __launch_bounds__(512) k_quotient_tail(const uint4 *__restrict__ rem_in, uint4 *__restrict__ q_base, const uint4 *__restrict__ point,
+                                                       u32 levels, uint4 *__restrict__ eval_out) {
+    __shared__ fe rem[1u << PK_QTAIL_MAX_LEVELS];
+    const u32 n = 1u << levels;
+    for (u32 j = threadIdx.x; j < n; j += blockDim.x) rem[j] = load_fe_plain(rem_in + 2 * (size_t)j);
+    __syncthreads();
+    for (u32 i = levels; i-- > 0;) {
+        const u32 half = 1u << i;
+        const fe x = load_fe_plain(point + 2 * (size_t)i);
+        // half <= 512 = blockDim: one element per thread
+        fe lo, d;
+        const bool on = threadIdx.x < half;
+        if (on) {
+            lo = rem[threadIdx.x];
+            d = fr_sub(rem[half + threadIdx.x], lo);
+            store_fe(q_base + 2 * ((size_t)half + threadIdx.x), d);
+        }
+        __syncthreads();
+        if (on) rem[threadIdx.x] = fr_add(lo, fr_mul(d, x));
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_fe(eval_out, rem[0]);
+}
+
+// Host side of `quotients`: poly (2^k scalars) -> q buffer (2^k entries, q_i at offset 2^i),
+// f(point) -> eval_out.  rem_a holds 2^(k-1) scalars, rem_b 2^(k-2).
+inline void pk_enqueue_quotients(const void *poly, u32 k, const void *d_point, void *q, void *rem_a, void *rem_b, void *eval_out,
+                                 u32 sm_count, pk_stream_t stream) {
+    const uint4 *src = (const uint4 *)poly;
+    uint4 *bufs[2] = {(uint4 *)rem_a, (uint4 *)rem_b};
+    int which = 0;
+    u32 level = k;
+    while (level > PK_QTAIL_MAX_LEVELS) {
+        const u32 i = level - 1, half = 1u << i;
+        u32 blocks = (half + 255) / 256;
+        const u32 cap = sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        PK_LAUNCH(k_quotient_fold, dim3(blocks), dim3(256), 0, stream, src, bufs[which], (uint4 *)q + 2 * (size_t)half,
+                  (const uint4 *)d_point + 2 * (size_t)i, half);
+        src = bufs[which];
+        which ^= 1;
+        level = i;
+    }
+    PK_LAUNCH(k_quotient_tail, dim3(1), dim3(512), 0, stream, src, (uint4 *)q, (const uint4 *)d_point, level, (uint4 *)eval_out);
+}
+
+// -------------------------------------------------------------- g_prime merge
+#define PK_LINCOMB_MAX 12
+struct LincombArgs {
+    const uint4 *poly[PK_LINCOMB_MAX];
+    fe coeff[PK_LINCOMB_MAX];
+    u32 count;
+    u32 accumulate;  // 1: add to what `out` already holds (more than PK_LINCOMB_MAX terms)
+};
+// out[j] (+)= sum_i coeff[i] * poly[i][j]   (multilinear.rs:208-213)
+__global__ void __launch_bounds__(256) k_fr_lincomb(LincombArgs a, size_t n, uint4 *__restrict__ out) {
+    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        fe acc = a.accumulate ? load_fe_plain(out + 2 * j) : fe_zero();
+        for (u32 i = 0; i < a.count; ++i) acc = fr_add(acc, fr_mul(a.coeff[i], load_fe(a.poly[i] + 2 * j)));
+        store_fe(out + 2 * j, acc);
+    }
+}
+
+// ------------------------------------------------------------------ eq tables
+// kzg.rs:183-191: hi[j] = s * last[j], lo[j] = last[j] - hi[j].
+__global__ void __launch_bounds__(256) k_eq_expand(const uint4 *__restrict__ last, uint4 *__restrict__ lo, uint4 *__restrict__ hi,
+                                                   const uint4 *__restrict__ s_ptr, u32 len) {
+    const fe s = load_fe_plain(s_ptr);
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x) {
+        const fe e = load_fe_plain(last + 2 * (size_t)j);
+        const fe h = fr_mul(s, e);
+        store_fe(hi + 2 * (size_t)j, h);
+        store_fe(lo + 2 * (size_t)j, fr_sub(e, h));
+    }
+}
+__global__ void k_fr_set_one(uint4 *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        fe one;  // R mod r: Montgomery form of 1
+        one.l[0] = 0x4ffffffbu; one.l[1] = 0xac96341cu; one.l[2] = 0x9f60cd29u; one.l[3] = 0x36fc7695u;
+        one.l[4] = 0x7879462eu; one.l[5] = 0x666ea36fu; one.l[6] = 0x9a07df2fu; one.l[7] = 0x0e0a77c1u;
+        store_fe(out, one);
+    }
+}
+// eqs as scalars: slice k (2^k values) at element offset 2^k - 1 of `out` (kzg.rs:199 order).
+inline void pk_enqueue_eq_scalars(const void *d_ss, u32 num_vars, void *out, u32 sm_count, pk_stream_t stream) {
+    uint4 *o = (uint4 *)out;
+    PK_LAUNCH(k_fr_set_one, dim3(1), dim3(32), 0, stream, o);
+    for (u32 k = 0; k < num_vars; ++k) {
+        const u32 len = 1u << k;
+        u32 blocks = (len + 255) / 256;
+        const u32 cap = sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        PK_LAUNCH(k_eq_expand, dim3(blocks), dim3(256), 0, stream, (const uint4 *)(o + 2 * ((size_t)len - 1)), o + 2 * ((size_t)2 * len - 1),
+                  o + 2 * ((size_t)3 * len - 1), (const uint4 *)d_ss + 2 * (size_t)k, len);
+    }
+}
+
+// ------------------------------------------------------------- fixed-base MSM
+// Signed 16-bit windows: 16 windows cover 254 bits plus the carry, the table holds
+// d * 2^(16w) * base for d = 1..2^15 (16 x 32768 x 64 B = 32 MiB, L2 resident); the
+// reference's unsigned table (msm.rs:16-31) is the same set of multiples, twice as many.
+#define PK_FIXED_C 16
+#define PK_FIXED_W 16
+#define PK_FIXED_ROW (1u << (PK_FIXED_C - 1))
+
+// offsets[w] = 2^(16w) * base, affine (the `offset` of msm.rs:22).  One thread.
+__global__ void k_fixed_offsets(const affine *__restrict__ base, affine *__restrict__ offsets) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    xyzz cur = xyzz_from_affine(*base);
+    for (u32 w = 0; w < PK_FIXED_W; ++w) {
+        offsets[w] = xyzz_to_affine(cur);
+        for (u32 b = 0; b < PK_FIXED_C; ++b) cur = xyzz_double(cur);
+    }
+}
+// rows[w][d-1] = d * offsets[w] (projective; normalised by k_table_normalize afterwards).
+__global__ void __launch_bounds__(128) k_fixed_table(const affine *__restrict__ offsets, xyzz *__restrict__ rows) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= PK_FIXED_W * PK_FIXED_ROW) return;
+    const u32 w = t / PK_FIXED_ROW, d = t % PK_FIXED_ROW + 1;
+    const affine off = offsets[w];
+    xyzz acc = xyzz_identity();
+    for (int bit = 31 - __clz(d); bit >= 0; --bit) {
+        acc = xyzz_double(acc);
+        if ((d >> bit) & 1) xyzz_madd(acc, off.x, off.y);
+    }
+    store_xyzz(rows + t, acc);
+}
+// out[i] = scalars[i] * base (windowed_scalar_mul, msm.rs:50-65, with signed digits).
+__global__ void __launch_bounds__(128, 4) k_fixed_base_mul(const uint4 *__restrict__ scalars, u32 n, const affine *__restrict__ table,
+                                                           xyzz *__restrict__ out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fe v = fr_to_canonical(load_fe(scalars + 2 * (size_t)i));  // to_repr, msm.rs:56
+    xyzz acc = xyzz_identity();
+    u32 carry = 0;
+    for (u32 w = 0; w < PK_FIXED_W; ++w) {
+        const u32 raw = ((v.l[w >> 1] >> ((w & 1) * 16)) & 0xffffu) + carry;
+        carry = raw > PK_FIXED_ROW ? 1u : 0u;
+        const u32 mag = carry ? (1u << PK_FIXED_C) - raw : raw;
+        if (mag == 0) continue;
+        const uint4 *tp = reinterpret_cast<const uint4 *>(table + (size_t)w * PK_FIXED_ROW + (mag - 1));
+        const fe x = load_fe(tp);
+        fe y = load_fe(tp + 2);
+        if (carry) y = fq_neg(y);
+        xyzz_madd<MulInline>(acc, x, y);
+    }
+    store_xyzz(out + i, acc);
+}
+
+// Table for one base: offsets, multiples, normalise.  tmp holds 16 x 32768 xyzz (64 MiB).
+inline void pk_enqueue_fixed_table(const void *d_base, affine *d_offsets, xyzz *tmp, affine *table, pk_stream_t stream) {
+    const u32 total = PK_FIXED_W * PK_FIXED_ROW;
+    PK_LAUNCH(k_fixed_offsets, dim3(1), dim3(32), 0, stream, (const affine *)d_base, d_offsets);
+    PK_LAUNCH(k_fixed_table, dim3((total + 127) / 128), dim3(128), 0, stream, (const affine *)d_offsets, tmp);
+    PK_LAUNCH(k_table_normalize, dim3(((total + 7) / 8 + 127) / 128), dim3(128), 0, stream, (const xyzz *)tmp, total, table);
+}
+// out_affine[i] = scalars[i] * base for n <= 2^22 scalars per call; tmp holds n xyzz.
+inline void pk_enqueue_fixed_base(const void *d_scalars, u32 n, const affine *table, xyzz *tmp, affine *out_affine, pk_stream_t stream) {
+    PK_LAUNCH(k_fixed_base_mul, dim3((n + 127) / 128), dim3(128), 0, stream, (const uint4 *)d_scalars, n, table, tmp);
+    PK_LAUNCH(k_table_normalize, dim3(((n + 7) / 8 + 127) / 128), dim3(128), 0, stream, (const xyzz *)tmp, n, out_affine);
+}
+
+}  // namespace pk

@@ -6,10 +6,14 @@ Mirrors, for BN254 (`M = Bn256`):
   MultilinearKzg::open          kzg.rs:276-302  (quotient commitments written to the transcript)
   quotients                     pcs/multilinear.rs:72-107
   UnivariateKzg::commit_coeffs  pcs/univariate/kzg.rs:24-30
+  MultilinearKzg::setup (prover half)  kzg.rs:167-212   -> setup()
+  g_prime merge                 pcs/multilinear.rs:203-213  -> linear_combination()
 Every one of them is `variable_base_msm(scalars, srs_slice)`; only the MSM runs on the
 GPU.  The scalar-field bookkeeping of `quotients` is done here with Python integers — it
-is the caller's CPU work in the reference too (field-only, out of scope per SURVEY.md §8)
-and is meant for the parity tests and small sizes, not for throughput.
+is the caller's CPU work in the reference too and is meant for the parity tests and
+small sizes.  The throughput path keeps polynomials resident (ResidentScalars): commit with
+keep=True, merge with linear_combination(), open with open_resident(); there `quotients`
+runs on the GPU as well and no scalar crosses PCIe twice.
 """
 from __future__ import annotations
 
@@ -17,7 +21,8 @@ from typing import List, Sequence, Tuple
 
 import numpy as np
 
-from .msm import G1Bases, variable_base_msm, variable_base_msm_batch, variable_base_msm_many
+from .msm import (G1Bases, ResidentScalars, fr_linear_combination, kzg_open_resident, kzg_setup_eqs, variable_base_msm,
+                  variable_base_msm_batch, variable_base_msm_batch_keep, variable_base_msm_many)
 
 FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 _MONT = 1 << 256
@@ -39,8 +44,8 @@ class MultilinearKzgProverParam:
     """`MultilinearKzgProverParams { g1, eqs }` (kzg.rs:55-77): eqs[k] holds the 2^k bases
     eq_j(s_0..s_{k-1}) * G.  Each slice is made resident on the GPU once."""
 
-    def __init__(self, eqs: Sequence[np.ndarray], device: int = 0, mode: int = 0):
-        self.eqs = [G1Bases(e, device=device, mode=mode) for e in eqs]
+    def __init__(self, eqs: Sequence, device: int = 0, mode: int = 0):
+        self.eqs = [e if isinstance(e, G1Bases) else G1Bases(e, device=device, mode=mode) for e in eqs]
         for k, e in enumerate(self.eqs):
             assert len(e) == 1 << k, f"eqs[{k}] must hold 2^{k} bases"
 
@@ -55,26 +60,40 @@ class MultilinearKzgProverParam:
             e.release()
 
 
-def _num_vars_of(evals: np.ndarray) -> int:
-    n = np.asarray(evals).reshape(-1, 4).shape[0]
+def setup(g1: np.ndarray, ss: np.ndarray, device: int = 0) -> MultilinearKzgProverParam:
+    """The prover half of MultilinearKzg::setup (kzg.rs:167-212) for the toxic-waste point
+    ss (num_vars Montgomery Fr): eq tables, fixed-base MSM by g1, batch normalise — all on the
+    GPU, every eqs[k] resident when it returns."""
+    return MultilinearKzgProverParam(kzg_setup_eqs(g1, ss, device=device), device=device)
+
+
+def _num_vars_of(evals) -> int:
+    n = len(evals) if isinstance(evals, ResidentScalars) else np.asarray(evals).reshape(-1, 4).shape[0]
     assert n and n & (n - 1) == 0, "a multilinear polynomial has 2^k evaluations"
     return n.bit_length() - 1
 
 
 def commit(pp: MultilinearKzgProverParam, evals: np.ndarray) -> np.ndarray:
     """kzg.rs:252-257: variable_base_msm(poly.evals(), pp.eq(poly.num_vars())).into()"""
-    k = _num_vars_of(evals)
+    k = _num_vars_of(evals)  # evals: [2^k, 4] host array or ResidentScalars
     if k > pp.num_vars():  # validate_input, pcs/multilinear.rs:26-58
         raise ValueError(f"Too many variates of poly to commit (param supports variates up to {pp.num_vars()} but got {k})")
     return variable_base_msm(evals, pp.eq(k))
 
 
-def batch_commit(pp: MultilinearKzgProverParam, polys: Sequence[np.ndarray]) -> List[np.ndarray]:
+def batch_commit(pp: MultilinearKzgProverParam, polys: Sequence[np.ndarray], keep: bool = False):
     """kzg.rs:259-274: one MSM per polynomial, in order.  Polynomials of equal size go down
-    as one pipelined batch (upload of the next overlaps the current MSM)."""
+    as one pipelined batch (upload of the next overlaps the current MSM).  keep=True also
+    returns the polynomials as ResidentScalars: (commitments, resident)."""
     polys = list(polys)
     if not polys:
-        return []
+        return ([], []) if keep else []
+    if keep:
+        k = _num_vars_of(polys[0])
+        if k > pp.num_vars():
+            raise ValueError(f"Too many variates of poly to batch commit (param supports variates up to {pp.num_vars()} but got {k})")
+        comms, resident = variable_base_msm_batch_keep(polys, pp.eq(k))
+        return list(comms), resident
     sizes = {_num_vars_of(p) for p in polys}
     if len(sizes) == 1 and len(polys) > 1:
         k = sizes.pop()
@@ -110,6 +129,22 @@ def open(pp: MultilinearKzgProverParam, evals: np.ndarray, point: Sequence[int])
     qs, value = quotients(fr_from_montgomery(evals), [int(x) for x in point])
     # the quotients do not depend on their commitments: one call, small MSMs run concurrently
     comms = variable_base_msm_many([fr_to_montgomery(q) for q in qs], [pp.eq(i) for i in range(k)])
+    return list(comms), value
+
+
+def linear_combination(polys: Sequence[ResidentScalars], coeffs: np.ndarray) -> ResidentScalars:
+    """pcs/multilinear.rs:203-213 (g_prime): sum_i coeffs[i] * polys[i], resident in, resident out."""
+    return fr_linear_combination(polys, coeffs)
+
+
+def open_resident(pp: MultilinearKzgProverParam, poly: ResidentScalars, point: np.ndarray) -> Tuple[List[np.ndarray], np.ndarray]:
+    """kzg.rs:276-302 on a resident polynomial; point is [k, 4] Montgomery Fr.  Returns the k
+    quotient commitments and f(point) as Montgomery limbs."""
+    k = _num_vars_of(poly)
+    pt = np.ascontiguousarray(point, dtype=np.uint64).reshape(-1, 4)
+    if k > pp.num_vars() or pt.shape[0] != k:
+        raise ValueError("Invalid point / polynomial size for open")
+    comms, value = kzg_open_resident(poly, pp.eqs, pt)
     return list(comms), value
 
 

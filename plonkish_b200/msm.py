@@ -72,12 +72,58 @@ class G1Bases:
                 _lib.check(rc, "plonkish_cuda_bases_register_device")
         self.handle = handle.value
 
+    @classmethod
+    def _adopt(cls, handle: int, n: int, device: int) -> "G1Bases":
+        """Wrap a handle the library produced itself (plonkish_cuda_kzg_setup_eqs_bn254)."""
+        self = cls.__new__(cls)
+        self.handle, self.n, self.device = int(handle), int(n), int(device)
+        return self
+
     def __len__(self) -> int:
         return self.n
+
+    def to_host(self, offset: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """The resident bases back on the host ([n, 8] uint64)."""
+        n = self.n - offset if n is None else n
+        out = np.zeros((n, 8), dtype=np.uint64)
+        _lib.check(_lib.lib().plonkish_cuda_bases_read(self.handle, offset, n, out.ctypes.data), "plonkish_cuda_bases_read")
+        return out
 
     def release(self) -> None:
         if self.handle:
             _lib.check(_lib.lib().plonkish_cuda_bases_release(self.handle), "plonkish_cuda_bases_release")
+            self.handle = 0
+
+
+class ResidentScalars:
+    """A polynomial's evaluations (n x bn256::Fr, Montgomery) kept in HBM between its commit
+    and its opening — poly.evals() of pcs/multilinear/kzg.rs:255,291 without the re-upload."""
+
+    def __init__(self, scalars, device: int = 0):
+        arr = _as_u64(scalars, 4, "scalars")
+        handle = ctypes.c_uint64(0)
+        _lib.check(_lib.lib().plonkish_cuda_scalars_register(device, arr.ctypes.data, arr.shape[0], ctypes.byref(handle)),
+                   "plonkish_cuda_scalars_register")
+        self.handle, self.n, self.device = handle.value, arr.shape[0], device
+
+    @classmethod
+    def _adopt(cls, handle: int, n: int, device: int) -> "ResidentScalars":
+        self = cls.__new__(cls)
+        self.handle, self.n, self.device = int(handle), int(n), int(device)
+        return self
+
+    def __len__(self) -> int:
+        return self.n
+
+    def to_host(self, offset: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = self.n - offset if n is None else n
+        out = np.zeros((n, 4), dtype=np.uint64)
+        _lib.check(_lib.lib().plonkish_cuda_scalars_read(self.handle, offset, n, out.ctypes.data), "plonkish_cuda_scalars_read")
+        return out
+
+    def release(self) -> None:
+        if self.handle:
+            _lib.check(_lib.lib().plonkish_cuda_scalars_release(self.handle), "plonkish_cuda_scalars_release")
             self.handle = 0
 
 
@@ -111,6 +157,12 @@ def variable_base_msm(scalars, bases, n_gpus: int = 1) -> np.ndarray:
     """
     lib = _lib.lib()
     out = np.zeros(8, dtype=np.uint64)
+    if isinstance(scalars, ResidentScalars):
+        assert isinstance(bases, G1Bases), "resident scalars need resident bases"
+        assert scalars.n <= bases.n, "more scalars than registered bases"  # msm.rs:90
+        _lib.check(lib.plonkish_cuda_msm_bn254_g1_resident(scalars.handle, bases.handle, scalars.n, out.ctypes.data),
+                   "plonkish_cuda_msm_bn254_g1_resident")
+        return out
     if isinstance(bases, (G1Bases, ShardedG1Bases)):
         sc = _as_u64(scalars, 4, "scalars")
         assert sc.shape[0] <= bases.n, "more scalars than registered bases"  # msm.rs:90
@@ -152,6 +204,75 @@ def variable_base_msm_batch(scalars_list: Sequence, bases: "G1Bases") -> np.ndar
     rc = _lib.lib().plonkish_cuda_msm_bn254_g1_batch(ptrs, count, bases.handle, n, out.ctypes.data)
     _lib.check(rc, "plonkish_cuda_msm_bn254_g1_batch")
     return out
+
+
+def variable_base_msm_batch_keep(scalars_list: Sequence, bases: "G1Bases"):
+    """variable_base_msm_batch that also leaves every polynomial resident: returns
+    ([count, 8] commitments, [ResidentScalars, ...])."""
+    arrs = [_as_u64(s, 4, "scalars") for s in scalars_list]
+    assert arrs, "empty batch"
+    n = arrs[0].shape[0]
+    assert n and all(a.shape[0] == n for a in arrs), "batch entries must have one non-zero length"
+    assert n <= bases.n, "more scalars than registered bases"  # msm.rs:90
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    out = np.zeros((len(arrs), 8), dtype=np.uint64)
+    handles = np.zeros(len(arrs), dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_batch_keep(ctypes.cast(ptrs, ctypes.c_void_p), len(arrs), bases.handle, n,
+                                                          out.ctypes.data, handles.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_batch_keep")
+    return out, [ResidentScalars._adopt(h, n, bases.device) for h in handles]
+
+
+def fr_linear_combination(polys: Sequence["ResidentScalars"], coeffs) -> "ResidentScalars":
+    """sum_i coeffs[i] * polys[i] as a new resident polynomial (the g_prime merge,
+    pcs/multilinear.rs:203-213).  coeffs: [count, 4] Montgomery Fr."""
+    cs = _as_u64(coeffs, 4, "coeffs")
+    assert len(polys) == cs.shape[0] and len(polys) > 0
+    n = min(p.n for p in polys)
+    hs = np.array([p.handle for p in polys], dtype=np.uint64)
+    out = ctypes.c_uint64(0)
+    rc = _lib.lib().plonkish_cuda_fr_linear_combination(hs.ctypes.data, cs.ctypes.data, len(polys), n, ctypes.byref(out))
+    _lib.check(rc, "plonkish_cuda_fr_linear_combination")
+    return ResidentScalars._adopt(out.value, n, polys[0].device)
+
+
+def kzg_open_resident(poly: "ResidentScalars", eqs: Sequence["G1Bases"], point):
+    """MultilinearKzg::open on a resident polynomial (kzg.rs:276-302): returns the num_vars
+    quotient commitments ([k, 8]) and f(point) (Montgomery limbs [4])."""
+    pt = _as_u64(point, 4, "point") if len(point) else np.zeros((0, 4), dtype=np.uint64)
+    k = pt.shape[0]
+    assert poly.n == 1 << k, "point / polynomial size mismatch"  # multilinear.rs:77
+    assert len(eqs) >= k
+    hs = np.array([e.handle for e in eqs[:k]], dtype=np.uint64)
+    comms = np.zeros((k, 8), dtype=np.uint64)
+    value = np.zeros(4, dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_kzg_open_bn254(poly.handle, hs.ctypes.data if k else None, pt.ctypes.data if k else None, k,
+                                                 comms.ctypes.data if k else None, value.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_kzg_open_bn254")
+    return comms, value
+
+
+def fixed_base_msm(base, scalars, device: int = 0) -> np.ndarray:
+    """fixed_base_msm + batch_normalize (msm.rs:16-31, 50-81; kzg.rs:204-207):
+    [n, 8] affine points scalars[i] * base."""
+    b = np.ascontiguousarray(base, dtype=np.uint64).reshape(8)
+    sc = _as_u64(scalars, 4, "scalars")
+    out = np.zeros((sc.shape[0], 8), dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_fixed_base_msm_bn254_g1(device, b.ctypes.data, sc.ctypes.data, sc.shape[0], out.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_fixed_base_msm_bn254_g1")
+    return out
+
+
+def kzg_setup_eqs(g1, ss, device: int = 0):
+    """The prover half of MultilinearKzg::setup (kzg.rs:167-212) on the GPU: returns
+    [G1Bases(eqs[0]), ..., G1Bases(eqs[num_vars])], resident, never in host memory."""
+    g = np.ascontiguousarray(g1, dtype=np.uint64).reshape(8)
+    s = _as_u64(ss, 4, "ss") if len(ss) else np.zeros((0, 4), dtype=np.uint64)
+    k = s.shape[0]
+    handles = np.zeros(k + 1, dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_kzg_setup_eqs_bn254(device, g.ctypes.data, s.ctypes.data if k else None, k, handles.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_kzg_setup_eqs_bn254")
+    return [G1Bases._adopt(h, 1 << i, device) for i, h in enumerate(handles)]
 
 
 def variable_base_msm_many(scalars_list: Sequence, bases_list: Sequence["G1Bases"]) -> np.ndarray:

@@ -5,6 +5,7 @@
 #include "cuda_emul.h"
 
 #include "../../plonkish_b200/csrc/msm_kernels.cuh"
+#include "../../plonkish_b200/csrc/poly_kernels.cuh"
 
 #include <stdlib.h>
 
@@ -121,5 +122,34 @@ int emul_msm_table_chunked(const void *scalars, const void *bases, u32 n_table, 
     memcpy(out_affine64, &out, 64);
     free(arena); free(cur); free(table);
     return 0;
+}
+
+// ---- the callers either side of the MSM (poly_kernels.cuh)
+// quotients: q_out has 2^k scalars (q_i at offset 2^i), eval_out one.
+void emul_quotients(const void *poly, u32 k, const void *point, void *q_out, void *eval_out) {
+    const size_t n = (size_t)1 << k;
+    std::vector<fe> ra(n / 2 + 1), rb(n / 4 + 1);
+    pk_enqueue_quotients(poly, k, point, q_out, ra.data(), rb.data(), eval_out, 4, 0);
+}
+void emul_fr_lincomb(const void *const *polys, const void *coeffs, u32 count, u32 n, void *out) {
+    for (u32 done = 0; done < count; done += PK_LINCOMB_MAX) {
+        LincombArgs a;
+        a.count = count - done < PK_LINCOMB_MAX ? count - done : PK_LINCOMB_MAX;
+        a.accumulate = done ? 1u : 0u;
+        for (u32 i = 0; i < a.count; ++i) {
+            a.poly[i] = (const uint4 *)polys[done + i];
+            memcpy(a.coeff[i].l, (const char *)coeffs + (size_t)(done + i) * 32, 32);
+        }
+        PK_LAUNCH(k_fr_lincomb, dim3(3), dim3(64), 0, 0, a, (size_t)n, (uint4 *)out);
+    }
+}
+void emul_eq_scalars(const void *ss, u32 num_vars, void *out) { pk_enqueue_eq_scalars(ss, num_vars, out, 2, 0); }
+// out[i] = scalars[i] * base through the signed-window table.
+void emul_fixed_base(const void *base64, const void *scalars, u32 n, void *out_affine) {
+    const size_t entries = (size_t)PK_FIXED_W * PK_FIXED_ROW;
+    std::vector<affine> table(entries), offsets(PK_FIXED_W);
+    std::vector<xyzz> tmp(entries > n ? entries : n);
+    pk_enqueue_fixed_table(base64, offsets.data(), tmp.data(), table.data(), 0);
+    pk_enqueue_fixed_base(scalars, n, table.data(), tmp.data(), (affine *)out_affine, 0);
 }
 }
