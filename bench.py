@@ -148,47 +148,118 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------- HyperPlonk::prove MSM-sequence surrogate
+FQ_MODULUS = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+
+
+def g1_generator(np):
+    """(1, 2) as Montgomery limbs, the layout of bn256::G1Affine::generator()."""
+    b = b"".join((v * (1 << 256) % FQ_MODULUS).to_bytes(32, "little") for v in (1, 2))
+    return np.frombuffer(b, dtype=np.uint64).copy()
+
+
 def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
     """The MSM calls HyperPlonk::prove makes for vanilla_plonk at 2^k rows (SURVEY.md §3.1):
     4 commits of 2^k points (3 witness polys + 1 permutation z-poly, backend/hyperplonk.rs:201,
     251-252) and the k quotient commitments of MultilinearKzg::open with 2^(k-1), ..., 2, 1 points
-    (kzg.rs:291-293), each a blocking host-scalar call against the resident eqs[i] slice."""
+    (kzg.rs:291-293) against the resident eqs[i] slices of an SRS built on the device
+    (MultilinearKzg::setup, kzg.rs:167-212).  Two forms:
+      gpu_ms           every call takes host scalars (the drop-in for msm.rs alone; the opened polynomial's
+                       quotients are stand-ins of the right sizes);
+      gpu_resident_ms  the committed polynomials stay in HBM (batch_commit keep), g_prime is merged there
+                       (multilinear.rs:203-213) and open() computes its quotients there (multilinear.rs:72-107):
+                       the same 4 + k commitments plus the real quotient arithmetic, no scalar uploaded twice."""
+    from plonkish_b200 import kzg
+
     n = 1 << k
-    d_bases = pk.synth_bases_device(n, 7, 3, device=dev)
+    ss = pk.random_scalars(k, seed=77)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    regs = [pk.G1Bases(d_bases[: 1 << i].contiguous()) for i in range(k + 1)]
-    torch.cuda.synchronize()
+    pp = kzg.setup(g1_generator(np), ss)
     setup_s = time.perf_counter() - t0
-    host_t = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-    host = host_t.numpy().view(np.uint64)
-    host[:] = pk.random_scalars(n, seed=4242)
+    regs = pp.eqs
+    polys = []
+    for j in range(4):
+        t = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+        h = t.numpy().view(np.uint64)
+        h[:] = pk.random_scalars(n, seed=4242 + j)
+        polys.append(h)
+    host = polys[0]
+    coeffs = pk.random_scalars(4, seed=78)
+    point = pk.random_scalars(k, seed=79)
 
     def run():
         # batch_commit of the 3 witness polynomials (hyperplonk.rs:201), then the z-poly commit (:251)
-        outs = list(pk.variable_base_msm_batch([host, host, host], regs[k])) + [pk.variable_base_msm(host, regs[k])]
+        outs = list(pk.variable_base_msm_batch(polys[:3], regs[k])) + [pk.variable_base_msm(polys[3], regs[k])]
         # open: the k quotient commitments in one call (kzg.rs:291-293), small ones concurrently
         outs += list(pk.variable_base_msm_many([host[: 1 << i] for i in reversed(range(k))], [regs[i] for i in reversed(range(k))]))
         return outs
+
+    def run_resident():
+        c3, r3 = kzg.batch_commit(pp, polys[:3], keep=True)
+        c1, r1 = kzg.batch_commit(pp, polys[3:], keep=True)
+        g_prime = kzg.linear_combination(r3 + r1, coeffs)
+        q_comms, value = kzg.open_resident(pp, g_prime, point)
+        for r in r3 + r1 + [g_prime]:
+            r.release()
+        return list(c3) + list(c1), q_comms, value
 
     run()
     t0 = time.perf_counter()
     outs = run()
     gpu_ms = (time.perf_counter() - t0) * 1e3
-    res = {"k": k, "msm_calls": 4 + k, "points": 4 * n + n - 1, "gpu_ms": gpu_ms, "resident_srs_setup_s": setup_s}
+    run_resident()
+    t0 = time.perf_counter()
+    comms, q_comms, value = run_resident()
+    resident_ms = (time.perf_counter() - t0) * 1e3
+    res = {"k": k, "msm_calls": 4 + k, "points": 4 * n + n - 1, "gpu_ms": gpu_ms, "gpu_resident_ms": resident_ms,
+           "srs_setup_on_device_s": setup_s, "srs_points": 2 * n - 1}
     if cpu:
         from oracle import pyoracle as po
 
         cores = po.host_threads()
-        bases_h = d_bases.cpu().numpy().view(np.uint64)
+        eqs_h = [r.to_host() for r in regs]
         t0 = time.perf_counter()
-        ref = [po.variable_base_msm(host, bases_h, cores) for _ in range(4)]
-        ref += [po.variable_base_msm(host[: 1 << i], bases_h[: 1 << i], cores) for i in reversed(range(k))]
+        ref = [po.variable_base_msm(p, eqs_h[k], cores) for p in polys]
+        t_commit = time.perf_counter() - t0
+        ref_host_open = [po.variable_base_msm(host[: 1 << i], eqs_h[i], cores) for i in reversed(range(k))]
         res["cpu_ms"] = (time.perf_counter() - t0) * 1e3
         res["cpu_cores"] = cores
-        res["bit_exact_vs_cpu"] = bool(all((a == b).all() for a, b in zip(outs, ref)))
-    for r in regs:
-        r.release()
+        res["bit_exact_vs_cpu"] = bool(all((a == b).all() for a, b in zip(outs, ref + ref_host_open)))
+        # the resident form on the CPU: merge, quotients, their commitments (single-threaded field part)
+        t0 = time.perf_counter()
+        g_prime_h = po.fr_linear_combination(polys, coeffs)
+        qs, want_value = po.quotients(g_prime_h, point)
+        ref_q = [po.variable_base_msm(qs[i], eqs_h[i], cores) for i in range(k)]
+        res["cpu_resident_ms"] = (t_commit + time.perf_counter() - t0) * 1e3
+        res["resident_bit_exact_vs_cpu"] = bool(all((a == b).all() for a, b in zip(comms, ref)) and all((a == b).all() for a, b in zip(q_comms, ref_q))
+                                                and (value == want_value).all())
+    pp.release()
+    return res
+
+
+def srs_setup_bench(pk, torch, np, k: int, cpu: bool):
+    """fixed_base_msm + batch_normalize (msm.rs:16-31, 50-81; kzg.rs:195-208) on the GPU: 2^22 scalars host to host, and the
+    CPU port on a bounded sample with the window the reference would pick for a 2^k setup."""
+    n = 1 << 22
+    sc = pk.random_scalars(n, seed=91)
+    g = g1_generator(np)
+    pk.fixed_base_msm(g, sc[: 1 << 16])
+    t0 = time.perf_counter()
+    got = pk.fixed_base_msm(g, sc)
+    sec = time.perf_counter() - t0
+    res = {"what": "fixed_base_msm + batch_normalize of 2^22 scalars, host scalars in, affine points out (table build included)",
+           "gpu_mpoints_per_s": n / sec / 1e6, "gpu_ms": sec * 1e3}
+    if cpu:
+        from oracle import pyoracle as po
+
+        m = 1 << 17
+        window = po.window_size((2 << k) - 2)
+        cores = po.host_threads()
+        t0 = time.perf_counter()
+        want = po.fixed_base_msm(g, sc[:m], window=window, num_threads=cores)
+        sec_c = time.perf_counter() - t0
+        res.update({"cpu_mpoints_per_s": m / sec_c / 1e6, "cpu_cores": cores, "cpu_sample": f"2^17 scalars, window {window} (table build included)",
+                    "bit_exact_vs_cpu": bool((got[:m] == want).all())})
     return res
 
 
@@ -429,13 +500,15 @@ def run_ours(args) -> None:
         del d_scalars, d_bases
         reg.release()
         torch.cuda.empty_cache()
-        seq = {"what": "MSM calls of HyperPlonk::prove for vanilla_plonk (4 x 2^k + 2^(k-1) + ... + 1 points), host scalars, resident SRS; "
-                       "the field-only prover work between the calls stays in the Rust caller and is not included"}
+        seq = {"what": "MSM calls of HyperPlonk::prove for vanilla_plonk (4 x 2^k + 2^(k-1) + ... + 1 points) against an SRS built on the device; "
+                       "gpu_ms: host scalars per call; gpu_resident_ms: polynomials kept in HBM, g_prime merge and quotients on the GPU; "
+                       "sum-check and the other field-only prover work stay in the Rust caller and are not included"}
         seq["k%d" % args.prove_k] = prove_msm_sequence(pk, torch, np, args.prove_k, dev, cpu=False)
         if not args.no_cpu_baseline:
             seq["k20"] = prove_msm_sequence(pk, torch, np, min(20, args.prove_k), dev, cpu=True)
         line["hyperplonk_prove_msm"] = seq
         line["univariate_kzg_k22"] = univariate_sequence(pk, torch, np, 22, dev)
+        line["srs_fixed_base_msm"] = srs_setup_bench(pk, torch, np, args.prove_k, cpu=not args.no_cpu_baseline)
     if rank == 0:
         emit(line)
     if distributed:

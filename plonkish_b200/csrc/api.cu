@@ -115,6 +115,19 @@ static int grow(DeviceBuffer &b, size_t bytes) {
     return 0;
 }
 
+// Resident polynomials come and go once per proof: they are carved from the device's stream-ordered
+// pool (kept warm, see create_ctx_locked) so that neither side synchronises the device the way
+// cudaMalloc / cudaFree do.  Every entry point ends with its streams joined and idle, so a pointer
+// obtained here is usable on all of the context's streams.
+static int pool_alloc(Ctx *c, void **p, size_t bytes) {
+    CUDA_TRY(cudaMallocAsync(p, bytes, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+static void pool_free(Ctx *c, void *p) {
+    if (p && cudaFreeAsync(p, c->stream) != cudaSuccess) cudaGetLastError();
+}
+
 // Contexts are created on first use of a device, so a one-process-per-GPU rank only
 // ever touches its own GPU.  Caller must not hold g_mu.
 static int create_ctx_locked(int device) {
@@ -126,6 +139,12 @@ static int create_ctx_locked(int device) {
     if (prop.major < 10)
         return fail(PLONKISH_CUDA_E_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     c->sm_count = prop.multiProcessorCount;
+    {
+        cudaMemPool_t pool;
+        unsigned long long keep_all = ~0ull;  // freed resident polynomials stay in the pool for the next proof
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->chunk_ready[i], cudaEventDisableTiming));
@@ -488,7 +507,8 @@ extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_pa
 // PCIe).  The points are cut into chunks; chunk k+1 is copied on the copy stream while the
 // compute stream decomposes, sorts and accumulates chunk k into its own bucket array
 // (MsmPlan::chunk); one bucket reduce at the end adds the arrays.
-static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &bases, size_t n, xyzz **d_result) {
+static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &bases, size_t n, xyzz **d_result, void *d_dst = nullptr) {
+    if (!d_dst) d_dst = c->scalars.ptr;  // where the uploaded scalars live (a caller keeping them resident passes its own buffer)
     // Chunk boundaries.  Only the first chunk's copy is exposed, so it is small; later chunks
     // grow (1/8, 3/8, 1/2) and each copies while its predecessor computes.  Measured at 2^24:
     // 53.6 ms unchunked, 51.6 ms for two halves (4- and 8-way equal splits lose to per-chunk costs).
@@ -531,7 +551,7 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
     MsmPlan last = plan0;
     for (size_t k = 0, done = 0; k < nchunks; done = cuts[k], ++k) {
         const size_t cnt = cuts[k] - done;
-        char *d_chunk = (char *)c->scalars.ptr + done * PLONKISH_CUDA_SCALAR_BYTES;
+        char *d_chunk = (char *)d_dst + done * PLONKISH_CUDA_SCALAR_BYTES;
         cudaStream_t cs = (nchunks > 1) ? c->copy_stream : c->stream;
         CUDA_TRY(cudaMemcpyAsync(d_chunk, (const char *)h_scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES,
                                  cudaMemcpyHostToDevice, cs));
@@ -627,8 +647,8 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     std::vector<void *> kept(count, nullptr);
     if (keep) {
         for (size_t j = 0; j < count; ++j) {
-            if (cudaMalloc(&kept[j], bytes) != cudaSuccess) {
-                for (size_t i = 0; i < j; ++i) cudaFree(kept[i]);
+            if (pool_alloc(c, &kept[j], bytes) != 0) {
+                for (size_t i = 0; i < j; ++i) pool_free(c, kept[i]);
                 return fail(PLONKISH_CUDA_E_CUDA, "msm_batch: cannot keep %zu x %zu bytes of scalars resident", count, bytes);
             }
         }
@@ -637,13 +657,20 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     }
     if ((rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES))) return rc;
     MsmPlan plan = plan_for(c, view, n, 0);
-    if ((rc = grow(c->arena, pk_workspace_bytes(plan)))) return rc;
-    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    if ((rc = grow(c->arena, pk_workspace_bytes(plan)))) return rc;  // before anything is in flight: growing synchronises
+    void *bufs[2] = {c->scalars.ptr, c->scalars2.ptr};
+    // MSM 0: nothing to hide its upload behind, so it goes up in growing chunks, each copying
+    // while its predecessor computes (enqueue_host_msm); sizes the arena for the chunked layout.
+    {
+        xyzz *res0 = nullptr;
+        if ((rc = enqueue_host_msm(c, scalars_list[0], view, n, &res0, keep ? kept[0] : bufs[0]))) return rc;
+        PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res0, 1u, (affine *)c->batch_out.ptr, (xyzz *)nullptr);
+        CUDA_TRY(cudaEventRecord(c->buf_free[0], c->stream));
+    }
     MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
     ws.result = (xyzz *)((char *)c->d_out + 256);
-    void *bufs[2] = {c->scalars.ptr, c->scalars2.ptr};
-    if (c->has_last && !keep) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->last_done, 0));  // staging buffers may still be read
-    for (size_t j = 0; j < count; ++j) {
+    // MSM j >= 1: its upload runs on the copy stream while MSM j-1 computes
+    for (size_t j = 1; j < count; ++j) {
         const int b = (int)(j & 1);
         void *dst = keep ? kept[j] : bufs[b];
         if (j >= 2 && !keep) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->buf_free[b], 0));  // MSM j-2 has consumed this buffer
@@ -1537,7 +1564,8 @@ extern "C" int plonkish_cuda_scalars_register(int device, const void *scalars, s
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
     void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_SCALAR_BYTES));
+    int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(d, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *handle = publish_scalars(device, d, n);
@@ -1553,9 +1581,11 @@ extern "C" int plonkish_cuda_scalars_release(uint64_t handle) {
         e = it->second;
         g_scalars.erase(it);
     }
-    CUDA_TRY(cudaSetDevice(e.dev));
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaFree(e.d_ptr));
+    Ctx *c = ctx_for(e.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "scalars_release: device %d not initialised", e.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    pool_free(c, e.d_ptr);  // ordered after everything enqueued on the context's stream
     return PLONKISH_CUDA_OK;
 }
 
@@ -1630,7 +1660,8 @@ extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handl
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
     void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_SCALAR_BYTES));
+    int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)c->sm_count * 8) blocks = (size_t)c->sm_count * 8;
     for (size_t done = 0; done < count; done += PK_LINCOMB_MAX) {
