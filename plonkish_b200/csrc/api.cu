@@ -251,7 +251,11 @@ static int make_resident(Ctx *c, const void *src, bool src_is_device, size_t n, 
     if (src_is_device) CUDA_TRY(cudaDeviceSynchronize());
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     bool want_table = (mode == 2) || (mode == 0 && precompute_enabled());
-    const uint32_t tc = pk_table_window_bits((u32)(n > 0xffffffffull ? 0xffffffffull : n));
+    uint32_t tc = pk_table_window_bits((u32)(n > 0xffffffffull ? 0xffffffffull : n));
+    if (const char *e = getenv("PLONKISH_CUDA_TABLE_C")) {  // tuning override: window bits of the table
+        const long v = atol(e);
+        if (v >= 8 && v <= 22) tc = (uint32_t)v;
+    }
     const uint32_t tw = pk_windows_for(tc);
     const size_t table_bytes = (size_t)tw * n * PLONKISH_CUDA_AFFINE_BYTES, cur_bytes = n * sizeof(xyzz);
     if (want_table) {

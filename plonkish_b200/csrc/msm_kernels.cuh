@@ -107,6 +107,22 @@ inline u32 pk_default_window_bits(u32 n) {
     return 8;
 }
 
+// Bucket reduce geometry: thread j owns buckets [j*rb, (j+1)*rb) of a group.  Every thread pays a
+// fixed ~400 field products (its small scalar multiplication and the warp sum) on top of 28 per
+// bucket, so rb grows with the bucket count until the groups together fill the GPU with about two
+// warps per scheduler; rb need not divide B (the last thread's range is cut).
+#define PK_RED_BLOCK 128
+inline void pk_plan_reduce(MsmPlan &p, u32 sm_count) {
+    const unsigned long long target = (unsigned long long)sm_count * 4ull * 32ull * 2ull;  // threads over all groups
+    const unsigned long long groups = p.ngroups ? p.ngroups : 1;
+    unsigned long long rb = ((unsigned long long)p.B * groups + target - 1) / target;
+    if (rb < 8) rb = 8;
+    if (rb > p.B) rb = p.B;
+    p.rb = (u32)rb;
+    p.red_threads = (p.B + p.rb - 1) / p.rb;
+    p.red_blocks = (p.red_threads + PK_RED_BLOCK - 1) / PK_RED_BLOCK;
+}
+
 inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     MsmPlan p;
     p.n = n;
@@ -140,9 +156,8 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     // one warp -> a 32-thread terminal launch; otherwise whole 128-thread blocks
     p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
     p.blk_acc = (t1 <= 32) ? 32u : 128u;
-    p.rb = p.B < 8 ? p.B : 8;
-    p.red_threads = p.B / p.rb;
-    p.red_blocks = (p.red_threads + 255) / 256;
+    p.ngroups = p.W;
+    pk_plan_reduce(p, sm_count);
     p.blk = 256;
     p.serial_items = 8192;
     p.blk_stage = 512;
@@ -155,10 +170,12 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
 }
 
 // Window width used when a resident base slice of n_registered points is expanded
-// into its table of window multiples: buckets (2^(c-1), one set) stay ~1/32 of the
-// adds (n * W).
+// into its table of window multiples.  One bucket set serves all windows, so the reduce
+// costs ~30-40 field products per bucket against 10 per (point, window) in the accumulate:
+// measured on B200 (tools/table_c_sweep.py, 2^16..2^24) the total is flat or best at
+// c = log2(n) - 1 (n/4 buckets, ~50 entries per bucket), capped at 22 by the sort's digit widths.
 inline u32 pk_table_window_bits(u32 n_registered) {
-    int c = (int)pk_ceil_log2(n_registered < 2 ? 2 : n_registered) - 4;
+    int c = (int)pk_ceil_log2(n_registered < 2 ? 2 : n_registered) - 1;
     if (c < 8) c = 8;
     if (c > 22) c = 22;
     return (u32)c;
@@ -194,9 +211,7 @@ inline MsmPlan pk_make_plan_b(u32 n, u32 c, u32 stride, u32 sm_count) {
     unsigned long long t1 = (emax + L - 1) / L;
     p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
     p.blk_acc = (t1 <= 32) ? 32u : 128u;
-    p.rb = p.B < 8 ? p.B : 8;
-    p.red_threads = p.B / p.rb;
-    p.red_blocks = (p.red_threads + 255) / 256;
+    pk_plan_reduce(p, sm_count);
     return p;
 }
 
@@ -206,6 +221,7 @@ struct MsmWorkspace {
     u32 *tile_hist;     // [ntiles][nbins]
     u32 *bin_total;     // [nbins]
     u32 *bin_start;     // [nbins + 1]
+    u32 *slice_prefix;  // [nbins + 1] mode 1: first level-2 slice of every bin
     u32 *l1;            // [n * W] entries after the bin scatter (mode 1: u64 entries)
     u32 *sorted;        // [n * W] (sign << 31 | point index), ordered by (window, bucket)
     u32 *bucket_start;  // [nbuckets + 1]
@@ -234,7 +250,7 @@ inline size_t pk_workspace_bytes(const MsmPlan &p) {
     s += pk_align256(sizeof(xyzz) * 32);
     s += pk_align256(sizeof(xyzz));
     s += pk_align256(sizeof(u32) * p.nbins);
-    s += pk_align256(sizeof(u32) * (p.nbins + 1));
+    s += 2 * pk_align256(sizeof(u32) * (p.nbins + 1));
     s += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
     s += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
     s += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
@@ -258,6 +274,7 @@ inline MsmWorkspace pk_carve_workspace(const MsmPlan &p, void *arena) {
     w.result = (xyzz *)q; q += pk_align256(sizeof(xyzz));
     w.bin_total = (u32 *)q; q += pk_align256(sizeof(u32) * p.nbins);
     w.bin_start = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbins + 1));
+    w.slice_prefix = (u32 *)q; q += pk_align256(sizeof(u32) * (p.nbins + 1));
     w.digits = (u16 *)q; q += pk_align256((p.mode ? sizeof(u32) : sizeof(u16)) * (size_t)p.W * p.n_pad);
     w.tile_hist = (u32 *)q; q += pk_align256(sizeof(u32) * (size_t)p.ntiles * p.nbins);
     w.l1 = (u32 *)q; q += pk_align256((p.mode ? sizeof(unsigned long long) : sizeof(u32)) * e);
@@ -681,31 +698,57 @@ __global__ void __launch_bounds__(512) k_scatter_staged_b(const u32 *__restrict_
     }
 }
 
-// Level 2 histogram: grid (nbins, nslices).  Block (bin, s) counts the low bucket bits of
-// slices s, s + nslices, ... of its bin and adds them to the global per-bucket counts.
+// Level 2 works on slices of <= `slice` consecutive entries of one bin.  The slices of all bins are
+// numbered consecutively (slice_prefix[bin] = number of the bin's first slice) and block b takes
+// slice b, so a bin that holds far more than its share (a short top window, skewed scalars) is
+// spread over as many blocks as it has slices.
+__global__ void __launch_bounds__(1024) k_slice_prefix(const u32 *__restrict__ bin_start, u32 nbins, u32 slice, u32 *__restrict__ slice_prefix) {
+    __shared__ u32 cnt[1024];
+    __shared__ u32 start[1024];
+    __shared__ u32 scratch[64];
+    for (u32 b = threadIdx.x; b < 1024; b += blockDim.x) cnt[b] = (b < nbins) ? (bin_start[b + 1] - bin_start[b] + slice - 1) / slice : 0u;
+    __syncthreads();
+    const u32 total = block_exclusive_scan(cnt, start, 1024, scratch);
+    for (u32 b = threadIdx.x; b < nbins; b += blockDim.x) slice_prefix[b] = start[b];
+    if (threadIdx.x == 0) slice_prefix[nbins] = total;
+}
+// The (bin, entry range) of slice number b; false when b is past the last slice.
+PK_HD bool slice_of_block(const u32 *__restrict__ slice_prefix, const u32 *__restrict__ bin_start, u32 nbins, u32 slice, u32 b, u32 &bin, u32 &sb,
+                          u32 &se) {
+    if (b >= slice_prefix[nbins]) return false;
+    u32 lo = 0, hi = nbins;  // last bin with slice_prefix[bin] <= b (empty bins repeat the value: take the last)
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (slice_prefix[mid] <= b) lo = mid; else hi = mid;
+    }
+    bin = lo;
+    const u32 end = bin_start[bin + 1];
+    sb = bin_start[bin] + (b - slice_prefix[bin]) * slice;
+    se = (sb + slice < end) ? sb + slice : end;
+    return true;
+}
+
+// Level 2 histogram: block b counts the low bucket bits of slice b and adds them to the global
+// per-bucket counts.
 __global__ void __launch_bounds__(256) k_bucket_hist_b(const u16 *__restrict__ l1_key, MsmPlan p, const u32 *__restrict__ bin_start,
-                                                       u32 slice, u32 *__restrict__ bucket_cnt) {
+                                                       const u32 *__restrict__ slice_prefix, u32 slice, u32 *__restrict__ bucket_cnt) {
     __shared__ u32 cnt[4096];
-    const u32 bin = blockIdx.x;
-    const u32 beg = bin_start[bin], end = bin_start[bin + 1];
-    if (beg + blockIdx.y * slice >= end) return;
+    u32 bin, sb, se;
+    if (!slice_of_block(slice_prefix, bin_start, p.nbins, slice, blockIdx.x, bin, sb, se)) return;
     const u32 nlo = 1u << p.lo_bits;
     for (u32 k = threadIdx.x; k < nlo; k += blockDim.x) cnt[k] = 0;
     __syncthreads();
     constexpr int U = 8;
-    for (u32 sb = beg + blockIdx.y * slice; sb < end; sb += gridDim.y * slice) {
-        const u32 se = (sb + slice < end) ? sb + slice : end;
-        for (u32 q0 = sb + threadIdx.x; q0 < se; q0 += blockDim.x * U) {
-            u32 k[U];
+    for (u32 q0 = sb + threadIdx.x; q0 < se; q0 += blockDim.x * U) {
+        u32 k[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const u32 q = q0 + (u32)u * blockDim.x;
-                k[u] = (q < se) ? (u32)l1_key[q] : 0xffffffffu;
-            }
+        for (int u = 0; u < U; ++u) {
+            const u32 q = q0 + (u32)u * blockDim.x;
+            k[u] = (q < se) ? (u32)l1_key[q] : 0xffffffffu;
+        }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (k[u] != 0xffffffffu) atomicAdd(&cnt[k[u]], 1u);
-            }
+        for (int u = 0; u < U; ++u) {
+            if (k[u] != 0xffffffffu) atomicAdd(&cnt[k[u]], 1u);
         }
     }
     __syncthreads();
@@ -798,33 +841,29 @@ __global__ void __launch_bounds__(1024) k_scan_apply(u32 *__restrict__ v, u32 n,
 // Level 2 scatter: same slicing as the histogram; partitions each slice by the low bucket
 // bits into the final (window-free) order.  gcursor = per-bucket cursors (bucket starts).
 __global__ void __launch_bounds__(512) k_bucket_scatter_staged_b(const u32 *__restrict__ l1_val, const u16 *__restrict__ l1_key, MsmPlan p,
-                                                                 const u32 *__restrict__ bin_start, u32 slice, u32 *__restrict__ gcursor,
-                                                                 u32 *__restrict__ sorted) {
+                                                                 const u32 *__restrict__ bin_start, const u32 *__restrict__ slice_prefix, u32 slice,
+                                                                 u32 *__restrict__ gcursor, u32 *__restrict__ sorted) {
     PK_DYN_SMEM(u32, smem);
-    const u32 bin = blockIdx.x;
-    const u32 beg = bin_start[bin], end = bin_start[bin + 1];
-    if (beg + blockIdx.y * slice >= end) return;
+    u32 bin, sb, se;
+    if (!slice_of_block(slice_prefix, bin_start, p.nbins, slice, blockIdx.x, bin, sb, se)) return;
     const u32 nlo = 1u << p.lo_bits;
     const u32 S = blockDim.x * PK_STAGE_EPT;
     const StageSmem m = stage_carve(smem, nlo, S);
     for (u32 d = threadIdx.x; d < nlo; d += blockDim.x) m.lcnt[d] = 0;
     __syncthreads();
     u32 *cur = gcursor + (size_t)bin * nlo;
-    for (u32 sb = beg + blockIdx.y * slice; sb < end; sb += gridDim.y * slice) {
-        const u32 se = (sb + slice < end) ? sb + slice : end;
-        for (u32 s0 = sb; s0 < se; s0 += S) {
-            u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
-            bool ok[PK_STAGE_EPT];
+    for (u32 s0 = sb; s0 < se; s0 += S) {
+        u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
+        bool ok[PK_STAGE_EPT];
 #pragma unroll
-            for (int e = 0; e < PK_STAGE_EPT; ++e) {
-                const u32 q = s0 + threadIdx.x + (u32)e * blockDim.x;
-                ok[e] = q < se;
-                dig[e] = ok[e] ? (u32)l1_key[q] : 0u;
-                val[e] = ok[e] ? l1_val[q] : 0u;
-                aux[e] = 0;
-            }
-            staged_partition<PK_STAGE_EPT>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr);
+        for (int e = 0; e < PK_STAGE_EPT; ++e) {
+            const u32 q = s0 + threadIdx.x + (u32)e * blockDim.x;
+            ok[e] = q < se;
+            dig[e] = ok[e] ? (u32)l1_key[q] : 0u;
+            val[e] = ok[e] ? l1_val[q] : 0u;
+            aux[e] = 0;
         }
+        staged_partition<PK_STAGE_EPT>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr);
     }
 }
 
@@ -1071,16 +1110,18 @@ PK_HD xyzz xyzz_mul_small(const xyzz &pnt, u32 k) {
 // grid (red_blocks, W), block 256.  Thread j of window w owns buckets
 // [j*rb, (j+1)*rb): sum_i (j*rb + i + 1) * B_i = acc + (j*rb) * run, where run is
 // the plain sum and acc the running-sum total (msm.rs:175-179 restated per chunk).
-__global__ void __launch_bounds__(256, 2) k_bucket_reduce(const xyzz *__restrict__ bucket_sum,
-                                                       MsmPlan p, xyzz *__restrict__ block_out) {
-    __shared__ xyzz warp_part[8];
+__global__ void __launch_bounds__(PK_RED_BLOCK, 4) k_bucket_reduce(const xyzz *__restrict__ bucket_sum,
+                                                                MsmPlan p, xyzz *__restrict__ block_out) {
+    __shared__ xyzz warp_part[PK_RED_BLOCK / 32];
     const u32 w = blockIdx.y;
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     xyzz contrib = xyzz_identity();
     if (j < p.red_threads) {
         xyzz run = xyzz_identity(), acc = xyzz_identity();
-        for (int i = (int)p.rb - 1; i >= 0; --i) {
-            const u32 g = w * p.B + j * p.rb + (u32)i;
+        const u32 first = j * p.rb;
+        const u32 cnt = (first + p.rb <= p.B) ? p.rb : p.B - first;  // the last thread's range may be short
+        for (int i = (int)cnt - 1; i >= 0; --i) {
+            const u32 g = w * p.B + first + (u32)i;
             for (u32 k = 0; k < p.nchunks; ++k)  // untouched buckets are zeroed = identity
                 run = xyzz_add(run, load_xyzz(bucket_sum + (size_t)k * p.nbuckets + g));
             acc = xyzz_add(acc, run);
@@ -1217,13 +1258,15 @@ inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void
         PK_SET_SMEM(k_scatter_staged_b, smem1);
         PK_LAUNCH(k_scatter_staged_b, dim3(p.ntiles), dim3(p.blk_stage), smem1, stream, digits32, p, ws.bin_total, l1_val, l1_key);
         PK_MARK(marks, 3, stream);
-        const u32 slice = 4 * S, nslices = 8;
-        PK_LAUNCH(k_bucket_hist_b, dim3(p.nbins, nslices), dim3(p.blk), 0, stream, l1_key, p, ws.bin_start, slice, ws.bucket_cur);
+        const u32 slice = 4 * S;
+        const u32 max_slices = (u32)((emax + slice - 1) / slice) + p.nbins;  // every bin may end in a partial slice
+        PK_LAUNCH(k_slice_prefix, dim3(1), dim3(1024), 0, stream, ws.bin_start, p.nbins, slice, ws.slice_prefix);
+        PK_LAUNCH(k_bucket_hist_b, dim3(max_slices), dim3(p.blk), 0, stream, l1_key, p, ws.bin_start, ws.slice_prefix, slice, ws.bucket_cur);
         pk_enqueue_scan(ws.bucket_cur, p.nbuckets, ws.bucket_start, ws.scan_tmp, stream);
         const size_t smem2 = stage_smem_bytes(1u << p.lo_bits, S);
         PK_SET_SMEM(k_bucket_scatter_staged_b, smem2);
-        PK_LAUNCH(k_bucket_scatter_staged_b, dim3(p.nbins, nslices), dim3(p.blk_stage), smem2, stream, l1_val, l1_key, p, ws.bin_start, slice,
-                  ws.bucket_cur, ws.sorted);
+        PK_LAUNCH(k_bucket_scatter_staged_b, dim3(max_slices), dim3(p.blk_stage), smem2, stream, l1_val, l1_key, p, ws.bin_start, ws.slice_prefix,
+                  slice, ws.bucket_cur, ws.sorted);
         PK_MARK(marks, 4, stream);
     }
 
@@ -1251,7 +1294,7 @@ inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void
 // (plus *prev if given).
 inline void pk_enqueue_reduce(const MsmPlan &p, const MsmWorkspace &ws, const xyzz *prev, pk_stream_t stream,
                               const StageMarks *marks = nullptr) {
-    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.ngroups), dim3(256), 0, stream, ws.bucket_sum, p, ws.block_out);
+    PK_LAUNCH(k_bucket_reduce, dim3(p.red_blocks, p.ngroups), dim3(PK_RED_BLOCK), 0, stream, ws.bucket_sum, p, ws.block_out);
     PK_MARK(marks, 7, stream);
     PK_LAUNCH(k_window_weight, dim3(p.ngroups), dim3(32), 0, stream, ws.block_out, p, ws.win_out);
     PK_LAUNCH(k_window_sum, dim3(1), dim3(32), 0, stream, ws.win_out, p.ngroups, prev, ws.result);
