@@ -1472,6 +1472,8 @@ __global__ void k_debug_field(int op, const fe *a, const fe *b, fe *out, u32 n) 
         case 4: r = fq_inv(a[i]); break;
         case 5: r = mont_mul<FrMod>(a[i], b[i]); break;
         case 7: r = fq_inv_fast(a[i]); break;
+        case 8: r = fq_mul_sum(a[i], b[i], b[i], a[(i + 1) % n]); break;        // a*b + b*a'  (a' = next element of a)
+        case 9: r = mont_mul_sum<FrMod>(a[i], a[i], b[i], b[(i + 1) % n]); break;  // Fr: a^2 + b*b'
         default: r = fq_neg(a[i]); break;
     }
     out[i] = r;

@@ -280,7 +280,59 @@ PK_HD fe mont_mul(const fe &a, const fe &b) {
     return r;
 }
 
+// (a*b + c*d) / 2^256 mod m with ONE reduction: every row adds both partial products before
+// the m*q step, 200 multiply instructions instead of 272 for two products and an addition.
+// Bounds: T_{i+1} < T_i / 2^32 + (a + c + m)(1 - 2^-32) keeps T < 3m - 3 < 2^256 for a, c < m, so
+// the accumulators never carry out of their top pairs (3 * m7 * 2^32 < 2^64 for both moduli) and
+// two conditional subtractions finish.
+template <class MOD>
+PK_HD fe mont_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) {
+    u32 m[8];
+    MOD::limbs(m);
+    u32 ev[8], od[8];
+    {
+        const u32 y = b.l[0], z = d.l[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u64 pe = (u64)a.l[2 * k] * y, po = (u64)a.l[2 * k + 1] * y;
+            ev[2 * k] = (u32)pe; ev[2 * k + 1] = (u32)(pe >> 32);
+            od[2 * k] = (u32)po; od[2 * k + 1] = (u32)(po >> 32);
+        }
+        cmad8(od, c.l[1], c.l[3], c.l[5], c.l[7], z);
+        od[7] += cmad8(ev, c.l[0], c.l[2], c.l[4], c.l[6], z);
+        const u32 q = ev[0] * MOD::inv();
+        cmad8(od, m[1], m[3], m[5], m[7], q);
+        od[7] += cmad8(ev, m[0], m[2], m[4], m[6], q);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        u32 *E = (i & 1) ? od : ev;
+        u32 *O = (i & 1) ? ev : od;
+        const u32 y = b.l[i], z = d.l[i];
+        shift_mad8(E[0], O[1], O, a.l[1], a.l[3], a.l[5], a.l[7], y);
+        O[7] += cmad8(E, a.l[0], a.l[2], a.l[4], a.l[6], y);
+        cmad8(O, c.l[1], c.l[3], c.l[5], c.l[7], z);
+        O[7] += cmad8(E, c.l[0], c.l[2], c.l[4], c.l[6], z);
+        const u32 q = E[0] * MOD::inv();
+        cmad8(O, m[1], m[3], m[5], m[7], q);
+        O[7] += cmad8(E, m[0], m[2], m[4], m[6], q);
+    }
+    fe r;
+    {
+        u32 sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sh[k] = od[k + 1];
+        sh[7] = 0;
+        add8(r.l, ev, sh);
+    }
+    final_sub<MOD>(r.l);
+    final_sub<MOD>(r.l);
+    return r;
+}
+
 PK_HD fe fq_mul(const fe &a, const fe &b) { return mont_mul<FqMod>(a, b); }
+// a*b + c*d (Montgomery), one reduction
+PK_HD fe fq_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) { return mont_mul_sum<FqMod>(a, b, c, d); }
 PK_HD fe fq_sqr(const fe &a) { return mont_mul<FqMod>(a, a); }
 
 template <class MOD>

@@ -24,17 +24,22 @@ namespace pk {
 // instructions) thrash the instruction cache.
 struct MulInline {
     static PK_HD fe mul(const fe &a, const fe &b) { return fq_mul(a, b); }
+    static PK_HD fe mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) { return fq_mul_sum(a, b, c, d); }
 };
 #if !defined(PLONKISH_EMUL)
 __device__ __noinline__ fe fq_mul_call(fe a, fe b) { return mont_mul<FqMod>(a, b); }
+__device__ __noinline__ fe fq_mul_sum_call(fe a, fe b, fe c, fe d) { return mont_mul_sum<FqMod>(a, b, c, d); }
 struct MulCall {
     static PK_HD fe mul(const fe &a, const fe &b) { return fq_mul_call(a, b); }
+    static PK_HD fe mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) { return fq_mul_sum_call(a, b, c, d); }
 };
 #else
 typedef MulInline MulCall;
 #endif
 #define PK_MUL(a, b) M::mul(a, b)
 #define PK_SQR(a) M::mul(a, a)
+// a*b - c*d with one Montgomery reduction (the y-coordinate of every formula below)
+#define PK_MUL_DIFF(a, b, c, d) M::mul_sum(a, b, fq_neg(c), d)
 
 struct affine {  // 64 B, (0,0) = identity — the layout of halo2_curves G1Affine [ext]
     fe x, y;
@@ -69,7 +74,7 @@ PK_HD xyzz xyzz_double_affine(const affine &p) {
     fe xx = PK_SQR(p.x);
     fe m = fq_add(fq_dbl(xx), xx);
     r.x = fq_sub(PK_SQR(m), fq_dbl(s));
-    r.y = fq_sub(PK_MUL(m, fq_sub(s, r.x)), PK_MUL(w, p.y));
+    r.y = PK_MUL_DIFF(m, fq_sub(s, r.x), w, p.y);
     r.zz = v;
     r.zzz = w;
     return r;
@@ -87,7 +92,7 @@ PK_HD xyzz xyzz_double(const xyzz &p) {
     fe xx = PK_SQR(p.x);
     fe m = fq_add(fq_dbl(xx), xx);
     r.x = fq_sub(PK_SQR(m), fq_dbl(s));
-    r.y = fq_sub(PK_MUL(m, fq_sub(s, r.x)), PK_MUL(w, p.y));
+    r.y = PK_MUL_DIFF(m, fq_sub(s, r.x), w, p.y);
     r.zz = PK_MUL(v, p.zz);
     r.zzz = PK_MUL(w, p.zzz);
     return r;
@@ -119,7 +124,7 @@ PK_HD void xyzz_madd(xyzz &acc, const fe &x2, const fe &y2) {
     fe ppp = PK_MUL(p, pp);
     fe q = PK_MUL(acc.x, pp);
     fe x3 = fq_sub(fq_sub(PK_SQR(r), ppp), fq_dbl(q));
-    fe y3 = fq_sub(PK_MUL(r, fq_sub(q, x3)), PK_MUL(acc.y, ppp));
+    fe y3 = PK_MUL_DIFF(r, fq_sub(q, x3), acc.y, ppp);
     acc.x = x3;
     acc.y = y3;
     acc.zz = PK_MUL(acc.zz, pp);
@@ -146,7 +151,7 @@ PK_HD xyzz xyzz_add(const xyzz &a, const xyzz &b) {
     fe q = PK_MUL(u1, pp);
     xyzz o;
     o.x = fq_sub(fq_sub(PK_SQR(r), ppp), fq_dbl(q));
-    o.y = fq_sub(PK_MUL(r, fq_sub(q, o.x)), PK_MUL(s1, ppp));
+    o.y = PK_MUL_DIFF(r, fq_sub(q, o.x), s1, ppp);
     o.zz = PK_MUL(PK_MUL(a.zz, b.zz), pp);
     o.zzz = PK_MUL(PK_MUL(a.zzz, b.zzz), ppp);
     return o;
@@ -168,5 +173,6 @@ PK_HD affine xyzz_to_affine(const xyzz &p) {
 
 #undef PK_MUL
 #undef PK_SQR
+#undef PK_MUL_DIFF
 
 }  // namespace pk

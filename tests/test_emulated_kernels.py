@@ -24,6 +24,7 @@ def emul():
     lib.emul_msm.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp, vp]
     lib.emul_fq_mul.argtypes = [vp, vp, vp]
     lib.emul_fr_to_canonical.argtypes = [vp, vp]
+    lib.emul_fq_mul_sum.argtypes = [vp, vp, vp, vp, vp]
     lib.emul_plan.argtypes = [u32, u32, u32, vp]
     lib.emul_msm_table.argtypes = [vp, vp, u32, u32, u32, u32, vp]
 
@@ -67,6 +68,24 @@ def test_field_restatement(emul):
         out = np.zeros(8, dtype=np.uint32)
         emul.emul_fr_to_canonical(la.ctypes.data, out.ctypes.data)
         assert int.from_bytes(out.tobytes(), "little") == v
+
+
+def test_fused_two_product_reduction(emul):
+    # (a*b + c*d)/R mod p with one reduction: the y-coordinate form of every point formula.  Extremes
+    # (all operands p-1, limbs of all ones below p) exercise the 3p bound of the running value.
+    rng = np.random.default_rng(6)
+    rinv = pow(br.MONT, -1, br.P)
+    top = (br.P >> 224 << 224) - 1  # largest value below p whose low 7 limbs are all ones
+    edge = [0, 1, br.P - 1, br.P - 2, top, (1 << 224) - 1, (1 << 253) + ((1 << 32) - 1)]
+    vals = edge + [int.from_bytes(rng.bytes(32), "little") % br.P for _ in range(12)]
+    limbs = lambda v: np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint32).copy()
+    out = np.zeros(8, dtype=np.uint32)
+    for a in vals:
+        for b in edge + vals[-3:]:
+            for c, d in [(a, b), (br.P - 1, br.P - 1), (top, top), (vals[-1], 0), (b, a), (vals[-2], vals[-4])]:
+                la, lb, lc, ld = limbs(a), limbs(b), limbs(c), limbs(d)  # keep the arrays alive across the call
+                emul.emul_fq_mul_sum(la.ctypes.data, lb.ctypes.data, lc.ctypes.data, ld.ctypes.data, out.ctypes.data)
+                assert int.from_bytes(out.tobytes(), "little") == (a * b + c * d) * rinv % br.P, (a, b, c, d)
 
 
 def test_plan_invariants(emul):

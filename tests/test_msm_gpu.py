@@ -56,6 +56,20 @@ def test_ptx_field_arithmetic_matches_python_ints(pk):
     assert _ints(_field_op(pk, 1, _limbs32(a), _limbs32(b))) == [(x + y) % br.P for x, y in zip(a, b)]
     assert _ints(_field_op(pk, 2, _limbs32(a), _limbs32(b))) == [(x - y) % br.P for x, y in zip(a, b)]
     assert _ints(_field_op(pk, 6, _limbs32(a))) == [(-x) % br.P for x in a]
+    # fused a*b + c*d with one reduction (ops 8, 9), extremes included: every operand p-1 / r-1
+    for op, mod in ((8, br.P), (9, br.R)):
+        top = (mod >> 224 << 224) - 1
+        edge = [0, 1, mod - 1, mod - 2, top, (1 << 224) - 1, mod - 1, mod - 1]
+        x = edge + [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(3000)]
+        y = [mod - 1, mod - 1, mod - 1, top, top, 1, 0, mod - 2] + [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(3000)]
+        rinv = pow(br.MONT, -1, mod)
+        got = _ints(_field_op(pk, op, _limbs32(x), _limbs32(y)))
+        n = len(x)
+        if op == 8:
+            want = [(x[i] * y[i] + y[i] * x[(i + 1) % n]) * rinv % mod for i in range(n)]
+        else:
+            want = [(x[i] * x[i] + y[i] * y[(i + 1) % n]) * rinv % mod for i in range(n)]
+        assert got == want
     # Fr Montgomery -> canonical (halo2_curves to_repr at msm.rs:153)
     ks = [0, 1, br.R - 1, (br.R - 1) // 2] + [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(500)]
     mont = np.frombuffer(b"".join(br.scalar_to_bytes(k) for k in ks), dtype=np.uint64).reshape(-1, 4)
