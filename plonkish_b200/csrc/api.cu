@@ -514,15 +514,28 @@ extern "C" int plonkish_cuda_g1_sum_partials_device(int device, const void *d_pa
 static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &bases, size_t n, xyzz **d_result, void *d_dst = nullptr) {
     if (!d_dst) d_dst = c->scalars.ptr;  // where the uploaded scalars live (a caller keeping them resident passes its own buffer)
     // Chunk boundaries.  Only the first chunk's copy is exposed, so it is small; later chunks
-    // grow (1/8, 3/8, 1/2) and each copies while its predecessor computes.  Measured at 2^24:
-    // 53.6 ms unchunked, 51.6 ms for two halves (4- and 8-way equal splits lose to per-chunk costs).
+    // grow (1/16, 1/4, 11/16 at n >= 2^23; 1/4, 3/4 from 2^20) and each copies while its predecessor
+    // computes.  Measured (tools/e2e_chunks.py): 2^24 48.4 ms unchunked, 42.8 ms chunked (38.5 ms with
+    // the scalars already resident); 2^22 14.0 -> 13.1 ms; equal 4- and 8-way splits lose to per-chunk costs.
     std::vector<size_t> cuts;  // chunk end offsets
     const char *env = getenv("PLONKISH_CUDA_HOST_CHUNKS");  // tuning override: N equal chunks
     const long forced = env ? atol(env) : 0;
-    if (forced >= 1 && forced <= 16) {
+    const char *env_cuts = getenv("PLONKISH_CUDA_HOST_CUTS");  // tuning override: chunk ends as fractions, e.g. "0.25,1"
+    if (env_cuts && n >= ((size_t)1 << 20) && n <= MAX_POINTS_PER_LAUNCH) {
+        for (const char *q = env_cuts; *q;) {
+            char *e = nullptr;
+            const double fr = strtod(q, &e);
+            if (e == q) break;
+            if (fr > 0 && fr <= 1.0) cuts.push_back((size_t)((double)n * fr));
+            q = (*e == ',') ? e + 1 : e;
+        }
+        if (cuts.empty() || cuts.back() != n) cuts.push_back(n);
+    } else if (forced >= 1 && forced <= 16) {
         for (long k = 1; k <= forced; ++k) cuts.push_back(n * (size_t)k / (size_t)forced);
     } else if (n >= ((size_t)1 << 23) && n <= MAX_POINTS_PER_LAUNCH) {
-        cuts = {n / 8, n / 2, n};
+        cuts = {n / 16, 5 * (n / 16), n};
+    } else if (n >= ((size_t)1 << 20) && n <= MAX_POINTS_PER_LAUNCH) {
+        cuts = {n / 4, n};
     } else {
         const size_t pieces = (n + MAX_POINTS_PER_LAUNCH - 1) / MAX_POINTS_PER_LAUNCH;
         for (size_t k = 1; k <= pieces; ++k) cuts.push_back(n * k / pieces);

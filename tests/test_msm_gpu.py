@@ -275,10 +275,10 @@ def test_table_at_2pow22_known_discrete_log(pk, oracle):
     reg.release()
 
 
-@pytest.mark.parametrize("n", [(1 << 22) + 5, 1 << 23])
+@pytest.mark.parametrize("n", [(1 << 20) + 3, (1 << 22) + 5, 1 << 23])
 def test_host_path_chunk_pipeline(pk, oracle, n):
-    # Host scalars at 2^23 and above are copied in chunks that overlap with compute; every
-    # chunk fills its own bucket array and one reduce adds them (api.cu enqueue_host_msm).
+    # Host scalars at 2^20 and above are copied in chunks (two, three from 2^23) that overlap with
+    # compute; every chunk fills its own bucket array and one reduce adds them (api.cu enqueue_host_msm).
     sc = pk.random_scalars(n, seed=n % 1000)
     d_bs = pk.synth_bases_device(n, 3, 5)
     want = oracle.known_dlog_answer(3, 5, sc)
@@ -286,13 +286,13 @@ def test_host_path_chunk_pipeline(pk, oracle, n):
 
     for mode in (pk.G1Bases.TABLE, pk.G1Bases.PLAIN):
         reg = pk.G1Bases(d_bs, mode=mode)
-        for chunks in ("", "3"):
-            if chunks:
-                os.environ["PLONKISH_CUDA_HOST_CHUNKS"] = chunks
+        for var, chunks in (("", ""), ("PLONKISH_CUDA_HOST_CHUNKS", "3"), ("PLONKISH_CUDA_HOST_CHUNKS", "1"), ("PLONKISH_CUDA_HOST_CUTS", "0.01,0.3,0.31,1")):
+            if var:
+                os.environ[var] = chunks
             try:
-                assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes(), (mode, chunks)
+                assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes(), (mode, var, chunks)
             finally:
-                os.environ.pop("PLONKISH_CUDA_HOST_CHUNKS", None)
+                os.environ.pop(var, None)
         reg.release()
 
 

@@ -1,4 +1,5 @@
-"""Times the host-scalar C-ABI call at 2^24 for several chunk counts (PLONKISH_CUDA_HOST_CHUNKS)."""
+"""Times the host-scalar C-ABI call for several chunkings (PLONKISH_CUDA_HOST_CHUNKS = equal chunks,
+PLONKISH_CUDA_HOST_CUTS = chunk ends as fractions)."""
 import os, sys, time, subprocess, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -17,9 +18,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     # plain H2D copy time for reference
     d = torch.empty_like(host, device="cuda"); torch.cuda.synchronize()
     t = time.perf_counter(); d.copy_(host); torch.cuda.synchronize(); cp = (time.perf_counter() - t) * 1e3
-    print(json.dumps({"chunks": os.environ.get("PLONKISH_CUDA_HOST_CHUNKS"), "log_n": log_n, "ms": round(ms, 2), "h2d_ms": round(cp, 2)}))
+    print(json.dumps({"chunks": os.environ.get("PLONKISH_CUDA_HOST_CHUNKS"), "cuts": os.environ.get("PLONKISH_CUDA_HOST_CUTS"), "log_n": log_n, "ms": round(ms, 2), "h2d_ms": round(cp, 2)}))
 else:
-    for log_n in (24, 22):
-        for ch in ("1", "2", "4", "8"):
-            env = dict(os.environ, PLONKISH_CUDA_HOST_CHUNKS=ch)
+    for log_n in (24, 22, 20):
+        subprocess.run([sys.executable, __file__, "child", str(log_n)], env=dict(os.environ))  # library default
+        for cuts in ("1", "0.125,1", "0.25,1", "0.2,0.6,1", "0.125,0.5,1", "0.0625,0.25,0.625,1", "0.1,0.4,1", "0.125,0.4375,1", "0.0625,0.3125,1"):
+            env = dict(os.environ, PLONKISH_CUDA_HOST_CUTS=cuts)
             subprocess.run([sys.executable, __file__, "child", str(log_n)], env=env)
