@@ -17,6 +17,14 @@ extern "C" {
     fn plonkish_cuda_msm_bn254_g1_gather(scalars: *const *const c_void, bases: *const *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_batch(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_many(scalars_list: *const *const c_void, handles: *const u64, ns: *const usize, count: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_bases_release(handle: u64) -> c_int;
+    fn plonkish_cuda_bases_read(handle: u64, offset: usize, n: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_scalars_release(handle: u64) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1_batch_keep(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void, scalars_handles: *mut u64) -> c_int;
+    fn plonkish_cuda_fr_linear_combination(handles: *const u64, coeffs: *const c_void, count: usize, n: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_kzg_open_bn254(scalars_handle: u64, eq_handles: *const u64, point: *const c_void, num_vars: usize, out_comms: *mut c_void, out_eval: *mut c_void) -> c_int;
+    fn plonkish_cuda_fixed_base_msm_bn254_g1(device: c_int, base: *const c_void, scalars: *const c_void, n: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_kzg_setup_eqs_bn254(device: c_int, g1: *const c_void, ss: *const c_void, num_vars: usize, handles_out: *mut u64) -> c_int;
 }
 
 static INIT: Once = Once::new();
@@ -157,4 +165,107 @@ pub fn commit_quotients_bn254(quotients: &[Vec<Fr>], eqs: &[Vec<G1Affine>]) -> V
         "plonkish_cuda_msm_bn254_g1_many",
     );
     out.into_iter().map(|b| unsafe { std::mem::transmute::<[u8; 64], G1Affine>(b) }).collect()
+}
+
+// ---- the callers either side of the MSM ------------------------
+
+/// A polynomial's evaluations kept in HBM between `batch_commit` and `open`
+/// (pcs/multilinear/kzg.rs:259-274 -> :276-302): what `poly.evals()` is to the reference.
+pub struct ResidentPoly {
+    handle: u64,
+    num_vars: usize,
+}
+impl Drop for ResidentPoly {
+    fn drop(&mut self) {
+        unsafe { plonkish_cuda_scalars_release(self.handle) };
+    }
+}
+
+/// The prover half of `MultilinearKzg::setup` (kzg.rs:167-212) built on the GPU: `eqs[k]` for
+/// k = 0..=num_vars, registered as resident base slices and never materialised on the host.
+pub struct ResidentEqs {
+    handles: Vec<u64>,
+}
+impl ResidentEqs {
+    pub fn setup(g1: &G1Affine, ss: &[Fr]) -> Self {
+        init();
+        let mut handles = vec![0u64; ss.len() + 1];
+        check(
+            unsafe { plonkish_cuda_kzg_setup_eqs_bn254(0, g1 as *const G1Affine as *const c_void, ss.as_ptr() as *const c_void, ss.len(), handles.as_mut_ptr()) },
+            "plonkish_cuda_kzg_setup_eqs_bn254",
+        );
+        Self { handles }
+    }
+    pub fn num_vars(&self) -> usize {
+        self.handles.len() - 1 // kzg.rs:68-70
+    }
+    /// `eqs[k]` back on the host, for `MultilinearKzgProverParams { g1, eqs }` serialisation (kzg.rs:55-77).
+    pub fn eq_to_host(&self, k: usize) -> Vec<G1Affine> {
+        let mut out = vec![G1Affine::default(); 1 << k];
+        check(unsafe { plonkish_cuda_bases_read(self.handles[k], 0, out.len(), out.as_mut_ptr() as *mut c_void) }, "plonkish_cuda_bases_read");
+        out
+    }
+    /// `batch_commit` (kzg.rs:259-274) of polynomials with `num_vars` variables each, leaving them resident.
+    pub fn batch_commit_keep(&self, polys: &[&[Fr]]) -> (Vec<G1Affine>, Vec<ResidentPoly>) {
+        let n = polys[0].len();
+        assert!(n.is_power_of_two() && polys.iter().all(|p| p.len() == n));
+        let k = n.trailing_zeros() as usize;
+        let ptrs: Vec<*const c_void> = polys.iter().map(|p| p.as_ptr() as *const c_void).collect();
+        let mut out = vec![G1Affine::default(); polys.len()];
+        let mut hs = vec![0u64; polys.len()];
+        check(
+            unsafe { plonkish_cuda_msm_bn254_g1_batch_keep(ptrs.as_ptr(), polys.len(), self.handles[k], n, out.as_mut_ptr() as *mut c_void, hs.as_mut_ptr()) },
+            "plonkish_cuda_msm_bn254_g1_batch_keep",
+        );
+        (out, hs.into_iter().map(|handle| ResidentPoly { handle, num_vars: k }).collect())
+    }
+    /// `MultilinearKzg::open` (kzg.rs:276-302): the quotient commitments in transcript order and f(point).
+    pub fn open(&self, poly: &ResidentPoly, point: &[Fr]) -> (Vec<G1Affine>, Fr) {
+        assert_eq!(poly.num_vars, point.len()); // multilinear.rs:77
+        let mut comms = vec![G1Affine::default(); point.len()];
+        let mut eval = Fr::zero();
+        check(
+            unsafe {
+                plonkish_cuda_kzg_open_bn254(poly.handle, self.handles.as_ptr(), point.as_ptr() as *const c_void, point.len(),
+                                             comms.as_mut_ptr() as *mut c_void, &mut eval as *mut Fr as *mut c_void)
+            },
+            "plonkish_cuda_kzg_open_bn254",
+        );
+        (comms, eval)
+    }
+}
+impl Drop for ResidentEqs {
+    fn drop(&mut self) {
+        for h in &self.handles {
+            unsafe { plonkish_cuda_bases_release(*h) };
+        }
+    }
+}
+
+/// The g_prime merge of `batch_open` (pcs/multilinear.rs:203-213): sum_i coeffs[i] * polys[i], in HBM.
+pub fn linear_combination(polys: &[&ResidentPoly], coeffs: &[Fr]) -> ResidentPoly {
+    assert_eq!(polys.len(), coeffs.len());
+    let hs: Vec<u64> = polys.iter().map(|p| p.handle).collect();
+    let num_vars = polys[0].num_vars;
+    let mut handle = 0u64;
+    check(
+        unsafe { plonkish_cuda_fr_linear_combination(hs.as_ptr(), coeffs.as_ptr() as *const c_void, hs.len(), 1 << num_vars, &mut handle) },
+        "plonkish_cuda_fr_linear_combination",
+    );
+    ResidentPoly { handle, num_vars }
+}
+
+/// `fixed_base_msm(window_size, &window_table(window_size, base), scalars)` followed by
+/// `batch_normalize` (msm.rs:16-31, 67-81; kzg.rs:195-208; univariate/kzg.rs:187-199).
+pub fn fixed_base_msm_bn254(base: &G1Affine, scalars: &[Fr]) -> Vec<G1Affine> {
+    init();
+    let mut out = vec![G1Affine::default(); scalars.len()];
+    check(
+        unsafe {
+            plonkish_cuda_fixed_base_msm_bn254_g1(0, base as *const G1Affine as *const c_void, scalars.as_ptr() as *const c_void, scalars.len(),
+                                                  out.as_mut_ptr() as *mut c_void)
+        },
+        "plonkish_cuda_fixed_base_msm_bn254_g1",
+    );
+    out
 }
