@@ -147,6 +147,33 @@ int plonkish_cuda_fixed_base_msm_bn254_g1(int device, const void *base_affine64,
 int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affine64, const void *ss_mont32, size_t num_vars,
                                       uint64_t *handles_out);
 
+/* ---- sum check ---------------------------------------------------------
+ * ClassicSumCheck<EvaluationsProver>::prove (piop/sum_check/classic.rs:208-240) round by round.  The
+ * caller owns the transcript: it writes each round message, squeezes the challenge (classic.rs:226-229)
+ * and hands it back; the tables stay in HBM.
+ *
+ * The expression is flattened: sum_t coeffs[t] * prod_{j in [offsets[t], offsets[t+1])} poly[term_polys[j]],
+ * times poly[common_poly] when common_poly >= 0 (the eq(x, y) of a zero check).  Every polynomial is a
+ * resident table of 2^num_vars evaluations (scalars_register / batch_keep / fr_linear_combination); eq_xy,
+ * identity and Lagrange tables and rotated copies, which the reference keeps implicit (classic.rs:40-75,
+ * 104-126), are materialised by the caller.  Limits: 32 polynomials, 32 terms, 8 factors per term, degree 8.
+ * The resident polynomials are not modified. */
+int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t num_polys, size_t num_vars, const void *term_coeffs_mont32,
+                               const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms, int common_poly,
+                               uint64_t *state_handle);
+/* Degree of the round polynomial: max factors per term (+ 1 with a common factor); negative on error. */
+int plonkish_cuda_sumcheck_degree(uint64_t state_handle);
+/* The round message without its first entry (piop/sum_check/classic/eval.rs:101-131):
+ * out_evals_mont32[x-1] = sum_b expr(r_0, .., r_{round-1}, X = x, b) for x = 1..degree, over the pairs
+ * (2b, 2b+1) of every table (eval.rs:236-243).  The caller sets evals[0] = sum - evals[1] (eval.rs:128). */
+int plonkish_cuda_sumcheck_round(uint64_t state_handle, void *out_evals_mont32);
+/* ProverState::next_round (classic.rs:90-141): fix the lowest variable of every table at the challenge
+ * (MultilinearPolynomial::fix_var, poly/multilinear.rs:179-189: out[b] = (e[2b+1] - e[2b]) * x + e[2b]). */
+int plonkish_cuda_sumcheck_fix_var(uint64_t state_handle, const void *challenge_mont32);
+/* ProverState::into_evals (classic.rs:143-149) after num_vars rounds: num_polys field elements. */
+int plonkish_cuda_sumcheck_final_evals(uint64_t state_handle, void *out_evals_mont32);
+int plonkish_cuda_sumcheck_free(uint64_t state_handle);
+
 /* Same as plonkish_cuda_msm_bn254_g1 for the reference's non-contiguous callers, which pass iterators of
  * references (chain![..] at pcs/univariate/kzg.rs:346,408; .map(|c| &c.0) at
  * pcs/multilinear/kzg.rs:145): gathers the n scalars and n bases into staging first. */

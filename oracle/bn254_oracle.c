@@ -693,3 +693,48 @@ void oracle_fixed_base_msm(const og1_affine_t *base, size_t window_size, const o
     free(tasks);
     free(table);
 }
+
+/* ----------------------------------------------------------------- sum check */
+
+/* piop/sum_check/classic/eval.rs:101-131 on explicit tables: for every pair b the tables are read at
+ * (2b, 2b+1) (eval.rs:236-243), the point X = 1 is e[2b+1] and every further point adds the step
+ * e[2b+1] - e[2b] (eval.rs:268-300); out[x-1] = sum_b expr(X = x) for x = 1..degree.  expr =
+ * sum_t coeffs[t] * prod_j polys[term_polys[j]] (j in [offsets[t], offsets[t+1])), times polys[common]
+ * when common >= 0. */
+void oracle_sumcheck_round(const ofe_t *const *polys, size_t num_polys, size_t size, const ofe_t *coeffs,
+                           const uint32_t *offsets, const uint32_t *term_polys, size_t num_terms, int common,
+                           size_t degree, ofe_t *out) {
+    ofe_t *val = (ofe_t *)malloc(sizeof(ofe_t) * num_polys), *step = (ofe_t *)malloc(sizeof(ofe_t) * num_polys);
+    memset(out, 0, sizeof(ofe_t) * degree);
+    for (size_t b = 0; b < size; ++b) {
+        for (size_t p = 0; p < num_polys; ++p) {
+            val[p] = polys[p][2 * b + 1];
+            fe_sub(FR, polys[p][2 * b + 1].l, polys[p][2 * b].l, step[p].l);
+        }
+        for (size_t x = 0; x < degree; ++x) {
+            ofe_t total;
+            memset(&total, 0, sizeof(total));
+            for (size_t t = 0; t < num_terms; ++t) {
+                ofe_t prod = coeffs[t];
+                for (uint32_t j = offsets[t]; j < offsets[t + 1]; ++j) mont_mul(FR, prod.l, val[term_polys[j]].l, prod.l);
+                fe_add(FR, total.l, prod.l, total.l);
+            }
+            if (common >= 0) mont_mul(FR, total.l, val[common].l, total.l);
+            fe_add(FR, out[x].l, total.l, out[x].l);
+            for (size_t p = 0; p < num_polys; ++p) fe_add(FR, val[p].l, step[p].l, val[p].l);
+        }
+    }
+    free(val);
+    free(step);
+}
+
+/* MultilinearPolynomial::fix_var (poly/multilinear.rs:179-189, merge_into :599-618):
+ * out[b] = (e[2b+1] - e[2b]) * x + e[2b] for b < n/2. */
+void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out) {
+    for (size_t b = 0; b < n / 2; ++b) {
+        ofe_t d;
+        fe_sub(FR, evals[2 * b + 1].l, evals[2 * b].l, d.l);
+        mont_mul(FR, d.l, x->l, d.l);
+        fe_add(FR, d.l, evals[2 * b].l, out[b].l);
+    }
+}

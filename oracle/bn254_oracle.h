@@ -24,6 +24,7 @@
  *   util/arithmetic/msm.rs:16-31,50-81  window_table, fixed_base_msm
  *   pcs/multilinear.rs:72-107, 203-213  quotients, g_prime merge
  *   pcs/multilinear/kzg.rs:174-208      eq tables of the SRS
+ *   piop/sum_check/classic.rs:90-141, classic/eval.rs:101-131, poly/multilinear.rs:179-189   sum-check rounds
  * The field / curve arithmetic the reference gets from the un-vendored
  * third-party crate halo2_curves 0.3.3 (plonkish_backend/Cargo.toml:7, patched
  * at Cargo.toml:9-11, no lockfile) is restated from the published BN254
@@ -101,6 +102,15 @@ void oracle_kzg_eq_scalars(const ofe_t *ss, size_t num_vars, ofe_t *out);
  * out[i] = scalars[i] * base, affine. */
 void oracle_fixed_base_msm(const og1_affine_t *base, size_t window_size, const ofe_t *scalars, size_t n, int num_threads,
                            og1_affine_t *out);
+
+/* ---- sum check ---- */
+/* piop/sum_check/classic/eval.rs:101-131 on explicit tables of 2*size evaluations: out[x-1] = sum_b expr(X = x),
+ * x = 1..degree, expr = sum_t coeffs[t] * prod polys[term_polys[offsets[t]..offsets[t+1])] (* polys[common]). */
+void oracle_sumcheck_round(const ofe_t *const *polys, size_t num_polys, size_t size, const ofe_t *coeffs,
+                           const uint32_t *offsets, const uint32_t *term_polys, size_t num_terms, int common,
+                           size_t degree, ofe_t *out);
+/* MultilinearPolynomial::fix_var (poly/multilinear.rs:179-189, 599-618): n evaluations in, n/2 out. */
+void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,8 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fr_linear_combination.argtypes = [vp, vp, sz, sz, vp]
         _lib.oracle_kzg_eq_scalars.argtypes = [vp, sz, vp]
         _lib.oracle_fixed_base_msm.argtypes = [vp, sz, vp, sz, ci, vp]
+        _lib.oracle_sumcheck_round.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, sz, vp]
+        _lib.oracle_fix_var.argtypes = [vp, sz, vp, vp]
     return _lib
 
 
@@ -248,4 +250,39 @@ def fixed_base_msm(base, scalars, window: int | None = None, num_threads: int | 
         num_threads = host_threads()
     out = np.zeros((n, 8), dtype=np.uint64)
     lib().oracle_fixed_base_msm(_ptr(base), int(window), _ptr(scalars), n, int(num_threads), _ptr(out))
+    return out
+
+
+def flatten_terms(terms):
+    """[(coeff limbs[4], [poly indices])] -> (coeffs [T,4] uint64, offsets [T+1] uint32, polys uint32)."""
+    coeffs = np.stack([_u64(c).reshape(4) for c, _ in terms])
+    offsets = np.zeros(len(terms) + 1, dtype=np.uint32)
+    flat = []
+    for t, (_, idx) in enumerate(terms):
+        flat.extend(int(i) for i in idx)
+        offsets[t + 1] = len(flat)
+    return coeffs, offsets, np.array(flat if flat else [0], dtype=np.uint32)
+
+
+def sumcheck_round(polys, terms, common: int = -1) -> np.ndarray:
+    """piop/sum_check/classic/eval.rs:101-131: evaluations of the round polynomial at X = 1..degree."""
+    polys = [_u64(p).reshape(-1, 4) for p in polys]
+    n = polys[0].shape[0]
+    assert n >= 2 and all(p.shape[0] == n for p in polys)
+    coeffs, offsets, flat = flatten_terms(terms)
+    degree = max(len(idx) for _, idx in terms) + (1 if common >= 0 else 0)
+    degree = max(degree, 1)
+    ptrs = (ctypes.c_void_p * len(polys))(*[p.ctypes.data for p in polys])
+    out = np.zeros((degree, 4), dtype=np.uint64)
+    lib().oracle_sumcheck_round(ctypes.cast(ptrs, ctypes.c_void_p), len(polys), n // 2, _ptr(coeffs), _ptr(offsets), _ptr(flat),
+                                len(terms), int(common), degree, _ptr(out))
+    return out
+
+
+def fix_var(evals, x) -> np.ndarray:
+    """MultilinearPolynomial::fix_var (poly/multilinear.rs:179-189)."""
+    evals = _u64(evals).reshape(-1, 4)
+    x = _u64(x).reshape(4)
+    out = np.zeros((evals.shape[0] // 2, 4), dtype=np.uint64)
+    lib().oracle_fix_var(_ptr(evals), evals.shape[0], _ptr(x), _ptr(out))
     return out

@@ -35,6 +35,12 @@ EXPORTS = (
     "plonkish_cuda_kzg_open_bn254",
     "plonkish_cuda_fixed_base_msm_bn254_g1",
     "plonkish_cuda_kzg_setup_eqs_bn254",
+    "plonkish_cuda_sumcheck_new",
+    "plonkish_cuda_sumcheck_degree",
+    "plonkish_cuda_sumcheck_round",
+    "plonkish_cuda_sumcheck_fix_var",
+    "plonkish_cuda_sumcheck_final_evals",
+    "plonkish_cuda_sumcheck_free",
     "plonkish_cuda_msm_bn254_g1_gather",
     "plonkish_cuda_bases_register_sharded",
     "plonkish_cuda_msm_bn254_g1_multi",
@@ -89,6 +95,12 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_many.argtypes = [vp, vp, vp, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
+    lib.plonkish_cuda_sumcheck_new.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_sumcheck_degree.argtypes = [u64]
+    lib.plonkish_cuda_sumcheck_round.argtypes = [u64, vp]
+    lib.plonkish_cuda_sumcheck_fix_var.argtypes = [u64, vp]
+    lib.plonkish_cuda_sumcheck_final_evals.argtypes = [u64, vp]
+    lib.plonkish_cuda_sumcheck_free.argtypes = [u64]
     lib.plonkish_cuda_scalars_register.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_scalars_release.argtypes = [u64]
     lib.plonkish_cuda_scalars_read.argtypes = [u64, sz, sz, vp]

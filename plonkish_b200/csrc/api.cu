@@ -28,6 +28,7 @@ static std::atomic<unsigned long long> g_launches{0};
 
 #include "msm_kernels.cuh"
 #include "poly_kernels.cuh"
+#include "sumcheck_kernels.cuh"
 
 using namespace pk;
 
@@ -1571,7 +1572,9 @@ struct ScalarsEntry {
 };
 static std::map<uint64_t, ScalarsEntry> g_scalars;
 
+static void release_all_sumcheck();
 static void release_all_scalars() {  // caller holds g_mu
+    release_all_sumcheck();
     for (auto &kv : g_scalars) {
         cudaSetDevice(kv.second.dev);
         cudaFree(kv.second.d_ptr);
@@ -1884,5 +1887,189 @@ extern "C" int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affi
         cleanup();
     }
     for (size_t k = 0; k <= num_vars; ++k) handles_out[k] = publish(entries[k]);
+    return PLONKISH_CUDA_OK;
+}
+
+// ================================================================== sum check
+// ClassicSumCheck<EvaluationsProver>::prove (piop/sum_check/classic.rs:208-240) as a round-by-round
+// state on the device: the caller owns the transcript (it hashes each round message to draw the
+// challenge, classic.rs:226-229), the device owns the tables.
+struct SumcheckState {
+    int dev = 0;
+    u32 num_vars = 0, round = 0, num_polys = 0;
+    SumcheckExpr ex;
+    std::vector<const void *> cur;          // current table of every polynomial
+    std::vector<void *> buf_a, buf_b;       // state-owned halves: 2^(k-1) and 2^(k-2) evaluations per polynomial
+    void *block = nullptr;                  // one pooled allocation behind buf_a / buf_b / scratch
+    void *partials = nullptr, *d_out = nullptr, *d_chal = nullptr, *d_final = nullptr;
+};
+static std::map<uint64_t, SumcheckState> g_sumcheck;
+
+static void release_all_sumcheck() {  // caller holds g_mu
+    for (auto &kv : g_sumcheck) {
+        cudaSetDevice(kv.second.dev);
+        cudaFree(kv.second.block);
+    }
+    g_sumcheck.clear();
+}
+
+extern "C" int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t num_polys, size_t num_vars, const void *term_coeffs,
+                                          const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms, int common_poly,
+                                          uint64_t *state_handle) {
+    if (!poly_handles || !state_handle || !term_offsets || (num_terms && !term_coeffs)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: null argument");
+    if (num_polys == 0 || num_polys > PK_SC_MAX_POLYS) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: %zu polynomials (1..%d supported)", num_polys, PK_SC_MAX_POLYS);
+    if (num_terms == 0 || num_terms > PK_SC_MAX_TERMS) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: %zu terms (1..%d supported)", num_terms, PK_SC_MAX_TERMS);
+    if (num_vars == 0 || num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: num_vars = %zu (1..28 supported)", num_vars);  // classic.rs:41
+    if (common_poly >= (int)num_polys) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: common factor %d out of range", common_poly);
+    SumcheckState st;
+    st.num_vars = (u32)num_vars; st.num_polys = (u32)num_polys;
+    memset(&st.ex, 0, sizeof(st.ex));
+    st.ex.num_terms = (u32)num_terms; st.ex.num_polys = (u32)num_polys; st.ex.common = common_poly < 0 ? -1 : common_poly;
+    u32 degree = 0;
+    for (size_t t = 0; t < num_terms; ++t) {
+        const uint32_t beg = term_offsets[t], end = term_offsets[t + 1];
+        if (end < beg || end - beg > PK_SC_MAX_FACTORS) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: term %zu has %u factors (0..%d supported)", t, end - beg, PK_SC_MAX_FACTORS);
+        st.ex.nfac[t] = (unsigned char)(end - beg);
+        for (uint32_t j = beg; j < end; ++j) {
+            if (!term_polys || term_polys[j] >= num_polys) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: term %zu names polynomial %u of %zu", t, term_polys ? term_polys[j] : 0u, num_polys);
+            st.ex.fac[t][j - beg] = (unsigned char)term_polys[j];
+        }
+        memcpy(st.ex.coeff[t].l, (const char *)term_coeffs + t * PLONKISH_CUDA_SCALAR_BYTES, PLONKISH_CUDA_SCALAR_BYTES);
+        static const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};  // R mod r
+        st.ex.has_coeff[t] = memcmp(st.ex.coeff[t].l, FR_ONE, 32) != 0;
+        if (end - beg > degree) degree = end - beg;
+    }
+    if (st.ex.common >= 0) degree += 1;
+    if (degree < 1) degree = 1;
+    if (degree > PK_SC_MAX_DEGREE) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: degree %u exceeds %d", degree, PK_SC_MAX_DEGREE);
+    st.ex.degree = degree;
+    const size_t n = (size_t)1 << num_vars;
+    for (size_t p = 0; p < num_polys; ++p) {
+        ScalarsEntry se;
+        if (!lookup_scalars(poly_handles[p], se)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: unknown scalars handle %llu", (unsigned long long)poly_handles[p]);
+        if (se.n != n) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: polynomial %zu holds %zu evaluations, expected 2^%zu", p, se.n, num_vars);
+        if (p == 0) st.dev = se.dev;
+        if (se.dev != st.dev) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: polynomials live on different devices");
+        st.cur.push_back(se.d_ptr);
+    }
+    Ctx *c = ctx_for(st.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_new: device %d not initialised", st.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t half = n / 2, quarter = n / 4 ? n / 4 : 1;
+    const size_t max_blocks = (size_t)c->sm_count * 2;
+    const size_t elems = num_polys * (half + quarter) + max_blocks * PK_SC_MAX_DEGREE + PK_SC_MAX_DEGREE + 1 + num_polys;
+    int rc = pool_alloc(c, &st.block, elems * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    char *q = (char *)st.block;
+    for (size_t p = 0; p < num_polys; ++p) { st.buf_a.push_back(q); q += half * 32; }
+    for (size_t p = 0; p < num_polys; ++p) { st.buf_b.push_back(q); q += quarter * 32; }
+    st.partials = q; q += max_blocks * PK_SC_MAX_DEGREE * 32;
+    st.d_out = q; q += PK_SC_MAX_DEGREE * 32;
+    st.d_chal = q; q += 32;
+    st.d_final = q;
+    std::lock_guard<std::mutex> lk2(g_mu);
+    const uint64_t h = g_next_handle++;
+    g_sumcheck[h] = st;
+    *state_handle = h;
+    return PLONKISH_CUDA_OK;
+}
+
+static bool lookup_sumcheck(uint64_t handle, SumcheckState &out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_sumcheck.find(handle);
+    if (it == g_sumcheck.end()) return false;
+    out = it->second;
+    return true;
+}
+
+extern "C" int plonkish_cuda_sumcheck_degree(uint64_t state_handle) {
+    SumcheckState st;
+    if (!lookup_sumcheck(state_handle, st)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_degree: unknown state %llu", (unsigned long long)state_handle);
+    return (int)st.ex.degree;
+}
+
+// The round message without its first entry: out[x-1] = sum_b expr(.., X = x, b) for x = 1..degree
+// (eval.rs:101-131; the caller sets evals[0] = sum - evals[1], eval.rs:128).
+extern "C" int plonkish_cuda_sumcheck_round(uint64_t state_handle, void *out_evals) {
+    SumcheckState st;
+    if (!out_evals) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round: null output");
+    if (!lookup_sumcheck(state_handle, st)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round: unknown state %llu", (unsigned long long)state_handle);
+    if (st.round >= st.num_vars) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round: all %u rounds are done", st.num_vars);
+    Ctx *c = ctx_for(st.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_round: device %d not initialised", st.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    SumcheckPolys polys;
+    memset(&polys, 0, sizeof(polys));
+    for (u32 p = 0; p < st.num_polys; ++p) polys.p[p] = (const uint4 *)st.cur[p];
+    const u32 size = 1u << (st.num_vars - st.round - 1);  // ProverState::size, classic.rs:86-88
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    pk_enqueue_sumcheck_round(polys, st.ex, size, st.partials, st.d_out, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_evals, st.d_out, (size_t)st.ex.degree * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PLONKISH_CUDA_OK;
+}
+
+// ProverState::next_round (classic.rs:90-141): every table is fixed at the challenge.
+extern "C" int plonkish_cuda_sumcheck_fix_var(uint64_t state_handle, const void *challenge) {
+    SumcheckState st;
+    if (!challenge) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_fix_var: null challenge");
+    if (!lookup_sumcheck(state_handle, st)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_fix_var: unknown state %llu", (unsigned long long)state_handle);
+    if (st.round >= st.num_vars) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_fix_var: all %u variables are fixed", st.num_vars);
+    Ctx *c = ctx_for(st.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_fix_var: device %d not initialised", st.dev);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CUDA_TRY(cudaSetDevice(c->dev));
+        SumcheckFoldArgs a;
+        memset(&a, 0, sizeof(a));
+        std::vector<void *> &dst = (st.round % 2 == 0) ? st.buf_a : st.buf_b;
+        for (u32 p = 0; p < st.num_polys; ++p) { a.in[p] = (const uint4 *)st.cur[p]; a.out[p] = (uint4 *)dst[p]; }
+        const u32 size = 1u << (st.num_vars - st.round - 1);
+        CUDA_TRY(cudaMemcpyAsync(st.d_chal, challenge, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        pk_enqueue_sumcheck_fold(a, st.num_polys, st.d_chal, size, (u32)c->sm_count, c->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // the caller's challenge buffer is free again
+        for (u32 p = 0; p < st.num_polys; ++p) st.cur[p] = dst[p];
+        st.round += 1;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_sumcheck[state_handle] = st;
+    return PLONKISH_CUDA_OK;
+}
+
+// ProverState::into_evals (classic.rs:143-149): every polynomial at the point of all challenges.
+extern "C" int plonkish_cuda_sumcheck_final_evals(uint64_t state_handle, void *out_evals) {
+    SumcheckState st;
+    if (!out_evals) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_final_evals: null output");
+    if (!lookup_sumcheck(state_handle, st)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_final_evals: unknown state %llu", (unsigned long long)state_handle);
+    if (st.round != st.num_vars) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_final_evals: %u of %u variables fixed", st.round, st.num_vars);  // classic.rs:144
+    Ctx *c = ctx_for(st.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_final_evals: device %d not initialised", st.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    for (u32 p = 0; p < st.num_polys; ++p)
+        CUDA_TRY(cudaMemcpyAsync((char *)st.d_final + (size_t)p * 32, st.cur[p], 32, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_evals, st.d_final, (size_t)st.num_polys * 32, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_sumcheck_free(uint64_t state_handle) {
+    SumcheckState st;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_sumcheck.find(state_handle);
+        if (it == g_sumcheck.end()) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_free: unknown state %llu", (unsigned long long)state_handle);
+        st = it->second;
+        g_sumcheck.erase(it);
+    }
+    Ctx *c = ctx_for(st.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_free: device %d not initialised", st.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    pool_free(c, st.block);
     return PLONKISH_CUDA_OK;
 }

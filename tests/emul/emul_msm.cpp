@@ -6,6 +6,7 @@
 
 #include "../../plonkish_b200/csrc/msm_kernels.cuh"
 #include "../../plonkish_b200/csrc/poly_kernels.cuh"
+#include "../../plonkish_b200/csrc/sumcheck_kernels.cuh"
 
 #include <stdlib.h>
 
@@ -157,5 +158,31 @@ void emul_fixed_base(const void *base64, const void *scalars, u32 n, void *out_a
     std::vector<xyzz> tmp(entries > n ? entries : n);
     pk_enqueue_fixed_table(base64, offsets.data(), tmp.data(), table.data(), 0);
     pk_enqueue_fixed_base(scalars, n, table.data(), tmp.data(), (affine *)out_affine, 0);
+}
+
+// ---- sum-check rounds (sumcheck_kernels.cuh): tables of n evaluations each, flattened expression
+void emul_sumcheck_round(const void *const *polys, u32 num_polys, u32 n, const void *coeffs, const u32 *offsets, const u32 *term_polys,
+                         u32 num_terms, int common, u32 degree, u32 sm_count, void *out) {
+    SumcheckPolys ps;
+    SumcheckExpr ex;
+    memset(&ps, 0, sizeof(ps));
+    memset(&ex, 0, sizeof(ex));
+    for (u32 p = 0; p < num_polys; ++p) ps.p[p] = (const uint4 *)polys[p];
+    static const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    ex.num_terms = num_terms; ex.num_polys = num_polys; ex.degree = degree; ex.common = common;
+    for (u32 t = 0; t < num_terms; ++t) {
+        memcpy(ex.coeff[t].l, (const char *)coeffs + (size_t)t * 32, 32);
+        ex.has_coeff[t] = memcmp(ex.coeff[t].l, FR_ONE, 32) != 0;
+        ex.nfac[t] = (unsigned char)(offsets[t + 1] - offsets[t]);
+        for (u32 j = offsets[t]; j < offsets[t + 1]; ++j) ex.fac[t][j - offsets[t]] = (unsigned char)term_polys[j];
+    }
+    std::vector<fe> partials((size_t)sm_count * 2 * PK_SC_MAX_DEGREE + 8);
+    pk_enqueue_sumcheck_round(ps, ex, n / 2, partials.data(), out, sm_count, 0);
+}
+void emul_sumcheck_fold(const void *const *polys, void *const *outs, u32 num_polys, u32 n, const void *challenge, u32 sm_count) {
+    SumcheckFoldArgs a;
+    memset(&a, 0, sizeof(a));
+    for (u32 p = 0; p < num_polys; ++p) { a.in[p] = (const uint4 *)polys[p]; a.out[p] = (uint4 *)outs[p]; }
+    pk_enqueue_sumcheck_fold(a, num_polys, challenge, n / 2, sm_count, 0);
 }
 }
