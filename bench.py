@@ -263,6 +263,64 @@ def srs_setup_bench(pk, torch, np, k: int, cpu: bool):
     return res
 
 
+def sum_check_bench(pk, torch, np, k: int, cpu: bool):
+    """The zero check of HyperPlonk::prove for vanilla_plonk (backend/hyperplonk.rs:262-277) as ClassicSumCheck runs it
+    (piop/sum_check/classic.rs:208-240): 9 tables (eq, 5 selectors, 3 witness columns) of 2^k evaluations, degree 4,
+    k rounds of round-polynomial evaluations + table folds on the GPU; the challenges are stand-ins for the transcript's.
+    CPU: the oracle's restatement of the same rounds, one thread, on tables of 2^18 evaluations."""
+    from plonkish_b200 import sumcheck
+
+    n = 1 << k
+    tables = [pk.ResidentScalars(pk.random_scalars(n, seed=300 + i)) for i in range(9)]
+    one = sumcheck._to_mont(1)
+    terms = [(one, [1, 6]), (one, [2, 7]), (one, [3, 6, 7]), (one, [4, 8]), (one, [5])]
+    chal = pk.random_scalars(k, seed=399)
+
+    def run():
+        prover = sumcheck.SumCheckProver(tables, terms, common=0)
+        msgs = []
+        for rnd in range(k):
+            msgs.append(prover.round_evals())
+            prover.fix_var(chal[rnd])
+        finals = prover.final_evals()
+        prover.free()
+        return msgs, finals
+
+    run()
+    t0 = time.perf_counter()
+    msgs, finals = run()
+    gpu_ms = (time.perf_counter() - t0) * 1e3
+    res = {"what": "zero check of vanilla_plonk as ClassicSumCheck<EvaluationsProver> runs it: 9 resident tables of 2^k evaluations, degree 4, "
+                   "k rounds (round-polynomial evaluations at X = 1..4 + fold of every table), stand-in challenges",
+           "k": k, "gpu_ms": gpu_ms, "gpu_mpairs_per_s_first_round_equiv": (n - 1) / gpu_ms / 1e3}
+    if cpu:
+        from oracle import pyoracle as po
+
+        kc = min(18, k)
+        host = [t.to_host(0, 1 << kc) for t in tables]
+        sub = [pk.ResidentScalars(h) for h in host]
+        prover = sumcheck.SumCheckProver(sub, terms, common=0)
+        ok = True
+        cur = host
+        t0 = time.perf_counter()
+        ref = []
+        for rnd in range(kc):
+            ref.append(po.sumcheck_round(cur, terms, 0))
+            cur = [po.fix_var(p, chal[rnd]) for p in cur]
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        for rnd in range(kc):
+            ok = ok and prover.round_evals().tobytes() == ref[rnd].tobytes()
+            prover.fix_var(chal[rnd])
+        ok = ok and prover.final_evals().tobytes() == np.stack([p[0] for p in cur]).tobytes()
+        prover.free()
+        for r in sub:
+            r.release()
+        res.update({"cpu_ms": cpu_ms, "cpu_k": kc, "cpu_cores": 1, "cpu_mpairs_per_s": ((1 << kc) - 1) / cpu_ms / 1e3, "bit_exact_vs_cpu": bool(ok)})
+    for t in tables:
+        t.release()
+    return res
+
+
 def univariate_sequence(pk, torch, np, k: int, dev):
     """BASELINE.json config 4 restated synthetically: UnivariateKzg commit = one MSM over
     the SRS prefix (pcs/univariate/kzg.rs:24-30, witness-like 68-bit limb values with zero padding) and
@@ -511,6 +569,7 @@ def run_ours(args) -> None:
         line["hyperplonk_prove_msm"] = seq
         line["univariate_kzg_k22"] = univariate_sequence(pk, torch, np, 22, dev)
         line["srs_fixed_base_msm"] = srs_setup_bench(pk, torch, np, args.prove_k, cpu=not args.no_cpu_baseline)
+        line["sum_check_zero_check"] = sum_check_bench(pk, torch, np, args.prove_k, cpu=not args.no_cpu_baseline)
     if rank == 0:
         emit(line)
     if distributed:

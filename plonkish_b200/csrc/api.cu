@@ -1957,7 +1957,7 @@ extern "C" int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t n
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
     const size_t half = n / 2, quarter = n / 4 ? n / 4 : 1;
-    const size_t max_blocks = (size_t)c->sm_count * 2;
+    const size_t max_blocks = (size_t)c->sm_count * 16;
     const size_t elems = num_polys * (half + quarter) + max_blocks * PK_SC_MAX_DEGREE + PK_SC_MAX_DEGREE + 1 + num_polys;
     int rc = pool_alloc(c, &st.block, elems * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;

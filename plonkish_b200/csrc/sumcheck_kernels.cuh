@@ -13,7 +13,7 @@
 // which the reference keeps implicit (classic.rs:40-75, 104-126); the round values are the same field elements.
 //
 // k_sumcheck_round is one pass over all tables (HBM: 64 B per polynomial and pair) with
-// degree * (sum of term degrees) Fr products per pair: IMAD bound for plonkish expressions.
+// degree * (sum of term degrees - terms + 1) Fr products per pair: IMAD bound for plonkish expressions.
 // Also compiled by g++ against tests/emul/cuda_emul.h (PLONKISH_EMUL) for the CPU suite.
 #pragma once
 #include "poly_kernels.cuh"
@@ -53,64 +53,66 @@ PK_HD void sc_store(u32 *base, u32 p, u32 nthreads, u32 tid, const fe &v) {
     for (int i = 0; i < 8; ++i) base[((size_t)p * 8 + i) * nthreads + tid] = v.l[i];
 }
 
-// sum over the terms at the current point of every table (values in shared memory)
-PK_HD fe sc_eval_terms(const SumcheckExpr &ex, const u32 *val, u32 nthreads, u32 tid) {
-    fe total = fe_zero();
-    for (u32 t = 0; t < ex.num_terms; ++t) {
-        fe prod;
-        if (ex.nfac[t] == 0) {
-            prod = ex.coeff[t];
-        } else {
-            prod = sc_load(val, ex.fac[t][0], nthreads, tid);
-            for (u32 j = 1; j < ex.nfac[t]; ++j) prod = fr_mul(prod, sc_load(val, ex.fac[t][j], nthreads, tid));
-            if (ex.has_coeff[t]) prod = fr_mul(prod, ex.coeff[t]);
-        }
-        total = fr_add(total, prod);
-    }
-    if (ex.common >= 0) total = fr_mul(total, sc_load(val, (u32)ex.common, nthreads, tid));
-    return total;
+// The table entries of pair b at the points X = x0 + 1 and x0 + 2: e[2b+1] + x0 * step and one step further
+// (eval.rs:268-300: the point X = 1 is e[2b+1], every further point adds e[2b+1] - e[2b]).
+PK_HD void sc_points(const uint4 *__restrict__ table, u32 b, u32 x0, fe &v0, fe &v1) {
+    const uint4 *src = table + 4 * (size_t)b;  // e[2b] then e[2b+1]: 64 contiguous bytes
+    const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
+    const fe step = fr_sub(hi, lo);
+    v0 = hi;
+    for (u32 i = 0; i < x0; ++i) v0 = fr_add(v0, step);
+    v1 = fr_add(v0, step);
 }
 
 // partials[block][x-1] = sum over the block's pairs b of expr(tables at (.., X = x, b)), x = 1..degree.
-// Dynamic shared memory: 2 * num_polys * 8 * blockDim words (value and step of every table per thread).
-__global__ void __launch_bounds__(128) k_sumcheck_round(SumcheckPolys polys, SumcheckExpr ex, u32 size, uint4 *__restrict__ partials) {
-    PK_DYN_SMEM(u32, smem);
+// Term-major: every factor is read where it is used (the 64 bytes of a pair stay in L1 across the terms and
+// passes), two points of X per pass so that two independent product chains are in flight; no staging of the
+// tables, so occupancy is set by registers alone.  Dynamic shared memory: degree * 8 * blockDim words (the
+// running sums of every thread, limb-major).
+__global__ void __launch_bounds__(128, 4) k_sumcheck_round(SumcheckPolys polys, SumcheckExpr ex, u32 size, uint4 *__restrict__ partials) {
+    PK_DYN_SMEM(u32, acc);
     const u32 nt = blockDim.x, tid = threadIdx.x;
-    u32 *val = smem, *step = smem + (size_t)ex.num_polys * 8 * nt;
-    fe acc[PK_SC_MAX_DEGREE];
-#pragma unroll
-    for (int x = 0; x < PK_SC_MAX_DEGREE; ++x) acc[x] = fe_zero();
+    for (u32 x = 0; x < ex.degree; ++x) sc_store(acc, x, nt, tid, fe_zero());
     for (u32 b = blockIdx.x * nt + tid; b < size; b += gridDim.x * nt) {
-        for (u32 p = 0; p < ex.num_polys; ++p) {
-            const uint4 *src = polys.p[p] + 4 * (size_t)b;      // e[2b] then e[2b+1]
-            const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
-            sc_store(val, p, nt, tid, hi);                      // X = 1
-            sc_store(step, p, nt, tid, fr_sub(hi, lo));
-        }
-#pragma unroll
-        for (int x = 0; x < PK_SC_MAX_DEGREE; ++x) {
-            if ((u32)x < ex.degree) {
-                acc[x] = fr_add(acc[x], sc_eval_terms(ex, val, nt, tid));
-                if ((u32)x + 1 < ex.degree) {
-                    for (u32 p = 0; p < ex.num_polys; ++p)     // X -> X + 1
-                        sc_store(val, p, nt, tid, fr_add(sc_load(val, p, nt, tid), sc_load(step, p, nt, tid)));
+        for (u32 x0 = 0; x0 < ex.degree; x0 += 2) {
+            const bool two = x0 + 1 < ex.degree;
+            fe tot0 = fe_zero(), tot1 = fe_zero();
+            for (u32 t = 0; t < ex.num_terms; ++t) {
+                fe p0 = ex.coeff[t], p1 = ex.coeff[t];
+                if (ex.nfac[t]) {
+                    sc_points(polys.p[ex.fac[t][0]], b, x0, p0, p1);
+                    for (u32 j = 1; j < ex.nfac[t]; ++j) {
+                        fe v0, v1;
+                        sc_points(polys.p[ex.fac[t][j]], b, x0, v0, v1);
+                        p0 = fr_mul(p0, v0);
+                        if (two) p1 = fr_mul(p1, v1);
+                    }
+                    if (ex.has_coeff[t]) {
+                        p0 = fr_mul(p0, ex.coeff[t]);
+                        if (two) p1 = fr_mul(p1, ex.coeff[t]);
+                    }
                 }
+                tot0 = fr_add(tot0, p0);
+                tot1 = fr_add(tot1, p1);
             }
+            if (ex.common >= 0) {
+                fe v0, v1;
+                sc_points(polys.p[ex.common], b, x0, v0, v1);
+                tot0 = fr_mul(tot0, v0);
+                if (two) tot1 = fr_mul(tot1, v1);
+            }
+            sc_store(acc, x0, nt, tid, fr_add(sc_load(acc, x0, nt, tid), tot0));
+            if (two) sc_store(acc, x0 + 1, nt, tid, fr_add(sc_load(acc, x0 + 1, nt, tid), tot1));
         }
     }
-    // block sum through shared memory (reusing the value slots: one fe per thread, tree over threads)
+    // block sum: binary tree over the threads, one point of X at a time
     __syncthreads();
-#pragma unroll
-    for (int x = 0; x < PK_SC_MAX_DEGREE; ++x) {
-        if ((u32)x >= ex.degree) continue;
-        sc_store(val, 0, nt, tid, acc[x]);
-        __syncthreads();
+    for (u32 x = 0; x < ex.degree; ++x) {
         for (u32 s = nt >> 1; s >= 1; s >>= 1) {
-            if (tid < s) sc_store(val, 0, nt, tid, fr_add(sc_load(val, 0, nt, tid), sc_load(val, 0, nt, tid + s)));
+            if (tid < s) sc_store(acc, x, nt, tid, fr_add(sc_load(acc, x, nt, tid), sc_load(acc, x, nt, tid + s)));
             __syncthreads();
         }
-        if (tid == 0) store_fe(partials + 2 * ((size_t)blockIdx.x * ex.degree + x), sc_load(val, 0, nt, 0));
-        __syncthreads();
+        if (tid == 0) store_fe(partials + 2 * ((size_t)blockIdx.x * ex.degree + x), sc_load(acc, x, nt, 0));
     }
 }
 
@@ -134,20 +136,14 @@ __global__ void __launch_bounds__(256) k_sumcheck_fold(SumcheckFoldArgs a, const
     }
 }
 
-// Threads per block such that value + step slots of every table fit in shared memory (<= 200 KB).
-inline u32 pk_sumcheck_block(u32 num_polys) {
-    const u32 fit = (200u * 1024u) / (64u * (num_polys ? num_polys : 1));
-    u32 t = 128;  // a power of two: the block sum is a binary tree
-    while (t > 32 && t > fit) t >>= 1;
-    return t;
-}
-inline size_t pk_sumcheck_smem(u32 num_polys, u32 block) { return (size_t)64 * num_polys * block; }
+inline u32 pk_sumcheck_block(u32) { return 128; }  // a power of two: the block sum is a binary tree
+inline size_t pk_sumcheck_smem(u32 degree, u32 block) { return (size_t)32 * degree * block; }
 
 // One round over tables of 2 * size evaluations each: degree values into d_out (X = 1..degree).
-// partials: max_blocks * degree field elements of scratch.
+// partials: 16 * sm_count * degree field elements of scratch (more than the largest grid).
 inline u32 pk_sumcheck_grid(u32 size, u32 block, u32 sm_count) {
     u32 blocks = (size + block - 1) / block;
-    const u32 cap = sm_count * 2;
+    const u32 cap = sm_count * 4;  // persistent: 4 blocks of 128 threads per SM (registers)
     if (blocks > cap) blocks = cap;
     return blocks ? blocks : 1;
 }
@@ -155,7 +151,7 @@ inline void pk_enqueue_sumcheck_round(const SumcheckPolys &polys, const Sumcheck
                                       pk_stream_t stream) {
     const u32 block = pk_sumcheck_block(ex.num_polys);
     const u32 blocks = pk_sumcheck_grid(size, block, sm_count);
-    const size_t smem = pk_sumcheck_smem(ex.num_polys, block);
+    const size_t smem = pk_sumcheck_smem(ex.degree, block);
     PK_SET_SMEM(k_sumcheck_round, smem);
     PK_LAUNCH(k_sumcheck_round, dim3(blocks), dim3(block), smem, stream, polys, ex, size, (uint4 *)partials);
     PK_LAUNCH(k_sumcheck_sum_partials, dim3(1), dim3(32), 0, stream, (const uint4 *)partials, blocks, ex.degree, (uint4 *)d_out);

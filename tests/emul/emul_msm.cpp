@@ -176,7 +176,7 @@ void emul_sumcheck_round(const void *const *polys, u32 num_polys, u32 n, const v
         ex.nfac[t] = (unsigned char)(offsets[t + 1] - offsets[t]);
         for (u32 j = offsets[t]; j < offsets[t + 1]; ++j) ex.fac[t][j - offsets[t]] = (unsigned char)term_polys[j];
     }
-    std::vector<fe> partials((size_t)sm_count * 2 * PK_SC_MAX_DEGREE + 8);
+    std::vector<fe> partials((size_t)sm_count * 16 * PK_SC_MAX_DEGREE + 8);
     pk_enqueue_sumcheck_round(ps, ex, n / 2, partials.data(), out, sm_count, 0);
 }
 void emul_sumcheck_fold(const void *const *polys, void *const *outs, u32 num_polys, u32 n, const void *challenge, u32 sm_count) {
