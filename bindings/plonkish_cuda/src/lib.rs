@@ -25,6 +25,13 @@ extern "C" {
     fn plonkish_cuda_kzg_open_bn254(scalars_handle: u64, eq_handles: *const u64, point: *const c_void, num_vars: usize, out_comms: *mut c_void, out_eval: *mut c_void) -> c_int;
     fn plonkish_cuda_fixed_base_msm_bn254_g1(device: c_int, base: *const c_void, scalars: *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_kzg_setup_eqs_bn254(device: c_int, g1: *const c_void, ss: *const c_void, num_vars: usize, handles_out: *mut u64) -> c_int;
+    fn plonkish_cuda_sumcheck_new(polys: *const u64, num_polys: usize, num_vars: usize, coeffs: *const c_void, offsets: *const u32, term_polys: *const u32,
+                                  num_terms: usize, common_poly: c_int, state: *mut u64) -> c_int;
+    fn plonkish_cuda_sumcheck_degree(state: u64) -> c_int;
+    fn plonkish_cuda_sumcheck_round(state: u64, out_evals: *mut c_void) -> c_int;
+    fn plonkish_cuda_sumcheck_fix_var(state: u64, challenge: *const c_void) -> c_int;
+    fn plonkish_cuda_sumcheck_final_evals(state: u64, out_evals: *mut c_void) -> c_int;
+    fn plonkish_cuda_sumcheck_free(state: u64) -> c_int;
 }
 
 static INIT: Once = Once::new();
@@ -268,4 +275,51 @@ pub fn fixed_base_msm_bn254(base: &G1Affine, scalars: &[Fr]) -> Vec<G1Affine> {
         "plonkish_cuda_fixed_base_msm_bn254_g1",
     );
     out
+}
+
+/// `ClassicSumCheck<EvaluationsProver>::prove` (piop/sum_check/classic.rs:208-240) over resident tables.
+/// `terms[t] = (coeff, factors)` is the flattened expression sum_t coeff * prod polys[factor]; `common` is the
+/// table multiplying the whole sum (the eq(x, y) of a zero check).  `squeeze` stands for
+/// `msg.write(transcript)?; transcript.squeeze_challenge()` (classic.rs:226-229) and `evaluate` for
+/// `msg.evaluate(&aux, &challenge)` (eval.rs:50-52): both stay with the caller's transcript and field code.
+pub fn sum_check_prove(
+    polys: &[&ResidentPoly],
+    terms: &[(Fr, Vec<u32>)],
+    common: Option<usize>,
+    sum: Fr,
+    mut squeeze: impl FnMut(&[Fr]) -> Fr,
+    evaluate: impl Fn(&[Fr], &Fr) -> Fr,
+) -> (Vec<Fr>, Vec<Fr>) {
+    let num_vars = polys[0].num_vars;
+    let hs: Vec<u64> = polys.iter().map(|p| p.handle).collect();
+    let coeffs: Vec<Fr> = terms.iter().map(|t| t.0).collect();
+    let mut offsets = vec![0u32];
+    let mut flat = Vec::new();
+    for (_, f) in terms {
+        flat.extend_from_slice(f);
+        offsets.push(flat.len() as u32);
+    }
+    let mut state = 0u64;
+    check(
+        unsafe {
+            plonkish_cuda_sumcheck_new(hs.as_ptr(), hs.len(), num_vars, coeffs.as_ptr() as *const c_void, offsets.as_ptr(), flat.as_ptr(), terms.len(),
+                                       common.map_or(-1, |c| c as c_int), &mut state)
+        },
+        "plonkish_cuda_sumcheck_new",
+    );
+    let degree = unsafe { plonkish_cuda_sumcheck_degree(state) } as usize;
+    let (mut sum, mut challenges) = (sum, Vec::with_capacity(num_vars));
+    for _ in 0..num_vars {
+        let mut msg = vec![Fr::zero(); degree + 1];
+        check(unsafe { plonkish_cuda_sumcheck_round(state, msg[1..].as_mut_ptr() as *mut c_void) }, "plonkish_cuda_sumcheck_round");
+        msg[0] = sum - msg[1]; // eval.rs:128
+        let challenge = squeeze(&msg);
+        sum = evaluate(&msg, &challenge); // classic.rs:232
+        check(unsafe { plonkish_cuda_sumcheck_fix_var(state, &challenge as *const Fr as *const c_void) }, "plonkish_cuda_sumcheck_fix_var");
+        challenges.push(challenge);
+    }
+    let mut evals = vec![Fr::zero(); polys.len()];
+    check(unsafe { plonkish_cuda_sumcheck_final_evals(state, evals.as_mut_ptr() as *mut c_void) }, "plonkish_cuda_sumcheck_final_evals");
+    unsafe { plonkish_cuda_sumcheck_free(state) };
+    (challenges, evals) // classic.rs:239
 }
