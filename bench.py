@@ -498,8 +498,8 @@ def run_ours(args) -> None:
         "madd_stream_ceiling_products_per_s": madd_streams["madd_1acc_128regs"],
         "frac_of_madd_stream": (float(n) * plan["windows"] * MODMUL_PER_MIXED_ADD / (stages["accumulate"] * 1e-3)) / madd_streams["madd_1acc_128regs"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one 2^24-point launch in the committed ncu --set full capture
-        # (profiles/r01_v3_kernels_ncu_raw.csv: 29.47 GB + 0.23 GB), scaled to this launch's entry count
-        "traffic": 29.70e9 * (float(n) * plan["windows"]) / (16777216.0 * 13),
+        # (profiles/r01_final_kernels_ncu_raw.csv: 27.25 GB + 0.39 GB at 12 windows), scaled to this launch's entry count
+        "traffic": 27.64e9 * (float(n) * plan["windows"]) / (16777216.0 * 12),
         "traffic_source": "ncu capture under profiles/ (not measured in this run); algorithmic gather = entries x 68 B",
         "algorithmic_bytes": float(n) * plan["windows"] * 68,
     }
