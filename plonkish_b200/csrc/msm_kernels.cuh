@@ -81,7 +81,7 @@ struct MsmPlan {
     u32 red_blocks;   // K4 blocks per window
     u32 blk;          // threads per block of the streaming kernels (256; tests shrink it)
     u32 serial_items; // item levels above this many items let every lane fold 8 items serially first
-    u32 blk_stage;    // threads per block of the staged partition kernels (512; tests shrink it)
+    u32 blk_stage;    // threads per block of the staged partition kernels (512, 1024 from 2^24 points; tests shrink it)
     u32 mode;         // 0: one bucket set per window (any bases); 1: one bucket set, bases are a table of
                       //    precomputed window multiples T[w][i] = 2^(c*w) * P_i (resident bases only)
     u32 ngroups;      // bucket sets: W in mode 0, 1 in mode 1
@@ -202,6 +202,10 @@ inline MsmPlan pk_make_plan_b(u32 n, u32 c, u32 stride, u32 sm_count) {
     p.nbuckets = p.B;
     p.ngroups = 1;
     p.stride = stride;
+    // 1 024-thread stages (16 K entries) double the run length of both sort levels; they pay once there are
+    // enough tiles to fill the GPU with one such block per SM (measured at 2^24: scatter 1.22 -> 1.03 ms,
+    // level 2 1.35 -> 1.27 ms; at 2^22 the 64 tiles are too few: 0.41 -> 0.55 ms)
+    p.blk_stage = (p.ntiles >= 256) ? 1024 : 512;
     unsigned long long emax = (unsigned long long)n * p.W;
     unsigned long long resident = (unsigned long long)sm_count * 512ull;
     unsigned long long L = emax / (resident * 3ull);
@@ -661,7 +665,7 @@ PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val)[EPT],
 // Level 1: one block per tile of points, all windows.  Partitions (bucket, table index)
 // pairs by the high bucket bits into l1_val (sign << 31 | table index) and l1_key (low bits).
 #define PK_STAGE_EPT 16
-__global__ void __launch_bounds__(512) k_scatter_staged_b(const u32 *__restrict__ digits, MsmPlan p, u32 *__restrict__ gcursor,
+__global__ void __launch_bounds__(1024) k_scatter_staged_b(const u32 *__restrict__ digits, MsmPlan p, u32 *__restrict__ gcursor,
                                                           u32 *__restrict__ l1_val, u16 *__restrict__ l1_key) {
     PK_DYN_SMEM(u32, smem);
     const u32 S = blockDim.x * PK_STAGE_EPT;
@@ -840,7 +844,7 @@ __global__ void __launch_bounds__(1024) k_scan_apply(u32 *__restrict__ v, u32 n,
 
 // Level 2 scatter: same slicing as the histogram; partitions each slice by the low bucket
 // bits into the final (window-free) order.  gcursor = per-bucket cursors (bucket starts).
-__global__ void __launch_bounds__(512) k_bucket_scatter_staged_b(const u32 *__restrict__ l1_val, const u16 *__restrict__ l1_key, MsmPlan p,
+__global__ void __launch_bounds__(1024) k_bucket_scatter_staged_b(const u32 *__restrict__ l1_val, const u16 *__restrict__ l1_key, MsmPlan p,
                                                                  const u32 *__restrict__ bin_start, const u32 *__restrict__ slice_prefix, u32 slice,
                                                                  u32 *__restrict__ gcursor, u32 *__restrict__ sorted) {
     PK_DYN_SMEM(u32, smem);
