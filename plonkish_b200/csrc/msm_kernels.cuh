@@ -1114,7 +1114,7 @@ PK_HD xyzz xyzz_mul_small(const xyzz &pnt, u32 k) {
 // grid (red_blocks, W), block 256.  Thread j of window w owns buckets
 // [j*rb, (j+1)*rb): sum_i (j*rb + i + 1) * B_i = acc + (j*rb) * run, where run is
 // the plain sum and acc the running-sum total (msm.rs:175-179 restated per chunk).
-__global__ void __launch_bounds__(PK_RED_BLOCK, 4) k_bucket_reduce(const xyzz *__restrict__ bucket_sum,
+__global__ void __launch_bounds__(PK_RED_BLOCK, 3) k_bucket_reduce(const xyzz *__restrict__ bucket_sum,
                                                                 MsmPlan p, xyzz *__restrict__ block_out) {
     __shared__ xyzz warp_part[PK_RED_BLOCK / 32];
     const u32 w = blockIdx.y;
