@@ -543,9 +543,33 @@ PK_HD fe fq_inv_fast(const fe &a) {
 
 // Fr Montgomery form -> canonical integer (halo2_curves `to_repr`, called at
 // msm.rs:153): one Montgomery reduction, i.e. a product with the plain integer 1.
-PK_HD fe fr_to_canonical(const fe &a) {
-    fe one = {{1, 0, 0, 0, 0, 0, 0, 0}};
-    return mont_mul<FrMod>(a, one);
+// a / 2^256 mod m for a < m: the reduction half of a Montgomery product (8 rounds of T = (T + q*m) >> 32 with
+// q = T[0] * (-m^-1)), 64 + 8 multiply instructions instead of the 136 of a product with one.  T stays below 2m.
+template <class MOD>
+PK_HD fe mont_reduce(const fe &a) {
+    u32 m[8], t[8];
+    MOD::limbs(m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = a.l[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const u32 q = t[0] * MOD::inv();
+        u64 c = ((u64)q * m[0] + t[0]) >> 32;  // low word is zero by construction
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            const u64 p = (u64)q * m[j] + t[j] + c;
+            t[j - 1] = (u32)p;
+            c = p >> 32;
+        }
+        t[7] = (u32)c;  // T < 2m < 2^255: no ninth word
+    }
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    final_sub<MOD>(r.l);
+    return r;
 }
+
+PK_HD fe fr_to_canonical(const fe &a) { return mont_reduce<FrMod>(a); }
 
 }  // namespace pk
