@@ -204,8 +204,8 @@ inline MsmPlan pk_make_plan_b(u32 n, u32 c, u32 stride, u32 sm_count) {
     p.stride = stride;
     // 1 024-thread stages (16 K entries) double the run length of both sort levels; they pay once there are
     // enough tiles to fill the GPU with one such block per SM (measured at 2^24: scatter 1.22 -> 1.03 ms,
-    // level 2 1.35 -> 1.27 ms; at 2^22 the 64 tiles are too few: 0.41 -> 0.55 ms)
-    p.blk_stage = (p.tile >= 65536 && p.ntiles >= 256) ? 1024 : 512;  // i.e. from 2^24 points
+    // level 2 1.35 -> 1.27 ms; smaller MSMs have tiles shorter than such a stage: 2^22 0.41 -> 0.55 ms)
+    p.blk_stage = (p.tile >= 16384) ? 1024 : 512;  // a tile row holds at least one 16 K-entry stage: n > 2^23
     unsigned long long emax = (unsigned long long)n * p.W;
     unsigned long long resident = (unsigned long long)sm_count * 512ull;
     unsigned long long L = emax / (resident * 3ull);
