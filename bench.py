@@ -507,7 +507,7 @@ def run_ours(args) -> None:
         "kernel": "the two sort levels (k_scatter_staged_b, k_bucket_hist_b, k_bucket_scatter_staged_b; plain bases: k_scatter_bins, k_sort_bins)", "bound": "hbm", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9,
         "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
         "frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": sort_ms,
-        # table layout, 2^24: k_scatter_staged_b 0.95 + 1.32 GB, k_bucket_hist_b 0.44 GB, k_bucket_scatter_staged_b 1.68 + 1.11 GB (same capture)
+        # table layout, 2^24, c = 22: k_scatter_staged_b 0.81 + 1.16 GB, k_bucket_hist_b 0.41 GB, k_bucket_scatter_staged_b 1.36 + 0.90 GB (same capture)
         "traffic": (5.51e9 * entries / (16777216.0 * 13)) if not plan["idx_bits"] else None,
         "algorithmic_bytes": sort_bytes,
     }
