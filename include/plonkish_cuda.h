@@ -268,7 +268,8 @@ int plonkish_cuda_synth_bases_device(int device, void *d_out_affine64, size_t fi
  * field ops (32-byte elements): 0 Fq mul, 1 Fq add, 2 Fq sub, 3 Fr Montgomery->canonical
  * (halo2_curves to_repr, msm.rs:153), 4 Fq inverse (Fermat ladder), 5 Fr mul, 6 Fq negate,
  * 7 Fq inverse (safegcd, the one the library uses), 8 Fq fused a[i]*b[i] + b[i]*a[(i+1)%n] with one
- * reduction (the y-coordinate form of the point formulas), 9 the same shape in Fr: a[i]^2 + b[i]*b[(i+1)%n].
+ * reduction (the y-coordinate form of the point formulas), 9 the same shape in Fr: a[i]^2 + b[i]*b[(i+1)%n],
+ * 10 Fq square (symmetric partial products taken once), 11 Fr square.
  * point ops (128-byte X,Y,ZZ,ZZZ slots; b's first 64 bytes are an affine point for op 0):
  * 0 mixed add, 1 full add, 2 double, 3 to_affine (result in the first 64 bytes). */
 int plonkish_cuda_debug_field_op(int device, int op, const void *a32, const void *b32, void *out32, size_t n);

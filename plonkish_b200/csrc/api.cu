@@ -1506,6 +1506,8 @@ __global__ void k_debug_field(int op, const fe *a, const fe *b, fe *out, u32 n) 
         case 7: r = fq_inv_fast(a[i]); break;
         case 8: r = fq_mul_sum(a[i], b[i], b[i], a[(i + 1) % n]); break;        // a*b + b*a'  (a' = next element of a)
         case 9: r = mont_mul_sum<FrMod>(a[i], a[i], b[i], b[(i + 1) % n]); break;  // Fr: a^2 + b*b'
+        case 10: r = fq_sqr(a[i]); break;                                          // symmetric squaring
+        case 11: r = mont_sqr<FrMod>(a[i]); break;
         default: r = fq_neg(a[i]); break;
     }
     out[i] = r;

@@ -330,10 +330,204 @@ PK_HD fe mont_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) {
     return r;
 }
 
+
+// ---- variants of the two row blocks that skip the partial products of the first S limb pairs (squaring: the
+// symmetric products of row i are taken in the earlier rows).  Skipped pairs of the shifted accumulator still move
+// down two words and carry on, with add-with-carry on the ALU pipe instead of a multiply.
+#ifndef PLONKISH_EMUL
+template <int S>
+PK_HD u32 cmad8_from(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    u32 c = 0;
+    if constexpr (S == 0) {
+        asm(
+            "mad.lo.cc.u32  %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    else if constexpr (S == 1) {
+        asm(
+            "mad.lo.cc.u32  %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    else if constexpr (S == 2) {
+        asm(
+            "mad.lo.cc.u32  %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    else if constexpr (S == 3) {
+        asm(
+            "mad.lo.cc.u32  %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, 0, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    return c;  // S == 4: nothing to add
+}
+template <int S>
+PK_HD void shift_mad8_from(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
+    if constexpr (S == 0) {
+        asm(
+            "add.cc.u32     %0, %0, %9;\n\t"
+            "madc.lo.cc.u32 %1, %10, %14, %3;\n\t"
+            "madc.hi.cc.u32 %2, %10, %14, %4;\n\t"
+            "madc.lo.cc.u32 %3, %11, %14, %5;\n\t"
+            "madc.hi.cc.u32 %4, %11, %14, %6;\n\t"
+            "madc.lo.cc.u32 %5, %12, %14, %7;\n\t"
+            "madc.hi.cc.u32 %6, %12, %14, %8;\n\t"
+            "madc.lo.cc.u32 %7, %13, %14, 0;\n\t"
+            "madc.hi.u32    %8, %13, %14, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+    }
+    else if constexpr (S == 1) {
+        asm(
+            "add.cc.u32     %0, %0, %9;\n\t"
+            "addc.cc.u32    %1, %3, 0;\n\t"
+            "addc.cc.u32    %2, %4, 0;\n\t"
+            "madc.lo.cc.u32 %3, %11, %14, %5;\n\t"
+            "madc.hi.cc.u32 %4, %11, %14, %6;\n\t"
+            "madc.lo.cc.u32 %5, %12, %14, %7;\n\t"
+            "madc.hi.cc.u32 %6, %12, %14, %8;\n\t"
+            "madc.lo.cc.u32 %7, %13, %14, 0;\n\t"
+            "madc.hi.u32    %8, %13, %14, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+    }
+    else if constexpr (S == 2) {
+        asm(
+            "add.cc.u32     %0, %0, %9;\n\t"
+            "addc.cc.u32    %1, %3, 0;\n\t"
+            "addc.cc.u32    %2, %4, 0;\n\t"
+            "addc.cc.u32    %3, %5, 0;\n\t"
+            "addc.cc.u32    %4, %6, 0;\n\t"
+            "madc.lo.cc.u32 %5, %12, %14, %7;\n\t"
+            "madc.hi.cc.u32 %6, %12, %14, %8;\n\t"
+            "madc.lo.cc.u32 %7, %13, %14, 0;\n\t"
+            "madc.hi.u32    %8, %13, %14, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+    }
+    else if constexpr (S == 3) {
+        asm(
+            "add.cc.u32     %0, %0, %9;\n\t"
+            "addc.cc.u32    %1, %3, 0;\n\t"
+            "addc.cc.u32    %2, %4, 0;\n\t"
+            "addc.cc.u32    %3, %5, 0;\n\t"
+            "addc.cc.u32    %4, %6, 0;\n\t"
+            "addc.cc.u32    %5, %7, 0;\n\t"
+            "addc.cc.u32    %6, %8, 0;\n\t"
+            "madc.lo.cc.u32 %7, %13, %14, 0;\n\t"
+            "madc.hi.u32    %8, %13, %14, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+    }
+    else if constexpr (S == 4) {
+        asm(
+            "add.cc.u32     %0, %0, %9;\n\t"
+            "addc.cc.u32    %1, %3, 0;\n\t"
+            "addc.cc.u32    %2, %4, 0;\n\t"
+            "addc.cc.u32    %3, %5, 0;\n\t"
+            "addc.cc.u32    %4, %6, 0;\n\t"
+            "addc.cc.u32    %5, %7, 0;\n\t"
+            "addc.cc.u32    %6, %8, 0;\n\t"
+            "addc.cc.u32    %7, 0, 0;\n\t"
+            "addc.u32       %8, 0, 0;"
+            : "+r"(e0), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+            : "r"(carry_word), "r"(x1), "r"(x3), "r"(x5), "r"(x7), "r"(y));
+    }
+}
+#else
+template <int S>
+inline u32 cmad8_from(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    return cmad8(acc, S > 0 ? 0u : x0, S > 1 ? 0u : x2, S > 2 ? 0u : x4, S > 3 ? 0u : x6, y);
+}
+template <int S>
+inline void shift_mad8_from(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
+    shift_mad8(e0, carry_word, o, S > 0 ? 0u : x1, S > 1 ? 0u : x3, S > 2 ? 0u : x5, S > 3 ? 0u : x7, y);
+}
+#endif
+
+// One row i >= 1 of the squaring: T += a_i * (a_i at word i, the doubled tail 2 * (a >> 32(i+1)) above it), then one
+// reduction step.  x[] holds the row's multiplicand limbs (entries below i unused).
+template <class MOD, int I>
+PK_HD void sqr_row(u32 *ev, u32 *od, const u32 *x, u32 y, const u32 *m) {
+    u32 *E = (I & 1) ? od : ev;
+    u32 *O = (I & 1) ? ev : od;
+    shift_mad8_from<I / 2>(E[0], O[1], O, x[1], x[3], x[5], x[7], y);       // odd limbs below I skipped
+    O[7] += cmad8_from<(I + 1) / 2>(E, x[0], x[2], x[4], x[6], y);          // even limbs below I skipped
+    const u32 q = E[0] * MOD::inv();
+    cmad8(O, m[1], m[3], m[5], m[7], q);
+    O[7] += cmad8(E, m[0], m[2], m[4], m[6], q);
+}
+
+// a*a / 2^256 mod m, a < m: 36 + 64 wide multiplies instead of 128.  Row i multiplies a_i by a_i and by the limbs of
+// the doubled tail 2 * (a >> 32(i+1)) only; the running value stays below 3m < 2^256 (a row adds at most 2^32 * 2a),
+// the final value below 2m.
+template <class MOD>
+PK_HD fe mont_sqr(const fe &a) {
+    u32 m[8], d[8];
+    MOD::limbs(m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = (a.l[i] << 1) | (i ? (a.l[i - 1] >> 31) : 0u);  // limbs of 2a (a < 2^254)
+    u32 ev[8], od[8];
+    {   // row 0: every product
+        const u32 y = a.l[0];
+        const u32 x[8] = {a.l[0], a.l[1] << 1, d[2], d[3], d[4], d[5], d[6], d[7]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u64 pe = (u64)x[2 * k] * y, po = (u64)x[2 * k + 1] * y;
+            ev[2 * k] = (u32)pe; ev[2 * k + 1] = (u32)(pe >> 32);
+            od[2 * k] = (u32)po; od[2 * k + 1] = (u32)(po >> 32);
+        }
+        const u32 q = ev[0] * MOD::inv();
+        cmad8(od, m[1], m[3], m[5], m[7], q);
+        od[7] += cmad8(ev, m[0], m[2], m[4], m[6], q);
+    }
+#define PK_SQR_ROW(I)                                                                                         \
+    {                                                                                                         \
+        u32 x[8];                                                                                             \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) x[j] = (j == I) ? a.l[I] : (j == I + 1) ? (a.l[j] << 1) : d[j]; \
+        sqr_row<MOD, I>(ev, od, x, a.l[I], m);                                                                \
+    }
+    PK_SQR_ROW(1) PK_SQR_ROW(2) PK_SQR_ROW(3) PK_SQR_ROW(4) PK_SQR_ROW(5) PK_SQR_ROW(6) PK_SQR_ROW(7)
+#undef PK_SQR_ROW
+    fe r;
+    {
+        u32 sh[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sh[k] = od[k + 1];
+        sh[7] = 0;
+        add8(r.l, ev, sh);
+    }
+    final_sub<MOD>(r.l);
+    return r;
+}
+
 PK_HD fe fq_mul(const fe &a, const fe &b) { return mont_mul<FqMod>(a, b); }
 // a*b + c*d (Montgomery), one reduction
 PK_HD fe fq_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) { return mont_mul_sum<FqMod>(a, b, c, d); }
-PK_HD fe fq_sqr(const fe &a) { return mont_mul<FqMod>(a, a); }
+PK_HD fe fq_sqr(const fe &a) { return mont_sqr<FqMod>(a); }
 
 template <class MOD>
 PK_HD fe mod_add(const fe &a, const fe &b) {

@@ -25,19 +25,22 @@ namespace pk {
 struct MulInline {
     static PK_HD fe mul(const fe &a, const fe &b) { return fq_mul(a, b); }
     static PK_HD fe mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) { return fq_mul_sum(a, b, c, d); }
+    static PK_HD fe sqr(const fe &a) { return fq_sqr(a); }
 };
 #if !defined(PLONKISH_EMUL)
 __device__ __noinline__ fe fq_mul_call(fe a, fe b) { return mont_mul<FqMod>(a, b); }
 __device__ __noinline__ fe fq_mul_sum_call(fe a, fe b, fe c, fe d) { return mont_mul_sum<FqMod>(a, b, c, d); }
+__device__ __noinline__ fe fq_sqr_call(fe a) { return mont_sqr<FqMod>(a); }
 struct MulCall {
     static PK_HD fe mul(const fe &a, const fe &b) { return fq_mul_call(a, b); }
     static PK_HD fe mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) { return fq_mul_sum_call(a, b, c, d); }
+    static PK_HD fe sqr(const fe &a) { return fq_sqr_call(a); }
 };
 #else
 typedef MulInline MulCall;
 #endif
 #define PK_MUL(a, b) M::mul(a, b)
-#define PK_SQR(a) M::mul(a, a)
+#define PK_SQR(a) M::sqr(a)
 // a*b - c*d with one Montgomery reduction (the y-coordinate of every formula below)
 #define PK_MUL_DIFF(a, b, c, d) M::mul_sum(a, b, fq_neg(c), d)
 

@@ -23,6 +23,12 @@ void emul_fq_mul(const u32 *a, const u32 *b, u32 *o) {
     fe r = fq_mul(x, y);
     memcpy(o, &r, 32);
 }
+void emul_fq_sqr(const u32 *a, u32 *o) {
+    fe x;
+    memcpy(&x, a, 32);
+    fe r = fq_sqr(x);
+    memcpy(o, &r, 32);
+}
 void emul_fq_mul_sum(const u32 *a, const u32 *b, const u32 *c, const u32 *d, u32 *o) {
     fe x, y, z, w;
     memcpy(&x, a, 32); memcpy(&y, b, 32); memcpy(&z, c, 32); memcpy(&w, d, 32);

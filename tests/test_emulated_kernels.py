@@ -25,6 +25,7 @@ def emul():
     lib.emul_fq_mul.argtypes = [vp, vp, vp]
     lib.emul_fr_to_canonical.argtypes = [vp, vp]
     lib.emul_fq_mul_sum.argtypes = [vp, vp, vp, vp, vp]
+    lib.emul_fq_sqr.argtypes = [vp, vp]
     lib.emul_plan.argtypes = [u32, u32, u32, vp]
     lib.emul_msm_table.argtypes = [vp, vp, u32, u32, u32, u32, vp]
 
@@ -86,6 +87,20 @@ def test_fused_two_product_reduction(emul):
                 la, lb, lc, ld = limbs(a), limbs(b), limbs(c), limbs(d)  # keep the arrays alive across the call
                 emul.emul_fq_mul_sum(la.ctypes.data, lb.ctypes.data, lc.ctypes.data, ld.ctypes.data, out.ctypes.data)
                 assert int.from_bytes(out.tobytes(), "little") == (a * b + c * d) * rinv % br.P, (a, b, c, d)
+
+
+def test_symmetric_squaring(emul):
+    # a*a/R with the symmetric partial products taken once (row i multiplies the doubled tail above limb i only)
+    rng = np.random.default_rng(8)
+    rinv = pow(br.MONT, -1, br.P)
+    top = (br.P >> 224 << 224) - 1
+    vals = [0, 1, 2, br.P - 1, br.P - 2, top, (1 << 224) - 1, (1 << 253) + ((1 << 32) - 1), int("7fffffff" * 7, 16), int("80000000" * 7, 16),
+            int("ffffffff" * 7, 16)] + [int.from_bytes(rng.bytes(32), "little") % br.P for _ in range(500)]
+    out = np.zeros(8, dtype=np.uint32)
+    for v in vals:
+        la = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint32).copy()
+        emul.emul_fq_sqr(la.ctypes.data, out.ctypes.data)
+        assert int.from_bytes(out.tobytes(), "little") == v * v * rinv % br.P, v
 
 
 def test_plan_invariants(emul):

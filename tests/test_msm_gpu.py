@@ -70,6 +70,13 @@ def test_ptx_field_arithmetic_matches_python_ints(pk):
         else:
             want = [(x[i] * x[i] + y[i] * y[(i + 1) % n]) * rinv % mod for i in range(n)]
         assert got == want
+    # squaring with the symmetric partial products taken once (ops 10, 11)
+    for op, mod in ((10, br.P), (11, br.R)):
+        top = (mod >> 224 << 224) - 1
+        x = [0, 1, 2, mod - 1, mod - 2, top, (1 << 224) - 1, (1 << 253) + ((1 << 32) - 1), int("7fffffff" * 7, 16), int("80000000" * 7, 16),
+             int("ffffffff" * 7, 16)] + [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(4000)]
+        rinv = pow(br.MONT, -1, mod)
+        assert _ints(_field_op(pk, op, _limbs32(x))) == [v * v * rinv % mod for v in x]
     # Fr Montgomery -> canonical (halo2_curves to_repr at msm.rs:153)
     ks = [0, 1, br.R - 1, (br.R - 1) // 2] + [int.from_bytes(rng.bytes(32), "little") % br.R for _ in range(500)]
     mont = np.frombuffer(b"".join(br.scalar_to_bytes(k) for k in ks), dtype=np.uint64).reshape(-1, 4)
