@@ -1,0 +1,88 @@
+"""Randomised stress of the GPU arithmetic and the MSM against Python integers / the oracle (run on a GPU box).
+Field level: products, fused two-product sums and squarings on structured limb patterns (all-ones / all-zero limbs,
+values around the modulus) and random values.  MSM level: random sizes, both bucket layouts, duplicates, identities,
+negated pairs, skewed scalars."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+import plonkish_b200 as pk
+from plonkish_b200 import _lib
+from oracle import pyoracle as po, bigint_ref as br
+
+seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+
+def limbs32(vals):
+    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), dtype=np.uint64).reshape(-1, 4).copy()
+def ints(arr):
+    return [int.from_bytes(row.tobytes(), "little") for row in arr]
+def field_op(op, a, b=None):
+    out = np.zeros_like(a)
+    _lib.check(_lib.lib().plonkish_cuda_debug_field_op(0, op, a.ctypes.data, None if b is None else b.ctypes.data, out.ctypes.data, a.shape[0]), "debug_field_op")
+    return out
+
+def structured(mod, count):
+    vals = []
+    pats = [0, 0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 1, 0xFFFFFFFE]
+    while len(vals) < count:
+        v = 0
+        for i in range(8):
+            choice = int(rng.integers(0, 8))
+            limb = pats[choice] if choice < len(pats) else int(rng.integers(0, 1 << 32))
+            v |= limb << (32 * i)
+        vals.append(v % mod)
+    return vals
+
+t_end = time.time() + seconds * 0.4
+rounds = 0
+while time.time() < t_end:
+    for mod, op_mul, op_sum, op_sqr in ((br.P, 0, 8, 10), (br.R, 5, 9, 11)):
+        n = 20000
+        x = structured(mod, n // 2) + [mod - 1 - int(v) for v in rng.integers(0, 1000, n // 4)] + [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(n // 4)]
+        y = structured(mod, n // 2) + [int.from_bytes(rng.bytes(32), "little") % mod for _ in range(n // 2)]
+        rinv = pow(br.MONT, -1, mod)
+        X, Y = limbs32(x), limbs32(y)
+        assert ints(field_op(op_mul, X, Y)) == [a * b * rinv % mod for a, b in zip(x, y)], "mul"
+        assert ints(field_op(op_sqr, X)) == [a * a * rinv % mod for a in x], "sqr"
+        got = ints(field_op(op_sum, X, Y))
+        if op_sum == 8:
+            want = [(x[i] * y[i] + y[i] * x[(i + 1) % n]) * rinv % mod for i in range(n)]
+        else:
+            want = [(x[i] * x[i] + y[i] * y[(i + 1) % n]) * rinv % mod for i in range(n)]
+        assert got == want, "mul_sum"
+    rounds += 1
+print(f"field fuzz: {rounds} rounds x 2 fields x 20000 elements x 3 ops ok", flush=True)
+
+t_end = time.time() + seconds * 0.6
+cases = 0
+while time.time() < t_end:
+    n = int(2 ** rng.uniform(0, 17))
+    bases = po.known_dlog_bases(int(rng.integers(1, 1000)), int(rng.integers(1, 1000)), n)
+    kind = int(rng.integers(0, 6))
+    sc = pk.random_scalars(n, seed=int(rng.integers(0, 1 << 31)))
+    if kind == 1:   # small integers / selectors
+        vals = rng.integers(0, 3, n)
+        sc = np.stack([po.from_canonical(1, po.int_to_limbs([0, 1, br.R - 1][int(v)]))[0] for v in vals]) if n <= 4096 else sc
+    elif kind == 2:  # duplicates
+        bases[:] = bases[rng.integers(0, max(1, n // 8), n)]
+    elif kind == 3:  # identities mixed in
+        bases[rng.random(n) < 0.3] = 0
+    elif kind == 4 and n >= 2:  # P and -P with equal scalars
+        half = n // 2
+        neg = bases[:half].copy()
+        for i in range(min(half, 64)):
+            y = int.from_bytes(neg[i, 4:].tobytes(), "little")
+            neg[i, 4:] = np.frombuffer(((br.P - y) % br.P).to_bytes(32, "little"), dtype=np.uint64) if y else neg[i, 4:]
+        m = min(half, 64)
+        bases[half:half + m] = neg[:m]
+        sc[half:half + m] = sc[:m]
+    want = po.variable_base_msm(sc, bases)
+    assert pk.variable_base_msm(sc, bases).tobytes() == want.tobytes(), ("plain", n, kind)
+    for mode in (pk.G1Bases.TABLE, pk.G1Bases.PLAIN):
+        reg = pk.G1Bases(bases, mode=mode)
+        assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes(), (mode, n, kind)
+        use = int(rng.integers(1, n + 1))
+        assert pk.variable_base_msm(sc[:use], reg).tobytes() == po.variable_base_msm(sc[:use], bases[:use]).tobytes(), ("prefix", mode, n, use, kind)
+        reg.release()
+    cases += 1
+print(f"msm fuzz: {cases} random cases x (unregistered, table, plain, prefix) ok", flush=True)
