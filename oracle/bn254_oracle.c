@@ -738,3 +738,69 @@ void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out) {
         fe_add(FR, d.l, evals[2 * b].l, out[b].l);
     }
 }
+
+/* ---------------------------------------------------------------- transcript */
+
+/* Keccak-f[1600] and Keccak256 (original padding 0x01, rate 136): the hash behind Keccak256Transcript
+ * (util/transcript.rs:100-131, util/hash.rs:5-8; the reference takes it from the sha3 crate [ext]).  Restated from
+ * the published Keccak specification; pinned in the tests by the public digests of "" and "abc" and against the
+ * independent Python implementation in plonkish_b200/transcript.py. */
+static uint64_t rol64(uint64_t v, unsigned n) { return n ? (v << n) | (v >> (64 - n)) : v; }
+
+static void keccak_f1600(uint64_t a[25]) {
+    static const uint64_t RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+        0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800AULL, 0x800000008000000AULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    /* rho offsets walked along the pi cycle starting at lane (1, 0) */
+    static const unsigned RHO[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const unsigned PI[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    for (int round = 0; round < 24; ++round) {
+        uint64_t c[5];
+        for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; ++x) {
+            const uint64_t d = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+            for (int y = 0; y < 25; y += 5) a[y + x] ^= d;
+        }
+        uint64_t cur = a[1];
+        for (int i = 0; i < 24; ++i) {
+            const uint64_t next = a[PI[i]];
+            a[PI[i]] = rol64(cur, RHO[i]);
+            cur = next;
+        }
+        for (int y = 0; y < 25; y += 5) {
+            uint64_t row[5];
+            for (int x = 0; x < 5; ++x) row[x] = a[y + x];
+            for (int x = 0; x < 5; ++x) a[y + x] = row[x] ^ (~row[(x + 1) % 5] & row[(x + 2) % 5]);
+        }
+        a[0] ^= RC[round];
+    }
+}
+
+void oracle_keccak256(const uint8_t *data, size_t len, uint8_t out[32]) {
+    uint64_t st[25];
+    uint8_t block[136];
+    memset(st, 0, sizeof(st));
+    while (1) {
+        const size_t take = len < 136 ? len : 136;
+        memset(block, 0, sizeof(block));
+        memcpy(block, data, take);
+        const int last = take < 136;
+        if (last) {
+            block[take] ^= 0x01;
+            block[135] ^= 0x80;
+        }
+        for (int i = 0; i < 17; ++i) {
+            uint64_t lane = 0;
+            for (int b = 7; b >= 0; --b) lane = (lane << 8) | block[8 * i + b];
+            st[i] ^= lane;
+        }
+        keccak_f1600(st);
+        if (last) break;
+        data += take;
+        len -= take;
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int b = 0; b < 8; ++b) out[8 * i + b] = (uint8_t)(st[i] >> (8 * b));
+}

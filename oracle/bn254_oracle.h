@@ -112,6 +112,9 @@ void oracle_sumcheck_round(const ofe_t *const *polys, size_t num_polys, size_t s
 /* MultilinearPolynomial::fix_var (poly/multilinear.rs:179-189, 599-618): n evaluations in, n/2 out. */
 void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out);
 
+/* Keccak256 (original Keccak padding) as used by Keccak256Transcript (util/transcript.rs:100-131, util/hash.rs:5-8). */
+void oracle_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
+
 #ifdef __cplusplus
 }
 #endif

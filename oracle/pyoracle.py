@@ -68,6 +68,7 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fixed_base_msm.argtypes = [vp, sz, vp, sz, ci, vp]
         _lib.oracle_sumcheck_round.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, sz, vp]
         _lib.oracle_fix_var.argtypes = [vp, sz, vp, vp]
+        _lib.oracle_keccak256.argtypes = [ctypes.c_char_p, sz, vp]
     return _lib
 
 
@@ -286,3 +287,10 @@ def fix_var(evals, x) -> np.ndarray:
     out = np.zeros((evals.shape[0] // 2, 4), dtype=np.uint64)
     lib().oracle_fix_var(_ptr(evals), evals.shape[0], _ptr(x), _ptr(out))
     return out
+
+
+def keccak256(data: bytes) -> bytes:
+    """Keccak256 with the original padding (the hash of Keccak256Transcript, util/transcript.rs:100-131)."""
+    out = np.zeros(32, dtype=np.uint8)
+    lib().oracle_keccak256(bytes(data), len(data), _ptr(out))
+    return out.tobytes()

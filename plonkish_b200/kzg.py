@@ -148,6 +148,14 @@ def open_resident(pp: MultilinearKzgProverParam, poly: ResidentScalars, point: n
     return list(comms), value
 
 
+def open_to_transcript(pp: MultilinearKzgProverParam, poly: ResidentScalars, point: np.ndarray, transcript) -> np.ndarray:
+    """`MultilinearKzg::open` as the prover runs it (kzg.rs:276-302): the quotient commitments are written to the
+    transcript in order (`write_commitments`, kzg.rs:299); returns f(point) (the `remainder`, Montgomery limbs)."""
+    comms, value = open_resident(pp, poly, point)
+    transcript.write_commitments(comms)
+    return value
+
+
 def commit_coeffs(powers_of_s_g1: G1Bases, coeffs: np.ndarray) -> np.ndarray:
     """pcs/univariate/kzg.rs:24-30: variable_base_msm(coeffs, &powers_of_s_g1[..coeffs.len()])."""
     return variable_base_msm(coeffs, powers_of_s_g1)

@@ -120,3 +120,16 @@ def prove(polys: Sequence[ResidentScalars], terms, claimed_sum: int, squeeze_cha
     finally:
         prover.free()
     return msgs, challenges, evals
+
+
+def prove_to_transcript(polys: Sequence[ResidentScalars], terms, claimed_sum: int, transcript, common: int = -1):
+    """`ClassicSumCheck::prove` with the reference's transcript calls (classic.rs:226-229): every round message goes
+    down with `write_field_elements` (eval.rs:37-39), the challenge comes from `squeeze_challenge`.
+    `transcript` is a plonkish_b200.transcript.Keccak256Transcript.  Returns (challenges, evals)."""
+
+    def squeeze(msg: List[int]) -> int:
+        transcript.write_field_elements(msg)
+        return transcript.squeeze_challenge()
+
+    _, challenges, evals = prove(polys, terms, claimed_sum, squeeze, common)
+    return challenges, evals
