@@ -25,6 +25,7 @@ extern "C" {
     fn plonkish_cuda_kzg_open_bn254(scalars_handle: u64, eq_handles: *const u64, point: *const c_void, num_vars: usize, out_comms: *mut c_void, out_eval: *mut c_void) -> c_int;
     fn plonkish_cuda_fixed_base_msm_bn254_g1(device: c_int, base: *const c_void, scalars: *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_kzg_setup_eqs_bn254(device: c_int, g1: *const c_void, ss: *const c_void, num_vars: usize, handles_out: *mut u64) -> c_int;
+    fn plonkish_cuda_eq_table(device: c_int, y: *const c_void, num_vars: usize, handle: *mut u64) -> c_int;
     fn plonkish_cuda_sumcheck_new(polys: *const u64, num_polys: usize, num_vars: usize, coeffs: *const c_void, offsets: *const u32, term_polys: *const u32,
                                   num_terms: usize, common_poly: c_int, state: *mut u64) -> c_int;
     fn plonkish_cuda_sumcheck_degree(state: u64) -> c_int;
@@ -247,6 +248,14 @@ impl Drop for ResidentEqs {
             unsafe { plonkish_cuda_bases_release(*h) };
         }
     }
+}
+
+/// `MultilinearPolynomial::eq_xy(y)` as a resident table (the zero-check factor of piop/sum_check/classic.rs:57-61).
+pub fn eq_xy(y: &[Fr]) -> ResidentPoly {
+    init();
+    let mut handle = 0u64;
+    check(unsafe { plonkish_cuda_eq_table(0, y.as_ptr() as *const c_void, y.len(), &mut handle) }, "plonkish_cuda_eq_table");
+    ResidentPoly { handle, num_vars: y.len() }
 }
 
 /// The g_prime merge of `batch_open` (pcs/multilinear.rs:203-213): sum_i coeffs[i] * polys[i], in HBM.

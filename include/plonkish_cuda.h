@@ -111,6 +111,11 @@ int plonkish_cuda_scalars_read(uint64_t handle, size_t offset, size_t n, void *o
  * how a device-built SRS (kzg_setup_eqs) is serialised (pcs/multilinear/kzg.rs:55-77). */
 int plonkish_cuda_bases_read(uint64_t handle, size_t offset, size_t n, void *out_affine64);
 
+/* MultilinearPolynomial::eq_xy(y) as a resident polynomial: the 2^num_vars evaluations of eq(x, y), lowest variable
+ * first — what the sum-check prover state builds for a zero check (piop/sum_check/classic.rs:57-61).  Release with
+ * scalars_release. */
+int plonkish_cuda_eq_table(int device, const void *y_mont32, size_t num_vars, uint64_t *handle);
+
 /* MultilinearKzg::commit on a resident polynomial (pcs/multilinear/kzg.rs:252-257):
  * variable_base_msm(first n resident scalars, first n bases of the slice) -> affine. */
 int plonkish_cuda_msm_bn254_g1_resident(uint64_t scalars_handle, uint64_t bases_handle, size_t n, void *out_affine64);
@@ -173,6 +178,11 @@ int plonkish_cuda_sumcheck_fix_var(uint64_t state_handle, const void *challenge_
 /* ProverState::into_evals (classic.rs:143-149) after num_vars rounds: num_polys field elements. */
 int plonkish_cuda_sumcheck_final_evals(uint64_t state_handle, void *out_evals_mont32);
 int plonkish_cuda_sumcheck_free(uint64_t state_handle);
+
+/* Keccak-f[1600] on 25 little-endian lanes (lane (x, y) at index x + 5 y), host code: the permutation of the reference's
+ * Keccak256Transcript (util/transcript.rs:100-131; util/hash.rs:5-8 takes Keccak256 from the sha3 crate).  The host
+ * mirrors build the sponge and the transcript rules on top of it. */
+void plonkish_cuda_keccak_f1600(uint64_t state[25]);
 
 /* Same as plonkish_cuda_msm_bn254_g1 for the reference's non-contiguous callers, which pass iterators of
  * references (chain![..] at pcs/univariate/kzg.rs:346,408; .map(|c| &c.0) at

@@ -127,6 +127,12 @@ inline std::vector<G1Affine> fixed_base_msm(const G1Affine &base, const std::vec
     check(plonkish_cuda_fixed_base_msm_bn254_g1(device, &base, scalars.data(), scalars.size(), out.data()), "plonkish_cuda_fixed_base_msm_bn254_g1");
     return out;
 }
+// MultilinearPolynomial::eq_xy(y): eq(x, y) over the hypercube, resident (the zero-check factor, classic.rs:57-61).
+inline MultilinearPolynomial eq_xy(const std::vector<Fr> &y, int device = 0) {
+    uint64_t h = 0;
+    check(plonkish_cuda_eq_table(device, y.data(), y.size(), &h), "plonkish_cuda_eq_table");
+    return MultilinearPolynomial::adopt(h, size_t(1) << y.size());
+}
 // pcs/multilinear.rs:203-213: sum_i coeffs[i] * polys[i].
 inline MultilinearPolynomial linear_combination(const std::vector<const MultilinearPolynomial *> &polys, const std::vector<Fr> &coeffs) {
     if (polys.empty() || polys.size() != coeffs.size()) throw std::invalid_argument("linear_combination: polys and coeffs differ in length");

@@ -12,6 +12,7 @@ from .msm import (  # noqa: F401
     variable_base_msm_batch_keep,
     fr_linear_combination,
     kzg_open_resident,
+    eq_table,
     fixed_base_msm,
     kzg_setup_eqs,
     variable_base_msm,

@@ -1659,6 +1659,33 @@ extern "C" int plonkish_cuda_bases_read(uint64_t handle, size_t offset, size_t n
     return PLONKISH_CUDA_OK;
 }
 
+// MultilinearPolynomial::eq_xy(y) (poly/multilinear.rs; used by the sum-check prover state, classic.rs:57-61) as a
+// resident table: evaluations of eq(x, y) over the boolean hypercube, lowest variable first — the same recurrence
+// as the eq tables of the SRS (kzg.rs:178-192), kept as scalars.
+extern "C" int plonkish_cuda_eq_table(int device, const void *y, size_t num_vars, uint64_t *handle) {
+    if (!handle || (num_vars && !y)) return fail(PLONKISH_CUDA_E_INVALID, "eq_table: null argument");
+    if (num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "eq_table: num_vars = %zu exceeds 28", num_vars);
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "eq_table: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t n = (size_t)1 << num_vars, total = 2 * n - 1;
+    void *all = nullptr, *out = nullptr;
+    int rc = pool_alloc(c, &all, (total + num_vars + 1) * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    if ((rc = pool_alloc(c, &out, n * PLONKISH_CUDA_SCALAR_BYTES))) { pool_free(c, all); return rc; }
+    void *d_y = (char *)all + total * PLONKISH_CUDA_SCALAR_BYTES;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_y, y, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    pk_enqueue_eq_scalars(d_y, (u32)num_vars, all, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaMemcpyAsync(out, (char *)all + (n - 1) * PLONKISH_CUDA_SCALAR_BYTES, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    pool_free(c, all);
+    *handle = publish_scalars(device, out, n);
+    return PLONKISH_CUDA_OK;
+}
+
 // commit from resident evaluations: variable_base_msm(poly.evals(), pp.eq(k)).into() (kzg.rs:255)
 extern "C" int plonkish_cuda_msm_bn254_g1_resident(uint64_t scalars_handle, uint64_t bases_handle, size_t n, void *out_affine64) {
     const auto t0 = std::chrono::steady_clock::now();
@@ -2075,3 +2102,31 @@ extern "C" int plonkish_cuda_sumcheck_free(uint64_t state_handle) {
     pool_free(c, st.block);
     return PLONKISH_CUDA_OK;
 }
+
+// ================================================================= transcript
+// Keccak-f[1600], host code: the permutation behind the reference's Keccak256Transcript (util/transcript.rs:100-131,
+// util/hash.rs:5-8 — the sha3 crate on the Rust side).  The transcript itself (absorb / squeeze order, byte orders)
+// lives in the host mirrors (plonkish_b200/transcript.py); only the 24 rounds are here, because they dominate a pure
+// Python transcript.  Lane (x, y) is state[x + 5 y].
+extern "C" void plonkish_cuda_keccak_f1600(uint64_t state[25]) {
+    static const uint64_t RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL, 0x0000000080000001ULL,
+        0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+        0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+        0x000000000000800AULL, 0x800000008000000AULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int ROT[5][5] = {{0, 36, 3, 41, 18}, {1, 44, 10, 45, 2}, {62, 6, 43, 15, 61}, {28, 55, 25, 21, 56}, {27, 20, 39, 8, 14}};  // [x][y]
+    auto rol = [](uint64_t v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; };
+    uint64_t *a = state, b[25];
+    for (int round = 0; round < 24; ++round) {
+        uint64_t c[5], d[5];
+        for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; ++x) d[x] = c[(x + 4) % 5] ^ rol(c[(x + 1) % 5], 1);
+        for (int i = 0; i < 25; ++i) a[i] ^= d[i % 5];
+        for (int x = 0; x < 5; ++x)
+            for (int y = 0; y < 5; ++y) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol(a[x + 5 * y], ROT[x][y]);
+        for (int y = 0; y < 5; ++y)
+            for (int x = 0; x < 5; ++x) a[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        a[0] ^= RC[round];
+    }
+}
+

@@ -236,6 +236,16 @@ def fr_linear_combination(polys: Sequence["ResidentScalars"], coeffs) -> "Reside
     return ResidentScalars._adopt(out.value, n, polys[0].device)
 
 
+def eq_table(y, device: int = 0) -> "ResidentScalars":
+    """eq(x, y) over the boolean hypercube as a resident polynomial (MultilinearPolynomial::eq_xy, the zero-check factor
+    of piop/sum_check/classic.rs:57-61).  y: [k, 4] Montgomery Fr."""
+    ys = _as_u64(y, 4, "y") if len(y) else np.zeros((0, 4), dtype=np.uint64)
+    k = ys.shape[0]
+    handle = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_eq_table(device, ys.ctypes.data if k else None, k, ctypes.byref(handle)), "plonkish_cuda_eq_table")
+    return ResidentScalars._adopt(handle.value, 1 << k, device)
+
+
 def kzg_open_resident(poly: "ResidentScalars", eqs: Sequence["G1Bases"], point):
     """MultilinearKzg::open on a resident polynomial (kzg.rs:276-302): returns the num_vars
     quotient commitments ([k, 8]) and f(point) (Montgomery limbs [4])."""

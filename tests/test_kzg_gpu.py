@@ -185,6 +185,26 @@ def test_batch_commit_keep_then_merge_then_open(pk, oracle):
     pp.release()
 
 
+def test_eq_table_matches_the_product_formula_and_the_oracle(pk, oracle):
+    # MultilinearPolynomial::eq_xy (poly/multilinear.rs:91-130): evals[b] = prod_i (b_i ? y_i : 1 - y_i)
+    for k in (0, 1, 5, 12):
+        y = oracle.random_scalars(max(k, 1), 200 + k)[:k]
+        table = pk.eq_table(y)
+        got = table.to_host()
+        assert len(table) == 1 << k
+        want = oracle.kzg_eq_scalars(y)[k] if k else _fr(oracle, 1).reshape(1, 4)  # same recurrence as the SRS tables (kzg.rs:178-192)
+        assert got.tobytes() == np.ascontiguousarray(want).tobytes()
+        if k == 5:
+            rinv = pow(br.MONT, -1, R)
+            yi = [int.from_bytes(row.tobytes(), "little") * rinv % R for row in y]
+            for b in (0, 1, 6, 21, 31):
+                v = 1
+                for i in range(k):
+                    v = v * (yi[i] if (b >> i) & 1 else (1 - yi[i])) % R
+                assert int.from_bytes(got[b].tobytes(), "little") * rinv % R == v
+        table.release()
+
+
 def test_argument_errors(pk, oracle):
     from plonkish_b200 import _lib, kzg
 

@@ -23,6 +23,14 @@ def test_keccak256_public_known_answers_and_hashlib(oracle):
         assert tr.keccak256(msg).hex() == digest
         assert oracle.keccak256(msg).hex() == digest
     rng = np.random.default_rng(1)
+    # the library's host routine and the Python rounds are the same permutation
+    from plonkish_b200 import _lib
+
+    for _ in range(20):
+        lanes = [int(v) for v in rng.integers(0, 1 << 64, 25, dtype=np.uint64)]
+        arr = np.array(lanes, dtype=np.uint64)
+        _lib.load().plonkish_cuda_keccak_f1600(arr.ctypes.data)
+        assert [int(v) for v in arr] == tr.keccak_f1600(lanes)
     for n in (0, 1, 31, 32, 64, 135, 136, 137, 271, 272, 273, 1000, 5000):
         data = rng.bytes(n)
         assert tr.sha3_256(data) == hashlib.sha3_256(data).digest(), n   # same permutation and sponge, SHA-3 domain byte
@@ -112,7 +120,8 @@ def test_proof_bytes_of_zero_check_and_opening_match_the_oracle():
     comms, resident = kzg.batch_commit(pp, [a, b, c], keep=True)
     t_gpu.write_commitments(comms)                                   # witness commitments (backend/hyperplonk.rs:201-202)
     y = t_gpu.squeeze_challenges(k)                                  # zero-check point (hyperplonk.rs:262)
-    eq = pk.ResidentScalars(eq_table(y))
+    eq = pk.eq_table(_mont(y))                                       # MultilinearPolynomial::eq_xy(y) on the device (classic.rs:57-61)
+    assert eq.to_host().tobytes() == eq_table(y).tobytes()
     challenges, evals = sumcheck.prove_to_transcript([eq] + resident, terms, 0, t_gpu, common=0)
     t_gpu.write_field_elements(evals[1:])                            # evaluations of the witness polynomials (hyperplonk.rs:279-285)
     value = kzg.open_to_transcript(pp, resident[0], _mont(challenges), t_gpu)
