@@ -494,14 +494,17 @@ def run_ours(args) -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]  # per-step boundaries for min / median
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         out = step_device()
+        marks[i].record()
     e1.record()
     barrier()
     t_wall1 = time.time()
     launches = pk.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
+    step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
     if distributed:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -596,7 +599,7 @@ def run_ours(args) -> None:
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "ms_step_min": min(step_ms), "ms_step_median": statistics.median(step_ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
         "config": {
             "workload": f"one BN254 G1 variable_base_msm of {world} x 2^{args.log_n} points (2^{args.log_n} per GPU), "
