@@ -86,3 +86,51 @@ while time.time() < t_end:
         reg.release()
     cases += 1
 print(f"msm fuzz: {cases} random cases x (unregistered, table, plain, prefix) ok", flush=True)
+
+# ---- the callers either side of the MSM: random open / merge / sum-check cases against the oracle
+from plonkish_b200 import kzg
+from plonkish_b200.sumcheck import SumCheckProver
+
+t_end = time.time() + seconds * 0.3
+cases = 0
+one = po.from_canonical(1, po.int_to_limbs(1))[0]
+while time.time() < t_end:
+    k = int(rng.integers(1, 13))
+    seed = int(rng.integers(0, 1 << 30))
+    ss = po.random_scalars(k, seed)
+    pp = kzg.setup(po.generator(), ss)
+    eqs = [pp.eq(i).to_host() for i in range(k + 1)]
+    count = int(rng.integers(1, 6))
+    polys = [po.random_scalars(1 << k, seed + 1 + j) for j in range(count)]
+    comms, res = kzg.batch_commit(pp, polys, keep=True)
+    for p, c in zip(polys, comms):
+        assert c.tobytes() == po.variable_base_msm(p, eqs[k]).tobytes(), ("commit", k)
+    coeffs = po.random_scalars(count, seed + 50)
+    merged = kzg.linear_combination(res, coeffs)
+    merged_h = po.fr_linear_combination(polys, coeffs)
+    assert merged.to_host().tobytes() == merged_h.tobytes(), ("merge", k, count)
+    point = po.random_scalars(k, seed + 60)
+    q_comms, value = kzg.open_resident(pp, merged, point)
+    qs, want = po.quotients(merged_h, point)
+    assert value.tobytes() == want.tobytes() and all(a.tobytes() == po.variable_base_msm(q, eqs[i]).tobytes() for i, (a, q) in enumerate(zip(q_comms, qs))), ("open", k)
+    # a random expression over the same tables
+    nterms = int(rng.integers(1, 7))
+    terms = []
+    for t in range(nterms):
+        nf = int(rng.integers(0 if t else 1, 5))
+        terms.append((one if rng.random() < 0.4 else po.random_scalars(1, seed + 70 + t)[0], [int(i) for i in rng.integers(0, count, nf)]))
+    common = int(rng.integers(-1, count))
+    prover = SumCheckProver(res, terms, common)
+    cur = polys
+    for rnd in range(k):
+        assert prover.round_evals().tobytes() == po.sumcheck_round(cur, terms, common).tobytes(), ("sumcheck", k, rnd)
+        ch = po.random_scalars(1, seed + 90 + rnd)[0]
+        prover.fix_var(ch)
+        cur = [po.fix_var(p, ch) for p in cur]
+    assert prover.final_evals().tobytes() == np.stack([p[0] for p in cur]).tobytes()
+    prover.free()
+    for r in res + [merged]:
+        r.release()
+    pp.release()
+    cases += 1
+print(f"caller fuzz: {cases} random setup / commit / merge / open / sum-check cases ok", flush=True)
