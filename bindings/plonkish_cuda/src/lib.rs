@@ -25,6 +25,7 @@ extern "C" {
     fn plonkish_cuda_kzg_open_bn254(scalars_handle: u64, eq_handles: *const u64, point: *const c_void, num_vars: usize, out_comms: *mut c_void, out_eval: *mut c_void) -> c_int;
     fn plonkish_cuda_fixed_base_msm_bn254_g1(device: c_int, base: *const c_void, scalars: *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_kzg_setup_eqs_bn254(device: c_int, g1: *const c_void, ss: *const c_void, num_vars: usize, handles_out: *mut u64) -> c_int;
+    fn plonkish_cuda_kzg_setup_powers_bn254(device: c_int, g1: *const c_void, s: *const c_void, n: usize, handle: *mut u64) -> c_int;
     fn plonkish_cuda_eq_table(device: c_int, y: *const c_void, num_vars: usize, handle: *mut u64) -> c_int;
     fn plonkish_cuda_sumcheck_new(polys: *const u64, num_polys: usize, num_vars: usize, coeffs: *const c_void, offsets: *const u32, term_polys: *const u32,
                                   num_terms: usize, common_poly: c_int, state: *mut u64) -> c_int;
@@ -248,6 +249,22 @@ impl Drop for ResidentEqs {
             unsafe { plonkish_cuda_bases_release(*h) };
         }
     }
+}
+
+/// The G1 half of `UnivariateKzg::setup` (pcs/univariate/kzg.rs:175-195): `powers_of_s_g1`, built on the GPU and read back
+/// for `UnivariateKzgParam` (the slice stays registered for `commit_coeffs` under the usual (pointer, length) key once the
+/// returned vector is owned by the ProverParam).
+pub fn univariate_powers_of_s_g1(g1: &G1Affine, s: &Fr, poly_size: usize) -> Vec<G1Affine> {
+    init();
+    let mut handle = 0u64;
+    check(
+        unsafe { plonkish_cuda_kzg_setup_powers_bn254(0, g1 as *const G1Affine as *const c_void, s as *const Fr as *const c_void, poly_size, &mut handle) },
+        "plonkish_cuda_kzg_setup_powers_bn254",
+    );
+    let mut out = vec![G1Affine::default(); poly_size];
+    check(unsafe { plonkish_cuda_bases_read(handle, 0, poly_size, out.as_mut_ptr() as *mut c_void) }, "plonkish_cuda_bases_read");
+    unsafe { plonkish_cuda_bases_release(handle) };
+    out
 }
 
 /// `MultilinearPolynomial::eq_xy(y)` as a resident table (the zero-check factor of piop/sum_check/classic.rs:57-61).

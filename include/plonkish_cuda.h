@@ -152,6 +152,11 @@ int plonkish_cuda_fixed_base_msm_bn254_g1(int device, const void *base_affine64,
 int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affine64, const void *ss_mont32, size_t num_vars,
                                       uint64_t *handles_out);
 
+/* The G1 half of UnivariateKzg::setup (pcs/univariate/kzg.rs:175-195) on the device: powers(s).take(n), times g1 by
+ * fixed-base MSM, normalised, registered as one resident slice (powers_of_s_g1, the bases of commit_coeffs,
+ * pcs/univariate/kzg.rs:24-30; any prefix can be used, as trim does at :217-229).  Read back with bases_read. */
+int plonkish_cuda_kzg_setup_powers_bn254(int device, const void *g1_affine64, const void *s_mont32, size_t n, uint64_t *handle);
+
 /* ---- sum check ---------------------------------------------------------
  * ClassicSumCheck<EvaluationsProver>::prove (piop/sum_check/classic.rs:208-240) round by round.  The
  * caller owns the transcript: it writes each round message, squeezes the challenge (classic.rs:226-229)

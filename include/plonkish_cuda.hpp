@@ -127,6 +127,13 @@ inline std::vector<G1Affine> fixed_base_msm(const G1Affine &base, const std::vec
     check(plonkish_cuda_fixed_base_msm_bn254_g1(device, &base, scalars.data(), scalars.size(), out.data()), "plonkish_cuda_fixed_base_msm_bn254_g1");
     return out;
 }
+// The G1 half of UnivariateKzg::setup (pcs/univariate/kzg.rs:175-195): powers_of_s_g1[i] = s^i * g1, i < poly_size,
+// built and kept on the GPU; commit_coeffs (univariate/kzg.rs:24-30) is variable_base_msm(coeffs, powers_of_s_g1).
+inline G1Bases univariate_setup(const G1Affine &g1, const Fr &s, size_t poly_size, int device = 0) {
+    uint64_t h = 0;
+    check(plonkish_cuda_kzg_setup_powers_bn254(device, &g1, &s, poly_size, &h), "plonkish_cuda_kzg_setup_powers_bn254");
+    return G1Bases::adopt(h, poly_size);
+}
 // MultilinearPolynomial::eq_xy(y): eq(x, y) over the hypercube, resident (the zero-check factor, classic.rs:57-61).
 inline MultilinearPolynomial eq_xy(const std::vector<Fr> &y, int device = 0) {
     uint64_t h = 0;

@@ -15,6 +15,7 @@ from .msm import (  # noqa: F401
     eq_table,
     fixed_base_msm,
     kzg_setup_eqs,
+    kzg_setup_powers,
     variable_base_msm,
     variable_base_msm_batch,
     variable_base_msm_many,

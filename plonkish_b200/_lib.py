@@ -35,6 +35,7 @@ EXPORTS = (
     "plonkish_cuda_kzg_open_bn254",
     "plonkish_cuda_fixed_base_msm_bn254_g1",
     "plonkish_cuda_kzg_setup_eqs_bn254",
+    "plonkish_cuda_kzg_setup_powers_bn254",
     "plonkish_cuda_eq_table",
     "plonkish_cuda_keccak_f1600",
     "plonkish_cuda_sumcheck_new",
@@ -97,6 +98,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_many.argtypes = [vp, vp, vp, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_gather.argtypes = [vp, vp, sz, vp]
+    lib.plonkish_cuda_kzg_setup_powers_bn254.argtypes = [ci, vp, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_keccak_f1600.argtypes = [vp]
     lib.plonkish_cuda_keccak_f1600.restype = None
     lib.plonkish_cuda_eq_table.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]

@@ -1919,6 +1919,58 @@ extern "C" int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affi
     return PLONKISH_CUDA_OK;
 }
 
+// UnivariateKzg::setup's G1 half (pcs/univariate/kzg.rs:175-195) on the device: powers(s).take(n), times g1 by
+// fixed-base MSM, normalised, registered as one resident slice (powers_of_s_g1, the bases of commit_coeffs,
+// univariate/kzg.rs:24-30).  The G2 half (two points for the verifier) stays with the caller.
+extern "C" int plonkish_cuda_kzg_setup_powers_bn254(int device, const void *g1_affine64, const void *s, size_t n, uint64_t *handle) {
+    if (!g1_affine64 || !s || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "kzg_setup_powers: null argument or n == 0");
+    if (n > ((size_t)1 << 27)) return fail(PLONKISH_CUDA_E_INVALID, "kzg_setup_powers: n = %zu exceeds 2^27", n);
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "kzg_setup_powers: device %d not initialised", device);
+    BasesEntry e;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CUDA_TRY(cudaSetDevice(c->dev));
+        const size_t batch = n < FIXED_BATCH ? n : FIXED_BATCH;
+        void *d_pow = nullptr, *d_pts = nullptr, *d_s = nullptr;
+        FixedTable ft;
+        auto cleanup = [&] { cudaFree(d_pow); cudaFree(d_pts); cudaFree(d_s); ft.release(); };
+        if (cudaMalloc(&d_pow, n * PLONKISH_CUDA_SCALAR_BYTES) != cudaSuccess || cudaMalloc(&d_pts, n * PLONKISH_CUDA_AFFINE_BYTES) != cudaSuccess ||
+            cudaMalloc(&d_s, PLONKISH_CUDA_SCALAR_BYTES) != cudaSuccess) {
+            cleanup();
+            return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_powers: out of device memory for %zu points", n);
+        }
+        if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+        CUDA_TRY(cudaMemcpyAsync(d_s, s, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync((char *)c->d_out + 384, g1_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+        pk_enqueue_fr_powers(d_s, n, d_pow, c->stream);
+        int rc = fixed_table_build(c, (char *)c->d_out + 384, batch, ft);
+        if (rc) { cleanup(); return rc; }
+        for (size_t done = 0; done < n; done += batch) {
+            const size_t cnt = n - done < batch ? n - done : batch;
+            pk_enqueue_fixed_base((const char *)d_pow + done * PLONKISH_CUDA_SCALAR_BYTES, (u32)cnt, (const affine *)ft.table, (xyzz *)ft.tmp,
+                                  (affine *)((char *)d_pts + done * PLONKISH_CUDA_AFFINE_BYTES), c->stream);
+        }
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            cleanup();
+            return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_powers: kernel sequence failed");
+        }
+        cudaFree(d_pow); d_pow = nullptr;
+        ft.release();
+        void *d = nullptr;
+        uint32_t tc = 0;
+        bool owns = true;
+        rc = make_resident(c, d_pts, true, n, 0, &d, &tc, &owns);
+        if (rc) { cleanup(); return rc; }
+        if (!owns) { d_pts = nullptr; owns = true; }  // plain slice: the entry adopts the points as they are
+        e.n_shards = 1; e.dev = device; e.n = n; e.owns = true;
+        e.d_ptr.push_back(d); e.shard_n.push_back(n); e.table_c.push_back(tc);
+        cleanup();
+    }
+    *handle = publish(e);
+    return PLONKISH_CUDA_OK;
+}
+
 // ================================================================== sum check
 // ClassicSumCheck<EvaluationsProver>::prove (piop/sum_check/classic.rs:208-240) as a round-by-round
 // state on the device: the caller owns the transcript (it hashes each round message to draw the

@@ -145,6 +145,34 @@ inline void pk_enqueue_eq_scalars(const void *d_ss, u32 num_vars, void *out, u32
     }
 }
 
+// ------------------------------------------------------------------ powers of s
+// powers(s).take(n) (pcs/univariate/kzg.rs:180): out[i] = s^i.  Thread t starts its chunk of PK_POW_CHUNK consecutive
+// exponents at s^(t * chunk) (square-and-multiply) and walks it with one product per element.
+#define PK_POW_CHUNK 256
+__global__ void __launch_bounds__(128) k_fr_powers(const uint4 *__restrict__ s_ptr, size_t n, uint4 *__restrict__ out) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_POW_CHUNK;
+    if (first >= n) return;
+    const fe s = load_fe_plain(s_ptr);
+    fe one;  // R mod r
+    one.l[0] = 0x4ffffffbu; one.l[1] = 0xac96341cu; one.l[2] = 0x9f60cd29u; one.l[3] = 0x36fc7695u;
+    one.l[4] = 0x7879462eu; one.l[5] = 0x666ea36fu; one.l[6] = 0x9a07df2fu; one.l[7] = 0x0e0a77c1u;
+    fe cur = one;
+    for (int bit = 63; bit >= 0; --bit) {  // cur = s^first
+        cur = fr_mul(cur, cur);
+        if ((first >> bit) & 1) cur = fr_mul(cur, s);
+    }
+    const size_t end = (first + PK_POW_CHUNK < n) ? first + PK_POW_CHUNK : n;
+    for (size_t i = first; i < end; ++i) {
+        store_fe(out + 2 * i, cur);
+        cur = fr_mul(cur, s);
+    }
+}
+inline void pk_enqueue_fr_powers(const void *d_s, size_t n, void *out, pk_stream_t stream) {
+    const size_t threads = (n + PK_POW_CHUNK - 1) / PK_POW_CHUNK;
+    PK_LAUNCH(k_fr_powers, dim3((unsigned)((threads + 127) / 128)), dim3(128), 0, stream, (const uint4 *)d_s, n, (uint4 *)out);
+}
+
 // ------------------------------------------------------------- fixed-base MSM
 // Signed 16-bit windows: 16 windows cover 254 bits plus the carry, the table holds
 // d * 2^(16w) * base for d = 1..2^15 (16 x 32768 x 64 B = 32 MiB, L2 resident); the

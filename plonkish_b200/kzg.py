@@ -156,6 +156,13 @@ def open_to_transcript(pp: MultilinearKzgProverParam, poly: ResidentScalars, poi
     return value
 
 
+def univariate_setup(g1: np.ndarray, s: np.ndarray, poly_size: int, device: int = 0) -> G1Bases:
+    """The G1 half of UnivariateKzg::setup (pcs/univariate/kzg.rs:175-195): powers_of_s_g1, built and kept on the GPU."""
+    from .msm import kzg_setup_powers
+
+    return kzg_setup_powers(g1, s, poly_size, device=device)
+
+
 def commit_coeffs(powers_of_s_g1: G1Bases, coeffs: np.ndarray) -> np.ndarray:
     """pcs/univariate/kzg.rs:24-30: variable_base_msm(coeffs, &powers_of_s_g1[..coeffs.len()])."""
     return variable_base_msm(coeffs, powers_of_s_g1)

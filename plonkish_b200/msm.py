@@ -285,6 +285,17 @@ def kzg_setup_eqs(g1, ss, device: int = 0):
     return [G1Bases._adopt(h, 1 << i, device) for i, h in enumerate(handles)]
 
 
+def kzg_setup_powers(g1, s, n: int, device: int = 0) -> "G1Bases":
+    """The G1 half of UnivariateKzg::setup (pcs/univariate/kzg.rs:175-195) on the GPU: powers_of_s_g1[i] = s^i * g1
+    for i < n, resident."""
+    g = np.ascontiguousarray(g1, dtype=np.uint64).reshape(8)
+    sv = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+    handle = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_kzg_setup_powers_bn254(device, g.ctypes.data, sv.ctypes.data, n, ctypes.byref(handle)),
+               "plonkish_cuda_kzg_setup_powers_bn254")
+    return G1Bases._adopt(handle.value, n, device)
+
+
 def variable_base_msm_many(scalars_list: Sequence, bases_list: Sequence["G1Bases"]) -> np.ndarray:
     """Independent MSMs of different sizes, MSM j against the resident slice bases_list[j] ->
     [count, 8] affine points.  The quotient commitments of MultilinearKzg::open

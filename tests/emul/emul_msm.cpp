@@ -156,6 +156,7 @@ void emul_fr_lincomb(const void *const *polys, const void *coeffs, u32 count, u3
         PK_LAUNCH(k_fr_lincomb, dim3(3), dim3(64), 0, 0, a, (size_t)n, (uint4 *)out);
     }
 }
+void emul_fr_powers(const void *s, u32 n, void *out) { pk_enqueue_fr_powers(s, n, out, 0); }
 void emul_eq_scalars(const void *ss, u32 num_vars, void *out) { pk_enqueue_eq_scalars(ss, num_vars, out, 2, 0); }
 // out[i] = scalars[i] * base through the signed-window table.
 void emul_fixed_base(const void *base64, const void *scalars, u32 n, void *out_affine) {

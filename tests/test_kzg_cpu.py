@@ -35,6 +35,7 @@ def emul():
     lib.emul_fr_lincomb.argtypes = [vp, vp, u32, u32, vp]
     lib.emul_eq_scalars.argtypes = [vp, u32, vp]
     lib.emul_fixed_base.argtypes = [vp, vp, u32, vp]
+    lib.emul_fr_powers.argtypes = [vp, u32, vp]
     return lib
 
 
@@ -127,6 +128,16 @@ def test_emulated_merge_and_eq_kernels(emul, oracle):
         want = oracle.kzg_eq_scalars(ss) if k else [_fr(oracle, 1).reshape(1, 4)]
         for i, e in enumerate(want):
             assert out[(1 << i) - 1: (2 << i) - 1].tobytes() == np.ascontiguousarray(e).tobytes(), (k, i)
+
+
+def test_emulated_powers_kernel(emul, oracle):
+    # powers(s).take(n) (pcs/univariate/kzg.rs:180), chunks of 256 exponents per thread, ragged tail
+    s = oracle.random_scalars(1, 77)[0]
+    si = _ints(s)[0]
+    for n in (1, 2, 255, 256, 257, 1000):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        emul.emul_fr_powers(s.ctypes.data, n, out.ctypes.data)
+        assert _ints(out) == [pow(si, i, R) for i in range(n)], n
 
 
 def test_emulated_fixed_base_kernels(emul, oracle):

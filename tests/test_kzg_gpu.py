@@ -185,6 +185,26 @@ def test_batch_commit_keep_then_merge_then_open(pk, oracle):
     pp.release()
 
 
+def test_univariate_setup_matches_powers_times_generator(pk, oracle):
+    # UnivariateKzg::setup, G1 half (pcs/univariate/kzg.rs:175-195): powers_of_s_g1[i] = s^i * g1; commit_coeffs on it
+    from plonkish_b200 import kzg
+
+    g = oracle.generator()
+    s = oracle.random_scalars(1, 301)[0]
+    rinv = pow(br.MONT, -1, R)
+    si = int.from_bytes(s.tobytes(), "little") * rinv % R
+    for n in (1, 5, 300, 1 << 12):
+        srs = kzg.univariate_setup(g, s, n)
+        powers = np.stack([_fr(oracle, pow(si, i, R)) for i in range(n)])
+        want = oracle.fixed_base_msm(g, powers)
+        assert srs.to_host().tobytes() == want.tobytes(), n
+        coeffs = oracle.random_scalars(n, 302)
+        assert kzg.commit_coeffs(srs, coeffs).tobytes() == oracle.variable_base_msm(coeffs, want).tobytes()
+        if n > 4:  # a prefix, as trim hands out (univariate/kzg.rs:217-229)
+            assert kzg.commit_coeffs(srs, coeffs[: n // 2]).tobytes() == oracle.variable_base_msm(coeffs[: n // 2], want[: n // 2]).tobytes()
+        srs.release()
+
+
 def test_eq_table_matches_the_product_formula_and_the_oracle(pk, oracle):
     # MultilinearPolynomial::eq_xy (poly/multilinear.rs:91-130): evals[b] = prod_i (b_i ? y_i : 1 - y_i)
     for k in (0, 1, 5, 12):
