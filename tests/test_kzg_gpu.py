@@ -241,3 +241,46 @@ def test_argument_errors(pk, oracle):
     with pytest.raises(_lib.PlonkishCudaError):
         _lib.check(_lib.lib().plonkish_cuda_scalars_release(987654321), "scalars_release")
     pp.release()
+
+
+def test_widened_rows_on_a_second_device(pk, oracle):
+    # every handle carries its device: the same flow on cuda:1 while cuda:0 holds other state
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from plonkish_b200 import kzg
+    from plonkish_b200.sumcheck import SumCheckProver
+
+    k = 10
+    ss = oracle.random_scalars(k, 401)
+    pp0 = kzg.setup(oracle.generator(), ss, device=0)  # state on device 0 as well
+    pp = kzg.setup(oracle.generator(), ss, device=1)
+    eqs = [pp.eq(i).to_host() for i in range(k + 1)]
+    assert eqs[k].tobytes() == pp0.eq(k).to_host().tobytes()
+    polys = [oracle.random_scalars(1 << k, 410 + j) for j in range(2)]
+    res = [pk.ResidentScalars(p, device=1) for p in polys]
+    for p, r in zip(polys, res):
+        assert kzg.commit(pp, r).tobytes() == oracle.variable_base_msm(p, eqs[k]).tobytes()
+    coeffs = oracle.random_scalars(2, 420)
+    merged = kzg.linear_combination(res, coeffs)
+    assert merged.device == 1
+    merged_h = oracle.fr_linear_combination(polys, coeffs)
+    point = oracle.random_scalars(k, 421)
+    comms, value = kzg.open_resident(pp, merged, point)
+    qs, want = oracle.quotients(merged_h, point)
+    assert value.tobytes() == want.tobytes()
+    assert all(c.tobytes() == oracle.variable_base_msm(q, eqs[i]).tobytes() for i, (c, q) in enumerate(zip(comms, qs)))
+    eq = pk.eq_table(point, device=1)
+    terms = [(_fr(oracle, 1), [1, 2])]
+    prover = SumCheckProver([eq] + res, terms, common=0)
+    assert prover.round_evals().tobytes() == oracle.sumcheck_round([eq.to_host()] + polys, terms, 0).tobytes()
+    prover.free()
+    # mixing devices is refused
+    with pytest.raises(Exception):
+        kzg.open_resident(pp0, merged, point)
+    assert pk.fixed_base_msm(oracle.generator(), polys[0][:50], device=1).tobytes() == oracle.fixed_base_msm(oracle.generator(), polys[0][:50]).tobytes()
+    for r in res + [merged, eq]:
+        r.release()
+    pp.release()
+    pp0.release()
