@@ -130,6 +130,13 @@ static int pool_alloc(Ctx *c, void **p, size_t bytes) {
 static void pool_free(Ctx *c, void *p) {
     if (p && cudaFreeAsync(p, c->stream) != cudaSuccess) cudaGetLastError();
 }
+// Returns a pooled buffer on every exit path unless release() hands it on.
+struct PoolGuard {
+    Ctx *c;
+    void *p;
+    ~PoolGuard() { pool_free(c, p); }
+    void *release() { void *q = p; p = nullptr; return q; }
+};
 
 // Contexts are created on first use of a device, so a one-process-per-GPU rank only
 // ever touches its own GPU.  Caller must not hold g_mu.
@@ -665,10 +672,13 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     CUDA_TRY(cudaSetDevice(c->dev));
     const size_t bytes = n * PLONKISH_CUDA_SCALAR_BYTES;
     std::vector<void *> kept(count, nullptr);
+    struct KeptGuard {  // frees the kept buffers unless the call succeeds (publish takes them over)
+        Ctx *c; std::vector<void *> &v; bool armed = true;
+        ~KeptGuard() { if (armed) for (void *p : v) pool_free(c, p); }
+    } kept_guard{c, kept};
     if (keep) {
         for (size_t j = 0; j < count; ++j) {
             if (pool_alloc(c, &kept[j], bytes) != 0) {
-                for (size_t i = 0; i < j; ++i) pool_free(c, kept[i]);
                 return fail(PLONKISH_CUDA_E_CUDA, "msm_batch: cannot keep %zu x %zu bytes of scalars resident", count, bytes);
             }
         }
@@ -706,6 +716,7 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
     if ((rc = mark_done(c, c->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    kept_guard.armed = false;
     if (keep)
         for (size_t j = 0; j < count; ++j) keep[j] = publish_scalars(c->dev, kept[j], n);
     for (size_t j = 0; j < count; ++j) timer_report(n, t0);
@@ -1608,9 +1619,10 @@ extern "C" int plonkish_cuda_scalars_register(int device, const void *scalars, s
     void *d = nullptr;
     int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
+    PoolGuard d_guard{c, d};
     CUDA_TRY(cudaMemcpyAsync(d, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *handle = publish_scalars(device, d, n);
+    *handle = publish_scalars(device, d_guard.release(), n);
     return PLONKISH_CUDA_OK;
 }
 
@@ -1673,7 +1685,9 @@ extern "C" int plonkish_cuda_eq_table(int device, const void *y, size_t num_vars
     void *all = nullptr, *out = nullptr;
     int rc = pool_alloc(c, &all, (total + num_vars + 1) * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
-    if ((rc = pool_alloc(c, &out, n * PLONKISH_CUDA_SCALAR_BYTES))) { pool_free(c, all); return rc; }
+    PoolGuard all_guard{c, all};
+    if ((rc = pool_alloc(c, &out, n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    PoolGuard out_guard{c, out};
     void *d_y = (char *)all + total * PLONKISH_CUDA_SCALAR_BYTES;
     if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
     if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_y, y, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
@@ -1681,8 +1695,7 @@ extern "C" int plonkish_cuda_eq_table(int device, const void *y, size_t num_vars
     CUDA_TRY(cudaMemcpyAsync(out, (char *)all + (n - 1) * PLONKISH_CUDA_SCALAR_BYTES, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    pool_free(c, all);
-    *handle = publish_scalars(device, out, n);
+    *handle = publish_scalars(device, out_guard.release(), n);
     return PLONKISH_CUDA_OK;
 }
 
@@ -1731,6 +1744,7 @@ extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handl
     void *d = nullptr;
     int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
+    PoolGuard d_guard{c, d};
     size_t blocks = (n + 255) / 256;
     if (blocks > (size_t)c->sm_count * 8) blocks = (size_t)c->sm_count * 8;
     for (size_t done = 0; done < count; done += PK_LINCOMB_MAX) {
@@ -1745,7 +1759,7 @@ extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handl
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *out_handle = publish_scalars(c->dev, d, n);
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
     return PLONKISH_CUDA_OK;
 }
 
