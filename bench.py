@@ -10,10 +10,13 @@ limbs) and known-discrete-log bases B_i = (a + i*d)G generated on the GPU.
           (reference: msm.rs:101-114 chunk-per-thread + fold).
 `value`  device-resident inputs (scalars and bases already in HBM), CUDA-event timed.
 `e2e`    N = 1: the C-ABI host call plonkish_cuda_msm_bn254_g1 with the step's scalars in
-         pinned host memory and the bases resident (registered once, like the SRS of a
-         ProverParam); N > 1: pinned host scalars -> H2D -> sharded MSM -> result to host.
+         PAGEABLE host memory (what a Rust Vec<Fr> is) and the bases resident (registered
+         once, like the SRS of a ProverParam); `e2e_pinned` is the same from pinned memory.
+         N > 1: host scalars -> H2D -> sharded MSM -> NCCL gather -> result to host.
 `--impl reference`  the CPU restatement of the reference algorithm (oracle/, C port of
-         msm.rs:84-181, one pthread per chunk like rayon) on a bounded sample.
+         msm.rs:84-181, one pthread per chunk like rayon) on the same 2^LOG_N points per step.
+Every timed leg is checked against an independent answer (known discrete log of the synthetic
+bases, the KZG trapdoor of the synthetic SRS, or the CPU port) and carries "parity_checked".
 """
 from __future__ import annotations
 
@@ -42,11 +45,15 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24, help="log2 of the points per GPU")
-    ap.add_argument("--cpu-log-n", type=int, default=21, help="log2 of the cpu_baseline sample")
+    ap.add_argument("--cpu-log-n", type=int, default=24, help="log2 of the cpu_baseline sample (capped at --log-n)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="the reference arm stops adding steps beyond this many seconds")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plain-bases", action="store_true", help="do not expand the resident bases into the table of window multiples")
-    ap.add_argument("--prove-k", type=int, default=24, help="k of the HyperPlonk prove MSM-sequence surrogate (0 = skip)")
+    ap.add_argument("--prove-k", type=int, default=24, help="k of the HyperPlonk prove legs (0 = skip)")
+    ap.add_argument("--reps", type=int, default=3, help="repetitions of every auxiliary leg (min / median reported)")
+    ap.add_argument("--no-skew", action="store_true")
+    ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip rank 0's single-process multi-GPU leg")
     return ap.parse_args()
 
 
@@ -112,7 +119,8 @@ class ClockSampler:
 
 # -------------------------------------------------------------------- reference arm
 def run_reference(args) -> None:
-    """CPU restatement of the reference's variable_base_msm on this box's host cores."""
+    """CPU restatement of the reference's variable_base_msm on this box's host cores, on the same 2^log_n points per
+    step as the GPU arm (rank 0 only under torchrun)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -120,35 +128,48 @@ def run_reference(args) -> None:
 
     po.build()
     cores = po.host_threads()
-    log_n = min(args.log_n, args.cpu_log_n)
+    log_n = args.log_n
     n = 1 << log_n
-    scalars = po.random_scalars(n, seed=1234)
+    scalars = po.random_scalars(n, seed=1000)
     bases = po.known_dlog_bases(3, 5, n)
     want = po.known_dlog_answer(3, 5, scalars)
+    t_all = time.perf_counter()
+    warm = 0
     for _ in range(min(args.warmup, 1)):
+        t = time.perf_counter()
         po.variable_base_msm(scalars, bases, cores)
+        warm += 1
+        if time.perf_counter() - t > 20.0:
+            break
     times = []
-    for _ in range(args.steps):
+    for i in range(args.steps):
         t = time.perf_counter()
         got = po.variable_base_msm(scalars, bases, cores)
         times.append(time.perf_counter() - t)
         assert (got == want).all(), "oracle result differs from the known-dlog answer"
+        # the whole run has to end within minutes: stop early when the next step would not fit
+        if i + 1 < args.steps and (time.perf_counter() - t_all) + times[-1] > args.cpu_budget_s:
+            break
     sec = sum(times) / len(times)
     value = n / sec / 1e6
-    sample = f"2^{log_n} points per step (bounded sample of the 2^{args.log_n}-point workload), {cores} pthreads, C port of msm.rs:84-181"
+    sample = (f"2^{log_n} points per step (the GPU arm's workload), {len(times)} timed steps of {args.steps} requested "
+              f"(budget {args.cpu_budget_s:.0f} s), {cores} pthreads, C port of msm.rs:84-181, window = floor(ln(n / {cores}))")
     emit({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
-        "config": {"workload": f"BN254 G1 variable_base_msm, uniform random scalars, known-dlog bases, 2^{log_n} points/step on host cores"},
+        "config": {"workload": f"BN254 G1 variable_base_msm, uniform random scalars, known-dlog bases, 2^{log_n} points/step on host cores",
+                   "points_per_step": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "parity_checked": True,
         "gpu_launches": 0,
     })
 
 
-# ------------------------------------------------- HyperPlonk::prove MSM-sequence surrogate
+# ----------------------------------------------------------------------- small helpers
 FQ_MODULUS = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 
 
 def g1_generator(np):
@@ -157,7 +178,49 @@ def g1_generator(np):
     return np.frombuffer(b, dtype=np.uint64).copy()
 
 
-def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
+def pinned_copy(torch, np, arr):
+    t = torch.empty(arr.shape, dtype=torch.int64).pin_memory()
+    h = t.numpy().view(np.uint64)
+    h[:] = arr
+    return h, t  # keep t alive
+
+
+def timed_reps(fn, reps: int):
+    """fn() `reps` times after one warm-up -> (last result, {"ms_min", "ms_median", "ms_all"})."""
+    fn()
+    out, ms = None, []
+    for _ in range(max(reps, 1)):
+        t0 = time.perf_counter()
+        out = fn()
+        ms.append((time.perf_counter() - t0) * 1e3)
+    return out, {"ms_min": min(ms), "ms_median": statistics.median(ms), "ms_all": [round(v, 3) for v in ms]}
+
+
+def fr_int(limbs) -> int:
+    import numpy as np
+
+    return int.from_bytes(np.ascontiguousarray(limbs, dtype=np.uint64).tobytes(), "little") * pow(1 << 256, -1, FR_MODULUS) % FR_MODULUS
+
+
+class Trapdoor:
+    """The synthetic SRS has a known trapdoor: eqs[k][j] = eq_j(ss) * G (kzg.rs:174-212), so the commitment of a
+    multilinear polynomial f of i variables against eqs[i] is f(ss[:i]) * G — one multilinear evaluation (threaded
+    field arithmetic in the oracle) and one scalar multiplication, independent of the GPU path and of the MSM size."""
+
+    def __init__(self, po, np, ss):
+        self.po, self.np, self.ss = po, np, ss
+        self.cores = po.host_threads()
+        self.g = po.generator()
+
+    def commit(self, evals):
+        evals = self.np.ascontiguousarray(evals, dtype=self.np.uint64).reshape(-1, 4)
+        k = evals.shape[0].bit_length() - 1
+        v = self.po.evaluate_multilinear(evals, self.ss[:k], self.cores)
+        return self.po.scalar_mul(self.g, fr_int(v))
+
+
+# ------------------------------------------------- HyperPlonk::prove MSM-sequence surrogate
+def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool, reps: int):
     """The MSM calls HyperPlonk::prove makes for vanilla_plonk at 2^k rows (SURVEY.md §3.1):
     4 commits of 2^k points (3 witness polys + 1 permutation z-poly, backend/hyperplonk.rs:201,
     251-252) and the k quotient commitments of MultilinearKzg::open with 2^(k-1), ..., 2, 1 points
@@ -167,7 +230,9 @@ def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
                        quotients are stand-ins of the right sizes);
       gpu_resident_ms  the committed polynomials stay in HBM (batch_commit keep), g_prime is merged there
                        (multilinear.rs:203-213) and open() computes its quotients there (multilinear.rs:72-107):
-                       the same 4 + k commitments plus the real quotient arithmetic, no scalar uploaded twice."""
+                       the same 4 + k commitments plus the real quotient arithmetic, no scalar uploaded twice.
+    Parity: every commitment against the SRS trapdoor (Trapdoor); with cpu=True also against the CPU port's MSMs."""
+    from oracle import pyoracle as po
     from plonkish_b200 import kzg
 
     n = 1 << k
@@ -177,12 +242,7 @@ def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
     pp = kzg.setup(g1_generator(np), ss)
     setup_s = time.perf_counter() - t0
     regs = pp.eqs
-    polys = []
-    for j in range(4):
-        t = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-        h = t.numpy().view(np.uint64)
-        h[:] = pk.random_scalars(n, seed=4242 + j)
-        polys.append(h)
+    polys = [pk.random_scalars(n, seed=4242 + j) for j in range(4)]   # pageable, like poly.evals()
     host = polys[0]
     coeffs = pk.random_scalars(4, seed=78)
     point = pk.random_scalars(k, seed=79)
@@ -203,19 +263,23 @@ def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
             r.release()
         return list(c3) + list(c1), q_comms, value
 
-    run()
-    t0 = time.perf_counter()
-    outs = run()
-    gpu_ms = (time.perf_counter() - t0) * 1e3
-    run_resident()
-    t0 = time.perf_counter()
-    comms, q_comms, value = run_resident()
-    resident_ms = (time.perf_counter() - t0) * 1e3
-    res = {"k": k, "msm_calls": 4 + k, "points": 4 * n + n - 1, "gpu_ms": gpu_ms, "gpu_resident_ms": resident_ms,
-           "srs_setup_on_device_s": setup_s, "srs_points": 2 * n - 1}
+    outs, t_host = timed_reps(run, reps)
+    (comms, q_comms, value), t_res = timed_reps(run_resident, reps)
+    res = {"k": k, "msm_calls": 4 + k, "points": 4 * n + n - 1, "gpu_ms": t_host["ms_min"], "gpu_ms_median": t_host["ms_median"],
+           "gpu_resident_ms": t_res["ms_min"], "gpu_resident_ms_median": t_res["ms_median"], "reps": reps,
+           "srs_setup_on_device_s": setup_s, "srs_points": 2 * n - 1, "host_scalars": "pageable"}
+    # ---- parity through the trapdoor: commit(f) = f(ss) * G
+    td = Trapdoor(po, np, ss)
+    want_commits = [td.commit(p) for p in polys]
+    ok = all((a == b).all() for a, b in zip(outs[:4], want_commits)) and all((a == b).all() for a, b in zip(comms, want_commits))
+    ok = ok and all((outs[4 + j] == td.commit(host[: 1 << i])).all() for j, i in enumerate(reversed(range(k))))
+    g_prime_h = po.fr_linear_combination(polys, coeffs)
+    qs, want_value = po.quotients(g_prime_h, point)
+    ok = ok and (value == want_value).all() and all((q_comms[i] == td.commit(qs[i])).all() for i in range(k))
+    res["parity_checked"] = bool(ok)
+    res["parity_how"] = "every commitment == f(ss) * G for the SRS trapdoor ss (oracle field arithmetic + one scalar multiplication); f(point) vs the oracle's quotients"
+    assert ok, f"prove MSM sequence k={k}: a commitment differs from the trapdoor answer"
     if cpu:
-        from oracle import pyoracle as po
-
         cores = po.host_threads()
         eqs_h = [r.to_host() for r in regs]
         t0 = time.perf_counter()
@@ -233,25 +297,28 @@ def prove_msm_sequence(pk, torch, np, k: int, dev, cpu: bool):
         res["cpu_resident_ms"] = (t_commit + time.perf_counter() - t0) * 1e3
         res["resident_bit_exact_vs_cpu"] = bool(all((a == b).all() for a, b in zip(comms, ref)) and all((a == b).all() for a, b in zip(q_comms, ref_q))
                                                 and (value == want_value).all())
+        assert res["bit_exact_vs_cpu"] and res["resident_bit_exact_vs_cpu"]
     pp.release()
     return res
 
 
-def srs_setup_bench(pk, torch, np, k: int, cpu: bool):
+def srs_setup_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     """fixed_base_msm + batch_normalize (msm.rs:16-31, 50-81; kzg.rs:195-208) on the GPU: 2^22 scalars host to host, and the
     CPU port on a bounded sample with the window the reference would pick for a 2^k setup."""
+    from oracle import pyoracle as po
+
     n = 1 << 22
     sc = pk.random_scalars(n, seed=91)
     g = g1_generator(np)
-    pk.fixed_base_msm(g, sc[: 1 << 16])
-    t0 = time.perf_counter()
-    got = pk.fixed_base_msm(g, sc)
-    sec = time.perf_counter() - t0
-    res = {"what": "fixed_base_msm + batch_normalize of 2^22 scalars, host scalars in, affine points out (table build included)",
-           "gpu_mpoints_per_s": n / sec / 1e6, "gpu_ms": sec * 1e3}
+    got, t = timed_reps(lambda: pk.fixed_base_msm(g, sc), reps)
+    res = {"what": "fixed_base_msm + batch_normalize of 2^22 scalars, pageable host scalars in, affine points out (table build included)",
+           "gpu_mpoints_per_s": n / t["ms_min"] / 1e3, "gpu_ms": t["ms_min"], "gpu_ms_median": t["ms_median"], "reps": reps}
+    # parity: sum_i got[i] = (sum_i sc[i]) * G on a strided sample through the oracle, and (cpu) the CPU port element-wise
+    idx = np.arange(0, n, n // 4096)
+    spot = all((got[i] == po.scalar_mul(g, fr_int(sc[i]))).all() for i in idx[:64])
+    res["parity_checked"] = bool(spot)
+    res["parity_how"] = "64 strided outputs == scalar * G by the oracle's double-and-add" + ("; first 2^17 outputs vs the CPU port" if cpu else "")
     if cpu:
-        from oracle import pyoracle as po
-
         m = 1 << 17
         window = po.window_size((2 << k) - 2)
         cores = po.host_threads()
@@ -260,18 +327,23 @@ def srs_setup_bench(pk, torch, np, k: int, cpu: bool):
         sec_c = time.perf_counter() - t0
         res.update({"cpu_mpoints_per_s": m / sec_c / 1e6, "cpu_cores": cores, "cpu_sample": f"2^17 scalars, window {window} (table build included)",
                     "bit_exact_vs_cpu": bool((got[:m] == want).all())})
+        res["parity_checked"] = bool(spot and res["bit_exact_vs_cpu"])
+    assert res["parity_checked"], "fixed_base_msm differs from the oracle"
     return res
 
 
-def sum_check_bench(pk, torch, np, k: int, cpu: bool):
+def sum_check_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     """The zero check of HyperPlonk::prove for vanilla_plonk (backend/hyperplonk.rs:262-277) as ClassicSumCheck runs it
     (piop/sum_check/classic.rs:208-240): 9 tables (eq, 5 selectors, 3 witness columns) of 2^k evaluations, degree 4,
     k rounds of round-polynomial evaluations + table folds on the GPU; the challenges are stand-ins for the transcript's.
-    CPU: the oracle's restatement of the same rounds, one thread, on tables of 2^18 evaluations."""
+    Parity: every round message and the final evaluations against the oracle's restatement on all host cores (the same
+    2^k tables); cpu_ms is the oracle's single-threaded time at k = 18."""
+    from oracle import pyoracle as po
     from plonkish_b200 import sumcheck
 
     n = 1 << k
-    tables = [pk.ResidentScalars(pk.random_scalars(n, seed=300 + i)) for i in range(9)]
+    host_tables = [pk.random_scalars(n, seed=300 + i) for i in range(9)]
+    tables = [pk.ResidentScalars(t) for t in host_tables]
     one = sumcheck._to_mont(1)
     terms = [(one, [1, 6]), (one, [2, 7]), (one, [3, 6, 7]), (one, [4, 8]), (one, [5])]
     chal = pk.random_scalars(k, seed=399)
@@ -286,60 +358,55 @@ def sum_check_bench(pk, torch, np, k: int, cpu: bool):
         prover.free()
         return msgs, finals
 
-    run()
-    t0 = time.perf_counter()
-    msgs, finals = run()
-    gpu_ms = (time.perf_counter() - t0) * 1e3
+    (msgs, finals), t = timed_reps(run, reps)
     res = {"what": "zero check of vanilla_plonk as ClassicSumCheck<EvaluationsProver> runs it: 9 resident tables of 2^k evaluations, degree 4, "
                    "k rounds (round-polynomial evaluations at X = 1..4 + fold of every table), stand-in challenges",
-           "k": k, "gpu_ms": gpu_ms, "gpu_mpairs_per_s_first_round_equiv": (n - 1) / gpu_ms / 1e3}
+           "k": k, "gpu_ms": t["ms_min"], "gpu_ms_median": t["ms_median"], "reps": reps,
+           "gpu_mpairs_per_s_first_round_equiv": (n - 1) / t["ms_min"] / 1e3}
+    cores = po.host_threads()
+    cur, ok = host_tables, True
+    t0 = time.perf_counter()
+    for rnd in range(k):
+        ok = ok and msgs[rnd].tobytes() == po.sumcheck_round(cur, terms, 0, num_threads=cores if len(cur[0]) >= 1 << 12 else 1).tobytes()
+        cur = [po.fix_var(p, chal[rnd], cores if len(p) >= 1 << 14 else 1) for p in cur]
+    ok = ok and finals.tobytes() == np.stack([p[0] for p in cur]).tobytes()
+    res.update({"parity_checked": bool(ok), "parity_how": f"all {k} round messages and the 9 final evaluations == the oracle's restatement on {cores} threads",
+                "oracle_check_s": time.perf_counter() - t0})
+    assert ok, "sum-check rounds differ from the oracle"
     if cpu:
-        from oracle import pyoracle as po
-
         kc = min(18, k)
-        host = [t.to_host(0, 1 << kc) for t in tables]
-        sub = [pk.ResidentScalars(h) for h in host]
-        prover = sumcheck.SumCheckProver(sub, terms, common=0)
-        ok = True
+        host = [t_[: 1 << kc] for t_ in host_tables]
         cur = host
         t0 = time.perf_counter()
-        ref = []
         for rnd in range(kc):
-            ref.append(po.sumcheck_round(cur, terms, 0))
+            po.sumcheck_round(cur, terms, 0)
             cur = [po.fix_var(p, chal[rnd]) for p in cur]
         cpu_ms = (time.perf_counter() - t0) * 1e3
-        for rnd in range(kc):
-            ok = ok and prover.round_evals().tobytes() == ref[rnd].tobytes()
-            prover.fix_var(chal[rnd])
-        ok = ok and prover.final_evals().tobytes() == np.stack([p[0] for p in cur]).tobytes()
-        prover.free()
-        for r in sub:
-            r.release()
-        res.update({"cpu_ms": cpu_ms, "cpu_k": kc, "cpu_cores": 1, "cpu_mpairs_per_s": ((1 << kc) - 1) / cpu_ms / 1e3, "bit_exact_vs_cpu": bool(ok)})
-    for t in tables:
-        t.release()
+        res.update({"cpu_ms": cpu_ms, "cpu_k": kc, "cpu_cores": 1, "cpu_mpairs_per_s": ((1 << kc) - 1) / cpu_ms / 1e3})
+    for t_ in tables:
+        t_.release()
     return res
 
 
-def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool):
+def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     """The GPU-side compute of a HyperPlonk proof for vanilla_plonk end to end, driven by the reference's Keccak256
     transcript (util/transcript.rs:100-235): commit the three witness polynomials (backend/hyperplonk.rs:201, kept
     resident), zero check of the gate over eq(x, y) and five resident selectors (hyperplonk.rs:262-277 through
     piop/sum_check/classic.rs:208-240), g_prime merge of the witness polynomials (pcs/multilinear.rs:203-213) and its
     KZG opening at the sum-check point (kzg.rs:276-302).  The permutation / lookup arguments and witness generation are
-    not part of it.  With cpu=True the same proof is rebuilt through the oracle: the bytes must be identical."""
+    not part of it.  Parity: the same proof is rebuilt through the oracle — commitments through the SRS trapdoor
+    (cpu=False) or through the CPU port's MSMs (cpu=True, also timed) — and the proof BYTES must be identical."""
+    from oracle import pyoracle as po
     from plonkish_b200 import kzg, sumcheck
-    from plonkish_b200.transcript import FR_MODULUS, Keccak256Transcript
+    from plonkish_b200.sumcheck import interpolate_at
+    from plonkish_b200.transcript import Keccak256Transcript
 
     n = 1 << k
-    pp = kzg.setup(g1_generator(np), pk.random_scalars(k, seed=501))
-    witness = []
-    for j in range(3):
-        t = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-        h = t.numpy().view(np.uint64)
-        h[:] = pk.random_scalars(n, seed=510 + j)
-        witness.append(h)
-    selectors = [pk.ResidentScalars(pk.random_scalars(n, seed=520 + j)) for j in range(5)]  # q_l, q_r, q_m, q_o, q_c: preprocessed
+    ss = pk.random_scalars(k, seed=501)
+    pp = kzg.setup(g1_generator(np), ss)
+    witness = [pk.random_scalars(n, seed=510 + j) for j in range(3)]   # pageable host memory, like the witness polys
+    sel_h = [pk.random_scalars(n, seed=520 + j) for j in range(5)]     # q_l, q_r, q_m, q_o, q_c: preprocessed
+    selectors = [pk.ResidentScalars(s_) for s_ in sel_h]
     one = sumcheck._to_mont(1)
     # tables: 0 eq, 1..5 selectors, 6..8 witness
     terms = [(one, [1, 6]), (one, [2, 7]), (one, [3, 6, 7]), (one, [4, 8]), (one, [5])]
@@ -362,78 +429,136 @@ def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool):
             r.release()
         return t.into_proof()
 
-    run()
-    t0 = time.perf_counter()
-    proof = run()
-    gpu_ms = (time.perf_counter() - t0) * 1e3
+    proof, tm = timed_reps(run, reps)
     res = {"what": "commit 3 witness polynomials -> zero check (9 tables, degree 4) -> g_prime merge -> KZG open, Keccak256 transcript on the host, "
-                   "all polynomial data resident in HBM after one upload; permutation / lookup arguments and witness generation not included",
-           "k": k, "gpu_ms": gpu_ms, "proof_bytes": len(proof)}
+                   "all polynomial data resident in HBM after one upload from pageable memory; permutation / lookup arguments and witness generation not included",
+           "k": k, "gpu_ms": tm["ms_min"], "gpu_ms_median": tm["ms_median"], "gpu_ms_all": tm["ms_all"], "reps": reps, "proof_bytes": len(proof)}
+    # ---- the same proof through the oracle
+    cores = po.host_threads()
+    td = Trapdoor(po, np, ss)
+    eqs_h = [e.to_host() for e in pp.eqs] if cpu else None
+    commit = (lambda f, i: po.variable_base_msm(f, eqs_h[i], cores)) if cpu else (lambda f, i: td.commit(f))
+    t0 = time.perf_counter()
+    t = Keccak256Transcript()
+    t.write_commitments([commit(w, k) for w in witness])
+    y = t.squeeze_challenges(k)
+    cur = [po.kzg_eq_scalars(np.stack([sumcheck._to_mont(v) for v in y]))[k]] + sel_h + [np.array(w) for w in witness]
+    claim, challenges = 0, []
+    for _ in range(k):
+        thr = cores if (not cpu and len(cur[0]) >= 1 << 14) else 1
+        tail = [sumcheck._to_int(r) for r in po.sumcheck_round(cur, terms, 0, num_threads=thr)]
+        msg = [(claim - tail[0]) % FR_MODULUS] + tail
+        t.write_field_elements(msg)
+        ch = t.squeeze_challenge()
+        challenges.append(ch)
+        claim = interpolate_at(msg, ch)
+        cur = [po.fix_var(p, sumcheck._to_mont(ch), thr) for p in cur]
+    t.write_field_elements([sumcheck._to_int(p[0]) for p in cur[6:]])
+    coeffs = t.squeeze_challenges(3)
+    g_prime_h = po.fr_linear_combination(witness, np.stack([sumcheck._to_mont(c) for c in coeffs]))
+    qs, _ = po.quotients(g_prime_h, np.stack([sumcheck._to_mont(c) for c in challenges]))
+    t.write_commitments([commit(q, i) for i, q in enumerate(qs)])
+    same = bool(t.into_proof() == proof)
     if cpu:
-        from oracle import pyoracle as po
-        from plonkish_b200.sumcheck import interpolate_at
-
-        cores = po.host_threads()
-        eqs_h = [e.to_host() for e in pp.eqs]
-        sel_h = [s_.to_host() for s_ in selectors]
-        t0 = time.perf_counter()
-        t = Keccak256Transcript()
-        t.write_commitments([po.variable_base_msm(w, eqs_h[k], cores) for w in witness])
-        y = t.squeeze_challenges(k)
-        cur = [po.kzg_eq_scalars(np.stack([sumcheck._to_mont(v) for v in y]))[k]] + sel_h + [np.array(w) for w in witness]
-        claim, challenges = 0, []
-        for _ in range(k):
-            tail = [sumcheck._to_int(r) for r in po.sumcheck_round(cur, terms, 0)]
-            msg = [(claim - tail[0]) % FR_MODULUS] + tail
-            t.write_field_elements(msg)
-            ch = t.squeeze_challenge()
-            challenges.append(ch)
-            claim = interpolate_at(msg, ch)
-            cur = [po.fix_var(p, sumcheck._to_mont(ch)) for p in cur]
-        t.write_field_elements([sumcheck._to_int(p[0]) for p in cur[6:]])
-        coeffs = t.squeeze_challenges(3)
-        g_prime_h = po.fr_linear_combination(witness, np.stack([sumcheck._to_mont(c) for c in coeffs]))
-        qs, _ = po.quotients(g_prime_h, np.stack([sumcheck._to_mont(c) for c in challenges]))
-        t.write_commitments([po.variable_base_msm(q, eqs_h[i], cores) for i, q in enumerate(qs)])
-        res.update({"cpu_ms": (time.perf_counter() - t0) * 1e3, "cpu_cores": cores, "proof_bytes_identical_to_cpu": bool(t.into_proof() == proof)})
+        res.update({"cpu_ms": (time.perf_counter() - t0) * 1e3, "cpu_cores": cores, "proof_bytes_identical_to_cpu": same})
+    res["parity_checked"] = same
+    res["parity_how"] = ("proof bytes identical to the oracle's proof (CPU port MSMs, single-threaded sum check)" if cpu else
+                         "proof bytes identical to the oracle's proof (commitments through the SRS trapdoor f(ss) * G, sum check on all host cores)")
+    assert same, f"prove pipeline k={k}: proof bytes differ from the oracle's"
     for s_ in selectors:
         s_.release()
     pp.release()
     return res
 
 
-def univariate_sequence(pk, torch, np, k: int, dev):
+def univariate_sequence(pk, torch, np, k: int, dev, reps: int):
     """BASELINE.json config 4 restated synthetically: UnivariateKzg commit = one MSM over
-    the SRS prefix (pcs/univariate/kzg.rs:24-30, witness-like 68-bit limb values with zero padding) and
-    batch_open = two MSMs of ~2^k uniform coefficients (univariate/kzg.rs:330,353), host scalars,
-    resident powers_of_s_g1."""
+    the SRS prefix (pcs/univariate/kzg.rs:24-30, witness-like canonical 68-bit values with zero padding) and
+    batch_open = two MSMs of ~2^k uniform coefficients (univariate/kzg.rs:330,353), pageable host scalars,
+    resident powers_of_s_g1.  Parity: known discrete log of the synthetic SRS."""
+    from oracle import pyoracle as po
+
     n = 1 << k
     d_bases = pk.synth_bases_device(n, 11, 13, device=dev)
     torch.cuda.synchronize()
     reg = pk.G1Bases(d_bases)
     rng = np.random.default_rng(22)
-    limbs = np.zeros((n, 4), dtype=np.uint64)
+    canon = np.zeros((n, 4), dtype=np.uint64)
     live = n - n // 8                       # last eighth zero padding
-    limbs[:live, 0] = rng.integers(0, 1 << 63, size=live, dtype=np.uint64)
-    limbs[:live, 1] = rng.integers(0, 1 << 4, size=live, dtype=np.uint64)   # 68-bit canonical values ...
-    # ... as Montgomery representations they are full-width; the MSM sees uniform digits, so the 68-bit
-    # shape is emulated directly in Montgomery form: values whose Montgomery limbs are small.
+    canon[:live, 0] = rng.integers(0, 1 << 63, size=live, dtype=np.uint64)
+    canon[:live, 1] = rng.integers(0, 1 << 4, size=live, dtype=np.uint64)   # canonical 68-bit limb values (aggregation circuit limbs)
+    limbs = po.from_canonical(1, canon)     # their Montgomery representations are full width: that is what the MSM is handed
     uniform = pk.random_scalars(n, seed=2222)
-    host = [torch.from_numpy(a.view(np.int64)).pin_memory().numpy().view(np.uint64) for a in (limbs, uniform, uniform)]
+    host = [limbs, uniform, uniform]
 
-    def run():
-        return [pk.variable_base_msm(h, reg) for h in host]
-
-    run()
-    t0 = time.perf_counter()
-    run()
-    ms = (time.perf_counter() - t0) * 1e3
+    outs, t = timed_reps(lambda: [pk.variable_base_msm(h, reg) for h in host], reps)
+    ok = all((o == po.known_dlog_answer(11, 13, h)).all() for o, h in zip(outs, host))
     reg.release()
-    return {"k": k, "msm_calls": 3, "points": 3 * n, "gpu_ms": ms,
-            "what": "commit (small-limb scalars, 1/8 zero padding) + batch_open (2 uniform MSMs) of 2^k points each, host scalars"}
+    assert ok, "univariate sequence: a commitment differs from the known-dlog answer"
+    return {"k": k, "msm_calls": 3, "points": 3 * n, "gpu_ms": t["ms_min"], "gpu_ms_median": t["ms_median"], "reps": reps, "parity_checked": bool(ok),
+            "parity_how": "known discrete log of the synthetic SRS",
+            "what": "commit (68-bit canonical values in Montgomery form, 1/8 zero padding) + batch_open (2 uniform MSMs) of 2^k points each, pageable host scalars"}
+
+
+# ----------------------------------------------------------------------------- skew set
+def skew_scalars(pk, po, np, kind: str, n: int, rng):
+    def mont_const(v):
+        return np.frombuffer((v % FR_MODULUS * (1 << 256) % FR_MODULUS).to_bytes(32, "little"), dtype=np.uint64)
+
+    out = np.zeros((n, 4), dtype=np.uint64)
+    if kind == "selector":      # 0 / 1 / -1 with half zeros (backend/hyperplonk/util.rs:133-152)
+        pick = rng.integers(0, 4, n)
+        out[pick == 2] = mont_const(1)
+        out[pick == 3] = mont_const(FR_MODULUS - 1)
+    elif kind == "small-ints":  # permutation polynomials: values < 3 * 2^k (backend/hyperplonk/preprocessor.rs:184-190)
+        canon = np.zeros((n, 4), dtype=np.uint64)
+        canon[:, 0] = rng.integers(0, 3 * n, n, dtype=np.uint64)
+        out = po.from_canonical(1, canon)
+    elif kind == "all-ones":
+        out[:] = mont_const(1)
+    elif kind == "same-wide":
+        out[:] = mont_const(0x2AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA)
+    return out
+
+
+def skew_bench(pk, torch, np, d_uniform, reg, uniform_ms: float, n: int, dev):
+    """SURVEY.md §8(d) skew set on the timed configuration (table layout, device-resident scalars): preprocess-shaped
+    scalars.  Each leg is checked against the known-dlog answer; `vs_uniform` = ms / the uniform step."""
+    from oracle import pyoracle as po
+
+    rng = np.random.default_rng(1)
+    res = {"uniform_ms": uniform_ms}
+    for kind in ("selector", "small-ints", "all-ones", "same-wide"):
+        sc = skew_scalars(pk, po, np, kind, n, rng)
+        d_sc = torch.from_numpy(sc.view(np.int64)).to(dev)
+        got = pk.variable_base_msm_device(d_sc, reg).cpu().numpy().view(np.uint64)
+        ok = bool((got == po.known_dlog_answer(3, 5, sc)).all())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(3):
+            e0.record()
+            pk.variable_base_msm_device(d_sc, reg)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res[kind] = {"ms": min(ts), "ms_median": statistics.median(ts), "vs_uniform": min(ts) / uniform_ms, "parity_checked": ok}
+        assert ok, f"skew leg {kind}: result differs from the known-dlog answer"
+        del d_sc
+    res["slowest_vs_uniform"] = max(v["vs_uniform"] for v in res.values() if isinstance(v, dict))
+    return res
 
 
 # ------------------------------------------------------------------------- our arm
+def sum_points(points_u64):
+    """Affine sum of [k, 8] Montgomery points with the big-integer reference (independent of the C oracle and the GPU)."""
+    from oracle import bigint_ref as br
+
+    acc = None
+    for p in points_u64:
+        acc = br.add(acc, br.point_from_bytes(p.tobytes()))
+    return br.point_to_bytes(acc)
+
+
 def run_ours(args) -> None:
     import numpy as np
     import torch
@@ -441,6 +566,7 @@ def run_ours(args) -> None:
 
     import plonkish_b200 as pk
     from plonkish_b200 import _lib
+    from oracle import pyoracle as po  # the checker: every timed result is compared with an independent answer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -448,19 +574,22 @@ def run_ours(args) -> None:
     distributed = world > 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # host-side barrier while rank 0 drives all GPUs by itself
     _lib.lib()
+    po.build()
 
     n = 1 << args.log_n
     total_n = n * world
     a, d = 3, 5
     first = rank * n
-    # synthetic inputs (seeded): this rank's slice of the (world * n)-point MSM
-    scalars_host_t = torch.empty((n, 4), dtype=torch.int64).pin_memory()
-    scalars_np = scalars_host_t.numpy().view(np.uint64)
-    scalars_np[:] = pk.random_scalars(n, seed=1000 + rank)
-    d_scalars = scalars_host_t.to(dev)
+    # synthetic inputs (seeded): this rank's slice of the (world * n)-point MSM.  The host copy is plain numpy
+    # memory — pageable, like the Vec<Fr> behind poly.evals() — plus a pinned copy for the pinned-source number.
+    scalars_np = pk.random_scalars(n, seed=1000 + rank)
+    scalars_pin, _keep_pin = pinned_copy(torch, np, scalars_np)
+    d_scalars = torch.from_numpy(scalars_np.view(np.int64)).to(dev)
     d_bases = pk.synth_bases_device(n, a, d, device=dev, first=first)
     torch.cuda.synchronize()
     # The bases are the static SRS of a ProverParam: made resident once, outside the timed
@@ -472,10 +601,18 @@ def run_ours(args) -> None:
     register_s = time.perf_counter() - t_reg
     step_bases = d_bases if (args.plain_bases and args.window_bits) else reg
 
-    def step_device():
-        if distributed:
-            return pk.variable_base_msm_sharded(d_scalars, step_bases, window_bits=args.window_bits)
-        return pk.variable_base_msm_device(d_scalars, step_bases, window_bits=args.window_bits)
+    def expected_total(local_scalars, local_first):
+        """The known-dlog answer of the whole (all ranks) MSM: every rank evaluates its slice's answer with the oracle
+        (two field sums + one scalar multiplication), rank 0 adds the points with the big-integer reference."""
+        mine = po.known_dlog_answer(a + local_first * d, d, local_scalars)
+        if not distributed:
+            return mine.tobytes()
+        t = torch.from_numpy(mine.view(np.int64)).to(dev)
+        allp = torch.empty(world * 8, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allp, t)
+        return sum_points(allp.cpu().numpy().view(np.uint64).reshape(world, 8))
+
+    want = expected_total(scalars_np, first)
 
     def barrier():
         torch.cuda.synchronize()
@@ -483,59 +620,104 @@ def run_ours(args) -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        out = step_device()
-    barrier()
+    def timed_device(step, steps, warmup):
+        for _ in range(warmup):
+            out = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]  # per-step boundaries for min / median
+        barrier()
+        e0.record()
+        for i in range(steps):
+            out = step()
+            marks[i].record()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(steps)]
+        if distributed:
+            t = torch.tensor([ms_total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        return out, ms_total / steps, step_ms
+
+    def timed_host(step, steps, warmup=2):
+        for _ in range(warmup):
+            out = step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step()
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        if distributed:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return out, ms
+
+    def step_device():
+        if distributed:
+            return pk.variable_base_msm_sharded(d_scalars, step_bases, window_bits=args.window_bits)
+        return pk.variable_base_msm_device(d_scalars, step_bases, window_bits=args.window_bits)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_device()
+    barrier()
     launches0 = pk.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     t_wall0 = time.time()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]  # per-step boundaries for min / median
-    e0.record()
-    for i in range(args.steps):
-        out = step_device()
-        marks[i].record()
-    e1.record()
-    barrier()
+    out, ms_per_step, step_ms = timed_device(step_device, args.steps, 0)
     t_wall1 = time.time()
     launches = pk.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
-    step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(args.steps)]
-    if distributed:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     clocks = sampler.stop(t_wall0, t_wall1)
-    ms_per_step = ms_total / args.steps
     value = total_n / (ms_per_step * 1e-3) / 1e6
     result_dev = out.cpu().numpy().view(np.uint64)
+    assert result_dev.tobytes() == want, "the timed device-resident result differs from the known-dlog answer"
 
     # ---- e2e: host buffers through the public API, copies inside the timed region
-    if not distributed:
-        def step_e2e():
-            return pk.variable_base_msm(scalars_np, reg)
-    else:
-        def step_e2e():
-            return pk.variable_base_msm_sharded_host(scalars_np, reg).cpu().numpy().view(np.uint64)
+    def make_e2e(src):
+        if not distributed:
+            return lambda: pk.variable_base_msm(src, reg)
+        return lambda: pk.variable_base_msm_sharded_host(src, reg).cpu().numpy().view(np.uint64)
 
-    for _ in range(2):
-        e2e_out = step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_out = step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    if distributed:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    staged0 = pk.staged_bytes()
+    e2e_out, e2e_ms = timed_host(make_e2e(scalars_np), args.steps)
+    staged_per_step = (pk.staged_bytes() - staged0) // (args.steps + 2)
+    assert np.asarray(e2e_out).view(np.uint64).tobytes() == want, "the e2e (pageable) result differs from the known-dlog answer"
+    e2e_pin_out, e2e_pin_ms = timed_host(make_e2e(scalars_pin), args.steps)
+    assert np.asarray(e2e_pin_out).view(np.uint64).tobytes() == want, "the e2e (pinned) result differs from the known-dlog answer"
     e2e_value = total_n / (e2e_ms * 1e-3) / 1e6
-    assert (np.asarray(e2e_out).view(np.uint64) == result_dev).all(), "e2e and device-resident results differ"
+
+    # ---- strong scaling: ONE MSM of 2^log_n points in total, point-sharded over the ranks (BASELINE: "at 2^24 on 1/2/4/8")
+    strong = None
+    if distributed and not args.plain_bases:
+        n_s = n // world
+        d_bases_s = pk.synth_bases_device(n_s, a, d, device=dev, first=rank * n_s)
+        torch.cuda.synchronize()
+        reg_s = pk.G1Bases(d_bases_s)
+        d_scalars_s = d_scalars[:n_s].contiguous()
+        want_s = expected_total(scalars_np[:n_s], rank * n_s)
+        out_s, ms_s, step_ms_s = timed_device(lambda: pk.variable_base_msm_sharded(d_scalars_s, reg_s), args.steps, 3)
+        assert out_s.cpu().numpy().view(np.uint64).tobytes() == want_s, "strong-scaling result differs from the known-dlog answer"
+        src_s = scalars_np[:n_s]
+        e2e_s_out, e2e_s_ms = timed_host(lambda: pk.variable_base_msm_sharded_host(src_s, reg_s).cpu().numpy().view(np.uint64), args.steps)
+        assert np.asarray(e2e_s_out).view(np.uint64).tobytes() == want_s
+        plan_s = pk.msm_plan(n_s, 0, local_rank, bases=reg_s)
+        strong = {
+            "what": f"one MSM of 2^{args.log_n} points in total, {n_s} per GPU, device-resident slices, NCCL all_gather of the partials; max over ranks",
+            "total_points": n, "points_per_gpu": n_s, "ms_per_step": ms_s, "ms_step_min": min(step_ms_s), "value": n / (ms_s * 1e-3) / 1e6, "unit": UNIT,
+            "e2e_ms_per_step": e2e_s_ms, "e2e_value": n / (e2e_s_ms * 1e-3) / 1e6, "e2e_source": "pageable host scalars",
+            "window_bits": plan_s["window_bits"], "windows": plan_s["windows"],
+            # the weak step of this same run is one GPU doing 2^log_n points: the 1-GPU time of the strong-scaling problem
+            "one_gpu_ms_same_run": ms_per_step, "efficiency_vs_one_gpu_same_run": ms_per_step / (world * ms_s),
+            "parity_checked": True,
+        }
+        reg_s.release()
+        del d_bases_s, d_scalars_s
 
     # ---- roofline of the dominant kernel (K3 accumulate), timed live with CUDA events
     plan = pk.msm_plan(n, args.window_bits, local_rank, bases=None if step_bases is d_bases else reg)
@@ -543,6 +725,7 @@ def run_ours(args) -> None:
     stages = {k: statistics.mean(r[k] for r in stage_runs) for k in stage_runs[0]}
     pipe = pk.bench_integer_pipe(local_rank)
     madd_streams = pk.bench_madd(local_rank)
+    fp64 = pk.bench_fp64_pipe(local_rank)
     # the algorithmic figure is fixed at 16 windows x 10 modmul x 136 IMAD
     # = 21 760 IMAD per point, independent of the window width the plan actually uses.
     imad_per_launch = float(n) * 16 * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL
@@ -561,9 +744,12 @@ def run_ours(args) -> None:
     entries = float(n) * plan["windows"]
     if plan["idx_bits"]:  # plain bases: u16 digit in, u32 entry out; then u32 in, u32 out
         sort_bytes = entries * (2 + 4) + entries * (4 + 4)
+        decompose_bytes = float(n) * 32 + entries * 2
     else:                 # table layout: staged two-level partition
         sort_bytes = entries * (4 + 6) + entries * (2 + 6 + 4)  # level 1: digit in, value + key out; level 2: key (hist), key + value in, entry out
+        decompose_bytes = float(n) * 32 + entries * 4
     sort_ms = stages["bin_scatter"] + stages["bin_sort"]
+    traffic = load_ncu_traffic()
     roofline = {
         "kernel": "k_accumulate (XYZZ mixed additions, 254-bit Montgomery, IMAD.WIDE carry chains)",
         "bound": "imad", "achieved": achieved, "peak": peak, "unit": "TIMAD/s (32x32->64 multiply-adds)",
@@ -582,87 +768,172 @@ def run_ours(args) -> None:
         # the fraction of THAT ceiling the kernel runs at, in executed products
         "madd_stream_ceiling_products_per_s": madd_streams["madd_1acc_128regs"],
         "frac_of_madd_stream": (float(n) * plan["windows"] * MODMUL_PER_MIXED_ADD / (stages["accumulate"] * 1e-3)) / madd_streams["madd_1acc_128regs"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one 2^24-point launch in the committed ncu --set full capture
-        # (profiles/r01_final_kernels_ncu_raw.csv: 27.25 GB + 0.39 GB at 12 windows), scaled to this launch's entry count
-        "traffic": 27.64e9 * (float(n) * plan["windows"]) / (16777216.0 * 12),
-        "traffic_source": "ncu capture under profiles/ (not measured in this run); algorithmic gather = entries x 68 B",
-        "algorithmic_bytes": float(n) * plan["windows"] * 68,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture, scaled to this launch's entry count
+        "traffic": (traffic["k_accumulate"]["bytes"] * entries / traffic["k_accumulate"]["entries"]) if traffic and "k_accumulate" in traffic else None,
+        "traffic_source": traffic.get("source") if traffic else "no ncu capture found under profiles/",
+        "algorithmic_bytes": entries * 68,
     }
     roofline_sort = {
-        "kernel": "the two sort levels (k_scatter_staged_b, k_bucket_hist_b, k_bucket_scatter_staged_b; plain bases: k_scatter_bins, k_sort_bins)", "bound": "hbm", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9,
+        "kernel": "decompose + the two sort levels (table layout: k_decompose_b, k_scatter_staged_b, k_bucket_hist_b, k_bucket_scatter_staged_b; plain bases: k_decompose, k_scatter_bins, k_sort_bins)",
+        "bound": "hbm", "achieved": (sort_bytes + decompose_bytes) / ((sort_ms + stages["decompose"]) * 1e-3) / 1e9,
         "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
-        "frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": sort_ms,
-        # table layout, 2^24, c = 22: k_scatter_staged_b 0.81 + 1.16 GB, k_bucket_hist_b 0.41 GB, k_bucket_scatter_staged_b 1.36 + 0.90 GB (same capture)
-        "traffic": (5.51e9 * entries / (16777216.0 * 13)) if not plan["idx_bits"] else None,
-        "algorithmic_bytes": sort_bytes,
+        "frac": (sort_bytes + decompose_bytes) / ((sort_ms + stages["decompose"]) * 1e-3) / 1e9 / hbm_peak, "kernel_ms": sort_ms + stages["decompose"],
+        "sort_only": {"achieved": sort_bytes / (sort_ms * 1e-3) / 1e9, "frac": sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": sort_ms},
+        "traffic": (traffic["sort"]["bytes"] * entries / traffic["sort"]["entries"]) if traffic and "sort" in traffic and not plan["idx_bits"] else None,
+        "algorithmic_bytes": sort_bytes + decompose_bytes,
     }
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "ms_step_min": min(step_ms), "ms_step_median": statistics.median(step_ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic",
+        "parity_checked": True,
+        "parity_how": "timed device-resident result, e2e (pageable) and e2e (pinned) results == the known-discrete-log answer of the synthetic bases "
+                      "(oracle: two field sums + one scalar multiplication per rank, points added with the big-integer reference)",
         "config": {
             "workload": f"one BN254 G1 variable_base_msm of {world} x 2^{args.log_n} points (2^{args.log_n} per GPU), "
                         "uniform random Fr scalars, known-dlog bases (a+i*d)G, bases resident",
             "points_per_gpu": n, "window_bits": plan["window_bits"], "windows": plan["windows"],
             "bases": "plain affine array (one bucket set per window)" if step_bases is d_bases or args.plain_bases else
-                     f"resident table of window multiples, {plan['windows']} x 64 B per point, built once in {register_s:.2f} s (untimed)",
+                     f"resident table of window multiples, {plan['windows']} x 64 B per point ({plan['windows'] * 64 * n / 1e9:.1f} GB), built once in {register_s:.2f} s (untimed)",
             "parallelism": f"point-sharded x{world}" + (", NCCL all_gather of 128-byte partials" if distributed else ""),
             "l2": "inputs (scalars 32 B + bases 64 B per point) exceed the 126 MB L2 at this size; no explicit flush",
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 64 * world,
-                "path": "plonkish_cuda_msm_bn254_g1 (C ABI, pinned host scalars, registered bases)" if not distributed
-                        else "per rank: plonkish_cuda_msm_bn254_g1_host_partial (C ABI, pinned host scalars, registered bases) -> NCCL all_gather of partials -> fold -> host"},
+                "host_memory": "pageable (plain numpy, like a Rust Vec<Fr>): staged through the library's pinned ring",
+                "staged_bytes_per_step": int(staged_per_step),
+                "path": "plonkish_cuda_msm_bn254_g1 (C ABI, pageable host scalars, registered bases)" if not distributed
+                        else "per rank: plonkish_cuda_msm_bn254_g1_host_partial (C ABI, pageable host scalars, registered bases) -> NCCL all_gather of partials -> fold -> host"},
+        "e2e_pinned": {"value": total_n / (e2e_pin_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_pin_ms, "host_memory": "pinned (cudaHostAlloc)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_sort": roofline_sort,
         "stages_ms": stages,
         "integer_pipe": pipe,
+        "fp64_pipe": fp64,
         "madd_streams": madd_streams,
     }
+    if strong:
+        line["strong_2p%d" % args.log_n] = strong
 
     if rank == 0 and not args.no_cpu_baseline and not distributed:
-        from oracle import pyoracle as po
-
-        po.build()
         cores = po.host_threads()
         log_c = min(args.log_n, args.cpu_log_n)
         m = 1 << log_c
-        sc = scalars_np[:m].copy()
+        sc = scalars_np[:m]
         bs = d_bases[:m].cpu().numpy().view(np.uint64)
         t0 = time.perf_counter()
-        want = po.variable_base_msm(sc, bs, cores)
+        want_cpu = po.variable_base_msm(sc, bs, cores)
         sec = time.perf_counter() - t0
-        got = pk.variable_base_msm(sc, bs)
-        assert (got == want).all(), "GPU result differs from the CPU oracle on the cpu_baseline sample"
+        got = result_dev if m == n else pk.variable_base_msm(sc, reg)
+        assert (got == want_cpu).all(), "GPU result differs from the CPU oracle on the cpu_baseline sample"
         line["cpu_baseline"] = {
             "value": m / sec / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first 2^{log_c} points of the step's inputs, one pass, C port of msm.rs:84-181 with {cores} pthreads; "
-                      "GPU result on the same sample checked bit-exact",
+            "sample": f"{'all' if m == n else 'first'} 2^{log_c} points of the step's inputs, one pass, C port of msm.rs:84-181 with {cores} pthreads; "
+                      "the GPU's timed result on the same points checked bit-exact against it",
+            "seconds": sec,
         }
-    if rank == 0 and not distributed and args.prove_k:
+    if rank == 0 and not distributed and not args.no_skew and step_bases is reg:
+        line["skew"] = skew_bench(pk, torch, np, d_scalars, reg, ms_per_step, n, dev)
+    if not distributed and args.prove_k:
         del d_scalars, d_bases
         reg.release()
         torch.cuda.empty_cache()
+        cpu = not args.no_cpu_baseline
         seq = {"what": "MSM calls of HyperPlonk::prove for vanilla_plonk (4 x 2^k + 2^(k-1) + ... + 1 points) against an SRS built on the device; "
-                       "gpu_ms: host scalars per call; gpu_resident_ms: polynomials kept in HBM, g_prime merge and quotients on the GPU; "
-                       "sum-check and the other field-only prover work stay in the Rust caller and are not included"}
-        seq["k%d" % args.prove_k] = prove_msm_sequence(pk, torch, np, args.prove_k, dev, cpu=False)
-        if not args.no_cpu_baseline:
-            seq["k20"] = prove_msm_sequence(pk, torch, np, min(20, args.prove_k), dev, cpu=True)
+                       "gpu_ms: pageable host scalars per call; gpu_resident_ms: polynomials kept in HBM, g_prime merge and quotients on the GPU; "
+                       "sum-check and the other field-only prover work stay in the Rust caller and are not included; min of `reps` runs"}
+        seq["k%d" % args.prove_k] = prove_msm_sequence(pk, torch, np, args.prove_k, dev, cpu=False, reps=args.reps)
+        if cpu:
+            seq["k20"] = prove_msm_sequence(pk, torch, np, min(20, args.prove_k), dev, cpu=True, reps=args.reps)
         line["hyperplonk_prove_msm"] = seq
-        line["univariate_kzg_k22"] = univariate_sequence(pk, torch, np, 22, dev)
-        line["srs_fixed_base_msm"] = srs_setup_bench(pk, torch, np, args.prove_k, cpu=not args.no_cpu_baseline)
-        line["sum_check_zero_check"] = sum_check_bench(pk, torch, np, args.prove_k, cpu=not args.no_cpu_baseline)
-        pipe = {"k%d" % args.prove_k: prove_pipeline_bench(pk, torch, np, args.prove_k, cpu=False)}
-        if not args.no_cpu_baseline:
-            pipe["k18"] = prove_pipeline_bench(pk, torch, np, min(18, args.prove_k), cpu=True)
-        line["hyperplonk_prove_pipeline"] = pipe
+        line["univariate_kzg_k22"] = univariate_sequence(pk, torch, np, min(22, args.prove_k), dev, args.reps)
+        line["srs_fixed_base_msm"] = srs_setup_bench(pk, torch, np, args.prove_k, cpu=cpu, reps=args.reps)
+        line["sum_check_zero_check"] = sum_check_bench(pk, torch, np, args.prove_k, cpu=cpu, reps=args.reps)
+        pipe_leg = {"k%d" % args.prove_k: prove_pipeline_bench(pk, torch, np, args.prove_k, cpu=False, reps=args.reps)}
+        if cpu:
+            pipe_leg["k18"] = prove_pipeline_bench(pk, torch, np, min(18, args.prove_k), cpu=True, reps=args.reps)
+        line["hyperplonk_prove_pipeline"] = pipe_leg
+    if distributed and not args.no_single_process and not args.plain_bases:
+        # rank 0 alone drives all `world` GPUs through the C ABI's multi-GPU entry (one process, NCCL gather inside the
+        # library); the other ranks free their memory and wait on a host-side (gloo) barrier so their GPUs stay idle
+        if rank != 0:
+            del d_scalars, d_bases
+            reg.release()
+            torch.cuda.empty_cache()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                line["single_process"] = single_process_leg(pk, torch, np, args, world, a, d, want, ms_per_step, e2e_ms, e2e_pin_ms)
+            except Exception as e:  # noqa: BLE001 - keep the primary numbers if this leg cannot run
+                line["single_process"] = {"error": f"{type(e).__name__}: {e}"}
+        dist.barrier(group=host_group)
     if rank == 0:
         emit(line)
     if distributed:
         dist.destroy_process_group()
+
+
+def single_process_leg(pk, torch, np, args, world: int, a: int, d: int, want: bytes, weak_ms: float, e2e_ms: float, e2e_pin_ms: float):
+    """plonkish_cuda_msm_bn254_g1_multi over all GPUs from ONE process: the same world x 2^log_n-point MSM the ranks just
+    did together (same seeds, so the same expected point), host scalars in, affine point out."""
+    n = 1 << args.log_n
+    total = n * world
+    host = np.empty((total, 4), dtype=np.uint64)          # pageable
+    for r in range(world):
+        host[r * n:(r + 1) * n] = pk.random_scalars(n, seed=1000 + r)
+    shards = [pk.synth_bases_device(n, a, d, device=torch.device("cuda", g), first=g * n) for g in range(world)]
+    for g in range(world):
+        torch.cuda.synchronize(g)
+    t0 = time.perf_counter()
+    reg = pk.ShardedG1Bases.from_device(shards, total)
+    register_s = time.perf_counter() - t0
+    del shards
+
+    def timed(src, steps):
+        for _ in range(2):
+            out = pk.variable_base_msm(src, reg)
+        ts = []
+        for _ in range(steps):
+            t = time.perf_counter()
+            out = pk.variable_base_msm(src, reg)
+            ts.append((time.perf_counter() - t) * 1e3)
+        return out, ts
+
+    out, ts = timed(host, args.steps)
+    assert out.tobytes() == want, "single-process multi-GPU result differs from the known-dlog answer"
+    res = {"what": f"one process, {world} GPUs, plonkish_cuda_msm_bn254_g1_multi: one host thread per device, chunk-pipelined uploads, ncclAllGather of the partials",
+           "points": total, "e2e_pageable_ms": statistics.mean(ts), "e2e_pageable_ms_min": min(ts), "e2e_pageable_value": total / (statistics.mean(ts) * 1e-3) / 1e6,
+           "torchrun_e2e_pageable_ms": e2e_ms, "torchrun_e2e_pinned_ms": e2e_pin_ms, "torchrun_device_ms": weak_ms,
+           "register_s": register_s, "parity_checked": True}
+    try:
+        pin, keep = pinned_copy(torch, np, host)
+        out, ts = timed(pin, args.steps)
+        assert out.tobytes() == want
+        res.update({"e2e_pinned_ms": statistics.mean(ts), "e2e_pinned_ms_min": min(ts), "e2e_pinned_value": total / (statistics.mean(ts) * 1e-3) / 1e6,
+                    "vs_torchrun_pinned": statistics.mean(ts) / e2e_pin_ms})
+        del pin, keep
+    except RuntimeError as e:  # pinning world x 512 MB may be refused
+        res["e2e_pinned_error"] = str(e)
+    reg.release()
+    return res
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest committed `ncu --set full` summary
+    (profiles/*_traffic.json, written by tools/ncu_summary.py from the raw CSV page)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        data = json.load(open(files[-1]))
+        data["source"] = "profiles/" + os.path.basename(files[-1]) + " (ncu --set full capture of this round, not measured in this run)"
+        return data
+    except Exception:  # noqa: BLE001
+        return None
 
 
 _REAL_STDOUT = None

@@ -61,10 +61,31 @@ const char *plonkish_cuda_last_error(void);
  * Uploads n affine bases to `device` and returns a handle.  The reference re-reads
  * its SRS from host memory on every call (ProverParam.eqs, pcs/multilinear/kzg.rs:55-77;
  * powers_of_s_g1, pcs/univariate/kzg.rs:24-30); the SRS is static per ProverParam, so
- * the shim registers each slice once, keyed by (pointer, length), and passes the
- * handle afterwards.  A later MSM may use any prefix n' <= n of a registered slice. */
+ * a ProverParam wrapper registers each slice once and passes the handle afterwards.  A later
+ * MSM may use any prefix n' <= n of a registered slice (a prefix shorter than 1/16 of the
+ * slice runs on the plain bases, row 0 of the table).  Handles are reference counted:
+ * release while another thread's call still uses the slice frees the memory when that call
+ * is done. */
 int plonkish_cuda_bases_register(int device, const void *bases_affine64, size_t n, uint64_t *handle);
 int plonkish_cuda_bases_release(uint64_t handle);
+
+/* Borrowed slices.  Inside variable_base_msm (msm.rs:84-87) the shim only sees `&[G1Affine]`: it
+ * cannot tell a ProverParam's static SRS slice from a temporary whose address the allocator will
+ * reuse (ipa.rs g_lo/g_hi, hyrax.rs rows, a second setup in one process).  bases_cached looks the
+ * address up in a cache inside the library and trusts a hit only if the content fingerprint taken
+ * at registration (first 8 points, the last one, 24 pseudo-random positions; for a prefix also the
+ * prefix's last point against the device copy) matches what is at that address now; otherwise the
+ * stale entry is released and the slice registered afresh.  A longer slice at a cached address
+ * replaces the entry; a shorter one uses its prefix (&powers_of_s_g1[..len],
+ * pcs/univariate/kzg.rs:28).  Least-recently-used entries are released once the cache holds
+ * more than the byte limit (default: half of the device's memory). */
+int plonkish_cuda_bases_cached(int device, const void *bases_affine64, size_t n, uint64_t *handle);
+/* Forget (and release) the entry cached for this address: the Drop hook of the slice's owner. */
+int plonkish_cuda_bases_cache_evict(const void *bases_affine64);
+/* Bytes of device memory the cache may hold (0 = default); evicts down to it at once. */
+int plonkish_cuda_bases_cache_limit(size_t max_bytes);
+/* out[0] = cached slices, out[1] = bytes of device memory they hold. */
+int plonkish_cuda_bases_cache_stats(size_t out[2]);
 
 /* Same, from a device pointer on `device` (no host copy).  Registration expands the slice
  * into a table of window multiples T[w][i] = 2^(c*w) * P_i (W = ceil(254/c) rows, c chosen
@@ -78,9 +99,12 @@ int plonkish_cuda_bases_register_device(int device, const void *d_bases_affine64
 /* ---- the hot path, host buffers in, host result out -----------------------------------
  * out = sum_i scalars[i] * bases[i].  Exactly one of (bases_affine64, bases_handle != 0)
  * selects the bases; with a handle the bases are not copied again.  Runs on the
- * handle's device, or device 0.  Replaces msm.rs:84-115 for C = bn256::G1Affine;
- * when PLONKISH_CUDA_TIMER=1 it prints the reference's timer label
- * "variable_base_msm-{n}" (msm.rs:92) with the elapsed time to stderr. */
+ * handle's device, or device 0.  Replaces msm.rs:84-115 for C = bn256::G1Affine.
+ * Scalars (and unregistered bases) may live in pageable memory — a Rust Vec<Fr> is: such
+ * uploads go through the library's pinned staging ring (copier threads + one cudaMemcpyAsync
+ * per 4 MiB piece) so that they overlap the compute like uploads from pinned memory do.
+ * With the timer on (plonkish_cuda_timer_config) it prints the reference's timer lines
+ * "Start:/End: variable_base_msm-{n}" (msm.rs:92) in ark_std perf_trace format. */
 int plonkish_cuda_msm_bn254_g1(const void *scalars_mont32, const void *bases_affine64, uint64_t bases_handle, size_t n,
                                void *out_affine64);
 
@@ -195,12 +219,18 @@ void plonkish_cuda_keccak_f1600(uint64_t state[25]);
 int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs, const void *const *base_ptrs, size_t n,
                                       void *out_affine64);
 
-/* Point-sharded over the first n_gpus devices: GPU g runs the whole
- * pipeline on points [g*ceil(n/G), (g+1)*ceil(n/G)), the G projective partials are
- * gathered on device 0 and added there.  This is msm.rs:101-114 (chunk per thread,
- * fold the partials) lifted from threads to GPUs.  bases_affine64 is uploaded per
- * call unless bases_handle names a slice registered with .._register_sharded. */
+/* Point-sharded over the first n_gpus devices of this process: GPU g runs the
+ * whole pipeline on points [g*ceil(n/G), (g+1)*ceil(n/G)) — one host thread per device, the
+ * shard's scalars uploaded in chunks overlapped with its compute, as in the single-GPU call —
+ * the G 128-byte projective partials are gathered with ncclAllGather (ncclCommInitAll
+ * communicator, NVLink) and device 0 adds and normalises them.  This is msm.rs:101-114 (chunk
+ * per thread, fold the partials) lifted from threads to GPUs.  bases_affine64 is uploaded per
+ * call unless bases_handle names a slice registered with .._register_sharded.  NCCL is loaded at
+ * run time (libnccl.so.2); without it the call fails with PLONKISH_CUDA_E_COMM. */
 int plonkish_cuda_bases_register_sharded(int n_gpus, const void *bases_affine64, size_t n, uint64_t *handle);
+/* The same from device memory: d_bases_affine64[g] points at shard g (ceil(n/G) points; trailing shards may be short
+ * or empty) on device g; mode as in plonkish_cuda_bases_register_device. */
+int plonkish_cuda_bases_register_sharded_device(int n_gpus, const void *const *d_bases_affine64, size_t n, int mode, uint64_t *handle);
 int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars_mont32, const void *bases_affine64,
                                      uint64_t bases_handle, size_t n, void *out_affine64);
 
@@ -246,6 +276,25 @@ int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const vo
 
 /* Kernels launched by the library in this process since init (for bench accounting). */
 uint64_t plonkish_cuda_launch_count(void);
+/* Bytes uploaded through the pinned staging ring so far (pageable sources). */
+uint64_t plonkish_cuda_staged_bytes(void);
+
+/* The reference's timer lines (msm.rs:92 -> util/timer.rs:19-24 -> ark_std perf_trace; parsed by
+ * benchmark/src/bin/plotter.rs:337-373).  mode: 0 off, 1 stderr, 2 stdout (also PLONKISH_CUDA_TIMER=1 /
+ * =stdout); depth: nesting depth of the caller's open timers (indentation of the lines; also
+ * PLONKISH_CUDA_TIMER_DEPTH).  Every entry point prints one Start/End pair per MSM it performs, named
+ * variable_base_msm-{n}: a single call with its wall time; the batch entry with each MSM's own span on the
+ * compute stream; the many / open entries, whose MSMs run concurrently, with the call's wall time split by
+ * the library's load model — in every case the lines of one call add up to the call's duration, which is
+ * what the plotter's cost breakdown needs (it subtracts them from the enclosing timer). */
+int plonkish_cuda_timer_config(int mode, int depth);
+/* One Start/End pair "variable_base_msm-{n}" with the given duration, in the configured mode (for a host mirror that
+ * composes an MSM out of several calls and times it itself). */
+void plonkish_cuda_timer_emit(size_t n, double ms);
+
+/* FP64-pipe probe: out[0] = independent fma.rz.f64 per second; out[1] = DFMA per second and out[2] =
+ * mad.wide.u32 per second when the two are interleaved 1:1 in one instruction stream. */
+int plonkish_cuda_bench_fp64_pipe(int device, double out[3]);
 
 /* Integer-pipe microbenchmarks on `device` (CUDA-event timed):
  *   out[0] = independent mad.wide.u32 (IMAD.WIDE.U32) per second, all SMs busy

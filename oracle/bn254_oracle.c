@@ -739,6 +739,68 @@ void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out) {
     }
 }
 
+/* Threaded forms of the two sum-check loops for the full-size checks in bench.py: the pair range is cut into
+ * contiguous chunks, one pthread each (the way parallelize splits loops, util/parallel.rs:27-56); field addition is
+ * exact, so the per-chunk partial sums add up to the same round message bit for bit. */
+typedef struct {
+    const ofe_t *const *polys; size_t num_polys, first, count; const ofe_t *coeffs; const uint32_t *offsets, *term_polys;
+    size_t num_terms; int common; size_t degree; ofe_t *out;
+} sc_task_t;
+static void *sc_task_run(void *arg) {
+    sc_task_t *t = (sc_task_t *)arg;
+    const ofe_t **shifted = (const ofe_t **)malloc(sizeof(ofe_t *) * t->num_polys);
+    for (size_t p = 0; p < t->num_polys; ++p) shifted[p] = t->polys[p] + 2 * t->first;
+    oracle_sumcheck_round(shifted, t->num_polys, t->count, t->coeffs, t->offsets, t->term_polys, t->num_terms, t->common, t->degree, t->out);
+    free(shifted);
+    return NULL;
+}
+void oracle_sumcheck_round_mt(const ofe_t *const *polys, size_t num_polys, size_t size, const ofe_t *coeffs,
+                              const uint32_t *offsets, const uint32_t *term_polys, size_t num_terms, int common,
+                              size_t degree, int num_threads, ofe_t *out) {
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > size) num_threads = size ? (int)size : 1;
+    const size_t per = (size + num_threads - 1) / num_threads;
+    sc_task_t *tasks = (sc_task_t *)calloc(num_threads, sizeof(sc_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+    ofe_t *partial = (ofe_t *)calloc((size_t)num_threads * degree, sizeof(ofe_t));
+    for (int t = 0; t < num_threads; ++t) {
+        const size_t first = (size_t)t * per;
+        const size_t count = first >= size ? 0 : (first + per <= size ? per : size - first);
+        sc_task_t k = {polys, num_polys, first, count, coeffs, offsets, term_polys, num_terms, common, degree, partial + (size_t)t * degree};
+        tasks[t] = k;
+        pthread_create(&threads[t], NULL, sc_task_run, &tasks[t]);
+    }
+    memset(out, 0, sizeof(ofe_t) * degree);
+    for (int t = 0; t < num_threads; ++t) {
+        pthread_join(threads[t], NULL);
+        for (size_t x = 0; x < degree; ++x) fe_add(FR, out[x].l, partial[(size_t)t * degree + x].l, out[x].l);
+    }
+    free(tasks); free(threads); free(partial);
+}
+typedef struct { const ofe_t *evals; size_t n; const ofe_t *x; ofe_t *out; } fv_task_t;
+static void *fv_task_run(void *arg) {
+    fv_task_t *t = (fv_task_t *)arg;
+    oracle_fix_var(t->evals, t->n, t->x, t->out);
+    return NULL;
+}
+void oracle_fix_var_mt(const ofe_t *evals, size_t n, const ofe_t *x, int num_threads, ofe_t *out) {
+    const size_t half = n / 2;
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > half) num_threads = half ? (int)half : 1;
+    const size_t per = (half + num_threads - 1) / num_threads;
+    fv_task_t *tasks = (fv_task_t *)calloc(num_threads, sizeof(fv_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+    for (int t = 0; t < num_threads; ++t) {
+        const size_t first = (size_t)t * per;
+        const size_t count = first >= half ? 0 : (first + per <= half ? per : half - first);
+        fv_task_t k = {evals + 2 * first, 2 * count, x, out + first};
+        tasks[t] = k;
+        pthread_create(&threads[t], NULL, fv_task_run, &tasks[t]);
+    }
+    for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+    free(tasks); free(threads);
+}
+
 /* ---------------------------------------------------------------- transcript */
 
 /* Keccak-f[1600] and Keccak256 (original padding 0x01, rate 136): the hash behind Keccak256Transcript
@@ -803,4 +865,12 @@ void oracle_keccak256(const uint8_t *data, size_t len, uint8_t out[32]) {
     }
     for (int i = 0; i < 4; ++i)
         for (int b = 0; b < 8; ++b) out[8 * i + b] = (uint8_t)(st[i] >> (8 * b));
+}
+
+/* Array forms of the two conversions (the element-wise ctypes loop is too slow for the 2^24-element bench inputs). */
+void oracle_fe_from_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out) {
+    for (size_t i = 0; i < n; ++i) oracle_fe_from_canonical(which, in + 4 * i, (ofe_t *)(out + 4 * i));
+}
+void oracle_fe_to_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out) {
+    for (size_t i = 0; i < n; ++i) oracle_fe_to_canonical(which, (const ofe_t *)(in + 4 * i), out + 4 * i);
 }

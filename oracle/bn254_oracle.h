@@ -111,9 +111,18 @@ void oracle_sumcheck_round(const ofe_t *const *polys, size_t num_polys, size_t s
                            size_t degree, ofe_t *out);
 /* MultilinearPolynomial::fix_var (poly/multilinear.rs:179-189, 599-618): n evaluations in, n/2 out. */
 void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out);
+/* The same two loops cut over num_threads pthreads (identical results: field addition is exact). */
+void oracle_sumcheck_round_mt(const ofe_t *const *polys, size_t num_polys, size_t size, const ofe_t *coeffs,
+                              const uint32_t *offsets, const uint32_t *term_polys, size_t num_terms, int common,
+                              size_t degree, int num_threads, ofe_t *out);
+void oracle_fix_var_mt(const ofe_t *evals, size_t n, const ofe_t *x, int num_threads, ofe_t *out);
 
 /* Keccak256 (original Keccak padding) as used by Keccak256Transcript (util/transcript.rs:100-131, util/hash.rs:5-8). */
 void oracle_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
+
+/* Array forms of oracle_fe_from_canonical / oracle_fe_to_canonical. */
+void oracle_fe_from_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out);
+void oracle_fe_to_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,8 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fe_inv.argtypes = [ci, vp, vp]
         _lib.oracle_fe_from_canonical.argtypes = [ci, vp, vp]
         _lib.oracle_fe_to_canonical.argtypes = [ci, vp, vp]
+        _lib.oracle_fe_from_canonical_n.argtypes = [ci, vp, sz, vp]
+        _lib.oracle_fe_to_canonical_n.argtypes = [ci, vp, sz, vp]
         _lib.oracle_g1_generator.argtypes = [vp]
         _lib.oracle_g1_is_on_curve.argtypes = [vp]
         _lib.oracle_g1_is_on_curve.restype = ci
@@ -68,6 +70,8 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fixed_base_msm.argtypes = [vp, sz, vp, sz, ci, vp]
         _lib.oracle_sumcheck_round.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, sz, vp]
         _lib.oracle_fix_var.argtypes = [vp, sz, vp, vp]
+        _lib.oracle_sumcheck_round_mt.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, sz, ci, vp]
+        _lib.oracle_fix_var_mt.argtypes = [vp, sz, vp, ci, vp]
         _lib.oracle_keccak256.argtypes = [ctypes.c_char_p, sz, vp]
     return _lib
 
@@ -110,16 +114,14 @@ def fe_op(op: str, which: int, a, b=None) -> np.ndarray:
 def to_canonical(which: int, a) -> np.ndarray:
     a = _u64(a).reshape(-1, 4)
     out = np.zeros_like(a)
-    for i in range(a.shape[0]):
-        lib().oracle_fe_to_canonical(which, _ptr(a[i]), _ptr(out[i]))
+    lib().oracle_fe_to_canonical_n(which, _ptr(a), a.shape[0], _ptr(out))
     return out
 
 
 def from_canonical(which: int, c) -> np.ndarray:
     c = _u64(c).reshape(-1, 4)
     out = np.zeros_like(c)
-    for i in range(c.shape[0]):
-        lib().oracle_fe_from_canonical(which, _ptr(c[i]), _ptr(out[i]))
+    lib().oracle_fe_from_canonical_n(which, _ptr(c), c.shape[0], _ptr(out))
     return out
 
 
@@ -265,7 +267,7 @@ def flatten_terms(terms):
     return coeffs, offsets, np.array(flat if flat else [0], dtype=np.uint32)
 
 
-def sumcheck_round(polys, terms, common: int = -1) -> np.ndarray:
+def sumcheck_round(polys, terms, common: int = -1, num_threads: int = 1) -> np.ndarray:
     """piop/sum_check/classic/eval.rs:101-131: evaluations of the round polynomial at X = 1..degree."""
     polys = [_u64(p).reshape(-1, 4) for p in polys]
     n = polys[0].shape[0]
@@ -275,18 +277,36 @@ def sumcheck_round(polys, terms, common: int = -1) -> np.ndarray:
     degree = max(degree, 1)
     ptrs = (ctypes.c_void_p * len(polys))(*[p.ctypes.data for p in polys])
     out = np.zeros((degree, 4), dtype=np.uint64)
+    if num_threads > 1:
+        lib().oracle_sumcheck_round_mt(ctypes.cast(ptrs, ctypes.c_void_p), len(polys), n // 2, _ptr(coeffs), _ptr(offsets), _ptr(flat),
+                                       len(terms), int(common), degree, int(num_threads), _ptr(out))
+        return out
     lib().oracle_sumcheck_round(ctypes.cast(ptrs, ctypes.c_void_p), len(polys), n // 2, _ptr(coeffs), _ptr(offsets), _ptr(flat),
                                 len(terms), int(common), degree, _ptr(out))
     return out
 
 
-def fix_var(evals, x) -> np.ndarray:
+def fix_var(evals, x, num_threads: int = 1) -> np.ndarray:
     """MultilinearPolynomial::fix_var (poly/multilinear.rs:179-189)."""
     evals = _u64(evals).reshape(-1, 4)
     x = _u64(x).reshape(4)
     out = np.zeros((evals.shape[0] // 2, 4), dtype=np.uint64)
-    lib().oracle_fix_var(_ptr(evals), evals.shape[0], _ptr(x), _ptr(out))
+    if num_threads > 1:
+        lib().oracle_fix_var_mt(_ptr(evals), evals.shape[0], _ptr(x), int(num_threads), _ptr(out))
+    else:
+        lib().oracle_fix_var(_ptr(evals), evals.shape[0], _ptr(x), _ptr(out))
     return out
+
+
+def evaluate_multilinear(evals, point, num_threads: int = 1) -> np.ndarray:
+    """MultilinearPolynomial::evaluate (poly/multilinear.rs:142-170 in effect): fix every variable in turn, lowest first.
+    evals [2^k, 4], point [k, 4] -> [4] (Montgomery)."""
+    cur = _u64(evals).reshape(-1, 4)
+    pt = _u64(point).reshape(-1, 4)
+    assert cur.shape[0] == 1 << pt.shape[0]
+    for i in range(pt.shape[0]):
+        cur = fix_var(cur, pt[i], num_threads if cur.shape[0] >= 1 << 14 else 1)
+    return cur[0].copy()
 
 
 def keccak256(data: bytes) -> bytes:

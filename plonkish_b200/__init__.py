@@ -28,6 +28,13 @@ from .msm import (  # noqa: F401
     launch_count,
     bench_integer_pipe,
     bench_madd,
+    bench_fp64_pipe,
+    cached_bases,
+    cache_evict,
+    cache_limit,
+    cache_stats,
+    timer_config,
+    staged_bytes,
     random_scalars,
 )
 from .distributed import shard_bounds, variable_base_msm_sharded, variable_base_msm_sharded_host  # noqa: F401

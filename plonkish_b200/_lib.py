@@ -22,6 +22,15 @@ EXPORTS = (
     "plonkish_cuda_bases_register",
     "plonkish_cuda_bases_release",
     "plonkish_cuda_bases_register_device",
+    "plonkish_cuda_bases_cached",
+    "plonkish_cuda_bases_cache_evict",
+    "plonkish_cuda_bases_cache_limit",
+    "plonkish_cuda_bases_cache_stats",
+    "plonkish_cuda_timer_config",
+    "plonkish_cuda_timer_emit",
+    "plonkish_cuda_bases_register_sharded_device",
+    "plonkish_cuda_staged_bytes",
+    "plonkish_cuda_bench_fp64_pipe",
     "plonkish_cuda_msm_bn254_g1",
     "plonkish_cuda_msm_bn254_g1_batch",
     "plonkish_cuda_msm_bn254_g1_many",
@@ -94,6 +103,17 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_bases_register.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_bases_release.argtypes = [u64]
     lib.plonkish_cuda_bases_register_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_bases_cached.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_bases_cache_evict.argtypes = [vp]
+    lib.plonkish_cuda_bases_cache_limit.argtypes = [sz]
+    lib.plonkish_cuda_bases_cache_stats.argtypes = [ctypes.POINTER(sz)]
+    lib.plonkish_cuda_timer_config.argtypes = [ci, ci]
+    lib.plonkish_cuda_timer_emit.argtypes = [sz, ctypes.c_double]
+    lib.plonkish_cuda_timer_emit.restype = None
+    lib.plonkish_cuda_bases_register_sharded_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_staged_bytes.argtypes = []
+    lib.plonkish_cuda_staged_bytes.restype = u64
+    lib.plonkish_cuda_bench_fp64_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_many.argtypes = [vp, vp, vp, sz, vp]

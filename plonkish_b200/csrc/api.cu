@@ -13,12 +13,17 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace pk {
@@ -83,14 +88,55 @@ struct Ctx {
     std::mutex mu;
 };
 
+// Device memory behind a handle.  Handles are reference counted: the map holds one reference, every call in
+// flight (through its BasesView / ScalarsEntry copy) and every sum-check state another, so a *_release racing
+// with an enqueued MSM — Rust's Drop on one rayon worker while another still commits — frees the memory only
+// after the last user is gone.
+struct DevBlock {
+    int dev = 0;
+    void *ptr = nullptr;
+    bool owns = true;        // false: borrows the caller's device memory
+    Ctx *pool_ctx = nullptr; // != nullptr: carved from the stream-ordered pool of that context
+    size_t bytes = 0;
+    ~DevBlock() {
+        if (!ptr || !owns) return;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(dev);
+        if (pool_ctx) {
+            if (cudaFreeAsync(ptr, pool_ctx->stream) != cudaSuccess) cudaGetLastError();  // ordered after everything enqueued on the context's stream
+        } else {
+            cudaDeviceSynchronize();
+            cudaFree(ptr);
+        }
+        cudaSetDevice(cur);
+    }
+};
+typedef std::shared_ptr<DevBlock> BlockRef;
+static BlockRef make_block(int dev, void *ptr, bool owns, Ctx *pool_ctx, size_t bytes) {
+    BlockRef b = std::make_shared<DevBlock>();
+    b->dev = dev; b->ptr = ptr; b->owns = owns; b->pool_ctx = pool_ctx; b->bytes = bytes;
+    return b;
+}
+
 struct BasesEntry {
     int n_shards = 1;                 // 1: whole slice on `dev`; G: shard g on device g
     int dev = 0;
     size_t n = 0;
     std::vector<void *> d_ptr;        // per shard: plain bases, or the table of window multiples (row 0 = the bases)
+    std::vector<BlockRef> keep;       // per shard: owner of d_ptr (null for an empty shard)
     std::vector<size_t> shard_n;
     std::vector<uint32_t> table_c;    // per shard: window bits of the table, 0 = plain bases (no table)
-    bool owns = true;                 // false: d_ptr borrows the caller's device memory
+    void add_shard(int device, void *d, bool owns, size_t cnt, uint32_t tc) {
+        const size_t bytes = cnt * PLONKISH_CUDA_AFFINE_BYTES * (tc ? pk_windows_for(tc) : 1);
+        d_ptr.push_back(d); shard_n.push_back(cnt); table_c.push_back(tc);
+        keep.push_back(d ? make_block(device, d, owns, nullptr, bytes) : BlockRef());
+    }
+    size_t device_bytes() const {
+        size_t t = 0;
+        for (const BlockRef &b : keep) if (b && b->owns) t += b->bytes;
+        return t;
+    }
 };
 
 // What an MSM launch sequence reads its bases from.
@@ -98,12 +144,26 @@ struct BasesView {
     const void *ptr = nullptr;
     uint32_t table_c = 0;   // 0: plain affine array; else table T[w*stride + i]
     size_t stride = 0;
+    BlockRef keep;          // keeps the memory alive for the duration of the call
 };
 
 static std::mutex g_mu;
 static std::vector<Ctx *> g_ctx;
 static std::map<uint64_t, BasesEntry> g_bases;
 static uint64_t g_next_handle = 1;
+
+// Borrowed-slice cache (plonkish_cuda_bases_cached): host address -> registered handle, validated by content.
+struct CachedBases {
+    uint64_t handle = 0;
+    size_t n = 0, bytes = 0;
+    int dev = 0;
+    unsigned long long tick = 0;
+    std::vector<std::pair<size_t, uint64_t>> samples;  // (position, FNV-1a of the 64-byte point)
+};
+static std::mutex g_cache_mu;
+static std::map<uintptr_t, CachedBases> g_bases_cache;
+static unsigned long long g_cache_tick = 0;
+static size_t g_cache_limit = 0;  // 0: half of the device's memory
 
 static int grow(DeviceBuffer &b, size_t bytes) {
     if (bytes <= b.bytes) return 0;
@@ -140,8 +200,15 @@ struct PoolGuard {
 
 // Contexts are created on first use of a device, so a one-process-per-GPU rank only
 // ever touches its own GPU.  Caller must not hold g_mu.
+static int create_ctx_fill(Ctx *c, int device);
 static int create_ctx_locked(int device) {
     Ctx *c = new Ctx();
+    const int rc = create_ctx_fill(c, device);
+    if (rc != PLONKISH_CUDA_OK) { delete c; return rc; }  // (streams / events created before the failing call die with the process' context)
+    g_ctx[device] = c;
+    return PLONKISH_CUDA_OK;
+}
+static int create_ctx_fill(Ctx *c, int device) {
     c->dev = device;
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -168,7 +235,6 @@ static int create_ctx_locked(int device) {
     }
     CUDA_TRY(cudaMalloc(&c->d_out, 512));  // see the slot map at Ctx::d_out
     CUDA_TRY(cudaMallocHost(&c->h_out, 256));
-    g_ctx[device] = c;
     return PLONKISH_CUDA_OK;
 }
 
@@ -178,6 +244,157 @@ static Ctx *ctx_for(int device) {
     if (!g_ctx[device] && create_ctx_locked(device) != PLONKISH_CUDA_OK) return nullptr;
     return g_ctx[device];
 }
+
+
+// ------------------------------------------------------------- pageable uploads
+// The reference hands variable_base_msm borrowed slices (`poly.evals()`, kzg.rs:255): a Rust Vec<Fr> is
+// pageable memory.  cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread, one
+// thread, a few GB/s, and nothing overlaps it.  Uploads from unregistered host memory therefore go through the
+// library's own pinned ring: a few copier threads move 4 MiB pieces into pinned slots and enqueue one
+// cudaMemcpyAsync per piece on the destination stream, so the host-side copy of the next pieces runs while the
+// DMA engine moves the current one (about the bandwidth of the pinned path once 4+ threads copy).  Pinned /
+// registered sources (cudaPointerGetAttributes) keep the direct single cudaMemcpyAsync.
+class Stager {
+public:
+    static const size_t SLOT = (size_t)4 << 20;
+    static Stager &get() {
+        static Stager *s = new Stager();  // leaked on purpose: worker threads outlive static destruction
+        return *s;
+    }
+    // Copies [src, src + bytes) to device memory dst on `stream`; returns when every piece is enqueued
+    // (the source may be reused), not when the DMA is done.
+    cudaError_t run(int dev, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+        std::lock_guard<std::mutex> job_lock(job_mu_);
+        if (!ensure_ready(dev)) return cudaErrorMemoryAllocation;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            src_ = (const char *)src; dst_ = (char *)dst; bytes_ = bytes; stream_ = stream; dev_ = dev;
+            npieces_ = (bytes + SLOT - 1) / SLOT; next_ = 0; done_ = 0; err_ = cudaSuccess;
+            ++job_id_;
+        }
+        cv_work_.notify_all();
+        work(dev);  // the caller copies too
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return done_ == npieces_; });
+        base_ += npieces_;
+        npieces_ = 0;
+        return err_;
+    }
+    int threads() const { return nthreads_; }
+
+private:
+    Stager() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int t = hw >= 32 ? 8 : hw >= 16 ? 6 : hw >= 8 ? 4 : 2;
+        if (const char *e = getenv("PLONKISH_CUDA_COPY_THREADS")) {
+            const long v = atol(e);
+            if (v >= 1 && v <= 64) t = (int)v;
+        }
+        nthreads_ = t;
+        nslots_ = 2 * t + 2;
+    }
+    bool ensure_ready(int dev) {
+        if (slots_.empty()) {
+            slots_.resize(nslots_, nullptr);
+            for (int i = 0; i < nslots_; ++i) {
+                if (cudaHostAlloc(&slots_[i], SLOT, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); slots_.clear(); return false; }
+            }
+            slot_done_.assign(nslots_, 0);
+            slot_ev_.assign(nslots_, std::vector<cudaEvent_t>());
+            slot_dev_.assign(nslots_, -1);
+            for (int i = 0; i < nthreads_ - 1; ++i) std::thread([this] { worker(); }).detach();
+        }
+        for (int i = 0; i < nslots_; ++i) {
+            if ((int)slot_ev_[i].size() <= dev) slot_ev_[i].resize(dev + 1, nullptr);
+            if (!slot_ev_[i][dev]) {
+                cudaSetDevice(dev);
+                if (cudaEventCreateWithFlags(&slot_ev_[i][dev], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+            }
+        }
+        return true;
+    }
+    void worker() {
+        unsigned long long seen = 0;
+        for (;;) {
+            int dev;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return job_id_ != seen && next_ < npieces_; });
+                seen = job_id_;
+                dev = dev_;
+            }
+            work(dev);
+        }
+    }
+    void work(int dev) {
+        cudaSetDevice(dev);
+        for (;;) {
+            size_t i;
+            unsigned long long g;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (next_ >= npieces_) return;
+                i = next_++;
+                g = base_ + i;
+            }
+            const int s = (int)(g % (unsigned long long)nslots_);
+            {   // the slot's previous piece (global number g - nslots) must have recorded its event, then finished its DMA
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_slot_.wait(lk, [&] { return g < (unsigned long long)nslots_ || slot_done_[s] == g - nslots_ + 1; });
+            }
+            cudaError_t e = cudaSuccess;
+            if (slot_dev_[s] >= 0) e = cudaEventSynchronize(slot_ev_[s][slot_dev_[s]]);
+            const size_t off = i * SLOT;
+            const size_t len = bytes_ - off < SLOT ? bytes_ - off : SLOT;
+            memcpy(slots_[s], src_ + off, len);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dst_ + off, slots_[s], len, cudaMemcpyHostToDevice, stream_);
+            if (e == cudaSuccess) e = cudaEventRecord(slot_ev_[s][dev], stream_);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                slot_dev_[s] = dev;
+                slot_done_[s] = g + 1;
+                if (e != cudaSuccess && err_ == cudaSuccess) err_ = e;
+                ++done_;
+            }
+            cv_slot_.notify_all();
+            cv_done_.notify_all();
+        }
+    }
+    int nthreads_ = 2, nslots_ = 6;
+    std::vector<void *> slots_;
+    std::vector<std::vector<cudaEvent_t>> slot_ev_;  // [slot][device]
+    std::vector<int> slot_dev_;                      // device whose event the slot's last piece recorded
+    std::vector<unsigned long long> slot_done_;      // global number + 1 of the last piece recorded on the slot
+    std::mutex job_mu_, mu_;
+    std::condition_variable cv_work_, cv_done_, cv_slot_;
+    const char *src_ = nullptr;
+    char *dst_ = nullptr;
+    size_t bytes_ = 0, npieces_ = 0, next_ = 0, done_ = 0;
+    unsigned long long base_ = 0, job_id_ = 0;
+    cudaStream_t stream_ = nullptr;
+    int dev_ = 0;
+    cudaError_t err_ = cudaSuccess;
+};
+
+static std::atomic<unsigned long long> g_staged_bytes{0};
+// Host -> device copy of caller memory on `stream` (current device = c->dev).  Returns once the source may be reused.
+static cudaError_t upload(Ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    static const bool staging = [] {
+        const char *e = getenv("PLONKISH_CUDA_STAGING");
+        return !(e && e[0] == '0');
+    }();
+    if (staging && bytes >= ((size_t)1 << 20)) {
+        cudaPointerAttributes attr;
+        const cudaError_t q = cudaPointerGetAttributes(&attr, src);
+        if (q != cudaSuccess) cudaGetLastError();
+        if (q == cudaSuccess && attr.type == cudaMemoryTypeUnregistered) {
+            g_staged_bytes.fetch_add(bytes, std::memory_order_relaxed);
+            return Stager::get().run(c->dev, dst, src, bytes, stream);
+        }
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+}
+extern "C" uint64_t plonkish_cuda_staged_bytes(void) { return g_staged_bytes.load(); }
 
 extern "C" int plonkish_cuda_init(int n_devices) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -190,36 +407,18 @@ extern "C" int plonkish_cuda_init(int n_devices) {
     return PLONKISH_CUDA_OK;
 }
 
-static std::atomic<bool> g_peers_enabled{false};
-// Direct NVLink peer copies for the single-process multi-GPU gather (ignored where unsupported).
-static void enable_peer_access(int n_gpus) {
-    if (g_peers_enabled.exchange(true)) return;
-    for (int a = 0; a < n_gpus; ++a) {
-        for (int b = 0; b < n_gpus; ++b) {
-            int can = 0;
-            if (a == b || cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) continue;
-            cudaSetDevice(a);
-            if (cudaDeviceEnablePeerAccess(b, 0) != cudaSuccess) cudaGetLastError();
-        }
-    }
-}
-
 extern "C" int plonkish_cuda_device_count(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     return (int)g_ctx.size();
 }
 
 static void release_all_scalars();
+static void nccl_shutdown();
 extern "C" void plonkish_cuda_shutdown(void) {
+    nccl_shutdown();
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto &kv : g_bases) {
-        for (size_t s = 0; s < kv.second.d_ptr.size(); ++s) {
-            if (!kv.second.owns) continue;
-            cudaSetDevice(kv.second.n_shards == 1 ? kv.second.dev : (int)s);
-            cudaFree(kv.second.d_ptr[s]);
-        }
-    }
-    g_bases.clear();
+    g_bases.clear();  // the blocks free themselves (DevBlock)
+    g_bases_cache.clear();
     release_all_scalars();
     for (Ctx *c : g_ctx) {
         if (!c) continue;
@@ -259,7 +458,6 @@ static int make_resident(Ctx *c, const void *src, bool src_is_device, size_t n, 
     CUDA_TRY(cudaSetDevice(c->dev));
     // One-time, heavyweight: order after whatever stream produced a device-side source.
     if (src_is_device) CUDA_TRY(cudaDeviceSynchronize());
-    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     bool want_table = (mode == 2) || (mode == 0 && precompute_enabled());
     uint32_t tc = pk_table_window_bits((u32)(n > 0xffffffffull ? 0xffffffffull : n));
     if (const char *e = getenv("PLONKISH_CUDA_TABLE_C")) {  // tuning override: window bits of the table
@@ -284,25 +482,34 @@ static int make_resident(Ctx *c, const void *src, bool src_is_device, size_t n, 
         CUDA_TRY(cudaMalloc(&d, n * PLONKISH_CUDA_AFFINE_BYTES));
         // stream-ordered with everything that will read it (a plain cudaMemcpy from pageable memory may
         // return while the DMA is still in flight on the legacy stream, which c->stream does not wait for)
-        CUDA_TRY(cudaMemcpyAsync(d, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        {
+            const cudaError_t ce = upload(c, d, src, n * PLONKISH_CUDA_AFFINE_BYTES, c->stream);
+            const cudaError_t se = ce == cudaSuccess ? cudaStreamSynchronize(c->stream) : ce;
+            if (se != cudaSuccess) { cudaFree(d); return fail(PLONKISH_CUDA_E_CUDA, "bases_register: upload failed: %s", cudaGetErrorString(se)); }
+        }
         *out_ptr = d; *owns = true;
         return PLONKISH_CUDA_OK;
     }
     void *table = nullptr, *cur = nullptr, *staged = nullptr;
-    CUDA_TRY(cudaMalloc(&table, table_bytes));
-    CUDA_TRY(cudaMalloc(&cur, cur_bytes));
+    cudaError_t ce = cudaMalloc(&table, table_bytes);
+    if (ce == cudaSuccess) ce = cudaMalloc(&cur, cur_bytes);
     const void *d_src = src;
-    if (!src_is_device) {
-        CUDA_TRY(cudaMalloc(&staged, n * PLONKISH_CUDA_AFFINE_BYTES));
-        CUDA_TRY(cudaMemcpyAsync(staged, src, n * PLONKISH_CUDA_AFFINE_BYTES, kind, c->stream));  // ordered before the table kernels
+    if (ce == cudaSuccess && !src_is_device) {
+        ce = cudaMalloc(&staged, n * PLONKISH_CUDA_AFFINE_BYTES);
+        if (ce == cudaSuccess) ce = upload(c, staged, src, n * PLONKISH_CUDA_AFFINE_BYTES, c->stream);  // ordered before the table kernels
         d_src = staged;
     }
-    pk_enqueue_table_build(d_src, (u32)n, tc, tw, (xyzz *)cur, (affine *)table, c->stream);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaFree(cur));
-    if (staged) CUDA_TRY(cudaFree(staged));
+    if (ce == cudaSuccess) {
+        pk_enqueue_table_build(d_src, (u32)n, tc, tw, (xyzz *)cur, (affine *)table, c->stream);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    cudaFree(cur);
+    cudaFree(staged);
+    if (ce != cudaSuccess) {
+        cudaFree(table);
+        return fail(PLONKISH_CUDA_E_CUDA, "bases_register: building the table of %u x %zu points failed: %s", tw, n, cudaGetErrorString(ce));
+    }
     *out_ptr = table; *out_c = tc; *owns = true;
     return PLONKISH_CUDA_OK;
 }
@@ -323,10 +530,11 @@ static int register_one(int device, const void *src, bool src_is_device, size_t 
         std::lock_guard<std::mutex> lk(c->mu);
         void *d = nullptr;
         uint32_t tc = 0;
-        int rc = make_resident(c, src, src_is_device, n, mode, &d, &tc, &e.owns);
+        bool owns = true;
+        int rc = make_resident(c, src, src_is_device, n, mode, &d, &tc, &owns);
         if (rc) return rc;
         e.n_shards = 1; e.dev = device; e.n = n;
-        e.d_ptr.push_back(d); e.shard_n.push_back(n); e.table_c.push_back(tc);
+        e.add_shard(device, d, owns, n, tc);
     }
     *handle = publish(e);
     return PLONKISH_CUDA_OK;
@@ -360,7 +568,35 @@ extern "C" int plonkish_cuda_bases_register_sharded(int n_gpus, const void *base
             int rc = make_resident(c, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, false, cnt, 0, &d, &tc, &owns);
             if (rc) return rc;
         }
-        e.d_ptr.push_back(d); e.shard_n.push_back(cnt); e.table_c.push_back(tc);
+        e.add_shard(g, d, true, cnt, tc);  // an error below frees the earlier shards with `e`
+    }
+    *handle = publish(e);
+    return PLONKISH_CUDA_OK;
+}
+
+// The same from device memory: d_bases[g] points at shard g (ceil(n/G) points, the last shards short or empty)
+// on device g.  mode as in bases_register_device.
+extern "C" int plonkish_cuda_bases_register_sharded_device(int n_gpus, const void *const *d_bases, size_t n, int mode, uint64_t *handle) {
+    if (!d_bases || !handle || n == 0 || n_gpus < 1 || mode < 0 || mode > 2) return fail(PLONKISH_CUDA_E_INVALID, "bases_register_sharded_device: bad argument");
+    if (n_gpus > plonkish_cuda_device_count()) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_register_sharded_device: %d GPUs requested, %d initialised", n_gpus, plonkish_cuda_device_count());
+    const size_t per = (n + n_gpus - 1) / n_gpus;  // msm.rs:101 chunk_size
+    BasesEntry e;
+    e.n_shards = n_gpus; e.dev = 0; e.n = n;
+    for (int g = 0; g < n_gpus; ++g) {
+        const size_t beg = (size_t)g * per;
+        const size_t cnt = beg >= n ? 0 : (beg + per <= n ? per : n - beg);
+        void *d = nullptr;
+        uint32_t tc = 0;
+        bool owns = true;
+        if (cnt) {
+            if (!d_bases[g]) return fail(PLONKISH_CUDA_E_INVALID, "bases_register_sharded_device: null shard %d", g);
+            Ctx *c = ctx_for(g);
+            if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_register_sharded_device: device %d not initialised", g);
+            std::lock_guard<std::mutex> lk(c->mu);
+            int rc = make_resident(c, d_bases[g], true, cnt, mode, &d, &tc, &owns);
+            if (rc) return rc;
+        }
+        e.add_shard(g, d, owns, cnt, tc);
     }
     *handle = publish(e);
     return PLONKISH_CUDA_OK;
@@ -375,12 +611,125 @@ extern "C" int plonkish_cuda_bases_release(uint64_t handle) {
         e = it->second;
         g_bases.erase(it);
     }
-    for (size_t s = 0; s < e.d_ptr.size(); ++s) {
-        if (!e.d_ptr[s] || !e.owns) continue;
-        CUDA_TRY(cudaSetDevice(e.n_shards == 1 ? e.dev : (int)s));
-        CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaFree(e.d_ptr[s]));
+    // `e` holds the map's reference now: the memory is freed here, or by the last call still using the slice
+    return PLONKISH_CUDA_OK;
+}
+
+// ---- borrowed slices: the cache behind the Rust shim's variable_base_msm --------------------------------------
+// Inside variable_base_msm the shim sees a borrowed &[G1Affine] and nothing else (msm.rs:84-87): it cannot know
+// whether the slice is a ProverParam's SRS (static: worth a resident table) or a temporary that will be freed and
+// whose address the allocator will hand to the next Vec (IPA's folded generators, Hyrax rows, a second setup).  So
+// the cache is keyed by address but trusted only after its content fingerprint — the first points, the last one
+// and two dozen pseudo-random positions, hashed at registration — matches what is at that address now; a mismatch
+// evicts the entry and registers the slice afresh.  A longer slice at a cached address replaces the entry, a
+// shorter one uses its prefix (&powers_of_s_g1[..len], univariate/kzg.rs:28).  Entries are evicted least recently
+// used first once the resident tables exceed the byte limit (default: half of the device's memory).
+static uint64_t fnv1a64(const unsigned char *p, size_t len) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t i = 0; i < len; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+static void cache_sample_positions(size_t n, std::vector<size_t> &pos) {
+    pos.clear();
+    for (size_t i = 0; i < n && i < 8; ++i) pos.push_back(i);
+    if (n > 8) pos.push_back(n - 1);
+    for (uint64_t k = 1; n > 9 && k <= 24; ++k) pos.push_back((size_t)((k * 0x9e3779b97f4a7c15ull) % n));
+}
+static void cache_drop_locked(std::map<uintptr_t, CachedBases>::iterator it) {  // caller holds g_cache_mu
+    const uint64_t h = it->second.handle;
+    g_bases_cache.erase(it);
+    plonkish_cuda_bases_release(h);
+}
+
+extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64, size_t n, uint64_t *handle) {
+    if (!bases_affine64 || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "bases_cached: null argument or n == 0");
+    const unsigned char *src = (const unsigned char *)bases_affine64;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_bases_cache.find((uintptr_t)src);
+    if (it != g_bases_cache.end()) {
+        CachedBases &e = it->second;
+        bool ok = e.dev == device && e.n >= n;
+        for (size_t k = 0; ok && k < e.samples.size(); ++k) {
+            if (e.samples[k].first >= n) continue;  // beyond the caller's slice: not ours to read
+            ok = fnv1a64(src + e.samples[k].first * PLONKISH_CUDA_AFFINE_BYTES, PLONKISH_CUDA_AFFINE_BYTES) == e.samples[k].second;
+        }
+        if (ok && n < e.n) ok = fnv1a64(src + (n - 1) * PLONKISH_CUDA_AFFINE_BYTES, PLONKISH_CUDA_AFFINE_BYTES) ==
+                                 [&] { unsigned char b[PLONKISH_CUDA_AFFINE_BYTES]; return plonkish_cuda_bases_read(e.handle, n - 1, 1, b) == 0 ? fnv1a64(b, sizeof(b)) : 0; }();
+        if (ok) {
+            e.tick = ++g_cache_tick;
+            *handle = e.handle;
+            return PLONKISH_CUDA_OK;
+        }
+        cache_drop_locked(it);  // stale address, another device, or a longer slice than the one registered
     }
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_cached: device %d not initialised (call plonkish_cuda_init)", device);
+    size_t limit = g_cache_limit;
+    if (!limit) {
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(device);
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) limit = total_b / 2;
+    }
+    const size_t estimate = n * PLONKISH_CUDA_AFFINE_BYTES * pk_windows_for(pk_table_window_bits((u32)(n > 0xffffffffull ? 0xffffffffull : n)));
+    for (;;) {  // make room: least recently used first
+        size_t total = 0;
+        auto lru = g_bases_cache.end();
+        for (auto j = g_bases_cache.begin(); j != g_bases_cache.end(); ++j) {
+            total += j->second.bytes;
+            if (lru == g_bases_cache.end() || j->second.tick < lru->second.tick) lru = j;
+        }
+        if (lru == g_bases_cache.end() || total + estimate <= limit) break;
+        cache_drop_locked(lru);
+    }
+    CachedBases e;
+    int rc = plonkish_cuda_bases_register(device, bases_affine64, n, &e.handle);
+    if (rc) return rc;
+    e.n = n; e.dev = device; e.tick = ++g_cache_tick;
+    {
+        std::lock_guard<std::mutex> lk2(g_mu);
+        e.bytes = g_bases[e.handle].device_bytes();
+    }
+    std::vector<size_t> pos;
+    cache_sample_positions(n, pos);
+    for (size_t q : pos) e.samples.push_back({q, fnv1a64(src + q * PLONKISH_CUDA_AFFINE_BYTES, PLONKISH_CUDA_AFFINE_BYTES)});
+    g_bases_cache[(uintptr_t)src] = e;
+    *handle = e.handle;
+    return PLONKISH_CUDA_OK;
+}
+
+// Drop hook for the owner of a cached slice (ProverParam's Drop in the shim): forget and free it now.
+extern "C" int plonkish_cuda_bases_cache_evict(const void *bases_affine64) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_bases_cache.find((uintptr_t)bases_affine64);
+    if (it == g_bases_cache.end()) return PLONKISH_CUDA_OK;
+    cache_drop_locked(it);
+    return PLONKISH_CUDA_OK;
+}
+
+// max_bytes of resident tables the cache may hold (0 = default, half of the device's memory); evicts down to it.
+extern "C" int plonkish_cuda_bases_cache_limit(size_t max_bytes) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_limit = max_bytes;
+    for (;;) {
+        size_t total = 0;
+        auto lru = g_bases_cache.end();
+        for (auto j = g_bases_cache.begin(); j != g_bases_cache.end(); ++j) {
+            total += j->second.bytes;
+            if (lru == g_bases_cache.end() || j->second.tick < lru->second.tick) lru = j;
+        }
+        if (!max_bytes || lru == g_bases_cache.end() || total <= max_bytes) break;
+        cache_drop_locked(lru);
+    }
+    return PLONKISH_CUDA_OK;
+}
+
+// out[0] = entries, out[1] = bytes of device memory they hold.
+extern "C" int plonkish_cuda_bases_cache_stats(size_t out[2]) {
+    if (!out) return fail(PLONKISH_CUDA_E_INVALID, "bases_cache_stats: null output");
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    out[0] = g_bases_cache.size();
+    out[1] = 0;
+    for (auto &kv : g_bases_cache) out[1] += kv.second.bytes;
     return PLONKISH_CUDA_OK;
 }
 
@@ -438,15 +787,74 @@ static int mark_done(Ctx *c, cudaStream_t stream) {
     return PLONKISH_CUDA_OK;
 }
 
+// ------------------------------------------------------------------- timer lines
+// The reference wraps every MSM in start_timer(|| format!("variable_base_msm-{}", n)) (msm.rs:92, util/timer.rs:19-24:
+// ark_std's perf_trace) and benchmark/src/bin/plotter.rs:337-373 rebuilds its cost breakdown from those Start/End
+// lines.  A single call keeps that line on the Rust side.  The batch / many / open entry points replace several
+// reference calls, so the library prints one Start/End pair per MSM itself, in perf_trace's format, each with that
+// MSM's own share of the call (the shares add up to the call's duration: the plotter subtracts them from the parent).
+// mode: 0 off, 1 stderr, 2 stdout (PLONKISH_CUDA_TIMER=1 / stdout); depth = nesting depth of the caller's timers.
+static std::atomic<int> g_timer_mode{-1}, g_timer_depth{-1};
+static int timer_mode() {
+    int m = g_timer_mode.load(std::memory_order_relaxed);
+    if (m >= 0) return m;
+    const char *e = getenv("PLONKISH_CUDA_TIMER");
+    m = !e ? 0 : (e[0] == '1' ? 1 : (e[0] == '2' || e[0] == 's') ? 2 : 0);
+    g_timer_mode.store(m);
+    return m;
+}
+static int timer_depth() {
+    int d = g_timer_depth.load(std::memory_order_relaxed);
+    if (d >= 0) return d;
+    const char *e = getenv("PLONKISH_CUDA_TIMER_DEPTH");
+    d = e ? (int)atol(e) : 0;
+    if (d < 0 || d > 32) d = 0;
+    g_timer_depth.store(d);
+    return d;
+}
+extern "C" int plonkish_cuda_timer_config(int mode, int depth) {
+    if (mode < 0 || mode > 2 || depth < 0 || depth > 32) return fail(PLONKISH_CUDA_E_INVALID, "timer_config: mode 0..2, depth 0..32");
+    g_timer_mode.store(mode);
+    g_timer_depth.store(depth);
+    return PLONKISH_CUDA_OK;
+}
+static void timer_emit(size_t n, double ms) {
+    const int mode = timer_mode();
+    if (!mode) return;
+    FILE *f = mode == 2 ? stdout : stderr;
+    const int indent = 2 * timer_depth();
+    std::string pad;
+    for (int i = 0; i < indent; ++i) pad += "\xc2\xb7";  // PAD_CHAR of perf_trace (U+00B7)
+    char msg[96], dur[48];
+    snprintf(msg, sizeof(msg), "variable_base_msm-%zu ", n);
+    const double ns = ms * 1e6;
+    if (ns >= 1e9) snprintf(dur, sizeof(dur), "%.3fs", ns / 1e9);
+    else if (ns >= 1e6) snprintf(dur, sizeof(dur), "%.3fms", ns / 1e6);
+    else if (ns >= 1e3) snprintf(dur, sizeof(dur), "%.3f\xc2\xb5s", ns / 1e3);
+    else snprintf(dur, sizeof(dur), "%.0fns", ns);
+    std::string line = pad + "Start:   " + (std::string(msg, strlen(msg) - 1)) + "\n" + pad + "End:     " + msg;
+    for (int w = (int)strlen(msg); w < 75 - indent; ++w) line += '.';
+    line += dur;
+    line += "\n";
+    fputs(line.c_str(), f);
+    fflush(f);
+}
+// One Start/End pair for an MSM the caller timed itself (a host mirror composing several calls).
+extern "C" void plonkish_cuda_timer_emit(size_t n, double ms) { timer_emit(n, ms); }
+static double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
 static void timer_report(size_t n, std::chrono::steady_clock::time_point t0) {
-    static const bool enabled = [] {
-        const char *e = getenv("PLONKISH_CUDA_TIMER");
-        return e && e[0] == '1';
-    }();
-    if (!enabled) return;
-    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    // Same label as start_timer(|| format!("variable_base_msm-{}", n)) at msm.rs:92.
-    fprintf(stderr, "variable_base_msm-%zu ....... %.3fms\n", n, ms);
+    if (timer_mode()) timer_emit(n, ms_since(t0));
+}
+// Several MSMs that ran concurrently inside one call: the call's duration is split by the library's own load model
+// (0.6 ms of launch latency + 3 ns per point, see enqueue_many), so the lines add up to the call.
+static void timer_report_shared(const std::vector<size_t> &ns, std::chrono::steady_clock::time_point t0) {
+    if (!timer_mode()) return;
+    const double total = ms_since(t0);
+    double wsum = 0;
+    for (size_t n : ns) wsum += (double)n + 200000.0;
+    for (size_t n : ns) timer_emit(n, total * ((double)n + 200000.0) / wsum);
 }
 
 // --------------------------------------------------------------- device entry
@@ -491,6 +899,11 @@ static int view_of(uint64_t handle, size_t n, int shard, BasesView &v, int *devi
     v.ptr = e.d_ptr[shard];
     v.table_c = e.table_c[shard];
     v.stride = e.shard_n[shard];
+    v.keep = e.keep[shard];
+    // A short prefix of a long slice (&powers_of_s_g1[..len], univariate/kzg.rs:28) would pay for the table's full
+    // bucket set (2^(c-1) buckets sized for the whole slice): below 1/16 of the slice the plain layout on row 0 of
+    // the table — the bases themselves — is cheaper.
+    if (v.table_c && n && v.table_c > pk_table_window_bits((u32)n) + 3) v.table_c = 0;
     if (device) *device = e.n_shards == 1 ? e.dev : shard;
     return PLONKISH_CUDA_OK;
 }
@@ -580,8 +993,7 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
         const size_t cnt = cuts[k] - done;
         char *d_chunk = (char *)d_dst + done * PLONKISH_CUDA_SCALAR_BYTES;
         cudaStream_t cs = (nchunks > 1) ? c->copy_stream : c->stream;
-        CUDA_TRY(cudaMemcpyAsync(d_chunk, (const char *)h_scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES,
-                                 cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(upload(c, d_chunk, (const char *)h_scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, cs));
         if (nchunks > 1) {
             CUDA_TRY(cudaEventRecord(c->chunk_ready[k], cs));
             CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[k], 0));
@@ -626,7 +1038,7 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
     if (!bases_handle) {
         rc = grow(c->bases_tmp, n * PLONKISH_CUDA_AFFINE_BYTES);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(c->bases_tmp.ptr, bases, n * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(upload(c, c->bases_tmp.ptr, bases, n * PLONKISH_CUDA_AFFINE_BYTES, c->stream));
         view.ptr = c->bases_tmp.ptr;
     }
     xyzz *res = nullptr;
@@ -689,6 +1101,14 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     MsmPlan plan = plan_for(c, view, n, 0);
     if ((rc = grow(c->arena, pk_workspace_bytes(plan)))) return rc;  // before anything is in flight: growing synchronises
     void *bufs[2] = {c->scalars.ptr, c->scalars2.ptr};
+    const bool timed = timer_mode() != 0;
+    std::vector<cudaEvent_t> tev;  // timed: the end of every MSM on the compute stream, for one timer line each
+    struct TevGuard { std::vector<cudaEvent_t> &v; ~TevGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); } } tev_guard{tev};
+    if (timed) {
+        tev.resize(count + 1, nullptr);
+        for (auto &e : tev) CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventRecord(tev[0], c->stream));
+    }
     // MSM 0: nothing to hide its upload behind, so it goes up in growing chunks, each copying
     // while its predecessor computes (enqueue_host_msm); sizes the arena for the chunked layout.
     {
@@ -696,6 +1116,7 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
         if ((rc = enqueue_host_msm(c, scalars_list[0], view, n, &res0, keep ? kept[0] : bufs[0]))) return rc;
         PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, res0, 1u, (affine *)c->batch_out.ptr, (xyzz *)nullptr);
         CUDA_TRY(cudaEventRecord(c->buf_free[0], c->stream));
+        if (timed) CUDA_TRY(cudaEventRecord(tev[1], c->stream));
     }
     MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
     ws.result = (xyzz *)((char *)c->d_out + 256);
@@ -704,13 +1125,14 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
         const int b = (int)(j & 1);
         void *dst = keep ? kept[j] : bufs[b];
         if (j >= 2 && !keep) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->buf_free[b], 0));  // MSM j-2 has consumed this buffer
-        CUDA_TRY(cudaMemcpyAsync(dst, scalars_list[j], bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(upload(c, dst, scalars_list[j], bytes, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->chunk_ready[b], c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
         pk_enqueue_msm(plan, dst, view.ptr, ws, nullptr, c->stream);
         CUDA_TRY(cudaEventRecord(c->buf_free[b], c->stream));  // scalars are dead after the decompose; recorded after the whole MSM for simplicity
         PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, ws.result, 1u,
                   (affine *)((char *)c->batch_out.ptr + j * PLONKISH_CUDA_AFFINE_BYTES), (xyzz *)nullptr);
+        if (timed) CUDA_TRY(cudaEventRecord(tev[j + 1], c->stream));
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
@@ -719,7 +1141,23 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     kept_guard.armed = false;
     if (keep)
         for (size_t j = 0; j < count; ++j) keep[j] = publish_scalars(c->dev, kept[j], n);
-    for (size_t j = 0; j < count; ++j) timer_report(n, t0);
+    if (timed) {
+        // MSM j's line: from the end of MSM j-1 to its own end on the compute stream (uploads overlap the
+        // predecessor); the host time before the first event and after the last goes to the first and last line
+        const double wall = ms_since(t0);
+        std::vector<double> ms(count, 0.0);
+        double dev_total = 0;
+        for (size_t j = 0; j < count; ++j) {
+            float f = 0;
+            CUDA_TRY(cudaEventElapsedTime(&f, tev[j], tev[j + 1]));
+            ms[j] = f;
+            dev_total += f;
+        }
+        const double rest = wall > dev_total ? wall - dev_total : 0.0;
+        ms[0] += rest * 0.5;
+        ms[count - 1] += rest * 0.5;
+        for (size_t j = 0; j < count; ++j) timer_emit(n, ms[j]);
+    }
     return PLONKISH_CUDA_OK;
 }
 
@@ -815,7 +1253,7 @@ static int enqueue_many(Ctx *c, const std::vector<ManyJob> &jobs, void *d_out_li
             lane_used[lane_of[j]] = true;
             const void *d_sc = jb.scalars;
             if (!jb.on_device) {
-                CUDA_TRY(cudaMemcpyAsync(ln.scalars.ptr, jb.scalars, jb.n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, ln.stream));
+                CUDA_TRY(upload(c, ln.scalars.ptr, jb.scalars, jb.n * PLONKISH_CUDA_SCALAR_BYTES, ln.stream));
                 d_sc = ln.scalars.ptr;
             }
             MsmPlan plan = plan_for(c, jb.view, jb.n, 0);
@@ -871,7 +1309,7 @@ extern "C" int plonkish_cuda_msm_bn254_g1_many(const void *const *scalars_list, 
     CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
     if ((rc = mark_done(c, c->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    for (size_t j = 0; j < count; ++j) timer_report(ns[j], t0);
+    timer_report_shared(std::vector<size_t>(ns, ns + count), t0);
     return PLONKISH_CUDA_OK;
 }
 
@@ -917,10 +1355,61 @@ extern "C" int plonkish_cuda_msm_bn254_g1_gather(const void *const *scalar_ptrs,
 }
 
 // ------------------------------------------------------------ multi-GPU entry
-// One process, G devices: shard g runs on device g's stream; the G projective
-// partials are copied to device 0 over NVLink peer copies and added there.  (The
-// one-process-per-GPU deployment gathers the same 128-byte partials with NCCL —
-// plonkish_b200/distributed.py.)
+// One process, G devices (msm.rs:101-114 lifted from rayon threads to GPUs): one host thread per device runs the
+// single-GPU host path on its shard — chunk-pipelined upload on the device's copy stream, decompose / sort /
+// accumulate / reduce on its compute stream — and leaves one 128-byte projective partial; the partials are gathered
+// with ncclAllGather over NVLink on a ncclCommInitAll communicator and device 0 adds them and normalises.  (The
+// one-process-per-GPU deployment does the same gather through torch.distributed — plonkish_b200/distributed.py.)
+// NCCL is dlopen'ed (libnccl.so.2): the library has no link-time dependency on it and fails loudly without it.
+typedef struct ncclComm *pk_ncclComm_t;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(pk_ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(pk_ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, pk_ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::vector<pk_ncclComm_t> comms;  // communicator of device g among devices 0..comms.size()-1
+};
+static std::mutex g_nccl_mu;
+static NcclApi g_nccl;
+
+static int nccl_ensure(int n_gpus) {  // caller holds g_nccl_mu
+    if (!g_nccl.lib) {
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return fail(PLONKISH_CUDA_E_COMM, "msm_multi: cannot load libnccl.so.2: %s", dlerror());
+        g_nccl.CommInitAll = (int (*)(pk_ncclComm_t *, int, const int *))dlsym(lib, "ncclCommInitAll");
+        g_nccl.CommDestroy = (int (*)(pk_ncclComm_t))dlsym(lib, "ncclCommDestroy");
+        g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, pk_ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+        g_nccl.GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+        g_nccl.GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+        g_nccl.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+        if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.GetErrorString) {
+            dlclose(lib);
+            return fail(PLONKISH_CUDA_E_COMM, "msm_multi: libnccl.so.2 lacks an expected symbol");
+        }
+        g_nccl.lib = lib;
+    }
+    if ((int)g_nccl.comms.size() == n_gpus) return PLONKISH_CUDA_OK;
+    for (pk_ncclComm_t cm : g_nccl.comms) g_nccl.CommDestroy(cm);
+    g_nccl.comms.assign(n_gpus, nullptr);
+    std::vector<int> devs(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) devs[g] = g;
+    const int r = g_nccl.CommInitAll(g_nccl.comms.data(), n_gpus, devs.data());
+    if (r != 0) {
+        g_nccl.comms.clear();
+        return fail(PLONKISH_CUDA_E_COMM, "msm_multi: ncclCommInitAll over %d devices failed: %s", n_gpus, g_nccl.GetErrorString(r));
+    }
+    return PLONKISH_CUDA_OK;
+}
+static void nccl_shutdown() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    for (pk_ncclComm_t cm : g_nccl.comms) g_nccl.CommDestroy(cm);
+    g_nccl.comms.clear();
+}
+
 extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars, const void *bases, uint64_t bases_handle, size_t n, void *out_affine64) {
     const auto t0 = std::chrono::steady_clock::now();
     if (!out_affine64) return fail(PLONKISH_CUDA_E_INVALID, "msm_multi: null output");
@@ -937,61 +1426,86 @@ extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars,
     std::vector<Ctx *> cs(n_gpus);
     for (int g = 0; g < n_gpus; ++g) {
         cs[g] = ctx_for(g);
-        if (!cs[g]) return PLONKISH_CUDA_E_NO_DEVICE;
+        if (!cs[g]) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_multi: device %d not initialised", g);
     }
-    enable_peer_access(n_gpus);
-    for (int g = 0; g < n_gpus; ++g) cs[g]->mu.lock();
-    int rc = PLONKISH_CUDA_OK;
-    auto unlock_all = [&] { for (int g = n_gpus - 1; g >= 0; --g) cs[g]->mu.unlock(); };
-#define MULTI_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { unlock_all(); return fail(PLONKISH_CUDA_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
-    rc = 0;
-    MULTI_TRY(cudaSetDevice(0));
-    if ((rc = grow(cs[0]->partials, (size_t)n_gpus * PLONKISH_CUDA_XYZZ_BYTES))) { unlock_all(); return rc; }
-    std::vector<cudaEvent_t> done(n_gpus, nullptr);
-    for (int g = 0; g < n_gpus; ++g) {
+    std::lock_guard<std::mutex> nccl_lock(g_nccl_mu);  // one multi-GPU call at a time (the communicators are shared)
+    int rc = n_gpus > 1 ? nccl_ensure(n_gpus) : PLONKISH_CUDA_OK;
+    if (rc) return rc;
+    struct LockAll {  // every device context for the whole call, in device order
+        std::vector<Ctx *> &v;
+        explicit LockAll(std::vector<Ctx *> &cs_) : v(cs_) { for (Ctx *c : v) c->mu.lock(); }
+        ~LockAll() { for (size_t g = v.size(); g-- > 0;) v[g]->mu.unlock(); }
+    } lock_all(cs);
+    // per device: [0, G) gathered partials, [G] this device's own
+    std::vector<int> rcs(n_gpus, 0);
+    std::vector<std::string> errs(n_gpus);
+    auto shard = [&](int g) {
         Ctx *c = cs[g];
-        const size_t beg = (size_t)g * per;
-        const size_t cnt = beg >= n ? 0 : (beg + per <= n ? per : n - beg);
-        MULTI_TRY(cudaSetDevice(g));
-        char *slot = (char *)cs[0]->partials.ptr + (size_t)g * PLONKISH_CUDA_XYZZ_BYTES;
-        if (cnt == 0) {
-            MULTI_TRY(cudaSetDevice(0));
-            MULTI_TRY(cudaMemsetAsync(slot, 0, PLONKISH_CUDA_XYZZ_BYTES, cs[0]->stream));
-            continue;
-        }
-        if ((rc = grow(c->scalars, cnt * PLONKISH_CUDA_SCALAR_BYTES))) { unlock_all(); return rc; }
-        MULTI_TRY(cudaMemcpyAsync(c->scalars.ptr, (const char *)scalars + beg * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
-        BasesView view;
-        if (bases_handle) {
-            view.ptr = entry.d_ptr[g];
-            view.table_c = entry.table_c[g];
-            view.stride = entry.shard_n[g];
-        } else {
-            if ((rc = grow(c->bases_tmp, cnt * PLONKISH_CUDA_AFFINE_BYTES))) { unlock_all(); return rc; }
-            MULTI_TRY(cudaMemcpyAsync(c->bases_tmp.ptr, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
-            view.ptr = c->bases_tmp.ptr;
-        }
-        xyzz *res = nullptr;
-        if ((rc = enqueue_device_msm(c, c->scalars.ptr, view, cnt, 0, c->stream, &res))) { unlock_all(); return rc; }
-        MULTI_TRY(cudaMemcpyPeerAsync(slot, 0, res, g, PLONKISH_CUDA_XYZZ_BYTES, c->stream));
-        if ((rc = mark_done(c, c->stream))) { unlock_all(); return rc; }
-        MULTI_TRY(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
-        MULTI_TRY(cudaEventRecord(done[g], c->stream));
+        auto run = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(g));
+            int r = grow(c->partials, (size_t)(n_gpus + 1) * PLONKISH_CUDA_XYZZ_BYTES);
+            if (r) return r;
+            char *send = (char *)c->partials.ptr + (size_t)n_gpus * PLONKISH_CUDA_XYZZ_BYTES;
+            const size_t beg = (size_t)g * per;
+            const size_t cnt = beg >= n ? 0 : (beg + per <= n ? per : n - beg);
+            if (cnt == 0) {  // trailing shard of a short MSM: the identity
+                if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+                CUDA_TRY(cudaMemsetAsync(send, 0, PLONKISH_CUDA_XYZZ_BYTES, c->stream));
+                return PLONKISH_CUDA_OK;
+            }
+            if ((r = grow(c->scalars, cnt * PLONKISH_CUDA_SCALAR_BYTES))) return r;
+            BasesView view;
+            if (bases_handle) {
+                view.ptr = entry.d_ptr[g];
+                view.table_c = entry.table_c[g];
+                view.stride = entry.shard_n[g];
+                view.keep = entry.keep[g];
+            } else {
+                if ((r = grow(c->bases_tmp, cnt * PLONKISH_CUDA_AFFINE_BYTES))) return r;
+                if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+                CUDA_TRY(upload(c, c->bases_tmp.ptr, (const char *)bases + beg * PLONKISH_CUDA_AFFINE_BYTES, cnt * PLONKISH_CUDA_AFFINE_BYTES, c->stream));
+                view.ptr = c->bases_tmp.ptr;
+            }
+            xyzz *res = nullptr;
+            if ((r = enqueue_host_msm(c, (const char *)scalars + beg * PLONKISH_CUDA_SCALAR_BYTES, view, cnt, &res))) return r;
+            CUDA_TRY(cudaMemcpyAsync(send, res, PLONKISH_CUDA_XYZZ_BYTES, cudaMemcpyDeviceToDevice, c->stream));
+            return PLONKISH_CUDA_OK;
+        };
+        rcs[g] = run();
+        if (rcs[g]) errs[g] = t_last_error;  // the message lives in the worker's thread-local slot
+    };
+    {
+        std::vector<std::thread> workers;
+        for (int g = 1; g < n_gpus; ++g) workers.emplace_back(shard, g);
+        shard(0);
+        for (auto &w : workers) w.join();
     }
-    MULTI_TRY(cudaSetDevice(0));
     for (int g = 0; g < n_gpus; ++g) {
-        if (done[g]) MULTI_TRY(cudaStreamWaitEvent(cs[0]->stream, done[g], 0));
+        if (rcs[g]) { t_last_error = errs[g]; return rcs[g]; }
     }
+    if (n_gpus > 1) {
+        int r = g_nccl.GroupStart();
+        for (int g = 0; r == 0 && g < n_gpus; ++g) {
+            char *recv = (char *)cs[g]->partials.ptr;
+            r = g_nccl.AllGather(recv + (size_t)n_gpus * PLONKISH_CUDA_XYZZ_BYTES, recv, PLONKISH_CUDA_XYZZ_BYTES, /* ncclChar */ 0, g_nccl.comms[g], cs[g]->stream);
+        }
+        const int r2 = g_nccl.GroupEnd();
+        if (r == 0) r = r2;
+        if (r != 0) return fail(PLONKISH_CUDA_E_COMM, "msm_multi: ncclAllGather of the partials failed: %s", g_nccl.GetErrorString(r));
+    } else {
+        CUDA_TRY(cudaSetDevice(0));
+        CUDA_TRY(cudaMemcpyAsync(cs[0]->partials.ptr, (char *)cs[0]->partials.ptr + PLONKISH_CUDA_XYZZ_BYTES, PLONKISH_CUDA_XYZZ_BYTES, cudaMemcpyDeviceToDevice, cs[0]->stream));
+    }
+    CUDA_TRY(cudaSetDevice(0));
     PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, cs[0]->stream, (const xyzz *)cs[0]->partials.ptr, (u32)n_gpus, (affine *)cs[0]->d_out, (xyzz *)nullptr);
-    MULTI_TRY(cudaGetLastError());
-    MULTI_TRY(cudaMemcpyAsync(cs[0]->h_out, cs[0]->d_out, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, cs[0]->stream));
-    MULTI_TRY(cudaStreamSynchronize(cs[0]->stream));
-    memcpy(out_affine64, cs[0]->h_out, PLONKISH_CUDA_AFFINE_BYTES);
-    for (int g = 0; g < n_gpus; ++g) {
-        if (done[g]) { cudaSetDevice(g); cudaEventDestroy(done[g]); }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(cs[0]->h_out, cs[0]->d_out, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, cs[0]->stream));
+    for (int g = n_gpus - 1; g >= 0; --g) {  // every device is idle again when the call returns
+        CUDA_TRY(cudaSetDevice(g));
+        if ((rc = mark_done(cs[g], cs[g]->stream))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(cs[g]->stream));
     }
-    unlock_all();
-#undef MULTI_TRY
+    memcpy(out_affine64, cs[0]->h_out, PLONKISH_CUDA_AFFINE_BYTES);
     timer_report(n, t0);
     return PLONKISH_CUDA_OK;
 }
@@ -1444,6 +1958,80 @@ extern "C" int plonkish_cuda_bench_inversion(int device, double out[2]) {
     return PLONKISH_CUDA_OK;
 }
 
+// ---- FP64 pipe probes: could 52-bit double-precision FMAs carry part of the field arithmetic next to the integer pipe?
+// 16 independent accumulators per thread, fma.rz.f64 each (DFMA).
+__global__ void __launch_bounds__(256) k_bench_dfma(double *out, u32 iters, u32 seed) {
+    double acc[16];
+    const double a = 1.0 + (double)(seed + threadIdx.x) * 1e-9, b = 1.0 - (double)(blockIdx.x + 1) * 1e-9;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = (double)k + a;
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[k]) : "d"(b), "d"(a));
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += acc[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// The same DFMA stream interleaved one to one with independent mad.wide.u32: do the two pipes issue side by side?
+__global__ void __launch_bounds__(256) k_bench_dfma_imad(double *out, u32 iters, u32 seed) {
+    double acc[8];
+    unsigned long long iacc[8];
+    const double a = 1.0 + (double)(seed + threadIdx.x) * 1e-9, b = 1.0 - (double)(blockIdx.x + 1) * 1e-9;
+    u32 x = seed + threadIdx.x * 2654435761u, y = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc[k] = (double)k + a; iacc[k] = (unsigned long long)(x + k) << 7; }
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(acc[k]) : "d"(b), "d"(a));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(iacc[k]) : "r"(x + (u32)k), "r"(y));
+        }
+        y += 0x9e3779b9u;
+    }
+    double s = 0;
+    unsigned long long t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += acc[k]; t ^= iacc[k]; }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s + (double)(t & 0xffff);
+}
+// out[0] = DFMA per second alone, out[1] = DFMA per second and out[2] = mad.wide.u32 per second when interleaved 1:1.
+extern "C" int plonkish_cuda_bench_fp64_pipe(int device, double out[3]) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out) return fail(PLONKISH_CUDA_E_INVALID, "bench_fp64_pipe: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const u32 iters = 2048;
+    float ms = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_dfma, dim3(blocks), dim3(threads), 0, c->stream, (double *)scratch, iters, 41u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    out[0] = (double)blocks * threads * 16.0 * iters / (ms * 1e-3);
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        PK_LAUNCH(k_bench_dfma_imad, dim3(blocks), dim3(threads), 0, c->stream, (double *)scratch, iters, 43u + rep);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    out[1] = out[2] = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
+}
+
 extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[6]) {
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bench_integer_pipe: device %d not initialised", device);
@@ -1582,16 +2170,13 @@ struct ScalarsEntry {
     int dev = 0;
     size_t n = 0;
     void *d_ptr = nullptr;
+    BlockRef keep;  // owner of d_ptr (pooled): copies of the entry keep it alive while a call or a sum-check state uses it
 };
 static std::map<uint64_t, ScalarsEntry> g_scalars;
 
 static void release_all_sumcheck();
 static void release_all_scalars() {  // caller holds g_mu
     release_all_sumcheck();
-    for (auto &kv : g_scalars) {
-        cudaSetDevice(kv.second.dev);
-        cudaFree(kv.second.d_ptr);
-    }
     g_scalars.clear();
 }
 static uint64_t publish_scalars(int dev, void *d_ptr, size_t n) {
@@ -1599,6 +2184,7 @@ static uint64_t publish_scalars(int dev, void *d_ptr, size_t n) {
     const uint64_t h = g_next_handle++;
     ScalarsEntry e;
     e.dev = dev; e.n = n; e.d_ptr = d_ptr;
+    e.keep = make_block(dev, d_ptr, true, g_ctx[dev], n * PLONKISH_CUDA_SCALAR_BYTES);
     g_scalars[h] = e;
     return h;
 }
@@ -1620,7 +2206,7 @@ extern "C" int plonkish_cuda_scalars_register(int device, const void *scalars, s
     int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
     PoolGuard d_guard{c, d};
-    CUDA_TRY(cudaMemcpyAsync(d, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(upload(c, d, scalars, n * PLONKISH_CUDA_SCALAR_BYTES, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *handle = publish_scalars(device, d_guard.release(), n);
     return PLONKISH_CUDA_OK;
@@ -1635,11 +2221,8 @@ extern "C" int plonkish_cuda_scalars_release(uint64_t handle) {
         e = it->second;
         g_scalars.erase(it);
     }
-    Ctx *c = ctx_for(e.dev);
-    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "scalars_release: device %d not initialised", e.dev);
-    std::lock_guard<std::mutex> lk(c->mu);
-    CUDA_TRY(cudaSetDevice(c->dev));
-    pool_free(c, e.d_ptr);  // ordered after everything enqueued on the context's stream
+    // `e` holds the map's reference: the buffer returns to the pool here (stream-ordered after everything enqueued on
+    // the context's stream), or when the last call / sum-check state still reading it is done
     return PLONKISH_CUDA_OK;
 }
 
@@ -1813,7 +2396,11 @@ extern "C" int plonkish_cuda_kzg_open_bn254(uint64_t scalars_handle, const uint6
     if ((rc = mark_done(c, c->stream))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(out_eval_mont32, c->h_out, PLONKISH_CUDA_SCALAR_BYTES);
-    for (size_t i = 0; i < num_vars; ++i) timer_report((size_t)1 << i, t0);
+    {
+        std::vector<size_t> sizes;
+        for (size_t i = 0; i < num_vars; ++i) sizes.push_back((size_t)1 << i);
+        timer_report_shared(sizes, t0);
+    }
     return PLONKISH_CUDA_OK;
 }
 
@@ -1825,6 +2412,7 @@ static const size_t FIXED_BATCH = (size_t)1 << 22;  // scalars per launch pair; 
 struct FixedTable {
     void *table = nullptr, *offsets = nullptr, *tmp = nullptr;  // tmp: max(table build, FIXED_BATCH) xyzz
     void release() { cudaFree(table); cudaFree(offsets); cudaFree(tmp); table = offsets = tmp = nullptr; }
+    ~FixedTable() { release(); }  // every early return gives the table back
 };
 // Caller holds c->mu.  d_base: one affine point in device memory.
 static int fixed_table_build(Ctx *c, const void *d_base, size_t max_batch, FixedTable &ft) {
@@ -1854,7 +2442,7 @@ extern "C" int plonkish_cuda_fixed_base_msm_bn254_g1(int device, const void *bas
     if ((rc = fixed_table_build(c, (char *)c->d_out + 384, batch, ft))) { ft.release(); return rc; }
     for (size_t done = 0; done < n; done += batch) {
         const size_t cnt = n - done < batch ? n - done : batch;
-        CUDA_TRY(cudaMemcpyAsync(c->scalars.ptr, (const char *)scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(upload(c, c->scalars.ptr, (const char *)scalars + done * PLONKISH_CUDA_SCALAR_BYTES, cnt * PLONKISH_CUDA_SCALAR_BYTES, c->stream));
         pk_enqueue_fixed_base(c->scalars.ptr, (u32)cnt, (const affine *)ft.table, (xyzz *)ft.tmp, (affine *)c->bases_tmp.ptr, c->stream);
         CUDA_TRY(cudaMemcpyAsync((char *)out_affine64_list + done * PLONKISH_CUDA_AFFINE_BYTES, c->bases_tmp.ptr, cnt * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -1888,9 +2476,12 @@ extern "C" int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affi
             cleanup();
             return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: out of device memory for %zu points", total);
         }
-        if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
-        if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_ss, ss, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync((char *)c->d_out + 384, g1_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+        {
+            cudaError_t e1 = c->has_last ? cudaStreamWaitEvent(c->stream, c->last_done, 0) : cudaSuccess;
+            if (e1 == cudaSuccess && num_vars) e1 = cudaMemcpyAsync(d_ss, ss, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream);
+            if (e1 == cudaSuccess) e1 = cudaMemcpyAsync((char *)c->d_out + 384, g1_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream);
+            if (e1 != cudaSuccess) { cleanup(); return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: %s", cudaGetErrorString(e1)); }
+        }
         pk_enqueue_eq_scalars(d_ss, (u32)num_vars, d_eq, (u32)c->sm_count, c->stream);
         int rc = fixed_table_build(c, (char *)c->d_out + 384, batch, ft);
         if (rc) { cleanup(); return rc; }
@@ -1918,16 +2509,16 @@ extern "C" int plonkish_cuda_kzg_setup_eqs_bn254(int device, const void *g1_affi
                 owns = true;
             }
             if (rc) {
-                for (size_t j = 0; j < k; ++j) cudaFree(entries[j].d_ptr[0]);
-                cleanup();
+                cleanup();  // the slices registered so far are freed with `entries`
                 return rc;
             }
             BasesEntry &e = entries[k];
-            e.n_shards = 1; e.dev = device; e.n = nk; e.owns = true;
-            e.d_ptr.push_back(d); e.shard_n.push_back(nk); e.table_c.push_back(tc);
+            e.n_shards = 1; e.dev = device; e.n = nk;
+            e.add_shard(device, d, true, nk, tc);
         }
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const cudaError_t sync_err = cudaStreamSynchronize(c->stream);
         cleanup();
+        if (sync_err != cudaSuccess) return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_eqs: %s", cudaGetErrorString(sync_err));
     }
     for (size_t k = 0; k <= num_vars; ++k) handles_out[k] = publish(entries[k]);
     return PLONKISH_CUDA_OK;
@@ -1954,9 +2545,12 @@ extern "C" int plonkish_cuda_kzg_setup_powers_bn254(int device, const void *g1_a
             cleanup();
             return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_powers: out of device memory for %zu points", n);
         }
-        if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
-        CUDA_TRY(cudaMemcpyAsync(d_s, s, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync((char *)c->d_out + 384, g1_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream));
+        {
+            cudaError_t e1 = c->has_last ? cudaStreamWaitEvent(c->stream, c->last_done, 0) : cudaSuccess;
+            if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(d_s, s, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream);
+            if (e1 == cudaSuccess) e1 = cudaMemcpyAsync((char *)c->d_out + 384, g1_affine64, PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyHostToDevice, c->stream);
+            if (e1 != cudaSuccess) { cleanup(); return fail(PLONKISH_CUDA_E_CUDA, "kzg_setup_powers: %s", cudaGetErrorString(e1)); }
+        }
         pk_enqueue_fr_powers(d_s, n, d_pow, c->stream);
         int rc = fixed_table_build(c, (char *)c->d_out + 384, batch, ft);
         if (rc) { cleanup(); return rc; }
@@ -1977,8 +2571,8 @@ extern "C" int plonkish_cuda_kzg_setup_powers_bn254(int device, const void *g1_a
         rc = make_resident(c, d_pts, true, n, 0, &d, &tc, &owns);
         if (rc) { cleanup(); return rc; }
         if (!owns) { d_pts = nullptr; owns = true; }  // plain slice: the entry adopts the points as they are
-        e.n_shards = 1; e.dev = device; e.n = n; e.owns = true;
-        e.d_ptr.push_back(d); e.shard_n.push_back(n); e.table_c.push_back(tc);
+        e.n_shards = 1; e.dev = device; e.n = n;
+        e.add_shard(device, d, true, n, tc);
         cleanup();
     }
     *handle = publish(e);
@@ -1994,6 +2588,7 @@ struct SumcheckState {
     u32 num_vars = 0, round = 0, num_polys = 0;
     SumcheckExpr ex;
     std::vector<const void *> cur;          // current table of every polynomial
+    std::vector<BlockRef> keep;             // the callers' resident polynomials, alive as long as the state reads them
     std::vector<void *> buf_a, buf_b;       // state-owned halves: 2^(k-1) and 2^(k-2) evaluations per polynomial
     void *block = nullptr;                  // one pooled allocation behind buf_a / buf_b / scratch
     void *partials = nullptr, *d_out = nullptr, *d_chal = nullptr, *d_final = nullptr;
@@ -2046,6 +2641,7 @@ extern "C" int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t n
         if (p == 0) st.dev = se.dev;
         if (se.dev != st.dev) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: polynomials live on different devices");
         st.cur.push_back(se.d_ptr);
+        st.keep.push_back(se.keep);
     }
     Ctx *c = ctx_for(st.dev);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_new: device %d not initialised", st.dev);
@@ -2128,6 +2724,7 @@ extern "C" int plonkish_cuda_sumcheck_fix_var(uint64_t state_handle, const void 
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(c->stream));  // the caller's challenge buffer is free again
         for (u32 p = 0; p < st.num_polys; ++p) st.cur[p] = dst[p];
+        st.keep.clear();  // the folded tables are state-owned: the callers' polynomials may go
         st.round += 1;
     }
     std::lock_guard<std::mutex> lk(g_mu);

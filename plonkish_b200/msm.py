@@ -95,6 +95,41 @@ class G1Bases:
             self.handle = 0
 
 
+def cached_bases(bases, device: int = 0) -> "G1Bases":
+    """The handle the Rust shim's variable_base_msm gets for a borrowed `&[G1Affine]` (msm.rs:84-87): looked up by
+    address in the library's cache and trusted only after its content fingerprint matches; see
+    plonkish_cuda_bases_cached.  `bases` must be a C-contiguous [n, 8] uint64 array (its address is the key).
+    The returned object does not own the handle: the cache does (evict with cache_evict)."""
+    arr = bases if isinstance(bases, np.ndarray) and bases.dtype == np.uint64 and bases.flags.c_contiguous else None
+    assert arr is not None and arr.ndim == 2 and arr.shape[1] == 8, "cached_bases needs a C-contiguous [n, 8] uint64 array"
+    handle = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_bases_cached(device, arr.ctypes.data, arr.shape[0], ctypes.byref(handle)), "plonkish_cuda_bases_cached")
+    return G1Bases._adopt(handle.value, arr.shape[0], device)
+
+
+def cache_evict(bases) -> None:
+    _lib.check(_lib.lib().plonkish_cuda_bases_cache_evict(bases.ctypes.data), "plonkish_cuda_bases_cache_evict")
+
+
+def cache_limit(max_bytes: int) -> None:
+    _lib.check(_lib.lib().plonkish_cuda_bases_cache_limit(max_bytes), "plonkish_cuda_bases_cache_limit")
+
+
+def cache_stats() -> dict:
+    out = (ctypes.c_size_t * 2)()
+    _lib.check(_lib.lib().plonkish_cuda_bases_cache_stats(out), "plonkish_cuda_bases_cache_stats")
+    return {"entries": int(out[0]), "bytes": int(out[1])}
+
+
+def timer_config(mode: int, depth: int = 0) -> None:
+    """0 off, 1 stderr, 2 stdout: the reference's `variable_base_msm-{n}` timer lines (msm.rs:92) in perf_trace format."""
+    _lib.check(_lib.load().plonkish_cuda_timer_config(mode, depth), "plonkish_cuda_timer_config")
+
+
+def staged_bytes() -> int:
+    return int(_lib.load().plonkish_cuda_staged_bytes())
+
+
 class ResidentScalars:
     """A polynomial's evaluations (n x bn256::Fr, Montgomery) kept in HBM between its commit
     and its opening — poly.evals() of pcs/multilinear/kzg.rs:255,291 without the re-upload."""
@@ -140,6 +175,19 @@ class ShardedG1Bases:
             "plonkish_cuda_bases_register_sharded",
         )
         self.handle = handle.value
+
+    @classmethod
+    def from_device(cls, shards, n: int, mode: int = 0) -> "ShardedG1Bases":
+        """shards[g]: CUDA tensor on device g holding points [g*ceil(n/G), (g+1)*ceil(n/G)) of the slice."""
+        self = cls.__new__(cls)
+        self.n, self.n_gpus = int(n), len(shards)
+        ptrs = (ctypes.c_void_p * len(shards))(*[t.data_ptr() if t is not None and t.numel() else None for t in shards])
+        handle = ctypes.c_uint64(0)
+        _lib.check(_lib.lib().plonkish_cuda_bases_register_sharded_device(len(shards), ctypes.cast(ptrs, ctypes.c_void_p), self.n, mode, ctypes.byref(handle)),
+                   "plonkish_cuda_bases_register_sharded_device")
+        self.handle = handle.value
+        self._keepalive = list(shards) if mode == 1 else None  # plain mode borrows the tensors
+        return self
 
     def release(self) -> None:
         if self.handle:
@@ -438,6 +486,12 @@ def bench_integer_pipe(device: int = 0) -> dict:
     _lib.check(_lib.lib().plonkish_cuda_bench_integer_pipe(device, out), "plonkish_cuda_bench_integer_pipe")
     return {"imad_wide_per_s": out[0], "fq_mul_per_s": out[1], "sm_max_mhz": out[2], "sm_count": int(out[3]),
             "imad32_per_s": out[4], "imad_wide_chain_per_s": out[5]}
+
+
+def bench_fp64_pipe(device: int = 0) -> dict:
+    out = (ctypes.c_double * 3)()
+    _lib.check(_lib.lib().plonkish_cuda_bench_fp64_pipe(device, out), "plonkish_cuda_bench_fp64_pipe")
+    return {"dfma_per_s": out[0], "dfma_per_s_mixed": out[1], "imad_wide_per_s_mixed": out[2]}
 
 
 def bench_madd(device: int = 0) -> dict:

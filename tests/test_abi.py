@@ -76,3 +76,35 @@ def test_shard_bounds_match_reference_chunking():
             got = [shard_bounds(n, world, r) for r in range(world)]
             assert got == want
             assert sum(e - b for b, e in got) == n
+
+
+def test_timer_lines_have_the_format_the_plotter_parses():
+    # msm.rs:92 -> util/timer.rs:19-24 -> ark_std perf_trace lines; benchmark/src/bin/plotter.rs:337-373, 504-515 parse them.
+    from plonkish_b200 import _lib
+    from plotter_parse import capture_fd2, plotter_parse
+
+    lib = _lib.load()
+    cases = [(1 << 24, 41.375), (1, 0.000731), (4096, 0.6612), (1 << 26, 1234.5)]
+    for depth in (0, 1, 3):
+        assert lib.plonkish_cuda_timer_config(1, depth) == 0
+
+        def emit():
+            for n, ms in cases:
+                lib.plonkish_cuda_timer_emit(n, ms)
+
+        _, text = capture_fd2(emit)
+        lib.plonkish_cuda_timer_config(0, 0)
+        # wrap in `depth` enclosing timers the way the prover's own start_timer calls nest (hyperplonk.rs:176-289)
+        pre = "".join("·" * (2 * i) + f"Start:   outer{i}\n" for i in range(depth))
+        post = "".join("·" * (2 * i) + f"End:     outer{i} ....1.000s\n" for i in reversed(range(depth)))
+        logs = plotter_parse(pre + text + post)
+        for _ in range(depth):
+            assert len(logs) == 1
+            logs = logs[0]["children"]
+        assert [l["name"] for l in logs] == [f"variable_base_msm-{n}" for n, _ in cases]
+        for l, (_, ms) in zip(logs, cases):
+            assert abs(l["ns"] - ms * 1e6) <= max(1.0, ms * 1e6 * 1e-3), (l, ms)
+        for line in text.splitlines():
+            if "End:" in line:
+                assert len(line.encode()) - 2 * depth >= 75  # the message is padded with dots to perf_trace's width
+    assert lib.plonkish_cuda_timer_config(3, 0) != 0
