@@ -7,16 +7,24 @@
 //! (msm.rs:90, :154).
 use halo2_curves::bn256::{Fr, G1Affine, G1};
 use halo2_curves::CurveAffine;
-use std::{collections::HashMap, ffi::CStr, mem::size_of, os::raw::{c_char, c_int, c_void}, sync::{Mutex, Once}};
+use std::{ffi::CStr, mem::size_of, os::raw::{c_char, c_int, c_void}, sync::{Once, OnceLock}};
 
 extern "C" {
     fn plonkish_cuda_init(n_devices: c_int) -> c_int;
+    fn plonkish_cuda_device_count() -> c_int;
     fn plonkish_cuda_last_error() -> *const c_char;
     fn plonkish_cuda_bases_register(device: c_int, bases: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    fn plonkish_cuda_bases_register_sharded(n_gpus: c_int, bases: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    fn plonkish_cuda_bases_cached(device: c_int, bases: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    fn plonkish_cuda_bases_cached_sharded(n_gpus: c_int, bases: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    fn plonkish_cuda_bases_cache_evict(bases: *const c_void) -> c_int;
+    fn plonkish_cuda_bases_cache_limit(max_bytes: usize) -> c_int;
     fn plonkish_cuda_msm_bn254_g1(scalars: *const c_void, bases: *const c_void, handle: u64, n: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1_multi(n_gpus: c_int, scalars: *const c_void, bases: *const c_void, handle: u64, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_gather(scalars: *const *const c_void, bases: *const *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_batch(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_many(scalars_list: *const *const c_void, handles: *const u64, ns: *const usize, count: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_timer_config(mode: c_int, depth: c_int) -> c_int;
     fn plonkish_cuda_bases_release(handle: u64) -> c_int;
     fn plonkish_cuda_bases_read(handle: u64, offset: usize, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_scalars_release(handle: u64) -> c_int;
@@ -37,10 +45,6 @@ extern "C" {
 }
 
 static INIT: Once = Once::new();
-/// (pointer, length) of a base slice -> device handle.  ProverParam slices
-/// (`eqs[k]`, pcs/multilinear/kzg.rs:74-76; `powers_of_s_g1`, pcs/univariate/kzg.rs:24-30)
-/// live as long as the ProverParam, so the address is a stable key.
-static BASES: Mutex<Option<HashMap<(usize, usize), u64>>> = Mutex::new(None);
 /// Slices shorter than this are not worth a resident copy: they are the throw-away vectors of
 /// sum_with_scalar folds (pcs.rs:175), not ProverParam slices.  Resident slices get the table of
 /// window multiples (no doubling chain: 0.5 ms instead of 1.7 ms for a small MSM).
@@ -64,12 +68,103 @@ fn init() {
         assert_eq!(&bytes[..8], &0xd35d438dc58f0d9du64.to_le_bytes());
         assert_eq!(&bytes[32..40], &0xa6ba871b8b1e1b3au64.to_le_bytes());
         check(unsafe { plonkish_cuda_init(0) }, "plonkish_cuda_init");
+        if let Some(bytes) = std::env::var("PLONKISH_CUDA_CACHE_BYTES").ok().and_then(|v| v.parse::<usize>().ok()) {
+            check(unsafe { plonkish_cuda_bases_cache_limit(bytes) }, "plonkish_cuda_bases_cache_limit");
+        }
+        // The per-call timer line stays on the Rust side (msm.rs:92 is kept by the patch); the library prints the lines
+        // of the composite entry points (batch / many / open), which replace several reference calls each.
+        if cfg!(feature = "timer") {
+            check(unsafe { plonkish_cuda_timer_config(2, timer_depth()) }, "plonkish_cuda_timer_config");
+        }
     });
+}
+
+/// Nesting depth the library's own timer lines are printed at (PLONKISH_CUDA_TIMER_DEPTH; ark_std keeps its
+/// indentation counter private): 2 inside HyperPlonk::prove's phase timers, the only place the composite
+/// entry points are called from.
+fn timer_depth() -> c_int {
+    std::env::var("PLONKISH_CUDA_TIMER_DEPTH").ok().and_then(|v| v.parse().ok()).unwrap_or(2)
+}
+
+/// GPUs a single MSM is point-sharded over (PLONKISH_CUDA_GPUS, default 1): msm.rs:101-114 with GPUs for threads.
+fn gpus() -> c_int {
+    static GPUS: OnceLock<c_int> = OnceLock::new();
+    *GPUS.get_or_init(|| {
+        let want = std::env::var("PLONKISH_CUDA_GPUS").ok().and_then(|v| v.parse::<c_int>().ok()).unwrap_or(1);
+        want.clamp(1, unsafe { plonkish_cuda_device_count() }.max(1))
+    })
+}
+/// Below this many points a sharded MSM is slower than one GPU (launch chain + gather ~0.75 ms).
+const MULTI_MIN: usize = 1 << 21;
+
+/// Handle for a borrowed base slice.  The shim cannot know whether `bases` is a ProverParam's static SRS slice or a
+/// temporary whose address the allocator will reuse (IPA's g_lo / g_hi, Hyrax rows, `trim`'s `to_vec()` of a second
+/// setup), so it never trusts an address: `plonkish_cuda_bases_cached` keys by address but validates a hit against a
+/// content fingerprint taken at registration, re-registers on mismatch, serves prefixes of a longer cached slice
+/// (`&powers_of_s_g1[..len]`, univariate/kzg.rs:28) from the one registration, and evicts least-recently-used tables
+/// beyond its byte limit.  Owners that know their lifetime use `RegisteredBases` instead.
+fn cached_handle(bases: &[G1Affine], n_gpus: c_int) -> u64 {
+    let mut h = 0u64;
+    if n_gpus > 1 {
+        check(unsafe { plonkish_cuda_bases_cached_sharded(n_gpus, bases.as_ptr() as *const c_void, bases.len(), &mut h) }, "plonkish_cuda_bases_cached_sharded");
+    } else {
+        check(unsafe { plonkish_cuda_bases_cached(0, bases.as_ptr() as *const c_void, bases.len(), &mut h) }, "plonkish_cuda_bases_cached");
+    }
+    h
+}
+
+/// Call from the Drop of whatever owns a slice that went through `variable_base_msm` (e.g. a ProverParam wrapper):
+/// frees its resident table at once instead of waiting for the LRU bound.
+pub fn forget_bases(bases: &[G1Affine]) {
+    unsafe { plonkish_cuda_bases_cache_evict(bases.as_ptr() as *const c_void) };
+}
+
+/// An explicitly registered base slice: the handle lives exactly as long as this value (a field of a ProverParam
+/// wrapper next to `eqs[k]` / `powers_of_s_g1`).  No address is ever used as a key.
+pub struct RegisteredBases {
+    handle: u64,
+    len: usize,
+    sharded: c_int,
+}
+impl RegisteredBases {
+    pub fn new(bases: &[G1Affine]) -> Self {
+        init();
+        let mut handle = 0u64;
+        let g = if bases.len() >= MULTI_MIN { gpus() } else { 1 };
+        if g > 1 {
+            check(unsafe { plonkish_cuda_bases_register_sharded(g, bases.as_ptr() as *const c_void, bases.len(), &mut handle) }, "plonkish_cuda_bases_register_sharded");
+        } else {
+            check(unsafe { plonkish_cuda_bases_register(0, bases.as_ptr() as *const c_void, bases.len(), &mut handle) }, "plonkish_cuda_bases_register");
+        }
+        Self { handle, len: bases.len(), sharded: g }
+    }
+    /// `variable_base_msm(scalars, &bases[..scalars.len()])` (kzg.rs:255, univariate/kzg.rs:28).
+    pub fn msm(&self, scalars: &[Fr]) -> G1Affine {
+        assert!(scalars.len() <= self.len); // msm.rs:90
+        let mut out = [0u8; 64];
+        if self.sharded > 1 {
+            assert_eq!(scalars.len(), self.len, "a sharded slice serves its full length only");
+            check(unsafe { plonkish_cuda_msm_bn254_g1_multi(self.sharded, scalars.as_ptr() as *const c_void, std::ptr::null(), self.handle, scalars.len(), out.as_mut_ptr() as *mut c_void) },
+                  "plonkish_cuda_msm_bn254_g1_multi");
+        } else {
+            check(unsafe { plonkish_cuda_msm_bn254_g1(scalars.as_ptr() as *const c_void, std::ptr::null(), self.handle, scalars.len(), out.as_mut_ptr() as *mut c_void) },
+                  "plonkish_cuda_msm_bn254_g1");
+        }
+        unsafe { std::mem::transmute(out) }
+    }
+}
+impl Drop for RegisteredBases {
+    fn drop(&mut self) {
+        // reference counted inside the library: a call still in flight on another rayon worker finishes first
+        unsafe { plonkish_cuda_bases_release(self.handle) };
+    }
 }
 
 /// `variable_base_msm` for BN254 G1 (msm.rs:84-115).  Accepts the same iterators of
 /// references; contiguous inputs (the commit paths, pcs/multilinear/kzg.rs:255,271,292;
-/// pcs/univariate/kzg.rs:28) go down as two slices, anything else is gathered.
+/// pcs/univariate/kzg.rs:28) go down as two slices, anything else is gathered.  With
+/// PLONKISH_CUDA_GPUS=G > 1, contiguous MSMs of 2^21 points and more are point-sharded over G GPUs
+/// (one host thread per device, NCCL gather of the partials — plonkish_cuda_msm_bn254_g1_multi).
 pub fn variable_base_msm_bn254<'a, 'b>(
     scalars: impl IntoIterator<Item = &'a Fr>,
     bases: impl IntoIterator<Item = &'b G1Affine>,
@@ -91,22 +186,22 @@ pub fn variable_base_msm_bn254<'a, 'b>(
     let b_contig = contiguous(b0, bases[n - 1] as *const G1Affine as usize, 64)
         && bases.windows(2).all(|w| (w[1] as *const G1Affine as usize) == (w[0] as *const G1Affine as usize) + 64);
     if s_contig && b_contig {
-        let handle = if n >= REGISTER_MIN {
-            let mut guard = BASES.lock().unwrap();
-            let map = guard.get_or_insert_with(HashMap::new);
-            *map.entry((b0, n)).or_insert_with(|| {
-                let mut h = 0u64;
-                check(unsafe { plonkish_cuda_bases_register(0, b0 as *const c_void, n, &mut h) }, "plonkish_cuda_bases_register");
-                h
-            })
-        } else {
-            0
-        };
+        // SAFETY: n consecutive G1Affine starting at bases[0], borrowed for the duration of this call.
+        let base_slice = unsafe { std::slice::from_raw_parts(b0 as *const G1Affine, n) };
+        let g = if n >= MULTI_MIN { gpus() } else { 1 };
+        let handle = if n >= REGISTER_MIN { cached_handle(base_slice, g) } else { 0 };
         let bases_ptr = if handle == 0 { b0 as *const c_void } else { std::ptr::null() };
-        check(
-            unsafe { plonkish_cuda_msm_bn254_g1(s0 as *const c_void, bases_ptr, handle, n, out.as_mut_ptr() as *mut c_void) },
-            "plonkish_cuda_msm_bn254_g1",
-        );
+        if g > 1 {
+            check(
+                unsafe { plonkish_cuda_msm_bn254_g1_multi(g, s0 as *const c_void, bases_ptr, handle, n, out.as_mut_ptr() as *mut c_void) },
+                "plonkish_cuda_msm_bn254_g1_multi",
+            );
+        } else {
+            check(
+                unsafe { plonkish_cuda_msm_bn254_g1(s0 as *const c_void, bases_ptr, handle, n, out.as_mut_ptr() as *mut c_void) },
+                "plonkish_cuda_msm_bn254_g1",
+            );
+        }
     } else {
         let sp: Vec<*const c_void> = scalars.iter().map(|s| *s as *const Fr as *const c_void).collect();
         let bp: Vec<*const c_void> = bases.iter().map(|b| *b as *const G1Affine as *const c_void).collect();
@@ -123,7 +218,8 @@ pub fn variable_base_msm_bn254<'a, 'b>(
 
 /// The loop of `MultilinearKzg::batch_commit` (pcs/multilinear/kzg.rs:259-274) in one call: every
 /// polynomial has `n` evaluations and is committed against the same `bases` slice; the upload of
-/// polynomial j+1 overlaps the MSM of polynomial j.  Returns the commitments in order.
+/// polynomial j+1 overlaps the MSM of polynomial j.  Returns the commitments in order.  With the `timer`
+/// feature the library prints one `variable_base_msm-{n}` Start/End pair per polynomial (msm.rs:92).
 pub fn batch_commit_bn254(polys: &[&[Fr]], bases: &[G1Affine]) -> Vec<G1Affine> {
     init();
     if polys.is_empty() {
@@ -131,15 +227,7 @@ pub fn batch_commit_bn254(polys: &[&[Fr]], bases: &[G1Affine]) -> Vec<G1Affine> 
     }
     let n = polys[0].len();
     assert!(polys.iter().all(|p| p.len() == n) && n <= bases.len());
-    let handle = {
-        let mut guard = BASES.lock().unwrap();
-        let map = guard.get_or_insert_with(HashMap::new);
-        *map.entry((bases.as_ptr() as usize, bases.len())).or_insert_with(|| {
-            let mut h = 0u64;
-            check(unsafe { plonkish_cuda_bases_register(0, bases.as_ptr() as *const c_void, bases.len(), &mut h) }, "plonkish_cuda_bases_register");
-            h
-        })
-    };
+    let handle = cached_handle(bases, 1);
     let ptrs: Vec<*const c_void> = polys.iter().map(|p| p.as_ptr() as *const c_void).collect();
     let mut out = vec![[0u8; 64]; polys.len()];
     check(
@@ -158,13 +246,7 @@ pub fn commit_quotients_bn254(quotients: &[Vec<Fr>], eqs: &[Vec<G1Affine>]) -> V
     assert!(quotients.len() <= eqs.len());
     let handles: Vec<u64> = quotients.iter().zip(eqs).map(|(q, e)| {
         assert!(q.len() <= e.len());
-        let mut guard = BASES.lock().unwrap();
-        let map = guard.get_or_insert_with(HashMap::new);
-        *map.entry((e.as_ptr() as usize, e.len())).or_insert_with(|| {
-            let mut h = 0u64;
-            check(unsafe { plonkish_cuda_bases_register(0, e.as_ptr() as *const c_void, e.len(), &mut h) }, "plonkish_cuda_bases_register");
-            h
-        })
+        cached_handle(e, 1)
     }).collect();
     let ptrs: Vec<*const c_void> = quotients.iter().map(|q| q.as_ptr() as *const c_void).collect();
     let ns: Vec<usize> = quotients.iter().map(|q| q.len()).collect();
@@ -252,8 +334,8 @@ impl Drop for ResidentEqs {
 }
 
 /// The G1 half of `UnivariateKzg::setup` (pcs/univariate/kzg.rs:175-195): `powers_of_s_g1`, built on the GPU and read back
-/// for `UnivariateKzgParam` (the slice stays registered for `commit_coeffs` under the usual (pointer, length) key once the
-/// returned vector is owned by the ProverParam).
+/// for `UnivariateKzgParam` (`commit_coeffs` on the returned vector goes through the content-validated cache like any
+/// other borrowed slice).
 pub fn univariate_powers_of_s_g1(g1: &G1Affine, s: &Fr, poly_size: usize) -> Vec<G1Affine> {
     init();
     let mut handle = 0u64;

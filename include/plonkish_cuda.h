@@ -80,6 +80,8 @@ int plonkish_cuda_bases_release(uint64_t handle);
  * pcs/univariate/kzg.rs:28).  Least-recently-used entries are released once the cache holds
  * more than the byte limit (default: half of the device's memory). */
 int plonkish_cuda_bases_cached(int device, const void *bases_affine64, size_t n, uint64_t *handle);
+/* The same for plonkish_cuda_msm_bn254_g1_multi: the slice is sharded over devices 0..n_gpus-1 (exact length only). */
+int plonkish_cuda_bases_cached_sharded(int n_gpus, const void *bases_affine64, size_t n, uint64_t *handle);
 /* Forget (and release) the entry cached for this address: the Drop hook of the slice's owner. */
 int plonkish_cuda_bases_cache_evict(const void *bases_affine64);
 /* Bytes of device memory the cache may hold (0 = default); evicts down to it at once. */

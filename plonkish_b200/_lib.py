@@ -23,6 +23,7 @@ EXPORTS = (
     "plonkish_cuda_bases_release",
     "plonkish_cuda_bases_register_device",
     "plonkish_cuda_bases_cached",
+    "plonkish_cuda_bases_cached_sharded",
     "plonkish_cuda_bases_cache_evict",
     "plonkish_cuda_bases_cache_limit",
     "plonkish_cuda_bases_cache_stats",
@@ -104,6 +105,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_bases_release.argtypes = [u64]
     lib.plonkish_cuda_bases_register_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
     lib.plonkish_cuda_bases_cached.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_bases_cached_sharded.argtypes = [ci, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_bases_cache_evict.argtypes = [vp]
     lib.plonkish_cuda_bases_cache_limit.argtypes = [sz]
     lib.plonkish_cuda_bases_cache_stats.argtypes = [ctypes.POINTER(sz)]

@@ -156,7 +156,7 @@ static uint64_t g_next_handle = 1;
 struct CachedBases {
     uint64_t handle = 0;
     size_t n = 0, bytes = 0;
-    int dev = 0;
+    int dev = 0, n_gpus = 1;  // n_gpus > 1: sharded over devices 0..n_gpus-1 (dev unused)
     unsigned long long tick = 0;
     std::vector<std::pair<size_t, uint64_t>> samples;  // (position, FNV-1a of the 64-byte point)
 };
@@ -641,14 +641,15 @@ static void cache_drop_locked(std::map<uintptr_t, CachedBases>::iterator it) {  
     plonkish_cuda_bases_release(h);
 }
 
-extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64, size_t n, uint64_t *handle) {
-    if (!bases_affine64 || !handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "bases_cached: null argument or n == 0");
+static int bases_cached_impl(int device, int n_gpus, const void *bases_affine64, size_t n, uint64_t *handle) {
+    if (!bases_affine64 || !handle || n == 0 || n_gpus < 1) return fail(PLONKISH_CUDA_E_INVALID, "bases_cached: null argument or n == 0");
     const unsigned char *src = (const unsigned char *)bases_affine64;
     std::lock_guard<std::mutex> lk(g_cache_mu);
     auto it = g_bases_cache.find((uintptr_t)src);
     if (it != g_bases_cache.end()) {
         CachedBases &e = it->second;
-        bool ok = e.dev == device && e.n >= n;
+        // a sharded entry serves exactly its own length (the shard boundaries depend on it)
+        bool ok = e.n_gpus == n_gpus && (n_gpus > 1 ? e.n == n : (e.dev == device && e.n >= n));
         for (size_t k = 0; ok && k < e.samples.size(); ++k) {
             if (e.samples[k].first >= n) continue;  // beyond the caller's slice: not ours to read
             ok = fnv1a64(src + e.samples[k].first * PLONKISH_CUDA_AFFINE_BYTES, PLONKISH_CUDA_AFFINE_BYTES) == e.samples[k].second;
@@ -662,6 +663,7 @@ extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64
         }
         cache_drop_locked(it);  // stale address, another device, or a longer slice than the one registered
     }
+    if (n_gpus > 1) device = 0;
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_cached: device %d not initialised (call plonkish_cuda_init)", device);
     size_t limit = g_cache_limit;
@@ -670,7 +672,9 @@ extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64
         cudaSetDevice(device);
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) limit = total_b / 2;
     }
-    const size_t estimate = n * PLONKISH_CUDA_AFFINE_BYTES * pk_windows_for(pk_table_window_bits((u32)(n > 0xffffffffull ? 0xffffffffull : n)));
+    // (a sharded slice holds 1/G of this on every device; the limit is per device)
+    const size_t per_dev = (n + n_gpus - 1) / n_gpus;
+    const size_t estimate = per_dev * PLONKISH_CUDA_AFFINE_BYTES * pk_windows_for(pk_table_window_bits((u32)(per_dev > 0xffffffffull ? 0xffffffffull : per_dev)));
     for (;;) {  // make room: least recently used first
         size_t total = 0;
         auto lru = g_bases_cache.end();
@@ -682,12 +686,13 @@ extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64
         cache_drop_locked(lru);
     }
     CachedBases e;
-    int rc = plonkish_cuda_bases_register(device, bases_affine64, n, &e.handle);
+    int rc = n_gpus > 1 ? plonkish_cuda_bases_register_sharded(n_gpus, bases_affine64, n, &e.handle)
+                        : plonkish_cuda_bases_register(device, bases_affine64, n, &e.handle);
     if (rc) return rc;
-    e.n = n; e.dev = device; e.tick = ++g_cache_tick;
+    e.n = n; e.dev = device; e.n_gpus = n_gpus; e.tick = ++g_cache_tick;
     {
         std::lock_guard<std::mutex> lk2(g_mu);
-        e.bytes = g_bases[e.handle].device_bytes();
+        e.bytes = g_bases[e.handle].device_bytes() / (size_t)n_gpus;
     }
     std::vector<size_t> pos;
     cache_sample_positions(n, pos);
@@ -695,6 +700,15 @@ extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64
     g_bases_cache[(uintptr_t)src] = e;
     *handle = e.handle;
     return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_bases_cached(int device, const void *bases_affine64, size_t n, uint64_t *handle) {
+    return bases_cached_impl(device, 1, bases_affine64, n, handle);
+}
+// The same for the multi-GPU entry: the slice is sharded over devices 0..n_gpus-1 (bases_register_sharded).
+extern "C" int plonkish_cuda_bases_cached_sharded(int n_gpus, const void *bases_affine64, size_t n, uint64_t *handle) {
+    if (n_gpus > plonkish_cuda_device_count()) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bases_cached_sharded: %d GPUs requested, %d initialised", n_gpus, plonkish_cuda_device_count());
+    return bases_cached_impl(0, n_gpus, bases_affine64, n, handle);
 }
 
 // Drop hook for the owner of a cached slice (ProverParam's Drop in the shim): forget and free it now.

@@ -230,11 +230,15 @@ def test_release_while_another_thread_is_using_the_handle(pk, oracle):
         t.start()
         time.sleep(0.004)
         handle = reg.handle
-        reg.release()
+        # (through the C ABI directly: the worker keeps presenting the same handle, as a Rust caller holding a copy would)
+        from plonkish_b200 import _lib
+
+        _lib.check(_lib.lib().plonkish_cuda_bases_release(handle), "plonkish_cuda_bases_release")
         # memory pressure on the freed table: a new registration may land on the same addresses
         other = pk.G1Bases(pk.synth_bases_device(n, 9, 2), mode=pk.G1Bases.TABLE)
         t.join()
         other.release()
+        reg.handle = 0
         for p in out.get("points", []):
             assert p.tobytes() == want.tobytes()
         if "error" in out:
