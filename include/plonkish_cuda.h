@@ -297,6 +297,10 @@ void plonkish_cuda_timer_emit(size_t n, double ms);
 /* FP64-pipe probe: out[0] = independent fma.rz.f64 per second; out[1] = DFMA per second and out[2] =
  * mad.wide.u32 per second when the two are interleaved 1:1 in one instruction stream. */
 int plonkish_cuda_bench_fp64_pipe(int device, double out[3]);
+/* Register-resident mixed-addition streams: out[0] = additions per second of the FP64-pipe formulas (dpfq.cuh) alone with
+ * dp_blocks_per_sm blocks of 128 threads per SM, out[1] = of the integer-pipe formulas alone with int_blocks_per_sm blocks
+ * per SM, out[2] / out[3] = of the same two kernels running at the same time on two streams, out[4] = wall ms of that run. */
+int plonkish_cuda_bench_dp_madd(int device, int dp_blocks_per_sm, int int_blocks_per_sm, double out[5]);
 
 /* Integer-pipe microbenchmarks on `device` (CUDA-event timed):
  *   out[0] = independent mad.wide.u32 (IMAD.WIDE.U32) per second, all SMs busy
@@ -335,9 +339,10 @@ int plonkish_cuda_synth_bases_device(int device, void *d_out_affine64, size_t fi
  * (halo2_curves to_repr, msm.rs:153), 4 Fq inverse (Fermat ladder), 5 Fr mul, 6 Fq negate,
  * 7 Fq inverse (safegcd, the one the library uses), 8 Fq fused a[i]*b[i] + b[i]*a[(i+1)%n] with one
  * reduction (the y-coordinate form of the point formulas), 9 the same shape in Fr: a[i]^2 + b[i]*b[(i+1)%n],
- * 10 Fq square (symmetric partial products taken once), 11 Fr square.
+ * 10 Fq square (symmetric partial products taken once), 11 Fr square, 12 Fq product and 13 Fq square on the FP64 pipe
+ * (dpfq.cuh: six 48-bit limbs in doubles, round-toward-zero DFMAs), 14 words -> double limbs -> words.
  * point ops (128-byte X,Y,ZZ,ZZZ slots; b's first 64 bytes are an affine point for op 0):
- * 0 mixed add, 1 full add, 2 double, 3 to_affine (result in the first 64 bytes). */
+ * 0 mixed add, 1 full add, 2 double, 3 to_affine (result in the first 64 bytes), 4 mixed add through the FP64-pipe formulas. */
 int plonkish_cuda_debug_field_op(int device, int op, const void *a32, const void *b32, void *out32, size_t n);
 int plonkish_cuda_debug_point_op(int device, int op, const void *a128, const void *b128, void *out128, size_t n);
 

@@ -29,6 +29,7 @@ from .msm import (  # noqa: F401
     bench_integer_pipe,
     bench_madd,
     bench_fp64_pipe,
+    bench_dp_madd,
     cached_bases,
     cache_evict,
     cache_limit,

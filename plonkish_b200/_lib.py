@@ -32,6 +32,7 @@ EXPORTS = (
     "plonkish_cuda_bases_register_sharded_device",
     "plonkish_cuda_staged_bytes",
     "plonkish_cuda_bench_fp64_pipe",
+    "plonkish_cuda_bench_dp_madd",
     "plonkish_cuda_msm_bn254_g1",
     "plonkish_cuda_msm_bn254_g1_batch",
     "plonkish_cuda_msm_bn254_g1_many",
@@ -116,6 +117,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_staged_bytes.argtypes = []
     lib.plonkish_cuda_staged_bytes.restype = u64
     lib.plonkish_cuda_bench_fp64_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.plonkish_cuda_bench_dp_madd.argtypes = [ci, ci, ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_many.argtypes = [vp, vp, vp, sz, vp]

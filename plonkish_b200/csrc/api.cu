@@ -34,6 +34,7 @@ static std::atomic<unsigned long long> g_launches{0};
 #include "msm_kernels.cuh"
 #include "poly_kernels.cuh"
 #include "sumcheck_kernels.cuh"
+#include "dpfq.cuh"
 
 using namespace pk;
 
@@ -2046,6 +2047,86 @@ extern "C" int plonkish_cuda_bench_fp64_pipe(int device, double out[3]) {
     return PLONKISH_CUDA_OK;
 }
 
+// ---- FP64-pipe mixed additions (dpfq.cuh): register-resident stream, alone and next to the integer-pipe stream
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bench_dp_madd(uint4 *out, u32 iters, u32 seed) {
+    fe x = fq_one(), y = fq_dbl(fq_one());
+    x.l[0] ^= seed + threadIdx.x; y.l[1] ^= blockIdx.x + 977u * threadIdx.x;
+    x.l[7] &= 0x0fffffffu; y.l[7] &= 0x0fffffffu;
+    dxyzz a = dxyzz_identity();
+    for (u32 it = 0; it < iters; ++it) {
+        dxyzz_madd(a, x, y);
+        x.l[0] += 2; y.l[0] += 6;
+    }
+    const xyzz w = dxyzz_to_words(a);
+    store_fe(out + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x), fq_add(w.x, fq_add(w.zz, fq_add(w.y, w.zzz))));
+}
+// out[0] = FP64-pipe mixed additions per second alone (dp_blocks_per_sm blocks of 128 threads per SM), out[1] = integer-pipe
+// mixed additions per second alone (int_blocks_per_sm blocks per SM), out[2] / out[3] = the same two when both kernels run
+// at the same time on two streams (each sized to leave room for the other), out[4] = wall ms of the concurrent run.
+extern "C" int plonkish_cuda_bench_dp_madd(int device, int dp_blocks_per_sm, int int_blocks_per_sm, double out[5]) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out || dp_blocks_per_sm < 1 || dp_blocks_per_sm > 4 || int_blocks_per_sm < 1 || int_blocks_per_sm > 4) return fail(PLONKISH_CUDA_E_INVALID, "bench_dp_madd: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned dp_blocks = (unsigned)c->sm_count * dp_blocks_per_sm, int_blocks = (unsigned)c->sm_count * int_blocks_per_sm;
+    void *s1 = nullptr, *s2 = nullptr;
+    CUDA_TRY(cudaMalloc(&s1, (size_t)dp_blocks * 128 * 32));
+    CUDA_TRY(cudaMalloc(&s2, (size_t)int_blocks * 128 * 32));
+    cudaEvent_t e[6];
+    for (auto &ev : e) CUDA_TRY(cudaEventCreate(&ev));
+    cudaStream_t sa = c->stream, sb = c->lanes[0].stream;
+    const u32 it_dp = 96, it_int = 192;
+    auto launch_dp = [&](cudaStream_t st, u32 seed) {
+        if (dp_blocks_per_sm >= 2) PK_LAUNCH((k_bench_dp_madd<2>), dim3(dp_blocks), dim3(128), 0, st, (uint4 *)s1, it_dp, seed);
+        else PK_LAUNCH((k_bench_dp_madd<1>), dim3(dp_blocks), dim3(128), 0, st, (uint4 *)s1, it_dp, seed);
+    };
+    auto launch_int = [&](cudaStream_t st, u32 seed) { PK_LAUNCH((k_bench_madd<0, 4>), dim3(int_blocks), dim3(128), 0, st, (uint4 *)s2, it_int, seed); };
+    float ms = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e[0], sa));
+        launch_dp(sa, 3u + rep);
+        CUDA_TRY(cudaEventRecord(e[1], sa));
+        CUDA_TRY(cudaEventSynchronize(e[1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e[0], e[1]));
+    }
+    out[0] = (double)dp_blocks * 128 * it_dp / (ms * 1e-3);
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e[0], sa));
+        launch_int(sa, 5u + rep);
+        CUDA_TRY(cudaEventRecord(e[1], sa));
+        CUDA_TRY(cudaEventSynchronize(e[1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms, e[0], e[1]));
+    }
+    out[1] = (double)int_blocks * 128 * it_int / (ms * 1e-3);
+    float ms_dp = 0, ms_int = 0, ms_all = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaEventRecord(e[0], sa));
+        CUDA_TRY(cudaStreamWaitEvent(sb, e[0], 0));
+        CUDA_TRY(cudaEventRecord(e[2], sb));
+        launch_int(sb, 9u + rep);
+        CUDA_TRY(cudaEventRecord(e[3], sb));
+        CUDA_TRY(cudaEventRecord(e[4], sa));
+        launch_dp(sa, 7u + rep);
+        CUDA_TRY(cudaEventRecord(e[1], sa));
+        CUDA_TRY(cudaStreamWaitEvent(sa, e[3], 0));
+        CUDA_TRY(cudaEventRecord(e[5], sa));
+        CUDA_TRY(cudaEventSynchronize(e[5]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_dp, e[4], e[1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_int, e[2], e[3]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_all, e[0], e[5]));
+    }
+    out[2] = (double)dp_blocks * 128 * it_dp / (ms_dp * 1e-3);
+    out[3] = (double)int_blocks * 128 * it_int / (ms_int * 1e-3);
+    out[4] = ms_all;
+    CUDA_TRY(cudaGetLastError());
+    for (auto &ev : e) cudaEventDestroy(ev);
+    CUDA_TRY(cudaFree(s1));
+    CUDA_TRY(cudaFree(s2));
+    return PLONKISH_CUDA_OK;
+}
+
 extern "C" int plonkish_cuda_bench_integer_pipe(int device, double out[6]) {
     Ctx *c = ctx_for(device);
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "bench_integer_pipe: device %d not initialised", device);
@@ -2121,6 +2202,9 @@ __global__ void k_debug_field(int op, const fe *a, const fe *b, fe *out, u32 n) 
         case 9: r = mont_mul_sum<FrMod>(a[i], a[i], b[i], b[(i + 1) % n]); break;  // Fr: a^2 + b*b'
         case 10: r = fq_sqr(a[i]); break;                                          // symmetric squaring
         case 11: r = mont_sqr<FrMod>(a[i]); break;
+        case 12: r = dp_to_mont256(dp_mul(dp_from_mont256(a[i]), dp_from_mont256(b[i]))); break;  // FP64-pipe product, memory form in and out
+        case 13: r = dp_to_mont256(dp_sqr(dp_from_mont256(a[i]))); break;
+        case 14: r = dp_to_words(dp_from_words(a[i])); break;                                   // limb conversions only
         default: r = fq_neg(a[i]); break;
     }
     out[i] = r;
@@ -2135,6 +2219,12 @@ __global__ void k_debug_point(int op, const xyzz *a, const xyzz *b, xyzz *out, u
         case 0: xyzz_madd(r, b[i].x, b[i].y); break;
         case 1: r = xyzz_add(a[i], b[i]); break;
         case 2: r = xyzz_double(a[i]); break;
+        case 4: {  // mixed addition through the FP64-pipe formulas, converted in and out
+            dxyzz d = dxyzz_from_words(a[i]);
+            dxyzz_madd(d, b[i].x, b[i].y);
+            r = dxyzz_to_words(d);
+            break;
+        }
         default: {
             const affine q = xyzz_to_affine(a[i]);
             r.x = q.x; r.y = q.y; r.zz = fe_zero(); r.zzz = fe_zero();

@@ -494,6 +494,13 @@ def bench_fp64_pipe(device: int = 0) -> dict:
     return {"dfma_per_s": out[0], "dfma_per_s_mixed": out[1], "imad_wide_per_s_mixed": out[2]}
 
 
+def bench_dp_madd(dp_blocks_per_sm: int = 1, int_blocks_per_sm: int = 2, device: int = 0) -> dict:
+    out = (ctypes.c_double * 5)()
+    _lib.check(_lib.lib().plonkish_cuda_bench_dp_madd(device, dp_blocks_per_sm, int_blocks_per_sm, out), "plonkish_cuda_bench_dp_madd")
+    return {"dp_madd_per_s_alone": out[0], "int_madd_per_s_alone": out[1], "dp_madd_per_s_together": out[2], "int_madd_per_s_together": out[3],
+            "together_ms": out[4]}
+
+
 def bench_madd(device: int = 0) -> dict:
     """Field products per second of register-resident mixed-addition streams (see the header)."""
     out = (ctypes.c_double * 5)()

@@ -7,6 +7,7 @@
 #include "../../plonkish_b200/csrc/msm_kernels.cuh"
 #include "../../plonkish_b200/csrc/poly_kernels.cuh"
 #include "../../plonkish_b200/csrc/sumcheck_kernels.cuh"
+#include "../../plonkish_b200/csrc/dpfq.cuh"
 
 #include <stdlib.h>
 
@@ -15,6 +16,52 @@
 using namespace pk;
 
 extern "C" {
+
+// FP64-pipe arithmetic (dpfq.cuh): fma() under FE_TOWARDZERO stands for __fma_rz.
+// op 0: out = a * b / 2^288 (raw limbs), 1: a^2 / 2^288, 2..4: a - b + {2, 4, 8} p, 5: a + b.  Limbs are 6 x u64 < 2^48.
+void emul_dp_raw(int op, const uint64_t *a6, const uint64_t *b6, uint64_t *o6) {
+    DpRoundGuard guard;
+    dfe a, b, r;
+    for (int i = 0; i < 6; ++i) { a.l[i] = (double)a6[i]; b.l[i] = (double)b6[i]; }
+    switch (op) {
+        case 0: r = dp_mul(a, b); break;
+        case 1: r = dp_sqr(a); break;
+        case 2: r = dp_sub_fe<2>(a, b); break;
+        case 3: r = dp_sub_fe<4>(a, b); break;
+        case 4: r = dp_sub_fe<8>(a, b); break;
+        default: r = dp_add_fe(a, b); break;
+    }
+    for (int i = 0; i < 6; ++i) o6[i] = (r.l[i] >= 0 && r.l[i] == (double)(uint64_t)r.l[i]) ? (uint64_t)r.l[i] : ~0ull;
+}
+// memory form in, memory form out: must equal fq_mul bit for bit.
+void emul_dp_mul_words(const u32 *a, const u32 *b, u32 *o) {
+    DpRoundGuard guard;
+    fe x, y;
+    memcpy(&x, a, 32); memcpy(&y, b, 32);
+    fe r = dp_to_mont256(dp_mul(dp_from_mont256(x), dp_from_mont256(y)));
+    memcpy(o, &r, 32);
+}
+void emul_dp_words_roundtrip(const u32 *a, u32 *o) {
+    DpRoundGuard guard;
+    fe x;
+    memcpy(&x, a, 32);
+    fe r = dp_to_words(dp_from_words(x));
+    memcpy(o, &r, 32);
+}
+// count mixed additions of pts (affine, memory form) into acc through the FP64-pipe formulas; acc in / out as XYZZ words.
+void emul_dxyzz_madd(u32 *acc128, const u32 *pts64, u32 count) {
+    DpRoundGuard guard;
+    xyzz a;
+    memcpy(&a, acc128, 128);
+    dxyzz d = dxyzz_from_words(a);
+    for (u32 k = 0; k < count; ++k) {
+        affine p;
+        memcpy(&p, pts64 + 16 * k, 64);
+        dxyzz_madd(d, p.x, p.y);
+    }
+    a = dxyzz_to_words(d);
+    memcpy(acc128, &a, 128);
+}
 
 // Field / point probes (the portable restatements of the carry-chain blocks).
 void emul_fq_mul(const u32 *a, const u32 *b, u32 *o) {
