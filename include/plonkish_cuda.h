@@ -155,6 +155,11 @@ int plonkish_cuda_msm_bn254_g1_batch_keep(const void *const *scalars_mont32_list
  * resident polynomials: the g_prime merge of pcs/multilinear.rs:203-213. */
 int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const void *coeffs_mont32, size_t count, size_t n,
                                         uint64_t *out_handle);
+/* UnivariatePolynomial::div_rem by (X - z) on resident coefficients (poly/univariate.rs:144-168): the quotient of
+ * UnivariateKzg::open (pcs/univariate/kzg.rs:281-282) and, one point after another, of the vanishing polynomials of
+ * batch_open (:327).  The quotient is a new resident vector of the same length (top coefficient zero; release with
+ * scalars_release), out_rem_mont32 the remainder, i.e. the polynomial's value at z. */
+int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *z_mont32, uint64_t *out_quotient_handle, void *out_rem_mont32);
 /* MultilinearKzg::open on a resident polynomial of 2^num_vars evaluations
  * (pcs/multilinear/kzg.rs:276-302): `quotients` (pcs/multilinear.rs:72-107) runs in HBM and
  * the num_vars quotient MSMs (kzg.rs:291-293) read their scalars from there.  eq_handles[i] =
@@ -297,6 +302,9 @@ void plonkish_cuda_timer_emit(size_t n, double ms);
 /* FP64-pipe probe: out[0] = independent fma.rz.f64 per second; out[1] = DFMA per second and out[2] =
  * mad.wide.u32 per second when the two are interleaved 1:1 in one instruction stream. */
 int plonkish_cuda_bench_fp64_pipe(int device, double out[3]);
+/* Issue probe: out[R] = independent mad.wide.u32 per second when R independent 32-bit adds (ALU pipe) are issued next to
+ * every multiply, R = 0..3: flat = the multiplier pipe is the bound, falling = instruction issue is. */
+int plonkish_cuda_bench_issue_mix(int device, double out[4]);
 /* Register-resident mixed-addition streams: out[0] = additions per second of the FP64-pipe formulas (dpfq.cuh) alone with
  * dp_blocks_per_sm blocks of 128 threads per SM, out[1] = of the integer-pipe formulas alone with int_blocks_per_sm blocks
  * per SM, out[2] / out[3] = of the same two kernels running at the same time on two streams, out[4] = wall ms of that run. */

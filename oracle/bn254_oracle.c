@@ -874,3 +874,22 @@ void oracle_fe_from_canonical_n(int which, const uint64_t *in, size_t n, uint64_
 void oracle_fe_to_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out) {
     for (size_t i = 0; i < n; ++i) oracle_fe_to_canonical(which, (const ofe_t *)(in + 4 * i), out + 4 * i);
 }
+
+/* UnivariatePolynomial::div_rem (poly/univariate.rs:144-168) for the divisor (X - z) of UnivariateKzg::open
+ * (pcs/univariate/kzg.rs:281-282): the reference's long division, specialised to divisor coefficients [-z, 1]:
+ * every step takes the leading remainder coefficient as the next quotient coefficient and subtracts
+ * quotient_coeff * divisor shifted into place.  q receives n - 1 coefficients, rem the remainder (the value at z). */
+void oracle_fr_div_linear(const ofe_t *coeffs, size_t n, const ofe_t *z, ofe_t *q, ofe_t *rem) {
+    if (n == 0) { memset(rem, 0, sizeof(*rem)); return; }
+    ofe_t *r = (ofe_t *)malloc(sizeof(ofe_t) * n);
+    memcpy(r, coeffs, sizeof(ofe_t) * n);
+    for (size_t degree = n - 1; degree-- > 0;) {   /* remainder.degree() - 1 = degree */
+        const ofe_t qc = r[degree + 1];           /* divisor_leading_inv = 1 */
+        ofe_t t;
+        q[degree] = qc;
+        mont_mul(FR, qc.l, z->l, t.l);            /* remainder[degree] -= qc * (-z) */
+        fe_add(FR, r[degree].l, t.l, r[degree].l);
+    }
+    *rem = r[0];
+    free(r);
+}

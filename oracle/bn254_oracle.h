@@ -120,6 +120,9 @@ void oracle_fix_var_mt(const ofe_t *evals, size_t n, const ofe_t *x, int num_thr
 /* Keccak256 (original Keccak padding) as used by Keccak256Transcript (util/transcript.rs:100-131, util/hash.rs:5-8). */
 void oracle_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
 
+/* div_rem by (X - z) (poly/univariate.rs:144-168 as UnivariateKzg::open calls it, pcs/univariate/kzg.rs:281-282). */
+void oracle_fr_div_linear(const ofe_t *coeffs, size_t n, const ofe_t *z, ofe_t *q, ofe_t *rem);
+
 /* Array forms of oracle_fe_from_canonical / oracle_fe_to_canonical. */
 void oracle_fe_from_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out);
 void oracle_fe_to_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out);

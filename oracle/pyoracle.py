@@ -48,6 +48,7 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fe_from_canonical.argtypes = [ci, vp, vp]
         _lib.oracle_fe_to_canonical.argtypes = [ci, vp, vp]
         _lib.oracle_fe_from_canonical_n.argtypes = [ci, vp, sz, vp]
+        _lib.oracle_fr_div_linear.argtypes = [vp, sz, vp, vp, vp]
         _lib.oracle_fe_to_canonical_n.argtypes = [ci, vp, sz, vp]
         _lib.oracle_g1_generator.argtypes = [vp]
         _lib.oracle_g1_is_on_curve.argtypes = [vp]
@@ -307,6 +308,17 @@ def evaluate_multilinear(evals, point, num_threads: int = 1) -> np.ndarray:
     for i in range(pt.shape[0]):
         cur = fix_var(cur, pt[i], num_threads if cur.shape[0] >= 1 << 14 else 1)
     return cur[0].copy()
+
+
+def fr_div_linear(coeffs, z):
+    """UnivariatePolynomial::div_rem by (X - z): returns (quotient [n-1, 4], remainder [4]) in Montgomery form."""
+    coeffs = _u64(coeffs).reshape(-1, 4)
+    z = _u64(z).reshape(4)
+    n = coeffs.shape[0]
+    q = np.zeros((max(n - 1, 0), 4), dtype=np.uint64)
+    rem = np.zeros(4, dtype=np.uint64)
+    lib().oracle_fr_div_linear(_ptr(coeffs), n, _ptr(z), _ptr(q) if n > 1 else None, _ptr(rem))
+    return q, rem
 
 
 def keccak256(data: bytes) -> bytes:

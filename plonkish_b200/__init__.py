@@ -11,6 +11,7 @@ from .msm import (  # noqa: F401
     ShardedG1Bases,
     variable_base_msm_batch_keep,
     fr_linear_combination,
+    fr_div_linear,
     kzg_open_resident,
     eq_table,
     fixed_base_msm,
@@ -30,6 +31,7 @@ from .msm import (  # noqa: F401
     bench_madd,
     bench_fp64_pipe,
     bench_dp_madd,
+    bench_issue_mix,
     cached_bases,
     cache_evict,
     cache_limit,

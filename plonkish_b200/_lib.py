@@ -33,6 +33,7 @@ EXPORTS = (
     "plonkish_cuda_staged_bytes",
     "plonkish_cuda_bench_fp64_pipe",
     "plonkish_cuda_bench_dp_madd",
+    "plonkish_cuda_bench_issue_mix",
     "plonkish_cuda_msm_bn254_g1",
     "plonkish_cuda_msm_bn254_g1_batch",
     "plonkish_cuda_msm_bn254_g1_many",
@@ -43,6 +44,7 @@ EXPORTS = (
     "plonkish_cuda_msm_bn254_g1_resident",
     "plonkish_cuda_msm_bn254_g1_batch_keep",
     "plonkish_cuda_fr_linear_combination",
+    "plonkish_cuda_fr_div_linear",
     "plonkish_cuda_kzg_open_bn254",
     "plonkish_cuda_fixed_base_msm_bn254_g1",
     "plonkish_cuda_kzg_setup_eqs_bn254",
@@ -117,6 +119,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_staged_bytes.argtypes = []
     lib.plonkish_cuda_staged_bytes.restype = u64
     lib.plonkish_cuda_bench_fp64_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.plonkish_cuda_bench_issue_mix.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_bench_dp_madd.argtypes = [ci, ci, ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_msm_bn254_g1.argtypes = [vp, vp, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_batch.argtypes = [vp, sz, u64, sz, vp]
@@ -139,6 +142,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_resident.argtypes = [u64, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_batch_keep.argtypes = [vp, sz, u64, sz, vp, vp]
     lib.plonkish_cuda_fr_linear_combination.argtypes = [vp, vp, sz, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_fr_div_linear.argtypes = [u64, vp, ctypes.POINTER(u64), vp]
     lib.plonkish_cuda_kzg_open_bn254.argtypes = [u64, vp, vp, sz, vp, vp]
     lib.plonkish_cuda_fixed_base_msm_bn254_g1.argtypes = [ci, vp, vp, sz, vp]
     lib.plonkish_cuda_kzg_setup_eqs_bn254.argtypes = [ci, vp, vp, sz, vp]

@@ -2047,6 +2047,66 @@ extern "C" int plonkish_cuda_bench_fp64_pipe(int device, double out[3]) {
     return PLONKISH_CUDA_OK;
 }
 
+// ---- is the accumulate loop bound by the multiplier pipe or by instruction issue?  8 independent mad.wide.u32 per
+// iteration, interleaved with 8 * R independent 32-bit adds (IADD3 on the ALU pipe) on other registers.
+template <int R>
+__global__ void __launch_bounds__(256) k_bench_imad_alu_mix(unsigned long long *out, u32 iters, u32 seed) {
+    unsigned long long acc[8];
+    u32 extra[8 * (R > 0 ? R : 1)];
+    u32 a = seed + threadIdx.x * 2654435761u, b = seed ^ (blockIdx.x * 40503u + 12345u + threadIdx.x * 7919u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = (unsigned long long)(a + k) << 7;
+#pragma unroll
+    for (int k = 0; k < 8 * (R > 0 ? R : 1); ++k) extra[k] = a ^ (k * 977u);
+    for (u32 it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + (u32)k), "r"(b));
+#pragma unroll
+            for (int j = 0; j < R; ++j) asm volatile("add.u32 %0, %0, %1;" : "+r"(extra[k * R + j]) : "r"(b));
+        }
+        b += 0x9e3779b9u;
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s ^= acc[k];
+#pragma unroll
+    for (int k = 0; k < 8 * (R > 0 ? R : 1); ++k) s += extra[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// out[R] = mad.wide.u32 per second with R adds issued next to every multiply, R = 0..3.
+extern "C" int plonkish_cuda_bench_issue_mix(int device, double out[4]) {
+    Ctx *c = ctx_for(device);
+    if (!c || !out) return fail(PLONKISH_CUDA_E_INVALID, "bench_issue_mix: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
+    void *scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const u32 iters = 4096;
+    for (int r = 0; r < 4; ++r) {
+        float ms = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0, c->stream));
+            if (r == 0) PK_LAUNCH((k_bench_imad_alu_mix<0>), dim3(blocks), dim3(threads), 0, c->stream, (unsigned long long *)scratch, iters, 51u + rep);
+            if (r == 1) PK_LAUNCH((k_bench_imad_alu_mix<1>), dim3(blocks), dim3(threads), 0, c->stream, (unsigned long long *)scratch, iters, 51u + rep);
+            if (r == 2) PK_LAUNCH((k_bench_imad_alu_mix<2>), dim3(blocks), dim3(threads), 0, c->stream, (unsigned long long *)scratch, iters, 51u + rep);
+            if (r == 3) PK_LAUNCH((k_bench_imad_alu_mix<3>), dim3(blocks), dim3(threads), 0, c->stream, (unsigned long long *)scratch, iters, 51u + rep);
+            CUDA_TRY(cudaEventRecord(e1, c->stream));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        out[r] = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaFree(scratch));
+    return PLONKISH_CUDA_OK;
+}
+
 // ---- FP64-pipe mixed additions (dpfq.cuh): register-resident stream, alone and next to the integer-pipe stream
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_bench_dp_madd(uint4 *out, u32 iters, u32 seed) {
@@ -2505,6 +2565,38 @@ extern "C" int plonkish_cuda_kzg_open_bn254(uint64_t scalars_handle, const uint6
         for (size_t i = 0; i < num_vars; ++i) sizes.push_back((size_t)1 << i);
         timer_report_shared(sizes, t0);
     }
+    return PLONKISH_CUDA_OK;
+}
+
+// UnivariatePolynomial::div_rem by (X - z) on resident coefficients (poly/univariate.rs:144-168): the quotient of
+// UnivariateKzg::open (pcs/univariate/kzg.rs:281-282) and, point by point, of batch_open's vanishing polynomials (:327).
+// The quotient comes back as a new resident vector of the same length n (coefficient n-1 is zero), the remainder —
+// the polynomial's value at z — as one Montgomery Fr.
+extern "C" int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *z_mont32, uint64_t *out_quotient_handle, void *out_rem_mont32) {
+    if (!z_mont32 || !out_quotient_handle || !out_rem_mont32) return fail(PLONKISH_CUDA_E_INVALID, "fr_div_linear: null argument");
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "fr_div_linear: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    Ctx *c = ctx_for(se.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_div_linear: device %d not initialised", se.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t n = se.n;
+    void *q = nullptr, *scratch = nullptr;
+    int rc = pool_alloc(c, &q, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard q_guard{c, q};
+    const size_t scratch_elems = pk_horner_scratch_elems(n) + 16;
+    if ((rc = pool_alloc(c, &scratch, scratch_elems * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    PoolGuard s_guard{c, scratch};
+    char *zs = (char *)scratch, *rem = zs + 8 * PLONKISH_CUDA_SCALAR_BYTES, *work = zs + 16 * PLONKISH_CUDA_SCALAR_BYTES;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(zs, z_mont32, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    pk_enqueue_div_linear(se.d_ptr, n, zs, work, q, rem, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, rem, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_rem_mont32, c->h_out, PLONKISH_CUDA_SCALAR_BYTES);
+    *out_quotient_handle = publish_scalars(c->dev, q_guard.release(), n);
     return PLONKISH_CUDA_OK;
 }
 

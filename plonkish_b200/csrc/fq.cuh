@@ -92,6 +92,37 @@ PK_HD u32 cmad8(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
     return c;
 }
 
+// The same with the carry-out added to `top` inside the chain (one IADD3.X; returning the carry as a value and adding
+// it afterwards costs a predicated add pair and a move: the accumulate loop is bound by instruction issue, where every
+// ALU instruction next to the multiplies costs about a cycle — plonkish_cuda_bench_issue_mix).
+PK_HD void cmad8_top(u32 *acc, u32 &top, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    asm("mad.lo.cc.u32  %0, %9,  %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9,  %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32       %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+          "+r"(acc[7]), "+r"(top)
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+}
+// ... and for a chain whose top pair has headroom: no carry-out at all.
+PK_HD void cmad8_nc(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    asm("mad.lo.cc.u32  %0, %8,  %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8,  %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9,  %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9,  %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32    %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+}
+
 // e0 += carry_word; then o[k] = o[k+2] + {x1,x3,x5,x7} * y pairs (o[8] = o[9] = 0), the
 // carry of the first add entering the chain.  The top pair cannot overflow because
 // x7 < 2^31 (operands < 2p < 2^255).
@@ -162,6 +193,8 @@ inline u32 cmad8(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
     }
     return (u32)carry;
 }
+inline void cmad8_top(u32 *acc, u32 &top, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) { top += cmad8(acc, x0, x2, x4, x6, y); }
+inline void cmad8_nc(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) { (void)cmad8(acc, x0, x2, x4, x6, y); }
 inline void shift_mad8(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
     const u32 x[4] = {x1, x3, x5, x7};
     u64 t = (u64)e0 + carry_word;
@@ -235,7 +268,10 @@ PK_HD void final_sub(u32 *r) {
 // the old even one (minus its dead word 0) into the odd one — the single
 // left-over word ev[1] is folded in by shift_mad8's first add.  136 multiply
 // instructions per product: 64 (a*b) + 64 (m*q) + 8 (q).
-template <class MOD>
+//
+// LAZY = true is the redundant-range form the accumulate loop uses: operands and result in [0, 2m) and no final
+// subtraction (a*b/R + m < 4m^2/R + m < 2m because 4m < R for both moduli; the running value stays below a + m < 3m).
+template <class MOD, bool LAZY = false>
 PK_HD fe mont_mul(const fe &a, const fe &b) {
     u32 m[8];
     MOD::limbs(m);
@@ -251,8 +287,8 @@ PK_HD fe mont_mul(const fe &a, const fe &b) {
             od[2 * k] = (u32)po; od[2 * k + 1] = (u32)(po >> 32);
         }
         const u32 q = ev[0] * MOD::inv();
-        cmad8(od, m[1], m[3], m[5], m[7], q);               // top pair has headroom: no carry-out
-        od[7] += cmad8(ev, m[0], m[2], m[4], m[6], q);      // carry sits at true word 8 = od word 7
+        cmad8_nc(od, m[1], m[3], m[5], m[7], q);               // top pair has headroom: no carry-out
+        cmad8_top(ev, od[7], m[0], m[2], m[4], m[6], q);      // carry sits at true word 8 = od word 7
     }
     // rows 1..7, roles of ev/od alternate
 #pragma unroll
@@ -261,10 +297,10 @@ PK_HD fe mont_mul(const fe &a, const fe &b) {
         u32 *O = (i & 1) ? ev : od;   // old even accumulator: word 0 is dead, word 1 folds into E[0]
         const u32 y = b.l[i];
         shift_mad8(E[0], O[1], O, a.l[1], a.l[3], a.l[5], a.l[7], y);
-        O[7] += cmad8(E, a.l[0], a.l[2], a.l[4], a.l[6], y);
+        cmad8_top(E, O[7], a.l[0], a.l[2], a.l[4], a.l[6], y);
         const u32 q = E[0] * MOD::inv();
-        cmad8(O, m[1], m[3], m[5], m[7], q);
-        O[7] += cmad8(E, m[0], m[2], m[4], m[6], q);
+        cmad8_nc(O, m[1], m[3], m[5], m[7], q);
+        cmad8_top(E, O[7], m[0], m[2], m[4], m[6], q);
     }
     // Row 7 ran with E = od, O = ev and left od[0] == 0; the last shift gives
     // T/2^256 = ev + (od >> 32).
@@ -276,7 +312,7 @@ PK_HD fe mont_mul(const fe &a, const fe &b) {
         sh[7] = 0;
         add8(r.l, ev, sh);
     }
-    final_sub<MOD>(r.l);
+    if (!LAZY) final_sub<MOD>(r.l);
     return r;
 }
 
@@ -285,7 +321,9 @@ PK_HD fe mont_mul(const fe &a, const fe &b) {
 // Bounds: T_{i+1} < T_i / 2^32 + (a + c + m)(1 - 2^-32) keeps T < 3m - 3 < 2^256 for a, c < m, so
 // the accumulators never carry out of their top pairs (3 * m7 * 2^32 < 2^64 for both moduli) and
 // two conditional subtractions finish.
-template <class MOD>
+// LAZY: operands in [0, 2m), running value below a + c + m < 5m < 2^256, result below 8m^2/R + m < 2.6m: one conditional
+// subtraction brings it under 2m.
+template <class MOD, bool LAZY = false>
 PK_HD fe mont_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) {
     u32 m[8];
     MOD::limbs(m);
@@ -298,11 +336,11 @@ PK_HD fe mont_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) {
             ev[2 * k] = (u32)pe; ev[2 * k + 1] = (u32)(pe >> 32);
             od[2 * k] = (u32)po; od[2 * k + 1] = (u32)(po >> 32);
         }
-        cmad8(od, c.l[1], c.l[3], c.l[5], c.l[7], z);
-        od[7] += cmad8(ev, c.l[0], c.l[2], c.l[4], c.l[6], z);
+        cmad8_nc(od, c.l[1], c.l[3], c.l[5], c.l[7], z);
+        cmad8_top(ev, od[7], c.l[0], c.l[2], c.l[4], c.l[6], z);
         const u32 q = ev[0] * MOD::inv();
-        cmad8(od, m[1], m[3], m[5], m[7], q);
-        od[7] += cmad8(ev, m[0], m[2], m[4], m[6], q);
+        cmad8_nc(od, m[1], m[3], m[5], m[7], q);
+        cmad8_top(ev, od[7], m[0], m[2], m[4], m[6], q);
     }
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
@@ -310,12 +348,12 @@ PK_HD fe mont_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) {
         u32 *O = (i & 1) ? ev : od;
         const u32 y = b.l[i], z = d.l[i];
         shift_mad8(E[0], O[1], O, a.l[1], a.l[3], a.l[5], a.l[7], y);
-        O[7] += cmad8(E, a.l[0], a.l[2], a.l[4], a.l[6], y);
-        cmad8(O, c.l[1], c.l[3], c.l[5], c.l[7], z);
-        O[7] += cmad8(E, c.l[0], c.l[2], c.l[4], c.l[6], z);
+        cmad8_top(E, O[7], a.l[0], a.l[2], a.l[4], a.l[6], y);
+        cmad8_nc(O, c.l[1], c.l[3], c.l[5], c.l[7], z);
+        cmad8_top(E, O[7], c.l[0], c.l[2], c.l[4], c.l[6], z);
         const u32 q = E[0] * MOD::inv();
-        cmad8(O, m[1], m[3], m[5], m[7], q);
-        O[7] += cmad8(E, m[0], m[2], m[4], m[6], q);
+        cmad8_nc(O, m[1], m[3], m[5], m[7], q);
+        cmad8_top(E, O[7], m[0], m[2], m[4], m[6], q);
     }
     fe r;
     {
@@ -326,7 +364,7 @@ PK_HD fe mont_mul_sum(const fe &a, const fe &b, const fe &c, const fe &d) {
         add8(r.l, ev, sh);
     }
     final_sub<MOD>(r.l);
-    final_sub<MOD>(r.l);
+    if (!LAZY) final_sub<MOD>(r.l);
     return r;
 }
 
@@ -383,6 +421,53 @@ PK_HD u32 cmad8_from(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
             : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
     }
     return c;  // S == 4: nothing to add
+}
+template <int S>
+PK_HD void cmad8_from_top(u32 *acc, u32 &top, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
+    if constexpr (S == 0) {
+        asm(
+            "mad.lo.cc.u32  %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    else if constexpr (S == 1) {
+        asm(
+            "mad.lo.cc.u32  %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    else if constexpr (S == 2) {
+        asm(
+            "mad.lo.cc.u32  %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
+    else if constexpr (S == 3) {
+        asm(
+            "mad.lo.cc.u32  %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32       %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(x0), "r"(x2), "r"(x4), "r"(x6), "r"(y));
+    }
 }
 template <int S>
 PK_HD void shift_mad8_from(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
@@ -463,6 +548,8 @@ inline u32 cmad8_from(u32 *acc, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) {
     return cmad8(acc, S > 0 ? 0u : x0, S > 1 ? 0u : x2, S > 2 ? 0u : x4, S > 3 ? 0u : x6, y);
 }
 template <int S>
+inline void cmad8_from_top(u32 *acc, u32 &top, u32 x0, u32 x2, u32 x4, u32 x6, u32 y) { top += cmad8_from<S>(acc, x0, x2, x4, x6, y); }
+template <int S>
 inline void shift_mad8_from(u32 &e0, u32 carry_word, u32 *o, u32 x1, u32 x3, u32 x5, u32 x7, u32 y) {
     shift_mad8(e0, carry_word, o, S > 0 ? 0u : x1, S > 1 ? 0u : x3, S > 2 ? 0u : x5, S > 3 ? 0u : x7, y);
 }
@@ -475,16 +562,17 @@ PK_HD void sqr_row(u32 *ev, u32 *od, const u32 *x, u32 y, const u32 *m) {
     u32 *E = (I & 1) ? od : ev;
     u32 *O = (I & 1) ? ev : od;
     shift_mad8_from<I / 2>(E[0], O[1], O, x[1], x[3], x[5], x[7], y);       // odd limbs below I skipped
-    O[7] += cmad8_from<(I + 1) / 2>(E, x[0], x[2], x[4], x[6], y);          // even limbs below I skipped
+    cmad8_from_top<(I + 1) / 2>(E, O[7], x[0], x[2], x[4], x[6], y);          // even limbs below I skipped
     const u32 q = E[0] * MOD::inv();
-    cmad8(O, m[1], m[3], m[5], m[7], q);
-    O[7] += cmad8(E, m[0], m[2], m[4], m[6], q);
+    cmad8_nc(O, m[1], m[3], m[5], m[7], q);
+    cmad8_top(E, O[7], m[0], m[2], m[4], m[6], q);
 }
 
 // a*a / 2^256 mod m, a < m: 36 + 64 wide multiplies instead of 128.  Row i multiplies a_i by a_i and by the limbs of
 // the doubled tail 2 * (a >> 32(i+1)) only; the running value stays below 3m < 2^256 (a row adds at most 2^32 * 2a),
 // the final value below 2m.
-template <class MOD>
+// LAZY as in mont_mul: a in [0, 2m) (2a < 2^256 still fits the eight limbs of d), result below 2m unreduced.
+template <class MOD, bool LAZY = false>
 PK_HD fe mont_sqr(const fe &a) {
     u32 m[8], d[8];
     MOD::limbs(m);
@@ -501,8 +589,8 @@ PK_HD fe mont_sqr(const fe &a) {
             od[2 * k] = (u32)po; od[2 * k + 1] = (u32)(po >> 32);
         }
         const u32 q = ev[0] * MOD::inv();
-        cmad8(od, m[1], m[3], m[5], m[7], q);
-        od[7] += cmad8(ev, m[0], m[2], m[4], m[6], q);
+        cmad8_nc(od, m[1], m[3], m[5], m[7], q);
+        cmad8_top(ev, od[7], m[0], m[2], m[4], m[6], q);
     }
 #define PK_SQR_ROW(I)                                                                                         \
     {                                                                                                         \
@@ -520,7 +608,7 @@ PK_HD fe mont_sqr(const fe &a) {
         sh[7] = 0;
         add8(r.l, ev, sh);
     }
-    final_sub<MOD>(r.l);
+    if (!LAZY) final_sub<MOD>(r.l);
     return r;
 }
 
@@ -556,6 +644,56 @@ PK_HD fe fq_neg(const fe &a) {
     u32 m[8];
     FqMod::limbs(m);
     sub8(r.l, m, a.l);
+    return r;
+}
+
+// ---- redundant-range forms for the accumulate loop: values in [0, 2p), no reduction after a product
+PK_HD void fq_two_p(u32 *t) {  // 2p
+    t[0] = 0xb0f9fa8eu; t[1] = 0x7841182du; t[2] = 0xd0e3951au; t[3] = 0x2f02d522u;
+    t[4] = 0x0302b0bbu; t[5] = 0x70a08b6du; t[6] = 0xc2634053u; t[7] = 0x60c89ce5u;
+}
+PK_HD fe fq_mul_lz(const fe &a, const fe &b) { return mont_mul<FqMod, true>(a, b); }
+PK_HD fe fq_sqr_lz(const fe &a) { return mont_sqr<FqMod, true>(a); }
+PK_HD fe fq_mul_sum_lz(const fe &a, const fe &b, const fe &c, const fe &d) { return mont_mul_sum<FqMod, true>(a, b, c, d); }
+PK_HD fe fq_add_lz(const fe &a, const fe &b) {  // a + b < 4p < 2^256, then minus 2p if it reaches it
+    fe r;
+    u32 t[8], d[8];
+    fq_two_p(t);
+    add8(r.l, a.l, b.l);
+    if (sub8(d, r.l, t) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = d[i];
+    }
+    return r;
+}
+PK_HD fe fq_sub_lz(const fe &a, const fe &b) {
+    fe r;
+    if (sub8(r.l, a.l, b.l)) {
+        u32 t[8];
+        fq_two_p(t);
+        add8(r.l, r.l, t);
+    }
+    return r;
+}
+PK_HD fe fq_neg_lz(const fe &a) {  // 2p - a, 0 -> 0
+    if (fe_is_zero(a)) return a;
+    fe r;
+    u32 t[8];
+    fq_two_p(t);
+    sub8(r.l, t, a.l);
+    return r;
+}
+PK_HD bool fq_is_zero_lz(const fe &a) {  // a in [0, 2p): congruent to zero iff 0 or p
+    u32 m[8];
+    FqMod::limbs(m);
+    u32 d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d |= a.l[i] ^ m[i];
+    return fe_is_zero(a) || d == 0;
+}
+PK_HD fe fq_canonical(const fe &a) {  // [0, 2p) -> [0, p)
+    fe r = a;
+    final_sub<FqMod>(r.l);
     return r;
 }
 

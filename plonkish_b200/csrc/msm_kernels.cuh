@@ -1041,6 +1041,7 @@ __global__ void __launch_bounds__(128, PK_ACC_MIN_BLOCKS) k_accumulate(const u32
         hk = g;
         for (u32 pos = s; pos < e; ++pos) {
             if (pos == next) {
+                acc = xyzz_canonical(acc);  // the loop keeps coordinates in [0, 2p)
                 if (!head_written) { store_xyzz(out_pts + 2 * (size_t)t, acc); head_written = true; } else { store_xyzz(bucket_sum + g, acc); }
                 acc = xyzz_identity();
                 do { ++g; next = bucket_start[g + 1]; } while (next <= pos);
@@ -1050,9 +1051,10 @@ __global__ void __launch_bounds__(128, PK_ACC_MIN_BLOCKS) k_accumulate(const u32
             const fe x = load_fe(bp);
             fe y = load_fe(bp + 2);
             if (entry >> 31) y = fq_neg(y);
-            xyzz_madd<MulInline>(acc, x, y);
+            xyzz_madd_lazy(acc, x, y);
         }
         tk = g;
+        acc = xyzz_canonical(acc);
     }
     out_keys[2 * (size_t)t] = hk;
     out_keys[2 * (size_t)t + 1] = tk;

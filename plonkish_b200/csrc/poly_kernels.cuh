@@ -173,6 +173,106 @@ inline void pk_enqueue_fr_powers(const void *d_s, size_t n, void *out, pk_stream
     PK_LAUNCH(k_fr_powers, dim3((unsigned)((threads + 127) / 128)), dim3(128), 0, stream, (const uint4 *)d_s, n, (uint4 *)out);
 }
 
+// ------------------------------------------------------- division by (X - z)
+// UnivariatePolynomial::div_rem by the divisor (X - z) (poly/univariate.rs:144-168 as called from UnivariateKzg::open,
+// pcs/univariate/kzg.rs:281-282, and, point after point, for the vanishing polynomials of batch_open, :327): with
+// h[i] = c[i] + z h[i+1] (h[n] = 0) the quotient is q[i-1] = h[i] and the remainder h[0].  The recurrence is cut into
+// chunks of PK_HORNER_CHUNK coefficients: every thread first runs its chunk with a zero carry-in, the chunk totals obey
+// the same recurrence with z^chunk (solved by recursion, three levels for 2^22 coefficients), and a second pass adds
+// z^(distance) * carry-in.  Three products per coefficient, 32-byte accesses.
+#define PK_HORNER_CHUNK 256
+__global__ void __launch_bounds__(128) k_horner_local(const uint4 *__restrict__ c, size_t n, const uint4 *__restrict__ z_ptr, uint4 *__restrict__ lh,
+                                                      uint4 *__restrict__ totals) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_HORNER_CHUNK;
+    if (first >= n) return;
+    const size_t end = (first + PK_HORNER_CHUNK < n) ? first + PK_HORNER_CHUNK : n;
+    const fe z = load_fe_plain(z_ptr);
+    fe acc = fe_zero();
+    for (size_t i = end; i-- > first;) {
+        acc = fr_add(load_fe_plain(c + 2 * i), fr_mul(z, acc));
+        store_fe(lh + 2 * i, acc);
+    }
+    store_fe(totals + 2 * t, acc);
+}
+// h[i] = lh[i] + z^(end - i) * carry[t + 1] for chunk t (carry = the solved recurrence of the totals; carry[chunks] = 0 is
+// not stored: the last chunk is final as it is).  shift = 1 writes h[i] to out[i - 1] and h[0] to rem (quotient layout).
+__global__ void __launch_bounds__(128) k_horner_fix(const uint4 *__restrict__ lh, size_t n, const uint4 *__restrict__ z_ptr, const uint4 *__restrict__ carry,
+                                                    size_t chunks, uint4 *__restrict__ out, int shift, uint4 *__restrict__ rem) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_HORNER_CHUNK;
+    if (first >= n) return;
+    const size_t end = (first + PK_HORNER_CHUNK < n) ? first + PK_HORNER_CHUNK : n;
+    const fe z = load_fe_plain(z_ptr);
+    const bool has = t + 1 < chunks;
+    const fe cin = has ? load_fe_plain(carry + 2 * (t + 1)) : fe_zero();
+    fe pw = z;
+    for (size_t i = end; i-- > first;) {
+        fe v = load_fe_plain(lh + 2 * i);
+        if (has) {
+            v = fr_add(v, fr_mul(pw, cin));
+            pw = fr_mul(pw, z);
+        }
+        if (!shift) store_fe(out + 2 * i, v);
+        else if (i) store_fe(out + 2 * (i - 1), v);
+        else store_fe(rem, v);
+    }
+}
+// one thread: the whole recurrence of a short array (the top of the recursion)
+__global__ void k_horner_serial(const uint4 *__restrict__ c, size_t n, const uint4 *__restrict__ z_ptr, uint4 *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const fe z = load_fe_plain(z_ptr);
+    fe acc = fe_zero();
+    for (size_t i = n; i-- > 0;) {
+        acc = fr_add(load_fe_plain(c + 2 * i), fr_mul(z, acc));
+        store_fe(out + 2 * i, acc);
+    }
+}
+// zs[l + 1] = zs[l]^256
+__global__ void k_horner_pow(uint4 *__restrict__ zs, u32 levels) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fe z = load_fe_plain(zs);
+    for (u32 l = 0; l < levels; ++l) {
+        for (int k = 0; k < 8; ++k) z = fr_mul(z, z);
+        store_fe(zs + 2 * (size_t)(l + 1), z);
+    }
+}
+inline size_t pk_horner_scratch_elems(size_t n) {  // lh of every level + the z powers
+    size_t total = 8, m = n;
+    while (m > 64) {
+        total += m;
+        m = (m + PK_HORNER_CHUNK - 1) / PK_HORNER_CHUNK;
+        total += m;  // totals (the next level's input)
+    }
+    return total + 64 + 64;
+}
+// out = h (shift 0) or the quotient with the remainder in *rem (shift 1).  c has n coefficients; zs[0] = z on entry
+// (8 element slots); scratch holds pk_horner_scratch_elems(n) elements.
+inline void pk_enqueue_horner(const uint4 *c, size_t n, uint4 *zs, u32 level, uint4 *scratch, uint4 *out, int shift, uint4 *rem, pk_stream_t stream) {
+    if (n <= 64) {
+        if (!shift) {
+            PK_LAUNCH(k_horner_serial, dim3(1), dim3(32), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), out);
+        } else {  // serial into scratch, then a one-chunk fix pass does the shifted copy
+            PK_LAUNCH(k_horner_serial, dim3(1), dim3(32), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), scratch);
+            PK_LAUNCH(k_horner_fix, dim3(1), dim3(128), 0, stream, (const uint4 *)scratch, n, (const uint4 *)(zs + 2 * (size_t)level), (const uint4 *)scratch, (size_t)1, out, 1, rem);
+        }
+        return;
+    }
+    const size_t chunks = (n + PK_HORNER_CHUNK - 1) / PK_HORNER_CHUNK;
+    uint4 *lh = scratch, *totals = scratch + 2 * n, *next = totals + 2 * chunks;
+    const unsigned blocks = (unsigned)((chunks + 127) / 128);
+    PK_LAUNCH(k_horner_local, dim3(blocks), dim3(128), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), lh, totals);
+    // the totals obey the same recurrence with z^256: solve in place of `totals` (h of the totals), using what follows as scratch
+    pk_enqueue_horner(totals, chunks, zs, level + 1, next, totals, 0, nullptr, stream);
+    PK_LAUNCH(k_horner_fix, dim3(blocks), dim3(128), 0, stream, (const uint4 *)lh, n, (const uint4 *)(zs + 2 * (size_t)level), (const uint4 *)totals, chunks, out, shift, rem);
+}
+// q (n - 1 coefficients, written to q[0 .. n-1); q[n-1] is set to zero) and rem = c mod (X - z).  z in zs[0].
+inline void pk_enqueue_div_linear(const void *c, size_t n, void *zs, void *scratch, void *q, void *rem, pk_stream_t stream) {
+    PK_LAUNCH(k_horner_pow, dim3(1), dim3(32), 0, stream, (uint4 *)zs, 4u);
+    PK_MEMSET0((uint4 *)q + 2 * (n - 1), 32, stream);
+    pk_enqueue_horner((const uint4 *)c, n, (uint4 *)zs, 0, (uint4 *)scratch, (uint4 *)q, 1, (uint4 *)rem, stream);
+}
+
 // ------------------------------------------------------------- fixed-base MSM
 // Signed 16-bit windows: 16 windows cover 254 bits plus the carry, the table holds
 // d * 2^(16w) * base for d = 1..2^15 (16 x 32768 x 64 B = 32 MiB, L2 resident); the

@@ -284,6 +284,16 @@ def fr_linear_combination(polys: Sequence["ResidentScalars"], coeffs) -> "Reside
     return ResidentScalars._adopt(out.value, n, polys[0].device)
 
 
+def fr_div_linear(poly: "ResidentScalars", z):
+    """poly / (X - z) on resident coefficients (poly/univariate.rs:144-168 for a linear divisor): returns
+    (quotient as ResidentScalars of the same length, top coefficient zero; remainder = poly(z) as Montgomery limbs [4])."""
+    zz = np.ascontiguousarray(z, dtype=np.uint64).reshape(4)
+    out = ctypes.c_uint64(0)
+    rem = np.zeros(4, dtype=np.uint64)
+    _lib.check(_lib.lib().plonkish_cuda_fr_div_linear(poly.handle, zz.ctypes.data, ctypes.byref(out), rem.ctypes.data), "plonkish_cuda_fr_div_linear")
+    return ResidentScalars._adopt(out.value, poly.n, poly.device), rem
+
+
 def eq_table(y, device: int = 0) -> "ResidentScalars":
     """eq(x, y) over the boolean hypercube as a resident polynomial (MultilinearPolynomial::eq_xy, the zero-check factor
     of piop/sum_check/classic.rs:57-61).  y: [k, 4] Montgomery Fr."""
@@ -492,6 +502,12 @@ def bench_fp64_pipe(device: int = 0) -> dict:
     out = (ctypes.c_double * 3)()
     _lib.check(_lib.lib().plonkish_cuda_bench_fp64_pipe(device, out), "plonkish_cuda_bench_fp64_pipe")
     return {"dfma_per_s": out[0], "dfma_per_s_mixed": out[1], "imad_wide_per_s_mixed": out[2]}
+
+
+def bench_issue_mix(device: int = 0) -> dict:
+    out = (ctypes.c_double * 4)()
+    _lib.check(_lib.lib().plonkish_cuda_bench_issue_mix(device, out), "plonkish_cuda_bench_issue_mix")
+    return {f"imad_wide_per_s_with_{r}_adds": out[r] for r in range(4)}
 
 
 def bench_dp_madd(dp_blocks_per_sm: int = 1, int_blocks_per_sm: int = 2, device: int = 0) -> dict:

@@ -63,6 +63,39 @@ void emul_dxyzz_madd(u32 *acc128, const u32 *pts64, u32 count) {
     memcpy(acc128, &a, 128);
 }
 
+// div_rem by (X - z): q receives n elements (q[n-1] = 0), rem one.
+void emul_div_linear(const u32 *c, uint64_t n, const u32 *z, u32 *q, u32 *rem) {
+    std::vector<unsigned char> scratch((pk_horner_scratch_elems(n) + 16) * 32);
+    memcpy(scratch.data(), z, 32);
+    pk_enqueue_div_linear(c, n, scratch.data(), scratch.data() + 16 * 32, q, rem, 0);
+}
+
+// redundant-range forms of the accumulate loop: op 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_sum (a*b + c*d); inputs in [0, 2p)
+void emul_fq_lazy(int op, const u32 *a, const u32 *b, const u32 *c, const u32 *d, u32 *o) {
+    fe x, y, z, w, r;
+    memcpy(&x, a, 32); memcpy(&y, b, 32); memcpy(&z, c, 32); memcpy(&w, d, 32);
+    switch (op) {
+        case 0: r = fq_mul_lz(x, y); break;
+        case 1: r = fq_sqr_lz(x); break;
+        case 2: r = fq_add_lz(x, y); break;
+        case 3: r = fq_sub_lz(x, y); break;
+        case 4: r = fq_neg_lz(x); break;
+        default: r = fq_mul_sum_lz(x, y, z, w); break;
+    }
+    memcpy(o, &r, 32);
+}
+void emul_xyzz_madd_lazy(u32 *acc128, const u32 *pts64, u32 count) {
+    xyzz a;
+    memcpy(&a, acc128, 128);
+    for (u32 k = 0; k < count; ++k) {
+        affine p;
+        memcpy(&p, pts64 + 16 * k, 64);
+        xyzz_madd_lazy(a, p.x, p.y);
+    }
+    a = xyzz_canonical(a);
+    memcpy(acc128, &a, 128);
+}
+
 // Field / point probes (the portable restatements of the carry-chain blocks).
 void emul_fq_mul(const u32 *a, const u32 *b, u32 *o) {
     fe x, y;

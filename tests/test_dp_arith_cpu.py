@@ -120,3 +120,57 @@ def test_point_formulas_match_the_integer_pipe_bit_for_bit(emul):
         for k in range(len(seq)):
             emul.emul_xyzz_madd(a2.ctypes.data, flat[16 * k:].ctypes.data)
         assert a1.tobytes() == a2.tobytes(), name
+
+
+def test_redundant_range_field_forms_of_the_accumulate_loop(emul):
+    # fq_*_lz (csrc/fq.cuh): operands and results in [0, 2p), no subtraction after a product; checked at the range's ends
+    emul.emul_fq_lazy.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5
+    rng = np.random.default_rng(9)
+    rinv = pow(1 << 256, -1, P)
+    ends = [0, 1, P - 1, P, P + 1, 2 * P - 1, 2 * P - 2, (1 << 254), (1 << 255) - 19]
+    vals = [v for v in ends if v < 2 * P] + [int.from_bytes(rng.bytes(32), "little") % (2 * P) for _ in range(40)]
+
+    def run(op, a, b=0, c=0, d=0):
+        out = np.zeros(8, dtype=np.uint32)
+        arrs = [_words(v) for v in (a, b, c, d)]
+        emul.emul_fq_lazy(op, *[x.ctypes.data for x in arrs], out.ctypes.data)
+        return int.from_bytes(out.tobytes(), "little")
+
+    for i, a in enumerate(vals):
+        b, c, d = vals[(5 * i + 2) % len(vals)], vals[(3 * i + 7) % len(vals)], vals[-1 - i % 9]
+        for x, y in ((a, b), (a, a), (2 * P - 1, 2 * P - 1), (a, 2 * P - 1)):
+            got = run(0, x, y)
+            assert got < 2 * P and got % P == x * y * rinv % P
+        got = run(1, a)
+        assert got < 2 * P and got % P == a * a * rinv % P
+        got = run(2, a, b)
+        assert got < 2 * P and got % P == (a + b) % P
+        got = run(3, a, b)
+        assert got < 2 * P and got % P == (a - b) % P
+        got = run(4, a)
+        assert got < 2 * P and got % P == (-a) % P
+        for w, x, y, z in ((a, b, c, d), (2 * P - 1, 2 * P - 1, 2 * P - 1, 2 * P - 1), (a, 2 * P - 1, 2 * P - 1, d)):
+            got = run(5, w, x, y, z)
+            assert got < 2 * P and got % P == (w * x + y * z) * rinv % P
+
+
+def test_lazy_point_formula_matches_the_canonical_one(emul):
+    emul.emul_xyzz_madd_lazy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    rng = np.random.default_rng(10)
+    pts = [br.scalar_mul(int(k), br.G) for k in rng.integers(1, 1 << 40, 40)]
+    seqs = {
+        "random": pts,
+        "doubling": [pts[0], pts[0], pts[1]],
+        "cancel": [pts[0], br.neg(pts[0]), pts[2], pts[3]],
+        "identity-bases": [None, pts[1], None, pts[2]],
+        "same-thrice": [pts[4]] * 3,
+        "double-late": pts[:5] + [br.msm([1] * 5, pts[:5])],   # the running sum itself comes back as a base: P + P at depth
+    }
+    for name, seq in seqs.items():
+        flat = np.concatenate([_affine_words(p) for p in seq])
+        a1 = np.zeros(32, dtype=np.uint32)
+        a2 = np.zeros(32, dtype=np.uint32)
+        emul.emul_xyzz_madd_lazy(a1.ctypes.data, flat.ctypes.data, len(seq))
+        for k in range(len(seq)):
+            emul.emul_xyzz_madd(a2.ctypes.data, flat[16 * k:].ctypes.data)
+        assert a1.tobytes() == a2.tobytes(), name

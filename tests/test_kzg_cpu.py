@@ -151,3 +151,28 @@ def test_emulated_fixed_base_kernels(emul, oracle):
     out = np.zeros((48, 8), dtype=np.uint64)
     emul.emul_fixed_base(g.ctypes.data, sc.ctypes.data, 48, out.ctypes.data)
     assert out.tobytes() == oracle.fixed_base_msm(g, sc).tobytes()
+
+
+def test_emulated_division_by_a_linear_factor_matches_the_oracle(oracle):
+    # poly/univariate.rs:144-168 for the divisor (X - z) (UnivariateKzg::open, pcs/univariate/kzg.rs:281-282): the chunked
+    # three-pass kernels (csrc/poly_kernels.cuh k_horner_*) run on the CPU against the oracle's long division
+    import ctypes
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    emul_dir = os.path.join(ROOT, "tests", "emul")
+    subprocess.run(["make", "-C", emul_dir], check=True, capture_output=True)
+    lib = ctypes.CDLL(os.path.join(emul_dir, "libemul_msm.so"))
+    lib.emul_div_linear.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    z = oracle.random_scalars(1, 11)[0]
+    for n in (1, 2, 3, 63, 64, 65, 255, 256, 257, 5000, 16384, 16385, 70001):
+        c = oracle.random_scalars(n, n)
+        q = np.full((n, 4), 0xAB, dtype=np.uint64)
+        rem = np.zeros(4, dtype=np.uint64)
+        lib.emul_div_linear(c.ctypes.data, n, z.ctypes.data, q.ctypes.data, rem.ctypes.data)
+        want_q, want_rem = oracle.fr_div_linear(c, z)
+        assert rem.tobytes() == want_rem.tobytes(), n
+        assert q[: n - 1].tobytes() == want_q.tobytes(), n
+        assert not q[n - 1].any(), n
