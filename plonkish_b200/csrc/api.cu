@@ -760,7 +760,15 @@ static bool lookup_bases(uint64_t handle, BasesEntry &out) {
 // Caller holds c->mu and has made c->dev current.  Enqueues the MSM over n device-
 // resident points on `stream`; leaves the projective sum in *d_xyzz_out (device).
 static MsmPlan plan_for(const Ctx *c, const BasesView &b, size_t n, uint32_t window_bits) {
-    if (b.table_c) return pk_make_plan_b((u32)n, b.table_c, (u32)b.stride, (u32)c->sm_count);
+    if (b.table_c) {
+        MsmPlan p = pk_make_plan_b((u32)n, b.table_c, (u32)b.stride, (u32)c->sm_count);
+        // Level 1 fused with the decomposition pays up to 2^21 points (measured, scatter stage: 2^18 0.089 -> 0.037 ms, 2^20
+        // 0.30 -> 0.115, 2^21 0.33 -> 0.22, 2^22 0.41 -> 0.41, 2^24 1.03 -> 1.40: one scalar conversion per thread and stage makes
+        // the big launches issue bound, while small ones save the digit round trip and a launch's worth of latency).
+        static const int fuse = [] { const char *e = getenv("PLONKISH_CUDA_FUSE_L1"); return e ? atoi(e) : -1; }();  // A/B switch: 0 / 1 force
+        p.fuse_l1 = fuse >= 0 ? (u32)(fuse != 0) : (n <= ((size_t)1 << 21) ? 1u : 0u);
+        return p;
+    }
     return pk_make_plan((u32)n, window_bits, (u32)c->sm_count);
 }
 

@@ -88,6 +88,7 @@ struct MsmPlan {
     u32 stride;       // mode 1: points per table row
     u32 chunk;        // which of the MSM's bucket arrays this launch sequence fills (host path pipelining)
     u32 nchunks;      // bucket arrays the reduce phase adds up (1 unless the host path cut the points into chunks)
+    u32 fuse_l1;      // mode 1, c >= 16: level 1 of the sort recomputes the digits from the scalars (no digit array)
 };
 
 inline u32 pk_ceil_log2(u32 v) {
@@ -170,6 +171,7 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     p.stride = 0;
     p.chunk = 0;
     p.nchunks = 1;
+    p.fuse_l1 = n <= (1u << 21) ? 1u : 0u;  // see plan_for in api.cu: the fused level 1 wins on small launches only
     return p;
 }
 
@@ -522,7 +524,9 @@ __global__ void __launch_bounds__(256) k_sort_bins(const u32 *__restrict__ l1, M
 // bucket |d| and the precomputed point T[w][i] = 2^(c*w) * P_i, so there is no
 // per-window reduction and no 2^(c*w) doubling chain at the end (msm.rs:162-164
 // disappears), and c can grow to 20-22 (fewer windows => fewer additions per point).
-template <int C>
+// STORE = false only counts (the fused level-1 scatter below recomputes the digits from the scalars instead of reading
+// them back: 32 B per point read twice instead of 4 W bytes written and read).
+template <int C, bool STORE = true>
 __global__ void __launch_bounds__(256) k_decompose_b(const uint4 *__restrict__ scalars, MsmPlan p, u32 *__restrict__ digits,
                                                      u32 *__restrict__ tile_hist) {
     constexpr int W = (254 + C - 1) / C + ((C * ((254 + C - 1) / C) < 255) ? 1 : 0);
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(256) k_decompose_b(const uint4 *__restrict__ s
                 enc = (sign << 31) | (mag - 1u);
                 atomicAdd(&hist[(mag - 1u) >> p.lo_bits], 1u);
             }
-            digits[(size_t)w * p.n_pad + i] = enc;
+            if (STORE) digits[(size_t)w * p.n_pad + i] = enc;
         }
     }
     __syncthreads();
@@ -703,6 +707,68 @@ __global__ void __launch_bounds__(1024) k_scatter_staged_b(const u32 *__restrict
             }
             staged_partition<PK_STAGE_EPT>(p.HI, dig, val, aux, ok, m, gcursor, l1_val, l1_key);
         }
+    }
+}
+
+// Level 1 fused with the decomposition (windows of 16 bits and more: W <= 16 entries per point): a stage is blockDim
+// points, every thread converts ONE scalar (to_repr, fold to <= (r-1)/2, signed digits — the code of k_decompose_b)
+// and contributes its W (bucket, table index) entries; all windows share the one bucket set, so they are partitioned
+// together.  The digit array is never written.
+template <int C>
+__global__ void __launch_bounds__(1024) k_scatter_fused_b(const uint4 *__restrict__ scalars, MsmPlan p, u32 *__restrict__ gcursor,
+                                                         u32 *__restrict__ l1_val, u16 *__restrict__ l1_key) {
+    constexpr int W = (254 + C - 1) / C + ((C * ((254 + C - 1) / C) < 255) ? 1 : 0);
+    constexpr u32 B = 1u << (C - 1);
+    static_assert(W <= PK_STAGE_EPT, "the fused scatter holds one point's digits per thread");
+    PK_DYN_SMEM(u32, smem);
+    const u32 S = blockDim.x * PK_STAGE_EPT;
+    const StageSmem m = stage_carve(smem, p.HI, S);
+    for (u32 d = threadIdx.x; d < p.HI; d += blockDim.x) m.lcnt[d] = 0;
+    __syncthreads();
+    const u32 beg = blockIdx.x * p.tile;
+    const u32 end = (beg + p.tile < p.n) ? beg + p.tile : p.n;
+    const u32 lo_mask = (1u << p.lo_bits) - 1u;
+    for (u32 s0 = beg; s0 < end; s0 += blockDim.x) {
+        u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
+        bool ok[PK_STAGE_EPT];
+#pragma unroll
+        for (int e = 0; e < PK_STAGE_EPT; ++e) { ok[e] = false; dig[e] = 0; val[e] = 0; aux[e] = 0; }
+        const u32 i = s0 + threadIdx.x;
+        if (i < end) {
+            fe v = fr_to_canonical(load_fe(scalars + 2 * (size_t)i));
+            const bool neg = fr_above_half(v);
+            if (neg) {
+                u32 mm[8];
+                FrMod::limbs(mm);
+                fe t;
+                sub8(t.l, mm, v.l);
+                v = t;
+            }
+            u32 carry = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int off = w * C;
+                const int word = off >> 5, sh = off & 31;
+                u32 raw = 0;
+                if (word < 8) {
+                    raw = v.l[word] >> sh;
+                    if (sh + C > 32 && word + 1 < 8) raw |= v.l[word + 1] << (32 - sh);
+                }
+                raw = (raw & ((1u << C) - 1u)) + carry;
+                const bool borrow = neg ? (raw >= B) : (raw > B);  // see k_decompose
+                const u32 mag = borrow ? (1u << C) - raw : raw;
+                carry = borrow ? 1u : 0u;
+                const u32 sign = (borrow ? 1u : 0u) ^ (neg ? 1u : 0u);
+                if (mag != 0) {
+                    const u32 b = mag - 1u;
+                    ok[w] = true;
+                    dig[w] = b >> p.lo_bits;
+                    aux[w] = b & lo_mask;
+                    val[w] = (sign << 31) | ((u32)w * p.stride + i);
+                }
+            }
+        }
+        staged_partition<PK_STAGE_EPT>(p.HI, dig, val, aux, ok, m, gcursor, l1_val, l1_key);
     }
 }
 
@@ -1251,22 +1317,41 @@ inline void pk_enqueue_buckets(const MsmPlan &p, const void *scalars, const void
         u16 *l1_key = reinterpret_cast<u16 *>(ws.l1 + emax);
         PK_MEMSET0(ws.bin_total, sizeof(u32) * p.HI, stream);
         PK_MEMSET0(ws.bucket_cur, sizeof(u32) * (p.nbuckets + 1), stream);
+        const bool fused = p.c >= 16 && p.fuse_l1;  // W <= 16: level 1 recomputes the digits, the first pass only counts
 #define PK_DECOMPOSE_B(C) case C: PK_LAUNCH(k_decompose_b<C>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
-        switch (p.c) {
-            PK_DECOMPOSE_B(8) PK_DECOMPOSE_B(9) PK_DECOMPOSE_B(10) PK_DECOMPOSE_B(11) PK_DECOMPOSE_B(12)
-            PK_DECOMPOSE_B(13) PK_DECOMPOSE_B(14) PK_DECOMPOSE_B(15) PK_DECOMPOSE_B(16) PK_DECOMPOSE_B(17)
-            PK_DECOMPOSE_B(18) PK_DECOMPOSE_B(19) PK_DECOMPOSE_B(20) PK_DECOMPOSE_B(21)
-            default: PK_LAUNCH(k_decompose_b<22>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
+#define PK_COUNT_B(C) case C: PK_LAUNCH((k_decompose_b<C, false>), dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
+        if (fused) {
+            switch (p.c) {
+                PK_COUNT_B(16) PK_COUNT_B(17) PK_COUNT_B(18) PK_COUNT_B(19) PK_COUNT_B(20) PK_COUNT_B(21)
+                default: PK_LAUNCH((k_decompose_b<22, false>), dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
+            }
+        } else {
+            switch (p.c) {
+                PK_DECOMPOSE_B(8) PK_DECOMPOSE_B(9) PK_DECOMPOSE_B(10) PK_DECOMPOSE_B(11) PK_DECOMPOSE_B(12)
+                PK_DECOMPOSE_B(13) PK_DECOMPOSE_B(14) PK_DECOMPOSE_B(15) PK_DECOMPOSE_B(16) PK_DECOMPOSE_B(17)
+                PK_DECOMPOSE_B(18) PK_DECOMPOSE_B(19) PK_DECOMPOSE_B(20) PK_DECOMPOSE_B(21)
+                default: PK_LAUNCH(k_decompose_b<22>, dim3(p.ntiles), dim3(p.blk), 0, stream, (const uint4 *)scalars, p, digits32, ws.bin_total); break;
+            }
         }
 #undef PK_DECOMPOSE_B
+#undef PK_COUNT_B
         PK_MARK(marks, 1, stream);
         // bin_total becomes the level-1 cursor array, bin_start the bin offsets (+ total).
         PK_LAUNCH(k_scan_inplace, dim3(1), dim3(1024), 0, stream, ws.bin_total, p.HI, ws.bin_start);
         PK_MARK(marks, 2, stream);
         const u32 S = p.blk_stage * PK_STAGE_EPT;
         const size_t smem1 = stage_smem_bytes(p.HI, S);
-        PK_SET_SMEM(k_scatter_staged_b, smem1);
-        PK_LAUNCH(k_scatter_staged_b, dim3(p.ntiles), dim3(p.blk_stage), smem1, stream, digits32, p, ws.bin_total, l1_val, l1_key);
+        if (fused) {
+#define PK_FUSED_B(C) case C: PK_SET_SMEM(k_scatter_fused_b<C>, smem1); PK_LAUNCH(k_scatter_fused_b<C>, dim3(p.ntiles), dim3(p.blk_stage), smem1, stream, (const uint4 *)scalars, p, ws.bin_total, l1_val, l1_key); break;
+            switch (p.c) {
+                PK_FUSED_B(16) PK_FUSED_B(17) PK_FUSED_B(18) PK_FUSED_B(19) PK_FUSED_B(20) PK_FUSED_B(21)
+                default: PK_SET_SMEM(k_scatter_fused_b<22>, smem1); PK_LAUNCH(k_scatter_fused_b<22>, dim3(p.ntiles), dim3(p.blk_stage), smem1, stream, (const uint4 *)scalars, p, ws.bin_total, l1_val, l1_key); break;
+            }
+#undef PK_FUSED_B
+        } else {
+            PK_SET_SMEM(k_scatter_staged_b, smem1);
+            PK_LAUNCH(k_scatter_staged_b, dim3(p.ntiles), dim3(p.blk_stage), smem1, stream, digits32, p, ws.bin_total, l1_val, l1_key);
+        }
         PK_MARK(marks, 3, stream);
         const u32 slice = 4 * S;
         const u32 max_slices = (u32)((emax + slice - 1) / slice) + p.nbins;  // every bin may end in a partial slice

@@ -150,7 +150,8 @@ def test_skewed_and_degenerate_inputs(emul, oracle):
     assert (emul.msm(sc, idb, 10, 1) == oracle.variable_base_msm(sc, idb, 2)).all()
 
 
-@pytest.mark.parametrize("n,use,c,sms", [(1, 1, 8, 148), (300, 77, 10, 2), (500, 500, 13, 1), (100, 100, 20, 1), (2000, 2000, 0, 1)])
+@pytest.mark.parametrize("n,use,c,sms", [(1, 1, 8, 148), (300, 77, 10, 2), (500, 500, 13, 1), (100, 100, 20, 1), (2000, 2000, 0, 1),
+                                          (300, 300, 16, 2), (70, 50, 22, 1), (150, 150, 17, 1)])  # c >= 16: level 1 fused with the decomposition
 def test_table_of_window_multiples(emul, oracle, n, use, c, sms):
     # mode 1: T[w][i] = 2^(c*w) * P_i built by the table kernels, one bucket set.
     sc = oracle.random_scalars(use, n + use)

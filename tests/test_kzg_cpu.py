@@ -176,3 +176,57 @@ def test_emulated_division_by_a_linear_factor_matches_the_oracle(oracle):
         assert rem.tobytes() == want_rem.tobytes(), n
         assert q[: n - 1].tobytes() == want_q.tobytes(), n
         assert not q[n - 1].any(), n
+
+
+def test_univariate_batch_open_host_logic_satisfies_the_verifier(oracle):
+    # pcs/univariate/kzg.rs:301-354: eval_sets, challenge powers, set scalars and the order of the transcript writes of the
+    # Python mirror, with the three polynomial operations supplied by the oracle (no GPU), against batch_verify's equation
+    from oracle import bigint_ref as br
+    from plonkish_b200 import univariate
+    from plonkish_b200.sumcheck import _to_int, _to_mont
+    from plonkish_b200.transcript import Keccak256Transcript
+    from univariate_verify import batch_verify_in_g1
+
+    R = br.R
+
+    class OracleOps:
+        @staticmethod
+        def linear_combination(polys, coeffs):
+            return oracle.fr_linear_combination(polys, np.stack([_to_mont(c) for c in coeffs]))
+
+        @staticmethod
+        def div_linear(poly, z):
+            q, rem = oracle.fr_div_linear(poly, _to_mont(z))
+            return np.concatenate([q, np.zeros((1, 4), dtype=np.uint64)]), _to_int(rem)
+
+        @staticmethod
+        def commit(srs, poly):
+            return oracle.variable_base_msm(poly, srs[: len(poly)])
+
+        @staticmethod
+        def release(p):
+            pass
+
+    n, s = 128, 0xC0FFEE1234567
+    srs = oracle.fixed_base_msm(oracle.generator(), np.stack([_to_mont(pow(s, i, R)) for i in range(n)]))
+    polys = [oracle.random_scalars(n, 40 + i) for i in range(4)]
+    coeffs = [[_to_int(r) for r in p] for p in polys]
+
+    def horner(c, x):
+        acc = 0
+        for v in reversed(c):
+            acc = (acc * x + v) % R
+        return acc
+
+    comms = [OracleOps.commit(srs, p) for p in polys]
+    points = [3, 0x55555, R - 2]
+    evals = [(0, 0), (0, 1), (1, 0), (2, 2), (3, 1), (3, 0), (2, 2)]
+    evals = [(p, x, horner(coeffs[p], points[x])) for p, x in evals]
+    t = Keccak256Transcript()
+    t.write_commitments(comms)
+    univariate.batch_open(srs, polys, points, evals, t, ops=OracleOps)
+    proof = t.into_proof()
+    pts = [(int.from_bytes(proof[i:i + 32], "big"), int.from_bytes(proof[i + 32:i + 64], "big")) for i in range(0, len(proof), 64)]
+    assert len(pts) == 6
+    sets = batch_verify_in_g1(comms, points, evals, pts[4], pts[5], s)
+    assert [st.polys for st in sets] == [[0, 3], [1], [2]] and sets[0].points == [0, 1] and sets[0].evals[1] == [evals[5][2], evals[4][2]]
