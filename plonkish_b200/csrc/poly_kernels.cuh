@@ -273,6 +273,199 @@ inline void pk_enqueue_div_linear(const void *c, size_t n, void *zs, void *scrat
     pk_enqueue_horner((const uint4 *)c, n, (uint4 *)zs, 0, (uint4 *)scratch, (uint4 *)q, 1, (uint4 *)rem, stream);
 }
 
+// ------------------------------------------------ permutation grand products
+// permutation_z_polys (backend/hyperplonk/prover.rs:252-345), the producer of the polynomial HyperPlonk commits at
+// backend/hyperplonk.rs:251-252.  Per chunk of permutation polynomials and per row b:
+//     product[b] = prod_i (beta * id_i(b) + gamma + value_i(b)) / prod_i (beta * sigma_i(b) + gamma + value_i(b)),
+// id_i(b) = (idx_i << num_vars) + b; then the running product over the rows in the order the reference's
+// BooleanHypercube iterates them (util/arithmetic/bh.rs:118-125: 0, then 1, X, X^2, ... in GF(2^k) modulo a primitive
+// polynomial), chunk after chunk within a row, and the result stored back in index order (nth_map, bh.rs:127-133).
+
+// a^(r-2) in Fr, 0 -> 0 (Field::invert's value; batch_invert at prover.rs:282 leaves zeros alone as well).
+PK_HD fe fr_inv(const fe &a) {
+    u32 e[8];
+    FrMod::limbs(e);
+    e[0] -= 2;  // r ends in ...0001: 0xf0000001 - 2, no borrow
+    fe one;     // R mod r
+    one.l[0] = 0x4ffffffbu; one.l[1] = 0xac96341cu; one.l[2] = 0x9f60cd29u; one.l[3] = 0x36fc7695u;
+    one.l[4] = 0x7879462eu; one.l[5] = 0x666ea36fu; one.l[6] = 0x9a07df2fu; one.l[7] = 0x0e0a77c1u;
+    fe acc = one, base = a;
+    for (int i = 0; i < 254; ++i) {
+        if ((e[i >> 5] >> (i & 31)) & 1u) acc = fr_mul(acc, base);
+        base = fr_mul(base, base);
+    }
+    return acc;
+}
+// Montgomery form of a small integer: v * R mod r = mont_mul(v, R^2 mod r).
+PK_HD fe fr_from_u64(unsigned long long v) {
+    fe x = fe_zero(), r2;
+    x.l[0] = (u32)v; x.l[1] = (u32)(v >> 32);
+    r2.l[0] = 0xae216da7u; r2.l[1] = 0x1bb8e645u; r2.l[2] = 0xe35c59e3u; r2.l[3] = 0x53fe3ab1u;
+    r2.l[4] = 0x53bb8085u; r2.l[5] = 0x8c49833du; r2.l[6] = 0x7f4e44a5u; r2.l[7] = 0x0216d0b1u;
+    return fr_mul(x, r2);
+}
+
+#define PK_PERM_MAX 8     // permutation polynomials per chunk (vanilla_plonk has three in one chunk)
+#define PK_PERM_STRIP 32  // rows per thread: one inversion per strip (Montgomery's trick)
+struct PermArgs {
+    const uint4 *value[PK_PERM_MAX];  // polys[*poly]: the witness column the permutation polynomial belongs to
+    const uint4 *sigma[PK_PERM_MAX];  // the permutation polynomial
+    unsigned long long id_offset[PK_PERM_MAX];  // idx << num_vars
+    u32 count;
+};
+__global__ void __launch_bounds__(128) k_perm_products(PermArgs a, const uint4 *__restrict__ beta_gamma, size_t n, uint4 *__restrict__ product) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_PERM_STRIP;
+    if (first >= n) return;
+    const u32 cnt = (u32)((first + PK_PERM_STRIP <= n) ? PK_PERM_STRIP : n - first);
+    const fe beta = load_fe_plain(beta_gamma), gamma = load_fe_plain(beta_gamma + 2);
+    fe one;
+    one.l[0] = 0x4ffffffbu; one.l[1] = 0xac96341cu; one.l[2] = 0x9f60cd29u; one.l[3] = 0x36fc7695u;
+    one.l[4] = 0x7879462eu; one.l[5] = 0x666ea36fu; one.l[6] = 0x9a07df2fu; one.l[7] = 0x0e0a77c1u;
+    // pass 1: prefix products of the denominators (left in `product`)
+    fe run = one;
+    for (u32 j = 0; j < cnt; ++j) {
+        fe den = one;
+        for (u32 i = 0; i < a.count; ++i)
+            den = fr_mul(den, fr_add(fr_add(fr_mul(beta, load_fe(a.sigma[i] + 2 * (first + j))), gamma), load_fe(a.value[i] + 2 * (first + j))));
+        store_fe(product + 2 * (first + j), run);      // prefix before row j
+        run = fr_mul(run, den);
+    }
+    fe inv = fr_inv(run);                               // a zero denominator zeroes the strip, as batch_invert would skip it: not reachable for a valid beta, gamma
+    // pass 2, backwards: 1 / den_j = inv * prefix_j, then the numerator
+    fe beta_id[PK_PERM_MAX];
+    for (u32 i = 0; i < a.count; ++i) beta_id[i] = fr_mul(beta, fr_from_u64(a.id_offset[i] + first + cnt - 1));
+    for (u32 j = cnt; j-- > 0;) {
+        fe den = one, num = one;
+        for (u32 i = 0; i < a.count; ++i) {
+            const fe v = load_fe(a.value[i] + 2 * (first + j));
+            den = fr_mul(den, fr_add(fr_add(fr_mul(beta, load_fe(a.sigma[i] + 2 * (first + j))), gamma), v));
+            num = fr_mul(num, fr_add(fr_add(beta_id[i], gamma), v));
+            beta_id[i] = fr_sub(beta_id[i], beta);
+        }
+        const fe inv_den = fr_mul(inv, load_fe_plain(product + 2 * (first + j)));
+        inv = fr_mul(inv, den);
+        store_fe(product + 2 * (first + j), fr_mul(num, inv_den));
+    }
+}
+
+// X^e in GF(2)[X] / primitive (degree k), e >= 0: the (e + 1)-th element of BooleanHypercube::iter after the leading 0.
+PK_HD u32 bh_pow_x(unsigned long long e, u32 k, u32 primitive) {
+    if (k == 0) return 1u;
+    auto mul = [&](u32 x, u32 y) {
+        unsigned long long acc = 0;
+        for (u32 i = 0; i < k; ++i)
+            if ((y >> i) & 1u) acc ^= (unsigned long long)x << i;
+        for (int i = (int)(2 * k) - 2; i >= (int)k; --i)
+            if ((acc >> i) & 1ull) acc ^= (unsigned long long)primitive << (i - k);
+        return (u32)acc;
+    };
+    u32 result = 1u, base = (k == 1) ? (2u ^ primitive) & 1u : 2u;  // X itself (reduced when k = 1: X = 1 mod X + 1)
+    while (e) {
+        if (e & 1ull) result = mul(result, base);
+        base = mul(base, base);
+        e >>= 1;
+    }
+    return result;
+}
+PK_HD u32 bh_next(u32 b, u32 k, u32 primitive) {  // bh.rs:141-146
+    b <<= 1;
+    b ^= (b >> k) * primitive;
+    return b;
+}
+// The factor sequence f_j = products[j % nc][bh(1 + j / nc)], j < m, gathered in scan order, with the running product of
+// every PK_SCAN_STRIP consecutive factors taken on the way: seq[j] = f_first * ... * f_j within the strip, totals[t] = the
+// strip's product.
+#define PK_SCAN_STRIP 256
+struct PermSeq {
+    const uint4 *product[PK_PERM_MAX];  // per chunk
+    u32 nc, k, primitive;
+};
+__global__ void __launch_bounds__(128) k_perm_gather_scan(PermSeq q, size_t m, uint4 *__restrict__ seq, uint4 *__restrict__ totals) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_SCAN_STRIP;
+    if (first >= m) return;
+    const size_t end = (first + PK_SCAN_STRIP < m) ? first + PK_SCAN_STRIP : m;
+    size_t nth = 1 + first / q.nc;       // row number in hypercube order
+    u32 c = (u32)(first % q.nc);
+    u32 b = bh_pow_x(nth - 1, q.k, q.primitive);
+    fe run = load_fe_plain(q.product[c] + 2 * (size_t)b);
+    store_fe(seq + 2 * first, run);
+    for (size_t j = first + 1; j < end; ++j) {
+        if (++c == q.nc) { c = 0; b = bh_next(b, q.k, q.primitive); }
+        run = fr_mul(run, load_fe_plain(q.product[c] + 2 * (size_t)b));
+        store_fe(seq + 2 * j, run);
+    }
+    store_fe(totals + 2 * t, run);
+}
+// in-place inclusive prefix product of a short array (the top of the recursion)
+__global__ void k_prodscan_serial(uint4 *__restrict__ v, size_t n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fe run = load_fe_plain(v);
+    for (size_t i = 1; i < n; ++i) {
+        run = fr_mul(run, load_fe_plain(v + 2 * i));
+        store_fe(v + 2 * i, run);
+    }
+}
+// strip-local inclusive prefix products of v (in place) and the strips' totals
+__global__ void __launch_bounds__(128) k_prodscan_local(uint4 *__restrict__ v, size_t n, uint4 *__restrict__ totals) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_SCAN_STRIP;
+    if (first >= n) return;
+    const size_t end = (first + PK_SCAN_STRIP < n) ? first + PK_SCAN_STRIP : n;
+    fe run = load_fe_plain(v + 2 * first);
+    for (size_t i = first + 1; i < end; ++i) {
+        run = fr_mul(run, load_fe_plain(v + 2 * i));
+        store_fe(v + 2 * i, run);
+    }
+    store_fe(totals + 2 * t, run);
+}
+// v[i] *= scanned_totals[strip - 1] for every strip but the first
+__global__ void __launch_bounds__(128) k_prodscan_fix(uint4 *__restrict__ v, size_t n, const uint4 *__restrict__ scanned_totals) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_SCAN_STRIP;
+    if (t == 0 || first >= n) return;
+    const size_t end = (first + PK_SCAN_STRIP < n) ? first + PK_SCAN_STRIP : n;
+    const fe cin = load_fe_plain(scanned_totals + 2 * (t - 1));
+    for (size_t i = first; i < end; ++i) store_fe(v + 2 * i, fr_mul(cin, load_fe_plain(v + 2 * i)));
+}
+// Inclusive prefix product of totals[0..n) in place (recursive: strips of 256).  scratch: n / 256 + ... elements.
+inline void pk_enqueue_prodscan(uint4 *v, size_t n, uint4 *scratch, pk_stream_t stream) {
+    if (n <= 64) {
+        PK_LAUNCH(k_prodscan_serial, dim3(1), dim3(32), 0, stream, v, n);
+        return;
+    }
+    const size_t strips = (n + PK_SCAN_STRIP - 1) / PK_SCAN_STRIP;
+    const unsigned blocks = (unsigned)((strips + 127) / 128);
+    PK_LAUNCH(k_prodscan_local, dim3(blocks), dim3(128), 0, stream, v, n, scratch);
+    pk_enqueue_prodscan(scratch, strips, scratch + 2 * strips, stream);
+    PK_LAUNCH(k_prodscan_fix, dim3(blocks), dim3(128), 0, stream, v, n, (const uint4 *)scratch);
+}
+// z polynomials from the scanned sequence: flat index i = c + nc * nth holds 0 (i < nc), 1 (i == nc) or seq[i - nc - 1];
+// polynomial c takes it at row bh(nth) (into_bh_order, prover.rs:333-341).
+__global__ void __launch_bounds__(128) k_perm_scatter(const uint4 *__restrict__ seq, PermSeq q, size_t rows, uint4 *const *__restrict__ out_polys) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t first = t * PK_SCAN_STRIP;      // rows in hypercube order handled by this thread
+    if (first >= rows) return;
+    const size_t end = (first + PK_SCAN_STRIP < rows) ? first + PK_SCAN_STRIP : rows;
+    fe one;
+    one.l[0] = 0x4ffffffbu; one.l[1] = 0xac96341cu; one.l[2] = 0x9f60cd29u; one.l[3] = 0x36fc7695u;
+    one.l[4] = 0x7879462eu; one.l[5] = 0x666ea36fu; one.l[6] = 0x9a07df2fu; one.l[7] = 0x0e0a77c1u;
+    u32 b = first ? bh_pow_x(first - 1, q.k, q.primitive) : 0u;
+    for (size_t nth = first; nth < end; ++nth) {
+        if (nth == 1) b = bh_pow_x(0, q.k, q.primitive);
+        else if (nth > first && nth > 1) b = bh_next(b, q.k, q.primitive);
+        for (u32 c = 0; c < q.nc; ++c) {
+            const size_t i = c + (size_t)q.nc * nth;
+            fe v;
+            if (i < q.nc) v = fe_zero();
+            else if (i == q.nc) v = one;
+            else v = load_fe_plain(seq + 2 * (i - q.nc - 1));
+            store_fe(out_polys[c] + 2 * (size_t)b, v);
+        }
+    }
+}
+
 // ------------------------------------------------------------- fixed-base MSM
 // Signed 16-bit windows: 16 windows cover 254 bits plus the carry, the table holds
 // d * 2^(16w) * base for d = 1..2^15 (16 x 32768 x 64 B = 32 MiB, L2 resident); the

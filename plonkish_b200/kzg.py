@@ -156,6 +156,67 @@ def open_to_transcript(pp: MultilinearKzgProverParam, poly: ResidentScalars, poi
     return value
 
 
+def eq_xy_table(point: Sequence[int]) -> List[int]:
+    """MultilinearPolynomial::eq_xy(y).evals() on canonical integers, lowest variable first (poly/multilinear.rs:91-130)."""
+    r = FR_MODULUS
+    evals = [1]
+    for y in point:
+        evals = [e * (1 - y) % r for e in evals] + [e * y % r for e in evals]
+    return evals
+
+
+def eq_xy_eval(x: Sequence[int], y: Sequence[int]) -> int:
+    """util::arithmetic::eq_xy_eval on canonical integers: prod_i (x_i y_i + (1 - x_i)(1 - y_i))."""
+    r = FR_MODULUS
+    out = 1
+    for a, b in zip(x, y):
+        out = out * ((a * b + (1 - a) * (1 - b)) % r) % r
+    return out
+
+
+def batch_open(pp: MultilinearKzgProverParam, num_vars: int, polys: Sequence[ResidentScalars], points: Sequence[Sequence[int]],
+               evals: Sequence[Tuple[int, int, int]], transcript) -> None:
+    """`additive::batch_open` (pcs/multilinear.rs:134-235), what MultilinearKzg::batch_open runs (kzg.rs:304-313), the
+    non-sanity-check path.  polys: resident polynomials of 2^num_vars evaluations; points: canonical-integer points;
+    evals: (poly index, point index, value) in the caller's order.  Writes the degree-2 sum check's coefficient messages
+    and the quotient commitments of the final opening to the transcript; every polynomial operation runs on the GPU."""
+    from . import sumcheck
+    from .msm import eq_table
+    from .transcript import fr_to_montgomery
+
+    r = FR_MODULUS
+    assert all(p.n == 1 << num_vars for p in polys) and all(len(pt) == num_vars for pt in points)  # validate_input, multilinear.rs:26-58
+    ell = max(len(evals) - 1, 0).bit_length()                                    # evals.len().next_power_of_two().ilog2()
+    t = transcript.squeeze_challenges(ell)
+    eq_xt = eq_xy_table(t)
+    # merged_polys (multilinear.rs:150-167): per point, the eq_xt-weighted sum of the polynomials evaluated there; a point
+    # with a single evaluation borrows the polynomial and keeps eq_xt_i as the scalar of its term
+    by_point: List[List[Tuple[int, int]]] = [[] for _ in points]
+    for (poly, point, _), w in zip(evals, eq_xt):
+        by_point[point].append((poly, w))
+    assert all(by_point), "every point needs at least one evaluation"
+    merged, owned = [], []
+    for entries in by_point:
+        if len(entries) == 1:
+            merged.append((entries[0][1], polys[entries[0][0]]))
+        else:
+            m = linear_combination([polys[i] for i, _ in entries], np.stack([fr_to_montgomery(w) for _, w in entries]))
+            owned.append(m)
+            merged.append((1, m))
+    eqs = [eq_table(np.stack([fr_to_montgomery(v) for v in pt])) for pt in points]
+    # expression sum_j eq_xy(j) * poly_j * scalar_j over the tables [eq_0, .., eq_{P-1}, poly_0, .., poly_{P-1}]
+    tables = eqs + [m for _, m in merged]
+    terms = [(fr_to_montgomery(scalar), [j, len(points) + j]) for j, (scalar, _) in enumerate(merged)]
+    tilde_gs_sum = sum(v * w for (_, _, v), w in zip(evals, eq_xt)) % r       # multilinear.rs:197-198
+    challenges, _ = sumcheck.prove_coefficients_to_transcript(tables, terms, tilde_gs_sum, transcript)
+    # g_prime (multilinear.rs:203-213) and its opening at the sum check's point (:227-234)
+    coeffs = [scalar * eq_xy_eval(challenges, pt) % r for (scalar, _), pt in zip(merged, points)]
+    g_prime = linear_combination([m for _, m in merged], np.stack([fr_to_montgomery(c) for c in coeffs]))
+    open_to_transcript(pp, g_prime, np.stack([fr_to_montgomery(c) for c in challenges]), transcript)
+    for x in owned + eqs + [g_prime]:
+        x.release()
+
+
 def univariate_setup(g1: np.ndarray, s: np.ndarray, poly_size: int, device: int = 0) -> G1Bases:
     """The G1 half of UnivariateKzg::setup (pcs/univariate/kzg.rs:175-195): powers_of_s_g1, built and kept on the GPU."""
     from .msm import kzg_setup_powers

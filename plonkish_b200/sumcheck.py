@@ -122,6 +122,36 @@ def prove(polys: Sequence[ResidentScalars], terms, claimed_sum: int, squeeze_cha
     return msgs, challenges, evals
 
 
+def prove_coefficients_to_transcript(polys: Sequence[ResidentScalars], terms, claimed_sum: int, transcript):
+    """`ClassicSumCheck<CoefficientsProver>::prove` (classic.rs:208-240 with classic/coeff.rs:68-147) for the degree-2
+    expressions of `additive::batch_open` (pcs/multilinear.rs:176-196: sum_j scalar_j * eq_xy(j) * poly_j): the round message
+    is the COEFFICIENT vector [c0, c1, c2] of the round polynomial (coeff.rs:21-23), with c0 = sum lhs0 * rhs0,
+    c2 = sum (lhs1 - lhs0)(rhs1 - rhs0) and c1 = sum - 2 c0 - c2 (coeff.rs:139-146).  The GPU round kernel returns the
+    polynomial's values at X = 1, 2; the same three coefficients follow from them and the running sum:
+    c0 = h(0) = sum - h(1), c2 = (h(2) - 2 h(1) + h(0)) / 2.  Returns (challenges, evals)."""
+    r = FR_MODULUS
+    inv2 = pow(2, -1, r)
+    prover = SumCheckProver(polys, terms, -1)
+    assert prover.degree == 2, "the coefficient form is implemented for products of two tables (coeff.rs:132-146)"
+    challenges: List[int] = []
+    total = claimed_sum % r
+    try:
+        for _ in range(prover.num_vars):
+            h1, h2 = (_to_int(row) for row in prover.round_evals())
+            c0 = (total - h1) % r
+            c2 = (h2 - 2 * h1 + c0) * inv2 % r
+            c1 = (total - 2 * c0 - c2) % r
+            transcript.write_field_elements([c0, c1, c2])
+            ch = transcript.squeeze_challenge()
+            challenges.append(ch)
+            total = (c0 + ch * (c1 + ch * c2)) % r       # horner(coeffs, challenge), coeff.rs:36-38
+            prover.fix_var(_to_mont(ch))
+        evals = [_to_int(row) for row in prover.final_evals()]
+    finally:
+        prover.free()
+    return challenges, evals
+
+
 def prove_to_transcript(polys: Sequence[ResidentScalars], terms, claimed_sum: int, transcript, common: int = -1):
     """`ClassicSumCheck::prove` with the reference's transcript calls (classic.rs:226-229): every round message goes
     down with `write_field_elements` (eval.rs:37-39), the challenge comes from `squeeze_challenge`.

@@ -284,3 +284,45 @@ def test_widened_rows_on_a_second_device(pk, oracle):
         r.release()
     pp.release()
     pp0.release()
+
+
+@pytest.mark.parametrize("k,shape", [(3, "single"), (6, "mixed"), (9, "mixed"), (7, "two-points-one-poly")])
+def test_batch_open_writes_the_reference_proof_bytes(pk, oracle, k, shape):
+    """additive::batch_open (pcs/multilinear.rs:134-235) through the GPU entry points against a restatement with Python
+    integers and the oracle's MSM (tests/batch_open_ref.py): identical transcript bytes — the coefficient messages of the
+    degree-2 sum check and the quotient commitments of the final opening."""
+    from batch_open_ref import batch_open_reference, to_int, to_mont
+    from plonkish_b200 import kzg
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    n = 1 << k
+    g = oracle.generator()
+    ss = pk.random_scalars(k, seed=31)
+    pp = kzg.setup(g, ss)
+    eqs_host = [e.to_host() for e in pp.eqs]
+    rng = np.random.default_rng(k)
+    num_polys = {"single": 1, "mixed": 5, "two-points-one-poly": 1}[shape]
+    polys_h = [pk.random_scalars(n, seed=70 + i) for i in range(num_polys)]
+    polys_i = [[to_int(r) for r in p] for p in polys_h]
+    points = [[int(x) for x in rng.integers(1, 1 << 62, k)] for _ in range({"single": 1, "mixed": 3, "two-points-one-poly": 2}[shape])]
+    pairs = {"single": [(0, 0)], "two-points-one-poly": [(0, 0), (0, 1)],
+             "mixed": [(0, 0), (1, 0), (2, 0), (3, 1), (4, 2), (3, 2), (0, 2)]}[shape]
+
+    def evaluate(poly, pt):
+        cur = poly
+        for x in pt:
+            cur = [(cur[2 * b] + (cur[2 * b + 1] - cur[2 * b]) * x) % br.R for b in range(len(cur) // 2)]
+        return cur[0]
+
+    evals = [(p, x, evaluate(polys_i[p], points[x])) for p, x in pairs]
+    resident = [pk.ResidentScalars(p) for p in polys_h]
+    t_gpu, t_ref = Keccak256Transcript(), Keccak256Transcript()
+    for t in (t_gpu, t_ref):
+        t.write_field_elements([v for _, _, v in evals])           # the evaluations are in the transcript before batch_open
+    kzg.batch_open(pp, k, resident, points, evals, t_gpu)
+    challenges, g_prime_eval = batch_open_reference(oracle, eqs_host, k, polys_i, points, evals, t_ref)
+    assert t_gpu.into_proof() == t_ref.into_proof()
+    assert len(t_gpu.into_proof()) == 32 * len(evals) + k * 3 * 32 + k * 64
+    for r_ in resident:
+        r_.release()
+    pp.release()
