@@ -388,14 +388,60 @@ def sum_check_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     return res
 
 
+def oracle_batch_open(po, np, commit, num_vars, polys, point, values, transcript, cores):
+    """additive::batch_open (pcs/multilinear.rs:134-235) for evaluations at ONE point, restated over the oracle's field
+    kernels (tests/batch_open_ref.py is the all-integer restatement the unit tests use; this one scales to 2^24):
+    merged polynomial, the degree-2 sum check in coefficient form (classic/coeff.rs:132-146), g_prime, open."""
+    from plonkish_b200.sumcheck import _to_int, _to_mont
+
+    r = FR_MODULUS
+    ell = max(len(values) - 1, 0).bit_length()
+    t = transcript.squeeze_challenges(ell)
+    eq_xt = [1]
+    for v in t:
+        eq_xt = [e * (1 - v) % r for e in eq_xt] + [e * v % r for e in eq_xt]
+    if len(polys) == 1:
+        scalar, merged = eq_xt[0], polys[0]
+    else:
+        scalar, merged = 1, po.fr_linear_combination(polys, np.stack([_to_mont(w) for w in eq_xt[: len(polys)]]))
+    claim = sum(v * w for v, w in zip(values, eq_xt)) % r
+    one = _to_mont(1)
+    cur = [po.kzg_eq_scalars(np.stack([_to_mont(v) for v in point]))[num_vars], merged]
+    terms = [(_to_mont(scalar), [0, 1])]
+    inv2 = pow(2, -1, r)
+    challenges = []
+    for _ in range(num_vars):
+        thr = cores if len(cur[0]) >= 1 << 14 else 1
+        h1, h2 = (_to_int(x) for x in po.sumcheck_round(cur, terms, -1, num_threads=thr))
+        c0 = (claim - h1) % r
+        c2 = (h2 - 2 * h1 + c0) * inv2 % r
+        c1 = (claim - 2 * c0 - c2) % r
+        transcript.write_field_elements([c0, c1, c2])
+        ch = transcript.squeeze_challenge()
+        challenges.append(ch)
+        claim = (c0 + ch * (c1 + ch * c2)) % r
+        cur = [po.fix_var(p, _to_mont(ch), thr) for p in cur]
+    e = 1
+    for a_, b_ in zip(challenges, point):
+        e = e * ((a_ * b_ + (1 - a_) * (1 - b_)) % r) % r
+    g_prime = po.fr_linear_combination([merged], np.stack([_to_mont(scalar * e % r)]))
+    qs, _ = po.quotients(g_prime, np.stack([_to_mont(c) for c in challenges]))
+    transcript.write_commitments([commit(q, i) for i, q in enumerate(qs)])
+
+
 def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool, reps: int):
-    """The GPU-side compute of a HyperPlonk proof for vanilla_plonk end to end, driven by the reference's Keccak256
-    transcript (util/transcript.rs:100-235): commit the three witness polynomials (backend/hyperplonk.rs:201, kept
-    resident), zero check of the gate over eq(x, y) and five resident selectors (hyperplonk.rs:262-277 through
-    piop/sum_check/classic.rs:208-240), g_prime merge of the witness polynomials (pcs/multilinear.rs:203-213) and its
-    KZG opening at the sum-check point (kzg.rs:276-302).  The permutation / lookup arguments and witness generation are
-    not part of it.  Parity: the same proof is rebuilt through the oracle — commitments through the SRS trapdoor
-    (cpu=False) or through the CPU port's MSMs (cpu=True, also timed) — and the proof BYTES must be identical."""
+    """The GPU-side compute of a HyperPlonk proof for vanilla_plonk, phase by phase as backend/hyperplonk.rs:164-291 runs
+    them, driven by the reference's Keccak256 transcript (util/transcript.rs:100-235): batch_commit of the three witness
+    polynomials (hyperplonk.rs:201, kept resident); beta, gamma; the permutation grand-product polynomial
+    (permutation_z_polys, prover.rs:252-345) and its commitment (hyperplonk.rs:251-252); alpha, y; the zero check
+    (hyperplonk.rs:262-277 through piop/sum_check/classic.rs:208-240) over eq(x, y) and the twelve polynomials; their
+    evaluations; and additive::batch_open (pcs/multilinear.rs:134-235: merged polynomial, the degree-2 sum check in
+    coefficient form, g_prime, MultilinearKzg::open).  Still a surrogate in one respect: the zero check's expression is
+    the vanilla_plonk gate only — the permutation constraint needs z at the rotated point (`Rotation::next`), and the
+    Expression -> tables compiler with rotations stays out of scope — so every polynomial is opened at the one
+    sum-check point.  Witness generation is not included.  Parity: the same proof is rebuilt through the oracle —
+    commitments through the SRS trapdoor (cpu=False) or through the CPU port's MSMs (cpu=True, also timed) — and the proof
+    BYTES must be identical."""
     from oracle import pyoracle as po
     from plonkish_b200 import kzg, sumcheck
     from plonkish_b200.sumcheck import interpolate_at
@@ -406,33 +452,53 @@ def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     pp = kzg.setup(g1_generator(np), ss)
     witness = [pk.random_scalars(n, seed=510 + j) for j in range(3)]   # pageable host memory, like the witness polys
     sel_h = [pk.random_scalars(n, seed=520 + j) for j in range(5)]     # q_l, q_r, q_m, q_o, q_c: preprocessed
+    # permutation polynomials: a random permutation of the 3 * 2^k cell ids (small integers, preprocessor.rs:184-190)
+    perm = np.random.default_rng(530).permutation(3 * n).astype(np.uint64)
+    canon = np.zeros((3 * n, 4), dtype=np.uint64)
+    canon[:, 0] = perm
+    sig_h = [a_.copy() for a_ in np.split(po.from_canonical(1, canon), 3)]
+    del canon, perm
     selectors = [pk.ResidentScalars(s_) for s_ in sel_h]
+    sigmas = [pk.ResidentScalars(s_) for s_ in sig_h]
     one = sumcheck._to_mont(1)
-    # tables: 0 eq, 1..5 selectors, 6..8 witness
+    # tables: 0 eq, 1..5 selectors, 6..8 witness, 9..11 permutation polynomials, 12 z
     terms = [(one, [1, 6]), (one, [2, 7]), (one, [3, 6, 7]), (one, [4, 8]), (one, [5])]
+    phases = []
 
     def run():
+        marks = [time.perf_counter()]
         t = Keccak256Transcript()
         comms, resident = kzg.batch_commit(pp, witness, keep=True)
         t.write_commitments(comms)
+        marks.append(time.perf_counter())
+        beta, gamma = t.squeeze_challenge(), t.squeeze_challenge()
+        (z,) = pk.permutation_z_polys(1, resident, sigmas, sumcheck._to_mont(beta), sumcheck._to_mont(gamma))
+        t.write_commitment(kzg.commit(pp, z))
+        marks.append(time.perf_counter())
+        t.squeeze_challenge()                                           # alpha: would weigh the constraints it separates
         y = t.squeeze_challenges(k)
         eq = pk.eq_table(np.stack([sumcheck._to_mont(v) for v in y]))
+        polys = selectors + resident + sigmas + [z]
         # the claimed sum of a random (unsatisfied) instance is whatever the first message implies: run with 0, as the
         # reference's prover would with a satisfying witness; the arithmetic per round is the same
-        challenges, evals = sumcheck.prove_to_transcript([eq] + selectors + resident, terms, 0, t, common=0)
-        t.write_field_elements(evals[6:])
-        coeffs = t.squeeze_challenges(3)
-        g_prime = kzg.linear_combination(resident, np.stack([sumcheck._to_mont(c) for c in coeffs]))
-        point = np.stack([sumcheck._to_mont(c) for c in challenges])
-        kzg.open_to_transcript(pp, g_prime, point, t)
-        for r in resident + [eq, g_prime]:
+        challenges, evals = sumcheck.prove_to_transcript([eq] + polys, terms, 0, t, common=0)
+        t.write_field_elements(evals[1:])
+        marks.append(time.perf_counter())
+        kzg.batch_open(pp, k, polys, [challenges], [(i, 0, v) for i, v in enumerate(evals[1:])], t)
+        marks.append(time.perf_counter())
+        for r in resident + [eq, z]:
             r.release()
+        marks.append(time.perf_counter())
+        phases.append([round((b_ - a_) * 1e3, 2) for a_, b_ in zip(marks, marks[1:])])
         return t.into_proof()
 
     proof, tm = timed_reps(run, reps)
-    res = {"what": "commit 3 witness polynomials -> zero check (9 tables, degree 4) -> g_prime merge -> KZG open, Keccak256 transcript on the host, "
-                   "all polynomial data resident in HBM after one upload from pageable memory; permutation / lookup arguments and witness generation not included",
-           "k": k, "gpu_ms": tm["ms_min"], "gpu_ms_median": tm["ms_median"], "gpu_ms_all": tm["ms_all"], "reps": reps, "proof_bytes": len(proof)}
+    res = {"what": "batch_commit of 3 witness polynomials -> permutation grand product z + commit -> zero check (13 tables, gate expression, degree 4) -> "
+                   "12 evaluations -> additive::batch_open (merge, degree-2 sum check, g_prime, KZG open), Keccak256 transcript on the host, all polynomial "
+                   "data resident in HBM after one upload from pageable memory; the permutation constraint's rotated opening and witness generation not included",
+           "k": k, "gpu_ms": tm["ms_min"], "gpu_ms_median": tm["ms_median"], "gpu_ms_all": tm["ms_all"], "reps": reps, "proof_bytes": len(proof),
+           "phases": ["batch_commit (upload + 3 MSMs)", "z polynomial + commit", "zero check + evaluations", "batch_open", "release"],
+           "phases_ms_all": phases[1:]}
     # ---- the same proof through the oracle
     cores = po.host_threads()
     td = Trapdoor(po, np, ss)
@@ -441,8 +507,13 @@ def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     t0 = time.perf_counter()
     t = Keccak256Transcript()
     t.write_commitments([commit(w, k) for w in witness])
+    beta, gamma = t.squeeze_challenge(), t.squeeze_challenge()
+    (z_h,) = po.permutation_z_polys(1, witness, sig_h, sumcheck._to_mont(beta), sumcheck._to_mont(gamma), num_threads=1 if cpu else cores)
+    t.write_commitment(commit(z_h, k))
+    t.squeeze_challenge()
     y = t.squeeze_challenges(k)
-    cur = [po.kzg_eq_scalars(np.stack([sumcheck._to_mont(v) for v in y]))[k]] + sel_h + [np.array(w) for w in witness]
+    host_polys = sel_h + [np.array(w) for w in witness] + sig_h + [z_h]
+    cur = [po.kzg_eq_scalars(np.stack([sumcheck._to_mont(v) for v in y]))[k]] + host_polys
     claim, challenges = 0, []
     for _ in range(k):
         thr = cores if (not cpu and len(cur[0]) >= 1 << 14) else 1
@@ -453,19 +524,19 @@ def prove_pipeline_bench(pk, torch, np, k: int, cpu: bool, reps: int):
         challenges.append(ch)
         claim = interpolate_at(msg, ch)
         cur = [po.fix_var(p, sumcheck._to_mont(ch), thr) for p in cur]
-    t.write_field_elements([sumcheck._to_int(p[0]) for p in cur[6:]])
-    coeffs = t.squeeze_challenges(3)
-    g_prime_h = po.fr_linear_combination(witness, np.stack([sumcheck._to_mont(c) for c in coeffs]))
-    qs, _ = po.quotients(g_prime_h, np.stack([sumcheck._to_mont(c) for c in challenges]))
-    t.write_commitments([commit(q, i) for i, q in enumerate(qs)])
+    values = [sumcheck._to_int(p[0]) for p in cur[1:]]
+    t.write_field_elements(values)
+    oracle_batch_open(po, np, commit, k, host_polys, challenges, values, t, 1 if cpu else cores)
     same = bool(t.into_proof() == proof)
     if cpu:
         res.update({"cpu_ms": (time.perf_counter() - t0) * 1e3, "cpu_cores": cores, "proof_bytes_identical_to_cpu": same})
+    else:
+        res["oracle_check_s"] = time.perf_counter() - t0
     res["parity_checked"] = same
-    res["parity_how"] = ("proof bytes identical to the oracle's proof (CPU port MSMs, single-threaded sum check)" if cpu else
-                         "proof bytes identical to the oracle's proof (commitments through the SRS trapdoor f(ss) * G, sum check on all host cores)")
+    res["parity_how"] = ("proof bytes identical to the oracle's proof (CPU port MSMs, single-threaded field work)" if cpu else
+                         "proof bytes identical to the oracle's proof (commitments through the SRS trapdoor f(ss) * G, field work on all host cores)")
     assert same, f"prove pipeline k={k}: proof bytes differ from the oracle's"
-    for s_ in selectors:
+    for s_ in selectors + sigmas:
         s_.release()
     pp.release()
     return res

@@ -160,6 +160,14 @@ int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const v
  * batch_open (:327).  The quotient is a new resident vector of the same length (top coefficient zero; release with
  * scalars_release), out_rem_mont32 the remainder, i.e. the polynomial's value at z. */
 int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *z_mont32, uint64_t *out_quotient_handle, void *out_rem_mont32);
+/* permutation_z_polys (backend/hyperplonk/prover.rs:252-345), the producer of the polynomials HyperPlonk commits at
+ * backend/hyperplonk.rs:251-252: per chunk of permutation polynomials the row-wise product of
+ * (beta * id + gamma + value) / (beta * sigma + gamma + value), then the running product over the rows in
+ * BooleanHypercube order (util/arithmetic/bh.rs:118-133), stored in index order.  value_handles[i] / sigma_handles[i]:
+ * the witness column and the permutation polynomial of permutation polynomial i (count of them, resident, 2^num_vars
+ * evaluations each), num_chunks = num_permutation_z_polys; out_handles receives num_chunks resident polynomials. */
+int plonkish_cuda_permutation_z_polys_bn254(const uint64_t *value_handles, const uint64_t *sigma_handles, size_t count, size_t num_chunks,
+                                            size_t num_vars, const void *beta_mont32, const void *gamma_mont32, uint64_t *out_handles);
 /* MultilinearKzg::open on a resident polynomial of 2^num_vars evaluations
  * (pcs/multilinear/kzg.rs:276-302): `quotients` (pcs/multilinear.rs:72-107) runs in HBM and
  * the num_vars quotient MSMs (kzg.rs:291-293) read their scalars from there.  eq_handles[i] =

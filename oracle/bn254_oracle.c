@@ -893,3 +893,118 @@ void oracle_fr_div_linear(const ofe_t *coeffs, size_t n, const ofe_t *z, ofe_t *
     *rem = r[0];
     free(r);
 }
+
+/* ---- permutation_z_polys (backend/hyperplonk/prover.rs:252-345) with BooleanHypercube (util/arithmetic/bh.rs) -------- */
+static const uint32_t BH_PRIMITIVES[32] = {1u, 3u, 7u, 11u, 19u, 37u, 67u, 131u, 285u, 529u, 1033u, 2053u, 4179u, 8219u, 16427u, 32771u, 65581u, 131081u,
+                                           262183u, 524327u, 1048585u, 2097157u, 4194307u, 8388641u, 16777243u, 33554441u, 67108935u, 134217767u,
+                                           268435465u, 536870917u, 1073741907u, 2147483657u}; /* bh.rs:5-38 */
+static size_t bh_next(size_t b, size_t num_vars, size_t primitive) { /* bh.rs:141-146 */
+    b <<= 1;
+    b ^= (b >> num_vars) * primitive;
+    return b;
+}
+/* BooleanHypercube::iter (bh.rs:118-125): 0, then 1 and its successors; out receives 2^num_vars entries. */
+void oracle_bh_iter(size_t num_vars, uint32_t *out) {
+    const size_t n = (size_t)1 << num_vars;
+    size_t b = 1;
+    out[0] = 0;
+    for (size_t i = 1; i < n; ++i) {
+        out[i] = (uint32_t)b;
+        b = bh_next(b, num_vars, BH_PRIMITIVES[num_vars]);
+    }
+}
+/* One chunk's products for rows [lo, hi) (prover.rs:267-299; `parallelize` cuts the rows the same way). */
+typedef struct {
+    const ofe_t *const *values, *const *sigmas; size_t first, last, num_vars, lo, hi; const ofe_t *beta, *gamma; ofe_t *product;
+} perm_task_t;
+static void *perm_task_run(void *arg) {
+    perm_task_t *t = (perm_task_t *)arg;
+    ofe_t *product = t->product;
+    uint64_t one_c[4] = {1, 0, 0, 0};
+    ofe_t one;
+    oracle_fe_from_canonical(1, one_c, &one);
+    for (size_t b = t->lo; b < t->hi; ++b) product[b] = one;
+    for (size_t i = t->first; i < t->last; ++i)
+        for (size_t b = t->lo; b < t->hi; ++b) {                                      /* product *= beta * permutation + gamma + value */
+            ofe_t v;
+            mont_mul(FR, t->beta->l, t->sigmas[i][b].l, v.l);
+            fe_add(FR, v.l, t->gamma->l, v.l);
+            fe_add(FR, v.l, t->values[i][b].l, v.l);
+            mont_mul(FR, product[b].l, v.l, product[b].l);
+        }
+    /* batch_invert (prover.rs:280-283): Montgomery's trick per strip — the same inverses as one by one */
+    {
+        enum { STRIP = 256 };
+        ofe_t prefix[STRIP];
+        for (size_t s0 = t->lo; s0 < t->hi; s0 += STRIP) {
+            const size_t cnt = t->hi - s0 < STRIP ? t->hi - s0 : STRIP;
+            ofe_t run = one, inv;
+            for (size_t j = 0; j < cnt; ++j) { prefix[j] = run; mont_mul(FR, run.l, product[s0 + j].l, run.l); }
+            fe_inv(FR, run.l, inv.l);
+            for (size_t j = cnt; j-- > 0;) {
+                ofe_t v;
+                mont_mul(FR, inv.l, prefix[j].l, v.l);
+                mont_mul(FR, inv.l, product[s0 + j].l, inv.l);
+                product[s0 + j] = v;
+            }
+        }
+    }
+    for (size_t i = t->first; i < t->last; ++i)
+        for (size_t b = t->lo; b < t->hi; ++b) {                                      /* product *= beta * id + gamma + value, id = (idx << num_vars) + b */
+            uint64_t id_c[4] = {((uint64_t)i << t->num_vars) + b, 0, 0, 0};
+            ofe_t id, v;
+            oracle_fe_from_canonical(1, id_c, &id);
+            mont_mul(FR, t->beta->l, id.l, v.l);
+            fe_add(FR, v.l, t->gamma->l, v.l);
+            fe_add(FR, v.l, t->values[i][b].l, v.l);
+            mont_mul(FR, product[b].l, v.l, product[b].l);
+        }
+    return NULL;
+}
+/* values[i], sigmas[i]: 2^num_vars Montgomery Fr each, i < count; out: num_chunks polynomials of 2^num_vars, one after another. */
+void oracle_permutation_z_polys_mt(size_t num_chunks, const ofe_t *const *values, const ofe_t *const *sigmas, size_t count, size_t num_vars,
+                                   const ofe_t *beta, const ofe_t *gamma, int num_threads, ofe_t *out) {
+    const size_t n = (size_t)1 << num_vars;
+    const size_t chunk_size = (count + num_chunks - 1) / num_chunks;                /* prover.rs:263 */
+    ofe_t *products = (ofe_t *)malloc(sizeof(ofe_t) * num_chunks * n);
+    uint64_t one_c[4] = {1, 0, 0, 0};
+    ofe_t one;
+    oracle_fe_from_canonical(1, one_c, &one);
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > n) num_threads = (int)n;
+    for (size_t chunk = 0; chunk < num_chunks; ++chunk) {
+        const size_t first = chunk * chunk_size, last = first + chunk_size < count ? first + chunk_size : count;
+        const size_t per = (n + num_threads - 1) / num_threads;
+        perm_task_t *tasks = (perm_task_t *)calloc(num_threads, sizeof(perm_task_t));
+        pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+        for (int t = 0; t < num_threads; ++t) {
+            const size_t lo = (size_t)t * per < n ? (size_t)t * per : n, hi = lo + per < n ? lo + per : n;
+            perm_task_t k = {values, sigmas, first, last, num_vars, lo, hi, beta, gamma, products + chunk * n};
+            tasks[t] = k;
+            pthread_create(&threads[t], NULL, perm_task_run, &tasks[t]);
+        }
+        for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+        free(tasks); free(threads);
+    }
+    /* z (prover.rs:303-320): num_chunks zeros, a one, then the running product over (row in hypercube order, chunk) */
+    const size_t flat = num_chunks << num_vars;
+    ofe_t *z = (ofe_t *)calloc(flat, sizeof(ofe_t));
+    uint32_t *order = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    oracle_bh_iter(num_vars, order);
+    size_t pos = num_chunks;
+    ofe_t state = one;
+    if (pos < flat) z[pos++] = one;
+    for (size_t nth = 1; nth < n && pos < flat; ++nth)
+        for (size_t chunk = 0; chunk < num_chunks && pos < flat; ++chunk) {
+            mont_mul(FR, state.l, products[chunk * n + order[nth]].l, state.l);
+            z[pos++] = state;
+        }
+    /* into_bh_order (prover.rs:333-341): poly_offset[b] = z[offset + num_chunks * nth_map[b]] */
+    for (size_t nth = 0; nth < n; ++nth)
+        for (size_t offset = 0; offset < num_chunks; ++offset) out[offset * n + order[nth]] = z[offset + num_chunks * nth];
+    free(products); free(z); free(order);
+}
+void oracle_permutation_z_polys(size_t num_chunks, const ofe_t *const *values, const ofe_t *const *sigmas, size_t count, size_t num_vars,
+                                const ofe_t *beta, const ofe_t *gamma, ofe_t *out) {
+    oracle_permutation_z_polys_mt(num_chunks, values, sigmas, count, num_vars, beta, gamma, 1, out);
+}

@@ -123,6 +123,13 @@ void oracle_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
 /* div_rem by (X - z) (poly/univariate.rs:144-168 as UnivariateKzg::open calls it, pcs/univariate/kzg.rs:281-282). */
 void oracle_fr_div_linear(const ofe_t *coeffs, size_t n, const ofe_t *z, ofe_t *q, ofe_t *rem);
 
+/* BooleanHypercube::iter (util/arithmetic/bh.rs:118-125) and permutation_z_polys (backend/hyperplonk/prover.rs:252-345). */
+void oracle_bh_iter(size_t num_vars, uint32_t *out);
+void oracle_permutation_z_polys(size_t num_chunks, const ofe_t *const *values, const ofe_t *const *sigmas, size_t count, size_t num_vars,
+                                const ofe_t *beta, const ofe_t *gamma, ofe_t *out);
+void oracle_permutation_z_polys_mt(size_t num_chunks, const ofe_t *const *values, const ofe_t *const *sigmas, size_t count, size_t num_vars,
+                                   const ofe_t *beta, const ofe_t *gamma, int num_threads, ofe_t *out);
+
 /* Array forms of oracle_fe_from_canonical / oracle_fe_to_canonical. */
 void oracle_fe_from_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out);
 void oracle_fe_to_canonical_n(int which, const uint64_t *in, size_t n, uint64_t *out);

@@ -49,6 +49,9 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fe_to_canonical.argtypes = [ci, vp, vp]
         _lib.oracle_fe_from_canonical_n.argtypes = [ci, vp, sz, vp]
         _lib.oracle_fr_div_linear.argtypes = [vp, sz, vp, vp, vp]
+        _lib.oracle_bh_iter.argtypes = [sz, vp]
+        _lib.oracle_permutation_z_polys.argtypes = [sz, vp, vp, sz, sz, vp, vp, vp]
+        _lib.oracle_permutation_z_polys_mt.argtypes = [sz, vp, vp, sz, sz, vp, vp, ci, vp]
         _lib.oracle_fe_to_canonical_n.argtypes = [ci, vp, sz, vp]
         _lib.oracle_g1_generator.argtypes = [vp]
         _lib.oracle_g1_is_on_curve.argtypes = [vp]
@@ -319,6 +322,27 @@ def fr_div_linear(coeffs, z):
     rem = np.zeros(4, dtype=np.uint64)
     lib().oracle_fr_div_linear(_ptr(coeffs), n, _ptr(z), _ptr(q) if n > 1 else None, _ptr(rem))
     return q, rem
+
+
+def bh_iter(num_vars: int) -> np.ndarray:
+    """BooleanHypercube::iter (util/arithmetic/bh.rs:118-125)."""
+    out = np.zeros(1 << num_vars, dtype=np.uint32)
+    lib().oracle_bh_iter(num_vars, _ptr(out))
+    return out
+
+
+def permutation_z_polys(num_chunks: int, values, sigmas, beta, gamma, num_threads: int = 1):
+    """backend/hyperplonk/prover.rs:252-345 -> list of num_chunks [2^k, 4] arrays."""
+    values = [_u64(v).reshape(-1, 4) for v in values]
+    sigmas = [_u64(v).reshape(-1, 4) for v in sigmas]
+    n = values[0].shape[0]
+    k = n.bit_length() - 1
+    vp_ = (ctypes.c_void_p * len(values))(*[v.ctypes.data for v in values])
+    sp_ = (ctypes.c_void_p * len(sigmas))(*[v.ctypes.data for v in sigmas])
+    out = np.zeros((num_chunks * n, 4), dtype=np.uint64)
+    lib().oracle_permutation_z_polys_mt(num_chunks, ctypes.cast(vp_, ctypes.c_void_p), ctypes.cast(sp_, ctypes.c_void_p), len(values), k,
+                                        _ptr(_u64(beta).reshape(4)), _ptr(_u64(gamma).reshape(4)), int(num_threads), _ptr(out))
+    return [out[c * n:(c + 1) * n].copy() for c in range(num_chunks)]
 
 
 def keccak256(data: bytes) -> bytes:

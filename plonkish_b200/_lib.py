@@ -45,6 +45,7 @@ EXPORTS = (
     "plonkish_cuda_msm_bn254_g1_batch_keep",
     "plonkish_cuda_fr_linear_combination",
     "plonkish_cuda_fr_div_linear",
+    "plonkish_cuda_permutation_z_polys_bn254",
     "plonkish_cuda_kzg_open_bn254",
     "plonkish_cuda_fixed_base_msm_bn254_g1",
     "plonkish_cuda_kzg_setup_eqs_bn254",
@@ -142,6 +143,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_msm_bn254_g1_resident.argtypes = [u64, u64, sz, vp]
     lib.plonkish_cuda_msm_bn254_g1_batch_keep.argtypes = [vp, sz, u64, sz, vp, vp]
     lib.plonkish_cuda_fr_linear_combination.argtypes = [vp, vp, sz, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_permutation_z_polys_bn254.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     lib.plonkish_cuda_fr_div_linear.argtypes = [u64, vp, ctypes.POINTER(u64), vp]
     lib.plonkish_cuda_kzg_open_bn254.argtypes = [u64, vp, vp, sz, vp, vp]
     lib.plonkish_cuda_fixed_base_msm_bn254_g1.argtypes = [ci, vp, vp, sz, vp]

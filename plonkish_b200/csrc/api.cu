@@ -2608,6 +2608,65 @@ extern "C" int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *
     return PLONKISH_CUDA_OK;
 }
 
+// permutation_z_polys (backend/hyperplonk/prover.rs:252-345): the grand-product polynomials HyperPlonk commits at
+// backend/hyperplonk.rs:251-252, from resident witness columns and permutation polynomials.  value_handles[i] /
+// sigma_handles[i]: the column polys[*poly] and its permutation polynomial for i < count (in the order of
+// pp.permutation_polys); num_chunks = pp.num_permutation_z_polys.  out_handles receives num_chunks resident polynomials.
+extern "C" int plonkish_cuda_permutation_z_polys_bn254(const uint64_t *value_handles, const uint64_t *sigma_handles, size_t count, size_t num_chunks,
+                                                       size_t num_vars, const void *beta_mont32, const void *gamma_mont32, uint64_t *out_handles) {
+    if (!value_handles || !sigma_handles || !beta_mont32 || !gamma_mont32 || !out_handles) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: null argument");
+    if (count == 0 || num_chunks == 0 || num_chunks > count) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: %zu polynomials in %zu chunks", count, num_chunks);
+    if (num_vars == 0 || num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: num_vars = %zu (1..28 supported)", num_vars);
+    const size_t chunk_size = (count + num_chunks - 1) / num_chunks;  // prover.rs:263
+    if (chunk_size > PK_PERM_MAX || num_chunks > PK_PERM_MAX) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: at most %d polynomials per chunk and %d chunks", PK_PERM_MAX, PK_PERM_MAX);
+    if ((count + chunk_size - 1) / chunk_size != num_chunks) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: %zu polynomials do not fill %zu chunks of %zu", count, num_chunks, chunk_size);
+    const size_t n = (size_t)1 << num_vars;
+    std::vector<ScalarsEntry> vals(count), sigs(count);
+    for (size_t i = 0; i < count; ++i) {
+        if (!lookup_scalars(value_handles[i], vals[i]) || !lookup_scalars(sigma_handles[i], sigs[i])) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: unknown scalars handle at %zu", i);
+        if (vals[i].n != n || sigs[i].n != n) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: polynomial %zu does not hold 2^%zu evaluations", i, num_vars);
+        if (vals[i].dev != vals[0].dev || sigs[i].dev != vals[0].dev) return fail(PLONKISH_CUDA_E_INVALID, "permutation_z_polys: polynomials live on different devices");
+    }
+    Ctx *c = ctx_for(vals[0].dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "permutation_z_polys: device %d not initialised", vals[0].dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t scratch_elems = pk_perm_z_scratch_elems(num_chunks, n);
+    void *work = nullptr;
+    int rc = pool_alloc(c, &work, (scratch_elems + 2 + 8) * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard work_guard{c, work};
+    std::vector<void *> outs(num_chunks, nullptr);
+    struct OutGuard { Ctx *c; std::vector<void *> &v; bool armed = true; ~OutGuard() { if (armed) for (void *p : v) pool_free(c, p); } } out_guard{c, outs};
+    for (size_t k = 0; k < num_chunks; ++k)
+        if ((rc = pool_alloc(c, &outs[k], n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    char *d_bg = (char *)work + scratch_elems * PLONKISH_CUDA_SCALAR_BYTES, *d_out_table = d_bg + 2 * PLONKISH_CUDA_SCALAR_BYTES;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    unsigned char bg[64];
+    memcpy(bg, beta_mont32, 32);
+    memcpy(bg + 32, gamma_mont32, 32);
+    CUDA_TRY(cudaMemcpyAsync(d_bg, bg, 64, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_out_table, outs.data(), num_chunks * sizeof(void *), cudaMemcpyHostToDevice, c->stream));
+    std::vector<PermArgs> chunks(num_chunks);
+    for (size_t k = 0; k < num_chunks; ++k) {
+        PermArgs &a = chunks[k];
+        memset(&a, 0, sizeof(a));
+        const size_t first = k * chunk_size;
+        a.count = (u32)(count - first < chunk_size ? count - first : chunk_size);
+        for (u32 i = 0; i < a.count; ++i) {
+            a.value[i] = (const uint4 *)vals[first + i].d_ptr;
+            a.sigma[i] = (const uint4 *)sigs[first + i].d_ptr;
+            a.id_offset[i] = (unsigned long long)(first + i) << num_vars;   // idx << num_vars, prover.rs:286
+        }
+    }
+    pk_enqueue_perm_z(chunks.data(), (u32)num_chunks, (u32)num_vars, d_bg, work, d_out_table, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out_guard.armed = false;
+    for (size_t k = 0; k < num_chunks; ++k) out_handles[k] = publish_scalars(c->dev, outs[k], n);
+    return PLONKISH_CUDA_OK;
+}
+
 // ============================================================== fixed-base MSM
 // fixed_base_msm (msm.rs:67-81) over a window table of one base (msm.rs:16-31) followed by
 // batch_normalize (kzg.rs:204-207, univariate/kzg.rs:196-199): out[i] = scalars[i] * base, affine.

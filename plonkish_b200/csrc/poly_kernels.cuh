@@ -466,6 +466,45 @@ __global__ void __launch_bounds__(128) k_perm_scatter(const uint4 *__restrict__ 
     }
 }
 
+// util/arithmetic/bh.rs:5-38: the primitive polynomial of every hypercube size.
+static const u32 PK_BH_PRIMITIVES[32] = {1u, 3u, 7u, 11u, 19u, 37u, 67u, 131u, 285u, 529u, 1033u, 2053u, 4179u, 8219u, 16427u, 32771u, 65581u, 131081u,
+                                         262183u, 524327u, 1048585u, 2097157u, 4194307u, 8388641u, 16777243u, 33554441u, 67108935u, 134217767u,
+                                         268435465u, 536870917u, 1073741907u, 2147483657u};
+// scratch of pk_enqueue_perm_z in 32-byte elements: products (nc * n) | scanned sequence | strip totals and their recursion
+inline size_t pk_perm_z_scratch_elems(size_t num_chunks, size_t n) {
+    const size_t m = num_chunks * n - num_chunks - 1;
+    const size_t strips = (m + PK_SCAN_STRIP - 1) / PK_SCAN_STRIP;
+    return num_chunks * n + m + 2 * strips + 256;
+}
+// chunks[k]: the permutation polynomials of chunk k; d_beta_gamma: beta, gamma (two elements, device); d_out_table: device
+// array of num_chunks output pointers (2^num_vars elements each).
+inline void pk_enqueue_perm_z(const PermArgs *chunks, u32 num_chunks, u32 num_vars, const void *d_beta_gamma, void *scratch, void *d_out_table,
+                              pk_stream_t stream) {
+    const size_t n = (size_t)1 << num_vars;
+    const size_t m = (size_t)num_chunks * n - num_chunks - 1;   // factors entering the flat z sequence (prover.rs:303-320)
+    const size_t strips = (m + PK_SCAN_STRIP - 1) / PK_SCAN_STRIP;
+    uint4 *d_products = (uint4 *)scratch;
+    uint4 *d_seq = d_products + 2 * (size_t)num_chunks * n;
+    uint4 *d_totals = d_seq + 2 * m;
+    PermSeq seq;
+    memset(&seq, 0, sizeof(seq));
+    seq.nc = num_chunks; seq.k = num_vars; seq.primitive = PK_BH_PRIMITIVES[num_vars];
+    const size_t pthreads = (n + PK_PERM_STRIP - 1) / PK_PERM_STRIP;
+    for (u32 k = 0; k < num_chunks; ++k) {
+        seq.product[k] = d_products + 2 * (size_t)k * n;
+        PK_LAUNCH(k_perm_products, dim3((unsigned)((pthreads + 127) / 128)), dim3(128), 0, stream, chunks[k], (const uint4 *)d_beta_gamma, n, d_products + 2 * (size_t)k * n);
+    }
+    if (m) {
+        PK_LAUNCH(k_perm_gather_scan, dim3((unsigned)((strips + 127) / 128)), dim3(128), 0, stream, seq, m, d_seq, d_totals);
+        if (strips > 1) {
+            pk_enqueue_prodscan(d_totals, strips, d_totals + 2 * strips, stream);
+            PK_LAUNCH(k_prodscan_fix, dim3((unsigned)((strips + 127) / 128)), dim3(128), 0, stream, d_seq, m, (const uint4 *)d_totals);
+        }
+    }
+    const size_t sthreads = (n + PK_SCAN_STRIP - 1) / PK_SCAN_STRIP;
+    PK_LAUNCH(k_perm_scatter, dim3((unsigned)((sthreads + 127) / 128)), dim3(128), 0, stream, (const uint4 *)d_seq, seq, n, (uint4 *const *)d_out_table);
+}
+
 // ------------------------------------------------------------- fixed-base MSM
 // Signed 16-bit windows: 16 windows cover 254 bits plus the carry, the table holds
 // d * 2^(16w) * base for d = 1..2^15 (16 x 32768 x 64 B = 32 MiB, L2 resident); the

@@ -284,6 +284,24 @@ def fr_linear_combination(polys: Sequence["ResidentScalars"], coeffs) -> "Reside
     return ResidentScalars._adopt(out.value, n, polys[0].device)
 
 
+def permutation_z_polys(num_chunks: int, values: Sequence["ResidentScalars"], sigmas: Sequence["ResidentScalars"], beta, gamma):
+    """permutation_z_polys (backend/hyperplonk/prover.rs:252-345) on resident polynomials: values[i] is the witness column of
+    permutation polynomial i, sigmas[i] the permutation polynomial; beta, gamma Montgomery limbs.  Returns num_chunks
+    ResidentScalars (the z polynomials committed at backend/hyperplonk.rs:251-252)."""
+    assert len(values) == len(sigmas) and len(values) > 0
+    n = values[0].n
+    num_vars = n.bit_length() - 1
+    vh = np.array([p.handle for p in values], dtype=np.uint64)
+    sh = np.array([p.handle for p in sigmas], dtype=np.uint64)
+    b = np.ascontiguousarray(beta, dtype=np.uint64).reshape(4)
+    g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+    out = np.zeros(num_chunks, dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_permutation_z_polys_bn254(vh.ctypes.data, sh.ctypes.data, len(values), num_chunks, num_vars, b.ctypes.data, g.ctypes.data,
+                                                            out.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_permutation_z_polys_bn254")
+    return [ResidentScalars._adopt(h, n, values[0].device) for h in out]
+
+
 def fr_div_linear(poly: "ResidentScalars", z):
     """poly / (X - z) on resident coefficients (poly/univariate.rs:144-168 for a linear divisor): returns
     (quotient as ResidentScalars of the same length, top coefficient zero; remainder = poly(z) as Montgomery limbs [4])."""

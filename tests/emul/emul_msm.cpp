@@ -63,6 +63,30 @@ void emul_dxyzz_madd(u32 *acc128, const u32 *pts64, u32 count) {
     memcpy(acc128, &a, 128);
 }
 
+// permutation_z_polys: values / sigmas are `count` arrays of 2^k elements; out receives num_chunks arrays of 2^k elements.
+void emul_permutation_z(const void *const *values, const void *const *sigmas, u32 count, u32 num_chunks, u32 k, const void *beta, const void *gamma, void *out) {
+    const size_t n = (size_t)1 << k;
+    const size_t chunk_size = (count + num_chunks - 1) / num_chunks;
+    std::vector<unsigned char> scratch(pk_perm_z_scratch_elems(num_chunks, n) * 32), bg(64);
+    memcpy(bg.data(), beta, 32);
+    memcpy(bg.data() + 32, gamma, 32);
+    std::vector<PermArgs> chunks(num_chunks);
+    std::vector<void *> outs(num_chunks);
+    for (u32 c = 0; c < num_chunks; ++c) {
+        PermArgs &a = chunks[c];
+        memset(&a, 0, sizeof(a));
+        const size_t first = c * chunk_size;
+        a.count = (u32)(count - first < chunk_size ? count - first : chunk_size);
+        for (u32 i = 0; i < a.count; ++i) {
+            a.value[i] = (const uint4 *)values[first + i];
+            a.sigma[i] = (const uint4 *)sigmas[first + i];
+            a.id_offset[i] = (unsigned long long)(first + i) << k;
+        }
+        outs[c] = (char *)out + (size_t)c * n * 32;
+    }
+    pk_enqueue_perm_z(chunks.data(), num_chunks, k, bg.data(), scratch.data(), outs.data(), 0);
+}
+
 // div_rem by (X - z): q receives n elements (q[n-1] = 0), rem one.
 void emul_div_linear(const u32 *c, uint64_t n, const u32 *z, u32 *q, u32 *rem) {
     std::vector<unsigned char> scratch((pk_horner_scratch_elems(n) + 16) * 32);
