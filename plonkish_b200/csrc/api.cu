@@ -76,6 +76,12 @@ struct Ctx {
     cudaEvent_t last_done = nullptr;  // end of the last enqueued MSM: orders arena reuse across streams
     bool has_last = false;
     DeviceBuffer arena, scalars, scalars2, bases_tmp, partials, batch_out, open_buf;
+    // per-proof temporaries that would otherwise come out of the pool in multi-GB pieces on every call (pool growth
+    // showed up as 40-80 ms swings between repetitions of one proof): `tmp` serves the eq table expansion, the division
+    // scratch and the grand-product scratch (one at a time: they run under mu, in stream order); `sc_block` backs ONE
+    // live sum-check state, a second concurrent state falls back to the pool
+    DeviceBuffer tmp, sc_block;
+    bool sc_block_busy = false;
     cudaEvent_t buf_free[2] = {};         // batch path: scalar buffer b may be overwritten again
     cudaEvent_t many_start = nullptr;     // many path: side lanes start after this point of the main stream
     struct Lane {                         // extra streams with their own scratch: small independent MSMs run side by side
@@ -426,7 +432,7 @@ extern "C" void plonkish_cuda_shutdown(void) {
         cudaSetDevice(c->dev);
         cudaDeviceSynchronize();
         cudaFree(c->arena.ptr); cudaFree(c->scalars.ptr); cudaFree(c->scalars2.ptr); cudaFree(c->bases_tmp.ptr); cudaFree(c->partials.ptr);
-        cudaFree(c->batch_out.ptr); cudaFree(c->open_buf.ptr);
+        cudaFree(c->batch_out.ptr); cudaFree(c->open_buf.ptr); cudaFree(c->tmp.ptr); cudaFree(c->sc_block.ptr);
         for (int i = 0; i < 2; ++i) cudaEventDestroy(c->buf_free[i]);
         cudaEventDestroy(c->many_start);
         for (auto &ln : c->lanes) {
@@ -2438,9 +2444,9 @@ extern "C" int plonkish_cuda_eq_table(int device, const void *y, size_t num_vars
     CUDA_TRY(cudaSetDevice(c->dev));
     const size_t n = (size_t)1 << num_vars, total = 2 * n - 1;
     void *all = nullptr, *out = nullptr;
-    int rc = pool_alloc(c, &all, (total + num_vars + 1) * PLONKISH_CUDA_SCALAR_BYTES);
+    int rc = grow(c->tmp, (total + num_vars + 1) * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
-    PoolGuard all_guard{c, all};
+    all = c->tmp.ptr;
     if ((rc = pool_alloc(c, &out, n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
     PoolGuard out_guard{c, out};
     void *d_y = (char *)all + total * PLONKISH_CUDA_SCALAR_BYTES;
@@ -2594,8 +2600,8 @@ extern "C" int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *
     if (rc) return rc;
     PoolGuard q_guard{c, q};
     const size_t scratch_elems = pk_horner_scratch_elems(n) + 16;
-    if ((rc = pool_alloc(c, &scratch, scratch_elems * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
-    PoolGuard s_guard{c, scratch};
+    if ((rc = grow(c->tmp, scratch_elems * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    scratch = c->tmp.ptr;
     char *zs = (char *)scratch, *rem = zs + 8 * PLONKISH_CUDA_SCALAR_BYTES, *work = zs + 16 * PLONKISH_CUDA_SCALAR_BYTES;
     if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
     CUDA_TRY(cudaMemcpyAsync(zs, z_mont32, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
@@ -2633,9 +2639,9 @@ extern "C" int plonkish_cuda_permutation_z_polys_bn254(const uint64_t *value_han
     CUDA_TRY(cudaSetDevice(c->dev));
     const size_t scratch_elems = pk_perm_z_scratch_elems(num_chunks, n);
     void *work = nullptr;
-    int rc = pool_alloc(c, &work, (scratch_elems + 2 + 8) * PLONKISH_CUDA_SCALAR_BYTES);
+    int rc = grow(c->tmp, (scratch_elems + 2 + 8) * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
-    PoolGuard work_guard{c, work};
+    work = c->tmp.ptr;
     std::vector<void *> outs(num_chunks, nullptr);
     struct OutGuard { Ctx *c; std::vector<void *> &v; bool armed = true; ~OutGuard() { if (armed) for (void *p : v) pool_free(c, p); } } out_guard{c, outs};
     for (size_t k = 0; k < num_chunks; ++k)
@@ -2860,6 +2866,8 @@ static std::map<uint64_t, SumcheckState> g_sumcheck;
 
 static void release_all_sumcheck() {  // caller holds g_mu
     for (auto &kv : g_sumcheck) {
+        Ctx *c = (size_t)kv.second.dev < g_ctx.size() ? g_ctx[kv.second.dev] : nullptr;
+        if (c && kv.second.block == c->sc_block.ptr) { c->sc_block_busy = false; continue; }  // freed with the context
         cudaSetDevice(kv.second.dev);
         cudaFree(kv.second.block);
     }
@@ -2913,8 +2921,14 @@ extern "C" int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t n
     const size_t half = n / 2, quarter = n / 4 ? n / 4 : 1;
     const size_t max_blocks = (size_t)c->sm_count * 16;
     const size_t elems = num_polys * (half + quarter) + max_blocks * PK_SC_MAX_DEGREE + PK_SC_MAX_DEGREE + 1 + num_polys;
-    int rc = pool_alloc(c, &st.block, elems * PLONKISH_CUDA_SCALAR_BYTES);
-    if (rc) return rc;
+    int rc;
+    if (!c->sc_block_busy) {
+        if ((rc = grow(c->sc_block, elems * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+        st.block = c->sc_block.ptr;
+        c->sc_block_busy = true;
+    } else if ((rc = pool_alloc(c, &st.block, elems * PLONKISH_CUDA_SCALAR_BYTES))) {
+        return rc;
+    }
     char *q = (char *)st.block;
     for (size_t p = 0; p < num_polys; ++p) { st.buf_a.push_back(q); q += half * 32; }
     for (size_t p = 0; p < num_polys; ++p) { st.buf_b.push_back(q); q += quarter * 32; }
@@ -3025,7 +3039,8 @@ extern "C" int plonkish_cuda_sumcheck_free(uint64_t state_handle) {
     if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_free: device %d not initialised", st.dev);
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->dev));
-    pool_free(c, st.block);
+    if (st.block == c->sc_block.ptr) c->sc_block_busy = false;  // the next state reuses it in stream order
+    else pool_free(c, st.block);
     return PLONKISH_CUDA_OK;
 }
 
