@@ -30,6 +30,11 @@ extern "C" {
     fn plonkish_cuda_scalars_release(handle: u64) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_batch_keep(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void, scalars_handles: *mut u64) -> c_int;
     fn plonkish_cuda_fr_linear_combination(handles: *const u64, coeffs: *const c_void, count: usize, n: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_fr_div_linear(handle: u64, z: *const c_void, out_quotient: *mut u64, out_rem: *mut c_void) -> c_int;
+    fn plonkish_cuda_scalars_register(device: c_int, scalars: *const c_void, n: usize, handle: *mut u64) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1_resident(scalars_handle: u64, bases_handle: u64, n: usize, out: *mut c_void) -> c_int;
+    fn plonkish_cuda_permutation_z_polys_bn254(values: *const u64, sigmas: *const u64, count: usize, num_chunks: usize, num_vars: usize,
+                                               beta: *const c_void, gamma: *const c_void, out_handles: *mut u64) -> c_int;
     fn plonkish_cuda_kzg_open_bn254(scalars_handle: u64, eq_handles: *const u64, point: *const c_void, num_vars: usize, out_comms: *mut c_void, out_eval: *mut c_void) -> c_int;
     fn plonkish_cuda_fixed_base_msm_bn254_g1(device: c_int, base: *const c_void, scalars: *const c_void, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_kzg_setup_eqs_bn254(device: c_int, g1: *const c_void, ss: *const c_void, num_vars: usize, handles_out: *mut u64) -> c_int;
@@ -368,6 +373,68 @@ pub fn linear_combination(polys: &[&ResidentPoly], coeffs: &[Fr]) -> ResidentPol
         "plonkish_cuda_fr_linear_combination",
     );
     ResidentPoly { handle, num_vars }
+}
+
+/// `permutation_z_polys` (backend/hyperplonk/prover.rs:252-345) on resident polynomials: `values[i]` is the witness column
+/// `polys[*poly]` of permutation polynomial i, `sigmas[i]` the permutation polynomial itself (in `pp.permutation_polys`
+/// order); returns `num_chunks` resident z polynomials, ready for `batch_commit` (hyperplonk.rs:251-252).
+pub fn permutation_z_polys(num_chunks: usize, values: &[&ResidentPoly], sigmas: &[&ResidentPoly], beta: &Fr, gamma: &Fr) -> Vec<ResidentPoly> {
+    assert_eq!(values.len(), sigmas.len());
+    let num_vars = values[0].num_vars;
+    let vh: Vec<u64> = values.iter().map(|p| p.handle).collect();
+    let sh: Vec<u64> = sigmas.iter().map(|p| p.handle).collect();
+    let mut out = vec![0u64; num_chunks];
+    check(
+        unsafe {
+            plonkish_cuda_permutation_z_polys_bn254(vh.as_ptr(), sh.as_ptr(), vh.len(), num_chunks, num_vars, beta as *const Fr as *const c_void,
+                                                    gamma as *const Fr as *const c_void, out.as_mut_ptr())
+        },
+        "plonkish_cuda_permutation_z_polys_bn254",
+    );
+    out.into_iter().map(|handle| ResidentPoly { handle, num_vars }).collect()
+}
+
+/// Coefficients of a univariate polynomial kept in HBM, for `UnivariateKzg::open` / `batch_open` (pcs/univariate/kzg.rs:264-354).
+pub struct ResidentCoeffs {
+    handle: u64,
+    len: usize,
+}
+impl Drop for ResidentCoeffs {
+    fn drop(&mut self) {
+        unsafe { plonkish_cuda_scalars_release(self.handle) };
+    }
+}
+impl ResidentCoeffs {
+    pub fn new(coeffs: &[Fr]) -> Self {
+        init();
+        let mut handle = 0u64;
+        check(unsafe { plonkish_cuda_scalars_register(0, coeffs.as_ptr() as *const c_void, coeffs.len(), &mut handle) }, "plonkish_cuda_scalars_register");
+        Self { handle, len: coeffs.len() }
+    }
+    /// `poly.div_rem(&(X - z))` (poly/univariate.rs:144-168): the quotient stays resident (same length, zero top coefficient).
+    pub fn div_linear(&self, z: &Fr) -> (ResidentCoeffs, Fr) {
+        let (mut q, mut rem) = (0u64, Fr::zero());
+        check(
+            unsafe { plonkish_cuda_fr_div_linear(self.handle, z as *const Fr as *const c_void, &mut q, &mut rem as *mut Fr as *mut c_void) },
+            "plonkish_cuda_fr_div_linear",
+        );
+        (ResidentCoeffs { handle: q, len: self.len }, rem)
+    }
+    /// `commit_coeffs` (pcs/univariate/kzg.rs:24-30) against a registered `powers_of_s_g1`.
+    pub fn commit(&self, powers_of_s_g1: &RegisteredBases) -> G1Affine {
+        assert!(self.len <= powers_of_s_g1.len);
+        let mut out = [0u8; 64];
+        check(
+            unsafe { plonkish_cuda_msm_bn254_g1_resident(self.handle, powers_of_s_g1.handle, self.len, out.as_mut_ptr() as *mut c_void) },
+            "plonkish_cuda_msm_bn254_g1_resident",
+        );
+        unsafe { std::mem::transmute(out) }
+    }
+    /// `UnivariateKzg::open` (kzg.rs:264-299): the quotient's commitment (what `write_commitment` takes) and poly(z).
+    pub fn open(&self, powers_of_s_g1: &RegisteredBases, z: &Fr) -> (G1Affine, Fr) {
+        let (quotient, eval) = self.div_linear(z);
+        (quotient.commit(powers_of_s_g1), eval)
+    }
 }
 
 /// `fixed_base_msm(window_size, &window_table(window_size, base), scalars)` followed by

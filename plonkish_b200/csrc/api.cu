@@ -276,7 +276,11 @@ public:
         {
             std::lock_guard<std::mutex> lk(mu_);
             src_ = (const char *)src; dst_ = (char *)dst; bytes_ = bytes; stream_ = stream; dev_ = dev;
-            npieces_ = (bytes + SLOT - 1) / SLOT; next_ = 0; done_ = 0; err_ = cudaSuccess;
+            // pieces shrink with the upload so that every copier gets a few and the first DMA starts early (a 4 MiB
+            // upload in 4 MiB pieces would be one thread's memcpy followed by one DMA)
+            size_t piece = (bytes / (4 * (size_t)nthreads_) + 0xffff) & ~(size_t)0xffff;
+            piece_ = piece < ((size_t)256 << 10) ? ((size_t)256 << 10) : (piece > SLOT ? SLOT : piece);
+            npieces_ = (bytes + piece_ - 1) / piece_; next_ = 0; done_ = 0; err_ = cudaSuccess;
             ++job_id_;
         }
         cv_work_.notify_all();
@@ -293,6 +297,13 @@ private:
     Stager() {
         unsigned hw = std::thread::hardware_concurrency();
         int t = hw >= 32 ? 8 : hw >= 16 ? 6 : hw >= 8 ? 4 : 2;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): the ranks share the host's cores
+            const long w = atol(e);
+            if (w > 1) {
+                const int per = (int)(hw / (unsigned long)w);
+                t = per < 2 ? 2 : (per < t ? per : t);
+            }
+        }
         if (const char *e = getenv("PLONKISH_CUDA_COPY_THREADS")) {
             const long v = atol(e);
             if (v >= 1 && v <= 64) t = (int)v;
@@ -351,8 +362,8 @@ private:
             }
             cudaError_t e = cudaSuccess;
             if (slot_dev_[s] >= 0) e = cudaEventSynchronize(slot_ev_[s][slot_dev_[s]]);
-            const size_t off = i * SLOT;
-            const size_t len = bytes_ - off < SLOT ? bytes_ - off : SLOT;
+            const size_t off = i * piece_;
+            const size_t len = bytes_ - off < piece_ ? bytes_ - off : piece_;
             memcpy(slots_[s], src_ + off, len);
             if (e == cudaSuccess) e = cudaMemcpyAsync(dst_ + off, slots_[s], len, cudaMemcpyHostToDevice, stream_);
             if (e == cudaSuccess) e = cudaEventRecord(slot_ev_[s][dev], stream_);
@@ -376,7 +387,7 @@ private:
     std::condition_variable cv_work_, cv_done_, cv_slot_;
     const char *src_ = nullptr;
     char *dst_ = nullptr;
-    size_t bytes_ = 0, npieces_ = 0, next_ = 0, done_ = 0;
+    size_t bytes_ = 0, piece_ = SLOT, npieces_ = 0, next_ = 0, done_ = 0;
     unsigned long long base_ = 0, job_id_ = 0;
     cudaStream_t stream_ = nullptr;
     int dev_ = 0;
