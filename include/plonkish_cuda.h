@@ -168,6 +168,22 @@ int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *z_mont32, u
  * evaluations each), num_chunks = num_permutation_z_polys; out_handles receives num_chunks resident polynomials. */
 int plonkish_cuda_permutation_z_polys_bn254(const uint64_t *value_handles, const uint64_t *sigma_handles, size_t count, size_t num_chunks,
                                             size_t num_vars, const void *beta_mont32, const void *gamma_mont32, uint64_t *out_handles);
+/* One table of a compiled sum-check expression.  The reference's evaluator keeps identity and Lagrange polynomials,
+ * constants and rotated queries implicit (piop/sum_check/classic.rs:40-75, 104-126; classic/eval.rs); a sub-expression of
+ * degree <= 1 such as w + beta * (offset + identity) + gamma (backend/hyperplonk/preprocessor.rs:153-165) is a
+ * multilinear polynomial itself, so it can be one explicit table with the same round values:
+ *   out[b] = constant + identity_coeff * b + sum_i coeffs[i] * poly_i[rotate(b, rotations[i])],  then out[rows[j]] += values[j]
+ * with rotate = BooleanHypercube::rotate (util/arithmetic/bh.rs:104-121).  poly_handles: `count` resident polynomials of
+ * 2^num_vars evaluations on `device` (count may be 0: identity, Lagrange and instance polynomials are sparse_rows /
+ * identity_coeff only); rotations may be null (all zero); constant / identity_coeff may be null (absent). */
+int plonkish_cuda_fr_affine_table(int device, size_t num_vars, const uint64_t *poly_handles, const int32_t *rotations, const void *coeffs_mont32,
+                                  size_t count, const void *constant_mont32, const void *identity_coeff_mont32, const uint64_t *sparse_rows,
+                                  const void *sparse_values_mont32, size_t sparse_count, uint64_t *out_handle);
+/* MultilinearPolynomial::evaluate (poly/multilinear.rs:137-156) of a resident polynomial at `count` points of num_vars
+ * Montgomery Fr each (points_mont32: count x num_vars x 32 B): the evaluations prove_sum_check needs at the rotated
+ * points (backend/hyperplonk/prover.rs:392-400 through evaluate_for_rotation, poly/multilinear.rs:191-263).
+ * out_evals_mont32: count x 32 B. */
+int plonkish_cuda_fr_evaluate(uint64_t scalars_handle, const void *points_mont32, size_t num_vars, size_t count, void *out_evals_mont32);
 /* MultilinearKzg::open on a resident polynomial of 2^num_vars evaluations
  * (pcs/multilinear/kzg.rs:276-302): `quotients` (pcs/multilinear.rs:72-107) runs in HBM and
  * the num_vars quotient MSMs (kzg.rs:291-293) read their scalars from there.  eq_handles[i] =

@@ -12,6 +12,8 @@ from .msm import (  # noqa: F401
     variable_base_msm_batch_keep,
     fr_linear_combination,
     fr_div_linear,
+    fr_affine_table,
+    fr_evaluate,
     permutation_z_polys,
     kzg_open_resident,
     eq_table,

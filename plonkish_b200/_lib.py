@@ -46,6 +46,8 @@ EXPORTS = (
     "plonkish_cuda_fr_linear_combination",
     "plonkish_cuda_fr_div_linear",
     "plonkish_cuda_permutation_z_polys_bn254",
+    "plonkish_cuda_fr_affine_table",
+    "plonkish_cuda_fr_evaluate",
     "plonkish_cuda_kzg_open_bn254",
     "plonkish_cuda_fixed_base_msm_bn254_g1",
     "plonkish_cuda_kzg_setup_eqs_bn254",
@@ -145,6 +147,8 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_fr_linear_combination.argtypes = [vp, vp, sz, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_permutation_z_polys_bn254.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     lib.plonkish_cuda_fr_div_linear.argtypes = [u64, vp, ctypes.POINTER(u64), vp]
+    lib.plonkish_cuda_fr_affine_table.argtypes = [ci, sz, vp, vp, vp, sz, vp, vp, vp, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_fr_evaluate.argtypes = [u64, vp, sz, sz, vp]
     lib.plonkish_cuda_kzg_open_bn254.argtypes = [u64, vp, vp, sz, vp, vp]
     lib.plonkish_cuda_fixed_base_msm_bn254_g1.argtypes = [ci, vp, vp, sz, vp]
     lib.plonkish_cuda_kzg_setup_eqs_bn254.argtypes = [ci, vp, vp, sz, vp]

@@ -2686,6 +2686,117 @@ extern "C" int plonkish_cuda_permutation_z_polys_bn254(const uint64_t *value_han
     return PLONKISH_CUDA_OK;
 }
 
+// One table of the compiled sum-check expression (plonkish_b200/expression.py; k_fr_affine in poly_kernels.cuh):
+//   out[b] = constant + identity_coeff * b + sum_i coeffs[i] * poly_i[rotate(b, rotations[i])],  then out[rows[j]] += values[j].
+// Covers what the reference's evaluator keeps implicit (piop/sum_check/classic.rs:40-75, 104-126): identity and Lagrange
+// polynomials, constants inside a linear factor such as w + beta * id + gamma (backend/hyperplonk/preprocessor.rs:153-165),
+// rotated queries (rotation_map, util/arithmetic/bh.rs:104-121, 135-137) and instance polynomials
+// (backend/hyperplonk/prover.rs:32-48).  Null pointers switch the constant / the identity term off.
+extern "C" int plonkish_cuda_fr_affine_table(int device, size_t num_vars, const uint64_t *poly_handles, const int32_t *rotations, const void *coeffs_mont32,
+                                             size_t count, const void *constant_mont32, const void *identity_coeff_mont32, const uint64_t *sparse_rows,
+                                             const void *sparse_values_mont32, size_t sparse_count, uint64_t *out_handle) {
+    if (!out_handle || (count && (!poly_handles || !coeffs_mont32)) || (sparse_count && (!sparse_rows || !sparse_values_mont32)))
+        return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: null argument");
+    if (num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: num_vars = %zu exceeds 28", num_vars);
+    const size_t n = (size_t)1 << num_vars;
+    static const unsigned char FR_ONE_BYTES[32] = {0xfb, 0xff, 0xff, 0x4f, 0x1c, 0x34, 0x96, 0xac, 0x29, 0xcd, 0x60, 0x9f, 0x95, 0x76, 0xfc, 0x36,
+                                                   0x2e, 0x46, 0x79, 0x78, 0x6f, 0xa3, 0x6e, 0x66, 0x2f, 0xdf, 0x07, 0x9a, 0xc1, 0x77, 0x0a, 0x0e};
+    std::vector<ScalarsEntry> es(count);
+    for (size_t i = 0; i < count; ++i) {
+        if (!lookup_scalars(poly_handles[i], es[i])) return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: unknown handle %llu", (unsigned long long)poly_handles[i]);
+        if (es[i].n != n) return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: polynomial %zu holds %zu evaluations, not 2^%zu", i, es[i].n, num_vars);
+        if (es[i].dev != device) return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: polynomial %zu lives on device %d, not %d", i, es[i].dev, device);
+        if (rotations && (size_t)(rotations[i] < 0 ? -rotations[i] : rotations[i]) > num_vars)
+            return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: rotation %d exceeds num_vars = %zu", rotations[i], num_vars);  // classic.rs:42
+    }
+    for (size_t j = 0; j < sparse_count; ++j)
+        if (sparse_rows[j] >= n) return fail(PLONKISH_CUDA_E_INVALID, "fr_affine_table: row %llu outside 2^%zu", (unsigned long long)sparse_rows[j], num_vars);
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_affine_table: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard d_guard{c, d};
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)c->sm_count * 8) blocks = (size_t)c->sm_count * 8;
+    // the first launch writes, further launches (more than PK_AFFINE_MAX sources) add their sources to it through a
+    // unit-coefficient read of the output itself
+    size_t done = 0;
+    bool first = true;
+    do {
+        AffineArgs a;
+        memset(&a, 0, sizeof(a));
+        a.num_vars = (u32)num_vars; a.primitive = PK_BH_PRIMITIVES[num_vars]; a.x_inv = PK_BH_X_INVS[num_vars];
+        u32 slot = 0;
+        if (first) {
+            if (constant_mont32) { a.has_constant = 1; memcpy(a.constant.l, constant_mont32, 32); }
+            if (identity_coeff_mont32) { a.has_id = 1; memcpy(a.id_coeff.l, identity_coeff_mont32, 32); }
+        } else {
+            a.poly[0] = (const uint4 *)d; a.rotation[0] = 0;
+            memcpy(a.coeff[0].l, FR_ONE_BYTES, 32);
+            slot = 1;
+        }
+        for (; slot < PK_AFFINE_MAX && done < count; ++slot, ++done) {
+            a.poly[slot] = (const uint4 *)es[done].d_ptr;
+            a.rotation[slot] = rotations ? rotations[done] : 0;
+            memcpy(a.coeff[slot].l, (const char *)coeffs_mont32 + done * PLONKISH_CUDA_SCALAR_BYTES, 32);
+            if (memcmp(a.coeff[slot].l, FR_ONE_BYTES, 32) != 0) a.has_coeff_mask |= 1u << slot;
+        }
+        a.count = slot;
+        PK_LAUNCH(k_fr_affine, dim3((unsigned)blocks), dim3(256), 0, c->stream, a, n, (uint4 *)d);
+        first = false;
+    } while (done < count);
+    if (sparse_count) {
+        if ((rc = grow(c->tmp, sparse_count * (PLONKISH_CUDA_SCALAR_BYTES + sizeof(unsigned long long)) + 64))) return rc;
+        char *d_vals = (char *)c->tmp.ptr, *d_rows = d_vals + sparse_count * PLONKISH_CUDA_SCALAR_BYTES;
+        CUDA_TRY(cudaMemcpyAsync(d_vals, sparse_values_mont32, sparse_count * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_rows, sparse_rows, sparse_count * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        PK_LAUNCH(k_fr_sparse_add, dim3(1), dim3(32), 0, c->stream, (uint4 *)d, (const unsigned long long *)d_rows, (const uint4 *)d_vals, (u32)sparse_count);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
+// MultilinearPolynomial::evaluate (poly/multilinear.rs:137-156) on a resident polynomial at `count` points of num_vars
+// Montgomery Fr each — what prove_sum_check asks for through evaluate_for_rotation (prover.rs:392-400,
+// poly/multilinear.rs:191-263: the polynomial at the 2^distance points of rotation_eval_points).  The variables are fixed
+// from the highest down like the remainder of `quotients` (multilinear.rs:85-97); the value is the same field element in
+// any order.  out_evals: count Montgomery Fr.
+extern "C" int plonkish_cuda_fr_evaluate(uint64_t scalars_handle, const void *points_mont32, size_t num_vars, size_t count, void *out_evals_mont32) {
+    if (count == 0) return PLONKISH_CUDA_OK;
+    if (!out_evals_mont32 || (num_vars && !points_mont32)) return fail(PLONKISH_CUDA_E_INVALID, "fr_evaluate: null argument");
+    if (num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "fr_evaluate: num_vars = %zu exceeds 28", num_vars);
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "fr_evaluate: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    const size_t n = (size_t)1 << num_vars;
+    if (se.n != n) return fail(PLONKISH_CUDA_E_INVALID, "fr_evaluate: polynomial holds %zu evaluations, points have %zu variables", se.n, num_vars);  // multilinear.rs:138
+    Ctx *c = ctx_for(se.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_evaluate: device %d not initialised", se.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc;
+    const size_t q_elems = n, ra = n / 2 + 1, rb = n / 4 + 1;
+    if ((rc = grow(c->open_buf, (q_elems + ra + rb + count * (num_vars + 1) + 2) * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    char *base = (char *)c->open_buf.ptr;
+    void *q = base, *rem_a = base + q_elems * 32, *rem_b = base + (q_elems + ra) * 32;
+    char *d_points = base + (q_elems + ra + rb) * 32, *d_evals = d_points + count * num_vars * 32;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_points, points_mont32, count * num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    for (size_t p = 0; p < count; ++p)
+        pk_enqueue_quotients(se.d_ptr, (u32)num_vars, d_points + p * num_vars * 32, q, rem_a, rem_b, d_evals + p * 32, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned char> host(count * PLONKISH_CUDA_SCALAR_BYTES);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), d_evals, host.size(), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_evals_mont32, host.data(), host.size());
+    return PLONKISH_CUDA_OK;
+}
+
 // ============================================================== fixed-base MSM
 // fixed_base_msm (msm.rs:67-81) over a window table of one base (msm.rs:16-31) followed by
 // batch_normalize (kzg.rs:204-207, univariate/kzg.rs:196-199): out[i] = scalars[i] * base, affine.

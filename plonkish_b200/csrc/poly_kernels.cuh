@@ -505,6 +505,50 @@ inline void pk_enqueue_perm_z(const PermArgs *chunks, u32 num_chunks, u32 num_va
     PK_LAUNCH(k_perm_scatter, dim3((unsigned)((sthreads + 127) / 128)), dim3(128), 0, stream, (const uint4 *)d_seq, seq, n, (uint4 *const *)d_out_table);
 }
 
+// ------------------------------------------------- affine tables for the sum-check expression compiler
+// The reference's sum check keeps identity / Lagrange polynomials, constants and rotated queries implicit in its
+// expression evaluator (piop/sum_check/classic.rs:40-75, 104-126; classic/eval.rs).  Every sub-expression of degree <= 1
+//     constant + id_coeff * identity + sum_i coeff_i * poly_i(rotated by r_i)         (+ a few single-row terms: Lagrange)
+// is a multilinear polynomial itself and fixing a variable commutes with the sum, so the compiler (plonkish_b200/
+// expression.py) materialises it as one table: the round values stay the same field elements.  The row of a rotated
+// query is BooleanHypercube::rotate (util/arithmetic/bh.rs:104-121), what classic.rs:105-125 gathers through
+// rotation_map.  HBM bound: 32 B written + 32 B per source read.
+#define PK_AFFINE_MAX 8
+static const u32 PK_BH_X_INVS[32] = {0u, 1u, 3u, 5u, 9u, 18u, 33u, 65u, 142u, 264u, 516u, 1026u, 2089u, 4109u, 8213u, 16385u, 32790u, 65540u,
+                                     131091u, 262163u, 524292u, 1048578u, 2097153u, 4194320u, 8388621u, 16777220u, 33554467u, 67108883u,
+                                     134217732u, 268435458u, 536870953u, 1073741828u};
+struct AffineArgs {
+    const uint4 *poly[PK_AFFINE_MAX];
+    fe coeff[PK_AFFINE_MAX];
+    int rotation[PK_AFFINE_MAX];
+    fe constant, id_coeff;  // Montgomery Fr
+    u32 count, has_constant, has_id, has_coeff_mask;  // bit i of has_coeff_mask: coeff[i] != 1
+    u32 num_vars, primitive, x_inv;
+};
+PK_HD u32 bh_rotate(u32 b, int rotation, u32 k, u32 primitive, u32 x_inv) {  // bh.rs:104-121, 141-153
+    for (; rotation > 0; --rotation) b = bh_next(b, k, primitive);
+    for (; rotation < 0; ++rotation) b = (b >> 1) ^ ((b & 1u) * x_inv);
+    return b;
+}
+__global__ void __launch_bounds__(256) k_fr_affine(AffineArgs a, size_t n, uint4 *out) {  // `out` may be a source too (unrotated)
+    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+        fe acc = a.has_constant ? a.constant : fe_zero();
+        if (a.has_id) acc = fr_add(acc, fr_mul(a.id_coeff, fr_from_u64(j)));
+        for (u32 i = 0; i < a.count; ++i) {
+            const size_t row = a.rotation[i] ? (size_t)bh_rotate((u32)j, a.rotation[i], a.num_vars, a.primitive, a.x_inv) : j;
+            const fe v = load_fe_plain(a.poly[i] + 2 * row);
+            acc = fr_add(acc, ((a.has_coeff_mask >> i) & 1u) ? fr_mul(a.coeff[i], v) : v);
+        }
+        store_fe(out + 2 * j, acc);
+    }
+}
+// out[rows[i]] += values[i] (Lagrange terms, instance polynomials: a handful of rows; rows are distinct or serialised by
+// the single thread).
+__global__ void k_fr_sparse_add(uint4 *__restrict__ out, const unsigned long long *__restrict__ rows, const uint4 *__restrict__ values, u32 count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (u32 i = 0; i < count; ++i) store_fe(out + 2 * rows[i], fr_add(load_fe_plain(out + 2 * rows[i]), load_fe_plain(values + 2 * (size_t)i)));
+}
+
 // ------------------------------------------------------------- fixed-base MSM
 // Signed 16-bit windows: 16 windows cover 254 bits plus the carry, the table holds
 // d * 2^(16w) * base for d = 1..2^15 (16 x 32768 x 64 B = 32 MiB, L2 resident); the

@@ -302,6 +302,40 @@ def permutation_z_polys(num_chunks: int, values: Sequence["ResidentScalars"], si
     return [ResidentScalars._adopt(h, n, values[0].device) for h in out]
 
 
+def fr_affine_table(num_vars: int, polys: Sequence["ResidentScalars"] = (), coeffs=None, rotations: Optional[Sequence[int]] = None, constant=None,
+                    identity_coeff=None, sparse_rows: Sequence[int] = (), sparse_values=None, device: int = 0) -> "ResidentScalars":
+    """One table of a compiled sum-check expression (plonkish_cuda_fr_affine_table):
+    out[b] = constant + identity_coeff * b + sum_i coeffs[i] * polys[i][rotate(b, rotations[i])], then out[rows[j]] += values[j].
+    coeffs / constant / identity_coeff / sparse_values are Montgomery limbs; rotate is BooleanHypercube::rotate
+    (util/arithmetic/bh.rs:104-121).  What the reference's sum check keeps implicit (piop/sum_check/classic.rs:40-75, 104-126)."""
+    count = len(polys)
+    hs = np.array([p.handle for p in polys] or [0], dtype=np.uint64)
+    cs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(count, 4) if count else np.zeros((1, 4), dtype=np.uint64)
+    rot = np.array(list(rotations) if rotations is not None else [0] * count or [0], dtype=np.int32)
+    assert not count or rot.shape[0] == count, "one rotation per polynomial"
+    const = None if constant is None else np.ascontiguousarray(constant, dtype=np.uint64).reshape(4)
+    idc = None if identity_coeff is None else np.ascontiguousarray(identity_coeff, dtype=np.uint64).reshape(4)
+    rows = np.array(list(sparse_rows) or [0], dtype=np.uint64)
+    vals = np.ascontiguousarray(sparse_values, dtype=np.uint64).reshape(len(sparse_rows), 4) if len(sparse_rows) else np.zeros((1, 4), dtype=np.uint64)
+    out = ctypes.c_uint64(0)
+    rc = _lib.lib().plonkish_cuda_fr_affine_table(device if not count else polys[0].device, num_vars, hs.ctypes.data, rot.ctypes.data, cs.ctypes.data, count,
+                                                  None if const is None else const.ctypes.data, None if idc is None else idc.ctypes.data,
+                                                  rows.ctypes.data, vals.ctypes.data, len(sparse_rows), ctypes.byref(out))
+    _lib.check(rc, "plonkish_cuda_fr_affine_table")
+    return ResidentScalars._adopt(out.value, 1 << num_vars, device if not count else polys[0].device)
+
+
+def fr_evaluate(poly: "ResidentScalars", points) -> np.ndarray:
+    """MultilinearPolynomial::evaluate (poly/multilinear.rs:137-156) of a resident polynomial at each of `points`
+    ([count, num_vars, 4] Montgomery Fr); returns [count, 4] Montgomery limbs."""
+    num_vars = poly.n.bit_length() - 1
+    pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, max(num_vars, 1), 4) if num_vars else np.zeros((len(points), 1, 4), dtype=np.uint64)
+    count = pts.shape[0]
+    out = np.zeros((count, 4), dtype=np.uint64)
+    _lib.check(_lib.lib().plonkish_cuda_fr_evaluate(poly.handle, pts.ctypes.data, num_vars, count, out.ctypes.data), "plonkish_cuda_fr_evaluate")
+    return out
+
+
 def fr_div_linear(poly: "ResidentScalars", z):
     """poly / (X - z) on resident coefficients (poly/univariate.rs:144-168 for a linear divisor): returns
     (quotient as ResidentScalars of the same length, top coefficient zero; remainder = poly(z) as Montgomery limbs [4])."""

@@ -290,6 +290,25 @@ void emul_sumcheck_round(const void *const *polys, u32 num_polys, u32 n, const v
     std::vector<fe> partials((size_t)sm_count * 16 * PK_SC_MAX_DEGREE + 8);
     pk_enqueue_sumcheck_round(ps, ex, n / 2, partials.data(), out, sm_count, 0);
 }
+// ---- affine tables of the sum-check compiler (poly_kernels.cuh k_fr_affine / k_fr_sparse_add)
+void emul_fr_affine(const void *const *polys, const int *rotations, const void *coeffs, u32 count, u32 num_vars, const void *constant,
+                    const void *id_coeff, const unsigned long long *rows, const void *values, u32 sparse_count, void *out) {
+    static const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    AffineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.num_vars = num_vars; a.primitive = PK_BH_PRIMITIVES[num_vars]; a.x_inv = PK_BH_X_INVS[num_vars];
+    a.count = count;
+    if (constant) { a.has_constant = 1; memcpy(a.constant.l, constant, 32); }
+    if (id_coeff) { a.has_id = 1; memcpy(a.id_coeff.l, id_coeff, 32); }
+    for (u32 i = 0; i < count; ++i) {
+        a.poly[i] = (const uint4 *)polys[i];
+        a.rotation[i] = rotations[i];
+        memcpy(a.coeff[i].l, (const char *)coeffs + (size_t)i * 32, 32);
+        if (memcmp(a.coeff[i].l, FR_ONE, 32) != 0) a.has_coeff_mask |= 1u << i;
+    }
+    PK_LAUNCH(k_fr_affine, dim3(3), dim3(64), 0, 0, a, (size_t)1 << num_vars, (uint4 *)out);
+    if (sparse_count) PK_LAUNCH(k_fr_sparse_add, dim3(1), dim3(32), 0, 0, (uint4 *)out, rows, (const uint4 *)values, sparse_count);
+}
 void emul_sumcheck_fold(const void *const *polys, void *const *outs, u32 num_polys, u32 n, const void *challenge, u32 sm_count) {
     SumcheckFoldArgs a;
     memset(&a, 0, sizeof(a));
