@@ -600,6 +600,80 @@ void oracle_fr_linear_combination(const ofe_t *const *polys, const ofe_t *coeffs
     }
 }
 
+/* Element-wise Fr vector operations on all host threads (bench input generation and the host-side tables of the
+ * compiled sum-check expression): op 0: a + b, 1: a - b, 2: a * b;
+ * oracle_fr_affine: out[j] = constant + id_coeff * j + sum_i coeffs[i] * polys[i][rows_i ? rows_i[j] : j] — the explicit
+ * form of a linear factor of the zero-check expression (backend/hyperplonk/preprocessor.rs:153-165) with its identity
+ * polynomial (piop/sum_check/classic.rs:92) and rotated queries (classic.rs:105-125). */
+typedef struct { int op; const ofe_t *a, *b; size_t n; ofe_t *out; } vec_task_t;
+static void *vec_task_run(void *arg) {
+    vec_task_t *t = (vec_task_t *)arg;
+    for (size_t j = 0; j < t->n; ++j) {
+        if (t->op == 0) fe_add(FR, t->a[j].l, t->b[j].l, t->out[j].l);
+        else if (t->op == 1) fe_sub(FR, t->a[j].l, t->b[j].l, t->out[j].l);
+        else mont_mul(FR, t->a[j].l, t->b[j].l, t->out[j].l);
+    }
+    return NULL;
+}
+void oracle_fr_vec_op(int op, const ofe_t *a, const ofe_t *b, size_t n, int num_threads, ofe_t *out) {
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > n) num_threads = n ? (int)n : 1;
+    const size_t per = (n + num_threads - 1) / num_threads;
+    vec_task_t *tasks = (vec_task_t *)calloc(num_threads, sizeof(vec_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+    for (int t = 0; t < num_threads; ++t) {
+        const size_t first = (size_t)t * per;
+        const size_t count = first >= n ? 0 : (first + per <= n ? per : n - first);
+        vec_task_t k = {op, a + first, b + first, count, out + first};
+        tasks[t] = k;
+        pthread_create(&threads[t], NULL, vec_task_run, &tasks[t]);
+    }
+    for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+    free(tasks); free(threads);
+}
+typedef struct {
+    const ofe_t *const *polys; const uint32_t *const *rows; const ofe_t *coeffs; size_t count;
+    const ofe_t *constant, *id_coeff; size_t first, n; ofe_t *out;
+} aff_task_t;
+static void *aff_task_run(void *arg) {
+    aff_task_t *t = (aff_task_t *)arg;
+    for (size_t j = t->first; j < t->first + t->n; ++j) {
+        ofe_t acc, tmp;
+        memset(&acc, 0, sizeof(acc));
+        if (t->constant) acc = *t->constant;
+        if (t->id_coeff) {
+            uint64_t c[4] = {(uint64_t)j, 0, 0, 0};
+            oracle_fe_from_canonical(1, c, &tmp);
+            mont_mul(FR, tmp.l, t->id_coeff->l, tmp.l);
+            fe_add(FR, acc.l, tmp.l, acc.l);
+        }
+        for (size_t i = 0; i < t->count; ++i) {
+            const size_t row = (t->rows && t->rows[i]) ? t->rows[i][j] : j;
+            mont_mul(FR, t->coeffs[i].l, t->polys[i][row].l, tmp.l);
+            fe_add(FR, acc.l, tmp.l, acc.l);
+        }
+        t->out[j] = acc;
+    }
+    return NULL;
+}
+void oracle_fr_affine(const ofe_t *const *polys, const uint32_t *const *rows, const ofe_t *coeffs, size_t count, const ofe_t *constant,
+                      const ofe_t *id_coeff, size_t n, int num_threads, ofe_t *out) {
+    if (num_threads < 1) num_threads = 1;
+    if ((size_t)num_threads > n) num_threads = n ? (int)n : 1;
+    const size_t per = (n + num_threads - 1) / num_threads;
+    aff_task_t *tasks = (aff_task_t *)calloc(num_threads, sizeof(aff_task_t));
+    pthread_t *threads = (pthread_t *)calloc(num_threads, sizeof(pthread_t));
+    for (int t = 0; t < num_threads; ++t) {
+        const size_t first = (size_t)t * per;
+        const size_t cnt = first >= n ? 0 : (first + per <= n ? per : n - first);
+        aff_task_t k = {polys, rows, coeffs, count, constant, id_coeff, first, cnt, out};
+        tasks[t] = k;
+        pthread_create(&threads[t], NULL, aff_task_run, &tasks[t]);
+    }
+    for (int t = 0; t < num_threads; ++t) pthread_join(threads[t], NULL);
+    free(tasks); free(threads);
+}
+
 /* pcs/multilinear/kzg.rs:174-193: eqs[0] = [1]; eqs[k+1] = [e - s_k*e for e in eqs[k]] ++ [s_k*e ...].
  * out holds 2^(num_vars+1) - 1 scalars, slice k at offset 2^k - 1 (the flat_map order of :199). */
 void oracle_kzg_eq_scalars(const ofe_t *ss, size_t num_vars, ofe_t *out) {

@@ -115,6 +115,9 @@ void oracle_fix_var(const ofe_t *evals, size_t n, const ofe_t *x, ofe_t *out);
 void oracle_sumcheck_round_mt(const ofe_t *const *polys, size_t num_polys, size_t size, const ofe_t *coeffs,
                               const uint32_t *offsets, const uint32_t *term_polys, size_t num_terms, int common,
                               size_t degree, int num_threads, ofe_t *out);
+void oracle_fr_vec_op(int op, const ofe_t *a, const ofe_t *b, size_t n, int num_threads, ofe_t *out);
+void oracle_fr_affine(const ofe_t *const *polys, const uint32_t *const *rows, const ofe_t *coeffs, size_t count, const ofe_t *constant,
+                      const ofe_t *id_coeff, size_t n, int num_threads, ofe_t *out);
 void oracle_fix_var_mt(const ofe_t *evals, size_t n, const ofe_t *x, int num_threads, ofe_t *out);
 
 /* Keccak256 (original Keccak padding) as used by Keccak256Transcript (util/transcript.rs:100-131, util/hash.rs:5-8). */

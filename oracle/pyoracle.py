@@ -76,6 +76,8 @@ def lib() -> ctypes.CDLL:
         _lib.oracle_fix_var.argtypes = [vp, sz, vp, vp]
         _lib.oracle_sumcheck_round_mt.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, sz, ci, vp]
         _lib.oracle_fix_var_mt.argtypes = [vp, sz, vp, ci, vp]
+        _lib.oracle_fr_vec_op.argtypes = [ci, vp, vp, sz, ci, vp]
+        _lib.oracle_fr_affine.argtypes = [vp, vp, vp, sz, vp, vp, sz, ci, vp]
         _lib.oracle_keccak256.argtypes = [ctypes.c_char_p, sz, vp]
     return _lib
 
@@ -234,6 +236,34 @@ def fr_linear_combination(polys, coeffs) -> np.ndarray:
     ptrs = (ctypes.c_void_p * len(polys))(*[p.ctypes.data for p in polys])
     out = np.zeros((n, 4), dtype=np.uint64)
     lib().oracle_fr_linear_combination(ctypes.cast(ptrs, ctypes.c_void_p), _ptr(coeffs), len(polys), n, _ptr(out))
+    return out
+
+
+def fr_vec_op(op: str, a, b, num_threads: int | None = None) -> np.ndarray:
+    """Element-wise a + b / a - b / a * b over [n, 4] Montgomery Fr arrays on the host threads."""
+    a, b = _u64(a).reshape(-1, 4), _u64(b).reshape(-1, 4)
+    assert a.shape == b.shape
+    out = np.zeros_like(a)
+    lib().oracle_fr_vec_op({"add": 0, "sub": 1, "mul": 2}[op], _ptr(a), _ptr(b), a.shape[0], int(num_threads or host_threads()), _ptr(out))
+    return out
+
+
+def fr_affine(n: int, polys=(), coeffs=None, rows=None, constant=None, id_coeff=None, num_threads: int | None = None) -> np.ndarray:
+    """out[j] = constant + id_coeff * j + sum_i coeffs[i] * polys[i][rows[i][j] if rows[i] is not None else j]: one
+    linear factor of a zero-check expression as an explicit table (preprocessor.rs:153-165; classic.rs:92, 105-125).
+    rows[i]: uint32 row map of a rotated query (BooleanHypercube::rotation_map) or None."""
+    polys = [_u64(p).reshape(-1, 4) for p in polys]
+    count = len(polys)
+    assert all(p.shape[0] == n for p in polys)
+    cs = _u64(coeffs).reshape(count, 4) if count else np.zeros((1, 4), dtype=np.uint64)
+    ptrs = (ctypes.c_void_p * max(count, 1))(*[p.ctypes.data for p in polys])
+    maps = [None if rows is None or rows[i] is None else np.ascontiguousarray(rows[i], dtype=np.uint32) for i in range(count)]
+    rptrs = (ctypes.c_void_p * max(count, 1))(*[None if m is None else m.ctypes.data for m in maps])
+    const = None if constant is None else _u64(constant).reshape(4)
+    idc = None if id_coeff is None else _u64(id_coeff).reshape(4)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    lib().oracle_fr_affine(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(rptrs, ctypes.c_void_p), _ptr(cs), count,
+                           None if const is None else _ptr(const), None if idc is None else _ptr(idc), n, int(num_threads or host_threads()), _ptr(out))
     return out
 
 

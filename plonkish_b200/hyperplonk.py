@@ -383,10 +383,18 @@ def prove_sum_check(num_instance_poly: int, expression: Expression, claimed_sum:
     return points(queries, x), evals
 
 
-def prove(pp: HyperPlonkProverParam, circuit, transcript) -> None:
+def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] = None) -> None:
     """HyperPlonk::prove (hyperplonk.rs:164-291).  circuit: .instances() -> canonical integers per instance column,
     .synthesize(round, challenges) -> witness polynomials of that round as [2^k, 4] Montgomery arrays (PlonkishCircuit,
-    backend.rs:125-133).  The proof goes to `transcript` (Keccak256Transcript)."""
+    backend.rs:125-133).  The proof goes to `transcript` (Keccak256Transcript).  marks: optional list receiving
+    (label, perf_counter()) at the reference's timer boundaries (hyperplonk.rs:192-288)."""
+    import time
+
+    def mark(label: str) -> None:
+        if marks is not None:
+            marks.append((label, time.perf_counter()))
+
+    mark("start")
     if pp.lookups:
         raise ValueError("HyperPlonk::prove: lookup arguments have no GPU producers in this library (prover.rs:50-250); no CPU fallback")
     instances = circuit.instances()
@@ -410,6 +418,7 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript) -> None:
             transcript.write_commitments(comms)
             witness_polys.extend(resident)
             challenges.extend(transcript.squeeze_challenges(num_c))
+        mark("witness batch_commit")
         polys = inst_polys + pp.preprocess_polys + witness_polys
         # Round n (no lookups: lookup_m_polys is empty and nothing is written, hyperplonk.rs:213-227)
         beta = transcript.squeeze_challenge()
@@ -420,15 +429,20 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript) -> None:
             z_polys = permutation_z_polys(pp.num_permutation_z_polys, [polys[idx] for idx, _ in pp.permutation_polys],
                                           [p for _, p in pp.permutation_polys], fr_to_montgomery(beta), fr_to_montgomery(gamma))
             owned.extend(z_polys)
+        mark("permutation_z_polys")
         transcript.write_commitments([kzg.commit(pp.pcs, z) for z in z_polys])
+        mark("z commit")
         # Round n+2 (hyperplonk.rs:256-273)
         alpha = transcript.squeeze_challenge()
         y = transcript.squeeze_challenges(pp.num_vars)
         polys = polys + [p for _, p in pp.permutation_polys] + z_polys
         challenges = challenges + [beta, gamma, alpha]
         pts, evals = prove_sum_check(len(pp.num_instances), pp.expression, 0, polys, challenges, y, transcript)   # prove_zero_check
+        mark("zero check + evals")
         # PCS open (hyperplonk.rs:277-288)
         kzg.batch_open(pp.pcs, pp.num_vars, polys, pts, evals, transcript)
+        mark("pcs_batch_open")
     finally:
         for p in owned:
             p.release()
+        mark("release")

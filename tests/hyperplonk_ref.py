@@ -18,7 +18,8 @@ from oracle import bigint_ref as br
 from test_permutation_cpu import bh_iter, z_polys_python
 
 R = br.R
-PRIMITIVES = [1, 3, 7, 11, 19, 37, 67, 131, 285, 529, 1033, 2053, 4179, 8219, 16427, 32771, 65581]
+PRIMITIVES = [1, 3, 7, 11, 19, 37, 67, 131, 285, 529, 1033, 2053, 4179, 8219, 16427, 32771, 65581, 131081, 262183, 524327, 1048585, 2097157, 4194307,
+              8388641, 16777243, 33554441, 67108935, 134217767, 268435465, 536870917, 1073741907, 2147483657]  # bh.rs:5-37
 DEGREE = 5            # 1 (eq) + 1 (z) + 3 (the permutation chunk)
 
 
@@ -90,6 +91,15 @@ def permutation_polys(k, perm_polys, cycles):
 def bh_next(b, k):
     b <<= 1
     return b ^ ((b >> k) * PRIMITIVES[k])
+
+
+def bh_prefix(k, count):
+    """The first `count` rows of BooleanHypercube::iter (bh.rs:123-130): all the verifier needs (instances, l_1)."""
+    out, b = [0], 1
+    while len(out) < count:
+        out.append(b)
+        b = bh_next(b, k)
+    return out
 
 
 def constraint(v, k, beta, gamma, alpha):
@@ -237,7 +247,7 @@ def verify_reference(keccak256, ss, k, instances, preprocess_comms, permutation_
     """hyperplonk.rs:293-362; raises AssertionError where the reference returns Err.  Commitments are affine integer
     pairs; ss: the setup's trapdoor (canonical integers)."""
     t = ProofReader(keccak256, proof)
-    order = bh_iter(k)
+    order = bh_prefix(k, max(len(instances), 1) + 1)
     for v in instances:
         t.common_field_element(v)
     witness_comms = t.read_commitments(3)
