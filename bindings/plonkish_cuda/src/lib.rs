@@ -31,6 +31,10 @@ extern "C" {
     fn plonkish_cuda_msm_bn254_g1_batch_keep(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void, scalars_handles: *mut u64) -> c_int;
     fn plonkish_cuda_fr_linear_combination(handles: *const u64, coeffs: *const c_void, count: usize, n: usize, out_handle: *mut u64) -> c_int;
     fn plonkish_cuda_fr_div_linear(handle: u64, z: *const c_void, out_quotient: *mut u64, out_rem: *mut c_void) -> c_int;
+    fn plonkish_cuda_fr_affine_table(device: c_int, num_vars: usize, polys: *const u64, rotations: *const i32, coeffs: *const c_void, count: usize,
+                                     constant: *const c_void, identity_coeff: *const c_void, sparse_rows: *const u64, sparse_values: *const c_void,
+                                     sparse_count: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_fr_evaluate(handle: u64, points: *const c_void, num_vars: usize, count: usize, out_evals: *mut c_void) -> c_int;
     fn plonkish_cuda_scalars_register(device: c_int, scalars: *const c_void, n: usize, handle: *mut u64) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_resident(scalars_handle: u64, bases_handle: u64, n: usize, out: *mut c_void) -> c_int;
     fn plonkish_cuda_permutation_z_polys_bn254(values: *const u64, sigmas: *const u64, count: usize, num_chunks: usize, num_vars: usize,
@@ -392,6 +396,40 @@ pub fn permutation_z_polys(num_chunks: usize, values: &[&ResidentPoly], sigmas: 
         "plonkish_cuda_permutation_z_polys_bn254",
     );
     out.into_iter().map(|handle| ResidentPoly { handle, num_vars }).collect()
+}
+
+/// One table of a compiled zero-check expression: `constant + identity_coeff * id + sum_i coeffs[i] * polys[i]` rotated by
+/// `rotations[i]` (BooleanHypercube::rotate, util/arithmetic/bh.rs:104-121), plus `values[j]` on row `rows[j]` (a Lagrange
+/// polynomial is one such row, an instance polynomial a handful: backend/hyperplonk/prover.rs:32-48).  What
+/// `ProverState` keeps implicit (piop/sum_check/classic.rs:40-75, 104-126) as an explicit multilinear table; the linear
+/// factors `w + beta * id + gamma` of the permutation constraint (preprocessor.rs:153-165) are one call each.
+pub fn affine_table(num_vars: usize, polys: &[&ResidentPoly], coeffs: &[Fr], rotations: &[i32], constant: Option<&Fr>, identity_coeff: Option<&Fr>,
+                    rows: &[u64], values: &[Fr]) -> ResidentPoly {
+    init();
+    assert!(polys.len() == coeffs.len() && polys.len() == rotations.len() && rows.len() == values.len());
+    let hs: Vec<u64> = polys.iter().map(|p| p.handle).collect();
+    let as_ptr = |f: Option<&Fr>| f.map_or(std::ptr::null(), |f| f as *const Fr as *const c_void);
+    let mut handle = 0u64;
+    check(
+        unsafe {
+            plonkish_cuda_fr_affine_table(0, num_vars, hs.as_ptr(), rotations.as_ptr(), coeffs.as_ptr() as *const c_void, hs.len(), as_ptr(constant),
+                                          as_ptr(identity_coeff), rows.as_ptr(), values.as_ptr() as *const c_void, rows.len(), &mut handle)
+        },
+        "plonkish_cuda_fr_affine_table",
+    );
+    ResidentPoly { handle, num_vars }
+}
+
+/// `MultilinearPolynomial::evaluate` at several points (poly/multilinear.rs:137-156), e.g. the 2^distance points of
+/// `evaluate_for_rotation` (poly/multilinear.rs:191-263) that `prove_sum_check` writes to the transcript (prover.rs:392-406).
+pub fn evaluate(poly: &ResidentPoly, points: &[Vec<Fr>]) -> Vec<Fr> {
+    let flat: Vec<Fr> = points.iter().flat_map(|p| { assert_eq!(p.len(), poly.num_vars); p.iter().copied() }).collect();
+    let mut out = vec![Fr::zero(); points.len()];
+    check(
+        unsafe { plonkish_cuda_fr_evaluate(poly.handle, flat.as_ptr() as *const c_void, poly.num_vars, points.len(), out.as_mut_ptr() as *mut c_void) },
+        "plonkish_cuda_fr_evaluate",
+    );
+    out
 }
 
 /// Coefficients of a univariate polynomial kept in HBM, for `UnivariateKzg::open` / `batch_open` (pcs/univariate/kzg.rs:264-354).

@@ -306,29 +306,33 @@ PK_HD fe fr_from_u64(unsigned long long v) {
 }
 
 #define PK_PERM_MAX 8     // permutation polynomials per chunk (vanilla_plonk has three in one chunk)
-#define PK_PERM_STRIP 32  // rows per thread: one inversion per strip (Montgomery's trick)
+#define PK_PERM_STRIP 32  // rows per thread at small sizes: one inversion (~370 products) per strip (Montgomery's trick)
+// From 2^20 rows a thread takes 128: the inversion's share drops from 11.5 to 2.9 products per row and 2^24 rows still fill the GPU 7 times over.
+inline u32 pk_perm_strip(size_t n) { return n >= ((size_t)1 << 20) ? 128u : (u32)PK_PERM_STRIP; }
 struct PermArgs {
     const uint4 *value[PK_PERM_MAX];  // polys[*poly]: the witness column the permutation polynomial belongs to
     const uint4 *sigma[PK_PERM_MAX];  // the permutation polynomial
     unsigned long long id_offset[PK_PERM_MAX];  // idx << num_vars
     u32 count;
 };
-__global__ void __launch_bounds__(128) k_perm_products(PermArgs a, const uint4 *__restrict__ beta_gamma, size_t n, uint4 *__restrict__ product) {
+__global__ void __launch_bounds__(128) k_perm_products(PermArgs a, const uint4 *__restrict__ beta_gamma, size_t n, u32 strip, uint4 *__restrict__ den_cache,
+                                                       uint4 *__restrict__ product) {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t first = t * PK_PERM_STRIP;
+    const size_t first = t * strip;
     if (first >= n) return;
-    const u32 cnt = (u32)((first + PK_PERM_STRIP <= n) ? PK_PERM_STRIP : n - first);
+    const u32 cnt = (u32)((first + strip <= n) ? strip : n - first);
     const fe beta = load_fe_plain(beta_gamma), gamma = load_fe_plain(beta_gamma + 2);
     fe one;
     one.l[0] = 0x4ffffffbu; one.l[1] = 0xac96341cu; one.l[2] = 0x9f60cd29u; one.l[3] = 0x36fc7695u;
     one.l[4] = 0x7879462eu; one.l[5] = 0x666ea36fu; one.l[6] = 0x9a07df2fu; one.l[7] = 0x0e0a77c1u;
-    // pass 1: prefix products of the denominators (left in `product`)
+    // pass 1: prefix products of the denominators (left in `product`), the denominators themselves in den_cache
     fe run = one;
     for (u32 j = 0; j < cnt; ++j) {
         fe den = one;
         for (u32 i = 0; i < a.count; ++i)
             den = fr_mul(den, fr_add(fr_add(fr_mul(beta, load_fe(a.sigma[i] + 2 * (first + j))), gamma), load_fe(a.value[i] + 2 * (first + j))));
         store_fe(product + 2 * (first + j), run);      // prefix before row j
+        store_fe(den_cache + 2 * (first + j), den);
         run = fr_mul(run, den);
     }
     fe inv = fr_inv(run);                               // a zero denominator zeroes the strip, as batch_invert would skip it: not reachable for a valid beta, gamma
@@ -336,15 +340,13 @@ __global__ void __launch_bounds__(128) k_perm_products(PermArgs a, const uint4 *
     fe beta_id[PK_PERM_MAX];
     for (u32 i = 0; i < a.count; ++i) beta_id[i] = fr_mul(beta, fr_from_u64(a.id_offset[i] + first + cnt - 1));
     for (u32 j = cnt; j-- > 0;) {
-        fe den = one, num = one;
+        fe num = one;
         for (u32 i = 0; i < a.count; ++i) {
-            const fe v = load_fe(a.value[i] + 2 * (first + j));
-            den = fr_mul(den, fr_add(fr_add(fr_mul(beta, load_fe(a.sigma[i] + 2 * (first + j))), gamma), v));
-            num = fr_mul(num, fr_add(fr_add(beta_id[i], gamma), v));
+            num = fr_mul(num, fr_add(fr_add(beta_id[i], gamma), load_fe(a.value[i] + 2 * (first + j))));
             beta_id[i] = fr_sub(beta_id[i], beta);
         }
         const fe inv_den = fr_mul(inv, load_fe_plain(product + 2 * (first + j)));
-        inv = fr_mul(inv, den);
+        inv = fr_mul(inv, load_fe_plain(den_cache + 2 * (first + j)));
         store_fe(product + 2 * (first + j), fr_mul(num, inv_den));
     }
 }
@@ -474,7 +476,7 @@ static const u32 PK_BH_PRIMITIVES[32] = {1u, 3u, 7u, 11u, 19u, 37u, 67u, 131u, 2
 inline size_t pk_perm_z_scratch_elems(size_t num_chunks, size_t n) {
     const size_t m = num_chunks * n - num_chunks - 1;
     const size_t strips = (m + PK_SCAN_STRIP - 1) / PK_SCAN_STRIP;
-    return num_chunks * n + m + 2 * strips + 256;
+    return num_chunks * n + m + 2 * strips + 256 + n;  // products, sequence, strip totals (+ their scan), the denominators of one chunk
 }
 // chunks[k]: the permutation polynomials of chunk k; d_beta_gamma: beta, gamma (two elements, device); d_out_table: device
 // array of num_chunks output pointers (2^num_vars elements each).
@@ -486,13 +488,15 @@ inline void pk_enqueue_perm_z(const PermArgs *chunks, u32 num_chunks, u32 num_va
     uint4 *d_products = (uint4 *)scratch;
     uint4 *d_seq = d_products + 2 * (size_t)num_chunks * n;
     uint4 *d_totals = d_seq + 2 * m;
+    uint4 *d_den = d_totals + 2 * (2 * strips + 256);
     PermSeq seq;
     memset(&seq, 0, sizeof(seq));
     seq.nc = num_chunks; seq.k = num_vars; seq.primitive = PK_BH_PRIMITIVES[num_vars];
-    const size_t pthreads = (n + PK_PERM_STRIP - 1) / PK_PERM_STRIP;
+    const u32 strip = pk_perm_strip(n);
+    const size_t pthreads = (n + strip - 1) / strip;
     for (u32 k = 0; k < num_chunks; ++k) {
         seq.product[k] = d_products + 2 * (size_t)k * n;
-        PK_LAUNCH(k_perm_products, dim3((unsigned)((pthreads + 127) / 128)), dim3(128), 0, stream, chunks[k], (const uint4 *)d_beta_gamma, n, d_products + 2 * (size_t)k * n);
+        PK_LAUNCH(k_perm_products, dim3((unsigned)((pthreads + 127) / 128)), dim3(128), 0, stream, chunks[k], (const uint4 *)d_beta_gamma, n, strip, d_den, d_products + 2 * (size_t)k * n);
     }
     if (m) {
         PK_LAUNCH(k_perm_gather_scan, dim3((unsigned)((strips + 127) / 128)), dim3(128), 0, stream, seq, m, d_seq, d_totals);
@@ -531,9 +535,19 @@ PK_HD u32 bh_rotate(u32 b, int rotation, u32 k, u32 primitive, u32 x_inv) {  // 
     return b;
 }
 __global__ void __launch_bounds__(256) k_fr_affine(AffineArgs a, size_t n, uint4 *out) {  // `out` may be a source too (unrotated)
-    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+    const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    // the identity term walks with the grid stride: id_coeff * j once, then one addition per row
+    fe id_term = fe_zero(), id_step = fe_zero();
+    if (a.has_id) {
+        id_term = fr_mul(a.id_coeff, fr_from_u64(first));
+        id_step = fr_mul(a.id_coeff, fr_from_u64(stride));
+    }
+    for (size_t j = first; j < n; j += stride) {
         fe acc = a.has_constant ? a.constant : fe_zero();
-        if (a.has_id) acc = fr_add(acc, fr_mul(a.id_coeff, fr_from_u64(j)));
+        if (a.has_id) {
+            acc = fr_add(acc, id_term);
+            id_term = fr_add(id_term, id_step);
+        }
         for (u32 i = 0; i < a.count; ++i) {
             const size_t row = a.rotation[i] ? (size_t)bh_rotate((u32)j, a.rotation[i], a.num_vars, a.primitive, a.x_inv) : j;
             const fe v = load_fe_plain(a.poly[i] + 2 * row);

@@ -53,76 +53,105 @@ PK_HD void sc_store(u32 *base, u32 p, u32 nthreads, u32 tid, const fe &v) {
     for (int i = 0; i < 8; ++i) base[((size_t)p * 8 + i) * nthreads + tid] = v.l[i];
 }
 
-// The table entries of pair b at the points X = x0 + 1 and x0 + 2: e[2b+1] + x0 * step and one step further
-// (eval.rs:268-300: the point X = 1 is e[2b+1], every further point adds e[2b+1] - e[2b]).
-PK_HD void sc_points(const uint4 *__restrict__ table, u32 b, u32 x0, fe &v0, fe &v1) {
-    const uint4 *src = table + 4 * (size_t)b;  // e[2b] then e[2b+1]: 64 contiguous bytes
-    const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
-    const fe step = fr_sub(hi, lo);
-    v0 = hi;
-    for (u32 i = 0; i < x0; ++i) v0 = fr_add(v0, step);
-    v1 = fr_add(v0, step);
+// Plain 256-bit addition without reduction: the values a + x * step (x <= 4, both below r) stay below 5r < 2^256 and are
+// only ever used as the MULTIPLIER operand of mont_mul (read limb by limb), whose bounds depend on the multiplicand
+// alone: the running value stays below a + r and the product below a * 5r / 2^256 + r < 1.95 r for a < r, so the one
+// conditional subtraction at the end of mont_mul still lands in [0, r).
+PK_HD fe fe_add_plain(const fe &a, const fe &b) {
+    fe r;
+    add8(r.l, a.l, b.l);
+    return r;
 }
 
-// partials[block][x-1] = sum over the block's pairs b of expr(tables at (.., X = x, b)), x = 1..degree.
-// Term-major: every factor is read where it is used (the 64 bytes of a pair stay in L1 across the terms and
-// passes), two points of X per pass so that two independent product chains are in flight; no staging of the
-// tables, so occupancy is set by registers alone.  Dynamic shared memory: degree * 8 * blockDim words (the
-// running sums of every thread, limb-major).
-__global__ void __launch_bounds__(128, 4) k_sumcheck_round(SumcheckPolys polys, SumcheckExpr ex, u32 size, uint4 *__restrict__ partials) {
+// partials[block][x-1] = sum over the block's pairs b of expr(tables at (.., X = x, b)), x = 1..D.
+// Term-major, factor by factor: a factor's pair (e[2b], e[2b+1]) is read once per term and walked through all D points
+// (eval.rs:268-300: X = 1 is e[2b+1], every further point adds e[2b+1] - e[2b]) while the term's D running products —
+// D independent multiplication chains — stay in registers; the first factor of a term walks in reduced form (it becomes
+// the multiplicand), every other factor by plain additions (fe_add_plain) while D <= 5.  The sums over the terms of one
+// pair are multiplied by the common factor's walk and added to the thread's running sums in shared memory (limb-major,
+// D * 8 * blockDim words).
+template <int D>
+__global__ void __launch_bounds__(128, (D <= 5 ? 3 : 2)) k_sumcheck_round_t(SumcheckPolys polys, SumcheckExpr ex, u32 size, uint4 *__restrict__ partials) {
     PK_DYN_SMEM(u32, acc);
+    constexpr bool PLAIN = D <= 5;
     const u32 nt = blockDim.x, tid = threadIdx.x;
-    for (u32 x = 0; x < ex.degree; ++x) sc_store(acc, x, nt, tid, fe_zero());
+    for (u32 x = 0; x < (u32)D; ++x) sc_store(acc, x, nt, tid, fe_zero());
     for (u32 b = blockIdx.x * nt + tid; b < size; b += gridDim.x * nt) {
-        for (u32 x0 = 0; x0 < ex.degree; x0 += 2) {
-            const bool two = x0 + 1 < ex.degree;
-            fe tot0 = fe_zero(), tot1 = fe_zero();
-            for (u32 t = 0; t < ex.num_terms; ++t) {
-                fe p0 = ex.coeff[t], p1 = ex.coeff[t];
-                if (ex.nfac[t]) {
-                    sc_points(polys.p[ex.fac[t][0]], b, x0, p0, p1);
-                    for (u32 j = 1; j < ex.nfac[t]; ++j) {
-                        fe v0, v1;
-                        sc_points(polys.p[ex.fac[t][j]], b, x0, v0, v1);
-                        p0 = fr_mul(p0, v0);
-                        if (two) p1 = fr_mul(p1, v1);
-                    }
-                    if (ex.has_coeff[t]) {
-                        p0 = fr_mul(p0, ex.coeff[t]);
-                        if (two) p1 = fr_mul(p1, ex.coeff[t]);
-                    }
+        fe tot[D];
+#pragma unroll
+        for (int x = 0; x < D; ++x) tot[x] = fe_zero();
+        for (u32 t = 0; t < ex.num_terms; ++t) {
+            fe prod[D];
+            if (ex.nfac[t] == 0) {
+#pragma unroll
+                for (int x = 0; x < D; ++x) tot[x] = fr_add(tot[x], ex.coeff[t]);
+                continue;
+            }
+            {
+                const uint4 *src = polys.p[ex.fac[t][0]] + 4 * (size_t)b;
+                const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
+                const fe step = fr_sub(hi, lo);
+                prod[0] = hi;
+#pragma unroll
+                for (int x = 1; x < D; ++x) prod[x] = fr_add(prod[x - 1], step);
+            }
+            for (u32 j = 1; j < ex.nfac[t]; ++j) {
+                const uint4 *src = polys.p[ex.fac[t][j]] + 4 * (size_t)b;
+                const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
+                const fe step = fr_sub(hi, lo);
+                fe v = hi;
+#pragma unroll
+                for (int x = 0; x < D; ++x) {
+                    if (x) v = PLAIN ? fe_add_plain(v, step) : fr_add(v, step);
+                    prod[x] = fr_mul(prod[x], v);
                 }
-                tot0 = fr_add(tot0, p0);
-                tot1 = fr_add(tot1, p1);
             }
-            if (ex.common >= 0) {
-                fe v0, v1;
-                sc_points(polys.p[ex.common], b, x0, v0, v1);
-                tot0 = fr_mul(tot0, v0);
-                if (two) tot1 = fr_mul(tot1, v1);
+            if (ex.has_coeff[t]) {
+#pragma unroll
+                for (int x = 0; x < D; ++x) prod[x] = fr_mul(prod[x], ex.coeff[t]);
             }
-            sc_store(acc, x0, nt, tid, fr_add(sc_load(acc, x0, nt, tid), tot0));
-            if (two) sc_store(acc, x0 + 1, nt, tid, fr_add(sc_load(acc, x0 + 1, nt, tid), tot1));
+#pragma unroll
+            for (int x = 0; x < D; ++x) tot[x] = fr_add(tot[x], prod[x]);
         }
+        if (ex.common >= 0) {
+            const uint4 *src = polys.p[ex.common] + 4 * (size_t)b;
+            const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
+            const fe step = fr_sub(hi, lo);
+            fe v = hi;
+#pragma unroll
+            for (int x = 0; x < D; ++x) {
+                if (x) v = PLAIN ? fe_add_plain(v, step) : fr_add(v, step);
+                tot[x] = fr_mul(tot[x], v);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < D; ++x) sc_store(acc, x, nt, tid, fr_add(sc_load(acc, x, nt, tid), tot[x]));
     }
     // block sum: binary tree over the threads, one point of X at a time
     __syncthreads();
-    for (u32 x = 0; x < ex.degree; ++x) {
+    for (u32 x = 0; x < (u32)D; ++x) {
         for (u32 s = nt >> 1; s >= 1; s >>= 1) {
             if (tid < s) sc_store(acc, x, nt, tid, fr_add(sc_load(acc, x, nt, tid), sc_load(acc, x, nt, tid + s)));
             __syncthreads();
         }
-        if (tid == 0) store_fe(partials + 2 * ((size_t)blockIdx.x * ex.degree + x), sc_load(acc, x, nt, 0));
+        if (tid == 0) store_fe(partials + 2 * ((size_t)blockIdx.x * D + x), sc_load(acc, x, nt, 0));
     }
 }
 
-// out[x] = sum_k partials[k][x]; one block, thread x.
-__global__ void k_sumcheck_sum_partials(const uint4 *__restrict__ partials, u32 nblocks, u32 degree, uint4 *__restrict__ out) {
-    const u32 x = threadIdx.x;
-    if (x >= degree) return;
+// out[x] = sum_k partials[k][x]: block x, 128 threads stride over the blocks' partial sums, then a binary tree in shared
+// memory (a single thread per point took 65 us for 444 partials, 3 ms over the 48 rounds of a k = 24 proof).
+__global__ void __launch_bounds__(128) k_sumcheck_sum_partials(const uint4 *__restrict__ partials, u32 nblocks, u32 degree, uint4 *__restrict__ out) {
+    __shared__ fe part[128];
+    const u32 x = blockIdx.x, tid = threadIdx.x;
     fe s = fe_zero();
-    for (u32 k = 0; k < nblocks; ++k) s = fr_add(s, load_fe_plain(partials + 2 * ((size_t)k * degree + x)));
-    store_fe(out + 2 * (size_t)x, s);
+    for (u32 k = tid; k < nblocks; k += blockDim.x) s = fr_add(s, load_fe_plain(partials + 2 * ((size_t)k * degree + x)));
+    part[tid] = s;
+    __syncthreads();
+    for (u32 w = blockDim.x >> 1; w >= 1; w >>= 1) {
+        if (tid < w) part[tid] = fr_add(part[tid], part[tid + w]);
+        __syncthreads();
+    }
+    if (tid == 0) store_fe(out + 2 * (size_t)x, part[0]);
 }
 
 // fix_var for every table in one launch (grid.y = table): out[b] = (e[2b+1] - e[2b]) * x + e[2b].
@@ -141,20 +170,29 @@ inline size_t pk_sumcheck_smem(u32 degree, u32 block) { return (size_t)32 * degr
 
 // One round over tables of 2 * size evaluations each: degree values into d_out (X = 1..degree).
 // partials: 16 * sm_count * degree field elements of scratch (more than the largest grid).
-inline u32 pk_sumcheck_grid(u32 size, u32 block, u32 sm_count) {
+inline u32 pk_sumcheck_blocks_per_sm(u32 degree) { return degree <= 5 ? 3u : 2u; }  // the launch bounds of k_sumcheck_round_t
+inline u32 pk_sumcheck_grid(u32 size, u32 block, u32 sm_count, u32 degree) {
     u32 blocks = (size + block - 1) / block;
-    const u32 cap = sm_count * 4;  // persistent: 4 blocks of 128 threads per SM (registers)
+    const u32 cap = sm_count * pk_sumcheck_blocks_per_sm(degree);  // persistent: one wave of resident blocks
     if (blocks > cap) blocks = cap;
     return blocks ? blocks : 1;
 }
 inline void pk_enqueue_sumcheck_round(const SumcheckPolys &polys, const SumcheckExpr &ex, u32 size, void *partials, void *d_out, u32 sm_count,
                                       pk_stream_t stream) {
     const u32 block = pk_sumcheck_block(ex.num_polys);
-    const u32 blocks = pk_sumcheck_grid(size, block, sm_count);
+    const u32 blocks = pk_sumcheck_grid(size, block, sm_count, ex.degree);
     const size_t smem = pk_sumcheck_smem(ex.degree, block);
-    PK_SET_SMEM(k_sumcheck_round, smem);
-    PK_LAUNCH(k_sumcheck_round, dim3(blocks), dim3(block), smem, stream, polys, ex, size, (uint4 *)partials);
-    PK_LAUNCH(k_sumcheck_sum_partials, dim3(1), dim3(32), 0, stream, (const uint4 *)partials, blocks, ex.degree, (uint4 *)d_out);
+#define PK_SC_CASE(DEG)                                                                                                    \
+    case DEG:                                                                                                              \
+        PK_SET_SMEM(k_sumcheck_round_t<DEG>, smem);                                                                        \
+        PK_LAUNCH(k_sumcheck_round_t<DEG>, dim3(blocks), dim3(block), smem, stream, polys, ex, size, (uint4 *)partials);   \
+        break;
+    switch (ex.degree) {
+        PK_SC_CASE(1) PK_SC_CASE(2) PK_SC_CASE(3) PK_SC_CASE(4) PK_SC_CASE(5) PK_SC_CASE(6) PK_SC_CASE(7) PK_SC_CASE(8)
+        default: break;  // plonkish_cuda_sumcheck_new refuses degrees outside 1..PK_SC_MAX_DEGREE
+    }
+#undef PK_SC_CASE
+    PK_LAUNCH(k_sumcheck_sum_partials, dim3(ex.degree), dim3(128), 0, stream, (const uint4 *)partials, blocks, ex.degree, (uint4 *)d_out);
 }
 inline void pk_enqueue_sumcheck_fold(const SumcheckFoldArgs &a, u32 num_polys, const void *d_challenge, u32 size, u32 sm_count, pk_stream_t stream) {
     u32 blocks = (size + 255) / 256;

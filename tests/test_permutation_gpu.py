@@ -19,7 +19,7 @@ def pk():
     return plonkish_b200
 
 
-@pytest.mark.parametrize("k,count,num_chunks", [(1, 1, 1), (2, 2, 2), (5, 3, 1), (9, 3, 3), (10, 5, 2), (13, 3, 1), (16, 3, 1), (18, 4, 2)])
+@pytest.mark.parametrize("k,count,num_chunks", [(1, 1, 1), (2, 2, 2), (5, 3, 1), (9, 3, 3), (10, 5, 2), (13, 3, 1), (16, 3, 1), (18, 4, 2), (20, 3, 1), (20, 2, 2)])
 def test_z_polys_match_the_oracle(pk, oracle, k, count, num_chunks):
     n = 1 << k
     values_h = [pk.random_scalars(n, seed=10 * k + i) for i in range(count)]

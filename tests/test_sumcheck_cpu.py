@@ -139,3 +139,23 @@ def test_emulated_round_and_fold_kernels(emul, oracle, num_polys, num_vars, num_
     emul.emul_sumcheck_fold(ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(optrs, ctypes.c_void_p), num_polys, n, x.ctypes.data, sms)
     for p, o in zip(polys, outs):
         assert o.tobytes() == oracle.fix_var(p, x).tobytes()
+
+
+@pytest.mark.parametrize("degree_terms", [4, 5])
+def test_emulated_round_kernel_on_extreme_values(emul, oracle, degree_terms):
+    """The walk X = 1..D of a non-leading factor runs on unreduced sums (fe_add_plain: e[2b+1] + x * step < 5r): tables of
+    0, 1, r - 1, r - 2 make every step and every walked value as large as they get."""
+    rng = np.random.default_rng(degree_terms)
+    num_vars, num_polys = 7, 6
+    n = 1 << num_vars
+    pool = [0, 1, R - 1, R - 2]
+    polys = [_mont([pool[int(v)] for v in rng.integers(0, 4, n)]) for _ in range(num_polys)]
+    terms = [(_mont([R - 1])[0], list(range(1, 1 + degree_terms))), (_mont([1])[0], [5, 4, 3]), (_mont([R - 2])[0], [2])]
+    coeffs, offsets, flat = oracle.flatten_terms(terms)
+    degree = degree_terms + 1
+    ptrs = (ctypes.c_void_p * num_polys)(*[p.ctypes.data for p in polys])
+    out = np.zeros((degree, 4), dtype=np.uint64)
+    emul.emul_sumcheck_round(ctypes.cast(ptrs, ctypes.c_void_p), num_polys, n, coeffs.ctypes.data, offsets.ctypes.data, flat.ctypes.data,
+                             len(terms), 0, degree, 1, out.ctypes.data)
+    terms_int = [(R - 1, list(range(1, 1 + degree_terms))), (1, [5, 4, 3]), (R - 2, [2])]
+    assert _ints(out) == _round_int([_ints(p) for p in polys], terms_int, 0, degree)

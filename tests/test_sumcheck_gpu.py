@@ -125,3 +125,31 @@ def test_argument_errors(pk, oracle):
     prover.free()
     p.release()
     q.release()
+
+
+@pytest.mark.parametrize("degree_terms", [4, 5])
+def test_round_kernel_on_extreme_values(pk, oracle, degree_terms):
+    """Non-leading factors walk X = 1..D as unreduced sums below 5r (fe_add_plain in csrc/sumcheck_kernels.cuh): tables of
+    0, 1, r - 1, r - 2 push every step and walked value to its bound; degree 6 takes the reduced walk."""
+    from plonkish_b200.sumcheck import SumCheckProver
+    from test_sumcheck_cpu import _round_int
+
+    rng = np.random.default_rng(degree_terms)
+    num_vars, num_polys = 9, 6
+    n = 1 << num_vars
+    pool = [0, 1, R - 1, R - 2]
+    polys = [_mont([pool[int(v)] for v in rng.integers(0, 4, n)]) for _ in range(num_polys)]
+    terms = [(_mont([R - 1])[0], list(range(1, 1 + degree_terms))), (_mont([1])[0], [5, 4, 3]), (_mont([R - 2])[0], [2])]
+    terms_int = [(R - 1, list(range(1, 1 + degree_terms))), (1, [5, 4, 3]), (R - 2, [2])]
+    resident = [pk.ResidentScalars(p) for p in polys]
+    prover = SumCheckProver(resident, terms, 0)
+    assert prover.degree == degree_terms + 1
+    cur = polys
+    for rnd in range(3):
+        assert _ints(prover.round_evals()) == _round_int([_ints(p) for p in cur], terms_int, 0, degree_terms + 1), rnd
+        ch = _mont([R - 1 - rnd])[0]
+        prover.fix_var(ch)
+        cur = [oracle.fix_var(p, ch) for p in cur]
+    prover.free()
+    for r in resident:
+        r.release()
