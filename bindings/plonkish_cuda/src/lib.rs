@@ -34,6 +34,10 @@ extern "C" {
     fn plonkish_cuda_fr_affine_table(device: c_int, num_vars: usize, polys: *const u64, rotations: *const i32, coeffs: *const c_void, count: usize,
                                      constant: *const c_void, identity_coeff: *const c_void, sparse_rows: *const u64, sparse_values: *const c_void,
                                      sparse_count: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_fr_expression_table(polys: *const u64, num_polys: usize, num_vars: usize, coeffs: *const c_void, offsets: *const u32, term_polys: *const u32,
+                                         num_terms: usize, common: c_int, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_lookup_m_poly_bn254(input: u64, table: u64, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_lookup_h_poly_bn254(input: u64, table: u64, m: u64, gamma: *const c_void, out_handle: *mut u64) -> c_int;
     fn plonkish_cuda_fr_evaluate(handle: u64, points: *const c_void, num_vars: usize, count: usize, out_evals: *mut c_void) -> c_int;
     fn plonkish_cuda_scalars_register(device: c_int, scalars: *const c_void, n: usize, handle: *mut u64) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_resident(scalars_handle: u64, bases_handle: u64, n: usize, out: *mut c_void) -> c_int;
@@ -418,6 +422,50 @@ pub fn affine_table(num_vars: usize, polys: &[&ResidentPoly], coeffs: &[Fr], rot
         "plonkish_cuda_fr_affine_table",
     );
     ResidentPoly { handle, num_vars }
+}
+
+/// A compiled expression on every row — `lookup_compressed_poly` (backend/hyperplonk/prover.rs:79-137) is one call:
+/// `terms[t] = (coeff, indices into polys)`, out[b] = sum_t coeff_t * prod_j polys[idx][b] (times `polys[common][b]`).
+pub fn expression_table(polys: &[&ResidentPoly], terms: &[(Fr, Vec<u32>)], common: Option<usize>) -> ResidentPoly {
+    let hs: Vec<u64> = polys.iter().map(|p| p.handle).collect();
+    let coeffs: Vec<Fr> = terms.iter().map(|(c, _)| *c).collect();
+    let mut offsets = vec![0u32];
+    let mut flat = Vec::new();
+    for (_, idx) in terms {
+        flat.extend_from_slice(idx);
+        offsets.push(flat.len() as u32);
+    }
+    let num_vars = polys[0].num_vars;
+    let mut handle = 0u64;
+    check(
+        unsafe {
+            plonkish_cuda_fr_expression_table(hs.as_ptr(), hs.len(), num_vars, coeffs.as_ptr() as *const c_void, offsets.as_ptr(), flat.as_ptr(), terms.len(),
+                                              common.map_or(-1, |c| c as c_int), &mut handle)
+        },
+        "plonkish_cuda_fr_expression_table",
+    );
+    ResidentPoly { handle, num_vars }
+}
+
+/// `lookup_m_poly` (backend/hyperplonk/prover.rs:145-192); `Err` when an input value is not in the table, like the
+/// reference's `Error::InvalidSnark("Invalid lookup input")`.
+pub fn lookup_m_poly(input: &ResidentPoly, table: &ResidentPoly) -> Result<ResidentPoly, String> {
+    let mut handle = 0u64;
+    let rc = unsafe { plonkish_cuda_lookup_m_poly_bn254(input.handle, table.handle, &mut handle) };
+    if rc != 0 {
+        return Err(unsafe { std::ffi::CStr::from_ptr(plonkish_cuda_last_error()) }.to_string_lossy().into_owned());
+    }
+    Ok(ResidentPoly { handle, num_vars: input.num_vars })
+}
+
+/// `lookup_h_poly` (backend/hyperplonk/prover.rs:206-250): 1 / (gamma + input) - m / (gamma + table).
+pub fn lookup_h_poly(input: &ResidentPoly, table: &ResidentPoly, m: &ResidentPoly, gamma: &Fr) -> ResidentPoly {
+    let mut handle = 0u64;
+    check(
+        unsafe { plonkish_cuda_lookup_h_poly_bn254(input.handle, table.handle, m.handle, gamma as *const Fr as *const c_void, &mut handle) },
+        "plonkish_cuda_lookup_h_poly_bn254",
+    );
+    ResidentPoly { handle, num_vars: input.num_vars }
 }
 
 /// `MultilinearPolynomial::evaluate` at several points (poly/multilinear.rs:137-156), e.g. the 2^distance points of

@@ -179,6 +179,19 @@ int plonkish_cuda_permutation_z_polys_bn254(const uint64_t *value_handles, const
 int plonkish_cuda_fr_affine_table(int device, size_t num_vars, const uint64_t *poly_handles, const int32_t *rotations, const void *coeffs_mont32,
                                   size_t count, const void *constant_mont32, const void *identity_coeff_mont32, const uint64_t *sparse_rows,
                                   const void *sparse_values_mont32, size_t sparse_count, uint64_t *out_handle);
+/* A compiled expression on every row: out[b] = (sum_t coeff_t * prod_j poly[fac_t,j][b]) (* poly[common][b]); the term
+ * encoding is plonkish_cuda_sumcheck_new's.  The compressed input / table polynomial of a lookup argument
+ * (lookup_compressed_poly, backend/hyperplonk/prover.rs:79-137) is one call. */
+int plonkish_cuda_fr_expression_table(const uint64_t *poly_handles, size_t num_polys, size_t num_vars, const void *term_coeffs_mont32,
+                                      const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms, int common_poly,
+                                      uint64_t *out_handle);
+/* lookup_m_poly (backend/hyperplonk/prover.rs:145-192): m[row] = number of input values equal to table[row]; a value
+ * present in several table rows is counted at the last of them (the reference's HashMap, :151).  Returns
+ * PLONKISH_CUDA_E_INVALID ("Invalid lookup input", :176-178) when an input value is not in the table. */
+int plonkish_cuda_lookup_m_poly_bn254(uint64_t input_handle, uint64_t table_handle, uint64_t *out_handle);
+/* lookup_h_poly (backend/hyperplonk/prover.rs:206-250): h = 1 / (gamma + input) - m / (gamma + table), resident in and out. */
+int plonkish_cuda_lookup_h_poly_bn254(uint64_t input_handle, uint64_t table_handle, uint64_t m_handle, const void *gamma_mont32,
+                                      uint64_t *out_handle);
 /* MultilinearPolynomial::evaluate (poly/multilinear.rs:137-156) of a resident polynomial at `count` points of num_vars
  * Montgomery Fr each (points_mont32: count x num_vars x 32 B): the evaluations prove_sum_check needs at the rotated
  * points (backend/hyperplonk/prover.rs:392-400 through evaluate_for_rotation, poly/multilinear.rs:191-263).

@@ -14,6 +14,9 @@ from .msm import (  # noqa: F401
     fr_div_linear,
     fr_affine_table,
     fr_evaluate,
+    fr_expression_table,
+    lookup_m_poly,
+    lookup_h_poly,
     permutation_z_polys,
     kzg_open_resident,
     eq_table,

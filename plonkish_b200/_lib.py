@@ -48,6 +48,9 @@ EXPORTS = (
     "plonkish_cuda_permutation_z_polys_bn254",
     "plonkish_cuda_fr_affine_table",
     "plonkish_cuda_fr_evaluate",
+    "plonkish_cuda_fr_expression_table",
+    "plonkish_cuda_lookup_m_poly_bn254",
+    "plonkish_cuda_lookup_h_poly_bn254",
     "plonkish_cuda_kzg_open_bn254",
     "plonkish_cuda_fixed_base_msm_bn254_g1",
     "plonkish_cuda_kzg_setup_eqs_bn254",
@@ -149,6 +152,9 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_fr_div_linear.argtypes = [u64, vp, ctypes.POINTER(u64), vp]
     lib.plonkish_cuda_fr_affine_table.argtypes = [ci, sz, vp, vp, vp, sz, vp, vp, vp, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_fr_evaluate.argtypes = [u64, vp, sz, sz, vp]
+    lib.plonkish_cuda_fr_expression_table.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_lookup_m_poly_bn254.argtypes = [u64, u64, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_lookup_h_poly_bn254.argtypes = [u64, u64, u64, vp, ctypes.POINTER(u64)]
     lib.plonkish_cuda_kzg_open_bn254.argtypes = [u64, vp, vp, sz, vp, vp]
     lib.plonkish_cuda_fixed_base_msm_bn254_g1.argtypes = [ci, vp, vp, sz, vp]
     lib.plonkish_cuda_kzg_setup_eqs_bn254.argtypes = [ci, vp, vp, sz, vp]

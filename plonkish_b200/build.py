@@ -7,7 +7,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [os.path.join(_HERE, "csrc", "api.cu")]
 HEADERS = [
-    os.path.join(_HERE, "csrc", h) for h in ("fq.cuh", "g1.cuh", "msm_kernels.cuh", "poly_kernels.cuh", "sumcheck_kernels.cuh", "dpfq.cuh")
+    os.path.join(_HERE, "csrc", h) for h in ("fq.cuh", "g1.cuh", "msm_kernels.cuh", "poly_kernels.cuh", "sumcheck_kernels.cuh", "lookup_kernels.cuh", "dpfq.cuh")
 ] + [os.path.join(os.path.dirname(_HERE), "include", "plonkish_cuda.h")]
 OUT = os.path.join(_HERE, "libplonkish_cuda.so")
 

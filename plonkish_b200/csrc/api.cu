@@ -34,6 +34,7 @@ static std::atomic<unsigned long long> g_launches{0};
 #include "msm_kernels.cuh"
 #include "poly_kernels.cuh"
 #include "sumcheck_kernels.cuh"
+#include "lookup_kernels.cuh"
 #include "dpfq.cuh"
 
 using namespace pk;
@@ -2797,6 +2798,104 @@ extern "C" int plonkish_cuda_fr_evaluate(uint64_t scalars_handle, const void *po
     return PLONKISH_CUDA_OK;
 }
 
+static int fill_expr(const char *what, size_t num_polys, const void *term_coeffs, const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms,
+                     int common_poly, SumcheckExpr &ex);
+// A compiled expression on every row: out[b] = (sum_t coeff_t * prod_j poly[fac_t,j][b]) (* poly[common][b]) — the
+// compressed input / table polynomial of a lookup (lookup_compressed_poly, backend/hyperplonk/prover.rs:79-137: the
+// reference evaluates the expression tree per row; here the tree arrives compiled into product terms over resident
+// tables, plonkish_b200/expression.py).  Same term encoding as plonkish_cuda_sumcheck_new.
+extern "C" int plonkish_cuda_fr_expression_table(const uint64_t *poly_handles, size_t num_polys, size_t num_vars, const void *term_coeffs,
+                                                 const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms, int common_poly,
+                                                 uint64_t *out_handle) {
+    if (!poly_handles || !out_handle) return fail(PLONKISH_CUDA_E_INVALID, "fr_expression_table: null argument");
+    if (num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "fr_expression_table: num_vars = %zu exceeds 28", num_vars);
+    SumcheckExpr ex;
+    int rc = fill_expr("fr_expression_table", num_polys, term_coeffs, term_offsets, term_polys, num_terms, common_poly, ex);
+    if (rc) return rc;
+    const size_t n = (size_t)1 << num_vars;
+    SumcheckPolys polys;
+    memset(&polys, 0, sizeof(polys));
+    std::vector<ScalarsEntry> es(num_polys);
+    for (size_t p = 0; p < num_polys; ++p) {
+        if (!lookup_scalars(poly_handles[p], es[p])) return fail(PLONKISH_CUDA_E_INVALID, "fr_expression_table: unknown scalars handle %llu", (unsigned long long)poly_handles[p]);
+        if (es[p].n != n) return fail(PLONKISH_CUDA_E_INVALID, "fr_expression_table: polynomial %zu holds %zu evaluations, expected 2^%zu", p, es[p].n, num_vars);
+        if (es[p].dev != es[0].dev) return fail(PLONKISH_CUDA_E_INVALID, "fr_expression_table: polynomials live on different devices");
+        polys.p[p] = (const uint4 *)es[p].d_ptr;
+    }
+    Ctx *c = ctx_for(es[0].dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_expression_table: device %d not initialised", es[0].dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    if ((rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    PoolGuard d_guard{c, d};
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    pk_enqueue_expr_rows(polys, ex, n, d, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
+// lookup_m_poly (backend/hyperplonk/prover.rs:145-192): m[row] = how many input values equal table[row], a value that
+// occurs in several table rows counted at the last of them (the HashMap of :151); PLONKISH_CUDA_E_INVALID with
+// "Invalid lookup input" when an input value is not in the table (:169-177).
+extern "C" int plonkish_cuda_lookup_m_poly_bn254(uint64_t input_handle, uint64_t table_handle, uint64_t *out_handle) {
+    if (!out_handle) return fail(PLONKISH_CUDA_E_INVALID, "lookup_m_poly: null argument");
+    ScalarsEntry in, tb;
+    if (!lookup_scalars(input_handle, in) || !lookup_scalars(table_handle, tb)) return fail(PLONKISH_CUDA_E_INVALID, "lookup_m_poly: unknown scalars handle");
+    if (in.n != tb.n || in.dev != tb.dev) return fail(PLONKISH_CUDA_E_INVALID, "lookup_m_poly: input holds %zu values on device %d, table %zu on device %d", in.n, in.dev, tb.n, tb.dev);
+    if (in.n >= ((size_t)1 << 30)) return fail(PLONKISH_CUDA_E_INVALID, "lookup_m_poly: %zu rows exceed 2^30", in.n);
+    const size_t n = in.n;
+    Ctx *c = ctx_for(in.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "lookup_m_poly: device %d not initialised", in.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc;
+    const size_t slots = pk_lookup_slots(n);
+    if ((rc = grow(c->tmp, (slots + n + 4) * sizeof(u32)))) return rc;
+    u32 *d_slots = (u32 *)c->tmp.ptr, *d_counts = d_slots + slots, *d_missing = d_counts + n;
+    void *d = nullptr;
+    if ((rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    PoolGuard d_guard{c, d};
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    pk_enqueue_lookup_m(in.d_ptr, tb.d_ptr, (u32)n, d_slots, d_counts, d_missing, d, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    u32 missing = 0;
+    CUDA_TRY(cudaMemcpyAsync(&missing, d_missing, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (missing) return fail(PLONKISH_CUDA_E_INVALID, "lookup_m_poly: Invalid lookup input");  // Error::InvalidSnark, prover.rs:176-178
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
+// lookup_h_poly (backend/hyperplonk/prover.rs:206-250): h = 1 / (gamma + input) - m / (gamma + table), one of the
+// polynomials committed at backend/hyperplonk.rs:251-252.
+extern "C" int plonkish_cuda_lookup_h_poly_bn254(uint64_t input_handle, uint64_t table_handle, uint64_t m_handle, const void *gamma_mont32,
+                                                 uint64_t *out_handle) {
+    if (!out_handle || !gamma_mont32) return fail(PLONKISH_CUDA_E_INVALID, "lookup_h_poly: null argument");
+    ScalarsEntry in, tb, mm;
+    if (!lookup_scalars(input_handle, in) || !lookup_scalars(table_handle, tb) || !lookup_scalars(m_handle, mm)) return fail(PLONKISH_CUDA_E_INVALID, "lookup_h_poly: unknown scalars handle");
+    if (in.n != tb.n || in.n != mm.n || in.dev != tb.dev || in.dev != mm.dev) return fail(PLONKISH_CUDA_E_INVALID, "lookup_h_poly: the three polynomials differ in size or device");
+    const size_t n = in.n;
+    Ctx *c = ctx_for(in.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "lookup_h_poly: device %d not initialised", in.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc;
+    if ((rc = grow(c->tmp, 2 * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    void *d = nullptr;
+    if ((rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    PoolGuard d_guard{c, d};
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(c->tmp.ptr, gamma_mont32, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    pk_enqueue_lookup_h(in.d_ptr, tb.d_ptr, mm.d_ptr, c->tmp.ptr, n, d, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
 // ============================================================== fixed-base MSM
 // fixed_base_msm (msm.rs:67-81) over a window table of one base (msm.rs:16-31) followed by
 // batch_normalize (kzg.rs:204-207, univariate/kzg.rs:196-199): out[i] = scalars[i] * base, affine.
@@ -2998,36 +3097,46 @@ static void release_all_sumcheck() {  // caller holds g_mu
     g_sumcheck.clear();
 }
 
-extern "C" int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t num_polys, size_t num_vars, const void *term_coeffs,
-                                          const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms, int common_poly,
-                                          uint64_t *state_handle) {
-    if (!poly_handles || !state_handle || !term_offsets || (num_terms && !term_coeffs)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: null argument");
-    if (num_polys == 0 || num_polys > PK_SC_MAX_POLYS) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: %zu polynomials (1..%d supported)", num_polys, PK_SC_MAX_POLYS);
-    if (num_terms == 0 || num_terms > PK_SC_MAX_TERMS) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: %zu terms (1..%d supported)", num_terms, PK_SC_MAX_TERMS);
-    if (num_vars == 0 || num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: num_vars = %zu (1..28 supported)", num_vars);  // classic.rs:41
-    if (common_poly >= (int)num_polys) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: common factor %d out of range", common_poly);
-    SumcheckState st;
-    st.num_vars = (u32)num_vars; st.num_polys = (u32)num_polys;
-    memset(&st.ex, 0, sizeof(st.ex));
-    st.ex.num_terms = (u32)num_terms; st.ex.num_polys = (u32)num_polys; st.ex.common = common_poly < 0 ? -1 : common_poly;
+// The flattened expression sum_t coeff_t * prod_j poly[fac_t,j] (* poly[common]) as the kernels take it; shared by the
+// sum-check state and plonkish_cuda_fr_expression_table.  Returns 0 or a failure already recorded with `what`.
+static int fill_expr(const char *what, size_t num_polys, const void *term_coeffs, const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms,
+                     int common_poly, SumcheckExpr &ex) {
+    if (!term_offsets || (num_terms && !term_coeffs)) return fail(PLONKISH_CUDA_E_INVALID, "%s: null argument", what);
+    if (num_polys == 0 || num_polys > PK_SC_MAX_POLYS) return fail(PLONKISH_CUDA_E_INVALID, "%s: %zu polynomials (1..%d supported)", what, num_polys, PK_SC_MAX_POLYS);
+    if (num_terms == 0 || num_terms > PK_SC_MAX_TERMS) return fail(PLONKISH_CUDA_E_INVALID, "%s: %zu terms (1..%d supported)", what, num_terms, PK_SC_MAX_TERMS);
+    if (common_poly >= (int)num_polys) return fail(PLONKISH_CUDA_E_INVALID, "%s: common factor %d out of range", what, common_poly);
+    memset(&ex, 0, sizeof(ex));
+    ex.num_terms = (u32)num_terms; ex.num_polys = (u32)num_polys; ex.common = common_poly < 0 ? -1 : common_poly;
     u32 degree = 0;
     for (size_t t = 0; t < num_terms; ++t) {
         const uint32_t beg = term_offsets[t], end = term_offsets[t + 1];
-        if (end < beg || end - beg > PK_SC_MAX_FACTORS) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: term %zu has %u factors (0..%d supported)", t, end - beg, PK_SC_MAX_FACTORS);
-        st.ex.nfac[t] = (unsigned char)(end - beg);
+        if (end < beg || end - beg > PK_SC_MAX_FACTORS) return fail(PLONKISH_CUDA_E_INVALID, "%s: term %zu has %u factors (0..%d supported)", what, t, end - beg, PK_SC_MAX_FACTORS);
+        ex.nfac[t] = (unsigned char)(end - beg);
         for (uint32_t j = beg; j < end; ++j) {
-            if (!term_polys || term_polys[j] >= num_polys) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: term %zu names polynomial %u of %zu", t, term_polys ? term_polys[j] : 0u, num_polys);
-            st.ex.fac[t][j - beg] = (unsigned char)term_polys[j];
+            if (!term_polys || term_polys[j] >= num_polys) return fail(PLONKISH_CUDA_E_INVALID, "%s: term %zu names polynomial %u of %zu", what, t, term_polys ? term_polys[j] : 0u, num_polys);
+            ex.fac[t][j - beg] = (unsigned char)term_polys[j];
         }
-        memcpy(st.ex.coeff[t].l, (const char *)term_coeffs + t * PLONKISH_CUDA_SCALAR_BYTES, PLONKISH_CUDA_SCALAR_BYTES);
+        memcpy(ex.coeff[t].l, (const char *)term_coeffs + t * PLONKISH_CUDA_SCALAR_BYTES, PLONKISH_CUDA_SCALAR_BYTES);
         static const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};  // R mod r
-        st.ex.has_coeff[t] = memcmp(st.ex.coeff[t].l, FR_ONE, 32) != 0;
+        ex.has_coeff[t] = memcmp(ex.coeff[t].l, FR_ONE, 32) != 0;
         if (end - beg > degree) degree = end - beg;
     }
-    if (st.ex.common >= 0) degree += 1;
+    if (ex.common >= 0) degree += 1;
     if (degree < 1) degree = 1;
-    if (degree > PK_SC_MAX_DEGREE) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: degree %u exceeds %d", degree, PK_SC_MAX_DEGREE);
-    st.ex.degree = degree;
+    ex.degree = degree;
+    return PLONKISH_CUDA_OK;
+}
+
+extern "C" int plonkish_cuda_sumcheck_new(const uint64_t *poly_handles, size_t num_polys, size_t num_vars, const void *term_coeffs,
+                                          const uint32_t *term_offsets, const uint32_t *term_polys, size_t num_terms, int common_poly,
+                                          uint64_t *state_handle) {
+    if (!poly_handles || !state_handle) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: null argument");
+    if (num_vars == 0 || num_vars > 28) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: num_vars = %zu (1..28 supported)", num_vars);  // classic.rs:41
+    SumcheckState st;
+    st.num_vars = (u32)num_vars; st.num_polys = (u32)num_polys;
+    int rc_expr = fill_expr("sumcheck_new", num_polys, term_coeffs, term_offsets, term_polys, num_terms, common_poly, st.ex);
+    if (rc_expr) return rc_expr;
+    if (st.ex.degree > PK_SC_MAX_DEGREE) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_new: degree %u exceeds %d", st.ex.degree, PK_SC_MAX_DEGREE);
     const size_t n = (size_t)1 << num_vars;
     for (size_t p = 0; p < num_polys; ++p) {
         ScalarsEntry se;

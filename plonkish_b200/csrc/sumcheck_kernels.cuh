@@ -20,7 +20,7 @@
 
 namespace pk {
 
-#define PK_SC_MAX_POLYS 32
+#define PK_SC_MAX_POLYS 48
 #define PK_SC_MAX_TERMS 32
 #define PK_SC_MAX_FACTORS 8
 #define PK_SC_MAX_DEGREE 8

@@ -15,9 +15,8 @@ Mirrors /root/reference/plonkish_backend/src/backend (M = Bn256, Pcs = Multiline
 Everything that touches 2^k field elements runs on the GPU: the commitments (MSM), permutation_z_polys, the tables of the
 compiled zero-check expression (expression.py), the sum-check rounds and folds, the evaluations at the rotated points and
 additive::batch_open.  The host keeps what is scalar work in the reference too: the transcript, the expression tree, the
-interpolation of a round message.  Lookup arguments (lookup_compressed_polys / lookup_m_polys / lookup_h_polys,
-prover.rs:50-250) are composed into the expression like the reference does but have no GPU producers: `prove` refuses a
-circuit with lookups instead of falling back to the CPU.
+interpolation of a round message.  Lookup arguments run on the GPU as well (lookup_compressed_polys / lookup_m_polys /
+lookup_h_polys, prover.rs:50-250: csrc/lookup_kernels.cuh).
 """
 from __future__ import annotations
 
@@ -28,7 +27,8 @@ import numpy as np
 
 from . import kzg, sumcheck
 from .expression import BooleanHypercube, CompiledExpression, Expression, Query, compile_expression
-from .msm import ResidentScalars, eq_table, fr_affine_table, fr_evaluate, permutation_z_polys
+from .msm import (ResidentScalars, eq_table, fr_affine_table, fr_evaluate, fr_expression_table, lookup_h_poly, lookup_m_poly,
+                  permutation_z_polys)
 from .transcript import fr_to_montgomery
 
 FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
@@ -352,6 +352,31 @@ def build_tables(compiled: CompiledExpression, num_vars: int, polys: Sequence[Re
     return out
 
 
+def lookup_compressed_polys(lookups, polys: Sequence[ResidentScalars], challenges: Sequence[int], betas: Sequence[int]) -> List[List[ResidentScalars]]:
+    """prover.rs:50-137: per lookup the compressed input and table polynomials, sum_i betas[i] * expression_i evaluated on
+    every row (identity = row, Lagrange = one row, rotated queries by BooleanHypercube::rotate).  The expression tree is
+    compiled like the zero check's and evaluated row-wise by k_expr_rows."""
+    num_vars = polys[0].n.bit_length() - 1
+    out = []
+    for lookup in lookups:
+        pair = []
+        for exprs in ([inp for inp, _ in lookup], [tab for _, tab in lookup]):
+            total = exprs[0] * betas[0]
+            for e, b in zip(exprs[1:], betas[1:]):
+                total = total + e * b
+            compiled = compile_expression(total, challenges)
+            if not compiled.terms:
+                pair.append(fr_affine_table(num_vars, device=polys[0].device))      # identically zero
+                continue
+            st = build_tables(compiled, num_vars, polys, [])
+            try:
+                pair.append(fr_expression_table(st.tables, [(fr_to_montgomery(c), idx) for c, idx in compiled.terms], compiled.common))
+            finally:
+                st.release()
+        out.append(pair)
+    return out
+
+
 def prove_sum_check(num_instance_poly: int, expression: Expression, claimed_sum: int, polys: Sequence[ResidentScalars], challenges: Sequence[int],
                     y: Sequence[int], transcript) -> Tuple[List[List[int]], List[Tuple[int, int, int]]]:
     """prover.rs:367-409: ClassicSumCheck<EvaluationsProver>::prove over the virtual polynomial, then the evaluations of
@@ -395,8 +420,6 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
             marks.append((label, time.perf_counter()))
 
     mark("start")
-    if pp.lookups:
-        raise ValueError("HyperPlonk::prove: lookup arguments have no GPU producers in this library (prover.rs:50-250); no CPU fallback")
     instances = circuit.instances()
     assert len(instances) == len(pp.num_instances)
     for num, column in zip(pp.num_instances, instances):
@@ -420,22 +443,32 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
             challenges.extend(transcript.squeeze_challenges(num_c))
         mark("witness batch_commit")
         polys = inst_polys + pp.preprocess_polys + witness_polys
-        # Round n (no lookups: lookup_m_polys is empty and nothing is written, hyperplonk.rs:213-227)
+        # Round n (hyperplonk.rs:213-227)
         beta = transcript.squeeze_challenge()
+        max_lookup_width = max([len(lookup) for lookup in pp.lookups] or [0])
+        betas = [pow(beta, i, R) for i in range(max_lookup_width)]                # powers(beta).take(max_lookup_width)
+        compressed = lookup_compressed_polys(pp.lookups, polys, challenges, betas)
+        owned.extend(p for pair in compressed for p in pair)
+        lookup_m_polys = [lookup_m_poly(inp, tab) for inp, tab in compressed]        # Err(InvalidSnark) -> PlonkishCudaError
+        owned.extend(lookup_m_polys)
+        transcript.write_commitments([kzg.commit(pp.pcs, m) for m in lookup_m_polys])
+        mark("lookup m polys + commit")
         # Round n+1 (hyperplonk.rs:231-252)
         gamma = transcript.squeeze_challenge()
+        lookup_h_polys = [lookup_h_poly(inp, tab, m, fr_to_montgomery(gamma)) for (inp, tab), m in zip(compressed, lookup_m_polys)]
+        owned.extend(lookup_h_polys)
         z_polys: List[ResidentScalars] = []
         if pp.permutation_polys:
             z_polys = permutation_z_polys(pp.num_permutation_z_polys, [polys[idx] for idx, _ in pp.permutation_polys],
                                           [p for _, p in pp.permutation_polys], fr_to_montgomery(beta), fr_to_montgomery(gamma))
             owned.extend(z_polys)
-        mark("permutation_z_polys")
-        transcript.write_commitments([kzg.commit(pp.pcs, z) for z in z_polys])
-        mark("z commit")
+        mark("lookup h polys + permutation_z_polys")
+        transcript.write_commitments([kzg.commit(pp.pcs, p) for p in lookup_h_polys + z_polys])
+        mark("h / z commit")
         # Round n+2 (hyperplonk.rs:256-273)
         alpha = transcript.squeeze_challenge()
         y = transcript.squeeze_challenges(pp.num_vars)
-        polys = polys + [p for _, p in pp.permutation_polys] + z_polys
+        polys = polys + [p for _, p in pp.permutation_polys] + lookup_m_polys + lookup_h_polys + z_polys
         challenges = challenges + [beta, gamma, alpha]
         pts, evals = prove_sum_check(len(pp.num_instances), pp.expression, 0, polys, challenges, y, transcript)   # prove_zero_check
         mark("zero check + evals")

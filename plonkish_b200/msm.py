@@ -16,7 +16,7 @@ Everything is computed on the GPU; there is no CPU path.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -323,6 +323,43 @@ def fr_affine_table(num_vars: int, polys: Sequence["ResidentScalars"] = (), coef
                                                   rows.ctypes.data, vals.ctypes.data, len(sparse_rows), ctypes.byref(out))
     _lib.check(rc, "plonkish_cuda_fr_affine_table")
     return ResidentScalars._adopt(out.value, 1 << num_vars, device if not count else polys[0].device)
+
+
+def fr_expression_table(polys: Sequence["ResidentScalars"], terms, common: int = -1) -> "ResidentScalars":
+    """A compiled expression on every row: out[b] = (sum_t coeff_t * prod_j polys[idx_t,j][b]) (* polys[common][b]);
+    terms = [(coeff limbs, [poly indices])] as for the sum check.  lookup_compressed_poly (prover.rs:79-137) is one call."""
+    n = polys[0].n
+    num_vars = n.bit_length() - 1
+    handles = np.array([p.handle for p in polys], dtype=np.uint64)
+    coeffs = np.stack([_as_u64(c, 4, "coeff").reshape(4) for c, _ in terms])
+    offsets = np.zeros(len(terms) + 1, dtype=np.uint32)
+    flat: List[int] = []
+    for t, (_, idx) in enumerate(terms):
+        flat.extend(int(i) for i in idx)
+        offsets[t + 1] = len(flat)
+    flat_arr = np.array(flat if flat else [0], dtype=np.uint32)
+    out = ctypes.c_uint64(0)
+    rc = _lib.lib().plonkish_cuda_fr_expression_table(handles.ctypes.data, len(polys), num_vars, coeffs.ctypes.data, offsets.ctypes.data, flat_arr.ctypes.data,
+                                                      len(terms), int(common), ctypes.byref(out))
+    _lib.check(rc, "plonkish_cuda_fr_expression_table")
+    return ResidentScalars._adopt(out.value, n, polys[0].device)
+
+
+def lookup_m_poly(compressed_input: "ResidentScalars", compressed_table: "ResidentScalars") -> "ResidentScalars":
+    """lookup_m_poly (backend/hyperplonk/prover.rs:145-192) on resident polynomials; PlonkishCudaError("Invalid lookup input")
+    when an input value is not in the table."""
+    out = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_lookup_m_poly_bn254(compressed_input.handle, compressed_table.handle, ctypes.byref(out)), "plonkish_cuda_lookup_m_poly_bn254")
+    return ResidentScalars._adopt(out.value, compressed_input.n, compressed_input.device)
+
+
+def lookup_h_poly(compressed_input: "ResidentScalars", compressed_table: "ResidentScalars", m: "ResidentScalars", gamma) -> "ResidentScalars":
+    """lookup_h_poly (backend/hyperplonk/prover.rs:206-250): 1 / (gamma + input) - m / (gamma + table); gamma Montgomery limbs."""
+    g = np.ascontiguousarray(gamma, dtype=np.uint64).reshape(4)
+    out = ctypes.c_uint64(0)
+    rc = _lib.lib().plonkish_cuda_lookup_h_poly_bn254(compressed_input.handle, compressed_table.handle, m.handle, g.ctypes.data, ctypes.byref(out))
+    _lib.check(rc, "plonkish_cuda_lookup_h_poly_bn254")
+    return ResidentScalars._adopt(out.value, compressed_input.n, compressed_input.device)
 
 
 def fr_evaluate(poly: "ResidentScalars", points) -> np.ndarray:

@@ -147,6 +147,15 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) {
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
+static inline unsigned atomicCAS(unsigned *p, unsigned expect, unsigned v) {
+    __atomic_compare_exchange_n(p, &expect, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expect;  // the old value, as CUDA returns it
+}
+static inline unsigned atomicMax(unsigned *p, unsigned v) {
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

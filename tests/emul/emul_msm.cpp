@@ -7,6 +7,7 @@
 #include "../../plonkish_b200/csrc/msm_kernels.cuh"
 #include "../../plonkish_b200/csrc/poly_kernels.cuh"
 #include "../../plonkish_b200/csrc/sumcheck_kernels.cuh"
+#include "../../plonkish_b200/csrc/lookup_kernels.cuh"
 #include "../../plonkish_b200/csrc/dpfq.cuh"
 
 #include <stdlib.h>
@@ -308,6 +309,38 @@ void emul_fr_affine(const void *const *polys, const int *rotations, const void *
     }
     PK_LAUNCH(k_fr_affine, dim3(3), dim3(64), 0, 0, a, (size_t)1 << num_vars, (uint4 *)out);
     if (sparse_count) PK_LAUNCH(k_fr_sparse_add, dim3(1), dim3(32), 0, 0, (uint4 *)out, rows, (const uint4 *)values, sparse_count);
+}
+// ---- lookup argument producers (lookup_kernels.cuh)
+static void emul_fill_expr(SumcheckPolys &ps, SumcheckExpr &ex, const void *const *polys, u32 num_polys, const void *coeffs, const u32 *offsets,
+                           const u32 *term_polys, u32 num_terms, int common, u32 degree) {
+    memset(&ps, 0, sizeof(ps));
+    memset(&ex, 0, sizeof(ex));
+    for (u32 p = 0; p < num_polys; ++p) ps.p[p] = (const uint4 *)polys[p];
+    static const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    ex.num_terms = num_terms; ex.num_polys = num_polys; ex.degree = degree; ex.common = common;
+    for (u32 t = 0; t < num_terms; ++t) {
+        memcpy(ex.coeff[t].l, (const char *)coeffs + (size_t)t * 32, 32);
+        ex.has_coeff[t] = memcmp(ex.coeff[t].l, FR_ONE, 32) != 0;
+        ex.nfac[t] = (unsigned char)(offsets[t + 1] - offsets[t]);
+        for (u32 j = offsets[t]; j < offsets[t + 1]; ++j) ex.fac[t][j - offsets[t]] = (unsigned char)term_polys[j];
+    }
+}
+void emul_expr_rows(const void *const *polys, u32 num_polys, u32 n, const void *coeffs, const u32 *offsets, const u32 *term_polys, u32 num_terms,
+                    int common, void *out) {
+    SumcheckPolys ps;
+    SumcheckExpr ex;
+    emul_fill_expr(ps, ex, polys, num_polys, coeffs, offsets, term_polys, num_terms, common, 1);
+    pk_enqueue_expr_rows(ps, ex, n, out, 1, 0);
+}
+// returns 1 when an input value is missing from the table (the reference's Err, prover.rs:176-178)
+int emul_lookup_m(const void *input, const void *table, u32 n, void *out) {
+    std::vector<u32> slots(pk_lookup_slots(n)), counts(n);
+    u32 missing = 0;
+    pk_enqueue_lookup_m(input, table, n, slots.data(), counts.data(), &missing, out, 2, 0);
+    return (int)missing;
+}
+void emul_lookup_h(const void *input, const void *table, const void *m, const void *gamma, u32 n, void *out) {
+    pk_enqueue_lookup_h(input, table, m, gamma, n, out, 0);
 }
 void emul_sumcheck_fold(const void *const *polys, void *const *outs, u32 num_polys, u32 n, const void *challenge, u32 sm_count) {
     SumcheckFoldArgs a;

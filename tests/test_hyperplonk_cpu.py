@@ -329,3 +329,105 @@ def test_emulated_affine_table_kernel_matches_python_integers(emul, k):
                             rw.ctypes.data, vs.ctypes.data, len(rows), out.ctypes.data)
         want = affine_table_python(k, polys, coeffs, rotations, constant, id_coeff, rows, values)
         assert out.tobytes() == ref.mont_rows(want).tobytes()
+
+
+# ------------------------------------------------------------------------------------------------ lookups
+def _lookup_info(hp, k, preprocess, cycles, num_instances):
+    pi, q_l, q_r, q_m, q_o, q_c, q_lookup, t_l, t_r, t_o, w_l, w_r, w_o = (Expression.polynomial(p) for p in range(13))
+    return hp.PlonkishCircuitInfo(
+        k=k, num_instances=[num_instances], preprocess_polys=preprocess, num_witness_polys=[3], num_challenges=[0],
+        constraints=[q_l * w_l + q_r * w_r + q_m * w_l * w_r + q_o * w_o + q_c + pi],
+        lookups=[[(q_lookup * w_l, t_l), (q_lookup * w_r, t_r), (q_lookup * w_o, t_o)]], permutations=cycles, max_degree=4)   # util.rs:63-86
+
+
+def test_compiled_lookup_expression_equals_the_tree_and_fits_the_kernel_limits():
+    hp = _hp()
+    rng = np.random.default_rng(21)
+    k = 4
+    info = _lookup_info(hp, k, [np.zeros((16, 4), dtype=np.uint64)] * 9, [[(10, 1)], [(11, 1)], [(12, 1)]], 0)
+    _, expression = hp.compose(info)
+    challenges = [_fe(rng) for _ in range(3)]
+    compiled = compile_expression(expression, challenges)
+    leaf = _leaf_values(expression, rng)
+    assert compiled.value(leaf) == expression.evaluate_field(lambda p: leaf(tuple(p)), lambda q: leaf(("poly", q.poly, q.rotation)), challenges)
+    assert compiled.common == -1 and compiled.degree == expression.degree() == 5      # the h term carries no eq_xy
+    plain = {a.leaf()[1] for a in compiled.atoms if a.is_leaf() and a.leaf()[0] == "poly" and a.leaf()[2] == 0}
+    riders = {q.poly for q in hp.pcs_query(expression, 1)} - plain
+    assert len(compiled.atoms) + len(riders) <= 48 and len(compiled.terms) <= 32 and max(len(f) for _, f in compiled.terms) <= 8
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_integer_lookup_prover_is_accepted_by_the_integer_verifier(oracle, k):
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    rng = np.random.default_rng(60 + k)
+    ss = [_fe(rng) for _ in range(k)]
+    eqs_host = [oracle.fixed_base_msm(oracle.generator(), e) for e in oracle.kzg_eq_scalars(ref.mont_rows(ss))]
+    commit = lambda f: oracle.variable_base_msm(ref.mont_rows(f), eqs_host[k])  # noqa: E731
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_with_lookup_circuit(k, rng)
+    sigmas = ref.permutation_polys(k, [10, 11, 12], cycles)
+    t = Keccak256Transcript()
+    state = ref.prove_reference_lookup(commit, ref.oracle_batch_open(oracle, eqs_host, k), k, instances, preprocess, witness, sigmas, t)
+    proof = t.into_proof()
+    assert sum(state["m"]) == 1 << k and state["m"][0] == 0     # every row looks something up; the repeated value 0 counts at row 1
+    affine = lambda limbs: br.point_from_bytes(np.ascontiguousarray(limbs).tobytes())  # noqa: E731
+    pre_comms = [affine(commit(p)) for p in preprocess]
+    perm_comms = [affine(commit(s)) for s in sigmas]
+    ref.verify_reference_lookup(oracle.keccak256, ss, k, instances, pre_comms, perm_comms, proof)
+    bad = bytearray(proof)
+    bad[6 * 64 + 11] ^= 1
+    with pytest.raises(AssertionError):
+        ref.verify_reference_lookup(oracle.keccak256, ss, k, instances, pre_comms, perm_comms, bytes(bad))
+
+
+@pytest.fixture(scope="module")
+def emul_lookup():
+    subprocess.run(["make", "-C", EMUL_DIR], check=True, capture_output=True)
+    lib = ctypes.CDLL(os.path.join(EMUL_DIR, "libemul_msm.so"))
+    vp, u32, ci = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
+    lib.emul_expr_rows.argtypes = [vp, u32, u32, vp, vp, vp, u32, ci, vp]
+    lib.emul_lookup_m.argtypes = [vp, vp, u32, vp]
+    lib.emul_lookup_m.restype = ci
+    lib.emul_lookup_h.argtypes = [vp, vp, vp, vp, u32, vp]
+    return lib
+
+
+def test_emulated_lookup_kernels_match_python_integers(emul_lookup, oracle):
+    rng = np.random.default_rng(77)
+    for k in (1, 5, 9):
+        n = 1 << k
+        # an expression on every row: 3 * p0 * p1 + p2 - 7 (times p3)
+        polys = [[_fe(rng) for _ in range(n)] for _ in range(4)]
+        terms_int = [(3, [0, 1]), (1, [2]), (R - 7, [])]
+        terms = [(ref.to_mont(c), idx) for c, idx in terms_int]
+        coeffs, offsets, flat = oracle.flatten_terms(terms)
+        arrs = [ref.mont_rows(p) for p in polys]
+        ptrs = (ctypes.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+        for common in (-1, 3):
+            out = np.zeros((n, 4), dtype=np.uint64)
+            emul_lookup.emul_expr_rows(ptrs, 4, n, coeffs.ctypes.data, offsets.ctypes.data, flat.ctypes.data, len(terms), common, out.ctypes.data)
+            want = [((3 * polys[0][b] * polys[1][b] + polys[2][b] - 7) * (polys[3][b] if common >= 0 else 1)) % R for b in range(n)]
+            assert out.tobytes() == ref.mont_rows(want).tobytes()
+        # multiplicities: a table with repeated values (0 twice, as util.rs:224-230 builds it), inputs drawn from it
+        table = [0, 0] + [_fe(rng) for _ in range(n - 2)] if n > 2 else [0] * n
+        if n > 4:
+            table[n - 1] = table[3]                                    # another repeated value: its last row is n - 1
+        inputs = [table[int(i)] for i in rng.integers(0, n, n)]
+        index = {v: i for i, v in enumerate(table)}
+        want_m = [0] * n
+        for v in inputs:
+            want_m[index[v]] += 1
+        tab_a, in_a = ref.mont_rows(table), ref.mont_rows(inputs)
+        m_out = np.zeros((n, 4), dtype=np.uint64)
+        assert emul_lookup.emul_lookup_m(in_a.ctypes.data, tab_a.ctypes.data, n, m_out.ctypes.data) == 0
+        assert m_out.tobytes() == ref.mont_rows(want_m).tobytes()
+        gamma = _fe(rng)
+        h_out = np.zeros((n, 4), dtype=np.uint64)
+        emul_lookup.emul_lookup_h(in_a.ctypes.data, tab_a.ctypes.data, m_out.ctypes.data, ref.to_mont(gamma).ctypes.data, n, h_out.ctypes.data)
+        want_h = ref.lookup_h_python(inputs, table, want_m, gamma)
+        assert h_out.tobytes() == ref.mont_rows(want_h).tobytes()
+        assert sum(want_h) % R == 0                                     # the argument's identity (prover.rs:245-247)
+        # an input outside the table is reported
+        bad = list(inputs)
+        bad[n // 2] = (max(table) + 1) % R if (max(table) + 1) % R not in index else 12345
+        assert emul_lookup.emul_lookup_m(ref.mont_rows(bad).ctypes.data, tab_a.ctypes.data, n, m_out.ctypes.data) == 1

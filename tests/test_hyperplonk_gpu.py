@@ -163,19 +163,101 @@ def test_gpu_proof_is_accepted_by_the_reference_verifier(pk, oracle, k):
     pp.release()
 
 
-def test_prove_refuses_lookups_instead_of_falling_back(pk, oracle):
+def _lookup_info(k, preprocess, cycles, num_instances):
     from plonkish_b200 import hyperplonk
     from plonkish_b200.expression import Expression
+
+    pi, q_l, q_r, q_m, q_o, q_c, q_lookup, t_l, t_r, t_o, w_l, w_r, w_o = (Expression.polynomial(p) for p in range(13))
+    return hyperplonk.PlonkishCircuitInfo(
+        k=k, num_instances=[num_instances], preprocess_polys=[ref.mont_rows(p) for p in preprocess], num_witness_polys=[3], num_challenges=[0],
+        constraints=[q_l * w_l + q_r * w_r + q_m * w_l * w_r + q_o * w_o + q_c + pi],
+        lookups=[[(q_lookup * w_l, t_l), (q_lookup * w_r, t_r), (q_lookup * w_o, t_o)]], permutations=cycles, max_degree=4)   # util.rs:63-86
+
+
+def _prove_lookup_on_gpu(pk, pp, k, instances, preprocess, witness, cycles):
+    from plonkish_b200 import hyperplonk
     from plonkish_b200.transcript import Keccak256Transcript
 
-    rng = np.random.default_rng(5)
-    k = 3
-    _, pp = _setup(pk, oracle, k, rng)
-    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_circuit(k, rng)
-    info = hyperplonk.vanilla_plonk_circuit_info(k, len(instances), [ref.mont_rows(p) for p in preprocess], cycles)
-    info.lookups = [[(Expression.polynomial(6), Expression.polynomial(1))]]
-    hpp, _ = hyperplonk.preprocess(pp, info)
-    with pytest.raises(ValueError):
-        hyperplonk.prove(hpp, _Circuit(instances, witness), Keccak256Transcript())
-    hpp.release()
+    hpp, hvp = hyperplonk.preprocess(pp, _lookup_info(k, preprocess, cycles, len(instances)))
+    t = Keccak256Transcript()
+    try:
+        hyperplonk.prove(hpp, _Circuit(instances, witness), t)
+    finally:
+        hpp.release()
+    return t.into_proof(), hvp
+
+
+@pytest.mark.parametrize("k", [1, 6, 12])
+def test_lookup_producers_match_python_integers(pk, oracle, k):
+    """plonkish_cuda_fr_expression_table / _lookup_m_poly / _lookup_h_poly (prover.rs:50-250) against Python integers:
+    repeated table values count at their last row, an input outside the table is refused."""
+    rng = np.random.default_rng(500 + k)
+    n = 1 << k
+    polys = [[_fe(rng) for _ in range(n)] for _ in range(4)]
+    resident = [pk.ResidentScalars(ref.mont_rows(p)) for p in polys]
+    terms = [(ref.to_mont(3), [0, 1]), (ref.to_mont(1), [2]), (ref.to_mont(R - 7), [])]
+    for common in (-1, 3):
+        out = pk.fr_expression_table(resident, terms, common)
+        want = [((3 * polys[0][b] * polys[1][b] + polys[2][b] - 7) * (polys[3][b] if common >= 0 else 1)) % R for b in range(n)]
+        assert out.to_host().tobytes() == ref.mont_rows(want).tobytes()
+        out.release()
+    table = ([0, 0] + [_fe(rng) for _ in range(n - 2)]) if n > 2 else [0] * n
+    if n > 4:
+        table[n - 1] = table[3]
+    inputs = [table[int(i)] for i in rng.integers(0, n, n)]
+    index = {v: i for i, v in enumerate(table)}
+    want_m = [0] * n
+    for v in inputs:
+        want_m[index[v]] += 1
+    tab, inp = pk.ResidentScalars(ref.mont_rows(table)), pk.ResidentScalars(ref.mont_rows(inputs))
+    m = pk.lookup_m_poly(inp, tab)
+    assert m.to_host().tobytes() == ref.mont_rows(want_m).tobytes()
+    gamma = _fe(rng)
+    h = pk.lookup_h_poly(inp, tab, m, ref.to_mont(gamma))
+    assert h.to_host().tobytes() == ref.mont_rows(ref.lookup_h_python(inputs, table, want_m, gamma)).tobytes()
+    bad = list(inputs)
+    bad[n // 2] = next(v for v in (12345, 12346, 12347) if v not in index)
+    bad_r = pk.ResidentScalars(ref.mont_rows(bad))
+    with pytest.raises(pk.PlonkishCudaError, match="Invalid lookup input"):
+        pk.lookup_m_poly(bad_r, tab)
+    for r_ in resident + [tab, inp, m, h, bad_r]:
+        r_.release()
+
+
+@pytest.mark.parametrize("k", [3, 4, 5])
+def test_lookup_proof_bytes_match_the_integer_reference_prover(pk, oracle, k):
+    """HyperPlonk::prove for vanilla_plonk_with_lookup (the reference's second test circuit, backend/hyperplonk.rs:371-427):
+    proof bytes identical to the all-integer prover, preprocess commitments identical to the oracle's."""
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    rng = np.random.default_rng(600 + k)
+    ss, pp = _setup(pk, oracle, k, rng)
+    eqs_host = [pp.eq(i).to_host() for i in range(k + 1)]
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_with_lookup_circuit(k, rng)
+    proof, hvp = _prove_lookup_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    commit = lambda f: oracle.variable_base_msm(ref.mont_rows(f), eqs_host[k])  # noqa: E731
+    sigmas = ref.permutation_polys(k, [10, 11, 12], cycles)
+    t = Keccak256Transcript()
+    ref.prove_reference_lookup(commit, ref.oracle_batch_open(oracle, eqs_host, k), k, instances, preprocess, witness, sigmas, t)
+    assert proof == t.into_proof()
+    pp.release()
+
+
+@pytest.mark.parametrize("k", [8, 11])
+def test_gpu_lookup_proof_is_accepted_by_the_reference_verifier(pk, oracle, k):
+    rng = np.random.default_rng(700 + k)
+    ss, pp = _setup(pk, oracle, k, rng)
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_with_lookup_circuit(k, rng)
+    proof, hvp = _prove_lookup_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    affine = lambda limbs: br.point_from_bytes(np.ascontiguousarray(limbs).tobytes())  # noqa: E731
+    pre = [affine(c) for c in hvp.preprocess_comms]
+    perm = [affine(c) for _, c in hvp.permutation_comms]
+    ref.verify_reference_lookup(oracle.keccak256, ss, k, instances, pre, perm, proof)
+    assert len(proof) == 6 * 64 + k * 6 * 32 + 20 * 32 + k * 3 * 32 + k * 64
+    # a witness value that is not in the table: lookup_m_polys fails like the reference (Error::InvalidSnark, prover.rs:176-178)
+    row = next(b for b in range(1 << k) if preprocess[5][b] == 1)
+    bad = [list(w) for w in witness]
+    bad[0][row] = (bad[0][row] + 1) % R
+    with pytest.raises(pk.PlonkishCudaError, match="Invalid lookup input"):
+        _prove_lookup_on_gpu(pk, pp, k, instances, preprocess, bad, cycles)
     pp.release()
