@@ -15,7 +15,11 @@ fn main() {
     let src = PathBuf::from(env::var("PLONKISH_CUDA_SRC").expect("set PLONKISH_CUDA_SRC or PLONKISH_CUDA_LIB_DIR"));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let api = src.join("plonkish_b200/csrc/api.cu");
-    for f in ["api.cu", "fq.cuh", "g1.cuh", "msm_kernels.cuh"] {
+    let host_copy = src.join("plonkish_b200/csrc/host_copy.cpp");
+    for f in [
+        "api.cu", "host_copy.cpp", "fq.cuh", "g1.cuh", "msm_kernels.cuh", "poly_kernels.cuh", "sumcheck_kernels.cuh", "lookup_kernels.cuh",
+        "dpfq.cuh",
+    ] {
         println!("cargo:rerun-if-changed={}", src.join("plonkish_b200/csrc").join(f).display());
     }
     let lib = out.join("libplonkish_cuda.so");
@@ -24,6 +28,7 @@ fn main() {
         .args(["-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
         .arg(&api)
+        .arg(&host_copy)
         .status()
         .expect("nvcc not found");
     assert!(status.success(), "nvcc failed");

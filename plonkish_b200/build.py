@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = [os.path.join(_HERE, "csrc", "api.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "api.cu"), os.path.join(_HERE, "csrc", "host_copy.cpp")]
 HEADERS = [
     os.path.join(_HERE, "csrc", h) for h in ("fq.cuh", "g1.cuh", "msm_kernels.cuh", "poly_kernels.cuh", "sumcheck_kernels.cuh", "lookup_kernels.cuh", "dpfq.cuh")
 ] + [os.path.join(os.path.dirname(_HERE), "include", "plonkish_cuda.h")]

@@ -262,6 +262,8 @@ static Ctx *ctx_for(int device) {
 // cudaMemcpyAsync per piece on the destination stream, so the host-side copy of the next pieces runs while the
 // DMA engine moves the current one (about the bandwidth of the pinned path once 4+ threads copy).  Pinned /
 // registered sources (cudaPointerGetAttributes) keep the direct single cudaMemcpyAsync.
+extern "C" void plonkish_cuda_host_copy(void *dst, const void *src, size_t len, int stream);  // host_copy.cpp
+
 class Stager {
 public:
     static const size_t SLOT = (size_t)4 << 20;
@@ -311,6 +313,7 @@ private:
         }
         nthreads_ = t;
         nslots_ = 2 * t + 2;
+        if (const char *e = getenv("PLONKISH_CUDA_STAGE_NT")) stream_stores_ = e[0] == '1';  // host_copy.cpp
     }
     bool ensure_ready(int dev) {
         if (slots_.empty()) {
@@ -365,7 +368,7 @@ private:
             if (slot_dev_[s] >= 0) e = cudaEventSynchronize(slot_ev_[s][slot_dev_[s]]);
             const size_t off = i * piece_;
             const size_t len = bytes_ - off < piece_ ? bytes_ - off : piece_;
-            memcpy(slots_[s], src_ + off, len);
+            plonkish_cuda_host_copy(slots_[s], src_ + off, len, stream_stores_ ? 1 : 0);
             if (e == cudaSuccess) e = cudaMemcpyAsync(dst_ + off, slots_[s], len, cudaMemcpyHostToDevice, stream_);
             if (e == cudaSuccess) e = cudaEventRecord(slot_ev_[s][dev], stream_);
             {
@@ -380,6 +383,7 @@ private:
         }
     }
     int nthreads_ = 2, nslots_ = 6;
+    bool stream_stores_ = false;
     std::vector<void *> slots_;
     std::vector<std::vector<cudaEvent_t>> slot_ev_;  // [slot][device]
     std::vector<int> slot_dev_;                      // device whose event the slot's last piece recorded
@@ -787,6 +791,26 @@ static MsmPlan plan_for(const Ctx *c, const BasesView &b, size_t n, uint32_t win
         // the big launches issue bound, while small ones save the digit round trip and a launch's worth of latency).
         static const int fuse = [] { const char *e = getenv("PLONKISH_CUDA_FUSE_L1"); return e ? atoi(e) : -1; }();  // A/B switch: 0 / 1 force
         p.fuse_l1 = fuse >= 0 ? (u32)(fuse != 0) : (n <= ((size_t)1 << 21) ? 1u : 0u);
+        // tuning overrides (read per call so that one process can sweep them): the run length of a K3 thread, directly or as
+        // the number of waves of resident threads the launch should make
+        if (const char *e = getenv("PLONKISH_CUDA_ACC_WAVES")) {
+            const double waves = atof(e);
+            if (waves > 0) {
+                double L = (double)n * p.W / ((double)c->sm_count * 512.0 * waves);
+                pk_set_run_length(p, (u32)(L < 16 ? 16 : L > 1024 ? 1024 : L));
+            }
+        }
+        if (const char *e = getenv("PLONKISH_CUDA_ACC_L")) {  // equal runs of L entries instead of the tiers
+            const long L = atol(e);
+            if (L >= 1 && L <= 4096) pk_set_run_length(p, (u32)L);
+        }
+        if (const char *e = getenv("PLONKISH_CUDA_ACC_TIERS")) {  // number of tiers (1 = equal runs of rem / (2 R))
+            const long J = atol(e);
+            if (J >= 1 && J <= 16 && p.acc_tiers) {
+                p.acc_tiers = (u32)J;
+                p.nthreads1 = pk_acc_threads((unsigned long long)p.n * p.W, p.acc_tiers, p.acc_resident);
+            }
+        }
         return p;
     }
     return pk_make_plan((u32)n, window_bits, (u32)c->sm_count);

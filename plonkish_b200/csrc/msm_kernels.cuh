@@ -89,6 +89,8 @@ struct MsmPlan {
     u32 chunk;        // which of the MSM's bucket arrays this launch sequence fills (host path pipelining)
     u32 nchunks;      // bucket arrays the reduce phase adds up (1 unless the host path cut the points into chunks)
     u32 fuse_l1;      // mode 1, c >= 16: level 1 of the sort recomputes the digits from the scalars (no digit array)
+    u32 acc_tiers;    // K3 run lengths: 0 = every thread takes L entries; J > 0 = up to J tiers of decreasing run length (pk_acc_run)
+    u32 acc_resident; // K3 threads the device holds at once (sm_count * 512)
 };
 
 inline u32 pk_ceil_log2(u32 v) {
@@ -128,6 +130,104 @@ inline void pk_plan_reduce(MsmPlan &p, u32 sm_count) {
     p.red_blocks = (p.red_threads + PK_RED_BLOCK - 1) / PK_RED_BLOCK;
 }
 
+// ---------------------------------------------------------------- K3 run lengths
+// Thread t of k_accumulate sums one run of consecutive sorted entries and leaves two items for the segmented
+// reduction.  Every run costs about 3.5 mixed additions on top of its entries (the items), and a launch of equal runs
+// ends with a ragged last wave: a slot that frees up late finds no work, about half a run's duration per slot
+// (measured on B200, tools/acc_run_length.py: the accumulate of 2^21 points takes 4.28 ms with 3 waves of 119-entry
+// runs, 3.65 ms with 24 waves of 16 — but then the items cost 0.64 ms instead of 0.14).  So the runs shrink as the launch
+// proceeds (guided self-scheduling; blocks are dispatched in index order): tier j takes half of what is left in runs
+// of rem / (2 R) entries — one wave of the R resident threads — until the runs reach 16 entries or the last of J tiers
+// takes the rest.  About (J + 1) R threads in all, a tail of 2^-(J+1) of the work.  The tiers depend on the actual
+// entry count (zero digits are dropped, skewed scalars drop most of them), so every thread derives its run from
+// `total` on the device; the host only sizes the launch (pk_acc_threads) for the largest count.
+#define PK_ACC_LMIN 16u
+#define PK_ACC_LMAX 1024u
+#ifndef PLONKISH_EMUL
+#define PK_HOST_DEVICE __host__ __device__ __forceinline__
+#else
+#define PK_HOST_DEVICE inline
+#endif
+PK_HOST_DEVICE u32 pk_acc_tier_len(u32 rem, u32 resident) {
+    const u32 r2 = 2u * resident;
+    u32 L = (rem + r2 - 1u) / r2;
+    L = (L + 7u) & ~7u;  // multiples of 8 keep the lanes' reads of `sorted` on sector boundaries
+    if (L < PK_ACC_LMIN) L = PK_ACC_LMIN;
+    if (L > PK_ACC_LMAX) L = PK_ACC_LMAX;
+    return L;
+}
+// The run [s, e) of thread t among nthreads for `total` entries; false when the thread has none.
+PK_HOST_DEVICE bool pk_acc_run(u32 t, u32 total, u32 tiers, u32 resident, u32 nthreads, u32 uniform_L, u32 &s, u32 &e) {
+    if (tiers == 0) {
+        const unsigned long long s64 = (unsigned long long)t * uniform_L;
+        if (s64 >= total) return false;
+        s = (u32)s64;
+        e = (total - s < uniform_L) ? total : s + uniform_L;
+        return true;
+    }
+    u32 start = 0, tid = t, avail = nthreads;
+    for (u32 j = 0; j < tiers; ++j) {
+        const u32 rem = total - start;
+        if (rem == 0 || avail == 0) return false;
+        u32 L = pk_acc_tier_len(rem, resident);
+        const u32 nb = (rem / 2u) / (128u * L);  // whole 128-thread blocks, so no idle thread sits between two runs
+        if (j + 1 == tiers || L == PK_ACC_LMIN || nb == 0 || nb * 128u >= avail) {
+            // last tier: everything that is left, in runs long enough for the threads that are left
+            u32 need = (rem + avail - 1u) / avail;
+            need = (need + 7u) & ~7u;
+            if (need > L) L = need;
+            const unsigned long long off = (unsigned long long)tid * L;
+            if (off >= rem) return false;
+            s = start + (u32)off;
+            e = (rem - (u32)off < L) ? total : s + L;
+            return true;
+        }
+        const u32 nt = nb * 128u;
+        if (tid < nt) {
+            s = start + tid * L;
+            e = s + L;
+            return true;
+        }
+        tid -= nt;
+        avail -= nt;
+        start += nt * L;
+    }
+    return false;
+}
+// Threads to launch so that pk_acc_run covers any total <= entries: a non-final tier holds at most max(R, rem / 2 / LMAX)
+// threads, the final one at most max(2 R, rem / LMAX) (+ rounding); never more than runs of LMIN entries would need.
+inline u32 pk_acc_threads(unsigned long long entries, u32 tiers, u32 resident) {
+    unsigned long long nt = 256ull;
+    for (u32 j = 0; j + 1 < tiers; ++j) {
+        const unsigned long long clamped = (entries >> (j + 1)) / PK_ACC_LMAX;  // half of what is left, in runs of LMAX
+        nt += clamped > resident ? clamped : resident;
+    }
+    const unsigned long long last = (entries >> (tiers - 1)) / PK_ACC_LMAX;
+    nt += last > 2ull * resident ? last : 2ull * resident;
+    const unsigned long long cap = (entries + PK_ACC_LMIN - 1) / PK_ACC_LMIN + 128ull * tiers;
+    if (nt > cap) nt = cap;
+    return (u32)((nt + 127ull) & ~127ull);
+}
+
+// Launch geometry of K3.  L > 0: equal runs of L entries (tuning / tests); L = 0: the tiers above.
+#define PK_ACC_TIERS 7u
+inline void pk_set_run_length(MsmPlan &p, u32 L) {
+    const unsigned long long emax = (unsigned long long)p.n * p.W;
+    if (L == 0 && emax > 32ull * PK_ACC_LMIN) {
+        p.acc_tiers = PK_ACC_TIERS;
+        p.L = pk_acc_tier_len((u32)emax, p.acc_resident);  // first tier's run for the largest entry count (reported by msm_plan)
+        p.nthreads1 = pk_acc_threads(emax, p.acc_tiers, p.acc_resident);
+        p.blk_acc = 128u;
+        return;
+    }
+    p.acc_tiers = 0;
+    p.L = L ? L : PK_ACC_LMIN;
+    const unsigned long long t1 = (emax + p.L - 1) / p.L;
+    // one warp -> a 32-thread terminal launch; otherwise whole 128-thread blocks
+    p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
+    p.blk_acc = (t1 <= 32) ? 32u : 128u;
+}
+
 inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     MsmPlan p;
     p.n = n;
@@ -151,16 +251,8 @@ inline MsmPlan pk_make_plan(u32 n, u32 c_override, u32 sm_count) {
     while (tile < 65536 && (n + tile - 1) / tile > 1024) tile <<= 1;
     p.tile = tile;
     p.ntiles = (n + tile - 1) / tile;
-    unsigned long long emax = (unsigned long long)n * p.W;
-    unsigned long long resident = (unsigned long long)sm_count * 512ull;
-    unsigned long long L = emax / (resident * 3ull);
-    if (L < 16) L = 16;
-    if (L > 256) L = 256;
-    p.L = (u32)L;
-    unsigned long long t1 = (emax + L - 1) / L;
-    // one warp -> a 32-thread terminal launch; otherwise whole 128-thread blocks
-    p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
-    p.blk_acc = (t1 <= 32) ? 32u : 128u;
+    p.acc_resident = sm_count * 512u;
+    pk_set_run_length(p, 0);
     p.ngroups = p.W;
     pk_plan_reduce(p, sm_count);
     p.blk = 256;
@@ -212,15 +304,7 @@ inline MsmPlan pk_make_plan_b(u32 n, u32 c, u32 stride, u32 sm_count) {
     // enough tiles to fill the GPU with one such block per SM (measured at 2^24: scatter 1.22 -> 1.03 ms,
     // level 2 1.35 -> 1.27 ms; smaller MSMs have tiles shorter than such a stage: 2^22 0.41 -> 0.55 ms)
     p.blk_stage = (p.tile >= 16384) ? 1024 : 512;  // a tile row holds at least one 16 K-entry stage: n > 2^23
-    unsigned long long emax = (unsigned long long)n * p.W;
-    unsigned long long resident = (unsigned long long)sm_count * 512ull;
-    unsigned long long L = emax / (resident * 3ull);
-    if (L < 16) L = 16;
-    if (L > 256) L = 256;
-    p.L = (u32)L;
-    unsigned long long t1 = (emax + L - 1) / L;
-    p.nthreads1 = (t1 <= 32) ? 32u : (u32)((t1 + 127ull) & ~127ull);
-    p.blk_acc = (t1 <= 32) ? 32u : 128u;
+    pk_set_run_length(p, 0);
     pk_plan_reduce(p, sm_count);
     return p;
 }
@@ -1089,13 +1173,11 @@ __global__ void __launch_bounds__(128, PK_ACC_MIN_BLOCKS) k_accumulate(const u32
                                                        u32 *__restrict__ out_keys, xyzz *__restrict__ out_pts) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 total = bucket_start[p.nbuckets];
-    const unsigned long long s64 = (unsigned long long)t * p.L;
     u32 hk = PK_INVALID_KEY, tk = PK_INVALID_KEY;
     xyzz acc = xyzz_identity();
     bool head_written = false;
-    if (s64 < total) {
-        const u32 s = (u32)s64;
-        const u32 e = (s + p.L < total) ? s + p.L : total;
+    u32 s = 0, e = 0;
+    if (pk_acc_run(t, total, p.acc_tiers, p.acc_resident, p.nthreads1, p.L, s, e)) {
         // largest g with bucket_start[g] <= s
         u32 lo = 0, hi = p.nbuckets;
         while (hi - lo > 1) {

@@ -171,6 +171,17 @@ void emul_plan(u32 n, u32 c, u32 sms, u32 *out /*[8]*/) {
     out[5] = p.tile; out[6] = p.L; out[7] = p.nthreads1;
 }
 
+// K3's run of every thread for `total` entries: s_out/e_out[nthreads] (s == e == 0xffffffff: no run).  Returns the
+// thread count pk_acc_threads sizes for `entries` (the largest total the launch is planned for).
+u32 emul_acc_runs(unsigned long long entries, u32 total, u32 tiers, u32 resident, u32 *s_out, u32 *e_out, u32 cap) {
+    const u32 nthreads = pk_acc_threads(entries, tiers, resident);
+    for (u32 t = 0; t < nthreads && t < cap; ++t) {
+        u32 s = 0, e = 0;
+        if (pk_acc_run(t, total, tiers, resident, nthreads, 0, s, e)) { s_out[t] = s; e_out[t] = e; } else { s_out[t] = e_out[t] = 0xffffffffu; }
+    }
+    return nthreads;
+}
+
 // Full launch sequence on host memory.  digits_out (optional): [W][n_pad] u16;
 // sorted_out / bucket_start_out (optional) sized n*W and nbuckets+1.
 int emul_msm(const void *scalars, const void *bases, u32 n, u32 c_override, u32 sm_count, u32 serial_items, void *out_affine64,

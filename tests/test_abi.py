@@ -108,3 +108,25 @@ def test_timer_lines_have_the_format_the_plotter_parses():
             if "End:" in line:
                 assert len(line.encode()) - 2 * depth >= 75  # the message is padded with dots to perf_trace's width
     assert lib.plonkish_cuda_timer_config(3, 0) != 0
+
+
+def test_staging_copy_with_streaming_stores_copies_exactly():
+    """host_copy.cpp: the copy into the pinned staging ring, plain and with non-temporal stores, for every
+    alignment of source and destination and lengths around the 128-byte blocks (bytes outside the range stay)."""
+    import ctypes
+
+    from plonkish_b200 import _lib
+
+    lib = _lib.load()
+    lib.plonkish_cuda_host_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    lib.plonkish_cuda_host_copy.restype = None
+    rng = np.random.default_rng(5)
+    for stream in (0, 1):
+        for ln in (0, 1, 31, 32, 33, 127, 128, 129, 4095, 65536, (1 << 18) + 77):
+            for so in (0, 1, 17):
+                for do in (0, 5, 32):
+                    src = rng.integers(0, 256, ln + 64, dtype=np.uint8)
+                    dst = np.zeros(ln + 128, dtype=np.uint8)
+                    lib.plonkish_cuda_host_copy(dst.ctypes.data + do, src.ctypes.data + so, ln, stream)
+                    assert (dst[do:do + ln] == src[so:so + ln]).all()
+                    assert not dst[:do].any() and not dst[do + ln:].any()

@@ -115,6 +115,42 @@ def test_plan_invariants(emul):
             assert threads * run >= n * w and threads % 32 == 0
 
 
+def test_accumulate_runs_partition_the_entries(emul):
+    """pk_acc_run (k_accumulate's tiers of decreasing run length): for any entry count up to the planned one the runs are
+    consecutive, cover [0, total) exactly once, busy threads come before idle ones, whole blocks share a run length in
+    the non-final tiers, and the runs shrink."""
+    import ctypes
+
+    u32 = ctypes.c_uint32
+    fn = emul.emul_acc_runs
+    fn.argtypes = [ctypes.c_uint64, u32, u32, u32, ctypes.c_void_p, ctypes.c_void_p, u32]
+    fn.restype = u32
+    rng = np.random.default_rng(11)
+    cases = [(148 * 512, e) for e in (600, 5000, 98304, 1 << 20, 7_864_320, 27_262_976, 201_326_592, (1 << 26) * 16)]
+    cases += [(512, e) for e in (600, 66000, 1 << 20)] + [(1024, 66000), (2048, 300000)]
+    for resident, entries in cases:
+        for tiers in (1, 2, 4, 7):
+            cap = 1 << 23
+            s = np.zeros(cap, dtype=np.uint32)
+            e = np.zeros(cap, dtype=np.uint32)
+            totals = [entries, entries - 1, entries // 2 + 3, entries // 6, 17, 1, 0] + [int(v) for v in rng.integers(0, entries + 1, 3)]
+            for total in totals:
+                nthreads = fn(entries, total, tiers, resident, s.ctypes.data, e.ctypes.data, cap)
+                assert nthreads % 128 == 0 and nthreads <= cap
+                ss, ee = s[:nthreads].astype(np.int64), e[:nthreads].astype(np.int64)
+                busy = ss != 0xffffffff
+                nb = int(busy.sum())
+                assert not busy[nb:].any(), "an idle thread sits before a busy one"
+                if total == 0:
+                    assert nb == 0
+                    continue
+                assert ss[0] == 0 and ee[nb - 1] == total
+                assert (ss[1:nb] == ee[:nb - 1]).all() and (ee[:nb] > ss[:nb]).all()
+                lens = ee[:nb] - ss[:nb]
+                assert (lens[:-1] >= lens[1:]).all() or (np.diff(lens[:-1]) <= 0).all(), "runs grow"
+                assert lens.max() <= max(1024, -(-total // nthreads) + 8)
+
+
 def test_golden_vectors(emul, golden):
     for case in golden["cases"]:
         sc, bs, want = case_arrays(case)
