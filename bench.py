@@ -898,6 +898,7 @@ def run_ours(args) -> None:
     staged0 = pk.staged_bytes()
     e2e_out, e2e_ms = timed_host(make_e2e(scalars_np), args.steps)
     staged_per_step = (pk.staged_bytes() - staged0) // (args.steps + 2)
+    staging_rate = pk.staging_rate_gbps()  # this rank's; below ~35 GB/s the library cuts the upload into five chunks instead of three
     assert np.asarray(e2e_out).view(np.uint64).tobytes() == want, "the e2e (pageable) result differs from the known-dlog answer"
     e2e_pin_out, e2e_pin_ms = timed_host(make_e2e(scalars_pin), args.steps)
     assert np.asarray(e2e_pin_out).view(np.uint64).tobytes() == want, "the e2e (pinned) result differs from the known-dlog answer"
@@ -1013,7 +1014,7 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 32 * world, "d2h_bytes_per_step": 64 * world,
                 "host_memory": "pageable (plain numpy, like a Rust Vec<Fr>): staged through the library's pinned ring",
-                "staged_bytes_per_step": int(staged_per_step),
+                "staged_bytes_per_step": int(staged_per_step), "staging_rate_gbps_rank0": round(staging_rate, 1),
                 "path": "plonkish_cuda_msm_bn254_g1 (C ABI, pageable host scalars, registered bases)" if not distributed
                         else "per rank: plonkish_cuda_msm_bn254_g1_host_partial (C ABI, pageable host scalars, registered bases) -> NCCL all_gather of partials -> fold -> host"},
         "e2e_pinned": {"value": total_n / (e2e_pin_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_pin_ms, "host_memory": "pinned (cudaHostAlloc)"},
@@ -1045,6 +1046,17 @@ def run_ours(args) -> None:
                       "the GPU's timed result on the same points checked bit-exact against it",
             "seconds": sec,
         }
+    if rank == 0 and not distributed and step_bases is reg:
+        # the same MSM on the plain affine bases (no table of window multiples: what an unregistered caller gets,
+        # one bucket set per window, c = 16), beside the headline that uses 12 x 64 B of table per point
+        reg_plain = pk.G1Bases(d_bases, mode=pk.G1Bases.PLAIN)
+        out_p, ms_p, step_ms_p = timed_device(lambda: pk.variable_base_msm_device(d_scalars, reg_plain), args.steps, 3)
+        assert out_p.cpu().numpy().view(np.uint64).tobytes() == want, "the plain-bases result differs from the known-dlog answer"
+        plan_p = pk.msm_plan(n, 0, local_rank, bases=reg_plain)
+        line["plain_bases"] = {"value": n / (ms_p * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_p, "ms_step_min": min(step_ms_p),
+                               "window_bits": plan_p["window_bits"], "windows": plan_p["windows"],
+                               "bases": "resident plain affine array, 64 B per point", "parity_checked": True}
+        reg_plain.release()
     if rank == 0 and not distributed and not args.no_skew and step_bases is reg:
         line["skew"] = skew_bench(pk, torch, np, d_scalars, reg, ms_per_step, n, dev)
     if not distributed and args.prove_k:

@@ -322,6 +322,9 @@ int plonkish_cuda_msm_profile_device(int device, const void *d_scalars, const vo
 uint64_t plonkish_cuda_launch_count(void);
 /* Bytes uploaded through the pinned staging ring so far (pageable sources). */
 uint64_t plonkish_cuda_staged_bytes(void);
+/* GB/s the staging ring sustained over its recent large uploads (0 before the first one); the host-scalar MSM cuts its
+ * points into more chunks when this falls below what its three-chunk pipeline needs. */
+double plonkish_cuda_staging_rate_gbps(void);
 
 /* The reference's timer lines (msm.rs:92 -> util/timer.rs:19-24 -> ark_std perf_trace; parsed by
  * benchmark/src/bin/plotter.rs:337-373).  mode: 0 off, 1 stderr, 2 stdout (also PLONKISH_CUDA_TIMER=1 /

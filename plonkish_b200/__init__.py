@@ -44,6 +44,7 @@ from .msm import (  # noqa: F401
     cache_stats,
     timer_config,
     staged_bytes,
+    staging_rate_gbps,
     random_scalars,
 )
 from .distributed import shard_bounds, variable_base_msm_sharded, variable_base_msm_sharded_host  # noqa: F401

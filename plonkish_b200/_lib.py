@@ -31,6 +31,7 @@ EXPORTS = (
     "plonkish_cuda_timer_emit",
     "plonkish_cuda_bases_register_sharded_device",
     "plonkish_cuda_staged_bytes",
+    "plonkish_cuda_staging_rate_gbps",
     "plonkish_cuda_bench_fp64_pipe",
     "plonkish_cuda_bench_dp_madd",
     "plonkish_cuda_bench_issue_mix",
@@ -124,6 +125,8 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_bases_register_sharded_device.argtypes = [ci, vp, sz, ci, ctypes.POINTER(u64)]
     lib.plonkish_cuda_staged_bytes.argtypes = []
     lib.plonkish_cuda_staged_bytes.restype = u64
+    lib.plonkish_cuda_staging_rate_gbps.argtypes = []
+    lib.plonkish_cuda_staging_rate_gbps.restype = ctypes.c_double
     lib.plonkish_cuda_bench_fp64_pipe.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_bench_issue_mix.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.plonkish_cuda_bench_dp_madd.argtypes = [ci, ci, ci, ctypes.POINTER(ctypes.c_double)]

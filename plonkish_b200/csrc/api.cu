@@ -276,6 +276,7 @@ public:
     cudaError_t run(int dev, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
         std::lock_guard<std::mutex> job_lock(job_mu_);
         if (!ensure_ready(dev)) return cudaErrorMemoryAllocation;
+        const auto t0 = std::chrono::steady_clock::now();
         {
             std::lock_guard<std::mutex> lk(mu_);
             src_ = (const char *)src; dst_ = (char *)dst; bytes_ = bytes; stream_ = stream; dev_ = dev;
@@ -292,9 +293,17 @@ public:
         cv_done_.wait(lk, [&] { return done_ == npieces_; });
         base_ += npieces_;
         npieces_ = 0;
+        // what the ring sustains on this host right now (several ranks share its memory bandwidth): the host-scalar MSM
+        // cuts its points into more, smaller chunks when uploads are slow (enqueue_host_msm)
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (sec > 0 && bytes >= ((size_t)32 << 20)) {
+            const double gbps = (double)bytes / sec * 1e-9, old = rate_gbps_.load(std::memory_order_relaxed);
+            rate_gbps_.store(old > 0 ? 0.5 * old + 0.5 * gbps : gbps, std::memory_order_relaxed);
+        }
         return err_;
     }
     int threads() const { return nthreads_; }
+    double rate_gbps() const { return rate_gbps_.load(std::memory_order_relaxed); }  // 0 until the first large upload
 
 private:
     Stager() {
@@ -313,7 +322,9 @@ private:
         }
         nthreads_ = t;
         nslots_ = 2 * t + 2;
-        if (const char *e = getenv("PLONKISH_CUDA_STAGE_NT")) stream_stores_ = e[0] == '1';  // host_copy.cpp
+        // host_copy.cpp: streaming stores into the ring (measured end to end from pageable memory, 2^24-point MSM: 38.5 ->
+        // 38.0 ms with one rank, 45.2 -> 43.3 ms with two ranks sharing the host); PLONKISH_CUDA_STAGE_NT=0 = plain memcpy
+        if (const char *e = getenv("PLONKISH_CUDA_STAGE_NT")) stream_stores_ = e[0] != '0';
     }
     bool ensure_ready(int dev) {
         if (slots_.empty()) {
@@ -383,7 +394,8 @@ private:
         }
     }
     int nthreads_ = 2, nslots_ = 6;
-    bool stream_stores_ = false;
+    bool stream_stores_ = true;
+    std::atomic<double> rate_gbps_{0.0};
     std::vector<void *> slots_;
     std::vector<std::vector<cudaEvent_t>> slot_ev_;  // [slot][device]
     std::vector<int> slot_dev_;                      // device whose event the slot's last piece recorded
@@ -401,25 +413,30 @@ private:
 
 static std::atomic<unsigned long long> g_staged_bytes{0};
 // Host -> device copy of caller memory on `stream` (current device = c->dev).  Returns once the source may be reused.
-static cudaError_t upload(Ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+static const size_t STAGE_MIN_BYTES = (size_t)32 << 20;
+// Whether an upload of `bytes` from src goes through the staging ring: unregistered (pageable) host memory only.
+static bool is_staged_source(const void *src, size_t bytes) {
     static const bool staging = [] {
         const char *e = getenv("PLONKISH_CUDA_STAGING");
         return !(e && e[0] == '0');
     }();
     // below 32 MiB the driver's own pageable path is as fast or faster (measured end to end, MSM of 2^17 / 2^19 / 2^20 /
     // 2^21 / 2^24 points: staged 1.46 / 3.26 / 4.96 / 7.70 / 39.4 ms, direct 1.15 / 2.90 / 4.91 / 9.76 / 72.8 ms)
-    if (staging && bytes >= ((size_t)32 << 20)) {
-        cudaPointerAttributes attr;
-        const cudaError_t q = cudaPointerGetAttributes(&attr, src);
-        if (q != cudaSuccess) cudaGetLastError();
-        if (q == cudaSuccess && attr.type == cudaMemoryTypeUnregistered) {
-            g_staged_bytes.fetch_add(bytes, std::memory_order_relaxed);
-            return Stager::get().run(c->dev, dst, src, bytes, stream);
-        }
+    if (!staging || bytes < STAGE_MIN_BYTES) return false;
+    cudaPointerAttributes attr;
+    const cudaError_t q = cudaPointerGetAttributes(&attr, src);
+    if (q != cudaSuccess) cudaGetLastError();
+    return q == cudaSuccess && attr.type == cudaMemoryTypeUnregistered;
+}
+static cudaError_t upload(Ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    if (is_staged_source(src, bytes)) {
+        g_staged_bytes.fetch_add(bytes, std::memory_order_relaxed);
+        return Stager::get().run(c->dev, dst, src, bytes, stream);
     }
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
 }
 extern "C" uint64_t plonkish_cuda_staged_bytes(void) { return g_staged_bytes.load(); }
+extern "C" double plonkish_cuda_staging_rate_gbps(void) { return Stager::get().rate_gbps(); }
 
 extern "C" int plonkish_cuda_init(int n_devices) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1023,7 +1040,16 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
     } else if (forced >= 1 && forced <= 16) {
         for (long k = 1; k <= forced; ++k) cuts.push_back(n * (size_t)k / (size_t)forced);
     } else if (n >= ((size_t)1 << 23) && n <= MAX_POINTS_PER_LAUNCH) {
-        cuts = {n / 16, 5 * (n / 16), n};
+        // The three-chunk geometry needs an upload rate of ~44 GB/s (11/16 of the scalars must arrive while a quarter of
+        // the points computes).  The staging ring sustains that for one rank; ranks sharing the host's memory bandwidth
+        // do not (two ranks: ~25 GB/s each), and then five chunks growing by 1.6x hide more than their fixed costs take
+        // (measured with two ranks, 2^24 points each, pageable: 43.0 -> 38.5 ms; pinned sources lose: 35.8 -> 38.7 ms).
+        const double rate = Stager::get().rate_gbps();
+        if (rate > 0 && rate < 35.0 && is_staged_source(h_scalars, n * 32)) {
+            cuts = {n / 16, (size_t)((double)n * 0.16), (size_t)((double)n * 0.32), (size_t)((double)n * 0.58), n};
+        } else {
+            cuts = {n / 16, 5 * (n / 16), n};
+        }
     } else if (n >= ((size_t)1 << 20) && n <= MAX_POINTS_PER_LAUNCH) {
         cuts = {n / 4, n};
     } else {

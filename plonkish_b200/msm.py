@@ -130,6 +130,11 @@ def staged_bytes() -> int:
     return int(_lib.load().plonkish_cuda_staged_bytes())
 
 
+def staging_rate_gbps() -> float:
+    """GB/s the pinned staging ring sustained over its recent large uploads (0.0 before the first)."""
+    return float(_lib.load().plonkish_cuda_staging_rate_gbps())
+
+
 class ResidentScalars:
     """A polynomial's evaluations (n x bn256::Fr, Montgomery) kept in HBM between its commit
     and its opening — poly.evals() of pcs/multilinear/kzg.rs:255,291 without the re-upload."""
