@@ -267,9 +267,20 @@ extern "C" void plonkish_cuda_host_copy(void *dst, const void *src, size_t len, 
 class Stager {
 public:
     static const size_t SLOT = (size_t)4 << 20;
-    static Stager &get() {
-        static Stager *s = new Stager();  // leaked on purpose: worker threads outlive static destruction
-        return *s;
+    // One ring per device in use.  A ring runs one upload at a time; the single-process multi-GPU entry uploads to all
+    // its devices at once (one host thread each), so it asks for `shards` rings that split the copier threads between
+    // them (set_shards) — with one ring for all, device B's small first chunk waited behind device A's large one.
+    static Stager &get(int dev = 0) {
+        static std::mutex mu;
+        static Stager *rings[PK_MAX_STAGERS] = {nullptr};  // leaked on purpose: worker threads outlive static destruction
+        const int shards = shards_().load(std::memory_order_relaxed);
+        const int k = shards > 1 ? (dev < 0 ? 0 : dev) % (shards < PK_MAX_STAGERS ? shards : PK_MAX_STAGERS) : 0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!rings[k]) rings[k] = new Stager(shards > 1 ? shards : 1);
+        return *rings[k];
+    }
+    static void set_shards(int n) {
+        if (n > shards_().load(std::memory_order_relaxed)) shards_().store(n, std::memory_order_relaxed);
     }
     // Copies [src, src + bytes) to device memory dst on `stream`; returns when every piece is enqueued
     // (the source may be reused), not when the DMA is done.
@@ -306,9 +317,15 @@ public:
     double rate_gbps() const { return rate_gbps_.load(std::memory_order_relaxed); }  // 0 until the first large upload
 
 private:
-    Stager() {
+    static const int PK_MAX_STAGERS = 16;
+    static std::atomic<int> &shards_() { static std::atomic<int> v{1}; return v; }
+    explicit Stager(int shards) {
         unsigned hw = std::thread::hardware_concurrency();
         int t = hw >= 32 ? 8 : hw >= 16 ? 6 : hw >= 8 ? 4 : 2;
+        if (shards > 1) {  // the rings of one process share the host's cores like the ranks of a torchrun job do
+            const int per = (int)(hw / (unsigned)shards);
+            t = per < 2 ? 2 : (per < t ? per : t);
+        }
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): the ranks share the host's cores
             const long w = atol(e);
             if (w > 1) {
@@ -431,7 +448,7 @@ static bool is_staged_source(const void *src, size_t bytes) {
 static cudaError_t upload(Ctx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
     if (is_staged_source(src, bytes)) {
         g_staged_bytes.fetch_add(bytes, std::memory_order_relaxed);
-        return Stager::get().run(c->dev, dst, src, bytes, stream);
+        return Stager::get(c->dev).run(c->dev, dst, src, bytes, stream);
     }
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
 }
@@ -1044,7 +1061,7 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
         // the points computes).  The staging ring sustains that for one rank; ranks sharing the host's memory bandwidth
         // do not (two ranks: ~25 GB/s each), and then five chunks growing by 1.6x hide more than their fixed costs take
         // (measured with two ranks, 2^24 points each, pageable: 43.0 -> 38.5 ms; pinned sources lose: 35.8 -> 38.7 ms).
-        const double rate = Stager::get().rate_gbps();
+        const double rate = Stager::get(c->dev).rate_gbps();
         if (rate > 0 && rate < 35.0 && is_staged_source(h_scalars, n * 32)) {
             cuts = {n / 16, (size_t)((double)n * 0.16), (size_t)((double)n * 0.32), (size_t)((double)n * 0.58), n};
         } else {
@@ -1522,6 +1539,7 @@ extern "C" int plonkish_cuda_msm_bn254_g1_multi(int n_gpus, const void *scalars,
         if (!cs[g]) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_multi: device %d not initialised", g);
     }
     std::lock_guard<std::mutex> nccl_lock(g_nccl_mu);  // one multi-GPU call at a time (the communicators are shared)
+    if (n_gpus > 1) Stager::set_shards(n_gpus);
     int rc = n_gpus > 1 ? nccl_ensure(n_gpus) : PLONKISH_CUDA_OK;
     if (rc) return rc;
     struct LockAll {  // every device context for the whole call, in device order
