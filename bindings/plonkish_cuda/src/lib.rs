@@ -52,6 +52,7 @@ extern "C" {
                                   num_terms: usize, common_poly: c_int, state: *mut u64) -> c_int;
     fn plonkish_cuda_sumcheck_degree(state: u64) -> c_int;
     fn plonkish_cuda_sumcheck_round(state: u64, out_evals: *mut c_void) -> c_int;
+    fn plonkish_cuda_sumcheck_round_factored(state: u64, out_evals: *mut c_void) -> c_int;
     fn plonkish_cuda_sumcheck_fix_var(state: u64, challenge: *const c_void) -> c_int;
     fn plonkish_cuda_sumcheck_final_evals(state: u64, out_evals: *mut c_void) -> c_int;
     fn plonkish_cuda_sumcheck_free(state: u64) -> c_int;
@@ -583,4 +584,68 @@ pub fn sum_check_prove(
     check(unsafe { plonkish_cuda_sumcheck_final_evals(state, evals.as_mut_ptr() as *mut c_void) }, "plonkish_cuda_sumcheck_final_evals");
     unsafe { plonkish_cuda_sumcheck_free(state) };
     (challenges, evals) // classic.rs:239
+}
+
+/// The zero check of `prove_zero_check` (backend/hyperplonk/prover.rs:347-365): `sum_check_prove` for an expression whose
+/// common table `polys[common]` is `eq_xy(y)` (classic.rs:57-61), run factored.  In round r the common factor's pair is
+/// (S (1 - y_r), S y_r), so the round polynomial is h(X) = (1 - y_r + X (2 y_r - 1)) G(X); the GPU returns G(1..degree-1)
+/// (`plonkish_cuda_sumcheck_round_factored`: one evaluation point fewer per pair), G(0) follows from h(0) + h(1) = sum and
+/// G(degree) from `evaluate` on G's own points.  The messages written are the ones `sum_check_prove` writes.
+pub fn zero_check_prove(
+    polys: &[&ResidentPoly],
+    terms: &[(Fr, Vec<u32>)],
+    common: usize,
+    y: &[Fr],
+    mut squeeze: impl FnMut(&[Fr]) -> Fr,
+    evaluate: impl Fn(&[Fr], &Fr) -> Fr,
+) -> (Vec<Fr>, Vec<Fr>) {
+    use halo2_curves::ff::Field;
+    let num_vars = polys[0].num_vars;
+    assert_eq!(y.len(), num_vars);
+    let hs: Vec<u64> = polys.iter().map(|p| p.handle).collect();
+    let coeffs: Vec<Fr> = terms.iter().map(|t| t.0).collect();
+    let mut offsets = vec![0u32];
+    let mut flat = Vec::new();
+    for (_, f) in terms {
+        flat.extend_from_slice(f);
+        offsets.push(flat.len() as u32);
+    }
+    let mut state = 0u64;
+    check(
+        unsafe {
+            plonkish_cuda_sumcheck_new(hs.as_ptr(), hs.len(), num_vars, coeffs.as_ptr() as *const c_void, offsets.as_ptr(), flat.as_ptr(), terms.len(),
+                                       common as c_int, &mut state)
+        },
+        "plonkish_cuda_sumcheck_new",
+    );
+    let degree = unsafe { plonkish_cuda_sumcheck_degree(state) } as usize;
+    let (mut sum, mut challenges) = (Fr::zero(), Vec::with_capacity(num_vars));
+    for y_r in y {
+        let (e0, e1) = (Fr::one() - y_r, *y_r);
+        let mut msg = vec![Fr::zero(); degree + 1];
+        match Option::<Fr>::from(e0.invert()) {
+            Some(inv_e0) if degree >= 2 => {
+                let mut g = vec![Fr::zero(); degree]; // G(0..degree-1)
+                check(unsafe { plonkish_cuda_sumcheck_round_factored(state, g[1..].as_mut_ptr() as *mut c_void) }, "plonkish_cuda_sumcheck_round_factored");
+                g[0] = (sum - e1 * g[1]) * inv_e0;
+                let g_top = evaluate(&g, &Fr::from(degree as u64));
+                g.push(g_top);
+                for (x, (m, gx)) in msg.iter_mut().zip(g.iter()).enumerate() {
+                    *m = (e0 + Fr::from(x as u64) * (e1 - e0)) * gx;
+                }
+            }
+            _ => {
+                check(unsafe { plonkish_cuda_sumcheck_round(state, msg[1..].as_mut_ptr() as *mut c_void) }, "plonkish_cuda_sumcheck_round");
+                msg[0] = sum - msg[1];
+            }
+        }
+        let challenge = squeeze(&msg);
+        sum = evaluate(&msg, &challenge);
+        check(unsafe { plonkish_cuda_sumcheck_fix_var(state, &challenge as *const Fr as *const c_void) }, "plonkish_cuda_sumcheck_fix_var");
+        challenges.push(challenge);
+    }
+    let mut evals = vec![Fr::zero(); polys.len()];
+    check(unsafe { plonkish_cuda_sumcheck_final_evals(state, evals.as_mut_ptr() as *mut c_void) }, "plonkish_cuda_sumcheck_final_evals");
+    unsafe { plonkish_cuda_sumcheck_free(state) };
+    (challenges, evals)
 }

@@ -245,6 +245,11 @@ int plonkish_cuda_sumcheck_degree(uint64_t state_handle);
  * out_evals_mont32[x-1] = sum_b expr(r_0, .., r_{round-1}, X = x, b) for x = 1..degree, over the pairs
  * (2b, 2b+1) of every table (eval.rs:236-243).  The caller sets evals[0] = sum - evals[1] (eval.rs:128). */
 int plonkish_cuda_sumcheck_round(uint64_t state_handle, void *out_evals_mont32);
+/* The same round for a zero check whose common factor is eq(x, y) (times a constant), factored: the round polynomial is
+ * h(X) = (1 - y_r + X (2 y_r - 1)) * G(X) with G of one degree less; out_evals receives G(1..degree-1), computed with the
+ * common factor's pair sum instead of its walk — one evaluation point fewer per pair.  The caller rebuilds the message
+ * h(0..degree) of eval.rs:101-131 from G and the running sum (G(0) from h(0) + h(1) = sum); plonkish_b200/sumcheck.py. */
+int plonkish_cuda_sumcheck_round_factored(uint64_t state_handle, void *out_evals_mont32);
 /* ProverState::next_round (classic.rs:90-141): fix the lowest variable of every table at the challenge
  * (MultilinearPolynomial::fix_var, poly/multilinear.rs:179-189: out[b] = (e[2b+1] - e[2b]) * x + e[2b]). */
 int plonkish_cuda_sumcheck_fix_var(uint64_t state_handle, const void *challenge_mont32);

@@ -61,6 +61,7 @@ EXPORTS = (
     "plonkish_cuda_sumcheck_new",
     "plonkish_cuda_sumcheck_degree",
     "plonkish_cuda_sumcheck_round",
+    "plonkish_cuda_sumcheck_round_factored",
     "plonkish_cuda_sumcheck_fix_var",
     "plonkish_cuda_sumcheck_final_evals",
     "plonkish_cuda_sumcheck_free",
@@ -141,6 +142,7 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_sumcheck_new.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, ctypes.POINTER(u64)]
     lib.plonkish_cuda_sumcheck_degree.argtypes = [u64]
     lib.plonkish_cuda_sumcheck_round.argtypes = [u64, vp]
+    lib.plonkish_cuda_sumcheck_round_factored.argtypes = [u64, vp]
     lib.plonkish_cuda_sumcheck_fix_var.argtypes = [u64, vp]
     lib.plonkish_cuda_sumcheck_final_evals.argtypes = [u64, vp]
     lib.plonkish_cuda_sumcheck_free.argtypes = [u64]

@@ -3281,6 +3281,35 @@ extern "C" int plonkish_cuda_sumcheck_round(uint64_t state_handle, void *out_eva
     return PLONKISH_CUDA_OK;
 }
 
+// The factored round of a zero check (SumcheckExpr::common_sum): out[x-1] = G(x) = sum_b S_b * expr(.., X = x, b) for
+// x = 1..degree-1, S_b = the common factor's pair sum.  Valid when the common factor is eq(x, y) times a constant; the
+// round polynomial is then h(X) = (1 - y_r + X (2 y_r - 1)) G(X), and the caller rebuilds the reference's message
+// (eval.rs:101-131) from G and the running sum — one evaluation point fewer per pair than plonkish_cuda_sumcheck_round.
+extern "C" int plonkish_cuda_sumcheck_round_factored(uint64_t state_handle, void *out_evals) {
+    SumcheckState st;
+    if (!out_evals) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round_factored: null output");
+    if (!lookup_sumcheck(state_handle, st)) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round_factored: unknown state %llu", (unsigned long long)state_handle);
+    if (st.round >= st.num_vars) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round_factored: all %u rounds are done", st.num_vars);
+    if (st.ex.common < 0 || st.ex.degree < 2) return fail(PLONKISH_CUDA_E_INVALID, "sumcheck_round_factored: the expression has no common factor");
+    Ctx *c = ctx_for(st.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "sumcheck_round_factored: device %d not initialised", st.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    SumcheckPolys polys;
+    memset(&polys, 0, sizeof(polys));
+    for (u32 p = 0; p < st.num_polys; ++p) polys.p[p] = (const uint4 *)st.cur[p];
+    const u32 size = 1u << (st.num_vars - st.round - 1);
+    SumcheckExpr ex = st.ex;
+    ex.degree = st.ex.degree - 1;
+    ex.common_sum = 1;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    pk_enqueue_sumcheck_round(polys, ex, size, st.partials, st.d_out, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_evals, st.d_out, (size_t)ex.degree * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PLONKISH_CUDA_OK;
+}
+
 // ProverState::next_round (classic.rs:90-141): every table is fixed at the challenge.
 extern "C" int plonkish_cuda_sumcheck_fix_var(uint64_t state_handle, const void *challenge) {
     SumcheckState st;

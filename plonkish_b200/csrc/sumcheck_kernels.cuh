@@ -32,6 +32,12 @@ struct SumcheckExpr {
     unsigned char fac[PK_SC_MAX_TERMS][PK_SC_MAX_FACTORS];  // polynomial indices
     u32 num_terms, num_polys, degree;
     int common;  // polynomial multiplying the whole sum, or -1
+    // 0: the common factor walks through X like every other factor.  1: the factored zero-check round — the common
+    // factor is eq(x, y) (times any constant), whose pair is (S (1 - y_r), S y_r) with S = e[2b] + e[2b+1] the eq value
+    // over the remaining variables, so h(X) = (1 - y_r + X (2 y_r - 1)) * G(X) with G(X) = sum_b S_b * expr_b(X) of one
+    // degree less: the kernel multiplies by S (no walk) at X = 1..degree, where `degree` is then deg G = deg h - 1, and
+    // the caller rebuilds the same message h(0..deg h) from G and the running sum (plonkish_b200/sumcheck.py).
+    int common_sum;
 };
 struct SumcheckPolys {
     const uint4 *p[PK_SC_MAX_POLYS];
@@ -116,12 +122,18 @@ __global__ void __launch_bounds__(128, (D <= 5 ? 3 : 2)) k_sumcheck_round_t(Sumc
         if (ex.common >= 0) {
             const uint4 *src = polys.p[ex.common] + 4 * (size_t)b;
             const fe lo = load_fe_plain(src), hi = load_fe_plain(src + 2);
-            const fe step = fr_sub(hi, lo);
-            fe v = hi;
+            if (ex.common_sum) {
+                const fe v = PLAIN ? fe_add_plain(lo, hi) : fr_add(lo, hi);  // < 2r: a multiplier, like the walked values
 #pragma unroll
-            for (int x = 0; x < D; ++x) {
-                if (x) v = PLAIN ? fe_add_plain(v, step) : fr_add(v, step);
-                tot[x] = fr_mul(tot[x], v);
+                for (int x = 0; x < D; ++x) tot[x] = fr_mul(tot[x], v);
+            } else {
+                const fe step = fr_sub(hi, lo);
+                fe v = hi;
+#pragma unroll
+                for (int x = 0; x < D; ++x) {
+                    if (x) v = PLAIN ? fe_add_plain(v, step) : fr_add(v, step);
+                    tot[x] = fr_mul(tot[x], v);
+                }
             }
         }
 #pragma unroll

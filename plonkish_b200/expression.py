@@ -317,6 +317,14 @@ class CompiledExpression:
     common: int                               # atom multiplying the whole sum (the eq_xy of a zero check), or -1
     degree: int                               # of the round polynomials: max factors per term (+ 1 with a common atom)
 
+    def common_eq_xy(self) -> Optional[int]:
+        """idx when the common atom is exactly the leaf eq_xy(idx) — the zero check's factor (preprocessor.rs:49-50),
+        which lets the rounds run factored (sumcheck.zero_check_message) — else None."""
+        if self.common < 0:
+            return None
+        a = self.atoms[self.common]
+        return a.leaf()[1] if a.is_leaf() and a.leaf()[0] == "eq_xy" else None
+
     def value(self, leaf_value: Callable[[Leaf], int]) -> int:
         vals = [a.value(leaf_value) for a in self.atoms]
         total = 0

@@ -391,7 +391,10 @@ def prove_sum_check(num_instance_poly: int, expression: Expression, claimed_sum:
     st = build_tables(compiled, num_vars, polys, [y], extra_polys=sorted({q.poly for q in queries}))
     try:
         terms = [(fr_to_montgomery(c), idx) for c, idx in compiled.terms]
-        x, table_evals = sumcheck.prove_to_transcript(st.tables, terms, claimed_sum, transcript, common=compiled.common)
+        # the zero check's eq_xy(0) = eq(x, y) is the common factor: its rounds run factored (one evaluation point fewer
+        # per pair, the same messages); any other expression takes the plain rounds
+        zc = list(y) if compiled.common_eq_xy() == 0 else None
+        x, table_evals = sumcheck.prove_to_transcript(st.tables, terms, claimed_sum, transcript, common=compiled.common, zero_check_point=zc)
     finally:
         st.release()
     offsets = point_offset(queries)

@@ -64,6 +64,13 @@ class SumCheckProver:
         _lib.check(_lib.lib().plonkish_cuda_sumcheck_round(self.state, out.ctypes.data), "plonkish_cuda_sumcheck_round")
         return out
 
+    def round_evals_factored(self) -> np.ndarray:
+        """Zero check with eq(x, y) as the common factor: G(1..degree-1) of h(X) = (1 - y_r + X (2 y_r - 1)) G(X)
+        ([degree - 1, 4] Montgomery limbs); see `zero_check_message`."""
+        out = np.zeros((self.degree - 1, 4), dtype=np.uint64)
+        _lib.check(_lib.lib().plonkish_cuda_sumcheck_round_factored(self.state, out.ctypes.data), "plonkish_cuda_sumcheck_round_factored")
+        return out
+
     def fix_var(self, challenge) -> None:
         ch = _as_u64(challenge, 4, "challenge").reshape(4)
         _lib.check(_lib.lib().plonkish_cuda_sumcheck_fix_var(self.state, ch.ctypes.data), "plonkish_cuda_sumcheck_fix_var")
@@ -80,6 +87,25 @@ class SumCheckProver:
             self.state = 0
 
 
+_BARY_WEIGHTS: dict = {}
+
+
+def _bary_weights(d: int) -> List[int]:
+    """1 / prod_{i != j} (j - i) for the points 0..d (they depend on d alone: computed once per degree)."""
+    w = _BARY_WEIGHTS.get(d)
+    if w is None:
+        r = FR_MODULUS
+        w = []
+        for j in range(d + 1):
+            den = 1
+            for i in range(d + 1):
+                if i != j:
+                    den = den * (j - i) % r
+            w.append(pow(den, -1, r))
+        _BARY_WEIGHTS[d] = w
+    return w
+
+
 def interpolate_at(evals: Sequence[int], x: int) -> int:
     """`Evaluations::evaluate`: the polynomial through (i, evals[i]), i = 0..degree, at x
     (barycentric form of util/arithmetic.rs:108-136; any exact interpolation gives the same value)."""
@@ -87,30 +113,76 @@ def interpolate_at(evals: Sequence[int], x: int) -> int:
     d = len(evals) - 1
     if 0 <= x <= d:
         return evals[x] % r
-    total = 0
+    weights = _bary_weights(d)
+    diffs = [(x - i) % r for i in range(d + 1)]
+    suffix = [1] * (d + 2)  # suffix[j] = prod_{i >= j} (x - i)
+    for i in range(d, -1, -1):
+        suffix[i] = suffix[i + 1] * diffs[i] % r
+    total, prefix = 0, 1
     for j, e in enumerate(evals):
-        num, den = 1, 1
-        for i in range(d + 1):
-            if i != j:
-                num = num * (x - i) % r
-                den = den * (j - i) % r
-        total = (total + e * num % r * pow(den, -1, r)) % r
-    return total
+        total += e * (prefix * suffix[j + 1] % r) % r * weights[j]
+        prefix = prefix * diffs[j] % r
+    return total % r
+
+
+def batch_inverse(vals: Sequence[int]) -> List[int]:
+    """Inverses mod r of the non-zero entries with one modular inversion (Montgomery's trick); 0 stays 0."""
+    r = FR_MODULUS
+    prefix, acc = [], 1
+    for v in vals:
+        prefix.append(acc)
+        if v % r:
+            acc = acc * v % r
+    inv = pow(acc, -1, r)
+    out = [0] * len(vals)
+    for i in range(len(vals) - 1, -1, -1):
+        if vals[i] % r:
+            out[i] = inv * prefix[i] % r
+            inv = inv * vals[i] % r
+    return out
+
+
+def zero_check_message(g_tail: Sequence[int], total: int, y_r: int, inv_e0: Optional[int] = None) -> Optional[List[int]]:
+    """The round message h(0..D) of a zero check from the factored round.  The common factor eq(x, y) of the round's
+    pair b is (S_b (1 - y_r), S_b y_r), so h(X) = l(X) G(X) with l(X) = 1 - y_r + X (2 y_r - 1) and
+    G(X) = sum_b S_b expr_b(X) of degree D - 1.  g_tail = G(1..D-1) from the GPU; G(0) follows from the running sum
+    h(0) + h(1) = total, G(D) from the D points of G.  The values are the field elements the reference's
+    `EvaluationsProver` sums up pair by pair (eval.rs:101-131) — the message is identical.  None when 1 - y_r is zero
+    (no G(0) from the sum: the caller runs the plain round)."""
+    r = FR_MODULUS
+    e0, e1 = (1 - y_r) % r, y_r % r
+    if e0 == 0:
+        return None
+    if inv_e0 is None:
+        inv_e0 = pow(e0, -1, r)
+    g = [(total - e1 * g_tail[0]) * inv_e0 % r] + [v % r for v in g_tail]            # G(0..D-1)
+    g.append(interpolate_at(g, len(g)))                                              # G(D)
+    return [(e0 + x * (e1 - e0)) % r * gx % r for x, gx in enumerate(g)]
 
 
 def prove(polys: Sequence[ResidentScalars], terms, claimed_sum: int, squeeze_challenge: Callable[[List[int]], int],
-          common: int = -1) -> Tuple[List[List[int]], List[int], List[int]]:
+          common: int = -1, zero_check_point: Optional[Sequence[int]] = None) -> Tuple[List[List[int]], List[int], List[int]]:
     """`ClassicSumCheck::prove` (classic.rs:208-240).  `squeeze_challenge(message)` stands for
     `msg.write(transcript)` + `transcript.squeeze_challenge()`; values are canonical integers.
-    Returns (round messages, challenges, evaluations of every polynomial at the challenges)."""
+    Returns (round messages, challenges, evaluations of every polynomial at the challenges).
+    zero_check_point = y (canonical integers) states that polys[common] is eq_xy(y) (classic.rs:57-61) times a constant:
+    the rounds then run factored (`zero_check_message`), the messages are the same."""
     prover = SumCheckProver(polys, terms, common)
     msgs: List[List[int]] = []
     challenges: List[int] = []
     total = claimed_sum % FR_MODULUS
+    factored = zero_check_point is not None and common >= 0 and prover.degree >= 2
+    if factored:
+        assert len(zero_check_point) == prover.num_vars, "zero_check_point must hold one value per variable"
+        inv_e0 = batch_inverse([(1 - int(v)) % FR_MODULUS for v in zero_check_point])  # y is known up front: one inversion
     try:
-        for _ in range(prover.num_vars):
-            tail = [_to_int(row) for row in prover.round_evals()]
-            msg = [(total - tail[0]) % FR_MODULUS] + tail  # evals[0] = sum - evals[1]  (eval.rs:128)
+        for rnd in range(prover.num_vars):
+            msg = None
+            if factored:
+                msg = zero_check_message([_to_int(row) for row in prover.round_evals_factored()], total, int(zero_check_point[rnd]), inv_e0[rnd])
+            if msg is None:
+                tail = [_to_int(row) for row in prover.round_evals()]
+                msg = [(total - tail[0]) % FR_MODULUS] + tail  # evals[0] = sum - evals[1]  (eval.rs:128)
             msgs.append(msg)
             ch = squeeze_challenge(msg) % FR_MODULUS
             challenges.append(ch)
@@ -152,7 +224,8 @@ def prove_coefficients_to_transcript(polys: Sequence[ResidentScalars], terms, cl
     return challenges, evals
 
 
-def prove_to_transcript(polys: Sequence[ResidentScalars], terms, claimed_sum: int, transcript, common: int = -1):
+def prove_to_transcript(polys: Sequence[ResidentScalars], terms, claimed_sum: int, transcript, common: int = -1,
+                        zero_check_point: Optional[Sequence[int]] = None):
     """`ClassicSumCheck::prove` with the reference's transcript calls (classic.rs:226-229): every round message goes
     down with `write_field_elements` (eval.rs:37-39), the challenge comes from `squeeze_challenge`.
     `transcript` is a plonkish_b200.transcript.Keccak256Transcript.  Returns (challenges, evals)."""
@@ -161,5 +234,5 @@ def prove_to_transcript(polys: Sequence[ResidentScalars], terms, claimed_sum: in
         transcript.write_field_elements(msg)
         return transcript.squeeze_challenge()
 
-    _, challenges, evals = prove(polys, terms, claimed_sum, squeeze, common)
+    _, challenges, evals = prove(polys, terms, claimed_sum, squeeze, common, zero_check_point)
     return challenges, evals

@@ -302,6 +302,26 @@ void emul_sumcheck_round(const void *const *polys, u32 num_polys, u32 n, const v
     std::vector<fe> partials((size_t)sm_count * 16 * PK_SC_MAX_DEGREE + 8);
     pk_enqueue_sumcheck_round(ps, ex, n / 2, partials.data(), out, sm_count, 0);
 }
+// The factored zero-check round (SumcheckExpr::common_sum): G(1..degree-1) into out; `degree` is the full round
+// polynomial's degree, as for emul_sumcheck_round.
+void emul_sumcheck_round_factored(const void *const *polys, u32 num_polys, u32 n, const void *coeffs, const u32 *offsets, const u32 *term_polys,
+                                  u32 num_terms, int common, u32 degree, u32 sm_count, void *out) {
+    SumcheckPolys ps;
+    SumcheckExpr ex;
+    memset(&ps, 0, sizeof(ps));
+    memset(&ex, 0, sizeof(ex));
+    for (u32 p = 0; p < num_polys; ++p) ps.p[p] = (const uint4 *)polys[p];
+    static const u32 FR_ONE[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    ex.num_terms = num_terms; ex.num_polys = num_polys; ex.degree = degree - 1; ex.common = common; ex.common_sum = 1;
+    for (u32 t = 0; t < num_terms; ++t) {
+        memcpy(ex.coeff[t].l, (const char *)coeffs + (size_t)t * 32, 32);
+        ex.has_coeff[t] = memcmp(ex.coeff[t].l, FR_ONE, 32) != 0;
+        ex.nfac[t] = (unsigned char)(offsets[t + 1] - offsets[t]);
+        for (u32 j = offsets[t]; j < offsets[t + 1]; ++j) ex.fac[t][j - offsets[t]] = (unsigned char)term_polys[j];
+    }
+    std::vector<fe> partials((size_t)sm_count * 16 * PK_SC_MAX_DEGREE + 8);
+    pk_enqueue_sumcheck_round(ps, ex, n / 2, partials.data(), out, sm_count, 0);
+}
 // ---- affine tables of the sum-check compiler (poly_kernels.cuh k_fr_affine / k_fr_sparse_add)
 void emul_fr_affine(const void *const *polys, const int *rotations, const void *coeffs, u32 count, u32 num_vars, const void *constant,
                     const void *id_coeff, const unsigned long long *rows, const void *values, u32 sparse_count, void *out) {

@@ -67,6 +67,7 @@ def emul():
     vp, u32, ci = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
     lib.emul_sumcheck_round.argtypes = [vp, u32, u32, vp, vp, vp, u32, ci, u32, u32, vp]
     lib.emul_sumcheck_fold.argtypes = [vp, vp, u32, u32, vp, u32]
+    lib.emul_sumcheck_round_factored.argtypes = [vp, u32, u32, vp, vp, vp, u32, ci, u32, u32, vp]
     return lib
 
 
@@ -159,3 +160,40 @@ def test_emulated_round_kernel_on_extreme_values(emul, oracle, degree_terms):
                              len(terms), 0, degree, 1, out.ctypes.data)
     terms_int = [(R - 1, list(range(1, 1 + degree_terms))), (1, [5, 4, 3]), (R - 2, [2])]
     assert _ints(out) == _round_int([_ints(p) for p in polys], terms_int, 0, degree)
+
+
+@pytest.mark.parametrize("k,max_fac,num_terms,sms", [(1, 2, 2, 1), (5, 3, 4, 1), (8, 4, 5, 2), (6, 6, 3, 1)])
+def test_factored_zero_check_rounds_give_the_same_messages(emul, oracle, k, max_fac, num_terms, sms):
+    """The factored round (common factor eq(x, y) entering as its pair sum, one evaluation point fewer) plus
+    sumcheck.zero_check_message rebuilds, round after round, exactly the message of the plain round
+    (eval.rs:101-131) — including after folds, when the eq table carries the product of the earlier eq factors."""
+    from plonkish_b200.sumcheck import interpolate_at, zero_check_message
+
+    n = 1 << k
+    num_polys = 5
+    y = _ints(oracle.random_scalars(k, 31 + k))
+    eq = [1]
+    for y_i in y:  # eq(x, y), lowest variable first (poly/multilinear.rs:91-130)
+        eq = [e * (1 - y_i) % R for e in eq] + [e * y_i % R for e in eq]
+    polys, terms = _random_case(oracle, num_polys, k, num_terms, max_fac, 0, 40 + k)
+    polys[0] = _mont(eq)
+    coeffs, offsets, flat = oracle.flatten_terms(terms)
+    degree = max(len(i) for _, i in terms) + 1
+    rng = np.random.default_rng(k)
+    claim = None
+    for rnd in range(k):
+        m = len(polys[0])
+        ptrs = (ctypes.c_void_p * num_polys)(*[p.ctypes.data for p in polys])
+        tail = _ints(oracle.sumcheck_round(polys, terms, 0))
+        if claim is None:  # h(0) + h(1) of the first round, directly
+            terms_int = [(_ints(c)[0], idx) for c, idx in terms]
+            claim = sum(_expr_int(terms_int, 0, [_ints(p[j: j + 1])[0] for p in polys]) for j in range(m)) % R
+        want = [(claim - tail[0]) % R] + tail
+        g = np.zeros((degree - 1, 4), dtype=np.uint64)
+        emul.emul_sumcheck_round_factored(ctypes.cast(ptrs, ctypes.c_void_p), num_polys, m, coeffs.ctypes.data, offsets.ctypes.data, flat.ctypes.data,
+                                          len(terms), 0, degree, sms, g.ctypes.data)
+        assert zero_check_message(_ints(g), claim, y[rnd]) == want, rnd
+        ch = int.from_bytes(rng.bytes(32), "little") % R
+        claim = interpolate_at(want, ch)
+        polys = [oracle.fix_var(p, _mont([ch])[0]) for p in polys]
+    assert zero_check_message([5, 7], 11, 1) is None  # 1 - y_r = 0: the caller runs the plain round
