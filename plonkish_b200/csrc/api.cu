@@ -3401,3 +3401,20 @@ extern "C" void plonkish_cuda_keccak_f1600(uint64_t state[25]) {
     }
 }
 
+
+#ifdef PK_STAGE_PROF
+// Experiment builds only: cycles per phase of the staged partition kernels, block 7's view (tools/stage_phase_probe.py).
+extern "C" int plonkish_cuda_debug_stage_prof(int device, unsigned long long out[16], int reset) {
+    Ctx *c = ctx_for(device);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "debug_stage_prof: device %d not initialised", device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (out) CUDA_TRY(cudaMemcpyFromSymbol(out, pk::g_stage_prof, 16 * sizeof(unsigned long long)));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        CUDA_TRY(cudaMemcpyToSymbol(pk::g_stage_prof, z, sizeof(z)));
+    }
+    return PLONKISH_CUDA_OK;
+}
+#endif

@@ -723,18 +723,32 @@ PK_HD StageSmem stage_carve(u32 *base, u32 R, u32 S) {
 }
 inline size_t stage_smem_bytes(u32 R, u32 S) { return sizeof(u32) * (3 * (size_t)R + 64 + 2 * (size_t)S); }
 
+// Optional phase timing of the staged partition (experiment builds only: -DPK_STAGE_PROF; tools/stage_phase_probe.py).
+#ifdef PK_STAGE_PROF
+__device__ unsigned long long g_stage_prof[16];
+#define PK_PROF_START() unsigned long long pk_prof_t = clock64()
+#define PK_PROF_ADD(k) do { if (blockIdx.x == 7 && threadIdx.x == 0) { const unsigned long long t1 = clock64(); atomicAdd(&g_stage_prof[k], t1 - pk_prof_t); pk_prof_t = t1; } } while (0)
+#else
+#define PK_PROF_START() ((void)0)
+#define PK_PROF_ADD(k) ((void)0)
+#endif
+
 // Partition the block's EPT*blockDim items by digit: rank in shared memory, stage the
 // items sorted by digit, claim one contiguous global range per (block, digit) run with a
 // single atomicAdd on gcursor[digit], then write the runs out with consecutive lanes on
 // consecutive addresses.  Needs lcnt zeroed on entry; leaves it zeroed.
 template <int EPT>
 PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val)[EPT], const u32 (&aux)[EPT], const bool (&ok)[EPT],
-                            const StageSmem &m, u32 *gcursor, u32 *out_val, u16 *out_aux) {
+                            const StageSmem &m, u32 *gcursor, u32 *out_val, u16 *out_aux, int prof_base = 0) {
+    PK_PROF_START();
+    (void)prof_base;
     u32 rank[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) rank[e] = ok[e] ? atomicAdd(&m.lcnt[dig[e]], 1u) : 0u;
     __syncthreads();
+    PK_PROF_ADD(prof_base + 1);
     const u32 total = block_exclusive_scan(m.lcnt, m.lstart, R, m.scratch);
+    PK_PROF_ADD(prof_base + 2);
     for (u32 d = threadIdx.x; d < R; d += blockDim.x) {
         const u32 c = m.lcnt[d];
         if (c) m.gbase[d] = atomicAdd(&gcursor[d], c);
@@ -748,6 +762,7 @@ PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val)[EPT],
         }
     }
     __syncthreads();
+    PK_PROF_ADD(prof_base + 3);
     for (u32 q = threadIdx.x; q < total; q += blockDim.x) {
         const u32 kb = m.saux[q];
         const u32 d = kb >> 16;
@@ -756,8 +771,10 @@ PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val)[EPT],
         if (out_aux) out_aux[g] = (u16)(kb & 0xffffu);
     }
     __syncthreads();
+    PK_PROF_ADD(prof_base + 4);
     for (u32 d = threadIdx.x; d < R; d += blockDim.x) m.lcnt[d] = 0;
     __syncthreads();
+    PK_PROF_ADD(prof_base + 5);
 }
 
 // Level 1: one block per tile of points, all windows.  Partitions (bucket, table index)
@@ -778,6 +795,7 @@ __global__ void __launch_bounds__(1024) k_scatter_staged_b(const u32 *__restrict
         const u32 *row = digits + (size_t)w * p.n_pad;
         const u32 base_idx = w * p.stride;
         for (u32 s0 = beg; s0 < end; s0 += S) {
+            PK_PROF_START();
             u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
             bool ok[PK_STAGE_EPT];
 #pragma unroll
@@ -795,6 +813,10 @@ __global__ void __launch_bounds__(1024) k_scatter_staged_b(const u32 *__restrict
                     val[u * 4 + k] = (d & 0x80000000u) | (base_idx + i + (u32)k);
                 }
             }
+#ifdef PK_STAGE_PROF
+            if (dig[0] == 0xdeadbeefu) l1_val[0] = 0;  // keep the loads ahead of the clock read
+#endif
+            PK_PROF_ADD(0);
             staged_partition<PK_STAGE_EPT>(p.HI, dig, val, aux, ok, m, gcursor, l1_val, l1_key);
         }
     }
@@ -1017,6 +1039,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter_staged_b(const u32 *__r
     __syncthreads();
     u32 *cur = gcursor + (size_t)bin * nlo;
     for (u32 s0 = sb; s0 < se; s0 += S) {
+        PK_PROF_START();
         u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
         bool ok[PK_STAGE_EPT];
 #pragma unroll
@@ -1027,7 +1050,11 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter_staged_b(const u32 *__r
             val[e] = ok[e] ? l1_val[q] : 0u;
             aux[e] = 0;
         }
-        staged_partition<PK_STAGE_EPT>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr);
+#ifdef PK_STAGE_PROF
+        if (dig[0] == 0xdeadbeefu) sorted[0] = 0;
+#endif
+        PK_PROF_ADD(8);
+        staged_partition<PK_STAGE_EPT>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr, 8);
     }
 }
 
