@@ -710,18 +710,34 @@ PK_HD u32 block_exclusive_scan(const u32 *cnt, u32 *start, u32 R, u32 *scratch) 
     return total;
 }
 
-// Shared-memory view used by the staged kernels (dynamic smem, all u32):
-//   lcnt[R] | lstart[R] | gbase[R] | scratch[64] | sval[S] | saux[S]
+// Shared-memory view used by the staged kernels (dynamic smem):
+//   u32 lcnt[R] | lstart[R] | gdelta[R] | scratch[64] | (pad to 8 bytes) | u64 stage[S]
+// A staged entry is one 64-bit word (digit << 48 | aux << 32 | value): one random store when it is staged and one load
+// when it is written out, instead of two each (the random shared accesses are what the stage phases wait for,
+// tools/stage_phase_probe.py).  gdelta[d] = global base of the block's run for digit d minus its start in the stage.
 struct StageSmem {
-    u32 *lcnt, *lstart, *gbase, *scratch, *sval, *saux;
+    u32 *lcnt, *lstart, *gdelta, *scratch;
+    unsigned long long *stage;
 };
+PK_HD u32 stage_words_before(u32 R) { return (3u * R + 64u + 1u) & ~1u; }
 PK_HD StageSmem stage_carve(u32 *base, u32 R, u32 S) {
     StageSmem m;
-    m.lcnt = base; m.lstart = base + R; m.gbase = base + 2 * R; m.scratch = base + 3 * R;
-    m.sval = base + 3 * R + 64; m.saux = m.sval + S;
+    (void)S;
+    m.lcnt = base; m.lstart = base + R; m.gdelta = base + 2 * R; m.scratch = base + 3 * R;
+    m.stage = reinterpret_cast<unsigned long long *>(base + stage_words_before(R));
     return m;
 }
-inline size_t stage_smem_bytes(u32 R, u32 S) { return sizeof(u32) * (3 * (size_t)R + 64 + 2 * (size_t)S); }
+inline size_t stage_smem_bytes(u32 R, u32 S) { return sizeof(u32) * ((size_t)((3u * R + 64u + 1u) & ~1u) + 2 * (size_t)S); }
+
+// L2 prefetch of a line the block reads in its next stage (the stage's own loads are issued right before their first
+// use, and with one block per SM nothing else hides their DRAM latency).
+PK_HD void prefetch_l2(const void *ptr) {
+#ifndef PLONKISH_EMUL
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
 
 // Optional phase timing of the staged partition (experiment builds only: -DPK_STAGE_PROF; tools/stage_phase_probe.py).
 #ifdef PK_STAGE_PROF
@@ -737,38 +753,43 @@ __device__ unsigned long long g_stage_prof[16];
 // items sorted by digit, claim one contiguous global range per (block, digit) run with a
 // single atomicAdd on gcursor[digit], then write the runs out with consecutive lanes on
 // consecutive addresses.  Needs lcnt zeroed on entry; leaves it zeroed.
-template <int EPT>
-PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val)[EPT], const u32 (&aux)[EPT], const bool (&ok)[EPT],
-                            const StageSmem &m, u32 *gcursor, u32 *out_val, u16 *out_aux, int prof_base = 0) {
+// LATE: the values are not needed to rank; they are loaded from late_src[late_q + e * blockDim] once the ranks are taken,
+// so that they are in flight during the scan instead of holding EPT registers through the rank phase.
+template <int EPT, bool AUX = true, bool LATE = false>
+PK_HD void staged_partition(u32 R, const u32 (&dig)[EPT], const u32 (&val_in)[EPT], const u32 (&aux)[EPT], const bool (&ok)[EPT],
+                            const StageSmem &m, u32 *gcursor, u32 *out_val, u16 *out_aux, int prof_base = 0,
+                            const u32 *late_src = nullptr, u32 late_q = 0) {
     PK_PROF_START();
     (void)prof_base;
     u32 rank[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) rank[e] = ok[e] ? atomicAdd(&m.lcnt[dig[e]], 1u) : 0u;
+    u32 val[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) val[e] = LATE ? (ok[e] ? late_src[late_q + (u32)e * blockDim.x] : 0u) : val_in[e];
     __syncthreads();
     PK_PROF_ADD(prof_base + 1);
     const u32 total = block_exclusive_scan(m.lcnt, m.lstart, R, m.scratch);
     PK_PROF_ADD(prof_base + 2);
     for (u32 d = threadIdx.x; d < R; d += blockDim.x) {
         const u32 c = m.lcnt[d];
-        if (c) m.gbase[d] = atomicAdd(&gcursor[d], c);
+        if (c) m.gdelta[d] = atomicAdd(&gcursor[d], c) - m.lstart[d];
     }
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         if (ok[e]) {
             const u32 pos = m.lstart[dig[e]] + rank[e];
-            m.sval[pos] = val[e];
-            m.saux[pos] = (dig[e] << 16) | aux[e];
+            reinterpret_cast<uint2 *>(m.stage)[pos] = make_uint2(val[e], AUX ? ((dig[e] << 16) | aux[e]) : (dig[e] << 16));
         }
     }
     __syncthreads();
     PK_PROF_ADD(prof_base + 3);
     for (u32 q = threadIdx.x; q < total; q += blockDim.x) {
-        const u32 kb = m.saux[q];
-        const u32 d = kb >> 16;
-        const u32 g = m.gbase[d] + (q - m.lstart[d]);
-        out_val[g] = m.sval[q];
-        if (out_aux) out_aux[g] = (u16)(kb & 0xffffu);
+        const uint2 v = reinterpret_cast<const uint2 *>(m.stage)[q];
+        const u32 kb = v.y;
+        const u32 g = m.gdelta[kb >> 16] + q;
+        out_val[g] = v.x;
+        if (AUX) out_aux[g] = (u16)(kb & 0xffffu);
     }
     __syncthreads();
     PK_PROF_ADD(prof_base + 4);
@@ -798,6 +819,18 @@ __global__ void __launch_bounds__(1024) k_scatter_staged_b(const u32 *__restrict
             PK_PROF_START();
             u32 dig[PK_STAGE_EPT], val[PK_STAGE_EPT], aux[PK_STAGE_EPT];
             bool ok[PK_STAGE_EPT];
+            if ((threadIdx.x & 7u) == 0) {  // the next stage's digits (same window further on, or the next window's row): one lane per 128-byte line
+                const bool same = s0 + S < end;
+                const u32 *nrow = same ? row : row + p.n_pad;
+                const u32 ns0 = same ? s0 + S : beg;
+                if (same || w + 1 < p.W) {
+#pragma unroll
+                    for (int u = 0; u < PK_STAGE_EPT / 4; ++u) {
+                        const u32 i = ns0 + 4 * (threadIdx.x + (u32)u * blockDim.x);
+                        if (i < end) prefetch_l2(nrow + i);
+                    }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < PK_STAGE_EPT / 4; ++u) {
                 const u32 i = s0 + 4 * (threadIdx.x + (u32)u * blockDim.x);
@@ -1047,14 +1080,14 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter_staged_b(const u32 *__r
             const u32 q = s0 + threadIdx.x + (u32)e * blockDim.x;
             ok[e] = q < se;
             dig[e] = ok[e] ? (u32)l1_key[q] : 0u;
-            val[e] = ok[e] ? l1_val[q] : 0u;
+            val[e] = 0;
             aux[e] = 0;
         }
 #ifdef PK_STAGE_PROF
         if (dig[0] == 0xdeadbeefu) sorted[0] = 0;
 #endif
         PK_PROF_ADD(8);
-        staged_partition<PK_STAGE_EPT>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr, 8);
+        staged_partition<PK_STAGE_EPT, false, true>(nlo, dig, val, aux, ok, m, cur, sorted, (u16 *)nullptr, 8, l1_val, s0 + threadIdx.x);
     }
 }
 
