@@ -430,15 +430,21 @@ private:
 
 static std::atomic<unsigned long long> g_staged_bytes{0};
 // Host -> device copy of caller memory on `stream` (current device = c->dev).  Returns once the source may be reused.
-static const size_t STAGE_MIN_BYTES = (size_t)32 << 20;
+// tuning override: PLONKISH_CUDA_STAGE_MIN_MB (uploads of at least this many MiB from pageable memory go through the ring)
+static const size_t STAGE_MIN_BYTES = [] {
+    const char *e = getenv("PLONKISH_CUDA_STAGE_MIN_MB");
+    const long v = e ? atol(e) : 0;
+    return (size_t)(v >= 1 && v <= 4096 ? v : 4) << 20;
+}();
 // Whether an upload of `bytes` from src goes through the staging ring: unregistered (pageable) host memory only.
 static bool is_staged_source(const void *src, size_t bytes) {
     static const bool staging = [] {
         const char *e = getenv("PLONKISH_CUDA_STAGING");
         return !(e && e[0] == '0');
     }();
-    // below 32 MiB the driver's own pageable path is as fast or faster (measured end to end, MSM of 2^17 / 2^19 / 2^20 /
-    // 2^21 / 2^24 points: staged 1.46 / 3.26 / 4.96 / 7.70 / 39.4 ms, direct 1.15 / 2.90 / 4.91 / 9.76 / 72.8 ms)
+    // From 4 MiB on the ring beats the driver's own pageable path (measured end to end with streaming stores, MSM of
+    // 2^17 / 2^18 / 2^19 / 2^20 / 2^21 points = 4 .. 64 MiB: staged 1.06 / 1.48 / 2.38 / 3.74 / 6.12 ms, with the ring only
+    // from 32 MiB 1.13 / 1.66 / 2.90 / 4.59 / 6.71 ms; before the streaming stores the driver's path won below 32 MiB).
     if (!staging || bytes < STAGE_MIN_BYTES) return false;
     cudaPointerAttributes attr;
     const cudaError_t q = cudaPointerGetAttributes(&attr, src);

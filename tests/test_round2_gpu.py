@@ -71,8 +71,8 @@ def test_pageable_pinned_and_unstaged_uploads_agree(pk, oracle, n):
     assert pk.variable_base_msm(pinned, reg).tobytes() == want.tobytes()
     assert pk.staged_bytes() == before, "a pinned source must not be staged"
     assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes()
-    # upload chunks of 32 MiB and more go through the ring, smaller ones down the driver's pageable path
-    assert (pk.staged_bytes() - before > 0) == (n >= 1 << 22)
+    # upload chunks of 4 MiB and more go through the ring, smaller ones down the driver's pageable path
+    assert (pk.staged_bytes() - before > 0) == (n >= 1 << 20)
     os.environ["PLONKISH_CUDA_COPY_THREADS"] = "3"  # (read once, at the first staged upload: harmless later)
     outs = pk.variable_base_msm_batch([sc, pinned, sc], reg)
     assert all(o.tobytes() == want.tobytes() for o in outs)
