@@ -1,6 +1,7 @@
 """In-tree build of libplonkish_cuda.so for sm_100a (nvcc cross-compiles without a GPU)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 
@@ -18,11 +19,25 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = OUT + ".stamp"
+
+
+def _fingerprint() -> str:
+    """sha256 over the compiler flags and every source / header: the library is rebuilt when its sources changed, however
+    the files' mtimes came out of a checkout or a copy (an mtime gate can skip a needed build)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in SOURCES + HEADERS:
+        h.update(p.encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+    with open(STAMP) as f:
+        return f.read().strip() != _fingerprint()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -33,6 +48,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(_fingerprint() + "\n")
     if verbose:
         print(res.stderr)
     return OUT

@@ -279,3 +279,71 @@ def test_multi_entry_on_the_visible_gpus(pk, oracle):
         assert pk.variable_base_msm(sc, reg).tobytes() == want.tobytes(), g
         reg.release()
         assert pk.variable_base_msm(sc[:5000], bs[:5000], n_gpus=g).tobytes() == oracle.known_dlog_answer(3, 5, sc[:5000]).tobytes(), g
+
+
+def _skewed(pk, n, kind, seed):
+    """Scalar sets of SURVEY.md 8d: a 0 / 1 / -1 selector column with half zeros, small integers, one value everywhere."""
+    from oracle import bigint_ref as br
+
+    rng = np.random.default_rng(seed)
+    r = br.R if hasattr(br, "R") else 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    mont = lambda v: np.frombuffer((v % r * (1 << 256) % r).to_bytes(32, "little"), dtype=np.uint64)  # noqa: E731
+    if kind == "selector":
+        pool = np.stack([mont(0), mont(1), mont(r - 1)])
+        return pool[rng.choice(3, size=n, p=[0.5, 0.25, 0.25])].copy()
+    if kind == "small":
+        pool = np.stack([mont(v) for v in range(64)])
+        return pool[rng.integers(0, 64, size=n)].copy()
+    return np.repeat(pk.random_scalars(1, seed)[:1], n, axis=0).copy()
+
+
+@pytest.mark.parametrize("n", [70001, (1 << 18) + 3, 1 << 20])
+def test_accumulate_tiers_and_equal_runs_give_the_same_point(pk, oracle, n):
+    """k_accumulate's runs (tiers of shrinking length derived from the entry count on the device, msm_kernels.cuh
+    pk_acc_run) against equal runs and other tier counts, on uniform scalars and on the skew set — whose entry counts are
+    a fraction of what the launch is sized for — all against the known-discrete-log answer."""
+    import torch
+
+    d_bs = pk.synth_bases_device(n, 3, 5)
+    reg = pk.G1Bases(d_bs, mode=pk.G1Bases.TABLE)
+    try:
+        for kind in ("uniform", "selector", "small", "same"):
+            sc = pk.random_scalars(n, seed=n % 991) if kind == "uniform" else _skewed(pk, n, kind, n % 991)
+            want = oracle.known_dlog_answer(3, 5, sc).tobytes()
+            d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+            for knob, value in ((None, None), ("PLONKISH_CUDA_ACC_TIERS", "1"), ("PLONKISH_CUDA_ACC_TIERS", "3"), ("PLONKISH_CUDA_ACC_TIERS", "12"),
+                                ("PLONKISH_CUDA_ACC_L", "64"), ("PLONKISH_CUDA_ACC_L", "1000"), ("PLONKISH_CUDA_ACC_WAVES", "2.5")):
+                if knob:
+                    os.environ[knob] = value
+                try:
+                    got = pk.variable_base_msm_device(d_sc, reg).cpu().numpy().view(np.uint64).tobytes()
+                finally:
+                    if knob:
+                        os.environ.pop(knob)
+                assert got == want, (kind, knob, value)
+    finally:
+        reg.release()
+
+
+def test_five_chunk_upload_and_the_staging_rate(pk, oracle):
+    """The chunk geometry the host-scalar MSM switches to when the staging ring is slow (ranks sharing a host), forced
+    here through PLONKISH_CUDA_HOST_CUTS, from pageable and from pinned memory; and the ring reports the rate of its
+    last large uploads."""
+    import torch
+
+    n = (1 << 23) + 7
+    sc = pk.random_scalars(n, seed=523)
+    want = oracle.known_dlog_answer(3, 5, sc).tobytes()
+    reg = pk.G1Bases(pk.synth_bases_device(n, 3, 5), mode=pk.G1Bases.TABLE)
+    keep, pinned = _pinned(torch, sc)
+    try:
+        assert pk.variable_base_msm(sc, reg).tobytes() == want
+        assert pk.staging_rate_gbps() > 0.5, "a 256 MiB pageable upload went through the ring: it must have measured its rate"
+        os.environ["PLONKISH_CUDA_HOST_CUTS"] = "0.0625,0.16,0.32,0.58,1"
+        try:
+            assert pk.variable_base_msm(sc, reg).tobytes() == want, "five chunks, pageable"
+            assert pk.variable_base_msm(pinned, reg).tobytes() == want, "five chunks, pinned"
+        finally:
+            os.environ.pop("PLONKISH_CUDA_HOST_CUTS")
+    finally:
+        reg.release()
