@@ -1063,13 +1063,31 @@ static int enqueue_host_msm(Ctx *c, const void *h_scalars, const BasesView &base
     } else if (forced >= 1 && forced <= 16) {
         for (long k = 1; k <= forced; ++k) cuts.push_back(n * (size_t)k / (size_t)forced);
     } else if (n >= ((size_t)1 << 23) && n <= MAX_POINTS_PER_LAUNCH) {
-        // The three-chunk geometry needs an upload rate of ~44 GB/s (11/16 of the scalars must arrive while a quarter of
-        // the points computes).  The staging ring sustains that for one rank; ranks sharing the host's memory bandwidth
-        // do not (two ranks: ~25 GB/s each), and then five chunks growing by 1.6x hide more than their fixed costs take
-        // (measured with two ranks, 2^24 points each, pageable: 43.0 -> 38.5 ms; pinned sources lose: 35.8 -> 38.7 ms).
+        // The three-chunk geometry (1/16, 1/4, 11/16) needs an upload rate of ~44 GB/s: 11/16 of the scalars must arrive
+        // while a quarter of the points computes.  The staging ring sustains that for one rank; ranks sharing the host's
+        // memory bandwidth do not (measured per rank: 28 GB/s with two ranks, 17 with four, 8.7 with eight), and the
+        // MSM itself consumes its scalars at ~16.5 GB/s (32 B x 516 Mpoints/s).  So the chunks grow by g = upload rate /
+        // consumption rate, from 1/16 of the points, in as few chunks as that takes and at most eight (every extra chunk
+        // costs ~1 ms: one more bucket array in the reduce, smaller launches); with g near one that is eight equal
+        // chunks.  Measured, 2^24 points per rank from pageable memory: two ranks 43.0 -> 38.2 ms (five chunks), four
+        // ranks 50.8 ms with five chunks (see DESIGN.md 6 for the final figures).  Pinned sources keep three chunks
+        // (five lose there: 35.8 -> 38.7 ms).
         const double rate = Stager::get(c->dev).rate_gbps();
-        if (rate > 0 && rate < 35.0 && is_staged_source(h_scalars, n * 32)) {
-            cuts = {n / 16, (size_t)((double)n * 0.16), (size_t)((double)n * 0.32), (size_t)((double)n * 0.58), n};
+        const double g_raw = rate / 16.5;
+        if (rate > 0 && g_raw < 2.6 && is_staged_source(h_scalars, n * 32)) {
+            const double g = g_raw < 1.0 ? 1.0 : g_raw;
+            const int max_chunks = 8;
+            double f[max_chunks], sum = 0;
+            int m = 0;
+            for (double v = 1.0 / 16.0; m < max_chunks && sum < 1.0; v *= g) { f[m++] = v; sum += v; }
+            double acc = 0;
+            for (int k = 0; k < m; ++k) {
+                acc += f[k] / sum;
+                size_t cut = k + 1 == m ? n : (size_t)((double)n * acc);
+                cut &= ~(size_t)7;  // chunk starts stay 256-byte aligned in the scalar buffer
+                if (k + 1 == m) cut = n;
+                cuts.push_back(cut);
+            }
         } else {
             cuts = {n / 16, 5 * (n / 16), n};
         }

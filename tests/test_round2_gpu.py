@@ -297,7 +297,7 @@ def _skewed(pk, n, kind, seed):
     return np.repeat(pk.random_scalars(1, seed)[:1], n, axis=0).copy()
 
 
-@pytest.mark.parametrize("n", [70001, (1 << 18) + 3, 1 << 20])
+@pytest.mark.parametrize("n", [70001, (1 << 19) + 3])
 def test_accumulate_tiers_and_equal_runs_give_the_same_point(pk, oracle, n):
     """k_accumulate's runs (tiers of shrinking length derived from the entry count on the device, msm_kernels.cuh
     pk_acc_run) against equal runs and other tier counts, on uniform scalars and on the skew set — whose entry counts are
@@ -311,8 +311,8 @@ def test_accumulate_tiers_and_equal_runs_give_the_same_point(pk, oracle, n):
             sc = pk.random_scalars(n, seed=n % 991) if kind == "uniform" else _skewed(pk, n, kind, n % 991)
             want = oracle.known_dlog_answer(3, 5, sc).tobytes()
             d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
-            for knob, value in ((None, None), ("PLONKISH_CUDA_ACC_TIERS", "1"), ("PLONKISH_CUDA_ACC_TIERS", "3"), ("PLONKISH_CUDA_ACC_TIERS", "12"),
-                                ("PLONKISH_CUDA_ACC_L", "64"), ("PLONKISH_CUDA_ACC_L", "1000"), ("PLONKISH_CUDA_ACC_WAVES", "2.5")):
+            for knob, value in ((None, None), ("PLONKISH_CUDA_ACC_TIERS", "1"), ("PLONKISH_CUDA_ACC_TIERS", "3"), ("PLONKISH_CUDA_ACC_L", "64"),
+                                ("PLONKISH_CUDA_ACC_WAVES", "2.5")):
                 if knob:
                     os.environ[knob] = value
                 try:
