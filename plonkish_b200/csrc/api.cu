@@ -90,7 +90,11 @@ struct Ctx {
         cudaEvent_t done = nullptr;
         DeviceBuffer arena, scalars;
         void *d_res = nullptr;            // 128-byte projective result slot
-    } lanes[PK_LANES];
+    } lanes[PK_LANES + 1];                // lanes[PK_LANES]: the "big lane" — every second LARGE MSM of a batch / many call
+                                          // runs there with its own full-size workspace, so that its decompose + sort (HBM and
+                                          // latency bound) fill the GPU while the previous MSM's accumulate drains and its
+                                          // single-wave reduce, item levels and finalize run (blocks of the older kernel are
+                                          // dispatched first, so the two accumulates do not fight)
     void *d_out = nullptr;  // [0,64) affine out, [192,256) synth step point, [256,384) running projective sum, [384,448) fixed base
     void *h_out = nullptr;  // pinned mirror of the affine result
     std::mutex mu;
@@ -1197,6 +1201,18 @@ extern "C" int plonkish_cuda_msm_bn254_g1(const void *scalars, const void *bases
 // works on MSM j, and the host waits once at the end.
 static uint64_t publish_scalars(int dev, void *d_ptr, size_t n);
 
+// PLONKISH_CUDA_BIG_LANE: 0 = off, 1 (default) = the batch entry alternates its MSMs between the main stream and the big
+// lane, 2 = the many / open entry does so too for its large MSMs.  Measured on B200: batch_commit of three 2^24-point
+// polynomials 101.9 -> 100.9 ms, of three 2^20-point ones 10.4 -> 9.8 ms (only the decompose and the small kernels find
+// room beside the previous MSM's reduce: the 1 024-thread sort blocks need a whole SM); open on 2^24 evaluations
+// 38.6 -> 39.2 ms, on 2^20 5.29 -> 5.08 ms, hence off there by default.
+static int big_lane_mode() {
+    static const int mode = [] { const char *e = getenv("PLONKISH_CUDA_BIG_LANE"); return e ? atoi(e) : 1; }();
+    return mode;
+}
+static bool big_lane_on() { return big_lane_mode() >= 1; }
+
+
 // keep != nullptr: every polynomial's scalars stay resident under keep[j] (its own allocation)
 // instead of passing through the two staging buffers.
 static int batch_impl(const void *const *scalars_list, size_t count, uint64_t bases_handle, size_t n, void *out_affine64_list, uint64_t *keep) {
@@ -1236,6 +1252,12 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     if ((rc = grow(c->arena, pk_workspace_bytes(plan)))) return rc;  // before anything is in flight: growing synchronises
     void *bufs[2] = {c->scalars.ptr, c->scalars2.ptr};
     const bool timed = timer_mode() != 0;
+    // Every second MSM runs on the big lane (own stream, own workspace): its decompose and sort overlap the previous
+    // MSM's draining accumulate, reduce, item levels and finalize.  Not when the timer lines are on: they measure each
+    // MSM's own span on the one compute stream.
+    Ctx::Lane &big = c->lanes[PK_LANES];
+    const bool alternate = big_lane_on() && !timed && count >= 2;
+    if (alternate && (rc = grow(big.arena, pk_workspace_bytes(plan)))) return rc;
     std::vector<cudaEvent_t> tev;  // timed: the end of every MSM on the compute stream, for one timer line each
     struct TevGuard { std::vector<cudaEvent_t> &v; ~TevGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); } } tev_guard{tev};
     if (timed) {
@@ -1254,19 +1276,35 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     }
     MsmWorkspace ws = pk_carve_workspace(plan, c->arena.ptr);
     ws.result = (xyzz *)((char *)c->d_out + 256);
+    MsmWorkspace ws_big = ws;
+    if (alternate) {
+        ws_big = pk_carve_workspace(plan, big.arena.ptr);
+        ws_big.result = (xyzz *)big.d_res;
+        // the big lane starts after everything enqueued so far on the main stream's predecessors (the previous call)
+        if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(big.stream, c->last_done, 0));
+    }
+    bool big_used = false;
     // MSM j >= 1: its upload runs on the copy stream while MSM j-1 computes
     for (size_t j = 1; j < count; ++j) {
         const int b = (int)(j & 1);
+        const bool on_big = alternate && (j & 1);
+        cudaStream_t st = on_big ? big.stream : c->stream;
+        const MsmWorkspace &w = on_big ? ws_big : ws;
         void *dst = keep ? kept[j] : bufs[b];
         if (j >= 2 && !keep) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->buf_free[b], 0));  // MSM j-2 has consumed this buffer
         CUDA_TRY(upload(c, dst, scalars_list[j], bytes, c->copy_stream));
         CUDA_TRY(cudaEventRecord(c->chunk_ready[b], c->copy_stream));
-        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
-        pk_enqueue_msm(plan, dst, view.ptr, ws, nullptr, c->stream);
-        CUDA_TRY(cudaEventRecord(c->buf_free[b], c->stream));  // scalars are dead after the decompose; recorded after the whole MSM for simplicity
-        PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, c->stream, ws.result, 1u,
+        CUDA_TRY(cudaStreamWaitEvent(st, c->chunk_ready[b], 0));
+        pk_enqueue_msm(plan, dst, view.ptr, w, nullptr, st);
+        CUDA_TRY(cudaEventRecord(c->buf_free[b], st));  // scalars are dead after the decompose; recorded after the whole MSM for simplicity
+        PK_LAUNCH(k_finalize, dim3(1), dim3(32), 0, st, w.result, 1u,
                   (affine *)((char *)c->batch_out.ptr + j * PLONKISH_CUDA_AFFINE_BYTES), (xyzz *)nullptr);
+        big_used = big_used || on_big;
         if (timed) CUDA_TRY(cudaEventRecord(tev[j + 1], c->stream));
+    }
+    if (big_used) {  // join the big lane before the results are read
+        CUDA_TRY(cudaEventRecord(big.done, big.stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, big.done, 0));
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
@@ -1348,7 +1386,8 @@ static int enqueue_many(Ctx *c, const std::vector<ManyJob> &jobs, void *d_out_li
     }
     std::vector<int> lane_of(count, -1);
     // size every lane's scratch once, before anything is enqueued (growing synchronises the device)
-    size_t lane_arena[NL] = {}, lane_scalars[NL] = {}, lane_load[NL] = {}, big_scalars = 0;
+    size_t lane_arena[NL] = {}, lane_scalars[NL] = {}, lane_load[NL] = {}, big_scalars = 0, big_arena = 0;
+    unsigned big_seen = 0;
     for (size_t j : order) {
         const ManyJob &jb = jobs[j];
         if (jb.n <= SMALL) {
@@ -1362,7 +1401,15 @@ static int enqueue_many(Ctx *c, const std::vector<ManyJob> &jobs, void *d_out_li
             const size_t sb = jb.on_device ? 0 : jb.n * PLONKISH_CUDA_SCALAR_BYTES;
             lane_scalars[l] = sb > lane_scalars[l] ? sb : lane_scalars[l];
         } else if (jb.on_device) {
-            if (jb.n <= MAX_POINTS_PER_LAUNCH && (rc = grow(c->arena, pk_workspace_bytes(plan_for(c, jb.view, jb.n, 0))))) return rc;
+            // large resident jobs alternate between the main stream and the big lane (opt-in: PLONKISH_CUDA_BIG_LANE=2)
+            const bool alt = big_lane_mode() >= 2 && jb.n <= MAX_POINTS_PER_LAUNCH && (big_seen++ & 1u);
+            const size_t a = jb.n <= MAX_POINTS_PER_LAUNCH ? pk_workspace_bytes(plan_for(c, jb.view, jb.n, 0)) : 0;
+            if (alt) {
+                lane_of[j] = NL;
+                big_arena = a > big_arena ? a : big_arena;
+            } else if (a && (rc = grow(c->arena, a))) {
+                return rc;
+            }
         } else {
             big_scalars = jb.n > big_scalars ? jb.n : big_scalars;
         }
@@ -1370,11 +1417,12 @@ static int enqueue_many(Ctx *c, const std::vector<ManyJob> &jobs, void *d_out_li
     for (int l = 0; l < NL; ++l) {
         if ((rc = grow(c->lanes[l].arena, lane_arena[l])) || (rc = grow(c->lanes[l].scalars, lane_scalars[l]))) return rc;
     }
+    if (big_arena && (rc = grow(c->lanes[NL].arena, big_arena))) return rc;
     if (big_scalars && (rc = grow(c->scalars, big_scalars * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
     CUDA_TRY(cudaMemsetAsync(d_out_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES, c->stream));  // n == 0 entries
     if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
     CUDA_TRY(cudaEventRecord(c->many_start, c->stream));  // lanes start after the memset / the producers of device scalars
-    bool lane_used[NL] = {};
+    bool lane_used[NL + 1] = {};
     // Enqueue smallest first: the latency-bound small MSMs start while the host is still launching the rest
     // and are done before the large ones need the whole GPU (largest first measured 2 ms slower at k = 20).
     std::reverse(order.begin(), order.end());
@@ -1406,7 +1454,7 @@ static int enqueue_many(Ctx *c, const std::vector<ManyJob> &jobs, void *d_out_li
         }
     }
     CUDA_TRY(cudaGetLastError());
-    for (int l = 0; l < NL; ++l) {
+    for (int l = 0; l <= NL; ++l) {
         if (!lane_used[l]) continue;
         CUDA_TRY(cudaEventRecord(c->lanes[l].done, c->lanes[l].stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->lanes[l].done, 0));
