@@ -291,7 +291,7 @@ public:
     cudaError_t run(int dev, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
         std::lock_guard<std::mutex> job_lock(job_mu_);
         if (!ensure_ready(dev)) return cudaErrorMemoryAllocation;
-        const auto t0 = std::chrono::steady_clock::now();
+        copy_ns_.store(0, std::memory_order_relaxed);
         {
             std::lock_guard<std::mutex> lk(mu_);
             src_ = (const char *)src; dst_ = (char *)dst; bytes_ = bytes; stream_ = stream; dev_ = dev;
@@ -310,9 +310,16 @@ public:
         npieces_ = 0;
         // what the ring sustains on this host right now (several ranks share its memory bandwidth): the host-scalar MSM
         // cuts its points into more, smaller chunks when uploads are slow (enqueue_host_msm)
-        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (sec > 0 && bytes >= ((size_t)32 << 20)) {
-            const double gbps = (double)bytes / sec * 1e-9, old = rate_gbps_.load(std::memory_order_relaxed);
+        // The rate is that of the host-side copies alone (bytes x copiers / time spent copying): it is the host's memory
+        // bandwidth that ranks share.  Wall time would also count the waits for ring slots whose DMA sits behind a stream
+        // dependency (the batch entry's second buffer waits for the MSM before last) and read as a slow host.
+        const double copy_sec = (double)copy_ns_.load(std::memory_order_relaxed) * 1e-9;
+        if (copy_sec > 0 && bytes >= ((size_t)32 << 20)) {
+            const size_t np = (bytes + piece_ - 1) / piece_;
+            const double par = (double)(np < (size_t)nthreads_ ? np : (size_t)nthreads_);
+            double gbps = (double)bytes * par / copy_sec * 1e-9;
+            if (gbps > 50.0) gbps = 50.0;  // the DMA engine's share of PCIe is the limit above that
+            const double old = rate_gbps_.load(std::memory_order_relaxed);
             rate_gbps_.store(old > 0 ? 0.5 * old + 0.5 * gbps : gbps, std::memory_order_relaxed);
         }
         return err_;
@@ -400,7 +407,10 @@ private:
             if (slot_dev_[s] >= 0) e = cudaEventSynchronize(slot_ev_[s][slot_dev_[s]]);
             const size_t off = i * piece_;
             const size_t len = bytes_ - off < piece_ ? bytes_ - off : piece_;
+            const auto c0 = std::chrono::steady_clock::now();
             plonkish_cuda_host_copy(slots_[s], src_ + off, len, stream_stores_ ? 1 : 0);
+            copy_ns_.fetch_add((unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - c0).count(),
+                               std::memory_order_relaxed);
             if (e == cudaSuccess) e = cudaMemcpyAsync(dst_ + off, slots_[s], len, cudaMemcpyHostToDevice, stream_);
             if (e == cudaSuccess) e = cudaEventRecord(slot_ev_[s][dev], stream_);
             {
@@ -417,6 +427,7 @@ private:
     int nthreads_ = 2, nslots_ = 6;
     bool stream_stores_ = true;
     std::atomic<double> rate_gbps_{0.0};
+    std::atomic<unsigned long long> copy_ns_{0};
     std::vector<void *> slots_;
     std::vector<std::vector<cudaEvent_t>> slot_ev_;  // [slot][device]
     std::vector<int> slot_dev_;                      // device whose event the slot's last piece recorded
@@ -1254,9 +1265,11 @@ static int batch_impl(const void *const *scalars_list, size_t count, uint64_t ba
     const bool timed = timer_mode() != 0;
     // Every second MSM runs on the big lane (own stream, own workspace): its decompose and sort overlap the previous
     // MSM's draining accumulate, reduce, item levels and finalize.  Not when the timer lines are on: they measure each
-    // MSM's own span on the one compute stream.
+    // MSM's own span on the one compute stream.  And only when every polynomial has its own resident buffer (keep): with
+    // the two recycled upload buffers an MSM on the big lane can get ahead of the first MSM's last chunk, whose end then
+    // frees buffer 0 late and stalls the third upload (measured: three 2^24-point MSMs 101.2 -> 109.4 ms).
     Ctx::Lane &big = c->lanes[PK_LANES];
-    const bool alternate = big_lane_on() && !timed && count >= 2;
+    const bool alternate = big_lane_on() && !timed && count >= 2 && keep != nullptr;
     if (alternate && (rc = grow(big.arena, pk_workspace_bytes(plan)))) return rc;
     std::vector<cudaEvent_t> tev;  // timed: the end of every MSM on the compute stream, for one timer line each
     struct TevGuard { std::vector<cudaEvent_t> &v; ~TevGuard() { for (cudaEvent_t e : v) cudaEventDestroy(e); } } tev_guard{tev};
