@@ -31,6 +31,12 @@ extern "C" {
     fn plonkish_cuda_msm_bn254_g1_batch_keep(scalars_list: *const *const c_void, count: usize, handle: u64, n: usize, out: *mut c_void, scalars_handles: *mut u64) -> c_int;
     fn plonkish_cuda_fr_linear_combination(handles: *const u64, coeffs: *const c_void, count: usize, n: usize, out_handle: *mut u64) -> c_int;
     fn plonkish_cuda_fr_div_linear(handle: u64, z: *const c_void, out_quotient: *mut u64, out_rem: *mut c_void) -> c_int;
+    fn plonkish_cuda_fr_quotients(handle: u64, point: *const c_void, num_vars: usize, out_q: *mut u64, out_eval: *mut c_void) -> c_int;
+    fn plonkish_cuda_msm_bn254_g1_many_resident(scalars_handle: u64, offsets: *const usize, bases_handles: *const u64, ns: *const usize, count: usize,
+                                                out: *mut c_void) -> c_int;
+    fn plonkish_cuda_zeromorph_q_hat_bn254(q_handle: u64, weights: *const c_void, num_vars: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_zeromorph_f_bn254(poly: u64, q_hat: u64, q: u64, z: *const c_void, c0: *const c_void, q_scalars: *const c_void, num_vars: usize,
+                                       out_handle: *mut u64) -> c_int;
     fn plonkish_cuda_fr_affine_table(device: c_int, num_vars: usize, polys: *const u64, rotations: *const i32, coeffs: *const c_void, count: usize,
                                      constant: *const c_void, identity_coeff: *const c_void, sparse_rows: *const u64, sparse_values: *const c_void,
                                      sparse_count: usize, out_handle: *mut u64) -> c_int;
@@ -521,6 +527,66 @@ impl ResidentCoeffs {
     pub fn open(&self, powers_of_s_g1: &RegisteredBases, z: &Fr) -> (G1Affine, Fr) {
         let (quotient, eval) = self.div_linear(z);
         (quotient.commit(powers_of_s_g1), eval)
+    }
+}
+
+/// The polynomial work of `Zeromorph::<UnivariateKzg<Bn256>>::open` (pcs/multilinear/zeromorph.rs:126-186) on a resident
+/// polynomial; the caller keeps the transcript and the scalar work (`eval_and_quotient_scalars`, :259-294).
+pub struct ZeromorphQuotients {
+    handle: u64, // packed: quotient i (2^i values) at element offset 2^i
+    num_vars: usize,
+}
+impl Drop for ZeromorphQuotients {
+    fn drop(&mut self) {
+        unsafe { plonkish_cuda_scalars_release(self.handle) };
+    }
+}
+impl ZeromorphQuotients {
+    /// `quotients(poly, point, ..)` (pcs/multilinear.rs:72-107; zeromorph.rs:149): the quotients stay in HBM, the remainder comes back.
+    pub fn new(poly: &ResidentPoly, point: &[Fr]) -> (Self, Fr) {
+        assert_eq!(poly.num_vars, point.len());
+        let (mut handle, mut eval) = (0u64, Fr::zero());
+        check(
+            unsafe { plonkish_cuda_fr_quotients(poly.handle, point.as_ptr() as *const c_void, point.len(), &mut handle, &mut eval as *mut Fr as *mut c_void) },
+            "plonkish_cuda_fr_quotients",
+        );
+        (Self { handle, num_vars: point.len() }, eval)
+    }
+    /// `UnivariateKzg::batch_commit` of the quotients (zeromorph.rs:150): q_i against `powers_of_s_g1[..2^i]`, one call.
+    pub fn commit(&self, powers_of_s_g1: &RegisteredBases) -> Vec<G1Affine> {
+        let sizes: Vec<usize> = (0..self.num_vars).map(|i| 1usize << i).collect();
+        let handles = vec![powers_of_s_g1.handle; self.num_vars];
+        let mut out = vec![G1Affine::default(); self.num_vars];
+        check(
+            unsafe {
+                plonkish_cuda_msm_bn254_g1_many_resident(self.handle, sizes.as_ptr(), handles.as_ptr(), sizes.as_ptr(), self.num_vars, out.as_mut_ptr() as *mut c_void)
+            },
+            "plonkish_cuda_msm_bn254_g1_many_resident",
+        );
+        out
+    }
+    /// `q_hat` (zeromorph.rs:157-168) for the challenge powers `powers(y).take(num_vars)`.
+    pub fn q_hat(&self, powers_of_y: &[Fr]) -> ResidentCoeffs {
+        assert_eq!(powers_of_y.len(), self.num_vars);
+        let mut handle = 0u64;
+        check(
+            unsafe { plonkish_cuda_zeromorph_q_hat_bn254(self.handle, powers_of_y.as_ptr() as *const c_void, self.num_vars, &mut handle) },
+            "plonkish_cuda_zeromorph_q_hat_bn254",
+        );
+        ResidentCoeffs { handle, len: 1 << self.num_vars }
+    }
+    /// `f` (zeromorph.rs:175-180): z * poly + q_hat, f[0] += c0 (= eval_scalar * eval), f += (q_scalars[i], q_i).
+    pub fn f(&self, poly: &ResidentPoly, q_hat: &ResidentCoeffs, z: &Fr, c0: &Fr, q_scalars: &[Fr]) -> ResidentCoeffs {
+        assert_eq!(q_scalars.len(), self.num_vars);
+        let mut handle = 0u64;
+        check(
+            unsafe {
+                plonkish_cuda_zeromorph_f_bn254(poly.handle, q_hat.handle, self.handle, z as *const Fr as *const c_void, c0 as *const Fr as *const c_void,
+                                                q_scalars.as_ptr() as *const c_void, self.num_vars, &mut handle)
+            },
+            "plonkish_cuda_zeromorph_f_bn254",
+        );
+        ResidentCoeffs { handle, len: 1 << self.num_vars }
     }
 }
 

@@ -160,6 +160,25 @@ int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const v
  * batch_open (:327).  The quotient is a new resident vector of the same length (top coefficient zero; release with
  * scalars_release), out_rem_mont32 the remainder, i.e. the polynomial's value at z. */
 int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *z_mont32, uint64_t *out_quotient_handle, void *out_rem_mont32);
+/* ---- Zeromorph<UnivariateKzg> (pcs/multilinear/zeromorph.rs), the multilinear PCS built on the univariate SRS --------
+ * `quotients` (pcs/multilinear.rs:72-107) of a resident polynomial of 2^num_vars evaluations at `point`, kept in HBM:
+ * *out_q_handle is a resident vector of 2^num_vars scalars holding quotient i (2^i values) at element offset 2^i (element
+ * 0 is zero), out_eval_mont32 the remainder f(point).  Zeromorph::open starts from it (zeromorph.rs:149). */
+int plonkish_cuda_fr_quotients(uint64_t scalars_handle, const void *point_mont32, size_t num_vars, uint64_t *out_q_handle, void *out_eval_mont32);
+/* `count` independent MSMs over sub-ranges of one resident vector: MSM j = scalars [offsets[j], offsets[j] + ns[j]) against
+ * the first ns[j] bases of bases_handles[j] (handles may repeat; all on the scalars' device).  With offsets[j] = ns[j] =
+ * 2^j and every handle = powers_of_s_g1 it is UnivariateKzg::batch_commit_and_write over Zeromorph's quotients
+ * (zeromorph.rs:150, univariate/kzg.rs:24-30) with no scalar crossing PCIe.  Results in out_affine64_list[j*64 ..]. */
+int plonkish_cuda_msm_bn254_g1_many_resident(uint64_t scalars_handle, const size_t *offsets, const uint64_t *bases_handles, const size_t *ns,
+                                             size_t count, void *out_affine64_list);
+/* q_hat of Zeromorph::open (zeromorph.rs:157-168) from the packed quotients: q_hat[2^n - 2^i + j] += weights[i] * q_i[j]
+ * with weights[i] = y^i (num_vars Montgomery Fr).  A new resident vector of 2^num_vars coefficients. */
+int plonkish_cuda_zeromorph_q_hat_bn254(uint64_t q_handle, const void *weights_mont32, size_t num_vars, uint64_t *out_handle);
+/* f of Zeromorph::open (zeromorph.rs:175-180): f = z * poly + q_hat, f[0] += c0 (= eval_scalar * eval), f[j] +=
+ * q_scalars[i] * q_i[j] for j < 2^i; poly's evaluations are read as coefficients.  A new resident vector, which
+ * UnivariateKzg::open (fr_div_linear + msm_bn254_g1_resident against open_pp) opens at x (zeromorph.rs:185). */
+int plonkish_cuda_zeromorph_f_bn254(uint64_t poly_handle, uint64_t q_hat_handle, uint64_t q_handle, const void *z_mont32, const void *c0_mont32,
+                                    const void *q_scalars_mont32, size_t num_vars, uint64_t *out_handle);
 /* permutation_z_polys (backend/hyperplonk/prover.rs:252-345), the producer of the polynomials HyperPlonk commits at
  * backend/hyperplonk.rs:251-252: per chunk of permutation polynomials the row-wise product of
  * (beta * id + gamma + value) / (beta * sigma + gamma + value), then the running product over the rows in

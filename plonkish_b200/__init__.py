@@ -12,6 +12,10 @@ from .msm import (  # noqa: F401
     variable_base_msm_batch_keep,
     fr_linear_combination,
     fr_div_linear,
+    fr_quotients,
+    variable_base_msm_many_resident,
+    zeromorph_q_hat,
+    zeromorph_f,
     fr_affine_table,
     fr_evaluate,
     fr_expression_table,

@@ -46,6 +46,10 @@ EXPORTS = (
     "plonkish_cuda_msm_bn254_g1_batch_keep",
     "plonkish_cuda_fr_linear_combination",
     "plonkish_cuda_fr_div_linear",
+    "plonkish_cuda_fr_quotients",
+    "plonkish_cuda_msm_bn254_g1_many_resident",
+    "plonkish_cuda_zeromorph_q_hat_bn254",
+    "plonkish_cuda_zeromorph_f_bn254",
     "plonkish_cuda_permutation_z_polys_bn254",
     "plonkish_cuda_fr_affine_table",
     "plonkish_cuda_fr_evaluate",
@@ -155,6 +159,10 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_fr_linear_combination.argtypes = [vp, vp, sz, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_permutation_z_polys_bn254.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     lib.plonkish_cuda_fr_div_linear.argtypes = [u64, vp, ctypes.POINTER(u64), vp]
+    lib.plonkish_cuda_fr_quotients.argtypes = [u64, vp, sz, ctypes.POINTER(u64), vp]
+    lib.plonkish_cuda_msm_bn254_g1_many_resident.argtypes = [u64, vp, vp, vp, sz, vp]
+    lib.plonkish_cuda_zeromorph_q_hat_bn254.argtypes = [u64, vp, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_zeromorph_f_bn254.argtypes = [u64, u64, u64, vp, vp, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_fr_affine_table.argtypes = [ci, sz, vp, vp, vp, sz, vp, vp, vp, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_fr_evaluate.argtypes = [u64, vp, sz, sz, vp]
     lib.plonkish_cuda_fr_expression_table.argtypes = [vp, sz, sz, vp, vp, vp, sz, ci, ctypes.POINTER(u64)]

@@ -2781,6 +2781,147 @@ extern "C" int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *
     return PLONKISH_CUDA_OK;
 }
 
+// `quotients` (pcs/multilinear.rs:72-107) on a resident polynomial, kept: the packed quotient buffer (q_i, 2^i values, at
+// element offset 2^i; element 0 is zero) comes back as a resident vector of 2^num_vars scalars and f(point) as one
+// Montgomery Fr.  What Zeromorph::open (pcs/multilinear/zeromorph.rs:149-150) starts from: it commits the quotients
+// (many_resident below) and reads them again for q_hat and f.
+extern "C" int plonkish_cuda_fr_quotients(uint64_t scalars_handle, const void *point, size_t num_vars, uint64_t *out_q_handle, void *out_eval_mont32) {
+    if (!out_q_handle || !out_eval_mont32 || (num_vars && !point)) return fail(PLONKISH_CUDA_E_INVALID, "fr_quotients: null argument");
+    if (num_vars > PK_ZM_MAX_VARS) return fail(PLONKISH_CUDA_E_INVALID, "fr_quotients: num_vars = %zu exceeds %d", num_vars, PK_ZM_MAX_VARS);
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "fr_quotients: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    const size_t n = (size_t)1 << num_vars;
+    if (se.n != n) return fail(PLONKISH_CUDA_E_INVALID, "fr_quotients: polynomial holds %zu evaluations, point has %zu variables", se.n, num_vars);  // multilinear.rs:77
+    Ctx *c = ctx_for(se.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_quotients: device %d not initialised", se.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *q = nullptr;
+    int rc = pool_alloc(c, &q, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard q_guard{c, q};
+    // two remainder buffers (2^(k-1), 2^(k-2)), point (k), eval (1)
+    const size_t ra = n / 2 + 1, rb = n / 4 + 1;
+    if ((rc = grow(c->open_buf, (ra + rb + num_vars + 2) * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    char *base = (char *)c->open_buf.ptr;
+    void *rem_a = base, *rem_b = base + ra * 32, *d_point = base + (ra + rb) * 32, *d_eval = base + (ra + rb + num_vars + 1) * 32;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    if (num_vars) CUDA_TRY(cudaMemcpyAsync(d_point, point, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(q, 0, PLONKISH_CUDA_SCALAR_BYTES, c->stream));
+    pk_enqueue_quotients(se.d_ptr, (u32)num_vars, d_point, q, rem_a, rem_b, d_eval, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, d_eval, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out_eval_mont32, c->h_out, PLONKISH_CUDA_SCALAR_BYTES);
+    *out_q_handle = publish_scalars(c->dev, q_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
+// `count` independent MSMs whose scalars are the sub-ranges [offsets[j], offsets[j] + ns[j]) of ONE resident vector, MSM j
+// against the first ns[j] bases of bases_handles[j]: UnivariateKzg::batch_commit_and_write over Zeromorph's quotients
+// (zeromorph.rs:150: q_i against powers_of_s_g1[..2^i], every handle the same registered slice) without a scalar crossing
+// PCIe; scheduling as in msm_bn254_g1_many (large ones in turn, small ones on the side lanes, one host wait).
+extern "C" int plonkish_cuda_msm_bn254_g1_many_resident(uint64_t scalars_handle, const size_t *offsets, const uint64_t *bases_handles, const size_t *ns,
+                                                        size_t count, void *out_affine64_list) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (count == 0) return PLONKISH_CUDA_OK;
+    if (!offsets || !bases_handles || !ns || !out_affine64_list) return fail(PLONKISH_CUDA_E_INVALID, "msm_many_resident: null argument");
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "msm_many_resident: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    std::vector<ManyJob> jobs(count);
+    bool any = false;
+    for (size_t j = 0; j < count; ++j) {
+        if (ns[j] == 0) continue;
+        if (offsets[j] > se.n || ns[j] > se.n - offsets[j])
+            return fail(PLONKISH_CUDA_E_INVALID, "msm_many_resident: MSM %zu reads [%zu, %zu) of %zu resident scalars", j, offsets[j], offsets[j] + ns[j], se.n);
+        if (!bases_handles[j]) return fail(PLONKISH_CUDA_E_INVALID, "msm_many_resident: MSM %zu lacks a bases handle", j);
+        int dev_j = 0;
+        int rc = view_of(bases_handles[j], ns[j], -1, jobs[j].view, &dev_j, "msm_many_resident");
+        if (rc) return rc;
+        if (dev_j != se.dev) return fail(PLONKISH_CUDA_E_INVALID, "msm_many_resident: bases of MSM %zu live on device %d, the scalars on %d", j, dev_j, se.dev);
+        jobs[j].scalars = (const char *)se.d_ptr + offsets[j] * PLONKISH_CUDA_SCALAR_BYTES;
+        jobs[j].on_device = true;
+        jobs[j].n = ns[j];
+        any = true;
+    }
+    if (!any) { memset(out_affine64_list, 0, count * PLONKISH_CUDA_AFFINE_BYTES); return PLONKISH_CUDA_OK; }
+    Ctx *c = ctx_for(se.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "msm_many_resident: device %d not initialised", se.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc = grow(c->batch_out, count * PLONKISH_CUDA_AFFINE_BYTES);
+    if (rc) return rc;
+    if ((rc = enqueue_many(c, jobs, c->batch_out.ptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_affine64_list, c->batch_out.ptr, count * PLONKISH_CUDA_AFFINE_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = mark_done(c, c->stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    timer_report_shared(std::vector<size_t>(ns, ns + count), t0);
+    return PLONKISH_CUDA_OK;
+}
+
+// Zeromorph's q_hat (zeromorph.rs:157-168) from the packed quotients of fr_quotients: q_hat[2^n - 2^i + j] += weights[i] *
+// q_i[j] (weights[i] = y^i, num_vars Montgomery Fr); a new resident vector of 2^num_vars coefficients.
+extern "C" int plonkish_cuda_zeromorph_q_hat_bn254(uint64_t q_handle, const void *weights_mont32, size_t num_vars, uint64_t *out_handle) {
+    if (!out_handle || (num_vars && !weights_mont32)) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_q_hat: null argument");
+    if (num_vars > PK_ZM_MAX_VARS) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_q_hat: num_vars = %zu exceeds %d", num_vars, PK_ZM_MAX_VARS);
+    ScalarsEntry qe;
+    if (!lookup_scalars(q_handle, qe)) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_q_hat: unknown scalars handle %llu", (unsigned long long)q_handle);
+    const size_t n = (size_t)1 << num_vars;
+    if (qe.n != n) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_q_hat: the quotient buffer holds %zu scalars, expected 2^%zu", qe.n, num_vars);
+    Ctx *c = ctx_for(qe.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "zeromorph_q_hat: device %d not initialised", qe.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard d_guard{c, d};
+    ZmWeights w;
+    memset(&w, 0, sizeof(w));
+    if (num_vars) memcpy(w.w, weights_mont32, num_vars * PLONKISH_CUDA_SCALAR_BYTES);
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    pk_enqueue_zm_q_hat(qe.d_ptr, w, (u32)num_vars, d, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
+// Zeromorph's f (zeromorph.rs:175-180): f = z * poly + q_hat, f[0] += c0 (= eval_scalar * eval), f[j] += q_scalars[i] *
+// q_i[j] for j < 2^i; poly = the 2^num_vars evaluations read as coefficients (:175).  A new resident vector, which
+// UnivariateKzg::open (fr_div_linear + msm_resident against open_pp) then opens at x.
+extern "C" int plonkish_cuda_zeromorph_f_bn254(uint64_t poly_handle, uint64_t q_hat_handle, uint64_t q_handle, const void *z_mont32, const void *c0_mont32,
+                                               const void *q_scalars_mont32, size_t num_vars, uint64_t *out_handle) {
+    if (!out_handle || !z_mont32 || !c0_mont32 || (num_vars && !q_scalars_mont32)) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_f: null argument");
+    if (num_vars > PK_ZM_MAX_VARS) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_f: num_vars = %zu exceeds %d", num_vars, PK_ZM_MAX_VARS);
+    ScalarsEntry pe, he, qe;
+    if (!lookup_scalars(poly_handle, pe) || !lookup_scalars(q_hat_handle, he) || !lookup_scalars(q_handle, qe))
+        return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_f: unknown scalars handle");
+    const size_t n = (size_t)1 << num_vars;
+    if (pe.n != n || he.n != n || qe.n != n) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_f: poly / q_hat / quotients hold %zu / %zu / %zu scalars, expected 2^%zu", pe.n, he.n, qe.n, num_vars);
+    if (he.dev != pe.dev || qe.dev != pe.dev) return fail(PLONKISH_CUDA_E_INVALID, "zeromorph_f: polynomials live on different devices");
+    Ctx *c = ctx_for(pe.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "zeromorph_f: device %d not initialised", pe.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard d_guard{c, d};
+    ZmWeights w;
+    memset(&w, 0, sizeof(w));
+    if (num_vars) memcpy(w.w, q_scalars_mont32, num_vars * PLONKISH_CUDA_SCALAR_BYTES);
+    fe z, c0;
+    memcpy(z.l, z_mont32, PLONKISH_CUDA_SCALAR_BYTES);
+    memcpy(c0.l, c0_mont32, PLONKISH_CUDA_SCALAR_BYTES);
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    pk_enqueue_zm_f(pe.d_ptr, he.d_ptr, qe.d_ptr, w, z, c0, (u32)num_vars, d, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
 // permutation_z_polys (backend/hyperplonk/prover.rs:252-345): the grand-product polynomials HyperPlonk commits at
 // backend/hyperplonk.rs:251-252, from resident witness columns and permutation polynomials.  value_handles[i] /
 // sigma_handles[i]: the column polys[*poly] and its permutation polynomial for i < count (in the order of

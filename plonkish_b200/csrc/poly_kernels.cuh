@@ -628,4 +628,55 @@ inline void pk_enqueue_fixed_base(const void *d_scalars, u32 n, const affine *ta
     PK_LAUNCH(k_table_normalize, dim3(((n + 7) / 8 + 127) / 128), dim3(128), 0, stream, (const xyzz *)tmp, n, out_affine);
 }
 
+// ------------------------------------------------------------------ Zeromorph
+// Zeromorph<UnivariateKzg>::open (pcs/multilinear/zeromorph.rs:126-186) builds two univariate polynomials of 2^n
+// coefficients out of the quotients of `quotients` (pcs/multilinear.rs:72-107, q_i of 2^i values packed at element
+// offset 2^i of `q`, as pk_enqueue_quotients leaves them).  Both are one pass over 2^n elements with 2^n products in
+// total (element m of either sum has as many terms as there are quotients long enough to reach it): HBM bound.
+#define PK_ZM_MAX_VARS 28
+struct ZmWeights {
+    fe w[PK_ZM_MAX_VARS];
+};
+// q_hat (zeromorph.rs:157-167): q_hat[2^n - 2^i + j] += y^i * q_i[j] for j < 2^i, every quotient aligned to the top.
+// With d = 2^n - m:  q_hat[m] = sum_{i < n, 2^i >= d} w[i] * q[2^(i+1) - d],  w[i] = y^i.
+__global__ void __launch_bounds__(256) k_zm_q_hat(const uint4 *__restrict__ q, ZmWeights a, u32 num_vars, uint4 *__restrict__ out) {
+    const size_t n = (size_t)1 << num_vars;
+    for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x) {
+        const size_t d = n - m;
+        u32 i0 = 0;
+        while (((size_t)1 << i0) < d) ++i0;
+        fe acc = fe_zero();
+        for (u32 i = i0; i < num_vars; ++i) acc = fr_add(acc, fr_mul(a.w[i], load_fe_plain(q + 2 * (((size_t)2 << i) - d))));
+        store_fe(out + 2 * m, acc);
+    }
+}
+// f (zeromorph.rs:175-180): f = z * poly + q_hat; f[0] += c0 (= eval_scalar * eval); f[j] += s_i * q_i[j] for j < 2^i,
+// every quotient aligned to the bottom:  f[m] = z poly[m] + q_hat[m] + sum_{i < n, 2^i > m} w[i] * q[2^i + m],  w[i] = s_i.
+__global__ void __launch_bounds__(256) k_zm_f(const uint4 *__restrict__ poly, const uint4 *__restrict__ q_hat, const uint4 *__restrict__ q,
+                                              ZmWeights a, fe z, fe c0, u32 num_vars, uint4 *__restrict__ out) {
+    const size_t n = (size_t)1 << num_vars;
+    for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x) {
+        fe acc = fr_add(fr_mul(z, load_fe(poly + 2 * m)), load_fe_plain(q_hat + 2 * m));
+        if (m == 0) acc = fr_add(acc, c0);
+        u32 i0 = 0;
+        while (((size_t)1 << i0) <= m) ++i0;
+        for (u32 i = i0; i < num_vars; ++i) acc = fr_add(acc, fr_mul(a.w[i], load_fe_plain(q + 2 * (((size_t)1 << i) + m))));
+        store_fe(out + 2 * m, acc);
+    }
+}
+inline u32 pk_zm_blocks(u32 num_vars, u32 sm_count) {
+    const size_t n = (size_t)1 << num_vars;
+    size_t blocks = (n + 255) / 256;
+    const size_t cap = (size_t)sm_count * 8;
+    return (u32)(blocks > cap ? cap : blocks);
+}
+inline void pk_enqueue_zm_q_hat(const void *q, const ZmWeights &w, u32 num_vars, void *out, u32 sm_count, pk_stream_t stream) {
+    PK_LAUNCH(k_zm_q_hat, dim3(pk_zm_blocks(num_vars, sm_count)), dim3(256), 0, stream, (const uint4 *)q, w, num_vars, (uint4 *)out);
+}
+inline void pk_enqueue_zm_f(const void *poly, const void *q_hat, const void *q, const ZmWeights &w, const fe &z, const fe &c0, u32 num_vars,
+                            void *out, u32 sm_count, pk_stream_t stream) {
+    PK_LAUNCH(k_zm_f, dim3(pk_zm_blocks(num_vars, sm_count)), dim3(256), 0, stream, (const uint4 *)poly, (const uint4 *)q_hat, (const uint4 *)q, w, z,
+              c0, num_vars, (uint4 *)out);
+}
+
 }  // namespace pk

@@ -175,11 +175,13 @@ def eq_xy_eval(x: Sequence[int], y: Sequence[int]) -> int:
 
 
 def batch_open(pp: MultilinearKzgProverParam, num_vars: int, polys: Sequence[ResidentScalars], points: Sequence[Sequence[int]],
-               evals: Sequence[Tuple[int, int, int]], transcript) -> None:
+               evals: Sequence[Tuple[int, int, int]], transcript, open_fn=None) -> None:
     """`additive::batch_open` (pcs/multilinear.rs:134-235), what MultilinearKzg::batch_open runs (kzg.rs:304-313), the
     non-sanity-check path.  polys: resident polynomials of 2^num_vars evaluations; points: canonical-integer points;
     evals: (poly index, point index, value) in the caller's order.  Writes the degree-2 sum check's coefficient messages
-    and the quotient commitments of the final opening to the transcript; every polynomial operation runs on the GPU."""
+    and the quotient commitments of the final opening to the transcript; every polynomial operation runs on the GPU.
+    open_fn(g_prime, challenges): another additive PCS's `open` for the last step (Zeromorph, zeromorph.rs:188-204);
+    default MultilinearKzg::open."""
     from . import sumcheck
     from .msm import eq_table
     from .transcript import fr_to_montgomery
@@ -212,7 +214,10 @@ def batch_open(pp: MultilinearKzgProverParam, num_vars: int, polys: Sequence[Res
     # g_prime (multilinear.rs:203-213) and its opening at the sum check's point (:227-234)
     coeffs = [scalar * eq_xy_eval(challenges, pt) % r for (scalar, _), pt in zip(merged, points)]
     g_prime = linear_combination([m for _, m in merged], np.stack([fr_to_montgomery(c) for c in coeffs]))
-    open_to_transcript(pp, g_prime, np.stack([fr_to_montgomery(c) for c in challenges]), transcript)
+    if open_fn is None:
+        open_to_transcript(pp, g_prime, np.stack([fr_to_montgomery(c) for c in challenges]), transcript)
+    else:
+        open_fn(g_prime, challenges)
     for x in owned + eqs + [g_prime]:
         x.release()
 

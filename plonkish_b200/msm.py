@@ -388,6 +388,64 @@ def fr_div_linear(poly: "ResidentScalars", z):
     return ResidentScalars._adopt(out.value, poly.n, poly.device), rem
 
 
+def fr_quotients(poly: "ResidentScalars", point):
+    """`quotients` (pcs/multilinear.rs:72-107) on a resident polynomial, kept in HBM: returns (packed quotients as
+    ResidentScalars of 2^k scalars — quotient i, 2^i values, at element offset 2^i, element 0 zero —, f(point) as
+    Montgomery limbs [4]).  point: [k, 4] Montgomery Fr."""
+    pt = _as_u64(point, 4, "point") if len(point) else np.zeros((0, 4), dtype=np.uint64)
+    k = pt.shape[0]
+    assert poly.n == 1 << k, "point / polynomial size mismatch"  # multilinear.rs:77
+    out = ctypes.c_uint64(0)
+    value = np.zeros(4, dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_fr_quotients(poly.handle, pt.ctypes.data if k else None, k, ctypes.byref(out), value.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_fr_quotients")
+    return ResidentScalars._adopt(out.value, poly.n, poly.device), value
+
+
+def variable_base_msm_many_resident(scalars: "ResidentScalars", offsets: Sequence[int], bases_list: Sequence["G1Bases"], ns: Sequence[int]) -> np.ndarray:
+    """len(ns) independent MSMs over sub-ranges of one resident vector: MSM j = scalars[offsets[j] : offsets[j] + ns[j]]
+    against the first ns[j] bases of bases_list[j] (UnivariateKzg::batch_commit_and_write over resident quotients,
+    pcs/multilinear/zeromorph.rs:150).  Returns [count, 8] affine points."""
+    count = len(ns)
+    assert len(offsets) == count and len(bases_list) == count
+    out = np.zeros((count, 8), dtype=np.uint64)
+    if count == 0:
+        return out
+    offs = (ctypes.c_size_t * count)(*[int(o) for o in offsets])
+    nn = (ctypes.c_size_t * count)(*[int(n) for n in ns])
+    hs = np.array([b.handle for b in bases_list], dtype=np.uint64)
+    rc = _lib.lib().plonkish_cuda_msm_bn254_g1_many_resident(scalars.handle, ctypes.cast(offs, ctypes.c_void_p), hs.ctypes.data,
+                                                             ctypes.cast(nn, ctypes.c_void_p), count, out.ctypes.data)
+    _lib.check(rc, "plonkish_cuda_msm_bn254_g1_many_resident")
+    return out
+
+
+def zeromorph_q_hat(q: "ResidentScalars", weights) -> "ResidentScalars":
+    """q_hat of Zeromorph::open (pcs/multilinear/zeromorph.rs:157-168) from the packed quotients of fr_quotients:
+    q_hat[2^n - 2^i + j] += weights[i] * q_i[j]; weights: [n, 4] Montgomery Fr (the powers of y)."""
+    w = _as_u64(weights, 4, "weights") if len(weights) else np.zeros((0, 4), dtype=np.uint64)
+    k = w.shape[0]
+    assert q.n == 1 << k, "weights / quotient buffer size mismatch"
+    out = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_zeromorph_q_hat_bn254(q.handle, w.ctypes.data if k else None, k, ctypes.byref(out)), "plonkish_cuda_zeromorph_q_hat_bn254")
+    return ResidentScalars._adopt(out.value, q.n, q.device)
+
+
+def zeromorph_f(poly: "ResidentScalars", q_hat: "ResidentScalars", q: "ResidentScalars", z, c0, q_scalars) -> "ResidentScalars":
+    """f of Zeromorph::open (zeromorph.rs:175-180): z * poly + q_hat, f[0] += c0, f[j] += q_scalars[i] * q_i[j] (j < 2^i).
+    z, c0: Montgomery limbs [4]; q_scalars: [n, 4]."""
+    w = _as_u64(q_scalars, 4, "q_scalars") if len(q_scalars) else np.zeros((0, 4), dtype=np.uint64)
+    k = w.shape[0]
+    assert poly.n == 1 << k and q_hat.n == poly.n and q.n == poly.n, "polynomial / quotient sizes mismatch"
+    zz = np.ascontiguousarray(z, dtype=np.uint64).reshape(4)
+    cc = np.ascontiguousarray(c0, dtype=np.uint64).reshape(4)
+    out = ctypes.c_uint64(0)
+    rc = _lib.lib().plonkish_cuda_zeromorph_f_bn254(poly.handle, q_hat.handle, q.handle, zz.ctypes.data, cc.ctypes.data, w.ctypes.data if k else None, k,
+                                                    ctypes.byref(out))
+    _lib.check(rc, "plonkish_cuda_zeromorph_f_bn254")
+    return ResidentScalars._adopt(out.value, poly.n, poly.device)
+
+
 def eq_table(y, device: int = 0) -> "ResidentScalars":
     """eq(x, y) over the boolean hypercube as a resident polynomial (MultilinearPolynomial::eq_xy, the zero-check factor
     of piop/sum_check/classic.rs:57-61).  y: [k, 4] Montgomery Fr."""

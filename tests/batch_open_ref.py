@@ -30,8 +30,9 @@ def fix_var(table, x):
     return [(table[2 * b] + (table[2 * b + 1] - table[2 * b]) * x) % R for b in range(len(table) // 2)]
 
 
-def batch_open_reference(oracle, eqs_host, num_vars, polys, points, evals, transcript):
-    """polys: lists of canonical integers (2^num_vars each); eqs_host[i]: the SRS slice of 2^i bases ([2^i, 8] limbs)."""
+def batch_open_reference(oracle, eqs_host, num_vars, polys, points, evals, transcript, open_fn=None):
+    """polys: lists of canonical integers (2^num_vars each); eqs_host[i]: the SRS slice of 2^i bases ([2^i, 8] limbs).
+    open_fn(g_prime, challenges, transcript): another PCS's open for the last step (Zeromorph); default MultilinearKzg::open."""
     ell = max(len(evals) - 1, 0).bit_length()
     t = transcript.squeeze_challenges(ell)
     eq_xt = eq_table(t)
@@ -70,6 +71,8 @@ def batch_open_reference(oracle, eqs_host, num_vars, polys, points, evals, trans
             e = e * ((a * b + (1 - a) * (1 - b)) % R) % R
         w = scalar * e % R
         g_prime = [(g + w * v) % R for g, v in zip(g_prime, m)]
+    if open_fn is not None:
+        return challenges, open_fn(g_prime, challenges, transcript)
     # MultilinearKzg::open (kzg.rs:276-302): quotients (multilinear.rs:72-107) and their commitments
     rem = g_prime
     comms = []

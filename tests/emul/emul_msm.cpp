@@ -260,6 +260,22 @@ void emul_quotients(const void *poly, u32 k, const void *point, void *q_out, voi
     std::vector<fe> ra(n / 2 + 1), rb(n / 4 + 1);
     pk_enqueue_quotients(poly, k, point, q_out, ra.data(), rb.data(), eval_out, 4, 0);
 }
+// Zeromorph's q_hat and f from the packed quotients (weights: num_vars x 32 B)
+void emul_zm_q_hat(const void *q, const void *weights, u32 num_vars, void *out) {
+    ZmWeights w;
+    memset(&w, 0, sizeof(w));
+    memcpy(w.w, weights, (size_t)num_vars * 32);
+    pk_enqueue_zm_q_hat(q, w, num_vars, out, 1, 0);
+}
+void emul_zm_f(const void *poly, const void *q_hat, const void *q, const void *weights, const void *z, const void *c0, u32 num_vars, void *out) {
+    ZmWeights w;
+    memset(&w, 0, sizeof(w));
+    memcpy(w.w, weights, (size_t)num_vars * 32);
+    fe zz, cc;
+    memcpy(zz.l, z, 32);
+    memcpy(cc.l, c0, 32);
+    pk_enqueue_zm_f(poly, q_hat, q, w, zz, cc, num_vars, out, 1, 0);
+}
 void emul_fr_lincomb(const void *const *polys, const void *coeffs, u32 count, u32 n, void *out) {
     for (u32 done = 0; done < count; done += PK_LINCOMB_MAX) {
         LincombArgs a;
