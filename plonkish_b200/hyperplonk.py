@@ -164,10 +164,19 @@ def canonical_u64_to_resident(values: np.ndarray, device: int = 0) -> ResidentSc
 
 
 # ------------------------------------------------------------------------------------ hyperplonk.rs
+def _pcs_of(pcs_pp):
+    """The PolynomialCommitmentScheme a prover parameter belongs to (HyperPlonk<Pcs>, hyperplonk.rs:76-95; pcs.rs:22-130):
+    MultilinearKzg (kzg.py) or Zeromorph<UnivariateKzg> (zeromorph.py) — the two the reference's tests instantiate over
+    Bn256's G1 besides Gemini (hyperplonk.rs:424-426).  Both modules expose commit / batch_commit(keep=True) / batch_open."""
+    from . import zeromorph
+
+    return zeromorph if isinstance(pcs_pp, zeromorph.ZeromorphKzgProverParam) else kzg
+
+
 @dataclass
 class HyperPlonkProverParam:
     """backend/hyperplonk.rs:38-57; polynomials resident in HBM."""
-    pcs: kzg.MultilinearKzgProverParam
+    pcs: object  # kzg.MultilinearKzgProverParam or zeromorph.ZeromorphKzgProverParam
     num_instances: List[int]
     num_witness_polys: List[int]
     num_challenges: List[int]
@@ -199,19 +208,20 @@ class HyperPlonkVerifierParam:
     permutation_comms: List[Tuple[int, np.ndarray]]
 
 
-def preprocess(pcs_pp: kzg.MultilinearKzgProverParam, info: PlonkishCircuitInfo, permutation_columns: Optional[Sequence[np.ndarray]] = None,
+def preprocess(pcs_pp, info: PlonkishCircuitInfo, permutation_columns: Optional[Sequence[np.ndarray]] = None,
                device: int = 0) -> Tuple[HyperPlonkProverParam, HyperPlonkVerifierParam]:
     """HyperPlonk::preprocess (hyperplonk.rs:97-162): commit the preprocessed and the permutation polynomials, compose the
     expression.  permutation_columns: the permutation polynomials as canonical uint64 columns when the caller already has
     them (a 2^24-row circuit builds them vectorised); default = permutation_polys_canonical over info.permutations."""
     num_vars = info.k
     preprocess_polys = [p if isinstance(p, ResidentScalars) else ResidentScalars(p, device=device) for p in info.preprocess_polys]
-    preprocess_comms = [kzg.commit(pcs_pp, p) for p in preprocess_polys]
+    pcs = _pcs_of(pcs_pp)
+    preprocess_comms = [pcs.commit(pcs_pp, p) for p in preprocess_polys]
     perm_idx = info.permutation_polys()
     cols = permutation_columns if permutation_columns is not None else permutation_polys_canonical(num_vars, perm_idx, info.permutations)
     assert len(cols) == len(perm_idx)
     permutation_polys = [canonical_u64_to_resident(np.ascontiguousarray(c, dtype=np.uint64), device) for c in cols]
-    permutation_comms = [kzg.commit(pcs_pp, p) for p in permutation_polys]
+    permutation_comms = [pcs.commit(pcs_pp, p) for p in permutation_polys]
     num_z, expression = compose(info)
     vp = HyperPlonkVerifierParam(list(info.num_instances), list(info.num_witness_polys), list(info.num_challenges), len(info.lookups), num_z,
                                  num_vars, expression, preprocess_comms, list(zip(perm_idx, permutation_comms)))
@@ -423,6 +433,7 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
             marks.append((label, time.perf_counter()))
 
     mark("start")
+    pcs = _pcs_of(pp.pcs)
     instances = circuit.instances()
     assert len(instances) == len(pp.num_instances)
     for num, column in zip(pp.num_instances, instances):
@@ -439,7 +450,7 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
         for rnd, (num_w, num_c) in enumerate(zip(pp.num_witness_polys, pp.num_challenges)):
             host = circuit.synthesize(rnd, challenges)
             assert len(host) == num_w
-            comms, resident = kzg.batch_commit(pp.pcs, host, keep=True)          # Pcs::batch_commit_and_write
+            comms, resident = pcs.batch_commit(pp.pcs, host, keep=True)          # Pcs::batch_commit_and_write
             owned.extend(resident)
             transcript.write_commitments(comms)
             witness_polys.extend(resident)
@@ -454,7 +465,7 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
         owned.extend(p for pair in compressed for p in pair)
         lookup_m_polys = [lookup_m_poly(inp, tab) for inp, tab in compressed]        # Err(InvalidSnark) -> PlonkishCudaError
         owned.extend(lookup_m_polys)
-        transcript.write_commitments([kzg.commit(pp.pcs, m) for m in lookup_m_polys])
+        transcript.write_commitments([pcs.commit(pp.pcs, m) for m in lookup_m_polys])
         mark("lookup m polys + commit")
         # Round n+1 (hyperplonk.rs:231-252)
         gamma = transcript.squeeze_challenge()
@@ -466,7 +477,7 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
                                           [p for _, p in pp.permutation_polys], fr_to_montgomery(beta), fr_to_montgomery(gamma))
             owned.extend(z_polys)
         mark("lookup h polys + permutation_z_polys")
-        transcript.write_commitments([kzg.commit(pp.pcs, p) for p in lookup_h_polys + z_polys])
+        transcript.write_commitments([pcs.commit(pp.pcs, p) for p in lookup_h_polys + z_polys])
         mark("h / z commit")
         # Round n+2 (hyperplonk.rs:256-273)
         alpha = transcript.squeeze_challenge()
@@ -476,7 +487,7 @@ def prove(pp: HyperPlonkProverParam, circuit, transcript, marks: Optional[list] 
         pts, evals = prove_sum_check(len(pp.num_instances), pp.expression, 0, polys, challenges, y, transcript)   # prove_zero_check
         mark("zero check + evals")
         # PCS open (hyperplonk.rs:277-288)
-        kzg.batch_open(pp.pcs, pp.num_vars, polys, pts, evals, transcript)
+        pcs.batch_open(pp.pcs, pp.num_vars, polys, pts, evals, transcript)
         mark("pcs_batch_open")
     finally:
         for p in owned:

@@ -88,8 +88,19 @@ def commit(pp: ZeromorphKzgProverParam, poly, ops=GpuOps) -> np.ndarray:
     return ops.commit(pp.commit_pp, poly)
 
 
-def batch_commit(pp: ZeromorphKzgProverParam, polys: Sequence, ops=GpuOps) -> List[np.ndarray]:
-    """zeromorph.rs:116-124: one commit per polynomial, in order."""
+def batch_commit(pp: ZeromorphKzgProverParam, polys: Sequence, keep: bool = False, ops=GpuOps):
+    """zeromorph.rs:116-124: one commit per polynomial, in order.  keep=True (host polynomials of one size): the pipelined
+    batch entry, which also leaves every polynomial resident — returns (commitments, [ResidentScalars])."""
+    polys = list(polys)
+    if keep:
+        from .msm import variable_base_msm_batch_keep
+
+        if not polys:
+            return [], []
+        if pp.degree() + 1 < len(polys[0]):
+            raise ValueError(f"Too large degree of poly to commit (param supports degree up to {pp.degree()} but got {len(polys[0])})")
+        comms, resident = variable_base_msm_batch_keep(polys, pp.commit_pp)
+        return list(comms), resident
     return [commit(pp, poly, ops) for poly in polys]
 
 

@@ -243,9 +243,10 @@ def eq_xy_eval(x, y):
     return out
 
 
-def verify_reference(keccak256, ss, k, instances, preprocess_comms, permutation_comms, proof: bytes) -> None:
+def verify_reference(keccak256, ss, k, instances, preprocess_comms, permutation_comms, proof: bytes, pcs_verify=None) -> None:
     """hyperplonk.rs:293-362; raises AssertionError where the reference returns Err.  Commitments are affine integer
-    pairs; ss: the setup's trapdoor (canonical integers)."""
+    pairs; ss: the setup's trapdoor (canonical integers).  pcs_verify(reader, g_prime_comm, point, g_prime_eval): another
+    additive PCS's verify for the last step (Zeromorph: zeromorph_ref.verify_reader_in_g1); default MultilinearKzg::verify."""
     t = ProofReader(keccak256, proof)
     order = bh_prefix(k, max(len(instances), 1) + 1)
     for v in instances:
@@ -293,6 +294,10 @@ def verify_reference(keccak256, ss, k, instances, preprocess_comms, permutation_
     eq_evals = [eq_xy_eval(ch2, pt) for pt in pts]
     scalars = [eq_evals[pt] * w % R for (_, pt, _), w in zip(evals, eq_xt)]
     g_prime_comm = br.msm(scalars, [comms[p] for p, _, _ in evals])
+    if pcs_verify is not None:
+        pcs_verify(t, g_prime_comm, ch2, g_prime_eval)
+        assert t.pos == len(proof), "trailing bytes in the proof"
+        return
     # MultilinearKzg::verify (kzg.rs:315-362): e(C - v g1, g2) = prod e(Q_i, s_i g2 - x_i g2), here in G1 with the trapdoor
     quotients = t.read_commitments(k)
     lhs = br.add(g_prime_comm, br.neg(br.scalar_mul(g_prime_eval, br.G)))

@@ -224,6 +224,88 @@ def test_lookup_producers_match_python_integers(pk, oracle, k):
         r_.release()
 
 
+def _zeromorph_setup(pk, oracle, k, s):
+    from plonkish_b200 import kzg, zeromorph
+
+    pp = zeromorph.trim(kzg.univariate_setup(oracle.generator(), ref.to_mont(s), 1 << k), 1 << k)
+    return pp, pp.commit_pp.to_host()
+
+
+def _zeromorph_reference(oracle, srs_h, k):
+    import zeromorph_ref as zr
+    from batch_open_ref import batch_open_reference
+
+    commit = lambda f: zr.commit_coeffs(oracle, srs_h, f)  # noqa: E731
+
+    def open_ref(g_prime, challenges, transcript):
+        return zr.open_reference(oracle, srs_h, srs_h, g_prime, challenges, 0, transcript)
+
+    def batch_open(polys, points, evals, transcript):
+        return batch_open_reference(oracle, None, k, polys, points, evals, transcript, open_fn=open_ref)
+
+    return commit, batch_open
+
+
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_zeromorph_proof_bytes_match_the_integer_reference_prover(pk, oracle, k):
+    """HyperPlonk<Zeromorph<UnivariateKzg<Bn256>>> (the reference's zeromorph_kzg tests, backend/hyperplonk.rs:426): the same
+    prover over the other BN254 multilinear PCS — proof bytes identical to the all-integer prover with Zeromorph's commit
+    and open restated in tests/zeromorph_ref.py."""
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    rng = np.random.default_rng(900 + k)
+    pp, srs_h = _zeromorph_setup(pk, oracle, k, 0x5EED5EED5EED1234567)
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_circuit(k, rng)
+    proof, hvp = _prove_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    commit, batch_open = _zeromorph_reference(oracle, srs_h, k)
+    sigmas = ref.permutation_polys(k, [6, 7, 8], cycles)
+    t = Keccak256Transcript()
+    ref.prove_reference(commit, batch_open, k, instances, preprocess, witness, sigmas, t)
+    assert proof == t.into_proof()
+    assert all((c == commit(p)).all() for c, p in zip(hvp.preprocess_comms, preprocess))
+    pp.release()
+
+
+@pytest.mark.parametrize("k", [8, 12])
+def test_zeromorph_gpu_proof_is_accepted_by_the_reference_verifier(pk, oracle, k):
+    # HyperPlonk::verify with Zeromorph::verify (zeromorph.rs:216-245) as the last step, in G1 with the setup's trapdoor
+    import zeromorph_ref as zr
+
+    rng = np.random.default_rng(980 + k)
+    s = 0x1357924680ACE1357924680ACE % br.R
+    pp, _ = _zeromorph_setup(pk, oracle, k, s)
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_circuit(k, rng)
+    proof, hvp = _prove_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    affine = lambda limbs: br.point_from_bytes(np.ascontiguousarray(limbs).tobytes())  # noqa: E731
+    pre = [affine(c) for c in hvp.preprocess_comms]
+    perm = [affine(c) for _, c in hvp.permutation_comms]
+    pcs_verify = lambda reader, comm, point, value: zr.verify_reader_in_g1(reader, comm, point, value, s)  # noqa: E731
+    ref.verify_reference(oracle.keccak256, None, k, instances, pre, perm, proof, pcs_verify=pcs_verify)
+    assert len(proof) == 4 * 64 + k * 6 * 32 + 14 * 32 + k * 3 * 32 + (k + 2) * 64
+    bad = [list(w) for w in witness]
+    bad[2][5] = (bad[2][5] + 1) % br.R
+    bad_proof, _ = _prove_on_gpu(pk, pp, k, instances, preprocess, bad, cycles)
+    with pytest.raises(AssertionError):
+        ref.verify_reference(oracle.keccak256, None, k, instances, pre, perm, bad_proof, pcs_verify=pcs_verify)
+    pp.release()
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_zeromorph_lookup_proof_bytes_match_the_integer_reference_prover(pk, oracle, k):
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    rng = np.random.default_rng(950 + k)
+    pp, srs_h = _zeromorph_setup(pk, oracle, k, 0xABCDEF987654321)
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_with_lookup_circuit(k, rng)
+    proof, _ = _prove_lookup_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    commit, batch_open = _zeromorph_reference(oracle, srs_h, k)
+    sigmas = ref.permutation_polys(k, [10, 11, 12], cycles)
+    t = Keccak256Transcript()
+    ref.prove_reference_lookup(commit, batch_open, k, instances, preprocess, witness, sigmas, t)
+    assert proof == t.into_proof()
+    pp.release()
+
+
 @pytest.mark.parametrize("k", [3, 4, 5])
 def test_lookup_proof_bytes_match_the_integer_reference_prover(pk, oracle, k):
     """HyperPlonk::prove for vanilla_plonk_with_lookup (the reference's second test circuit, backend/hyperplonk.rs:371-427):

@@ -107,3 +107,17 @@ def verify_in_g1(comm, point, eval_, q_comms, q_hat_comm, pi, transcript, s, off
     lhs = br.scalar_mul((s - x) % R, _point(pi))
     rhs = br.scalar_mul(pow(s, offset, R), c) if c is not None else None
     assert lhs == rhs, "the proof does not satisfy Zeromorph's verification equation"
+
+
+def verify_reader_in_g1(reader, comm, point, eval_, s, offset=0):
+    """The same equation over a proof reader (tests/hyperplonk_ref.py ProofReader: read_commitment(s) return affine integer
+    pairs): Zeromorph::verify as the last step of additive::batch_verify inside HyperPlonk::verify.  comm: affine pair."""
+    q_comms = reader.read_commitments(len(point))
+    y = reader.squeeze_challenge()
+    q_hat_comm = reader.read_commitment()
+    x = reader.squeeze_challenge()
+    z = reader.squeeze_challenge()
+    eval_scalar, q_scalars = eval_and_quotient_scalars(y, x, z, point)
+    c = br.msm([1, z, eval_scalar * eval_ % R] + q_scalars, [q_hat_comm, comm, br.G] + list(q_comms))
+    pi = reader.read_commitment()
+    assert br.scalar_mul((s - x) % R, pi) == br.scalar_mul(pow(s, offset, R), c), "Invalid Zeromorph KZG open"
