@@ -32,6 +32,9 @@ extern "C" {
     fn plonkish_cuda_fr_linear_combination(handles: *const u64, coeffs: *const c_void, count: usize, n: usize, out_handle: *mut u64) -> c_int;
     fn plonkish_cuda_fr_div_linear(handle: u64, z: *const c_void, out_quotient: *mut u64, out_rem: *mut c_void) -> c_int;
     fn plonkish_cuda_fr_quotients(handle: u64, point: *const c_void, num_vars: usize, out_q: *mut u64, out_eval: *mut c_void) -> c_int;
+    fn plonkish_cuda_scalars_slice(handle: u64, offset: usize, n: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_fr_linear_combination_padded(handles: *const u64, coeffs: *const c_void, count: usize, n: usize, out_handle: *mut u64) -> c_int;
+    fn plonkish_cuda_fr_gemini_folds(handle: u64, point: *const c_void, num_vars: usize, out_handle: *mut u64) -> c_int;
     fn plonkish_cuda_msm_bn254_g1_many_resident(scalars_handle: u64, offsets: *const usize, bases_handles: *const u64, ns: *const usize, count: usize,
                                                 out: *mut c_void) -> c_int;
     fn plonkish_cuda_zeromorph_q_hat_bn254(q_handle: u64, weights: *const c_void, num_vars: usize, out_handle: *mut u64) -> c_int;
@@ -588,6 +591,61 @@ impl ZeromorphQuotients {
         );
         ResidentCoeffs { handle, len: 1 << self.num_vars }
     }
+}
+
+/// The folds of `Gemini::<UnivariateKzg<Bn256>>::open` (pcs/multilinear/gemini.rs:98-108) kept in HBM: `fs[1..]`, packed.
+pub struct GeminiFolds {
+    handle: u64, // f_i (2^(num_vars - i) coefficients) at element offset 2^(num_vars - i)
+    num_vars: usize,
+}
+impl Drop for GeminiFolds {
+    fn drop(&mut self) {
+        unsafe { plonkish_cuda_scalars_release(self.handle) };
+    }
+}
+impl GeminiFolds {
+    pub fn new(poly: &ResidentPoly, point: &[Fr]) -> Self {
+        assert!(poly.num_vars == point.len() && !point.is_empty());
+        let mut handle = 0u64;
+        check(unsafe { plonkish_cuda_fr_gemini_folds(poly.handle, point.as_ptr() as *const c_void, point.len(), &mut handle) }, "plonkish_cuda_fr_gemini_folds");
+        Self { handle, num_vars: point.len() }
+    }
+    /// `UnivariateKzg::batch_commit(pp, &fs[1..])` (gemini.rs:124-128): f_i against `powers_of_s_g1[..2^(num_vars - i)]`, one call.
+    pub fn commit(&self, powers_of_s_g1: &RegisteredBases) -> Vec<G1Affine> {
+        let sizes: Vec<usize> = (1..self.num_vars).map(|i| 1usize << (self.num_vars - i)).collect();
+        let handles = vec![powers_of_s_g1.handle; sizes.len()];
+        let mut out = vec![G1Affine::default(); sizes.len()];
+        if sizes.is_empty() {
+            return out;
+        }
+        check(
+            unsafe { plonkish_cuda_msm_bn254_g1_many_resident(self.handle, sizes.as_ptr(), handles.as_ptr(), sizes.as_ptr(), sizes.len(), out.as_mut_ptr() as *mut c_void) },
+            "plonkish_cuda_msm_bn254_g1_many_resident",
+        );
+        out
+    }
+    /// `fs[i]` (1 <= i < num_vars) as coefficients of its own for `UnivariateKzg::batch_open` (gemini.rs:140); shares the memory.
+    pub fn fold(&self, i: usize) -> ResidentCoeffs {
+        assert!(i >= 1 && i < self.num_vars);
+        let len = 1usize << (self.num_vars - i);
+        let mut handle = 0u64;
+        check(unsafe { plonkish_cuda_scalars_slice(self.handle, len, len, &mut handle) }, "plonkish_cuda_scalars_slice");
+        ResidentCoeffs { handle, len }
+    }
+}
+
+/// `sum_i coeffs[i] * polys[i]` over coefficient vectors of different lengths (`f += (scalar, q)`, poly/univariate.rs):
+/// the sums of `UnivariateKzg::batch_open` (pcs/univariate/kzg.rs:330, 339-343) over Gemini's folds.
+pub fn linear_combination_padded(polys: &[&ResidentCoeffs], coeffs: &[Fr]) -> ResidentCoeffs {
+    assert!(!polys.is_empty() && polys.len() == coeffs.len());
+    let handles: Vec<u64> = polys.iter().map(|p| p.handle).collect();
+    let len = polys.iter().map(|p| p.len).max().unwrap();
+    let mut handle = 0u64;
+    check(
+        unsafe { plonkish_cuda_fr_linear_combination_padded(handles.as_ptr(), coeffs.as_ptr() as *const c_void, polys.len(), len, &mut handle) },
+        "plonkish_cuda_fr_linear_combination_padded",
+    );
+    ResidentCoeffs { handle, len }
 }
 
 /// `fixed_base_msm(window_size, &window_table(window_size, base), scalars)` followed by

@@ -171,6 +171,20 @@ int plonkish_cuda_fr_quotients(uint64_t scalars_handle, const void *point_mont32
  * (zeromorph.rs:150, univariate/kzg.rs:24-30) with no scalar crossing PCIe.  Results in out_affine64_list[j*64 ..]. */
 int plonkish_cuda_msm_bn254_g1_many_resident(uint64_t scalars_handle, const size_t *offsets, const uint64_t *bases_handles, const size_t *ns,
                                              size_t count, void *out_affine64_list);
+/* A handle on the sub-range [offset, offset + n) of a resident vector: shares the memory (no copy) and keeps it alive
+ * until the slice is released (scalars_release).  One quotient or one fold as a polynomial of its own. */
+int plonkish_cuda_scalars_slice(uint64_t handle, size_t offset, size_t n, uint64_t *out_handle);
+/* fr_linear_combination for univariate polynomials of different lengths (`f += (scalar, q)`, poly/univariate.rs; the sums
+ * of UnivariateKzg::batch_open, pcs/univariate/kzg.rs:330,339-343): a polynomial shorter than n counts as zero past its
+ * last coefficient; the result has n coefficients. */
+int plonkish_cuda_fr_linear_combination_padded(const uint64_t *scalars_handles, const void *coeffs_mont32, size_t count, size_t n,
+                                               uint64_t *out_handle);
+/* ---- Gemini<UnivariateKzg> (pcs/multilinear/gemini.rs) ------------------------------------------------------------
+ * The folds of Gemini::open (gemini.rs:98-108): f_i = merge_into(f_(i-1), point[i-1], 1, 0) (poly/multilinear.rs:599-618)
+ * for i = 1..num_vars-1, packed like the quotients: f_i (2^(num_vars-i) values) at element offset 2^(num_vars-i) of a new
+ * resident vector of 2^num_vars scalars (elements 0 and 1 zero).  They are committed with msm_bn254_g1_many_resident
+ * (gemini.rs:124-128) and opened with UnivariateKzg::batch_open through scalars_slice handles (gemini.rs:140). */
+int plonkish_cuda_fr_gemini_folds(uint64_t scalars_handle, const void *point_mont32, size_t num_vars, uint64_t *out_handle);
 /* q_hat of Zeromorph::open (zeromorph.rs:157-168) from the packed quotients: q_hat[2^n - 2^i + j] += weights[i] * q_i[j]
  * with weights[i] = y^i (num_vars Montgomery Fr).  A new resident vector of 2^num_vars coefficients. */
 int plonkish_cuda_zeromorph_q_hat_bn254(uint64_t q_handle, const void *weights_mont32, size_t num_vars, uint64_t *out_handle);

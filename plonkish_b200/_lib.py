@@ -47,6 +47,9 @@ EXPORTS = (
     "plonkish_cuda_fr_linear_combination",
     "plonkish_cuda_fr_div_linear",
     "plonkish_cuda_fr_quotients",
+    "plonkish_cuda_scalars_slice",
+    "plonkish_cuda_fr_linear_combination_padded",
+    "plonkish_cuda_fr_gemini_folds",
     "plonkish_cuda_msm_bn254_g1_many_resident",
     "plonkish_cuda_zeromorph_q_hat_bn254",
     "plonkish_cuda_zeromorph_f_bn254",
@@ -160,6 +163,9 @@ def load() -> ctypes.CDLL:
     lib.plonkish_cuda_permutation_z_polys_bn254.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     lib.plonkish_cuda_fr_div_linear.argtypes = [u64, vp, ctypes.POINTER(u64), vp]
     lib.plonkish_cuda_fr_quotients.argtypes = [u64, vp, sz, ctypes.POINTER(u64), vp]
+    lib.plonkish_cuda_scalars_slice.argtypes = [u64, sz, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_fr_linear_combination_padded.argtypes = [vp, vp, sz, sz, ctypes.POINTER(u64)]
+    lib.plonkish_cuda_fr_gemini_folds.argtypes = [u64, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_msm_bn254_g1_many_resident.argtypes = [u64, vp, vp, vp, sz, vp]
     lib.plonkish_cuda_zeromorph_q_hat_bn254.argtypes = [u64, vp, sz, ctypes.POINTER(u64)]
     lib.plonkish_cuda_zeromorph_f_bn254.argtypes = [u64, u64, u64, vp, vp, vp, sz, ctypes.POINTER(u64)]

@@ -2657,12 +2657,12 @@ extern "C" int plonkish_cuda_msm_bn254_g1_resident(uint64_t scalars_handle, uint
 }
 
 // g_prime = sum_i coeffs[i] * poly_i over resident polynomials (pcs/multilinear.rs:203-213).
-extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const void *coeffs, size_t count, size_t n, uint64_t *out_handle) {
+static int lincomb_impl(const uint64_t *scalars_handles, const void *coeffs, size_t count, size_t n, uint64_t *out_handle, bool padded) {
     if (!scalars_handles || !coeffs || !out_handle || count == 0 || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: bad argument");
     std::vector<ScalarsEntry> es(count);
     for (size_t i = 0; i < count; ++i) {
         if (!lookup_scalars(scalars_handles[i], es[i])) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: unknown handle %llu", (unsigned long long)scalars_handles[i]);
-        if (es[i].n < n) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: polynomial %zu holds %zu < %zu scalars", i, es[i].n, n);
+        if (!padded && es[i].n < n) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: polynomial %zu holds %zu < %zu scalars", i, es[i].n, n);
         if (es[i].dev != es[0].dev) return fail(PLONKISH_CUDA_E_INVALID, "fr_linear_combination: polynomials live on different devices");
     }
     Ctx *c = ctx_for(es[0].dev);
@@ -2681,6 +2681,7 @@ extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handl
         a.accumulate = done ? 1u : 0u;
         for (u32 i = 0; i < a.count; ++i) {
             a.poly[i] = (const uint4 *)es[done + i].d_ptr;
+            a.len[i] = padded && es[done + i].n < n ? es[done + i].n : n;
             memcpy(a.coeff[i].l, (const char *)coeffs + (done + i) * PLONKISH_CUDA_SCALAR_BYTES, PLONKISH_CUDA_SCALAR_BYTES);
         }
         PK_LAUNCH(k_fr_lincomb, dim3((unsigned)blocks), dim3(256), 0, c->stream, a, n, (uint4 *)d);
@@ -2689,6 +2690,15 @@ extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handl
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out_handle = publish_scalars(c->dev, d_guard.release(), n);
     return PLONKISH_CUDA_OK;
+}
+extern "C" int plonkish_cuda_fr_linear_combination(const uint64_t *scalars_handles, const void *coeffs, size_t count, size_t n, uint64_t *out_handle) {
+    return lincomb_impl(scalars_handles, coeffs, count, n, out_handle, false);
+}
+// Sums of univariate polynomials of different lengths (`f += (scalar, q)`, poly/univariate.rs; the combined quotient and f of
+// UnivariateKzg::batch_open over Gemini's folds, pcs/univariate/kzg.rs:330,339-343): a polynomial shorter than n counts as
+// zero past its last coefficient.
+extern "C" int plonkish_cuda_fr_linear_combination_padded(const uint64_t *scalars_handles, const void *coeffs, size_t count, size_t n, uint64_t *out_handle) {
+    return lincomb_impl(scalars_handles, coeffs, count, n, out_handle, true);
 }
 
 // MultilinearKzg::open on a resident polynomial (kzg.rs:276-302): the quotients of
@@ -2814,6 +2824,55 @@ extern "C" int plonkish_cuda_fr_quotients(uint64_t scalars_handle, const void *p
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(out_eval_mont32, c->h_out, PLONKISH_CUDA_SCALAR_BYTES);
     *out_q_handle = publish_scalars(c->dev, q_guard.release(), n);
+    return PLONKISH_CUDA_OK;
+}
+
+// A handle on the sub-range [offset, offset + n) of a resident vector: shares the memory (no copy) and keeps it alive
+// until the slice itself is released.  One quotient of fr_quotients or one fold of fr_gemini_folds as a polynomial of
+// its own for fr_div_linear / fr_linear_combination(_padded) / msm_bn254_g1_resident.
+extern "C" int plonkish_cuda_scalars_slice(uint64_t handle, size_t offset, size_t n, uint64_t *out_handle) {
+    if (!out_handle || n == 0) return fail(PLONKISH_CUDA_E_INVALID, "scalars_slice: null argument or n == 0");
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_scalars.find(handle);
+    if (it == g_scalars.end()) return fail(PLONKISH_CUDA_E_INVALID, "scalars_slice: unknown scalars handle %llu", (unsigned long long)handle);
+    const ScalarsEntry &src = it->second;
+    if (offset > src.n || n > src.n - offset) return fail(PLONKISH_CUDA_E_INVALID, "scalars_slice: [%zu, %zu) of %zu resident scalars", offset, offset + n, src.n);
+    ScalarsEntry e;
+    e.dev = src.dev; e.n = n; e.d_ptr = (char *)src.d_ptr + offset * PLONKISH_CUDA_SCALAR_BYTES;
+    e.keep = src.keep;
+    const uint64_t h = g_next_handle++;
+    g_scalars[h] = e;
+    *out_handle = h;
+    return PLONKISH_CUDA_OK;
+}
+
+// The folds of Gemini::open (pcs/multilinear/gemini.rs:98-108): f_0 = the polynomial's evaluations read as coefficients,
+// f_i = merge_into(f_(i-1), point[i-1], 1, 0) (poly/multilinear.rs:599-618) for i = 1..num_vars-1, kept in HBM packed
+// like the quotients: f_i (2^(num_vars-i) values) at element offset 2^(num_vars-i) of a resident vector of 2^num_vars
+// scalars (elements 0 and 1 are zero).  point: num_vars Montgomery Fr (the last one is not used, as in the reference).
+extern "C" int plonkish_cuda_fr_gemini_folds(uint64_t scalars_handle, const void *point, size_t num_vars, uint64_t *out_handle) {
+    if (!out_handle || !point) return fail(PLONKISH_CUDA_E_INVALID, "fr_gemini_folds: null argument");
+    if (num_vars == 0 || num_vars > PK_ZM_MAX_VARS) return fail(PLONKISH_CUDA_E_INVALID, "fr_gemini_folds: num_vars = %zu (1..%d supported)", num_vars, PK_ZM_MAX_VARS);
+    ScalarsEntry se;
+    if (!lookup_scalars(scalars_handle, se)) return fail(PLONKISH_CUDA_E_INVALID, "fr_gemini_folds: unknown scalars handle %llu", (unsigned long long)scalars_handle);
+    const size_t n = (size_t)1 << num_vars;
+    if (se.n != n) return fail(PLONKISH_CUDA_E_INVALID, "fr_gemini_folds: polynomial holds %zu evaluations, point has %zu variables", se.n, num_vars);
+    Ctx *c = ctx_for(se.dev);
+    if (!c) return fail(PLONKISH_CUDA_E_NO_DEVICE, "fr_gemini_folds: device %d not initialised", se.dev);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    void *d = nullptr;
+    int rc = pool_alloc(c, &d, n * PLONKISH_CUDA_SCALAR_BYTES);
+    if (rc) return rc;
+    PoolGuard d_guard{c, d};
+    if ((rc = grow(c->tmp, (num_vars + 1) * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
+    if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(c->tmp.ptr, point, num_vars * PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(d, 0, (n < 2 ? n : 2) * PLONKISH_CUDA_SCALAR_BYTES, c->stream));
+    pk_enqueue_gemini_folds(se.d_ptr, (u32)num_vars, c->tmp.ptr, d, (u32)c->sm_count, c->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_handle = publish_scalars(c->dev, d_guard.release(), n);
     return PLONKISH_CUDA_OK;
 }
 

@@ -99,15 +99,44 @@ inline void pk_enqueue_quotients(const void *poly, u32 k, const void *d_point, v
 struct LincombArgs {
     const uint4 *poly[PK_LINCOMB_MAX];
     fe coeff[PK_LINCOMB_MAX];
+    unsigned long long len[PK_LINCOMB_MAX];  // polynomial i holds len[i] values; past them it counts as zero (univariate sums of mixed degrees)
     u32 count;
     u32 accumulate;  // 1: add to what `out` already holds (more than PK_LINCOMB_MAX terms)
 };
-// out[j] (+)= sum_i coeff[i] * poly[i][j]   (multilinear.rs:208-213)
+// out[j] (+)= sum_i coeff[i] * poly[i][j]   (multilinear.rs:208-213; `f += (scalar, q)` of poly/univariate.rs for mixed lengths)
 __global__ void __launch_bounds__(256) k_fr_lincomb(LincombArgs a, size_t n, uint4 *__restrict__ out) {
     for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
         fe acc = a.accumulate ? load_fe_plain(out + 2 * j) : fe_zero();
-        for (u32 i = 0; i < a.count; ++i) acc = fr_add(acc, fr_mul(a.coeff[i], load_fe(a.poly[i] + 2 * j)));
+        for (u32 i = 0; i < a.count; ++i) {
+            if (j < a.len[i]) acc = fr_add(acc, fr_mul(a.coeff[i], load_fe(a.poly[i] + 2 * j)));
+        }
         store_fe(out + 2 * j, acc);
+    }
+}
+
+// ------------------------------------------------------------------ Gemini folds
+// merge_into(.., x_i, 1, 0) (poly/multilinear.rs:599-618) as Gemini::open applies it (pcs/multilinear/gemini.rs:101-108):
+// out[j] = (in[2j + 1] - in[2j]) * x + in[2j] for j < half.
+__global__ void __launch_bounds__(256) k_fr_fold_pairs(const uint4 *__restrict__ in, uint4 *__restrict__ out, const uint4 *__restrict__ x_ptr, size_t half) {
+    const fe x = load_fe_plain(x_ptr);
+    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < half; j += (size_t)gridDim.x * blockDim.x) {
+        const fe e0 = load_fe_plain(in + 4 * j);
+        const fe e1 = load_fe_plain(in + 4 * j + 2);
+        store_fe(out + 2 * j, fr_add(fr_mul(fr_sub(e1, e0), x), e0));
+    }
+}
+// fs[1..num_vars) of Gemini::open, packed like the quotients: f_i (2^(num_vars - i) values) at element offset
+// 2^(num_vars - i) of `out` (2^num_vars scalars; elements 0 and 1 are not written).  point[i - 1] folds f_(i-1) into f_i.
+inline void pk_enqueue_gemini_folds(const void *poly, u32 num_vars, const void *d_point, void *out, u32 sm_count, pk_stream_t stream) {
+    const uint4 *src = (const uint4 *)poly;
+    for (u32 i = 1; i < num_vars; ++i) {
+        const size_t half = (size_t)1 << (num_vars - i);
+        uint4 *dst = (uint4 *)out + 2 * half;
+        size_t blocks = (half + 255) / 256;
+        const size_t cap = (size_t)sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        PK_LAUNCH(k_fr_fold_pairs, dim3((unsigned)blocks), dim3(256), 0, stream, src, dst, (const uint4 *)d_point + 2 * (size_t)(i - 1), half);
+        src = dst;
     }
 }
 

@@ -166,17 +166,20 @@ def canonical_u64_to_resident(values: np.ndarray, device: int = 0) -> ResidentSc
 # ------------------------------------------------------------------------------------ hyperplonk.rs
 def _pcs_of(pcs_pp):
     """The PolynomialCommitmentScheme a prover parameter belongs to (HyperPlonk<Pcs>, hyperplonk.rs:76-95; pcs.rs:22-130):
-    MultilinearKzg (kzg.py) or Zeromorph<UnivariateKzg> (zeromorph.py) — the two the reference's tests instantiate over
-    Bn256's G1 besides Gemini (hyperplonk.rs:424-426).  Both modules expose commit / batch_commit(keep=True) / batch_open."""
-    from . import zeromorph
+    MultilinearKzg (kzg.py), Zeromorph<UnivariateKzg> (zeromorph.py) or Gemini<UnivariateKzg> (gemini.py) — the three the
+    reference's tests instantiate over Bn256 (hyperplonk.rs:424-426).  Each module exposes commit / batch_commit(keep=True) /
+    batch_open."""
+    from . import gemini, zeromorph
 
-    return zeromorph if isinstance(pcs_pp, zeromorph.ZeromorphKzgProverParam) else kzg
+    if isinstance(pcs_pp, zeromorph.ZeromorphKzgProverParam):
+        return zeromorph
+    return gemini if isinstance(pcs_pp, gemini.GeminiKzgProverParam) else kzg
 
 
 @dataclass
 class HyperPlonkProverParam:
     """backend/hyperplonk.rs:38-57; polynomials resident in HBM."""
-    pcs: object  # kzg.MultilinearKzgProverParam or zeromorph.ZeromorphKzgProverParam
+    pcs: object  # kzg.MultilinearKzgProverParam, zeromorph.ZeromorphKzgProverParam or gemini.GeminiKzgProverParam
     num_instances: List[int]
     num_witness_polys: List[int]
     num_challenges: List[int]

@@ -388,6 +388,37 @@ def fr_div_linear(poly: "ResidentScalars", z):
     return ResidentScalars._adopt(out.value, poly.n, poly.device), rem
 
 
+def fr_linear_combination_padded(polys: Sequence["ResidentScalars"], coeffs) -> "ResidentScalars":
+    """sum_i coeffs[i] * polys[i] for univariate polynomials of different lengths (shorter ones count as zero past their
+    last coefficient; `f += (scalar, q)`, poly/univariate.rs): a new resident polynomial of the longest length."""
+    cs = _as_u64(coeffs, 4, "coeffs")
+    assert len(polys) == cs.shape[0] and len(polys) > 0
+    n = max(p.n for p in polys)
+    hs = np.array([p.handle for p in polys], dtype=np.uint64)
+    out = ctypes.c_uint64(0)
+    rc = _lib.lib().plonkish_cuda_fr_linear_combination_padded(hs.ctypes.data, cs.ctypes.data, len(polys), n, ctypes.byref(out))
+    _lib.check(rc, "plonkish_cuda_fr_linear_combination_padded")
+    return ResidentScalars._adopt(out.value, n, polys[0].device)
+
+
+def scalars_slice(scalars: "ResidentScalars", offset: int, n: int) -> "ResidentScalars":
+    """A ResidentScalars on scalars[offset : offset + n] sharing the memory (kept alive until the slice is released)."""
+    out = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_scalars_slice(scalars.handle, offset, n, ctypes.byref(out)), "plonkish_cuda_scalars_slice")
+    return ResidentScalars._adopt(out.value, n, scalars.device)
+
+
+def fr_gemini_folds(poly: "ResidentScalars", point) -> "ResidentScalars":
+    """The folds f_1 .. f_(k-1) of Gemini::open (pcs/multilinear/gemini.rs:98-108), packed: f_i (2^(k-i) values) at
+    element offset 2^(k-i) of a new resident vector of 2^k scalars.  point: [k, 4] Montgomery Fr."""
+    pt = _as_u64(point, 4, "point")
+    k = pt.shape[0]
+    assert poly.n == 1 << k, "point / polynomial size mismatch"
+    out = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().plonkish_cuda_fr_gemini_folds(poly.handle, pt.ctypes.data, k, ctypes.byref(out)), "plonkish_cuda_fr_gemini_folds")
+    return ResidentScalars._adopt(out.value, poly.n, poly.device)
+
+
 def fr_quotients(poly: "ResidentScalars", point):
     """`quotients` (pcs/multilinear.rs:72-107) on a resident polynomial, kept in HBM: returns (packed quotients as
     ResidentScalars of 2^k scalars — quotient i, 2^i values, at element offset 2^i, element 0 zero —, f(point) as

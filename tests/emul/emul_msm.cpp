@@ -283,11 +283,28 @@ void emul_fr_lincomb(const void *const *polys, const void *coeffs, u32 count, u3
         a.accumulate = done ? 1u : 0u;
         for (u32 i = 0; i < a.count; ++i) {
             a.poly[i] = (const uint4 *)polys[done + i];
+            a.len[i] = n;
             memcpy(a.coeff[i].l, (const char *)coeffs + (size_t)(done + i) * 32, 32);
         }
         PK_LAUNCH(k_fr_lincomb, dim3(3), dim3(64), 0, 0, a, (size_t)n, (uint4 *)out);
     }
 }
+// polynomials of lens[i] values each, zero past them; out has n values
+void emul_fr_lincomb_padded(const void *const *polys, const uint64_t *lens, const void *coeffs, u32 count, u32 n, void *out) {
+    for (u32 done = 0; done < count; done += PK_LINCOMB_MAX) {
+        LincombArgs a;
+        a.count = count - done < PK_LINCOMB_MAX ? count - done : PK_LINCOMB_MAX;
+        a.accumulate = done ? 1u : 0u;
+        for (u32 i = 0; i < a.count; ++i) {
+            a.poly[i] = (const uint4 *)polys[done + i];
+            a.len[i] = lens[done + i];
+            memcpy(a.coeff[i].l, (const char *)coeffs + (size_t)(done + i) * 32, 32);
+        }
+        PK_LAUNCH(k_fr_lincomb, dim3(3), dim3(64), 0, 0, a, (size_t)n, (uint4 *)out);
+    }
+}
+// Gemini's folds, packed: out has 2^num_vars scalars, f_i at element offset 2^(num_vars - i)
+void emul_gemini_folds(const void *poly, u32 num_vars, const void *point, void *out) { pk_enqueue_gemini_folds(poly, num_vars, point, out, 1, 0); }
 void emul_fr_powers(const void *s, u32 n, void *out) { pk_enqueue_fr_powers(s, n, out, 0); }
 void emul_eq_scalars(const void *ss, u32 num_vars, void *out) { pk_enqueue_eq_scalars(ss, num_vars, out, 2, 0); }
 // out[i] = scalars[i] * base through the signed-window table.

@@ -290,6 +290,60 @@ def test_zeromorph_gpu_proof_is_accepted_by_the_reference_verifier(pk, oracle, k
     pp.release()
 
 
+@pytest.mark.parametrize("k", [2, 4])
+def test_gemini_proof_bytes_match_the_integer_reference_prover(pk, oracle, k):
+    """HyperPlonk<Gemini<UnivariateKzg<Bn256>>> (the reference's gemini_kzg tests, backend/hyperplonk.rs:425): proof bytes
+    identical to the all-integer prover whose commit is the oracle's MSM and whose final opening is Gemini::open's host
+    logic with every polynomial operation done by the oracle on the CPU."""
+    import zeromorph_ref as zr
+    from batch_open_ref import batch_open_reference
+    from plonkish_b200 import gemini, kzg
+    from plonkish_b200.transcript import Keccak256Transcript
+    from test_gemini_cpu import _oracle_ops
+
+    rng = np.random.default_rng(1100 + k)
+    pp = gemini.GeminiKzgProverParam(kzg.univariate_setup(oracle.generator(), ref.to_mont(0x600DF00D600DF00D), 1 << k))
+    srs_h = pp.powers_of_s_g1.to_host()
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_circuit(k, rng)
+    proof, hvp = _prove_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    commit = lambda f: zr.commit_coeffs(oracle, srs_h, f)  # noqa: E731
+    ops = _oracle_ops(oracle)
+
+    def open_ref(g_prime, challenges, transcript):
+        gemini.open(gemini.GeminiKzgProverParam(srs_h), zr.mont_rows(g_prime), challenges, transcript, ops)
+
+    batch_open = lambda polys, points, evals, transcript: batch_open_reference(oracle, None, k, polys, points, evals, transcript, open_fn=open_ref)  # noqa: E731
+    sigmas = ref.permutation_polys(k, [6, 7, 8], cycles)
+    t = Keccak256Transcript()
+    ref.prove_reference(commit, batch_open, k, instances, preprocess, witness, sigmas, t)
+    assert proof == t.into_proof()
+    pp.release()
+
+
+@pytest.mark.parametrize("k", [8, 11])
+def test_gemini_gpu_proof_is_accepted_by_the_reference_verifier(pk, oracle, k):
+    # HyperPlonk::verify with Gemini::verify (gemini.rs:168-197) as the last step, in G1 with the setup's trapdoor
+    import gemini_ref as gr
+    from plonkish_b200 import gemini, kzg
+
+    rng = np.random.default_rng(1200 + k)
+    s = 0xFACEFEED0BADF00D123 % br.R
+    pp = gemini.GeminiKzgProverParam(kzg.univariate_setup(oracle.generator(), ref.to_mont(s), 1 << k))
+    instances, preprocess, witness, cycles = ref.rand_vanilla_plonk_circuit(k, rng)
+    proof, hvp = _prove_on_gpu(pk, pp, k, instances, preprocess, witness, cycles)
+    affine = lambda limbs: br.point_from_bytes(np.ascontiguousarray(limbs).tobytes())  # noqa: E731
+    pre = [affine(c) for c in hvp.preprocess_comms]
+    perm = [affine(c) for _, c in hvp.permutation_comms]
+    pcs_verify = lambda reader, comm, point, value: gr.verify_reader_in_g1(reader, comm, point, value, s)  # noqa: E731
+    ref.verify_reference(oracle.keccak256, None, k, instances, pre, perm, proof, pcs_verify=pcs_verify)
+    bad = [list(w) for w in witness]
+    bad[2][5] = (bad[2][5] + 1) % br.R
+    bad_proof, _ = _prove_on_gpu(pk, pp, k, instances, preprocess, bad, cycles)
+    with pytest.raises(AssertionError):
+        ref.verify_reference(oracle.keccak256, None, k, instances, pre, perm, bad_proof, pcs_verify=pcs_verify)
+    pp.release()
+
+
 @pytest.mark.parametrize("k", [3, 4])
 def test_zeromorph_lookup_proof_bytes_match_the_integer_reference_prover(pk, oracle, k):
     from plonkish_b200.transcript import Keccak256Transcript

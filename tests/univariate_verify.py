@@ -29,6 +29,28 @@ def batch_verify_in_g1(comms, points, evals, q_comm, pi, s):
     beta, gamma = v.squeeze_challenge(), v.squeeze_challenge()
     v.write_commitment(as_limbs(q_comm))
     zc = v.squeeze_challenge()
+    _check_equation(sets, superset, beta, gamma, zc, [_point(c) for c in comms], q_comm, pi, points, s)
+    return sets
+
+
+def batch_verify_reader_in_g1(reader, comms, points, evals, s):
+    """The same over a proof reader (tests/hyperplonk_ref.py ProofReader) positioned at batch_open's first challenge: what
+    Gemini::verify ends with (pcs/multilinear/gemini.rs:196).  comms: affine integer pairs."""
+    from plonkish_b200 import univariate
+
+    sets, superset = univariate.eval_sets(evals)
+    beta, gamma = reader.squeeze_challenge(), reader.squeeze_challenge()
+    q_comm = reader.read_commitment()
+    zc = reader.squeeze_challenge()
+    pi = reader.read_commitment()
+    _check_equation(sets, superset, beta, gamma, zc, comms, q_comm, pi, points, s)
+    return sets
+
+
+def _check_equation(sets, superset, beta, gamma, zc, comms, q_comm, pi, points, s):
+    """kzg.rs:380-417 after the transcript reads; comms, q_comm, pi: affine integer pairs."""
+    from plonkish_b200 import univariate
+
     pb = univariate._powers(beta, max(len(st.polys) for st in sets))
     pg = univariate._powers(gamma, len(sets))
     normalized, normalizer = univariate.set_scalars(sets, pg, points, zc)
@@ -39,7 +61,7 @@ def batch_verify_in_g1(comms, points, evals, q_comm, pi, s):
     q_scalar = (-univariate.vanishing_eval([points[i] for i in superset], zc) * normalizer) % R
     f = None
     for sc, c in zip(scalars, comms):
-        f = br.add(f, br.scalar_mul(sc, _point(c)))
+        f = br.add(f, br.scalar_mul(sc, c))
     f = br.add(f, br.scalar_mul(q_scalar, q_comm))
 
     def r_eval(st):                                                    # kzg.rs:442-451: interpolate every poly's evals over the set's points at z
@@ -61,4 +83,3 @@ def batch_verify_in_g1(comms, points, evals, q_comm, pi, s):
     lhs = br.scalar_mul((s - zc) % R, pi)
     rhs = br.add(f, br.neg(br.scalar_mul(ev, br.G)))
     assert lhs == rhs, "the proof does not satisfy batch_verify's equation"
-    return sets
