@@ -682,6 +682,126 @@ def hyperplonk_prove_bench(pk, torch, np, k: int, cpu: bool, reps: int):
     return res
 
 
+# ------------------------------------------------- the other two BN254 multilinear PCSs (Zeromorph, Gemini)
+def _timed_ops(base, names):
+    """`base` (an ops class) with a wall clock per operation: every entry point synchronises before it returns."""
+
+    class Timed(base):
+        spans = {}
+
+    def wrap(name):
+        fn = getattr(base, name)
+
+        def wrapper(*a):
+            t = time.perf_counter()
+            r = fn(*a)
+            Timed.spans[name] = Timed.spans.get(name, 0.0) + (time.perf_counter() - t) * 1e3
+            return r
+
+        return staticmethod(wrapper)
+
+    for name in names:
+        setattr(Timed, name, wrap(name))
+    return Timed
+
+
+def pcs_schemes_bench(pk, torch, np, k: int, reps: int, with_prove: bool = True, which: str = "both"):
+    """Zeromorph<UnivariateKzg> and Gemini<UnivariateKzg> (pcs/multilinear/zeromorph.rs, gemini.rs; the reference tests
+    HyperPlonk over them at backend/hyperplonk.rs:425-426) on one GPU: commit + open of one 2^k-evaluation polynomial
+    with per-operation times, and HyperPlonk::prove for vanilla_plonk over the scheme on the synthetic circuit of
+    hyperplonk_prove_bench.  Parity: every opening satisfies the scheme's verifier equation (tests/zeromorph_ref.py,
+    tests/gemini_ref.py: the pairing check evaluated in G1 through the SRS trapdoor) for the oracle's evaluation of the
+    polynomial, and every HyperPlonk proof is accepted by the verifier restatement with that check as its last step."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    import gemini_ref as gr
+    import hyperplonk_ref as ref
+    import zeromorph_ref as zr
+    from oracle import bigint_ref as br
+    from oracle import pyoracle as po
+    from plonkish_b200 import gemini, hyperplonk, kzg, zeromorph
+    from plonkish_b200.sumcheck import _to_int, _to_mont
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    n, s = 1 << k, 0x2468ACE13579BDF2468ACE13579BDF % br.R
+    t0 = time.perf_counter()
+    powers = kzg.univariate_setup(g1_generator(np), _to_mont(s), n)
+    out = {"what": "commit + open of one 2^k-evaluation polynomial and HyperPlonk::prove for vanilla_plonk over Zeromorph / Gemini on the univariate "
+                   "KZG SRS; open_ops_ms: wall time per polynomial operation of the best open",
+           "k": k, "reps": reps, "srs_setup_on_device_s": time.perf_counter() - t0}
+    poly_h = pk.random_scalars(n, seed=1234)
+    poly = pk.ResidentScalars(poly_h)
+    circuit_parts = synth_vanilla_plonk_circuit(pk, po, np, k, seed=610) if with_prove else None
+    schemes = {
+        "zeromorph": (zeromorph, zeromorph.trim(powers, n), ("quotients", "commit_quotients", "q_hat", "f", "div_linear", "commit"),
+                      lambda reader, c, pt, val: zr.verify_reader_in_g1(reader, c, pt, val, s)),
+        "gemini": (gemini, gemini.GeminiKzgProverParam(powers), ("folds", "commit_folds", "evaluate", "linear_combination", "div_linear", "commit"),
+                   lambda reader, c, pt, val: gr.verify_reader_in_g1(reader, c, pt, val, s)),
+    }
+    for name, (mod, pp, op_names, pcs_verify) in schemes.items():
+        if which not in ("both", name):
+            continue
+        ops = _timed_ops(mod.GpuOps, op_names)
+
+        def run():
+            ops.spans = {}
+            t = Keccak256Transcript()
+            comm = mod.commit(pp, poly)
+            t.write_commitment(comm)
+            point = t.squeeze_challenges(k)
+            t.write_field_element(0)           # stands for the evaluation (written before open; the proof does not depend on it)
+            t1 = time.perf_counter()
+            value = mod.open(pp, poly, point, 0, t, ops) if mod is zeromorph else mod.open(pp, poly, point, t, ops)
+            return point, value, t.into_proof(), (time.perf_counter() - t1) * 1e3, dict(ops.spans)
+
+        runs = []
+        _, tm = timed_reps(lambda: runs.append(run()), reps)
+        best = min(runs[1:], key=lambda r_: r_[3])
+        point, value, proof = best[0], best[1], best[2]
+        res = {"commit_plus_open_ms": tm["ms_min"], "commit_plus_open_ms_median": tm["ms_median"], "open_ms": best[3],
+               "open_ops_ms": {a_: round(b_, 3) for a_, b_ in best[4].items()}, "open_proof_bytes": len(proof) - 96}
+        want = _to_int(po.evaluate_multilinear(poly_h, zr.mont_rows(point), po.host_threads()))
+        assert value is None or value == want, f"{name}: the remainder of quotients differs from the oracle's evaluation"
+        reader = ref.ProofReader(po.keccak256, proof)
+        c = reader.read_commitment()
+        assert reader.squeeze_challenges(k) == point
+        reader.read_field_element()
+        pcs_verify(reader, c, point, want)
+        assert reader.pos == len(proof)
+        res["parity_checked"] = True
+        res["parity_how"] = "the opening satisfies the scheme's verify equation (G1, SRS trapdoor) for the oracle's multilinear evaluation"
+        if with_prove:
+            instances, preprocess, witness, sigma = circuit_parts
+            info = hyperplonk.vanilla_plonk_circuit_info(k, k, preprocess, [[(6, 1)], [(7, 1)], [(8, 1)]])
+            hpp, hvp = hyperplonk.preprocess(pp, info, permutation_columns=sigma)
+
+            class Circuit:
+                def instances(self):
+                    return [instances]
+
+                def synthesize(self, rnd, challenges):
+                    return witness
+
+            phases = []
+
+            def prove():
+                t, marks = Keccak256Transcript(), []
+                hyperplonk.prove(hpp, Circuit(), t, marks)
+                phases.append({b_[0]: round((b_[1] - a_[1]) * 1e3, 2) for a_, b_ in zip(marks, marks[1:])})
+                return t.into_proof()
+
+            hp_proof, tp = timed_reps(prove, reps)
+            affine = lambda limbs: br.point_from_bytes(np.ascontiguousarray(limbs).tobytes())  # noqa: E731
+            ref.verify_reference(po.keccak256, None, k, instances, [affine(c_) for c_ in hvp.preprocess_comms],
+                                 [affine(c_) for _, c_ in hvp.permutation_comms], hp_proof, pcs_verify=pcs_verify)
+            res["hyperplonk_prove"] = {"gpu_ms": tp["ms_min"], "gpu_ms_median": tp["ms_median"], "proof_bytes": len(hp_proof), "phases_ms": phases[-1],
+                                       "verifier_accepts": True, "parity_checked": True}
+            hpp.release()
+        out[name] = res
+    poly.release()
+    powers.release()
+    return out
+
+
 def univariate_sequence(pk, torch, np, k: int, dev, reps: int):
     """BASELINE.json config 4 restated synthetically: UnivariateKzg commit = one MSM over
     the SRS prefix (pcs/univariate/kzg.rs:24-30, witness-like canonical 68-bit values with zero padding) and
@@ -1078,6 +1198,10 @@ def run_ours(args) -> None:
         if cpu:
             prove_leg["k20"] = hyperplonk_prove_bench(pk, torch, np, min(20, args.prove_k), cpu=True, reps=args.reps)
         line["hyperplonk_prove"] = prove_leg
+        try:
+            line["pcs_schemes"] = pcs_schemes_bench(pk, torch, np, min(20, args.prove_k), reps=args.reps)
+        except Exception as e:  # noqa: BLE001 - keep the primary numbers if this leg cannot run
+            line["pcs_schemes"] = {"error": f"{type(e).__name__}: {e}"}
     if distributed and not args.no_single_process and not args.plain_bases:
         # rank 0 alone drives all `world` GPUs through the C ABI's multi-GPU entry (one process, NCCL gather inside the
         # library); the other ranks free their memory and wait on a host-side (gloo) barrier so their GPUs stay idle
