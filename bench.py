@@ -705,7 +705,7 @@ def _timed_ops(base, names):
     return Timed
 
 
-def pcs_schemes_bench(pk, torch, np, k: int, reps: int, with_prove: bool = True, which: str = "both"):
+def pcs_schemes_bench(pk, torch, np, k: int, reps: int, with_prove: bool = True, which: str = "both", prefix_tables: bool = False):
     """Zeromorph<UnivariateKzg> and Gemini<UnivariateKzg> (pcs/multilinear/zeromorph.rs, gemini.rs; the reference tests
     HyperPlonk over them at backend/hyperplonk.rs:425-426) on one GPU: commit + open of one 2^k-evaluation polynomial
     with per-operation times, and HyperPlonk::prove for vanilla_plonk over the scheme on the synthetic circuit of
@@ -727,7 +727,11 @@ def pcs_schemes_bench(pk, torch, np, k: int, reps: int, with_prove: bool = True,
     powers = kzg.univariate_setup(g1_generator(np), _to_mont(s), n)
     out = {"what": "commit + open of one 2^k-evaluation polynomial and HyperPlonk::prove for vanilla_plonk over Zeromorph / Gemini on the univariate "
                    "KZG SRS; open_ops_ms: wall time per polynomial operation of the best open",
-           "k": k, "reps": reps, "srs_setup_on_device_s": time.perf_counter() - t0}
+           "k": k, "reps": reps, "srs_setup_on_device_s": time.perf_counter() - t0, "prefix_tables": prefix_tables}
+    if prefix_tables:  # own resident slices for the prefixes the quotient / fold commitments run against
+        t0 = time.perf_counter()
+        powers.prefix_tables = zeromorph.build_prefix_tables(powers, n)
+        out["prefix_tables_s"] = time.perf_counter() - t0
     poly_h = pk.random_scalars(n, seed=1234)
     poly = pk.ResidentScalars(poly_h)
     circuit_parts = synth_vanilla_plonk_circuit(pk, po, np, k, seed=610) if with_prove else None
@@ -798,6 +802,7 @@ def pcs_schemes_bench(pk, torch, np, k: int, reps: int, with_prove: bool = True,
             hpp.release()
         out[name] = res
     poly.release()
+    zeromorph.release_prefix_tables(powers)
     powers.release()
     return out
 

@@ -45,11 +45,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    stamp = _fingerprint()  # of what the compiler is about to read: a source edited during the build leaves the library stale
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     with open(STAMP, "w") as f:
-        f.write(_fingerprint() + "\n")
+        f.write(stamp + "\n")
     if verbose:
         print(res.stderr)
     return OUT

@@ -1025,7 +1025,9 @@ static int view_of(uint64_t handle, size_t n, int shard, BasesView &v, int *devi
     // A short prefix of a long slice (&powers_of_s_g1[..len], univariate/kzg.rs:28) would pay for the table's full
     // bucket set (2^(c-1) buckets sized for the whole slice): below 1/16 of the slice the plain layout on row 0 of
     // the table — the bases themselves — is cheaper.
-    if (v.table_c && n && v.table_c > pk_table_window_bits((u32)n) + 3) v.table_c = 0;
+    // PLONKISH_CUDA_PREFIX_SLACK: how many window bits beyond its own a prefix may inherit (default 3).
+    static const u32 slack = [] { const char *e = getenv("PLONKISH_CUDA_PREFIX_SLACK"); const int s = e ? atoi(e) : 3; return (u32)(s < 0 ? 0 : s > 16 ? 16 : s); }();
+    if (v.table_c && n && v.table_c > pk_table_window_bits((u32)n) + slack) v.table_c = 0;
     if (device) *device = e.n_shards == 1 ? e.dev : shard;
     return PLONKISH_CUDA_OK;
 }
@@ -2776,13 +2778,19 @@ extern "C" int plonkish_cuda_fr_div_linear(uint64_t scalars_handle, const void *
     int rc = pool_alloc(c, &q, n * PLONKISH_CUDA_SCALAR_BYTES);
     if (rc) return rc;
     PoolGuard q_guard{c, q};
-    const size_t scratch_elems = pk_horner_scratch_elems(n) + 16;
+    // PLONKISH_CUDA_HORNER_LOG_CHUNK: coefficients per thread of the division's two passes, as a power of two (4..8; default 4)
+    static const u32 log_chunk = [] {
+        const char *e = getenv("PLONKISH_CUDA_HORNER_LOG_CHUNK");
+        const int v = e ? atoi(e) : PK_HORNER_LOG_CHUNK;
+        return (u32)(v < 4 ? 4 : v > 8 ? 8 : v);
+    }();
+    const size_t scratch_elems = pk_horner_scratch_elems(n, log_chunk) + 16;
     if ((rc = grow(c->tmp, scratch_elems * PLONKISH_CUDA_SCALAR_BYTES))) return rc;
     scratch = c->tmp.ptr;
     char *zs = (char *)scratch, *rem = zs + 8 * PLONKISH_CUDA_SCALAR_BYTES, *work = zs + 16 * PLONKISH_CUDA_SCALAR_BYTES;
     if (c->has_last) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->last_done, 0));
     CUDA_TRY(cudaMemcpyAsync(zs, z_mont32, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyHostToDevice, c->stream));
-    pk_enqueue_div_linear(se.d_ptr, n, zs, work, q, rem, c->stream);
+    pk_enqueue_div_linear(se.d_ptr, n, zs, work, q, rem, c->stream, log_chunk);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(c->h_out, rem, PLONKISH_CUDA_SCALAR_BYTES, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -206,16 +206,17 @@ inline void pk_enqueue_fr_powers(const void *d_s, size_t n, void *out, pk_stream
 // UnivariatePolynomial::div_rem by the divisor (X - z) (poly/univariate.rs:144-168 as called from UnivariateKzg::open,
 // pcs/univariate/kzg.rs:281-282, and, point after point, for the vanishing polynomials of batch_open, :327): with
 // h[i] = c[i] + z h[i+1] (h[n] = 0) the quotient is q[i-1] = h[i] and the remainder h[0].  The recurrence is cut into
-// chunks of PK_HORNER_CHUNK coefficients: every thread first runs its chunk with a zero carry-in, the chunk totals obey
-// the same recurrence with z^chunk (solved by recursion, three levels for 2^22 coefficients), and a second pass adds
+// chunks of 2^log_chunk coefficients: every thread first runs its chunk with a zero carry-in, the chunk totals obey
+// the same recurrence with z^chunk (solved by recursion, five levels for 2^24 coefficients at chunk 16), and a second pass adds
 // z^(distance) * carry-in.  Three products per coefficient, 32-byte accesses.
-#define PK_HORNER_CHUNK 256
+#define PK_HORNER_LOG_CHUNK 4   // chunk = 16 coefficients per thread (256 until the last part of round 2: DESIGN.md 6d has the sweep)
 __global__ void __launch_bounds__(128) k_horner_local(const uint4 *__restrict__ c, size_t n, const uint4 *__restrict__ z_ptr, uint4 *__restrict__ lh,
-                                                      uint4 *__restrict__ totals) {
+                                                      uint4 *__restrict__ totals, u32 log_chunk) {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t first = t * PK_HORNER_CHUNK;
+    const size_t chunk = (size_t)1 << log_chunk;
+    const size_t first = t * chunk;
     if (first >= n) return;
-    const size_t end = (first + PK_HORNER_CHUNK < n) ? first + PK_HORNER_CHUNK : n;
+    const size_t end = (first + chunk < n) ? first + chunk : n;
     const fe z = load_fe_plain(z_ptr);
     fe acc = fe_zero();
     for (size_t i = end; i-- > first;) {
@@ -227,11 +228,12 @@ __global__ void __launch_bounds__(128) k_horner_local(const uint4 *__restrict__ 
 // h[i] = lh[i] + z^(end - i) * carry[t + 1] for chunk t (carry = the solved recurrence of the totals; carry[chunks] = 0 is
 // not stored: the last chunk is final as it is).  shift = 1 writes h[i] to out[i - 1] and h[0] to rem (quotient layout).
 __global__ void __launch_bounds__(128) k_horner_fix(const uint4 *__restrict__ lh, size_t n, const uint4 *__restrict__ z_ptr, const uint4 *__restrict__ carry,
-                                                    size_t chunks, uint4 *__restrict__ out, int shift, uint4 *__restrict__ rem) {
+                                                    size_t chunks, uint4 *__restrict__ out, int shift, uint4 *__restrict__ rem, u32 log_chunk) {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t first = t * PK_HORNER_CHUNK;
+    const size_t chunk = (size_t)1 << log_chunk;
+    const size_t first = t * chunk;
     if (first >= n) return;
-    const size_t end = (first + PK_HORNER_CHUNK < n) ? first + PK_HORNER_CHUNK : n;
+    const size_t end = (first + chunk < n) ? first + chunk : n;
     const fe z = load_fe_plain(z_ptr);
     const bool has = t + 1 < chunks;
     const fe cin = has ? load_fe_plain(carry + 2 * (t + 1)) : fe_zero();
@@ -257,49 +259,54 @@ __global__ void k_horner_serial(const uint4 *__restrict__ c, size_t n, const uin
         store_fe(out + 2 * i, acc);
     }
 }
-// zs[l + 1] = zs[l]^256
-__global__ void k_horner_pow(uint4 *__restrict__ zs, u32 levels) {
+// zs[l + 1] = zs[l]^chunk
+#define PK_HORNER_Z_SLOTS 8
+__global__ void k_horner_pow(uint4 *__restrict__ zs, u32 levels, u32 log_chunk) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     fe z = load_fe_plain(zs);
     for (u32 l = 0; l < levels; ++l) {
-        for (int k = 0; k < 8; ++k) z = fr_mul(z, z);
+        for (u32 k = 0; k < log_chunk; ++k) z = fr_mul(z, z);
         store_fe(zs + 2 * (size_t)(l + 1), z);
     }
 }
-inline size_t pk_horner_scratch_elems(size_t n) {  // lh of every level + the z powers
+inline size_t pk_horner_scratch_elems(size_t n, u32 log_chunk = PK_HORNER_LOG_CHUNK) {  // lh of every level + the totals
+    const size_t chunk = (size_t)1 << log_chunk;
     size_t total = 8, m = n;
     while (m > 64) {
         total += m;
-        m = (m + PK_HORNER_CHUNK - 1) / PK_HORNER_CHUNK;
+        m = (m + chunk - 1) / chunk;
         total += m;  // totals (the next level's input)
     }
     return total + 64 + 64;
 }
 // out = h (shift 0) or the quotient with the remainder in *rem (shift 1).  c has n coefficients; zs[0] = z on entry
-// (8 element slots); scratch holds pk_horner_scratch_elems(n) elements.
-inline void pk_enqueue_horner(const uint4 *c, size_t n, uint4 *zs, u32 level, uint4 *scratch, uint4 *out, int shift, uint4 *rem, pk_stream_t stream) {
+// (PK_HORNER_Z_SLOTS element slots: 2^28 coefficients need 6 levels at chunk 16); scratch holds pk_horner_scratch_elems(n) elements.
+inline void pk_enqueue_horner(const uint4 *c, size_t n, uint4 *zs, u32 level, uint4 *scratch, uint4 *out, int shift, uint4 *rem, pk_stream_t stream,
+                              u32 log_chunk) {
     if (n <= 64) {
         if (!shift) {
             PK_LAUNCH(k_horner_serial, dim3(1), dim3(32), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), out);
         } else {  // serial into scratch, then a one-chunk fix pass does the shifted copy
             PK_LAUNCH(k_horner_serial, dim3(1), dim3(32), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), scratch);
-            PK_LAUNCH(k_horner_fix, dim3(1), dim3(128), 0, stream, (const uint4 *)scratch, n, (const uint4 *)(zs + 2 * (size_t)level), (const uint4 *)scratch, (size_t)1, out, 1, rem);
+            PK_LAUNCH(k_horner_fix, dim3(1), dim3(128), 0, stream, (const uint4 *)scratch, n, (const uint4 *)(zs + 2 * (size_t)level), (const uint4 *)scratch, (size_t)1, out, 1, rem, 6u);
         }
         return;
     }
-    const size_t chunks = (n + PK_HORNER_CHUNK - 1) / PK_HORNER_CHUNK;
+    const size_t chunk = (size_t)1 << log_chunk;
+    const size_t chunks = (n + chunk - 1) / chunk;
     uint4 *lh = scratch, *totals = scratch + 2 * n, *next = totals + 2 * chunks;
     const unsigned blocks = (unsigned)((chunks + 127) / 128);
-    PK_LAUNCH(k_horner_local, dim3(blocks), dim3(128), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), lh, totals);
-    // the totals obey the same recurrence with z^256: solve in place of `totals` (h of the totals), using what follows as scratch
-    pk_enqueue_horner(totals, chunks, zs, level + 1, next, totals, 0, nullptr, stream);
-    PK_LAUNCH(k_horner_fix, dim3(blocks), dim3(128), 0, stream, (const uint4 *)lh, n, (const uint4 *)(zs + 2 * (size_t)level), (const uint4 *)totals, chunks, out, shift, rem);
+    PK_LAUNCH(k_horner_local, dim3(blocks), dim3(128), 0, stream, c, n, (const uint4 *)(zs + 2 * (size_t)level), lh, totals, log_chunk);
+    // the totals obey the same recurrence with z^chunk: solve in place of `totals` (h of the totals), using what follows as scratch
+    pk_enqueue_horner(totals, chunks, zs, level + 1, next, totals, 0, nullptr, stream, log_chunk);
+    PK_LAUNCH(k_horner_fix, dim3(blocks), dim3(128), 0, stream, (const uint4 *)lh, n, (const uint4 *)(zs + 2 * (size_t)level), (const uint4 *)totals, chunks, out, shift, rem, log_chunk);
 }
 // q (n - 1 coefficients, written to q[0 .. n-1); q[n-1] is set to zero) and rem = c mod (X - z).  z in zs[0].
-inline void pk_enqueue_div_linear(const void *c, size_t n, void *zs, void *scratch, void *q, void *rem, pk_stream_t stream) {
-    PK_LAUNCH(k_horner_pow, dim3(1), dim3(32), 0, stream, (uint4 *)zs, 4u);
+inline void pk_enqueue_div_linear(const void *c, size_t n, void *zs, void *scratch, void *q, void *rem, pk_stream_t stream,
+                                  u32 log_chunk = PK_HORNER_LOG_CHUNK) {
+    PK_LAUNCH(k_horner_pow, dim3(1), dim3(32), 0, stream, (uint4 *)zs, (u32)(PK_HORNER_Z_SLOTS - 1), log_chunk);
     PK_MEMSET0((uint4 *)q + 2 * (n - 1), 32, stream);
-    pk_enqueue_horner((const uint4 *)c, n, (uint4 *)zs, 0, (uint4 *)scratch, (uint4 *)q, 1, (uint4 *)rem, stream);
+    pk_enqueue_horner((const uint4 *)c, n, (uint4 *)zs, 0, (uint4 *)scratch, (uint4 *)q, 1, (uint4 *)rem, stream, log_chunk);
 }
 
 // ------------------------------------------------ permutation grand products

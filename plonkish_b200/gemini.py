@@ -40,25 +40,53 @@ class GpuOps(univariate.GpuOps):
     @staticmethod
     def commit_folds(powers_of_s_g1: G1Bases, folds: ResidentScalars, num_vars: int) -> np.ndarray:
         sizes = [1 << (num_vars - i) for i in range(1, num_vars)]  # f_i: 2^(n-i) scalars at offset 2^(n-i)
-        return variable_base_msm_many_resident(folds, sizes, [powers_of_s_g1] * len(sizes), sizes)
+        from .zeromorph import prefix_bases
+
+        return variable_base_msm_many_resident(folds, sizes, [prefix_bases(powers_of_s_g1, m) for m in sizes], sizes)
+
+    # evaluate() leaves its quotient here: batch_open starts the set of that polynomial with the same division
+    # (univariate.batch_open divides a single-polynomial set's polynomial itself), which then costs nothing
+    _quotients: dict = {}
 
     @staticmethod
     def evaluate(poly: ResidentScalars, x: int) -> int:
         q, rem = fr_div_linear(poly, _to_mont(x))  # the remainder of the division by (X - x) is poly(x)
-        q.release()
+        old = GpuOps._quotients.pop((poly.handle, x), None)
+        if old is not None:
+            old[0].release()
+        GpuOps._quotients[(poly.handle, x)] = (q, _to_int(rem))
         return _to_int(rem)
+
+    @staticmethod
+    def div_linear(poly: ResidentScalars, z: int):
+        hit = GpuOps._quotients.pop((poly.handle, z), None)
+        return hit if hit is not None else univariate.GpuOps.div_linear(poly, z)
+
+    @staticmethod
+    def drop_quotients() -> None:
+        """Release what evaluate() left and no division took over."""
+        for q, _ in GpuOps._quotients.values():
+            q.release()
+        GpuOps._quotients.clear()
 
 
 class GeminiKzgProverParam:
     """Gemini's ProverParam is UnivariateKzg's (gemini.rs:38): powers_of_s_g1 (univariate/kzg.rs:41-55)."""
 
-    def __init__(self, powers_of_s_g1: G1Bases):
+    def __init__(self, powers_of_s_g1: G1Bases, prefix_tables: bool = False):
         self.powers_of_s_g1 = powers_of_s_g1
+        if prefix_tables:  # own resident slices for the fold commitments' prefixes (zeromorph.build_prefix_tables)
+            from .zeromorph import build_prefix_tables
+
+            powers_of_s_g1.prefix_tables = build_prefix_tables(powers_of_s_g1, len(powers_of_s_g1))
 
     def degree(self) -> int:
         return len(self.powers_of_s_g1) - 1
 
     def release(self) -> None:
+        from .zeromorph import release_prefix_tables
+
+        release_prefix_tables(self.powers_of_s_g1)
         self.powers_of_s_g1.release()
 
 
@@ -117,10 +145,14 @@ def open(pp: GeminiKzgProverParam, poly, point: Sequence[int], transcript, ops=G
     points = open_points(beta, num_vars)
     evals = [(idx, pt, ops.evaluate(fs[idx], points[pt])) for idx, pt in open_queries(num_vars)]   # :135-137
     transcript.write_field_elements([v for _, _, v in evals[1:]])                        # :138
-    univariate.batch_open(pp.powers_of_s_g1, fs, points, evals, transcript, ops)          # :140
-    for v in views:
-        ops.release(v)
-    ops.release(folds)
+    try:
+        univariate.batch_open(pp.powers_of_s_g1, fs, points, evals, transcript, ops)      # :140
+    finally:
+        if hasattr(ops, "drop_quotients"):
+            ops.drop_quotients()
+        for v in views:
+            ops.release(v)
+        ops.release(folds)
 
 
 def batch_open(pp: GeminiKzgProverParam, num_vars: int, polys: Sequence, points: Sequence[Sequence[int]], evals: Sequence[Tuple[int, int, int]],

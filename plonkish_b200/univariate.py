@@ -133,9 +133,12 @@ def batch_open(powers_of_s_g1: G1Bases, polys: Sequence, points: Sequence[int], 
     gamma = transcript.squeeze_challenge()
     powers_of_beta = _powers(beta, max(len(s.polys) for s in sets))
     powers_of_gamma = _powers(gamma, len(sets))
-    fs, qs = [], []
+    fs, qs, owned = [], [], []
     for s in sets:
-        f = ops.linear_combination([polys[i] for i in s.polys], powers_of_beta[: len(s.polys)])          # kzg.rs:324-325
+        if len(s.polys) == 1:   # powers_of_beta[0] = 1: the combination of kzg.rs:324-325 is the polynomial itself, borrowed
+            f, own = polys[s.polys[0]], False
+        else:
+            f, own = ops.linear_combination([polys[i] for i in s.polys], powers_of_beta[: len(s.polys)]), True
         # f.div_rem(vanishing_poly): the quotient by prod (X - point) is the chain of quotients by each factor
         q = f
         for idx in s.points:
@@ -144,6 +147,7 @@ def batch_open(powers_of_s_g1: G1Bases, polys: Sequence, points: Sequence[int], 
                 ops.release(q)
             q = nxt
         fs.append(f)
+        owned.append(own)
         qs.append(q)
     q = ops.linear_combination(qs, powers_of_gamma)                                                      # kzg.rs:330
     for t in qs:
@@ -154,7 +158,8 @@ def batch_open(powers_of_s_g1: G1Bases, polys: Sequence, points: Sequence[int], 
     normalized_scalars, normalizer = set_scalars(sets, powers_of_gamma, points, z)
     q_scalar = (-vanishing_eval([points[i] for i in superset], z) * normalizer) % r
     f = ops.linear_combination(fs + [q], normalized_scalars + [q_scalar])                                 # kzg.rs:339-343
-    for t in fs + [q]:
-        ops.release(t)
+    for t, own in zip(fs + [q], owned + [True]):
+        if own:
+            ops.release(t)
     open(powers_of_s_g1, f, z, transcript, ops)                                                           # kzg.rs:353
     ops.release(f)

@@ -28,6 +28,30 @@ def _mont_rows(values: Sequence[int]) -> np.ndarray:
     return np.stack([_to_mont(v) for v in values]) if len(values) else np.zeros((0, 4), dtype=np.uint64)
 
 
+def build_prefix_tables(powers_of_s_g1: G1Bases, poly_size: int) -> dict:
+    """Optional: one resident slice of its own (with its own table of window multiples and window size) for every proper
+    power-of-two prefix of powers_of_s_g1 — the bases of the quotient / fold commitments (`&powers_of_s_g1[..2^i]`,
+    univariate/kzg.rs:28).  Without them a prefix inherits the full slice's window size (and pays its bucket set) down to
+    1/16 of the slice and falls back to the plain layout below; with them the chain of halving MSMs runs like
+    MultilinearKzg::open's over eqs[i].  Costs about as much HBM again as the full slice's table (14 GB at 2^24) and one
+    pass of the points through host memory.  Attach the result as `powers_of_s_g1.prefix_tables`."""
+    tables, size = {}, 1
+    while size < poly_size:
+        tables[size] = G1Bases(powers_of_s_g1.to_host(0, size), device=powers_of_s_g1.device)
+        size <<= 1
+    return tables
+
+
+def prefix_bases(powers_of_s_g1: G1Bases, size: int) -> G1Bases:
+    return getattr(powers_of_s_g1, "prefix_tables", {}).get(size, powers_of_s_g1)
+
+
+def release_prefix_tables(powers_of_s_g1: G1Bases) -> None:
+    for b in getattr(powers_of_s_g1, "prefix_tables", {}).values():
+        b.release()
+    powers_of_s_g1.prefix_tables = {}
+
+
 class GpuOps(univariate.GpuOps):
     """The polynomial operations of Zeromorph::open on resident vectors (plus UnivariateKzg::open's, inherited)."""
 
@@ -39,7 +63,7 @@ class GpuOps(univariate.GpuOps):
     @staticmethod
     def commit_quotients(powers_of_s_g1: G1Bases, q: ResidentScalars, num_vars: int) -> np.ndarray:
         sizes = [1 << i for i in range(num_vars)]  # q_i: 2^i scalars at offset 2^i, against powers_of_s_g1[..2^i]
-        return variable_base_msm_many_resident(q, sizes, [powers_of_s_g1] * num_vars, sizes)
+        return variable_base_msm_many_resident(q, sizes, [prefix_bases(powers_of_s_g1, m) for m in sizes], sizes)
 
     @staticmethod
     def q_hat(q: ResidentScalars, weights: Sequence[int]) -> ResidentScalars:
@@ -60,25 +84,30 @@ class ZeromorphKzgProverParam:
         return len(self.commit_pp) - 1  # zeromorph.rs:36-38
 
     def release(self) -> None:
+        release_prefix_tables(self.commit_pp)
         if self.open_pp is not self.commit_pp:
             self.open_pp.release()
         self.commit_pp.release()
 
 
-def trim(powers_of_s_g1: G1Bases, poly_size: int) -> ZeromorphKzgProverParam:
+def trim(powers_of_s_g1: G1Bases, poly_size: int, prefix_tables: bool = False) -> ZeromorphKzgProverParam:
     """Zeromorph::trim (zeromorph.rs:84-102), prover half: commit_pp = the first poly_size powers (UnivariateKzg::trim,
     univariate/kzg.rs:214-233), open_pp = the LAST poly_size powers (offset = len - poly_size).  With a setup of exactly
     poly_size powers the two coincide and share one resident slice; otherwise open_pp becomes a slice of its own (the
-    points pass through host memory once, at trim time)."""
+    points pass through host memory once, at trim time).  prefix_tables: build_prefix_tables for the quotient commitments."""
     total = len(powers_of_s_g1)
     if poly_size > total:
         raise ValueError(f"Too large poly_size to trim to (param supports poly_size up to {total} but got {poly_size})")
     offset = total - poly_size
     if offset == 0:
-        return ZeromorphKzgProverParam(powers_of_s_g1, powers_of_s_g1)
-    commit_pp = G1Bases(powers_of_s_g1.to_host(0, poly_size), device=powers_of_s_g1.device)
-    open_pp = G1Bases(powers_of_s_g1.to_host(offset, poly_size), device=powers_of_s_g1.device)
-    return ZeromorphKzgProverParam(commit_pp, open_pp)
+        pp = ZeromorphKzgProverParam(powers_of_s_g1, powers_of_s_g1)
+    else:
+        commit_pp = G1Bases(powers_of_s_g1.to_host(0, poly_size), device=powers_of_s_g1.device)
+        open_pp = G1Bases(powers_of_s_g1.to_host(offset, poly_size), device=powers_of_s_g1.device)
+        pp = ZeromorphKzgProverParam(commit_pp, open_pp)
+    if prefix_tables:  # see build_prefix_tables
+        pp.commit_pp.prefix_tables = build_prefix_tables(pp.commit_pp, poly_size)
+    return pp
 
 
 def commit(pp: ZeromorphKzgProverParam, poly, ops=GpuOps) -> np.ndarray:

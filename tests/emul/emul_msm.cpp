@@ -94,6 +94,12 @@ void emul_div_linear(const u32 *c, uint64_t n, const u32 *z, u32 *q, u32 *rem) {
     memcpy(scratch.data(), z, 32);
     pk_enqueue_div_linear(c, n, scratch.data(), scratch.data() + 16 * 32, q, rem, 0);
 }
+// the same with 2^log_chunk coefficients per thread (the library's PLONKISH_CUDA_HORNER_LOG_CHUNK)
+void emul_div_linear_chunk(const u32 *c, uint64_t n, const u32 *z, u32 *q, u32 *rem, u32 log_chunk) {
+    std::vector<unsigned char> scratch((pk_horner_scratch_elems(n, log_chunk) + 16) * 32);
+    memcpy(scratch.data(), z, 32);
+    pk_enqueue_div_linear(c, n, scratch.data(), scratch.data() + 16 * 32, q, rem, 0, log_chunk);
+}
 
 // redundant-range forms of the accumulate loop: op 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_sum (a*b + c*d); inputs in [0, 2p)
 void emul_fq_lazy(int op, const u32 *a, const u32 *b, const u32 *c, const u32 *d, u32 *o) {

@@ -176,6 +176,17 @@ def test_emulated_division_by_a_linear_factor_matches_the_oracle(oracle):
         assert rem.tobytes() == want_rem.tobytes(), n
         assert q[: n - 1].tobytes() == want_q.tobytes(), n
         assert not q[n - 1].any(), n
+    # every chunk size the library accepts (PLONKISH_CUDA_HORNER_LOG_CHUNK), sizes around the recursion's level boundaries
+    lib.emul_div_linear_chunk.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    for log_chunk in (4, 5, 6, 8):
+        for n in (1, 64, 65, (64 << log_chunk) - 1, (64 << log_chunk) + 1, 40000):
+            c = oracle.random_scalars(n, 1000 + n)
+            q = np.full((n, 4), 0xAB, dtype=np.uint64)
+            rem = np.zeros(4, dtype=np.uint64)
+            lib.emul_div_linear_chunk(c.ctypes.data, n, z.ctypes.data, q.ctypes.data, rem.ctypes.data, log_chunk)
+            want_q, want_rem = oracle.fr_div_linear(c, z)
+            assert rem.tobytes() == want_rem.tobytes(), (log_chunk, n)
+            assert q[: n - 1].tobytes() == want_q.tobytes() and not q[n - 1].any(), (log_chunk, n)
 
 
 def test_univariate_batch_open_host_logic_satisfies_the_verifier(oracle):

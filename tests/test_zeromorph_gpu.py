@@ -216,3 +216,26 @@ def test_batch_open_writes_the_reference_proof_bytes(pk, oracle, num_vars):
     for r_ in resident:
         r_.release()
     pp.release()
+
+
+def test_prefix_tables_leave_the_proofs_unchanged(pk, oracle):
+    # zeromorph.build_prefix_tables: own resident slices for &powers_of_s_g1[..2^i] change the MSMs' window sizes, not a byte
+    from plonkish_b200 import gemini, kzg, zeromorph
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    num_vars = 11
+    n, s = 1 << num_vars, 0x1CEB00DA % R
+    poly = pk.ResidentScalars(pk.random_scalars(n, seed=4321))
+    point = [int(x) for x in np.random.default_rng(5).integers(1, 1 << 62, num_vars)]
+    proofs = {}
+    for with_tables in (False, True):
+        powers = kzg.univariate_setup(oracle.generator(), _mont(s), n)
+        zpp = zeromorph.trim(powers, n, prefix_tables=with_tables)
+        assert len(getattr(powers, "prefix_tables", {})) == (num_vars if with_tables else 0)
+        t = Keccak256Transcript()
+        zeromorph.open(zpp, poly, point, 0, t)
+        gemini.open(gemini.GeminiKzgProverParam(powers), poly, point, t)   # finds the tables on the same slice
+        proofs[with_tables] = t.into_proof()
+        zpp.release()
+    assert proofs[False] == proofs[True]
+    poly.release()
