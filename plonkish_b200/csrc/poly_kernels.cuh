@@ -668,7 +668,8 @@ inline void pk_enqueue_fixed_base(const void *d_scalars, u32 n, const affine *ta
 // Zeromorph<UnivariateKzg>::open (pcs/multilinear/zeromorph.rs:126-186) builds two univariate polynomials of 2^n
 // coefficients out of the quotients of `quotients` (pcs/multilinear.rs:72-107, q_i of 2^i values packed at element
 // offset 2^i of `q`, as pk_enqueue_quotients leaves them).  Both are one pass over 2^n elements with 2^n products in
-// total (element m of either sum has as many terms as there are quotients long enough to reach it): HBM bound.
+// total (element m of either sum has as many terms as there are quotients long enough to reach it): one product per
+// 64 B moved, which on B200 is multiplier bound rather than HBM bound (profiles/r02_pcs_field_kernels_summary.txt).
 #define PK_ZM_MAX_VARS 28
 struct ZmWeights {
     fe w[PK_ZM_MAX_VARS];
