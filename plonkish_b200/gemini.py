@@ -138,15 +138,16 @@ def open(pp: GeminiKzgProverParam, poly, point: Sequence[int], transcript, ops=G
         raise ValueError(f"Too large degree of poly to open (param supports degree up to {pp.degree()} but got {len(poly)})")
     point = [int(x) % r for x in point]
     folds = ops.folds(poly, point)                                                        # :98-108
-    views = ops.fold_views(folds, num_vars)
-    fs = [poly] + views
-    transcript.write_commitments(ops.commit_folds(pp.powers_of_s_g1, folds, num_vars))   # batch_commit_and_write(&fs[1..]), :124-128
-    beta = transcript.squeeze_challenge()
-    points = open_points(beta, num_vars)
-    evals = [(idx, pt, ops.evaluate(fs[idx], points[pt])) for idx, pt in open_queries(num_vars)]   # :135-137
-    transcript.write_field_elements([v for _, _, v in evals[1:]])                        # :138
+    views = []
     try:
-        univariate.batch_open(pp.powers_of_s_g1, fs, points, evals, transcript, ops)      # :140
+        views = ops.fold_views(folds, num_vars)
+        fs = [poly] + views
+        transcript.write_commitments(ops.commit_folds(pp.powers_of_s_g1, folds, num_vars))   # batch_commit_and_write(&fs[1..]), :124-128
+        beta = transcript.squeeze_challenge()
+        points = open_points(beta, num_vars)
+        evals = [(idx, pt, ops.evaluate(fs[idx], points[pt])) for idx, pt in open_queries(num_vars)]   # :135-137
+        transcript.write_field_elements([v for _, _, v in evals[1:]])                        # :138
+        univariate.batch_open(pp.powers_of_s_g1, fs, points, evals, transcript, ops)          # :140
     finally:
         if hasattr(ops, "drop_quotients"):
             ops.drop_quotients()

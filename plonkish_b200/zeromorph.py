@@ -168,18 +168,22 @@ def open(pp: ZeromorphKzgProverParam, poly, point: Sequence[int], eval: int, tra
         raise ValueError(f"Too large degree of poly to open (param supports degree up to {pp.degree()} but got {len(poly)})")
     point = [int(p) % r for p in point]
     q, remainder = ops.quotients(poly, point)                                              # :149
-    transcript.write_commitments(ops.commit_quotients(pp.commit_pp, q, num_vars))          # batch_commit_and_write, :150
-    y = transcript.squeeze_challenge()
-    q_hat = ops.q_hat(q, _powers(y, num_vars))                                             # :158-168
-    transcript.write_commitment(ops.commit(pp.commit_pp, q_hat))                           # commit_and_write, :169
-    x = transcript.squeeze_challenge()
-    z = transcript.squeeze_challenge()
-    eval_scalar, q_scalars = eval_and_quotient_scalars(y, x, z, point)
-    f = ops.f(poly, q_hat, q, z, eval_scalar * (int(eval) % r) % r, q_scalars)             # :175-180
-    ops.release(q)
-    ops.release(q_hat)
-    univariate.open(pp.open_pp, f, x, transcript, ops)                                     # UnivariateKzg::open(&pp.open_pp, &f, .., &x, &ZERO), :185
-    ops.release(f)
+    owned = [q]
+    try:
+        transcript.write_commitments(ops.commit_quotients(pp.commit_pp, q, num_vars))      # batch_commit_and_write, :150
+        y = transcript.squeeze_challenge()
+        q_hat = ops.q_hat(q, _powers(y, num_vars))                                         # :158-168
+        owned.append(q_hat)
+        transcript.write_commitment(ops.commit(pp.commit_pp, q_hat))                       # commit_and_write, :169
+        x = transcript.squeeze_challenge()
+        z = transcript.squeeze_challenge()
+        eval_scalar, q_scalars = eval_and_quotient_scalars(y, x, z, point)
+        f = ops.f(poly, q_hat, q, z, eval_scalar * (int(eval) % r) % r, q_scalars)         # :175-180
+        owned.append(f)
+        univariate.open(pp.open_pp, f, x, transcript, ops)                                 # UnivariateKzg::open(&pp.open_pp, &f, .., &x, &ZERO), :185
+    finally:
+        for t in owned:
+            ops.release(t)
     return remainder
 
 
