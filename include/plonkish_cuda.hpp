@@ -150,6 +150,60 @@ inline MultilinearPolynomial linear_combination(const std::vector<const Multilin
     return MultilinearPolynomial::adopt(h, polys[0]->len());
 }
 
+// ---- the polynomial side of Zeromorph / Gemini over the univariate SRS (pcs/multilinear/zeromorph.rs, gemini.rs) ----
+// `quotients(poly, point, ..)` (pcs/multilinear.rs:72-107) kept in HBM: quotient i (2^i values) at element offset 2^i of the
+// returned vector (element 0 zero), and the remainder poly(point).
+inline std::pair<MultilinearPolynomial, Fr> quotients(const MultilinearPolynomial &poly, const std::vector<Fr> &point) {
+    if ((size_t(1) << point.size()) != poly.len()) throw std::invalid_argument("quotients: the point does not match the polynomial (multilinear.rs:77)");
+    uint64_t h = 0;
+    Fr eval{};
+    check(plonkish_cuda_fr_quotients(poly.handle(), point.data(), point.size(), &h, &eval), "plonkish_cuda_fr_quotients");
+    return {MultilinearPolynomial::adopt(h, poly.len()), eval};
+}
+// The folds fs[1..] of Gemini::open (gemini.rs:98-108), packed: f_i (2^(k-i) values) at element offset 2^(k-i).
+inline MultilinearPolynomial gemini_folds(const MultilinearPolynomial &poly, const std::vector<Fr> &point) {
+    if (point.empty() || (size_t(1) << point.size()) != poly.len()) throw std::invalid_argument("gemini_folds: the point does not match the polynomial");
+    uint64_t h = 0;
+    check(plonkish_cuda_fr_gemini_folds(poly.handle(), point.data(), point.size(), &h), "plonkish_cuda_fr_gemini_folds");
+    return MultilinearPolynomial::adopt(h, poly.len());
+}
+// UnivariateKzg::batch_commit over packed quotients / folds (zeromorph.rs:150, gemini.rs:124-128): the parts of `packed` at
+// element offset sizes[j], sizes[j] values long, each against powers_of_s_g1[..sizes[j]] (commit_coeffs, univariate/kzg.rs:24-30).
+inline std::vector<G1Affine> commit_packed(const MultilinearPolynomial &packed, const std::vector<size_t> &sizes, const G1Bases &powers_of_s_g1) {
+    std::vector<uint64_t> hs(sizes.size(), powers_of_s_g1.handle());
+    std::vector<G1Affine> out(sizes.size());
+    if (!sizes.empty())
+        check(plonkish_cuda_msm_bn254_g1_many_resident(packed.handle(), sizes.data(), hs.data(), sizes.data(), sizes.size(), out.data()),
+              "plonkish_cuda_msm_bn254_g1_many_resident");
+    return out;
+}
+// A polynomial on a sub-range of a resident vector (shares the memory): one fold or one quotient on its own.
+inline MultilinearPolynomial slice(const MultilinearPolynomial &v, size_t offset, size_t n) {
+    uint64_t h = 0;
+    check(plonkish_cuda_scalars_slice(v.handle(), offset, n, &h), "plonkish_cuda_scalars_slice");
+    return MultilinearPolynomial::adopt(h, n);
+}
+// q_hat (zeromorph.rs:157-168) and f (zeromorph.rs:175-180) of Zeromorph::open from the packed quotients.
+inline MultilinearPolynomial zeromorph_q_hat(const MultilinearPolynomial &q, const std::vector<Fr> &powers_of_y) {
+    uint64_t h = 0;
+    check(plonkish_cuda_zeromorph_q_hat_bn254(q.handle(), powers_of_y.data(), powers_of_y.size(), &h), "plonkish_cuda_zeromorph_q_hat_bn254");
+    return MultilinearPolynomial::adopt(h, q.len());
+}
+inline MultilinearPolynomial zeromorph_f(const MultilinearPolynomial &poly, const MultilinearPolynomial &q_hat, const MultilinearPolynomial &q, const Fr &z,
+                                         const Fr &c0, const std::vector<Fr> &q_scalars) {
+    uint64_t h = 0;
+    check(plonkish_cuda_zeromorph_f_bn254(poly.handle(), q_hat.handle(), q.handle(), &z, &c0, q_scalars.data(), q_scalars.size(), &h),
+          "plonkish_cuda_zeromorph_f_bn254");
+    return MultilinearPolynomial::adopt(h, poly.len());
+}
+// UnivariatePolynomial::div_rem by (X - z) (poly/univariate.rs:144-168): (quotient, remainder = value at z).
+inline std::pair<MultilinearPolynomial, Fr> div_linear(const MultilinearPolynomial &coeffs, const Fr &z) {
+    uint64_t h = 0;
+    Fr rem{};
+    check(plonkish_cuda_fr_div_linear(coeffs.handle(), &z, &h, &rem), "plonkish_cuda_fr_div_linear");
+    return {MultilinearPolynomial::adopt(h, coeffs.len()), rem};
+}
+
 // MultilinearKzgProverParams { g1, eqs } (kzg.rs:55-77) with every eqs[k] resident.
 class MultilinearKzgProverParam {
   public:

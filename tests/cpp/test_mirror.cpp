@@ -147,6 +147,68 @@ static int run() {
         REQUIRE(merged.evals() == w);
     }
 
+    // ---- Zeromorph / Gemini over the univariate SRS (zeromorph.rs:149-180, gemini.rs:98-128): kept quotients and folds,
+    //      their commitments from sub-ranges, q_hat and f, the division by X - x
+    {
+        const size_t kk = 6, nn = size_t(1) << kk;
+        const Fr s = random_fr();
+        std::vector<Fr> pw(nn, fr_from(1));
+        for (size_t i = 1; i < nn; ++i) pw[i] = fr_mul(pw[i - 1], s);
+        std::vector<G1Affine> powers(nn);
+        oracle_fixed_base_msm(&g_o, 5, (const ofe_t *)pw.data(), nn, 2, (og1_affine_t *)powers.data());
+        G1Bases srs = univariate_setup(g, s, nn);
+        REQUIRE(srs.to_host() == powers);
+        auto f_evals = random_frs(nn), u = random_frs(kk);
+        MultilinearPolynomial poly(f_evals.data(), nn);
+        auto [q, value] = plonkish::quotients(poly, u);
+        std::vector<Fr> want_q(nn);
+        Fr want_value;
+        oracle_quotients((const ofe_t *)f_evals.data(), (const ofe_t *)u.data(), kk, (ofe_t *)want_q.data(), (ofe_t *)&want_value);
+        auto got_q = q.evals();
+        REQUIRE(value == want_value && got_q[0] == fr_from(0));
+        for (size_t i = 1; i < nn; ++i) REQUIRE(got_q[i] == want_q[i]);
+        std::vector<size_t> sizes;
+        for (size_t i = 0; i < kk; ++i) sizes.push_back(size_t(1) << i);
+        auto q_comms = commit_packed(q, sizes, srs);
+        for (size_t i = 0; i < kk; ++i) {
+            std::vector<Fr> qi(got_q.begin() + sizes[i], got_q.begin() + 2 * sizes[i]);
+            REQUIRE(q_comms[i] == oracle_msm(qi, std::vector<G1Affine>(powers.begin(), powers.begin() + sizes[i])));
+        }
+        auto ys = random_frs(kk), ss_ = random_frs(kk);
+        const Fr z = random_fr(), c0 = random_fr();
+        auto q_hat = zeromorph_q_hat(q, ys);
+        auto ff = zeromorph_f(poly, q_hat, q, z, c0, ss_);
+        std::vector<Fr> want_hat(nn, fr_from(0)), want_f(nn);
+        for (size_t m = 0; m < nn; ++m) want_f[m] = fr_mul(z, f_evals[m]);
+        for (size_t i = 0; i < kk; ++i) {
+            for (size_t j = 0; j < sizes[i]; ++j) {
+                want_hat[nn - sizes[i] + j] = fr_add(want_hat[nn - sizes[i] + j], fr_mul(ys[i], got_q[sizes[i] + j]));
+                want_f[j] = fr_add(want_f[j], fr_mul(ss_[i], got_q[sizes[i] + j]));
+            }
+        }
+        for (size_t m = 0; m < nn; ++m) want_f[m] = fr_add(want_f[m], want_hat[m]);
+        want_f[0] = fr_add(want_f[0], c0);
+        REQUIRE(q_hat.evals() == want_hat && ff.evals() == want_f);
+        // div_rem by (X - x): quotient * (X - x) + remainder gives the polynomial back, the remainder is its value at x
+        const Fr x = random_fr();
+        auto [quot, rem] = div_linear(ff, x);
+        auto qc = quot.evals();
+        REQUIRE(qc[nn - 1] == fr_from(0));
+        for (size_t m = 0; m < nn; ++m) REQUIRE(fr_sub(m ? qc[m - 1] : rem, fr_mul(x, qc[m])) == want_f[m]);
+        // Gemini's folds: f_i[j] = (f_(i-1)[2j+1] - f_(i-1)[2j]) * u_(i-1) + f_(i-1)[2j], packed at offset 2^(kk-i); one as a slice
+        auto folds = gemini_folds(poly, u);
+        auto packed = folds.evals();
+        std::vector<Fr> cur = f_evals;
+        for (size_t i = 1; i < kk; ++i) {
+            std::vector<Fr> nxt(cur.size() / 2);
+            for (size_t j = 0; j < nxt.size(); ++j) nxt[j] = fr_add(fr_mul(fr_sub(cur[2 * j + 1], cur[2 * j]), u[i - 1]), cur[2 * j]);
+            for (size_t j = 0; j < nxt.size(); ++j) REQUIRE(packed[nxt.size() + j] == nxt[j]);
+            cur = nxt;
+        }
+        auto f2 = slice(folds, nn >> 2, nn >> 2);
+        REQUIRE(variable_base_msm(f2, srs) == commit_packed(folds, {nn >> 2}, srs)[0]);
+    }
+
     // ---- ClassicSumCheck::prove on a zero check eq * (a*b - c), c = a o b: sum 0 (classic.rs:208-240)
     {
         const size_t kk = 6, nn = size_t(1) << kk;
