@@ -1,4 +1,5 @@
-"""Randomised stress of the GPU arithmetic and the MSM against Python integers / the oracle (run on a GPU box).
+"""Randomised stress of the GPU arithmetic and the MSM against Python integers / the oracle (run on a GPU box):
+python tools/fuzz_gpu.py [seconds] [seed] [pcs].  The four phases take 0.4 / 0.6 / 0.3 / 0.2 of `seconds`.
 Field level: products, fused two-product sums and squarings on structured limb patterns (all-ones / all-zero limbs,
 values around the modulus) and random values.  MSM level: random sizes, both bucket layouts, duplicates, identities,
 negated pairs, skewed scalars."""
@@ -10,6 +11,8 @@ from plonkish_b200 import _lib
 from oracle import pyoracle as po, bigint_ref as br
 
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+only = sys.argv[3] if len(sys.argv) > 3 else ""   # "pcs": the Zeromorph / Gemini phase alone (the other phases get no time)
+share = (lambda f: 0.0) if only == "pcs" else (lambda f: f)
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 
 def limbs32(vals):
@@ -33,7 +36,7 @@ def structured(mod, count):
         vals.append(v % mod)
     return vals
 
-t_end = time.time() + seconds * 0.4
+t_end = time.time() + seconds * share(0.4)
 rounds = 0
 while time.time() < t_end:
     for mod, op_mul, op_sum, op_sqr in ((br.P, 0, 8, 10), (br.R, 5, 9, 11)):
@@ -53,7 +56,7 @@ while time.time() < t_end:
     rounds += 1
 print(f"field fuzz: {rounds} rounds x 2 fields x 20000 elements x 3 ops ok", flush=True)
 
-t_end = time.time() + seconds * 0.6
+t_end = time.time() + seconds * share(0.6)
 cases = 0
 while time.time() < t_end:
     n = int(2 ** rng.uniform(0, 17))
@@ -91,7 +94,7 @@ print(f"msm fuzz: {cases} random cases x (unregistered, table, plain, prefix) ok
 from plonkish_b200 import kzg
 from plonkish_b200.sumcheck import SumCheckProver
 
-t_end = time.time() + seconds * 0.3
+t_end = time.time() + seconds * share(0.3)
 cases = 0
 one = po.from_canonical(1, po.int_to_limbs(1))[0]
 while time.time() < t_end:
@@ -134,3 +137,54 @@ while time.time() < t_end:
     pp.release()
     cases += 1
 print(f"caller fuzz: {cases} random setup / commit / merge / open / sum-check cases ok", flush=True)
+
+# ---- Zeromorph / Gemini over a univariate SRS: random sizes, setup lengths and prefix slices, each proof against the scheme's
+#      verifier equation in G1 (tests/zeromorph_ref.py, tests/gemini_ref.py) for the oracle's evaluation of the polynomial
+sys.path.insert(0, "tests")
+import gemini_ref as gr
+import zeromorph_ref as zr
+from hyperplonk_ref import ProofReader
+from plonkish_b200 import gemini, zeromorph
+from plonkish_b200.sumcheck import _to_int, _to_mont
+from plonkish_b200.transcript import Keccak256Transcript
+
+t_end = time.time() + seconds * (1.0 if only == "pcs" else 0.2)
+cases = 0
+while time.time() < t_end:
+    k = int(rng.integers(2, 13))
+    n = 1 << k
+    extra = int(rng.integers(0, 40)) if rng.random() < 0.3 else 0
+    s = int(rng.integers(2, 1 << 62)) * int(rng.integers(2, 1 << 62)) % br.R
+    full = kzg.univariate_setup(po.generator(), _to_mont(s), n + extra)
+    zpp = zeromorph.trim(full, n, prefix_tables=bool(rng.random() < 0.5))
+    poly_h = po.random_scalars(n, int(rng.integers(0, 1 << 30)))
+    poly = pk.ResidentScalars(poly_h)
+    for scheme in ("zeromorph", "gemini"):
+        t = Keccak256Transcript()
+        gpp = gemini.GeminiKzgProverParam(zpp.commit_pp)
+        comm = zeromorph.commit(zpp, poly) if scheme == "zeromorph" else gemini.commit(gpp, poly)
+        t.write_commitment(comm)
+        point = t.squeeze_challenges(k)
+        value = _to_int(po.evaluate_multilinear(poly_h, zr.mont_rows(point)))
+        t.write_field_element(value)
+        if scheme == "zeromorph":
+            assert zeromorph.open(zpp, poly, point, value, t) == value, ("zeromorph remainder", k)
+        else:
+            gemini.open(gpp, poly, point, t)
+        proof = t.into_proof()
+        reader = ProofReader(po.keccak256, proof)
+        c = reader.read_commitment()
+        assert reader.squeeze_challenges(k) == point and reader.read_field_element() == value
+        if scheme == "zeromorph":
+            zr.verify_reader_in_g1(reader, c, point, value, s, extra)
+        else:
+            gr.verify_reader_in_g1(reader, c, point, value, s)
+        assert reader.pos == len(proof), (scheme, k)
+    poly.release()
+    if extra:
+        zpp.release()
+    else:
+        zeromorph.release_prefix_tables(zpp.commit_pp)
+    full.release()
+    cases += 1
+print(f"pcs fuzz: {cases} random Zeromorph + Gemini openings (setup longer than the polynomial in a third, prefix slices in half) verified", flush=True)
