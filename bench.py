@@ -1204,7 +1204,8 @@ def run_ours(args) -> None:
             prove_leg["k20"] = hyperplonk_prove_bench(pk, torch, np, min(20, args.prove_k), cpu=True, reps=args.reps)
         line["hyperplonk_prove"] = prove_leg
         try:
-            line["pcs_schemes"] = pcs_schemes_bench(pk, torch, np, min(20, args.prove_k), reps=args.reps)
+            # own resident slices for the SRS prefixes the quotient / fold commitments run against (disclosed in the leg)
+            line["pcs_schemes"] = pcs_schemes_bench(pk, torch, np, min(20, args.prove_k), reps=args.reps, prefix_tables=True)
         except Exception as e:  # noqa: BLE001 - keep the primary numbers if this leg cannot run
             line["pcs_schemes"] = {"error": f"{type(e).__name__}: {e}"}
     if distributed and not args.no_single_process and not args.plain_bases:
