@@ -679,9 +679,8 @@ struct ZmWeights {
 __global__ void __launch_bounds__(256) k_zm_q_hat(const uint4 *__restrict__ q, ZmWeights a, u32 num_vars, uint4 *__restrict__ out) {
     const size_t n = (size_t)1 << num_vars;
     for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x) {
-        const size_t d = n - m;
-        u32 i0 = 0;
-        while (((size_t)1 << i0) < d) ++i0;
+        const size_t d = n - m;                                   // 1 <= d <= 2^28
+        const u32 i0 = d > 1 ? 32u - (u32)__clz((u32)(d - 1)) : 0u;  // smallest i with 2^i >= d
         fe acc = fe_zero();
         for (u32 i = i0; i < num_vars; ++i) acc = fr_add(acc, fr_mul(a.w[i], load_fe_plain(q + 2 * (((size_t)2 << i) - d))));
         store_fe(out + 2 * m, acc);
@@ -695,8 +694,7 @@ __global__ void __launch_bounds__(256) k_zm_f(const uint4 *__restrict__ poly, co
     for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x) {
         fe acc = fr_add(fr_mul(z, load_fe(poly + 2 * m)), load_fe_plain(q_hat + 2 * m));
         if (m == 0) acc = fr_add(acc, c0);
-        u32 i0 = 0;
-        while (((size_t)1 << i0) <= m) ++i0;
+        const u32 i0 = m ? 32u - (u32)__clz((u32)m) : 0u;            // smallest i with 2^i > m (m < 2^28)
         for (u32 i = i0; i < num_vars; ++i) acc = fr_add(acc, fr_mul(a.w[i], load_fe_plain(q + 2 * (((size_t)1 << i) + m))));
         store_fe(out + 2 * m, acc);
     }
