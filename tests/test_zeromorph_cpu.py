@@ -189,3 +189,37 @@ def test_commit_and_open_reject_polynomials_larger_than_the_param(oracle):
         zeromorph.commit(pp, poly, _oracle_ops(oracle))
     with pytest.raises(ValueError, match="Too large degree of poly to open"):
         zeromorph.open(pp, poly, [1, 2, 3], 0, Keccak256Transcript(), _oracle_ops(oracle))
+
+
+def _golden_cases():
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "pcs_vectors.json")) as f:
+        return json.load(f)["cases"]
+
+
+def golden_inputs(case):
+    """(powers [n + extra, 8], evals [n, 4]) limb arrays and the integers of a committed known-answer case."""
+    powers = np.frombuffer(bytes.fromhex("".join(case["powers_of_s_g1"])), dtype=np.uint64).reshape(-1, 8).copy()
+    evals = np.frombuffer(bytes.fromhex("".join(case["evals"])), dtype=np.uint64).reshape(-1, 4).copy()
+    return powers, evals, [int(x, 16) for x in case["point"]], int(case["eval"], 16), bytes.fromhex(case["proof"])
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_golden_proofs_through_the_host_logic_and_the_c_oracle(oracle, idx):
+    # tests/golden/pcs_vectors.json was made with Python integers only (make_golden_pcs.py); here the product's host logic
+    # runs over the C oracle's MSM and vector operations and must write the same bytes
+    from plonkish_b200 import zeromorph
+    from plonkish_b200.transcript import Keccak256Transcript
+
+    case = _golden_cases()[idx]
+    powers, evals, point, value, proof = golden_inputs(case)
+    n, extra = 1 << case["num_vars"], case["extra"]
+    pp = zeromorph.ZeromorphKzgProverParam(powers[:n], powers[extra:])
+    ops = _oracle_ops(oracle)
+    t = Keccak256Transcript()
+    t.write_commitment(zeromorph.commit(pp, evals, ops))
+    assert t.squeeze_challenges(case["num_vars"]) == point
+    t.write_field_element(value)
+    assert zeromorph.open(pp, evals, point, value, t, ops) == value
+    assert t.into_proof() == proof

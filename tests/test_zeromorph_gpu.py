@@ -239,3 +239,28 @@ def test_prefix_tables_leave_the_proofs_unchanged(pk, oracle):
         zpp.release()
     assert proofs[False] == proofs[True]
     poly.release()
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_golden_proofs_through_the_c_abi(pk, idx):
+    # the committed known-answer proofs (tests/golden/pcs_vectors.json, Python integers only) through the GPU path
+    from plonkish_b200 import zeromorph
+    from plonkish_b200.transcript import Keccak256Transcript
+    from test_zeromorph_cpu import _golden_cases, golden_inputs
+
+    case = _golden_cases()[idx]
+    powers, evals, point, value, proof = golden_inputs(case)
+    n = 1 << case["num_vars"]
+    full = pk.G1Bases(powers)
+    pp = zeromorph.trim(full, n)
+    poly = pk.ResidentScalars(evals)
+    t = Keccak256Transcript()
+    t.write_commitment(zeromorph.commit(pp, poly))
+    assert t.squeeze_challenges(case["num_vars"]) == point
+    t.write_field_element(value)
+    assert zeromorph.open(pp, poly, point, value, t) == value
+    assert t.into_proof() == proof
+    poly.release()
+    if case["extra"]:
+        pp.release()
+    full.release()
